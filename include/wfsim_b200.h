@@ -1,0 +1,217 @@
+/*
+ * wfsim_b200 -- C-ABI of the B200-native WFSim hot path (wfsim_instructions -> strax raw_records).
+ *
+ * The reference (XENONnT/WFSim v1.2.2) is pure Python and has no FFI; the entry points below are
+ * what a ctypes binding inside the unchanged `RawRecordsFromFaxNT` plugin binds instead of the
+ * reference's Python call chain.  Each entry point cites the reference interface it replaces
+ * (paths relative to the reference checkout).  Plain pointers and sizes only; the caller owns
+ * every host buffer; the library owns device memory.  See INTEGRATION.md for the plugin-side stub.
+ *
+ * Return convention (all int-returning functions):
+ *    0   success
+ *   >0   WFS_E_CAPACITY: an output buffer is too small; `wfs_counts` holds the needed sizes,
+ *        re-allocate and call again (results are reproducible: counter-based Philox RNG)
+ *   <0   error; text via wfs_last_error()
+ */
+#ifndef WFSIM_B200_H
+#define WFSIM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WFS_ABI_VERSION 1
+#define WFS_E_CAPACITY 1
+#define WFS_E_CUDA (-1)
+#define WFS_E_ARG (-2)
+#define WFS_E_PULSE_CACHE_TOO_LONG (-3) /* "Pulse cache too long", wfsim/core/rawdata.py:219 */
+#define WFS_E_KEYBITS (-4)
+
+#define WFS_RECORD_BYTES 244      /* strax.raw_record_dtype(110) */
+#define WFS_SAMPLES_PER_RECORD 110
+#define WFS_INSTRUCTION_BYTES 70  /* wfsim/strax_interface.py:25-42 */
+#define WFS_TRUTH_BYTES 218       /* instruction_dtype + truth_extra_dtype, :49-73 */
+#define WFS_MAX_AP_ELEMENTS 8
+
+/* Scalar configuration: the fax_config keys the path reads (wfsim/core/*.py `self.config[...]`),
+ * flattened on the host by wfsim_b200/params.py.  Units as in the reference (ns, cm, V). */
+typedef struct wfs_params {
+    int32_t abi_version;
+    /* detector / channel layout: strax_interface.py:593-595, rawdata.py:241-254 */
+    int32_t detector_nt;            /* config['detector'] == 'XENONnT' */
+    int32_t n_tpc_pmts;
+    int32_t n_top_pmts;
+    int32_t he_first, he_last;      /* channel_map['he'] */
+    int32_t he_mult;                /* int(high_energy_deamplification_factor) (sic) */
+    int32_t n_rows;                 /* 801: rows of the reference's _raw_data */
+    /* digitizer: pulse.py:121-127, rawdata.py:211-222,263-272 */
+    int32_t dt;                     /* sample_duration */
+    int32_t template_length;        /* samples_before_pulse_center + samples_after_pulse_center */
+    int32_t pulse_left_margin;      /* samples_to_store_before + samples_before_pulse_center */
+    int32_t pulse_right_margin;     /* samples_to_store_after + samples_after_pulse_center */
+    int32_t trigger_window;
+    int32_t baseline;               /* digitizer_reference_baseline */
+    int32_t enable_noise;
+    int32_t zle_threshold;          /* for truth trigger counters, pulse.py:240-243 */
+    double current_2_adc;           /* pulse.py:33-35 */
+    int64_t right_raw_extension;    /* strax_interface.py:531 */
+    /* ---- sampling stages ---- */
+    int32_t s1_model_simple;        /* 'simple' in s1_model_type, s1.py:191 */
+    int32_t s1_model_optical;       /* 'optical_propagation' in s1_model_type, s1.py:186 (needs spline table) */
+    int32_t s2_luminescence_model;  /* 0 simple, 1 garfield, 2 garfield_gas_gap, s2.py:518-536 */
+    int32_t s2_time_model;          /* 0 's2_time_spread around zero', 1 zero_delay, 2 optical_propagation, s2.py:542-552 */
+    int32_t enable_pmt_afterpulses; /* rawdata.py:176 */
+    int32_t enable_electron_afterpulses; /* rawdata.py:194 */
+    int32_t enable_gate_afterpulses;     /* rawdata.py:198 */
+    int32_t save_full_truth;        /* rawdata.py:42 */
+    double p_double_pe_emision;     /* (sic) pulse.py:76 */
+    double pmt_transit_time_mean, pmt_transit_time_spread; /* pulse.py:54-55 */
+    double s1_detection_efficiency; /* s1.py:131 */
+    double s1_decay_time, s1_decay_spread; /* s1.py:193-194 */
+    double singlet_fraction_gas, singlet_lifetime_gas, triplet_lifetime_gas; /* pulse.py:321-341 */
+    double drift_velocity_liquid, drift_time_gate, diffusion_constant_longitudinal; /* s2.py:139-179 */
+    double electron_lifetime_liquid, electron_extraction_yield, electron_trapping_time; /* s2.py:212-286 */
+    double s2_secondary_sc_gain, s2_gain_spread, s2_time_spread; /* s2.py:197,309,550 */
+    double tpc_radius, tpc_length;
+    double pmt_ap_modifier, pmt_ap_t_modifier; /* afterpulse.py:193-223 */
+    double photoionization_modifier;           /* afterpulse.py:39 */
+    double photoelectric_modifier, photoelectric_p, photoelectric_t_center, photoelectric_t_spread; /* afterpulse.py:108-115 */
+    double ele_ap_n;                /* uniform_to_ele_ap.n, afterpulse.py:37 */
+    double s2_aft_sigma, s2_aft_skewness; /* s2.py:630-631 */
+} wfs_params;
+
+/* Tables (host pointers, copied to the device at wfs_create).  A NULL pointer means "absent". */
+typedef struct wfs_tables {
+    const double *templates;        /* [dt][template_length], pulse.py:146-187 */
+    const double *gains;            /* [n_tpc_pmts], strax_interface.py:584-587; 0 == turned off */
+    const int32_t *zle_thresholds;  /* [n_rows] baseline - (special|zle)_threshold - 1, rawdata.py:290-294 */
+    const double *noise;            /* [noise_len][noise_nch] resource.noise_data, rawdata.py:264-268 */
+    int64_t noise_len;
+    int32_t noise_nch;
+    /* SPE inverse CDF: pulse.py:189-227.  spe_row[ch] selects the row of spe_ppf used for ch */
+    const double *spe_ppf;          /* [n_spe_rows][spe_len] */
+    const int32_t *spe_row;         /* [n_tpc_pmts] */
+    int32_t n_spe_rows, spe_len;    /* spe_len == 2001 */
+    /* S2 luminescence 'simple' model: inverse CDF of emission time tabulated once for the
+     * constant gas gap (s2.py:317-378): t = interp(U, lum_cdf, lum_t) */
+    const double *lum_cdf, *lum_t;
+    int32_t lum_len;
+    /* PMT afterpulse elements (resource.uniform_to_pmt_ap, afterpulse.py:172-249) */
+    int32_t n_ap_elements;
+    int32_t ap_is_uniform[WFS_MAX_AP_ELEMENTS];
+    const double *ap_delay_cdf[WFS_MAX_AP_ELEMENTS];   /* [n_tpc_pmts][ap_delay_len] */
+    int32_t ap_delay_len[WFS_MAX_AP_ELEMENTS];
+    double ap_delay_bin[WFS_MAX_AP_ELEMENTS];
+    const double *ap_amp_cdf[WFS_MAX_AP_ELEMENTS];     /* [n_tpc_pmts or 1][ap_amp_len] */
+    int32_t ap_amp_len[WFS_MAX_AP_ELEMENTS];
+    int32_t ap_amp_rows[WFS_MAX_AP_ELEMENTS];
+    double ap_amp_bin[WFS_MAX_AP_ELEMENTS];
+    /* photo-ionisation delay distribution (uniform_to_ele_ap, afterpulse.py:33-80):
+     * inverse CDF of the delay histogram and the coarse time grid of _reduce_instruction_timing */
+    const double *pi_delay_icdf;    /* [pi_icdf_len] delay = interp(U) on a uniform U grid */
+    int32_t pi_icdf_len;
+    const double *pi_coarse_time;   /* [pi_coarse_len] */
+    int32_t pi_coarse_len;
+} wfs_tables;
+
+/* Per-instruction map values evaluated on the host with the reference's own map objects
+ * (straxen.InterpolatingMap is third party; DummyMap for config[0]).  All arrays [n_instr]
+ * unless noted; NULL -> the constant stated. */
+typedef struct wfs_instr_maps {
+    const double *s1_lce;           /* s1_lce_correction_map(xyz), s1.py:125; NULL -> 1 */
+    const double *s2_sc_gain;       /* get_s2_light_yield(positions) incl. /(1+p_dpe), s2.py:182-209 */
+    const double *s2_cy_extra;      /* p_surv (and map-driven extraction yield) factor, s2.py:227-252; NULL -> 1 */
+    const float *pattern;           /* [n_pattern_rows][n_tpc_pmts] un-normalised per-PMT pattern */
+    const int32_t *pattern_row;     /* [n_instr] row of `pattern` for the instruction; NULL -> row 0 */
+    int64_t n_pattern_rows;
+} wfs_instr_maps;
+
+typedef struct wfs_counts {
+    int64_t n_records[3];           /* raw_records, raw_records_he, raw_records_aqmon */
+    int64_t n_records_total;
+    int64_t n_truth;
+    int64_t n_photons;              /* photons superposed (after dead-PMT removal) */
+    int64_t n_pe;                   /* sum of truth n_pe (photons + DPE), pulse.py:262 */
+    int64_t n_pulses;               /* (pulse call, channel) pulses */
+    int64_t n_windows;              /* (digitisation group, channel) windows incl. HE rows */
+    int64_t n_intervals;            /* ZLE intervals */
+    int64_t n_samples;              /* samples digitised (window samples) */
+    int64_t n_groups;
+    int64_t n_pulse_calls;
+    int64_t n_instructions;
+    int64_t n_batches;
+    int64_t gpu_launches;           /* kernels launched by this call */
+    int64_t need_records;           /* capacities needed when WFS_E_CAPACITY */
+    int64_t need_truth;
+    double ms_total;                /* CUDA-event time of the device work of this call */
+    double ms_digitize;             /* of which: the digitize (superpose+ADC+noise+clip) kernel */
+    double ms_h2d, ms_d2h;
+} wfs_counts;
+
+/* Digitisation-group bookkeeping returned to the host-side chunker
+ * (replaces RawData.left/right as read by ChunkRawRecords, strax_interface.py:394-403). */
+typedef struct wfs_group_info {
+    int64_t left, right;            /* rawdata.py:215-222 (left made even) */
+    int64_t n_intervals;            /* ZLE intervals yielded by the group */
+} wfs_group_info;
+
+/* Lifetime.  `device` is the CUDA ordinal this handle is bound to (one handle per GPU). */
+int wfs_create(const wfs_params *params, const wfs_tables *tables, int device, void **handle);
+void wfs_destroy(void *handle);
+const char *wfs_last_error(void *handle);   /* handle may be NULL for create errors */
+int wfs_abi_version(void);
+void wfs_struct_sizes(int64_t *out5);       /* sizeof of the five structs above, for binding checks */
+int wfs_device_count(void);
+
+/* Pinned host memory for output buffers (so device->host copies are plain DMA). */
+void *wfs_host_alloc(int64_t bytes);
+void wfs_host_free(void *p);
+
+/* Deterministic entry: photons in, records out.
+ * Replaces Pulse.__call__ with preset gains (pulse.py:82-144) + Pulse.add_current (:276-318) +
+ * RawData.digitize_pulse_cache (rawdata.py:204-272) + RawData.ZLE (:274-311) + the record packing
+ * and (time, channel) sort of ChunkRawRecords (strax_interface.py:391-436,446-453).
+ *   pulse_call[i]  id of the Pulse call photon i belongs to (0..n_pulse_calls-1)
+ *   group_of[p]    digitisation group of pulse call p (0..n_groups-1)
+ *   ix_rand[g]     noise start offset of group g (rawdata.py:407-417); NULL -> drawn by Philox(seed)
+ * Output: `records` holds [raw_records | raw_records_he | raw_records_aqmon], each segment sorted
+ * by (time, channel); segment lengths in counts->n_records[].  `groups` (optional, [n_groups]).
+ * Host pointers unless `on_device` is non-zero (then all photon arrays and `records` are device
+ * pointers and no host<->device copy happens inside the call). */
+int wfs_simulate_photons(void *handle, int64_t n_photons, const int64_t *t_ns,
+                         const int32_t *channel, const double *gain, const int32_t *pulse_call,
+                         int64_t n_pulse_calls, const int32_t *group_of, int64_t n_groups,
+                         const int64_t *ix_rand, uint64_t seed, int on_device,
+                         uint8_t *records, int64_t cap_records, wfs_group_info *groups,
+                         wfs_counts *counts);
+
+/* Full path: instructions in, records + truth out.
+ * Replaces ChunkRawRecords.__call__ -> RawData.__call__ -> S1/S2/afterpulse Pulse calls ->
+ * digitize_pulse_cache -> ZLE -> record packing (strax_interface.py:368-497, rawdata.py:38-375).
+ *   instructions   packed 70-byte rows (instruction_dtype); any order
+ *   maps           per-instruction map values (see wfs_instr_maps)
+ * Output as wfs_simulate_photons plus `truth` (218-byte rows, one per Pulse call, ordered by
+ * Pulse-call execution order) and `groups` ([cap_groups]; counts->n_groups valid entries). */
+int wfs_simulate(void *handle, const uint8_t *instructions, int64_t n_instructions,
+                 const wfs_instr_maps *maps, uint64_t seed,
+                 uint8_t *records, int64_t cap_records, uint8_t *truth, int64_t cap_truth,
+                 wfs_group_info *groups, int64_t cap_groups, wfs_counts *counts);
+
+/* Device-resident variant for throughput measurement: instructions/maps are uploaded once with
+ * wfs_stage_instructions, wfs_run_staged runs the whole path with every buffer in HBM and leaves
+ * the records on the device (counts are still returned).  */
+int wfs_stage_instructions(void *handle, const uint8_t *instructions, int64_t n_instructions,
+                           const wfs_instr_maps *maps);
+int wfs_run_staged(void *handle, uint64_t seed, wfs_counts *counts);
+
+/* Stage-level entry points used by the statistical parity tests (each draws from the same
+ * Philox streams the full path uses). */
+int wfs_sample_stage(void *handle, int stage, const uint8_t *instructions, int64_t n_instructions,
+                     const wfs_instr_maps *maps, uint64_t seed, void *out, int64_t cap, int64_t *n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

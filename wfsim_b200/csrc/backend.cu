@@ -1,0 +1,814 @@
+// Deterministic back end of the WFSim hot path on B200 (sm_100a).
+//
+//   photons (t_ns, channel, gain, pulse call) resident in HBM
+//     -> ordered by (digitisation group, channel, pulse call, time)      [radix sort, primitives.cu]
+//     -> pulses  = runs of equal (group, channel, pulse call)            Pulse.__call__ pulse.py:82-144
+//     -> windows = runs of equal (group, channel)                        rawdata.py:231-235,258-259
+//     -> k_digitize: per (window, 512-sample tile) CTA: template superposition in fp64 with the
+//        reference's summation order, one rounding per pulse, integer sum over pulses, noise,
+//        baseline, clamp, int16 store + ZLE flag bits   pulse.py:276-318, rawdata.py:236-272,392-458
+//     -> k_zle: hysteresis interval finding on the flag bits             utils.py:13-58, rawdata.py:296-308
+//     -> record keys (class, time, channel) -> radix sort                strax.sort_by_time
+//     -> k_pack: 244-byte raw_records written at their final position    strax_interface.py:425-436
+//
+// HBM-bound integer/byte work: no tensor cores.  Accumulation is fp64 (B200 has full-rate FP64
+// FMA pipes; the mul/add are issued unfused to match the reference bit for bit).
+#include "backend.cuh"
+#include "philox.cuh"
+
+#include <algorithm>
+#include <limits.h>
+
+namespace wfs {
+
+enum Scalar {
+    S_NVALID = 0, S_NPULSES, S_NWIN, S_NTILES, S_NITVSLOTS, S_NREC, S_MINSAMPLE, S_MAXSAMPLE,
+    S_ERR, S_NITV, S_NSAMPLES, S_CLASS0, S_CLASS1, S_CLASS2, S_COUNT
+};
+
+struct WinMeta {
+    int64_t left;        // absolute sample index of the first sample of the window
+    int32_t len;         // samples
+    int32_t channel;     // output channel (he_first + ch for HE rows)
+    int32_t group;
+    int32_t mult;        // 1, or he_mult for HE rows
+    int32_t p0, p1;      // pulses [p0, p1) contributing to this window
+    int32_t pad0, pad1;
+};
+
+struct Interval {
+    int64_t left;        // absolute sample index
+    int64_t src;         // offset of the first sample in the dense buffer
+    int32_t len;         // pulse_length
+    int32_t channel;
+};
+
+struct KeyLayout {
+    int bits_rank, bits_group;
+    int shift_rank, shift_ch, shift_group;
+    int total_bits;
+};
+
+__device__ __forceinline__ int64_t floordiv(int64_t a, int64_t b) {
+    int64_t q = a / b;
+    return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void k_init(int64_t *group_tmin, int64_t *group_lr, uint32_t *group_nitv,
+                       int64_t n_groups, int64_t *scalars) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_groups) {
+        group_tmin[i] = LLONG_MAX;
+        group_lr[2 * i] = LLONG_MAX;
+        group_lr[2 * i + 1] = LLONG_MIN;
+        group_nitv[i] = 0;
+    }
+    if (i < S_COUNT) {
+        int64_t v = 0;
+        if (i == S_MINSAMPLE) v = LLONG_MAX;
+        if (i == S_MAXSAMPLE) v = LLONG_MIN;
+        scalars[i] = v;
+    }
+}
+
+__device__ __forceinline__ bool photon_valid(int32_t ch, int32_t pc, const DeviceConfig &c,
+                                             int64_t n_pc) {
+    // dead PMTs are skipped by Pulse.__call__ (pulse.py:89-90); channel -1 = "no pattern" (s2.py:670)
+    return ch >= 0 && ch < c.p.n_tpc_pmts && pc >= 0 && pc < n_pc && c.gains[ch] != 0.0;
+}
+
+__global__ void k_group_tmin(PhotonBatch b, DeviceConfig c, int64_t *group_tmin) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = false;
+    int g = -1;
+    int64_t t = LLONG_MAX;
+    if (i < b.n) {
+        int32_t ch = b.channel[i], pc = b.pulse_call[i];
+        valid = photon_valid(ch, pc, c, b.n_pulse_calls);
+        if (valid) {
+            g = b.pc_group[pc];
+            t = b.t[i];
+        }
+    }
+    // warp-aggregate: one atomic per distinct group in the warp
+    unsigned m = __match_any_sync(0xffffffffu, g);
+    int lane = threadIdx.x & 31;
+    int64_t mn = t;
+    for (int o = 0; o < 32; o++) {
+        int64_t other = __shfl_sync(0xffffffffu, t, o);
+        if ((m >> o) & 1u) mn = other < mn ? other : mn;
+    }
+    if (valid && (m & ((1u << lane) - 1u)) == 0) atomicMin((long long *)&group_tmin[g], (long long)mn);
+}
+
+__global__ void k_build_keys(PhotonBatch b, DeviceConfig c, KeyLayout kl, const int64_t *group_tmin,
+                             uint64_t *keys, uint32_t *vals, int64_t *scalars) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n) return;
+    int32_t ch = b.channel[i], pc = b.pulse_call[i];
+    uint64_t key;
+    if (photon_valid(ch, pc, c, b.n_pulse_calls)) {
+        int g = b.pc_group[pc];
+        int64_t rel = b.t[i] - group_tmin[g];
+        if (rel >= (int64_t(1) << kRelTimeBits)) {
+            scalars[S_ERR] = WFS_E_PULSE_CACHE_TOO_LONG;
+            rel = (int64_t(1) << kRelTimeBits) - 1;
+        }
+        key = (uint64_t)rel | ((uint64_t)b.pc_rank[pc] << kl.shift_rank) |
+              ((uint64_t)ch << kl.shift_ch) | ((uint64_t)g << kl.shift_group);
+    } else {
+        key = (uint64_t)b.n_groups << kl.shift_group;   // sorts behind every valid photon
+    }
+    keys[i] = key;
+    vals[i] = (uint32_t)i;
+}
+
+// After the sort: gather time/gain into sorted order and flag pulse / window starts.
+__global__ void k_gather_flags(PhotonBatch b, KeyLayout kl, const uint64_t *keys,
+                               const uint32_t *vals, int64_t *st, double *sg, uint64_t *flags,
+                               int64_t *scalars) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n) return;
+    uint64_t k = keys[i];
+    bool valid = (k >> kl.shift_group) < (uint64_t)b.n_groups;
+    uint64_t f = 0;
+    if (valid) {
+        uint32_t src = vals[i];
+        st[i] = b.t[src];
+        sg[i] = b.gain[src];
+        uint64_t kp = i > 0 ? keys[i - 1] : ~0ull;
+        bool newpulse = (i == 0) || ((k >> kl.shift_rank) != (kp >> kl.shift_rank));
+        bool newwin = (i == 0) || ((k >> kl.shift_ch) != (kp >> kl.shift_ch));
+        f = (newpulse ? 1ull : 0ull) | (newwin ? (1ull << 32) : 0ull);
+        bool next_valid = (i + 1 < b.n) && ((keys[i + 1] >> kl.shift_group) < (uint64_t)b.n_groups);
+        if (!next_valid) scalars[S_NVALID] = i + 1;
+    }
+    flags[i] = f;
+}
+
+__global__ void k_emit_pulses(int64_t n, KeyLayout kl, const uint64_t *keys, const uint64_t *flags,
+                              const uint64_t *pos, uint32_t *pulse_first, uint32_t *pulse_win,
+                              uint32_t *win_first_pulse, uint32_t *win_key, int64_t *scalars) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) {
+        uint64_t tot = pos[n];
+        uint32_t np = (uint32_t)tot, nw = (uint32_t)(tot >> 32);
+        scalars[S_NPULSES] = np;
+        scalars[S_NWIN] = nw;
+        pulse_first[np] = (uint32_t)scalars[S_NVALID];
+        win_first_pulse[nw] = np;
+        return;
+    }
+    uint64_t f = flags[i];
+    if (f & 1ull) {
+        uint64_t e = pos[i];
+        uint32_t p = (uint32_t)e, w = (uint32_t)(e >> 32);
+        if (!(f >> 32)) w -= 1;
+        pulse_first[p] = (uint32_t)i;
+        pulse_win[p] = w;
+        if (f >> 32) {
+            win_first_pulse[w] = p;
+            win_key[w] = (uint32_t)(keys[i] >> kl.shift_ch);   // (group << 10) | channel
+        }
+    }
+}
+
+// One thread per base window: pulse extents (pulse.py:118-127), window extents
+// (rawdata.py:231-235,258-259), HE twin (rawdata.py:241-249), group extents (rawdata.py:215-216).
+__global__ void k_window_extents(int64_t n_win, DeviceConfig c, const int64_t *st,
+                                 const uint32_t *pulse_first, const uint32_t *win_first_pulse,
+                                 const uint32_t *win_key, int64_t *pulse_left, WinMeta *meta,
+                                 uint64_t *win_scan_in, int64_t *group_lr, int64_t *scalars,
+                                 int he_rows) {
+    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_win) return;
+    const int dt = c.p.dt;
+    uint32_t p0 = win_first_pulse[w], p1 = win_first_pulse[w + 1];
+    int64_t lo = LLONG_MAX, hi = LLONG_MIN;
+    for (uint32_t p = p0; p < p1; p++) {
+        uint32_t a = pulse_first[p], b = pulse_first[p + 1];
+        int64_t l = floordiv(st[a], dt) - c.p.pulse_left_margin;
+        int64_t r = floordiv(st[b - 1], dt) + c.p.pulse_right_margin;
+        pulse_left[2 * (int64_t)p] = l;
+        pulse_left[2 * (int64_t)p + 1] = r;
+        lo = l < lo ? l : lo;
+        hi = r > hi ? r : hi;
+    }
+    uint32_t key = win_key[w];
+    int ch = key & ((1u << kChannelBits) - 1u);
+    int g = key >> kChannelBits;
+    atomicMin((long long *)&group_lr[2 * g], (long long)lo);
+    atomicMax((long long *)&group_lr[2 * g + 1], (long long)hi);
+    const int tw = c.p.trigger_window;
+    WinMeta m;
+    m.left = lo - tw;
+    int64_t len = hi - lo + 2 * tw + 1;
+    if (len > kMaxGroupSamples + 1) {
+        scalars[S_ERR] = WFS_E_PULSE_CACHE_TOO_LONG;
+        len = kMaxGroupSamples + 1;
+    }
+    m.len = (int32_t)len;
+    m.channel = ch;
+    m.group = g;
+    m.mult = 1;
+    m.p0 = (int32_t)p0;
+    m.p1 = (int32_t)p1;
+    m.pad0 = m.pad1 = 0;
+    meta[w] = m;
+    const int holdoff = 2 * tw + 1;
+    uint64_t tiles = (uint64_t)((len + kTile - 1) / kTile);
+    uint64_t icap = (uint64_t)(len / (holdoff + 1) + 2);
+    win_scan_in[w] = tiles | (icap << 32);
+    atomicMin((long long *)&scalars[S_MINSAMPLE], (long long)m.left);
+    atomicMax((long long *)&scalars[S_MAXSAMPLE], (long long)(m.left + len));
+    // HE twin
+    WinMeta h = m;
+    bool he = he_rows && c.p.detector_nt && ch < c.p.n_top_pmts;
+    if (he) {
+        h.channel = c.p.he_first + ch;
+        h.mult = c.p.he_mult;
+    } else {
+        h.len = 0;
+    }
+    meta[n_win + w] = h;
+    win_scan_in[n_win + w] = he ? (tiles | (icap << 32)) : 0ull;
+}
+
+// Noise start offset per group (rawdata.py:407-417) when not supplied by the caller.
+__global__ void k_group_noise(int64_t n_groups, DeviceConfig c, const int64_t *group_lr,
+                              const int64_t *ix_in, uint64_t seed, int64_t group_base,
+                              int64_t *ix_out, int64_t *scalars) {
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    int64_t lo = group_lr[2 * g], hi = group_lr[2 * g + 1];
+    if (lo != LLONG_MAX) {
+        int64_t left = lo - c.p.trigger_window, right = hi + c.p.trigger_window;
+        if (right - left >= kMaxGroupSamples) scalars[S_ERR] = WFS_E_PULSE_CACHE_TOO_LONG;
+    }
+    int64_t ix = 0;
+    if (ix_in) {
+        ix = ix_in[g];
+    } else if (c.p.enable_noise && c.noise_len > 0 && lo != LLONG_MAX) {
+        int64_t span = hi - lo + 2 * c.p.trigger_window;
+        int64_t high = c.noise_len - span - 1;
+        if (high < 0) high = c.noise_len - 1;
+        if (high > 0) {
+            Philox4 r = philox4x32(seed, RS_NOISE, (uint64_t)(group_base + g), 0);
+            uint64_t u = ((uint64_t)r.v[0] << 32) | r.v[1];
+            ix = (int64_t)__umul64hi(u, (uint64_t)high);
+        }
+    }
+    ix_out[g] = ix;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_digitize: one CTA per (window, tile).
+// ---------------------------------------------------------------------------------------------
+constexpr int kChunk = 512;                     // photons staged per pass
+constexpr int kSPT = kTile / kDigiThreads;      // samples per thread
+
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *a, uint32_t n, uint64_t key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if ((uint64_t)a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ int64_t lower_bound_i64(const int64_t *a, int64_t lo, int64_t hi, int64_t key) {
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kDigiThreads)
+k_digitize(int64_t n_tiles, int64_t n_wtot, DeviceConfig c, const WinMeta *__restrict__ meta,
+           const uint64_t *__restrict__ win_off /* tiles in low 32 */, const int64_t *__restrict__ st,
+           const double *__restrict__ sg, const uint32_t *__restrict__ pulse_first,
+           const int64_t *__restrict__ pulse_lr, const int64_t *__restrict__ group_ix,
+           int16_t *__restrict__ dense, uint32_t *__restrict__ zflags) {
+    __shared__ int32_t acc[kTile];
+    __shared__ uint32_t s_key[kChunk];
+    __shared__ double s_gain[kChunk];
+    __shared__ double s_tmpl[16 * 32];
+    __shared__ int64_t s_range[2];
+    const int tid = threadIdx.x;
+    const int dt = c.p.dt, tlen = c.p.template_length;
+    for (int i = tid; i < dt * tlen; i += kDigiThreads) s_tmpl[i] = c.templates[i];
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // locate the window owning this tile
+        int64_t lo = 0, hi = n_wtot;
+        while (lo < hi) {   // last w with (uint32)win_off[w] <= tile
+            int64_t mid = (lo + hi + 1) >> 1;
+            if ((int64_t)(uint32_t)win_off[mid] <= tile) lo = mid; else hi = mid - 1;
+        }
+        const int64_t w = lo;
+        const WinMeta m = meta[w];
+        const int64_t tile0 = (int64_t)(uint32_t)win_off[w];
+        const int tix = (int)(tile - tile0);
+        const int64_t a = m.left + (int64_t)tix * kTile;           // abs sample of tile start
+        const int nsamp = min(kTile, m.len - tix * kTile);
+        __syncthreads();
+        for (int i = tid; i < kTile; i += kDigiThreads) acc[i] = 0;
+        __syncthreads();
+
+        if (m.mult != 0) {
+            for (int p = m.p0; p < m.p1; p++) {
+                const int64_t pl = pulse_lr[2 * (int64_t)p], pr = pulse_lr[2 * (int64_t)p + 1];
+                if (pr < a || pl >= a + nsamp) continue;   // uniform across the CTA
+                if (tid == 0) {
+                    int64_t f0 = pulse_first[p], f1 = pulse_first[p + 1];
+                    // photons with q in [a - tlen + 1, a + nsamp - 1]
+                    s_range[0] = lower_bound_i64(st, f0, f1, (a - tlen + 1) * dt);
+                    s_range[1] = lower_bound_i64(st, f0, f1, (a + nsamp) * dt);
+                }
+                __syncthreads();
+                int64_t c0 = s_range[0];
+                const int64_t cend = s_range[1];
+                double cur[kSPT];
+#pragma unroll
+                for (int j = 0; j < kSPT; j++) cur[j] = 0.0;
+                while (c0 < cend) {
+                    int64_t c1 = c0 + kChunk < cend ? c0 + kChunk : cend;
+                    if (c1 < cend) {   // do not split a run of equal-ns photons (pulse.py:301-318)
+                        int64_t tb = st[c1];
+                        int64_t c1b = c1;
+                        while (c1b > c0 + 1 && st[c1b - 1] == tb) c1b--;
+                        if (c1b > c0 + 1 || st[c0] != tb) c1 = c1b;
+                    }
+                    const int nph = (int)(c1 - c0);
+                    __syncthreads();
+                    for (int i = tid; i < nph; i += kDigiThreads) {
+                        int64_t t = st[c0 + i];
+                        int64_t q = floordiv(t, dt);
+                        int r = (int)(t - q * dt);
+                        s_key[i] = (uint32_t)((q - a + tlen - 1) * dt + r);
+                        s_gain[i] = sg[c0 + i];
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int j = 0; j < kSPT; j++) {
+                        const int s = j * kDigiThreads + tid;
+                        if (s < nsamp) {
+                            uint32_t i = lower_bound_u32(s_key, nph, (uint64_t)s * dt);
+                            const uint32_t kend = (uint32_t)(s + tlen) * dt;
+                            double v = cur[j];
+                            while (i < (uint32_t)nph) {
+                                uint32_t kk = s_key[i];
+                                if (kk >= kend) break;
+                                double g = s_gain[i];
+                                i++;
+                                while (i < (uint32_t)nph && s_key[i] == kk) {
+                                    g = __dadd_rn(g, s_gain[i]);
+                                    i++;
+                                }
+                                int qs = kk / dt, r = kk - qs * dt;
+                                v = __dadd_rn(v, __dmul_rn(s_tmpl[r * tlen + (s - qs + tlen - 1)], g));
+                            }
+                            cur[j] = v;
+                        }
+                    }
+                    c0 = c1;
+                }
+                // one rounding per (pulse call, channel): rawdata.py:236-239
+#pragma unroll
+                for (int j = 0; j < kSPT; j++) {
+                    const int s = j * kDigiThreads + tid;
+                    const int64_t sa = a + s;
+                    if (s < nsamp && sa >= pl && sa <= pr) {
+                        long long adc = -(long long)rint(__dmul_rn(cur[j], c.p.current_2_adc));
+                        acc[s] += (int32_t)(adc * m.mult);
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // noise (rawdata.py:398-437), baseline (:439-447), clamp (:449-458), ZLE flag (:290-296)
+        const bool noisy = c.p.enable_noise && c.noise_t != nullptr && m.channel < c.noise_nch;
+        const int64_t ixr = noisy ? group_ix[m.group] : 0;
+        const int thr = c.zle_thr[m.channel];
+        int16_t *out = dense + tile * kTile;
+        uint32_t *fl = zflags + tile * (kTile / 32);
+#pragma unroll
+        for (int j = 0; j < kSPT; j++) {
+            const int s = j * kDigiThreads + tid;
+            bool flag = false;
+            if (s < nsamp) {
+                long long v = acc[s];
+                if (noisy) {
+                    int64_t ix = ixr + (int64_t)tix * kTile + s;
+                    if (ix >= c.noise_len) ix -= c.noise_len * (ix / c.noise_len);
+                    v = (long long)((double)v + c.noise_t[(int64_t)m.channel * c.noise_len + ix]);
+                }
+                v += c.p.baseline;
+                if (v < 0) v = 0;
+                flag = v < thr;
+                out[s] = (int16_t)v;
+            }
+            unsigned word = __ballot_sync(0xffffffffu, flag);
+            if ((tid & 31) == 0) fl[(j * kDigiThreads + tid) >> 5] = word;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_zle: one warp per window.  An interval starts at a flagged sample whose previous flagged
+// sample is more than `holdoff` away and ends at the flagged sample before the next start
+// (equivalent to the sequential scan of utils.py:13-58); then +-tw, clip, even alignment in
+// channel-local coordinates (rawdata.py:303-308).
+// ---------------------------------------------------------------------------------------------
+constexpr int kNeg = -(1 << 29);
+
+__device__ __forceinline__ int warp_excl_max(int v, int lane) {
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl = max(incl, u);
+    }
+    int ex = __shfl_up_sync(0xffffffffu, incl, 1);
+    return lane == 0 ? kNeg : ex;
+}
+
+__device__ __forceinline__ int warp_excl_sum(int v, int lane, int *total) {
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    *total = __shfl_sync(0xffffffffu, incl, 31);
+    return incl - v;
+}
+
+__device__ __forceinline__ void emit_interval(int s, int e, const WinMeta &m, int tw, int64_t dense0,
+                                              Interval *itv, uint32_t *itv_nrec, int64_t slot) {
+    int l = s - tw, r = e + tw;
+    l = max(0, min(l, m.len - 1));
+    r = max(0, min(r, m.len - 1));
+    l = (l + 1) & ~1;
+    r = r & ~1;
+    int plen = r - l + 1;
+    if (plen < 0) plen = 0;
+    Interval it;
+    it.left = m.left + l;
+    it.src = dense0 + l;
+    it.len = plen;
+    it.channel = m.channel;
+    itv[slot] = it;
+    itv_nrec[slot] = (uint32_t)((plen + WFS_SAMPLES_PER_RECORD - 1) / WFS_SAMPLES_PER_RECORD);
+}
+
+__global__ void __launch_bounds__(128)
+k_zle(int64_t n_wtot, DeviceConfig c, const WinMeta *__restrict__ meta,
+      const uint64_t *__restrict__ win_off, const uint32_t *__restrict__ zflags, Interval *itv,
+      uint32_t *itv_nrec, uint32_t *group_nitv, int64_t *scalars) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_wtot) return;
+    const WinMeta m = meta[w];
+    const uint64_t off = win_off[w], off1 = win_off[w + 1];
+    const int64_t slot0 = (int64_t)(off >> 32);
+    const int cap = (int)((off1 >> 32) - (off >> 32));
+    if (m.len == 0) return;
+    const int64_t tile0 = (int64_t)(uint32_t)off;
+    const uint32_t *fw = zflags + tile0 * (kTile / 32);
+    const int64_t dense0 = tile0 * kTile;
+    const int nwords = (m.len + 31) >> 5;
+    const int H = 2 * c.p.trigger_window + 1, tw = c.p.trigger_window;
+    int carry_last = kNeg, carry_start = kNeg, n_emitted = 0;
+    for (int c0 = 0; c0 < nwords; c0 += 32) {
+        const int wi = c0 + lane;
+        const uint32_t word = wi < nwords ? fw[wi] : 0u;
+        const int base = wi * 32;
+        const int lastpos = word ? base + 31 - __clz(word) : kNeg;
+        int pl = max(warp_excl_max(lastpos, lane), carry_last);
+        // pass 1: breaks in this word
+        uint32_t rising = word & ~(word << 1);
+        int nbreak = 0, lastbreak = kNeg;
+        for (uint32_t rb = rising; rb; rb &= rb - 1) {
+            int b = __ffs(rb) - 1;
+            uint32_t below = word & ((1u << b) - 1u);
+            int prev = below ? base + 31 - __clz(below) : pl;
+            if (base + b - prev > H) { nbreak++; lastbreak = base + b; }
+        }
+        int ps = max(warp_excl_max(lastbreak, lane), carry_start);
+        // an emission happens at every break that closes an open interval
+        int nem = nbreak - ((word != 0u && pl == kNeg && nbreak > 0) ? 1 : 0);
+        int tot;
+        int eoff = warp_excl_sum(nem, lane, &tot) + n_emitted;
+        // pass 2: emit closed intervals
+        int cur_start = ps;
+        for (uint32_t rb = rising; rb; rb &= rb - 1) {
+            int b = __ffs(rb) - 1;
+            uint32_t below = word & ((1u << b) - 1u);
+            int prev = below ? base + 31 - __clz(below) : pl;
+            if (base + b - prev > H) {
+                if (prev != kNeg) {
+                    if (eoff < cap) emit_interval(cur_start, prev, m, tw, dense0, itv, itv_nrec, slot0 + eoff);
+                    eoff++;
+                }
+                cur_start = base + b;
+            }
+        }
+        n_emitted += tot;
+        // carries for the next chunk of 32 words
+        int incl_last = max(pl, lastpos), incl_start = max(ps, lastbreak);
+        carry_last = __shfl_sync(0xffffffffu, incl_last, 31);
+        carry_start = __shfl_sync(0xffffffffu, incl_start, 31);
+    }
+    if (lane == 0) {
+        if (carry_last != kNeg) {   // close the last interval at the last flagged sample
+            if (n_emitted < cap) emit_interval(carry_start, carry_last, m, tw, dense0, itv, itv_nrec, slot0 + n_emitted);
+            n_emitted++;
+        }
+        if (n_emitted > cap) scalars[S_ERR] = WFS_E_ARG;   // cannot happen: cap is an upper bound
+        if (n_emitted) {
+            atomicAdd(&group_nitv[m.group], (uint32_t)n_emitted);
+            atomicAdd((unsigned long long *)&scalars[S_NITV], (unsigned long long)n_emitted);
+        }
+        atomicAdd((unsigned long long *)&scalars[S_NSAMPLES], (unsigned long long)m.len);
+    }
+    // unused slots
+    for (int k = n_emitted + lane; k < cap; k += 32) itv_nrec[slot0 + k] = 0;
+}
+
+__device__ __forceinline__ int channel_class(int ch, const wfs_params &p) {
+    // strax_interface.py:490-493
+    if (p.detector_nt) {
+        if (ch < p.he_first) return 0;
+        if (ch <= p.he_last) return 1;
+        return 2;
+    }
+    return 0;
+}
+
+__global__ void k_rec_keys(int64_t n_slots, DeviceConfig c, const Interval *itv,
+                           const uint32_t *itv_nrec, const uint32_t *itv_rec0, int64_t min_sample,
+                           int time_bits, uint64_t *rec_keys, uint32_t *rec_vals, uint32_t *rec_itv,
+                           int64_t *scalars) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    uint32_t n = itv_nrec[s];
+    if (!n) return;
+    const Interval it = itv[s];
+    const uint32_t r0 = itv_rec0[s];
+    const int cls = channel_class(it.channel, c.p);
+    for (uint32_t i = 0; i < n; i++) {
+        uint64_t trel = (uint64_t)(it.left + (int64_t)WFS_SAMPLES_PER_RECORD * i - min_sample);
+        rec_keys[r0 + i] = (uint64_t)it.channel | (trel << kChannelBits) |
+                           ((uint64_t)cls << (kChannelBits + time_bits));
+        rec_vals[r0 + i] = r0 + i;
+        rec_itv[r0 + i] = (uint32_t)s;
+    }
+    atomicAdd((unsigned long long *)&scalars[S_CLASS0 + cls], (unsigned long long)n);
+}
+
+// One warp per output record, records written at their final sorted position.
+__global__ void __launch_bounds__(256)
+k_pack(int64_t n_rec, DeviceConfig c, const uint32_t *__restrict__ rec_vals,
+       const uint32_t *__restrict__ rec_itv, const uint32_t *__restrict__ itv_rec0,
+       const Interval *__restrict__ itv, const int16_t *__restrict__ dense, uint32_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= n_rec) return;
+    const uint32_t r = rec_vals[j];
+    const uint32_t s = rec_itv[r];
+    const Interval it = itv[s];
+    const int i = (int)(r - itv_rec0[s]);
+    const int spr = WFS_SAMPLES_PER_RECORD;
+    const int length = min(it.len, spr * (i + 1)) - spr * i;
+    const int64_t time = (int64_t)c.p.dt * (it.left + (int64_t)spr * i);
+    uint32_t *o = out + j * (WFS_RECORD_BYTES / 4);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(dense + it.src + (int64_t)spr * i);
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        int wd = lane + 32 * k;
+        if (wd >= WFS_RECORD_BYTES / 4) break;
+        uint32_t v;
+        if (wd == 0) v = (uint32_t)(uint64_t)time;
+        else if (wd == 1) v = (uint32_t)((uint64_t)time >> 32);
+        else if (wd == 2) v = (uint32_t)length;
+        else if (wd == 3) v = ((uint32_t)(uint16_t)c.p.dt) | ((uint32_t)(uint16_t)it.channel << 16);
+        else if (wd == 4) v = (uint32_t)it.len;
+        else if (wd == 5) v = (uint32_t)(uint16_t)i;   // record_i, baseline = 0
+        else {
+            int s0 = 2 * (wd - 6);
+            v = 0;
+            if (s0 < length) {
+                v = src[wd - 6];
+                if (s0 + 1 >= length) v &= 0xffffu;
+            }
+        }
+        o[wd] = v;
+    }
+}
+
+__global__ void k_group_info(int64_t n_groups, DeviceConfig c, const int64_t *group_lr,
+                             const uint32_t *group_nitv, wfs_group_info *out) {
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    wfs_group_info gi;
+    int64_t lo = group_lr[2 * g], hi = group_lr[2 * g + 1];
+    if (lo == LLONG_MAX) {
+        gi.left = 0; gi.right = 0; gi.n_intervals = -1;   // empty group (no pulses)
+    } else {
+        gi.left = lo - c.p.trigger_window;
+        gi.right = hi + c.p.trigger_window;
+        if (gi.left % 2 != 0) gi.left -= 1;               // rawdata.py:221-222
+        gi.n_intervals = group_nitv[g];
+    }
+    out[g] = gi;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int bits_for(uint64_t n_values) {   // bits needed to hold values 0..n_values-1
+    int b = 0;
+    while ((uint64_t(1) << b) < n_values) b++;
+    return b;
+}
+
+Backend::Backend(const DeviceConfig *cfg, cudaStream_t stream, LaunchCounter *lc)
+    : cfg_(cfg), stream_(stream), lc_(lc) {
+    prim_.stream = stream;
+    prim_.lc = lc;
+    WFS_CUDA_CHECK(cudaEventCreate(&ev0_));
+    WFS_CUDA_CHECK(cudaEventCreate(&ev1_));
+    WFS_CUDA_CHECK(cudaHostAlloc((void **)&h_scalars_, sizeof(int64_t) * S_COUNT, cudaHostAllocDefault));
+}
+
+Backend::~Backend() {
+    release();
+    cudaEventDestroy(ev0_);
+    cudaEventDestroy(ev1_);
+    if (h_scalars_) cudaFreeHost(h_scalars_);
+}
+
+void Backend::release() {
+    DevBuf *all[] = {&keys_, &vals_, &st_, &sg_, &flags64_, &pulse_first_, &pulse_left_, &pulse_win_,
+                     &win_first_pulse_, &win_meta_, &win_scan_, &group_tmin_, &group_lr_, &scalars_,
+                     &dense_, &zflags_, &itv_, &itv_nrec_, &itv_rec0_, &rec_keys_, &rec_vals_,
+                     &rec_itv_, &group_nitv_, &group_ix_};
+    for (DevBuf *b : all) b->release();
+    prim_.release();
+}
+
+#define LAUNCH(kernel, grid, block, ...)                         \
+    do {                                                         \
+        kernel<<<(grid), (block), 0, stream_>>>(__VA_ARGS__);    \
+        lc_->n++;                                                \
+    } while (0)
+
+void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_records,
+                  wfs_group_info *group_info_out, BackendResult &res) {
+    const DeviceConfig &c = *cfg_;
+    res = BackendResult();
+    const int64_t n = b.n, ng = b.n_groups;
+    if (ng <= 0) return;
+    if (n >= (int64_t(1) << 31)) throw std::runtime_error("photon batch too large (>= 2^31)");
+    KeyLayout kl;
+    kl.bits_rank = bits_for((uint64_t)b.max_rank + 1);
+    kl.bits_group = bits_for((uint64_t)ng + 1);
+    kl.shift_rank = kRelTimeBits;
+    kl.shift_ch = kl.shift_rank + kl.bits_rank;
+    kl.shift_group = kl.shift_ch + kChannelBits;
+    kl.total_bits = kl.shift_group + kl.bits_group;
+    if (kl.total_bits > 64 || kl.bits_group + kChannelBits > 32) {
+        res.error = WFS_E_KEYBITS;
+        return;
+    }
+    const int T = 256;
+    scalars_.reserve(sizeof(int64_t) * S_COUNT);
+    group_tmin_.reserve(sizeof(int64_t) * ng);
+    group_lr_.reserve(sizeof(int64_t) * 2 * ng);
+    group_nitv_.reserve(sizeof(uint32_t) * ng);
+    int64_t *scal = scalars_.as<int64_t>();
+    LAUNCH(k_init, div_up(std::max<int64_t>(ng, S_COUNT), T), T, group_tmin_.as<int64_t>(),
+           group_lr_.as<int64_t>(), group_nitv_.as<uint32_t>(), ng, scal);
+    int64_t np = 0, nw = 0;
+    if (n > 0) {
+        keys_.reserve(sizeof(uint64_t) * n);
+        vals_.reserve(sizeof(uint32_t) * n);
+        st_.reserve(sizeof(int64_t) * n);
+        sg_.reserve(sizeof(double) * n);
+        flags64_.reserve(sizeof(uint64_t) * (n + 1));
+        LAUNCH(k_group_tmin, div_up(n, T), T, b, c, group_tmin_.as<int64_t>());
+        LAUNCH(k_build_keys, div_up(n, T), T, b, c, kl, group_tmin_.as<int64_t>(),
+               keys_.as<uint64_t>(), vals_.as<uint32_t>(), scal);
+        prim_.sort_pairs(keys_.as<uint64_t>(), vals_.as<uint32_t>(), n, kl.total_bits);
+        LAUNCH(k_gather_flags, div_up(n, T), T, b, kl, keys_.as<uint64_t>(), vals_.as<uint32_t>(),
+               st_.as<int64_t>(), sg_.as<double>(), flags64_.as<uint64_t>(), scal);
+        // positions: reuse the (now consumed) alt key buffer of the sort for the scan output
+        DevBuf &posbuf = prim_.sort_keys_alt;
+        posbuf.reserve(sizeof(uint64_t) * (n + 1));
+        prim_.exclusive_scan_u64(flags64_.as<uint64_t>(), posbuf.as<uint64_t>(), n, true);
+        // upper bounds: every photon its own pulse/window
+        pulse_first_.reserve(sizeof(uint32_t) * (n + 1));
+        pulse_win_.reserve(sizeof(uint32_t) * (n + 1));
+        win_first_pulse_.reserve(sizeof(uint32_t) * (n + 1));
+        DevBuf &winkey = prim_.sort_vals_alt;   // [n] u32, free after the sort
+        LAUNCH(k_emit_pulses, div_up(n + 1, T), T, n, kl, keys_.as<uint64_t>(),
+               flags64_.as<uint64_t>(), posbuf.as<uint64_t>(), pulse_first_.as<uint32_t>(),
+               pulse_win_.as<uint32_t>(), win_first_pulse_.as<uint32_t>(), winkey.as<uint32_t>(), scal);
+        WFS_CUDA_CHECK(cudaMemcpyAsync(h_scalars_, scal, sizeof(int64_t) * S_COUNT,
+                                       cudaMemcpyDeviceToHost, stream_));
+        WFS_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        if (h_scalars_[S_ERR]) { res.error = (int)h_scalars_[S_ERR]; return; }
+        res.n_valid_photons = h_scalars_[S_NVALID];
+        np = h_scalars_[S_NPULSES];
+        nw = h_scalars_[S_NWIN];
+    }
+    res.n_pulses = np;
+    const int64_t nwt = 2 * nw;
+    res.n_windows = 0;
+    int64_t n_tiles = 0, n_slots = 0, min_sample = 0, max_sample = 0;
+    const bool he_rows = c.p.detector_nt != 0;
+    static_assert(sizeof(WinMeta) == 40, "WinMeta layout");
+    DevBuf &group_ix_buf = group_ix_;
+    group_ix_buf.reserve(sizeof(int64_t) * ng);
+    if (nw > 0) {
+        pulse_left_.reserve(sizeof(int64_t) * 2 * np);
+        win_meta_.reserve(sizeof(WinMeta) * nwt);
+        win_scan_.reserve(sizeof(uint64_t) * (nwt + 1));
+        LAUNCH(k_window_extents, div_up(nw, T), T, nw, c, st_.as<int64_t>(),
+               pulse_first_.as<uint32_t>(), win_first_pulse_.as<uint32_t>(),
+               prim_.sort_vals_alt.as<uint32_t>(), pulse_left_.as<int64_t>(), win_meta_.as<WinMeta>(),
+               win_scan_.as<uint64_t>(), group_lr_.as<int64_t>(), scal, he_rows ? 1 : 0);
+        prim_.exclusive_scan_u64(win_scan_.as<uint64_t>(), win_scan_.as<uint64_t>(), nwt, true);
+    }
+    LAUNCH(k_group_noise, div_up(ng, T), T, ng, c, group_lr_.as<int64_t>(), b.ix_rand, b.seed,
+           b.group_base, group_ix_buf.as<int64_t>(), scal);
+    if (nw > 0) {
+        // total tiles / interval slots live in win_scan[nwt]
+        uint64_t tot;
+        WFS_CUDA_CHECK(cudaMemcpyAsync(h_scalars_, scal, sizeof(int64_t) * S_COUNT,
+                                       cudaMemcpyDeviceToHost, stream_));
+        WFS_CUDA_CHECK(cudaMemcpyAsync(&tot, win_scan_.as<uint64_t>() + nwt, sizeof(uint64_t),
+                                       cudaMemcpyDeviceToHost, stream_));
+        WFS_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        if (h_scalars_[S_ERR]) { res.error = (int)h_scalars_[S_ERR]; return; }
+        n_tiles = (int64_t)(uint32_t)tot;
+        n_slots = (int64_t)(tot >> 32);
+        min_sample = h_scalars_[S_MINSAMPLE];
+        max_sample = h_scalars_[S_MAXSAMPLE];
+        res.n_tiles = n_tiles;
+        dense_.reserve(sizeof(int16_t) * n_tiles * kTile);
+        zflags_.reserve(sizeof(uint32_t) * n_tiles * (kTile / 32));
+        itv_.reserve(sizeof(Interval) * n_slots);
+        itv_nrec_.reserve(sizeof(uint32_t) * (n_slots + 1));
+        itv_rec0_.reserve(sizeof(uint32_t) * (n_slots + 1));
+        WFS_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
+        int grid = (int)std::min<int64_t>(n_tiles, (int64_t)kNumSMs * 64);
+        LAUNCH(k_digitize, grid, kDigiThreads, n_tiles, nwt, c, win_meta_.as<WinMeta>(),
+               win_scan_.as<uint64_t>(), st_.as<int64_t>(), sg_.as<double>(),
+               pulse_first_.as<uint32_t>(), pulse_left_.as<int64_t>(), group_ix_buf.as<int64_t>(),
+               dense_.as<int16_t>(), zflags_.as<uint32_t>());
+        WFS_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
+        LAUNCH(k_zle, div_up(nwt * 32, 128), 128, nwt, c, win_meta_.as<WinMeta>(),
+               win_scan_.as<uint64_t>(), zflags_.as<uint32_t>(), itv_.as<Interval>(),
+               itv_nrec_.as<uint32_t>(), group_nitv_.as<uint32_t>(), scal);
+        prim_.exclusive_scan_u32(itv_nrec_.as<uint32_t>(), itv_rec0_.as<uint32_t>(), n_slots, true);
+        uint32_t nrec32;
+        WFS_CUDA_CHECK(cudaMemcpyAsync(&nrec32, itv_rec0_.as<uint32_t>() + n_slots, sizeof(uint32_t),
+                                       cudaMemcpyDeviceToHost, stream_));
+        WFS_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        res.n_records = nrec32;
+        WFS_CUDA_CHECK(cudaEventElapsedTime(&res.ms_digitize, ev0_, ev1_));
+    }
+    if (group_info_out)
+        LAUNCH(k_group_info, div_up(ng, T), T, ng, c, group_lr_.as<int64_t>(),
+               group_nitv_.as<uint32_t>(), group_info_out);
+    const int64_t nrec = res.n_records;
+    if (nrec > 0 && nrec <= cap_records) {
+        int time_bits = bits_for((uint64_t)(max_sample - min_sample + 1));
+        int key_bits = kChannelBits + time_bits + 2;
+        if (key_bits > 64) { res.error = WFS_E_KEYBITS; return; }
+        rec_keys_.reserve(sizeof(uint64_t) * nrec);
+        rec_vals_.reserve(sizeof(uint32_t) * nrec);
+        rec_itv_.reserve(sizeof(uint32_t) * nrec);
+        LAUNCH(k_rec_keys, div_up(n_slots, T), T, n_slots, c, itv_.as<Interval>(),
+               itv_nrec_.as<uint32_t>(), itv_rec0_.as<uint32_t>(), min_sample, time_bits,
+               rec_keys_.as<uint64_t>(), rec_vals_.as<uint32_t>(), rec_itv_.as<uint32_t>(), scal);
+        prim_.sort_pairs(rec_keys_.as<uint64_t>(), rec_vals_.as<uint32_t>(), nrec, key_bits);
+        LAUNCH(k_pack, div_up(nrec * 32, 256), 256, nrec, c, rec_vals_.as<uint32_t>(),
+               rec_itv_.as<uint32_t>(), itv_rec0_.as<uint32_t>(), itv_.as<Interval>(),
+               dense_.as<int16_t>(), reinterpret_cast<uint32_t *>(records_out));
+    }
+    WFS_CUDA_CHECK(cudaMemcpyAsync(h_scalars_, scal, sizeof(int64_t) * S_COUNT,
+                                   cudaMemcpyDeviceToHost, stream_));
+    WFS_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    WFS_CUDA_CHECK(cudaGetLastError());
+    if (h_scalars_[S_ERR]) res.error = (int)h_scalars_[S_ERR];
+    res.n_intervals = h_scalars_[S_NITV];
+    res.n_samples = h_scalars_[S_NSAMPLES];
+    res.n_windows = nwt;
+    for (int k = 0; k < 3; k++) res.n_rec_class[k] = h_scalars_[S_CLASS0 + k];
+}
+
+}  // namespace wfs

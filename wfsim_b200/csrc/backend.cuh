@@ -1,0 +1,74 @@
+// Deterministic back end: photons -> pulses -> windows -> ADC samples -> ZLE -> raw_records.
+#pragma once
+#include "common.cuh"
+#include "../../include/wfsim_b200.h"
+
+namespace wfs {
+
+constexpr int kTile = 512;          // samples per digitize tile (one CTA)
+constexpr int kDigiThreads = 128;
+constexpr int kRelTimeBits = 24;    // ns inside a digitisation group (< 1e6 samples * 10 ns)
+constexpr int kChannelBits = 10;
+constexpr int64_t kMaxGroupSamples = 1000000;  // rawdata.py:219
+
+// Device-resident tables + scalars shared by all kernels.
+struct DeviceConfig {
+    wfs_params p;
+    double *templates = nullptr;     // [dt][template_length]
+    double *gains = nullptr;         // [n_tpc_pmts]
+    int32_t *zle_thr = nullptr;      // [n_rows]
+    double *noise_t = nullptr;       // transposed: [noise_nch][noise_len]
+    int64_t noise_len = 0;
+    int32_t noise_nch = 0;
+};
+
+// Photons of one batch, resident in HBM, in arbitrary order.
+struct PhotonBatch {
+    int64_t n = 0;
+    const int64_t *t = nullptr;
+    const int32_t *channel = nullptr;
+    const double *gain = nullptr;
+    const int32_t *pulse_call = nullptr;   // batch-local pulse-call id
+    int64_t n_pulse_calls = 0;
+    const int32_t *pc_group = nullptr;     // [n_pulse_calls] batch-local group id
+    const int32_t *pc_rank = nullptr;      // [n_pulse_calls] rank of the pulse call inside its group
+    int32_t max_rank = 0;
+    int64_t n_groups = 0;
+    const int64_t *ix_rand = nullptr;      // [n_groups] or nullptr -> Philox(seed, group_base + g)
+    uint64_t seed = 0;
+    int64_t group_base = 0;                // global index of group 0 of this batch (RNG counter)
+};
+
+struct BackendResult {
+    int64_t n_valid_photons = 0, n_pulses = 0, n_windows = 0, n_tiles = 0;
+    int64_t n_intervals = 0, n_records = 0, n_samples = 0;
+    int64_t n_rec_class[3] = {0, 0, 0};
+    float ms_digitize = 0.f;
+    int error = 0;
+};
+
+class Backend {
+public:
+    Backend(const DeviceConfig *cfg, cudaStream_t stream, LaunchCounter *lc);
+    ~Backend();
+    // Runs the whole back end on a device-resident batch.  Records are produced in
+    // `records_out` (device pointer, capacity cap_records rows): [tpc | he | aqmon] segments each
+    // sorted by (time, channel).  group_info_out: device pointer [n_groups] or nullptr.
+    // If cap_records is too small, res.n_records holds the need and nothing is written.
+    void run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_records,
+             wfs_group_info *group_info_out, BackendResult &res);
+    void release();
+
+private:
+    const DeviceConfig *cfg_;
+    cudaStream_t stream_;
+    LaunchCounter *lc_;
+    Primitives prim_;
+    cudaEvent_t ev0_, ev1_;
+    int64_t *h_scalars_ = nullptr;   // pinned readback area
+    DevBuf keys_, vals_, st_, sg_, flags64_, pulse_first_, pulse_left_, pulse_win_, win_first_pulse_,
+        win_meta_, win_scan_, group_tmin_, group_lr_, scalars_, dense_, zflags_, itv_, itv_nrec_,
+        itv_rec0_, rec_keys_, rec_vals_, rec_itv_, group_nitv_, group_ix_;
+};
+
+}  // namespace wfs

@@ -1,0 +1,32 @@
+// Per-GPU simulator handle: device tables, streams, workspaces, back end + front end.
+#pragma once
+#include "backend.cuh"
+
+namespace wfs {
+
+struct Frontend;   // sampling stages + host scheduler (frontend.cu)
+
+struct Handle {
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_a, ev_b, ev_c, ev_d;
+    DeviceConfig cfg;
+    std::vector<void *> owned;          // device tables freed at destroy
+    std::vector<double> h_gains;
+    LaunchCounter launches;
+    Backend *backend = nullptr;
+    Frontend *frontend = nullptr;
+    std::string last_error;
+    // staging for host-pointer calls
+    DevBuf d_t, d_ch, d_gain, d_pc, d_pc_group, d_pc_rank, d_ix, d_records, d_groups;
+
+    Handle(const wfs_params &p, const wfs_tables &t, int dev);
+    ~Handle();
+    void frontend_init(const wfs_tables &t);
+    void frontend_release();
+};
+
+void pulse_call_ranks(const int32_t *group_of, int64_t n_pc, int64_t n_groups,
+                      std::vector<int32_t> &rank, int32_t &max_rank);
+
+}  // namespace wfs
