@@ -108,11 +108,11 @@ typedef struct wfs_tables {
     int32_t ap_amp_len[WFS_MAX_AP_ELEMENTS];
     int32_t ap_amp_rows[WFS_MAX_AP_ELEMENTS];
     double ap_amp_bin[WFS_MAX_AP_ELEMENTS];
-    /* photo-ionisation delay distribution (uniform_to_ele_ap, afterpulse.py:33-80):
-     * inverse CDF of the delay histogram and the coarse time grid of _reduce_instruction_timing */
-    const double *pi_delay_icdf;    /* [pi_icdf_len] delay = interp(U) on a uniform U grid */
-    int32_t pi_icdf_len;
+    /* photo-ionisation electrons (uniform_to_ele_ap, afterpulse.py:33-80): the coarse delay grid of
+     * _reduce_instruction_timing and the probability that one delay drawn from the delay
+     * histogram falls into each coarse bin (np.digitize convention) */
     const double *pi_coarse_time;   /* [pi_coarse_len] */
+    const double *pi_coarse_prob;   /* [pi_coarse_len] */
     int32_t pi_coarse_len;
 } wfs_tables;
 
@@ -126,6 +126,7 @@ typedef struct wfs_instr_maps {
     const float *pattern;           /* [n_pattern_rows][n_tpc_pmts] un-normalised per-PMT pattern */
     const int32_t *pattern_row;     /* [n_instr] row of `pattern` for the instruction; NULL -> row 0 */
     int64_t n_pattern_rows;
+    double s2_sc_gain_default;      /* used when s2_sc_gain is NULL */
 } wfs_instr_maps;
 
 typedef struct wfs_counts {
@@ -145,6 +146,8 @@ typedef struct wfs_counts {
     int64_t gpu_launches;           /* kernels launched by this call */
     int64_t need_records;           /* capacities needed when WFS_E_CAPACITY */
     int64_t need_truth;
+    int64_t need_groups;
+    int64_t need_batches;
     double ms_total;                /* CUDA-event time of the device work of this call */
     double ms_digitize;             /* of which: the digitize (superpose+ADC+noise+clip) kernel */
     double ms_h2d, ms_d2h;
@@ -162,7 +165,7 @@ int wfs_create(const wfs_params *params, const wfs_tables *tables, int device, v
 void wfs_destroy(void *handle);
 const char *wfs_last_error(void *handle);   /* handle may be NULL for create errors */
 int wfs_abi_version(void);
-void wfs_struct_sizes(int64_t *out5);       /* sizeof of the five structs above, for binding checks */
+void wfs_struct_sizes(int64_t *out6);       /* sizeof of the six structs of this header, for binding checks */
 int wfs_device_count(void);
 
 /* Pinned host memory for output buffers (so device->host copies are plain DMA). */
@@ -187,27 +190,45 @@ int wfs_simulate_photons(void *handle, int64_t n_photons, const int64_t *t_ns,
                          uint8_t *records, int64_t cap_records, wfs_group_info *groups,
                          wfs_counts *counts);
 
+/* Output buffers of the full path (caller-allocated host memory; NULL/0 = not wanted). */
+typedef struct wfs_outputs {
+    uint8_t *records;               /* 244-byte rows; per batch [raw_records | _he | _aqmon], batches in time order */
+    int64_t cap_records;
+    uint8_t *truth;                 /* 218-byte rows, one per Pulse call, in execution order */
+    int64_t cap_truth;
+    wfs_group_info *groups;         /* one per digitisation group, in time order */
+    int64_t cap_groups;
+    int64_t *batch_records;         /* [cap_batches][3]: records per data type of each batch */
+    int64_t cap_batches;
+} wfs_outputs;
+
 /* Full path: instructions in, records + truth out.
  * Replaces ChunkRawRecords.__call__ -> RawData.__call__ -> S1/S2/afterpulse Pulse calls ->
  * digitize_pulse_cache -> ZLE -> record packing (strax_interface.py:368-497, rawdata.py:38-375).
  *   instructions   packed 70-byte rows (instruction_dtype); any order
  *   maps           per-instruction map values (see wfs_instr_maps)
- * Output as wfs_simulate_photons plus `truth` (218-byte rows, one per Pulse call, ordered by
- * Pulse-call execution order) and `groups` ([cap_groups]; counts->n_groups valid entries). */
+ * When a capacity is too small the call still runs every batch (to learn the sizes), returns
+ * WFS_E_CAPACITY and leaves the needed sizes in counts->need_*; a second call with larger
+ * buffers reproduces the same data (Philox). */
 int wfs_simulate(void *handle, const uint8_t *instructions, int64_t n_instructions,
-                 const wfs_instr_maps *maps, uint64_t seed,
-                 uint8_t *records, int64_t cap_records, uint8_t *truth, int64_t cap_truth,
-                 wfs_group_info *groups, int64_t cap_groups, wfs_counts *counts);
+                 const wfs_instr_maps *maps, uint64_t seed, wfs_outputs *out, wfs_counts *counts);
 
-/* Device-resident variant for throughput measurement: instructions/maps are uploaded once with
- * wfs_stage_instructions, wfs_run_staged runs the whole path with every buffer in HBM and leaves
- * the records on the device (counts are still returned).  */
+/* Device-resident variant for throughput measurement: instructions/maps are parsed, planned and
+ * uploaded once by wfs_stage_instructions; wfs_run_staged then runs the whole path with every
+ * buffer in HBM and leaves the records on the device (counts are returned; `out` may carry
+ * truth/groups buffers, its records pointer is ignored). */
 int wfs_stage_instructions(void *handle, const uint8_t *instructions, int64_t n_instructions,
                            const wfs_instr_maps *maps);
-int wfs_run_staged(void *handle, uint64_t seed, wfs_counts *counts);
+int wfs_run_staged(void *handle, uint64_t seed, wfs_outputs *out, wfs_counts *counts);
 
-/* Stage-level entry points used by the statistical parity tests (each draws from the same
- * Philox streams the full path uses). */
+/* Stage-level dump used by the statistical parity tests: runs only the sampling front end (the
+ * same Philox streams the full path uses) and returns 32-byte rows
+ *   stage 0 (photons):  int64 t_ns; double gain; int32 channel; int32 instruction (index into the
+ *                       given array; the parent S2 for secondaries); int32 flags (1 = double-pe,
+ *                       2 = PMT afterpulse, 4 = photo-ionisation secondary); int32 secondary id
+ *   stage 1 (emitters): int64 t_ns; double 0; int32 n_photons; int32 instruction; int32 flags; int32 id
+ * Replaces nothing in the reference; it exposes S1/S2.photon_timings/photon_channels (s1.py:138-238,
+ * s2.py:258-315,504-682) and Pulse.__call__'s TTS/DPE/SPE draws (pulse.py:53-103) for testing. */
 int wfs_sample_stage(void *handle, int stage, const uint8_t *instructions, int64_t n_instructions,
                      const wfs_instr_maps *maps, uint64_t seed, void *out, int64_t cap, int64_t *n_out);
 

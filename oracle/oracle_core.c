@@ -229,3 +229,35 @@ int64_t orc_pack_records(int64_t n_itv, const int32_t *itv_ch, const int64_t *it
     }
     return n;
 }
+
+/* wfsim/core/pulse.py:82-144 (preset-gain form): photons of ONE Pulse call sorted by
+ * (channel, time).  Pass 1 (currents == NULL) returns the number of pulses and the total current
+ * length in out_n[0], out_n[1]; pass 2 fills p_ch/p_left/p_right/p_off and the currents. */
+void orc_pulse_call(int64_t n, const int64_t *t, const int32_t *ch, const double *gain,
+                    const double *gains, int64_t dt, int64_t left_margin, int64_t right_margin,
+                    const double *templates, int tlen, int32_t *p_ch, int64_t *p_left,
+                    int64_t *p_right, int64_t *p_off, double *currents, int64_t *out_n)
+{
+    int64_t np = 0, off = 0;
+    int64_t a = 0;
+    while (a < n) {
+        int64_t b = a + 1;
+        while (b < n && ch[b] == ch[a]) b++;
+        int32_t c = ch[a];
+        if (c >= 0 && gains[c] != 0.0) {      /* turned-off PMTs: pulse.py:89-90 */
+            int64_t q0 = t[a] / dt, q1 = t[b - 1] / dt;
+            if (t[a] % dt != 0 && t[a] < 0) q0--;
+            if (t[b - 1] % dt != 0 && t[b - 1] < 0) q1--;
+            int64_t left = q0 - left_margin, right = q1 + right_margin;
+            if (currents) {
+                p_ch[np] = c; p_left[np] = left; p_right[np] = right; p_off[np] = off;
+                orc_add_current(t + a, gain + a, b - a, left, dt, templates, tlen, currents + off);
+            }
+            np++;
+            off += right - left + 1;
+        }
+        a = b;
+    }
+    out_n[0] = np;
+    out_n[1] = off;
+}

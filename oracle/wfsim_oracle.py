@@ -127,48 +127,67 @@ def zle_thresholds(cfg, n_rows=801):
 # ------------------------------------------------------------------------------------------
 # deterministic back end
 # ------------------------------------------------------------------------------------------
+class Pulses:
+    """Pulses of one or more Pulse calls: arrays (channel, left, right, offset) + currents."""
+
+    def __init__(self, ch=None, left=None, right=None, off=None, cur=None):
+        self.ch = np.zeros(0, np.int32) if ch is None else ch
+        self.left = np.zeros(0, np.int64) if left is None else left
+        self.right = np.zeros(0, np.int64) if right is None else right
+        self.off = np.zeros(0, np.int64) if off is None else off
+        self.cur = np.zeros(0, np.float64) if cur is None else cur
+
+    def __len__(self):
+        return len(self.ch)
+
+    @staticmethod
+    def concat(parts):
+        parts = [p for p in parts if len(p)]
+        if not parts:
+            return Pulses()
+        shift = np.cumsum([0] + [len(p.cur) for p in parts[:-1]])
+        return Pulses(np.concatenate([p.ch for p in parts]), np.concatenate([p.left for p in parts]),
+                      np.concatenate([p.right for p in parts]),
+                      np.concatenate([p.off + s for p, s in zip(parts, shift)]),
+                      np.concatenate([p.cur for p in parts]))
+
+
 def pulse_call(cfg, templates, t, ch, gain):
-    """wfsim/core/pulse.py:82-144 with `_photon_gains` preset: per channel pulse extents and
-    float64 current.  Input photons of ONE pulse call, any order.  Returns list of pulses."""
+    """wfsim/core/pulse.py:82-144 with the photon gains already decided: per channel pulse
+    extents and float64 current.  Photons of ONE Pulse call, any order."""
     dt = cfg.get('sample_duration', 10)
-    gains = np.asarray(cfg['gains'])
+    gains = np.ascontiguousarray(cfg['gains'], np.float64)
     before = int(cfg['samples_to_store_before']) + cfg.get('samples_before_pulse_center', 2)
     after = int(cfg['samples_to_store_after']) + cfg.get('samples_after_pulse_center', 20)
     L = lib()
+    t = np.asarray(t, np.int64)
     order = np.lexsort((t, ch))           # by channel, then time (stable)
-    t, ch, gain = t[order], ch[order], gain[order]
-    pulses = []
-    bounds = np.flatnonzero(np.diff(ch)) + 1
-    starts = np.concatenate([[0], bounds])
-    stops = np.concatenate([bounds, [len(ch)]])
+    t = np.ascontiguousarray(t[order])
+    ch = np.ascontiguousarray(np.asarray(ch)[order], np.int32)
+    gain = np.ascontiguousarray(np.asarray(gain)[order], np.float64)
     tm = np.ascontiguousarray(templates, dtype=np.float64)
-    for a, b in zip(starts, stops):
-        c = int(ch[a])
-        if gains[c] == 0:                 # turned_off_pmts, pulse.py:89-90
-            continue
-        tt = np.ascontiguousarray(t[a:b], dtype=np.int64)
-        gg = np.ascontiguousarray(gain[a:b], dtype=np.float64)
-        left = int(tt[0] // dt) - before
-        right = int(tt[-1] // dt) + after
-        cur = np.zeros(right - left + 1)
-        L.orc_add_current(_p(tt), _p(gg), ctypes.c_int64(len(tt)), ctypes.c_int64(left),
-                          ctypes.c_int64(dt), _p(tm), ctypes.c_int(tm.shape[1]), _p(cur))
-        pulses.append(dict(channel=c, left=left, right=right, current=cur))
-    return pulses
+    out_n = np.zeros(2, np.int64)
+    args = (ctypes.c_int64(len(t)), _p(t), _p(ch), _p(gain), _p(gains), ctypes.c_int64(dt),
+            ctypes.c_int64(before), ctypes.c_int64(after), _p(tm), ctypes.c_int(tm.shape[1]))
+    L.orc_pulse_call(*args, None, None, None, None, None, _p(out_n))
+    n_p, n_c = int(out_n[0]), int(out_n[1])
+    P = Pulses(np.zeros(n_p, np.int32), np.zeros(n_p, np.int64), np.zeros(n_p, np.int64),
+               np.zeros(n_p, np.int64), np.zeros(n_c, np.float64))
+    if n_p:
+        L.orc_pulse_call(*args, _p(P.ch), _p(P.left), _p(P.right), _p(P.off), _p(P.cur), _p(out_n))
+    return P
 
 
 def digitize_zle(cfg, pulses, noise=None, ix_rand=0):
     """rawdata.py:204-311 for one pulse cache -> (itv_ch, itv_left, itv_right, itv_off, samples,
     (group_left, group_right))."""
     L = lib()
+    if isinstance(pulses, list):
+        pulses = Pulses.concat(pulses)
     n = len(pulses)
-    p_ch = np.array([p['channel'] for p in pulses], np.int32)
-    p_left = np.array([p['left'] for p in pulses], np.int64)
-    p_right = np.array([p['right'] for p in pulses], np.int64)
-    lens = p_right - p_left + 1
-    p_off = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
-    cur = np.concatenate([p['current'] for p in pulses]) if n else np.zeros(0)
-    cur = np.ascontiguousarray(cur, np.float64)
+    p_ch, p_left, p_right, p_off = (np.ascontiguousarray(a) for a in
+                                     (pulses.ch, pulses.left, pulses.right, pulses.off))
+    cur = np.ascontiguousarray(pulses.cur, np.float64)
     c = DigiCfg()
     c.current_2_adc = current_2_adc(cfg)
     c.trigger_window = cfg['trigger_window']
@@ -241,11 +260,10 @@ def simulate_photons(cfg, pcall, ch, t, gain, group_of, noise=None, ix_rand=None
     recs = []
     groups_lr = []
     for grp in range(n_groups):
-        cache = []
-        for pc in np.flatnonzero(group_of == grp):
-            m = pcall == pc
-            cache += pulse_call(cfg, templates, t[m], ch[m], gain[m])
-        if not cache:
+        cache = Pulses.concat([pulse_call(cfg, templates, t[pcall == pc], ch[pcall == pc],
+                                          gain[pcall == pc])
+                               for pc in np.flatnonzero(group_of == grp)])
+        if not len(cache):
             groups_lr.append(None)
             continue
         ir = 0 if ix_rand is None else ix_rand[grp]

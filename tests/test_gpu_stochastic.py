@@ -1,0 +1,159 @@
+"""GPU: statistical parity of the Philox sampling kernels with the reference (golden samples drawn
+by the unmodified reference, tests/golden/stoch_c0.npz) -- two-sample KS / chi-square at p > 0.01
+as BASELINE.json specifies -- plus exact consistency of the full path with the oracle's
+deterministic back end on the photons the GPU itself generated."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.conftest import GOLDEN, load_c0_config
+from tests.golden.make_golden_stoch import S1_AMP, S1_N, S1_Z, S2_AMP, S2_N, S2_Z, fixed_rows
+from tests.golden.synth_instructions import c0_like
+from tests.stat_helpers import P_MIN, chi2_counts_p, discrete_p, ks_p, mean_p
+from wfsim_b200.dtypes import instruction_dtype
+
+pytestmark = pytest.mark.gpu
+IDT = np.dtype(instruction_dtype)
+
+
+@pytest.fixture(scope='module')
+def gold():
+    return np.load(os.path.join(GOLDEN, 'stoch_c0.npz'))
+
+
+def make_sim(**cfg_extra):
+    from wfsim_b200.resource import Resource
+    from wfsim_b200.simulator import Simulator
+    cfg = load_c0_config(**cfg_extra)
+    z = np.load(os.path.join(GOLDEN, 'c0_tables.npz'))
+    res = Resource(cfg, spe_ppf=z['spe_unique'], spe_row=z['spe_row'][:494])
+    return Simulator(cfg, resource=res), cfg
+
+
+@pytest.fixture(scope='module')
+def sim():
+    s, _ = make_sim()
+    yield s
+    s.close()
+
+
+def test_s1_stage(sim, gold):
+    rows = fixed_rows(IDT, 1, S1_AMP, 4 * S1_N, S1_Z)
+    ph = sim.sample_stage(rows, stage=0, seed=11)
+    n = np.bincount(ph['instruction'], minlength=len(rows))
+    assert discrete_p(n, gold['s1_n_photon']) > P_MIN
+    trel = ph['t'] - rows['time'][ph['instruction']]
+    rng = np.random.default_rng(0)
+    assert ks_p(trel + rng.random(len(trel)), gold['s1_t_rel'] + rng.random(len(gold['s1_t_rel']))) > P_MIN
+    assert chi2_counts_p(np.bincount(ph['channel'], minlength=494), gold['s1_ch_hist']) > P_MIN
+    # double-pe fraction is Binomial(1, p_dpe) per photon (pulse.py:76-79)
+    from scipy import stats
+    k = int((ph['flags'] & 1).sum())
+    assert stats.binomtest(k, len(ph), 0.219).pvalue > 1e-3
+    # SPE factor of single-pe photons: table lookup with index int(U * 2000) + 1 (pulse.py:225-227)
+    single = ph[(ph['flags'] & 1) == 0]
+    fac = single['gain'] / sim.config['gains'][single['channel']]
+    assert discrete_p(np.round(fac), np.round(gold['spe_factor'])) > P_MIN
+
+
+def test_s2_stage(sim, gold):
+    rows = fixed_rows(IDT, 2, S2_AMP, 3 * S2_N, S2_Z)
+    em = sim.sample_stage(rows, stage=1, seed=12)
+    ph = sim.sample_stage(rows, stage=0, seed=12)
+    ne = np.bincount(em['instruction'], minlength=len(rows))
+    assert discrete_p(ne, gold['s2_n_electron']) > P_MIN
+    assert ks_p(em['t'] - rows['time'][em['instruction']], gold['s2_e_rel']) > P_MIN
+    nph_e = em['channel']                 # stage 1 rows carry n_photons in the channel slot
+    assert discrete_p(nph_e, gold['s2_ph_per_e']) > P_MIN
+    assert len(ph) == nph_e.sum()
+    dt = ph['t'] - np.repeat(em['t'], nph_e)          # photons are emitted in emitter order
+    sub = np.random.default_rng(1).choice(len(dt), 150000, replace=False)
+    assert discrete_p(dt[sub], gold['s2_dt_photon']) > P_MIN
+    assert chi2_counts_p(np.bincount(ph['channel'], minlength=494), gold['s2_ch_hist']) > P_MIN
+    assert mean_p(np.bincount(ph['instruction'], minlength=len(rows)), gold['s2_n_photon']) > P_MIN
+
+
+def test_chain_against_reference_and_invariants(sim, gold):
+    inst = gold['chain_instructions'].view(IDT)
+    ratios = {1: [], 2: []}
+    areas = {1: [], 2: []}
+    itv, adc = [], []
+    for seed in range(4):
+        out = sim.simulate(inst, seed=seed)
+        tr = out['truth']
+        assert len(tr) == len(gold['chain_truth_type'])
+        assert np.all(tr['n_pe'] >= tr['n_photon'])
+        assert np.all(tr['n_photon_bottom'] <= tr['n_photon'])
+        assert np.all(tr['n_pe_trigger'] <= tr['n_pe'])
+        assert np.all(np.diff(out['raw_records']['time']) >= 0)
+        assert len(out['raw_records_aqmon']) == 0
+        for typ in (1, 2):
+            m = tr['type'] == typ
+            ratios[typ].append(tr['n_photon'][m] / tr['amp'][m])
+            areas[typ].append(tr['raw_area'][m] / np.maximum(tr['n_photon'][m], 1))
+        rr = out['raw_records']
+        itv.append(int(out['groups']['n_intervals'].clip(0).sum()))
+        adc.append(int((16000 - rr['data'].astype(np.int64))[np.arange(110)[None, :] < rr['length'][:, None]].sum()))
+    for typ in (1, 2):
+        g = gold['chain_truth_type'] == typ
+        assert mean_p(np.concatenate(ratios[typ]), gold['chain_truth_n_photon'][g] / gold['chain_truth_amp'][g]) > P_MIN
+        assert mean_p(np.concatenate(areas[typ]),
+                      gold['chain_truth_raw_area'][g] / np.maximum(gold['chain_truth_n_photon'][g], 1)) > P_MIN
+    ref_itv, ref_samples, ref_area = gold['chain_totals']
+    assert abs(np.mean(itv) - ref_itv) < 0.05 * ref_itv
+    assert abs(np.mean(adc) - ref_area) < 0.05 * ref_area
+
+
+def group_of_photons(ph, groups, cfg):
+    left = groups['left'][:, None]
+    q = ph['t'] // cfg['sample_duration']
+    g = np.argmax((q[None, :] >= groups['left'][:, None]) & (q[None, :] <= groups['right'][:, None]), axis=0)
+    return g
+
+
+@pytest.mark.parametrize('extra', [{}, {'enable_noise': False, 'zle_threshold': 40}])
+def test_full_path_equals_oracle_back_end_on_gpu_photons(extra):
+    """Exactness of everything behind the sampling: take the photons the GPU generated (stage
+    dump, same seed) and push them through the CPU oracle's Pulse/digitise/ZLE/record code with the
+    same Pulse-call and group structure; the records must be bit-identical."""
+    from oracle import wfsim_oracle as orc
+    s, cfg = make_sim(**extra)
+    inst = c0_like(12, seed=3)
+    out = s.simulate(inst, seed=21)
+    ph = s.sample_stage(inst, stage=0, seed=21)
+    groups = out['groups']
+    live = ph['channel'] >= 0
+    ph = ph[live]
+    # Pulse call = instruction (save_full_truth) ; PMT afterpulses would be a second call
+    pcall = ph['instruction'] * 2 + ((ph['flags'] >> 1) & 1)
+    uniq, pc = np.unique(pcall, return_inverse=True)
+    g_of_ph = group_of_photons(ph, groups, cfg)
+    group_of = np.zeros(len(uniq), np.int32)
+    group_of[pc] = g_of_ph
+    want = orc.simulate_photons(cfg, pc.astype(np.int32), ph['channel'], ph['t'], ph['gain'], group_of)
+    assert out['raw_records'].tobytes() == want['raw_records'].tobytes()
+    for gi, lr in zip(groups, want['groups_lr']):
+        assert (gi['left'], gi['right']) == lr
+    s.close()
+
+
+def test_reproducible_and_independent_of_batching(sim):
+    inst = c0_like(16, seed=5)
+    a = sim.simulate(inst, seed=9)
+    b = sim.simulate(inst, seed=9)
+    assert a['raw_records'].tobytes() == b['raw_records'].tobytes()
+    assert a['truth'].tobytes() == b['truth'].tobytes()
+    c = sim.simulate(inst, seed=10)
+    assert c['raw_records'].tobytes() != a['raw_records'].tobytes()
+    os.environ['WFS_BATCH_INSTRUCTIONS'] = '6'        # force several device batches
+    try:
+        d = sim.simulate(inst, seed=9)
+        assert sim.last_counts['n_batches'] > 1
+    finally:
+        del os.environ['WFS_BATCH_INSTRUCTIONS']
+    assert d['raw_records'].tobytes() == a['raw_records'].tobytes()
+    assert d['truth'].tobytes() == a['truth'].tobytes()
+    # shuffled instruction order: same physics rows -> same records (Philox keyed by row index,
+    # so compare after undoing the permutation of identities is not possible; check counts only)
+    assert len(d['groups']) == len(a['groups'])

@@ -40,6 +40,13 @@ Handle::Handle(const wfs_params &p, const wfs_tables &t, int dev) : device(dev) 
     cfg.gains = upload(t.gains, (size_t)p.n_tpc_pmts, owned);
     cfg.zle_thr = upload(t.zle_thresholds, (size_t)p.n_rows, owned);
     h_gains.assign(t.gains, t.gains + p.n_tpc_pmts);
+    {
+        std::vector<double> cmax((size_t)p.dt, 0.0);
+        for (int r = 0; r < p.dt; r++)
+            for (int k = 0; k < p.template_length; k++)
+                cmax[r] = std::max(cmax[r], t.templates[(size_t)r * p.template_length + k]);
+        cfg.current_max = upload(cmax.data(), cmax.size(), owned);
+    }
     if (p.enable_noise && t.noise && t.noise_len > 0 && t.noise_nch > 0) {
         // transpose to [channel][sample]: a window reads consecutive samples of one channel
         std::vector<double> tr((size_t)t.noise_len * t.noise_nch);
@@ -105,6 +112,7 @@ void wfs_struct_sizes(int64_t *out) {
     out[2] = sizeof(wfs_instr_maps);
     out[3] = sizeof(wfs_counts);
     out[4] = sizeof(wfs_group_info);
+    out[5] = sizeof(wfs_outputs);
 }
 
 int wfs_device_count(void) {

@@ -72,6 +72,15 @@ __global__ void k_init(int64_t *group_tmin, int64_t *group_lr, uint32_t *group_n
     }
 }
 
+__device__ __forceinline__ int32_t pc_of(const PhotonBatch &b, int64_t i) {
+    int32_t v = b.pulse_call[i];
+    if (b.instr_run) {
+        int32_t run = b.instr_run[v];
+        return run < 0 ? -1 : 2 * run + ((b.flags[i] >> 1) & 1);
+    }
+    return v;
+}
+
 __device__ __forceinline__ bool photon_valid(int32_t ch, int32_t pc, const DeviceConfig &c,
                                              int64_t n_pc) {
     // dead PMTs are skipped by Pulse.__call__ (pulse.py:89-90); channel -1 = "no pattern" (s2.py:670)
@@ -84,7 +93,7 @@ __global__ void k_group_tmin(PhotonBatch b, DeviceConfig c, int64_t *group_tmin)
     int g = -1;
     int64_t t = LLONG_MAX;
     if (i < b.n) {
-        int32_t ch = b.channel[i], pc = b.pulse_call[i];
+        int32_t ch = b.channel[i], pc = pc_of(b, i);
         valid = photon_valid(ch, pc, c, b.n_pulse_calls);
         if (valid) {
             g = b.pc_group[pc];
@@ -106,7 +115,7 @@ __global__ void k_build_keys(PhotonBatch b, DeviceConfig c, KeyLayout kl, const 
                              uint64_t *keys, uint32_t *vals, int64_t *scalars) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= b.n) return;
-    int32_t ch = b.channel[i], pc = b.pulse_call[i];
+    int32_t ch = b.channel[i], pc = pc_of(b, i);
     uint64_t key;
     if (photon_valid(ch, pc, c, b.n_pulse_calls)) {
         int g = b.pc_group[pc];
@@ -234,6 +243,34 @@ __global__ void k_window_extents(int64_t n_win, DeviceConfig c, const int64_t *s
     }
     meta[n_win + w] = h;
     win_scan_in[n_win + w] = he ? (tiles | (icap << 32)) : 0ull;
+}
+
+// Truth quirk of Pulse.add_truth (pulse.py:251-255): `trigger_dpe` counts the above-threshold
+// photons among the FIRST n_double_pe photons of the channel slice, whichever they are.
+// One thread per pulse, photons in their sorted (time) order.
+__global__ void k_truth_pulses(int64_t n_pulses, PhotonBatch b, DeviceConfig c, const uint32_t *vals,
+                               const int64_t *st, const double *sg, const uint32_t *pulse_first,
+                               const uint32_t *pulse_win, const uint32_t *win_key) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pulses) return;
+    uint32_t a = pulse_first[p], e = pulse_first[p + 1];
+    int32_t pc = pc_of(b, vals[a]);
+    if (pc & 1) return;   // PMT-afterpulse calls carry preset gains: n_double_pe = 0 (pulse.py:106)
+    int ch = win_key[pulse_win[p]] & ((1u << kChannelBits) - 1u);
+    uint32_t ndpe = 0;
+    for (uint32_t i = a; i < e; i++) ndpe += b.flags[vals[i]] & 1u;
+    if (!ndpe) return;
+    const double thr = (double)(c.p.baseline - 1 - c.zle_thr[ch]) - 0.5;
+    int trig = 0;
+    for (uint32_t i = a; i < a + ndpe; i++) {
+        int64_t t = st[i];
+        int r = (int)(t - floordiv(t, c.p.dt) * c.p.dt);
+        if (sg[i] * c.current_max[r] * c.p.current_2_adc > thr) trig++;
+    }
+    if (trig) {
+        atomicAdd(&b.trig_dpe_out[2 * pc], trig);
+        if (ch >= c.p.n_top_pmts) atomicAdd(&b.trig_dpe_out[2 * pc + 1], trig);
+    }
 }
 
 // Noise start offset per group (rawdata.py:407-417) when not supplied by the caller.
@@ -742,6 +779,10 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
                win_scan_.as<uint64_t>(), group_lr_.as<int64_t>(), scal, he_rows ? 1 : 0);
         prim_.exclusive_scan_u64(win_scan_.as<uint64_t>(), win_scan_.as<uint64_t>(), nwt, true);
     }
+    if (np > 0 && b.trig_dpe_out && b.flags)
+        LAUNCH(k_truth_pulses, div_up(np, T), T, np, b, c, vals_.as<uint32_t>(), st_.as<int64_t>(),
+               sg_.as<double>(), pulse_first_.as<uint32_t>(), pulse_win_.as<uint32_t>(),
+               prim_.sort_vals_alt.as<uint32_t>());
     LAUNCH(k_group_noise, div_up(ng, T), T, ng, c, group_lr_.as<int64_t>(), b.ix_rand, b.seed,
            b.group_base, group_ix_buf.as<int64_t>(), scal);
     if (nw > 0) {

@@ -18,6 +18,7 @@ struct DeviceConfig {
     double *gains = nullptr;         // [n_tpc_pmts]
     int32_t *zle_thr = nullptr;      // [n_rows]
     double *noise_t = nullptr;       // transposed: [noise_nch][noise_len]
+    double *current_max = nullptr;   // [dt] max of each template row (pulse.py:32)
     int64_t noise_len = 0;
     int32_t noise_nch = 0;
 };
@@ -28,7 +29,12 @@ struct PhotonBatch {
     const int64_t *t = nullptr;
     const int32_t *channel = nullptr;
     const double *gain = nullptr;
-    const int32_t *pulse_call = nullptr;   // batch-local pulse-call id
+    const int32_t *pulse_call = nullptr;   // batch-local pulse-call id (or instruction index, see instr_run)
+    // generate mode: pulse_call[i] is the instruction index of photon i and the pulse-call id is
+    // 2 * instr_run[instruction] + is_afterpulse (flags bit 1); flags bit 0 = double-pe photon
+    const int32_t *instr_run = nullptr;
+    const uint8_t *flags = nullptr;
+    int32_t *trig_dpe_out = nullptr;       // [2 * n_pulse_calls] (total, bottom): pulse.py:255 quirk
     int64_t n_pulse_calls = 0;
     const int32_t *pc_group = nullptr;     // [n_pulse_calls] batch-local group id
     const int32_t *pc_rank = nullptr;      // [n_pulse_calls] rank of the pulse call inside its group

@@ -35,6 +35,21 @@ struct DevBuf {
         WFS_CUDA_CHECK(cudaMalloc(&p, want));
         cap = want;
     }
+    // grow, keeping the first `keep_bytes` of the old content
+    void reserve_keep(size_t bytes, size_t keep_bytes, cudaStream_t stream) {
+        if (bytes <= cap) return;
+        void *old = p;
+        size_t want = bytes + bytes / 2 + 256;
+        void *np_ = nullptr;
+        WFS_CUDA_CHECK(cudaMalloc(&np_, want));
+        if (old && keep_bytes) {
+            WFS_CUDA_CHECK(cudaMemcpyAsync(np_, old, keep_bytes, cudaMemcpyDeviceToDevice, stream));
+            WFS_CUDA_CHECK(cudaStreamSynchronize(stream));
+        }
+        if (old) WFS_CUDA_CHECK(cudaFree(old));
+        p = np_;
+        cap = want;
+    }
     void release() {
         if (p) cudaFree(p);
         p = nullptr;

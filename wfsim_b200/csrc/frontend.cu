@@ -1,32 +1,943 @@
-// Sampling front end (S1/S2/afterpulse photon generation) -- placeholder until the Philox
-// kernels land; the deterministic entry wfs_simulate_photons does not need it.
-#include "handle.cuh"
+// Front end: instruction parsing, batching, Philox sampling kernels, host-side emulation of the
+// reference's event scheduler (rawdata.py:38-157), truth rows (rawdata.py:313-375) and the
+// wfs_simulate / wfs_run_staged entry points.
+#include "frontend_kernels.cuh"
+
+#include <string.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <limits>
+#include <unordered_map>
 
 namespace wfs {
-struct Frontend {};
-void Handle::frontend_init(const wfs_tables &) { frontend = nullptr; }
-void Handle::frontend_release() {}
+
+// ---------------------------------------------------------------------------------------------
+// instruction rows (wfsim/strax_interface.py:25-42, packed, 70 bytes)
+// ---------------------------------------------------------------------------------------------
+template <typename T> static inline T rd(const uint8_t *p) { T v; memcpy(&v, p, sizeof(T)); return v; }
+template <typename T> static inline void wr(uint8_t *p, T v) { memcpy(p, &v, sizeof(T)); }
+
+static void parse_instructions(const uint8_t *rows, int64_t n, std::vector<HostInstr> &out) {
+    out.resize((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+        const uint8_t *r = rows + i * WFS_INSTRUCTION_BYTES;
+        HostInstr &h = out[i];
+        h.event_number = rd<int32_t>(r + 0);
+        h.type = rd<int8_t>(r + 4);
+        h.time = rd<int64_t>(r + 5);
+        h.x = rd<float>(r + 13); h.y = rd<float>(r + 17); h.z = rd<float>(r + 21);
+        h.amp = rd<int32_t>(r + 25);
+        h.recoil = rd<int8_t>(r + 29);
+        h.e_dep = rd<float>(r + 30); h.tot_e = rd<float>(r + 34);
+        h.g4id = rd<int32_t>(r + 38); h.vol_id = rd<int32_t>(r + 42);
+        h.local_field = rd<double>(r + 46);
+        h.n_excitons = rd<int32_t>(r + 54);
+        h.x_pri = rd<float>(r + 58); h.y_pri = rd<float>(r + 62); h.z_pri = rd<float>(r + 66);
+    }
+}
+
+// rawdata.py:61 -- evaluated by numpy in float32 (z is a float32 field, v a python scalar)
+static inline int64_t signal_time(int64_t time, float z, int type, double v) {
+    float q = z / (float)v;
+    int k = ((type % 2) + 2) % 2 - 1;   // python modulo: odd -> 0, even -> -1
+    q = q * (float)k;
+    return time + (int64_t)q;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host emulation of RawData.__call__ (rawdata.py:66-155): which instructions form a Pulse call
+// and which Pulse calls are digitised together.
+// ---------------------------------------------------------------------------------------------
+struct SchedIn {
+    int64_t n_prim = 0;
+    std::vector<int64_t> stime;     // signal time per batch-local instruction
+    std::vector<int8_t> type;
+    std::vector<int32_t> parent;    // primary that spawned the instruction, -1 for primaries
+    std::vector<int64_t> pend;      // end of the last pulse of the instruction [ns]; LLONG_MIN = no pulse
+    std::vector<std::pair<int32_t, int32_t>> clusters;   // [a, b) ranges over the primaries
+    int64_t rext = 100000;
+    bool save_full_truth = true;
+    double v = 1.0;
+};
+
+static void schedule(const SchedIn &in, std::vector<Run> &runs, int32_t &n_groups) {
+    const int64_t n_tot = (int64_t)in.stime.size();
+    std::vector<std::vector<int32_t>> children((size_t)in.n_prim);
+    for (int64_t i = in.n_prim; i < n_tot; i++) children[in.parent[i]].push_back((int32_t)i);
+    std::vector<int32_t> buffer;
+    bool have_end = false, cache = false;
+    int64_t last_end = 0;
+    int32_t group = 0;
+    size_t k = 0;
+    bool finished = false;
+    auto flush = [&]() { if (cache) { group++; cache = false; } };
+    auto by_time = [&](int32_t a, int32_t b) { return in.stime[a] < in.stime[b]; };
+    runs.clear();
+    while (!finished) {
+        if (k < in.clusters.size()) {                                          // A)
+            for (int32_t i = in.clusters[k].first; i < in.clusters[k].second; i++) buffer.push_back(i);
+            k++;
+        }
+        std::stable_sort(buffer.begin(), buffer.end(), by_time);               // B)
+        if (have_end && !buffer.empty() && in.stime[buffer[0]] - last_end > in.rext) flush();   // C)
+        std::vector<int32_t> remaining, spawned;
+        bool stop = false;
+        size_t a = 0;
+        while (a < buffer.size()) {                                            // D)
+            size_t b = a + 1;
+            while (b < buffer.size() && in.stime[buffer[b]] - in.stime[buffer[b - 1]] <= in.rext) b++;
+            if (stop) {
+                remaining.insert(remaining.end(), buffer.begin() + a, buffer.begin() + b);
+                a = b;
+                continue;
+            }
+            static const int kTypes[4] = {1, 2, 4, 6};
+            for (int ti = 0; ti < 4; ti++) {
+                const int ptype = kTypes[ti];
+                std::vector<int32_t> sel;
+                for (size_t j = a; j < b; j++) if (in.type[buffer[j]] == ptype) sel.push_back(buffer[j]);
+                if (sel.empty()) continue;
+                std::vector<std::vector<int32_t>> sets;
+                if (ptype == 1 || ptype == 2) {
+                    stop = true;
+                    if (in.save_full_truth) {
+                        for (int32_t s : sel) sets.push_back({s});
+                    } else {
+                        const int64_t gap = ptype == 1 ? 100 : (int64_t)(0.2 / in.v);
+                        sets.push_back({sel[0]});
+                        for (size_t j = 1; j < sel.size(); j++) {
+                            if (in.stime[sel[j]] - in.stime[sel[j - 1]] > gap) sets.push_back({});
+                            sets.back().push_back(sel[j]);
+                        }
+                    }
+                } else {
+                    sets.push_back(sel);
+                }
+                for (auto &set : sets) {
+                    Run r;
+                    r.type = ptype;
+                    r.group = group;
+                    r.instr = set;
+                    for (int32_t s : set) {
+                        if (in.pend[s] != LLONG_MIN) {
+                            cache = true;
+                            last_end = have_end ? std::max(last_end, in.pend[s]) : in.pend[s];
+                            have_end = true;
+                        }
+                        if (ptype == 2 && s < in.n_prim)
+                            spawned.insert(spawned.end(), children[s].begin(), children[s].end());
+                    }
+                    runs.push_back(std::move(r));
+                }
+            }
+            if (!stop) flush();
+            a = b;
+        }
+        buffer = remaining;
+        buffer.insert(buffer.end(), spawned.begin(), spawned.end());
+        finished = (k == in.clusters.size()) && buffer.empty();
+    }
+    flush();
+    n_groups = 0;
+    for (auto &r : runs) n_groups = std::max(n_groups, r.group + 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct BatchSpec {
+    int64_t first_cluster, last_cluster;   // [first, last)
+};
+
+struct Plan {
+    std::vector<HostInstr> instr;            // as given
+    std::vector<int64_t> stime;              // signal time per instruction
+    std::vector<int64_t> order;              // instruction indices ordered by signal time
+    std::vector<int64_t> cluster_start;      // offsets into `order` (+ sentinel)
+    std::vector<BatchSpec> batches;
+    // map values
+    std::vector<double> lce, scg, cy;
+    std::vector<float> pattern;
+    std::vector<int32_t> patrow;
+    int64_t pattern_rows = 0;
+    double scg_default = 0.0;
+};
+
+static int64_t env_i64(const char *name, int64_t dflt) {
+    const char *s = getenv(name);
+    return s ? atoll(s) : dflt;
+}
+
+static void make_plan(Handle *H, const uint8_t *rows, int64_t n, const wfs_instr_maps *maps, Plan &P) {
+    const wfs_params &p = H->cfg.p;
+    parse_instructions(rows, n, P.instr);
+    P.stime.resize((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+        const HostInstr &h = P.instr[i];
+        if (!(h.type == 1 || h.type == 2 || h.type == 4 || h.type == 6))
+            throw std::runtime_error("unsupported instruction type (expected 1, 2, 4 or 6)");
+        P.stime[i] = signal_time(h.time, h.z, h.type, p.drift_velocity_liquid);
+    }
+    P.order.resize((size_t)n);
+    for (int64_t i = 0; i < n; i++) P.order[i] = i;
+    std::stable_sort(P.order.begin(), P.order.end(), [&](int64_t a, int64_t b) { return P.stime[a] < P.stime[b]; });
+    P.cluster_start.clear();
+    for (int64_t j = 0; j < n; j++)
+        if (j == 0 || P.stime[P.order[j]] - P.stime[P.order[j - 1]] > p.right_raw_extension)
+            P.cluster_start.push_back(j);
+    P.cluster_start.push_back(n);
+    // maps
+    const int n_ch = p.n_tpc_pmts;
+    P.scg_default = maps ? maps->s2_sc_gain_default : 0.0;
+    if (P.scg_default == 0.0) P.scg_default = p.s2_secondary_sc_gain / (1.0 + p.p_double_pe_emision);
+    P.lce.assign((size_t)n, 1.0);
+    P.scg.assign((size_t)n, P.scg_default);
+    P.cy.assign((size_t)n, 1.0);
+    P.patrow.assign((size_t)n, 0);
+    if (maps && maps->s1_lce) std::copy(maps->s1_lce, maps->s1_lce + n, P.lce.begin());
+    if (maps && maps->s2_sc_gain) std::copy(maps->s2_sc_gain, maps->s2_sc_gain + n, P.scg.begin());
+    if (maps && maps->s2_cy_extra) std::copy(maps->s2_cy_extra, maps->s2_cy_extra + n, P.cy.begin());
+    if (maps && maps->pattern && maps->n_pattern_rows > 0) {
+        P.pattern_rows = maps->n_pattern_rows;
+        P.pattern.assign(maps->pattern, maps->pattern + maps->n_pattern_rows * n_ch);
+        if (maps->pattern_row) std::copy(maps->pattern_row, maps->pattern_row + n, P.patrow.begin());
+        for (int64_t i = 0; i < n; i++)
+            if (P.patrow[i] < 0 || P.patrow[i] >= P.pattern_rows) throw std::runtime_error("pattern_row out of range");
+    } else {
+        P.pattern_rows = 1;
+        P.pattern.assign((size_t)n_ch, 1.0f);
+    }
+    // batches: contiguous cluster ranges under a photon / sample budget
+    const int64_t ph_budget = env_i64("WFS_BATCH_PHOTONS", 48000000);
+    const int64_t sample_budget = env_i64("WFS_BATCH_SAMPLES", 1500000000);
+    const int64_t instr_budget = env_i64("WFS_BATCH_INSTRUCTIONS", 400000);
+    const bool secondaries = p.enable_electron_afterpulses && H->frontend && H->frontend->pi_coarse_len > 0;
+    const double quiet = (double)p.right_raw_extension +
+                         (secondaries ? H->frontend->h_pi_coarse_time.back() + 50000.0 : 0.0);
+    const int64_t n_cl = (int64_t)P.cluster_start.size() - 1;
+    P.batches.clear();
+    int64_t c0 = 0;
+    double ph = 0, smp = 0;
+    int64_t ni = 0;
+    for (int64_t c = 0; c < n_cl; c++) {
+        for (int64_t j = P.cluster_start[c]; j < P.cluster_start[c + 1]; j++) {
+            const HostInstr &h = P.instr[P.order[j]];
+            double e = h.type == 1 ? h.amp * P.lce[P.order[j]] * p.s1_detection_efficiency
+                                   : (double)h.amp * P.scg[P.order[j]] * 1.1;
+            if (p.enable_pmt_afterpulses) e *= 1.1;
+            ph += e;
+            smp += std::min(e, (double)n_ch) * 450.0 * (p.detector_nt ? 1.5 : 1.0);
+            ni++;
+        }
+        bool over = ph > ph_budget || smp > sample_budget || ni > instr_budget;
+        bool over2 = ph > 2 * ph_budget || smp > 2 * sample_budget || ni > 2 * instr_budget;
+        if (over && c + 1 < n_cl) {
+            double gap = (double)(P.stime[P.order[P.cluster_start[c + 1]]] - P.stime[P.order[P.cluster_start[c + 1] - 1]]);
+            if (gap > quiet || over2) {
+                P.batches.push_back({c0, c + 1});
+                c0 = c + 1;
+                ph = smp = 0;
+                ni = 0;
+            }
+        }
+    }
+    if (c0 < n_cl) P.batches.push_back({c0, n_cl});
+}
+
+// ---------------------------------------------------------------------------------------------
+struct PhotonDump {     // wfs_sample_stage
+    int stage = 0;
+    uint8_t *out = nullptr;
+    int64_t cap = 0, n = 0;
+};
+
+struct SimOut {
+    PhotonDump *dump = nullptr;
+    wfs_outputs *out = nullptr;
+    wfs_counts *counts = nullptr;
+    bool resident = false;
+    int64_t n_rec = 0, n_truth = 0, n_groups = 0, n_batches = 0;
+    bool overflow = false;
+};
+
+static GenCtx make_ctx(Frontend &F, uint64_t seed) {
+    GenCtx g;
+    memset(&g, 0, sizeof(g));
+    g.i_type = F.b_itype.as<int32_t>(); g.i_time = F.b_itime.as<int64_t>();
+    g.i_x = F.b_ix.as<float>(); g.i_y = F.b_iy.as<float>(); g.i_z = F.b_iz.as<float>();
+    g.i_amp = F.b_iamp.as<int32_t>(); g.i_gidx = F.b_igidx.as<uint64_t>();
+    g.i_lce = F.b_ilce.as<double>(); g.i_scg = F.b_iscg.as<double>(); g.i_cy = F.b_icy.as<double>();
+    g.i_pat = F.b_ipat.as<int32_t>();
+    g.i_dmean = F.b_dmean.as<double>(); g.i_dspread = F.b_dspread.as<double>();
+    g.i_nemit = F.b_nemit.as<uint32_t>(); g.i_emitoff = F.b_emitoff.as<uint32_t>();
+    g.i_nhits = F.b_nhits.as<int64_t>(); g.i_acc = F.b_acc.as<int64_t>();
+    g.cdf = F.b_cdf.as<double>(); g.cdf_ok = F.b_cdfok.as<int32_t>();
+    g.e_t = F.b_et.as<int64_t>(); g.e_instr = F.b_einstr.as<int32_t>();
+    g.e_nph = F.b_enph.as<uint32_t>(); g.e_phoff = F.b_ephoff.as<uint32_t>();
+    g.ph_t = F.b_pht.as<int64_t>(); g.ph_ch = F.b_phch.as<int32_t>(); g.ph_gain = F.b_phgain.as<double>();
+    g.ph_instr = F.b_phinstr.as<int32_t>(); g.ph_flags = F.b_phflags.as<uint8_t>();
+    g.ph_nap = F.b_phnap.as<uint8_t>(); g.ap_off = F.b_apoff.as<uint32_t>();
+    g.spe_ppf = F.spe_ppf; g.spe_row = F.spe_row; g.spe_len = F.spe_len;
+    g.lum_cdf = F.lum_cdf; g.lum_t = F.lum_t; g.lum_len = F.lum_len;
+    g.n_ap = F.H->cfg.p.enable_pmt_afterpulses ? F.n_ap : 0;
+    for (int e = 0; e < WFS_MAX_AP_ELEMENTS; e++) {
+        g.ap_is_uniform[e] = F.ap_is_uniform[e];
+        g.ap_delay_cdf[e] = F.ap_delay_cdf[e]; g.ap_delay_len[e] = F.ap_delay_len[e];
+        g.ap_delay_bin[e] = F.ap_delay_bin[e];
+        g.ap_amp_cdf[e] = F.ap_amp_cdf[e]; g.ap_amp_len[e] = F.ap_amp_len[e];
+        g.ap_amp_rows[e] = F.ap_amp_rows[e]; g.ap_amp_bin[e] = F.ap_amp_bin[e];
+    }
+    g.pi_time = F.pi_coarse_time; g.pi_prob = F.pi_coarse_prob; g.pi_len = F.pi_coarse_len;
+    g.seed = seed;
+    return g;
+}
+
+#define FLAUNCH(kernel, grid, block, ...)                          \
+    do {                                                           \
+        kernel<<<(grid), (block), 0, s>>>(__VA_ARGS__);            \
+        H->launches.n++;                                           \
+    } while (0)
+
+static void grow_instr(Frontend &F, int64_t n_new, int64_t n_old, cudaStream_t s) {
+    auto g = [&](DevBuf &b, size_t el) { b.reserve_keep(el * (size_t)n_new, el * (size_t)n_old, s); };
+    g(F.b_itype, 4); g(F.b_itime, 8); g(F.b_ix, 4); g(F.b_iy, 4); g(F.b_iz, 4); g(F.b_iamp, 4);
+    g(F.b_igidx, 8); g(F.b_ilce, 8); g(F.b_iscg, 8); g(F.b_icy, 8); g(F.b_ipat, 4);
+    g(F.b_dmean, 8); g(F.b_dspread, 8); g(F.b_nemit, 4); g(F.b_nhits, 8);
+    F.b_emitoff.reserve_keep(4 * (size_t)(n_new + 1), 4 * (size_t)(n_old + 1), s);
+    F.b_irun.reserve_keep(4 * (size_t)n_new, 0, s);
+}
+
+static void grow_photons(Frontend &F, int64_t n_new, int64_t n_old, cudaStream_t s) {
+    auto g = [&](DevBuf &b, size_t el) { b.reserve_keep(el * (size_t)n_new, el * (size_t)n_old, s); };
+    g(F.b_pht, 8); g(F.b_phch, 4); g(F.b_phgain, 8); g(F.b_phinstr, 4); g(F.b_phflags, 1); g(F.b_phnap, 1);
+}
+
+// Generate emitters and photons of instructions [i0, i1); arrays are appended.
+static void generate(Handle *H, Frontend &F, uint64_t seed, int64_t i0, int64_t i1, int64_t &n_emit,
+                     int64_t &n_ph) {
+    cudaStream_t s = H->stream;
+    const wfs_params &p = H->cfg.p;
+    if (i1 <= i0) return;
+    GenCtx g = make_ctx(F, seed);
+    FLAUNCH(k_instr, div_up(i1 - i0, 128), 128, g, p, (uint32_t)i0, (uint32_t)i1);
+    F.prim.exclusive_scan_u32(g.i_nemit, g.i_emitoff, i1, true);
+    uint32_t tot;
+    WFS_CUDA_CHECK(cudaMemcpyAsync(&tot, g.i_emitoff + i1, 4, cudaMemcpyDeviceToHost, s));
+    WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+    const int64_t e0 = n_emit, e1 = tot;
+    if (e1 >= (int64_t(1) << 31)) throw std::runtime_error("emitter batch too large");
+    F.b_et.reserve_keep(8 * (size_t)std::max<int64_t>(e1, 1), 8 * (size_t)e0, s);
+    F.b_einstr.reserve_keep(4 * (size_t)std::max<int64_t>(e1, 1), 4 * (size_t)e0, s);
+    F.b_enph.reserve_keep(4 * (size_t)std::max<int64_t>(e1, 1), 4 * (size_t)e0, s);
+    F.b_ephoff.reserve_keep(4 * (size_t)(e1 + 1), 0, s);
+    g = make_ctx(F, seed);
+    if (e1 > e0) FLAUNCH(k_emitters, div_up(e1 - e0, 128), 128, g, p, (uint32_t)i1, (uint32_t)e0, (uint32_t)e1);
+    F.prim.exclusive_scan_u32(g.e_nph, g.e_phoff, e1, true);
+    WFS_CUDA_CHECK(cudaMemcpyAsync(&tot, g.e_phoff + e1, 4, cudaMemcpyDeviceToHost, s));
+    WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+    const int64_t p0 = n_ph, p1 = tot;
+    if (p1 >= (int64_t(1) << 30)) throw std::runtime_error("photon batch too large; lower WFS_BATCH_PHOTONS");
+    grow_photons(F, std::max<int64_t>(p1, 1), p0, s);
+    g = make_ctx(F, seed);
+    if (p1 > p0)
+        FLAUNCH(k_photons, div_up(p1 - p0, 256), 256, g, p, H->cfg.gains, p.n_tpc_pmts, (uint32_t)e1,
+                (uint32_t)p0, (uint32_t)p1);
+    n_emit = e1;
+    n_ph = p1;
+    WFS_CUDA_CHECK(cudaGetLastError());
+}
+
+static void write_truth_row(uint8_t *row, const HostInstr &h0, int run_type, int64_t time, float x, float y,
+                            float z, int32_t amp, const int64_t *acc_sum /*A_COUNT summed*/,
+                            long double ph_mean, long double ph_sigma, long double e_mean,
+                            long double e_sigma, int32_t trig_dpe, int32_t trig_dpe_b, const wfs_params &p) {
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    memset(row, 0, WFS_TRUTH_BYTES);
+    wr<int32_t>(row + 0, h0.event_number);
+    wr<int8_t>(row + 4, (int8_t)run_type);
+    wr<int64_t>(row + 5, time);
+    wr<float>(row + 13, x); wr<float>(row + 17, y); wr<float>(row + 21, z);
+    wr<int32_t>(row + 25, amp);
+    wr<int8_t>(row + 29, h0.recoil);
+    wr<float>(row + 30, h0.e_dep); wr<float>(row + 34, h0.tot_e);
+    wr<int32_t>(row + 38, h0.g4id); wr<int32_t>(row + 42, h0.vol_id);
+    wr<double>(row + 46, h0.local_field);
+    wr<int32_t>(row + 54, h0.n_excitons);
+    wr<float>(row + 58, h0.x_pri); wr<float>(row + 62, h0.y_pri); wr<float>(row + 66, h0.z_pri);
+    const bool has_ph = acc_sum[A_NPHALL] > 0, has_e = acc_sum[A_NE] > 0;
+    const double t_last = has_ph ? (double)acc_sum[A_TMAX] : nan;
+    int64_t endtime = time;
+    if (has_ph) endtime = (int64_t)(t_last + (double)((p.template_length + 1) * p.dt));   // rawdata.py:347-352
+    wr<int64_t>(row + 70, endtime);
+    wr<int32_t>(row + 78, (int32_t)acc_sum[A_NE]);
+    wr<int32_t>(row + 82, (int32_t)acc_sum[A_NPH]);
+    wr<int32_t>(row + 86, (int32_t)(acc_sum[A_NPH] + acc_sum[A_NDPE]));
+    wr<int32_t>(row + 90, (int32_t)acc_sum[A_NTRIG]);
+    wr<int32_t>(row + 94, (int32_t)(acc_sum[A_NTRIG] + trig_dpe));
+    wr<double>(row + 98, (double)acc_sum[A_AREA] / kAreaScale);
+    wr<double>(row + 106, (double)acc_sum[A_AREA_TRIG] / kAreaScale);
+    wr<int32_t>(row + 114, (int32_t)acc_sum[A_NPH_B]);
+    wr<int32_t>(row + 118, (int32_t)(acc_sum[A_NPH_B] + acc_sum[A_NDPE_B]));
+    wr<int32_t>(row + 122, (int32_t)acc_sum[A_NTRIG_B]);
+    wr<int32_t>(row + 126, (int32_t)(acc_sum[A_NTRIG_B] + trig_dpe_b));
+    wr<double>(row + 130, (double)acc_sum[A_AREA_B] / kAreaScale);
+    wr<double>(row + 138, (double)acc_sum[A_AREA_TRIG_B] / kAreaScale);
+    wr<double>(row + 146, has_ph ? (double)acc_sum[A_TMIN] : nan);
+    wr<double>(row + 154, t_last);
+    wr<double>(row + 162, has_ph ? (double)ph_mean : nan);
+    wr<double>(row + 170, has_ph ? (double)ph_sigma : nan);
+    wr<float>(row + 178, std::numeric_limits<float>::quiet_NaN());
+    wr<float>(row + 182, std::numeric_limits<float>::quiet_NaN());
+    wr<double>(row + 186, has_e ? (double)acc_sum[A_ETMIN] : nan);
+    wr<double>(row + 194, has_e ? (double)acc_sum[A_ETMAX] : nan);
+    wr<double>(row + 202, has_e ? (double)e_mean : nan);
+    wr<double>(row + 210, has_e ? (double)e_sigma : nan);
+}
+
+// exact first/second moments of times over the instructions of a run -> mean and population std
+static void combine_moments(const std::vector<int32_t> &set, const std::vector<int64_t> &T,
+                            const int64_t *acc, int a_n, int a_s, int a_hi2, int a_hilo, int a_lo2,
+                            long double &mean, long double &sigma) {
+    __int128 S1 = 0, S2 = 0;
+    int64_t n = 0;
+    const int64_t T0 = T[set[0]];
+    for (int32_t i : set) {
+        const int64_t *a = acc + (int64_t)i * A_COUNT;
+        const int64_t ni = a[a_n];
+        if (!ni) continue;
+        __int128 s1 = a[a_s];
+        __int128 s2 = ((__int128)a[a_hi2] << 24) + ((__int128)a[a_hilo] << 13) + (__int128)a[a_lo2];
+        const __int128 d = T[i] - T0;
+        S1 += s1 + d * ni;
+        S2 += s2 + 2 * d * s1 + d * d * ni;
+        n += ni;
+    }
+    if (!n) { mean = sigma = 0; return; }
+    const long double m = (long double)S1 / (long double)n;
+    long double var = (long double)S2 / (long double)n - m * m;
+    if (var < 0) var = 0;
+    mean = (long double)T0 + m;
+    sigma = sqrtl(var);
+}
+
+static void simulate_batch(Handle *H, Plan &P, const BatchSpec &bs, uint64_t seed, SimOut &so,
+                           int64_t &group_base) {
+    Frontend &F = *H->frontend;
+    cudaStream_t s = H->stream;
+    const wfs_params &p = H->cfg.p;
+    const int n_ch = p.n_tpc_pmts;
+    const int64_t j0 = P.cluster_start[bs.first_cluster], j1 = P.cluster_start[bs.last_cluster];
+    const int64_t nprim = j1 - j0;
+    // ---- host SoA of the primaries (signal-time order) ----
+    std::vector<int32_t> h_type(nprim), h_amp(nprim), h_pat(nprim);
+    std::vector<int64_t> h_time(nprim);
+    std::vector<float> h_x(nprim), h_y(nprim), h_z(nprim);
+    std::vector<uint64_t> h_gidx(nprim);
+    std::vector<double> h_lce(nprim), h_scg(nprim), h_cy(nprim);
+    std::unordered_map<int32_t, int32_t> rowmap;
+    std::vector<int32_t> rows_used;
+    for (int64_t j = 0; j < nprim; j++) {
+        const int64_t gi = P.order[j0 + j];
+        const HostInstr &h = P.instr[gi];
+        h_type[j] = h.type; h_amp[j] = h.amp; h_time[j] = h.time;
+        h_x[j] = h.x; h_y[j] = h.y; h_z[j] = h.z;
+        h_gidx[j] = (uint64_t)gi;
+        h_lce[j] = P.lce[gi]; h_scg[j] = P.scg[gi]; h_cy[j] = P.cy[gi];
+        auto it = rowmap.find(P.patrow[gi]);
+        if (it == rowmap.end()) {
+            it = rowmap.emplace(P.patrow[gi], (int32_t)rows_used.size()).first;
+            rows_used.push_back(P.patrow[gi]);
+        }
+        h_pat[j] = it->second;
+    }
+    grow_instr(F, std::max<int64_t>(nprim, 1), 0, s);
+    auto up = [&](DevBuf &b, const void *src, size_t bytes) {
+        WFS_CUDA_CHECK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, s));
+    };
+    up(F.b_itype, h_type.data(), 4 * nprim); up(F.b_itime, h_time.data(), 8 * nprim);
+    up(F.b_ix, h_x.data(), 4 * nprim); up(F.b_iy, h_y.data(), 4 * nprim); up(F.b_iz, h_z.data(), 4 * nprim);
+    up(F.b_iamp, h_amp.data(), 4 * nprim); up(F.b_igidx, h_gidx.data(), 8 * nprim);
+    up(F.b_ilce, h_lce.data(), 8 * nprim); up(F.b_iscg, h_scg.data(), 8 * nprim);
+    up(F.b_icy, h_cy.data(), 8 * nprim); up(F.b_ipat, h_pat.data(), 4 * nprim);
+    // pattern rows of this batch -> CDF rows
+    const int64_t nrows = (int64_t)rows_used.size();
+    std::vector<float> h_rows((size_t)nrows * n_ch);
+    for (int64_t r = 0; r < nrows; r++)
+        memcpy(&h_rows[(size_t)r * n_ch], &P.pattern[(size_t)rows_used[r] * n_ch], sizeof(float) * n_ch);
+    F.b_pattern.reserve(sizeof(float) * h_rows.size());
+    F.b_cdf.reserve(sizeof(double) * h_rows.size());
+    F.b_cdfok.reserve(sizeof(int32_t) * nrows);
+    up(F.b_pattern, h_rows.data(), sizeof(float) * h_rows.size());
+    FLAUNCH(k_pattern_cdf, div_up(nrows, 64), 64, nrows, n_ch, F.b_pattern.as<float>(), H->cfg.gains,
+            F.b_cdf.as<double>(), F.b_cdfok.as<int32_t>());
+    // ---- pass A: primaries ----
+    int64_t n_emit = 0, n_ph = 0;
+    generate(H, F, seed, 0, nprim, n_emit, n_ph);
+    // ---- secondaries: photo-ionisation electrons of the S2 calls (rawdata.py:193-197) ----
+    int64_t ntot = nprim;
+    std::vector<int32_t> h_parent;
+    std::vector<int64_t> sec_time;
+    std::vector<float> sec_x, sec_y, sec_z;
+    std::vector<int32_t> sec_amp;
+    if (p.enable_gate_afterpulses) throw std::runtime_error("enable_gate_afterpulses is not supported yet");
+    if (p.enable_electron_afterpulses && F.pi_coarse_len > 0 && n_ph > 0) {
+        F.b_picount.reserve(4 * (size_t)(nprim + 1));
+        F.b_pioff.reserve(4 * (size_t)(nprim + 1));
+        GenCtx g = make_ctx(F, seed);
+        FLAUNCH(k_photoionization, div_up(nprim * 32, 128), 128, g, p, (uint32_t)nprim, 0,
+                F.b_picount.as<uint32_t>(), nullptr, 0u, nullptr);
+        F.prim.exclusive_scan_u32(F.b_picount.as<uint32_t>(), F.b_pioff.as<uint32_t>(), nprim, true);
+        uint32_t nsec;
+        WFS_CUDA_CHECK(cudaMemcpyAsync(&nsec, F.b_pioff.as<uint32_t>() + nprim, 4, cudaMemcpyDeviceToHost, s));
+        WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (nsec > 0) {
+            ntot = nprim + nsec;
+            grow_instr(F, ntot, nprim, s);
+            DevBuf d_parent;
+            d_parent.reserve(4 * (size_t)ntot);
+            g = make_ctx(F, seed);
+            FLAUNCH(k_photoionization, div_up(nprim * 32, 128), 128, g, p, (uint32_t)nprim, 1, nullptr,
+                    F.b_pioff.as<uint32_t>(), (uint32_t)nprim, d_parent.as<int32_t>());
+            h_parent.resize(nsec); sec_time.resize(nsec); sec_x.resize(nsec); sec_y.resize(nsec);
+            sec_z.resize(nsec); sec_amp.resize(nsec);
+            auto down = [&](void *dst, const void *src, size_t bytes) {
+                WFS_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+            };
+            down(h_parent.data(), d_parent.as<int32_t>() + nprim, 4 * (size_t)nsec);
+            down(sec_time.data(), F.b_itime.as<int64_t>() + nprim, 8 * (size_t)nsec);
+            down(sec_x.data(), F.b_ix.as<float>() + nprim, 4 * (size_t)nsec);
+            down(sec_y.data(), F.b_iy.as<float>() + nprim, 4 * (size_t)nsec);
+            down(sec_z.data(), F.b_iz.as<float>() + nprim, 4 * (size_t)nsec);
+            down(sec_amp.data(), F.b_iamp.as<int32_t>() + nprim, 4 * (size_t)nsec);
+            WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+            d_parent.release();
+            generate(H, F, seed, nprim, ntot, n_emit, n_ph);   // pass B
+        }
+    }
+    // ---- PMT afterpulses of every photon (rawdata.py:176-178) ----
+    int64_t n_ap = 0;
+    F.b_apoff.reserve(4 * (size_t)(n_ph + 1));
+    GenCtx g = make_ctx(F, seed);
+    if (g.n_ap > 0 && n_ph > 0) {
+        // ap_off = exclusive scan of ph_nap (widened to u32)
+        FLAUNCH(k_widen_u8, div_up(n_ph, 256), 256, g.ph_nap, g.ap_off, (uint32_t)n_ph);
+        F.prim.exclusive_scan_u32(g.ap_off, g.ap_off, n_ph, true);
+        uint32_t tot;
+        WFS_CUDA_CHECK(cudaMemcpyAsync(&tot, g.ap_off + n_ph, 4, cudaMemcpyDeviceToHost, s));
+        WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+        n_ap = tot;
+        if (n_ap > 0) {
+            grow_photons(F, n_ph + n_ap, n_ph, s);
+            g = make_ctx(F, seed);
+            FLAUNCH(k_ap_fill, div_up(n_ph, 256), 256, g, p, H->cfg.gains, (uint32_t)n_emit, (uint32_t)n_ph,
+                    (uint32_t)n_ph);
+        }
+    } else {
+        WFS_CUDA_CHECK(cudaMemsetAsync(F.b_apoff.p, 0, 4 * (size_t)(n_ph + 1), s));
+    }
+    if (so.dump) {   // stage-level dump for the statistical parity tests
+        PhotonDump &d = *so.dump;
+        const int64_t base = d.n;
+        if (d.stage == 0) {
+            const int64_t m = n_ph + n_ap;
+            std::vector<int64_t> t(m); std::vector<double> gn(m); std::vector<int32_t> ch(m), in_(m);
+            std::vector<uint8_t> fl(m);
+            WFS_CUDA_CHECK(cudaMemcpyAsync(t.data(), F.b_pht.p, 8 * m, cudaMemcpyDeviceToHost, s));
+            WFS_CUDA_CHECK(cudaMemcpyAsync(gn.data(), F.b_phgain.p, 8 * m, cudaMemcpyDeviceToHost, s));
+            WFS_CUDA_CHECK(cudaMemcpyAsync(ch.data(), F.b_phch.p, 4 * m, cudaMemcpyDeviceToHost, s));
+            WFS_CUDA_CHECK(cudaMemcpyAsync(in_.data(), F.b_phinstr.p, 4 * m, cudaMemcpyDeviceToHost, s));
+            WFS_CUDA_CHECK(cudaMemcpyAsync(fl.data(), F.b_phflags.p, m, cudaMemcpyDeviceToHost, s));
+            WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+            for (int64_t q = 0; q < m; q++) {
+                if (base + q < d.cap) {
+                    uint8_t *r = d.out + (base + q) * 32;
+                    const int32_t li = in_[q];
+                    const bool sec = li >= nprim;
+                    const int32_t root = sec ? h_parent[li - nprim] : li;
+                    wr<int64_t>(r, t[q]); wr<double>(r + 8, gn[q]); wr<int32_t>(r + 16, ch[q]);
+                    wr<int32_t>(r + 20, (int32_t)P.order[j0 + root]);
+                    wr<int32_t>(r + 24, (int32_t)fl[q] | (sec ? 4 : 0));
+                    wr<int32_t>(r + 28, sec ? li - (int32_t)nprim : -1);
+                }
+            }
+            d.n += m;
+        } else {
+            std::vector<int64_t> t(n_emit); std::vector<int32_t> in_(n_emit); std::vector<uint32_t> np_(n_emit);
+            WFS_CUDA_CHECK(cudaMemcpyAsync(t.data(), F.b_et.p, 8 * n_emit, cudaMemcpyDeviceToHost, s));
+            WFS_CUDA_CHECK(cudaMemcpyAsync(in_.data(), F.b_einstr.p, 4 * n_emit, cudaMemcpyDeviceToHost, s));
+            WFS_CUDA_CHECK(cudaMemcpyAsync(np_.data(), F.b_enph.p, 4 * n_emit, cudaMemcpyDeviceToHost, s));
+            WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+            for (int64_t q = 0; q < n_emit; q++) {
+                if (base + q < d.cap) {
+                    uint8_t *r = d.out + (base + q) * 32;
+                    const int32_t li = in_[q];
+                    const bool sec = li >= nprim;
+                    const int32_t root = sec ? h_parent[li - nprim] : li;
+                    wr<int64_t>(r, t[q]); wr<double>(r + 8, 0.0); wr<int32_t>(r + 16, (int32_t)np_[q]);
+                    wr<int32_t>(r + 20, (int32_t)P.order[j0 + root]);
+                    wr<int32_t>(r + 24, sec ? 4 : 0);
+                    wr<int32_t>(r + 28, sec ? li - (int32_t)nprim : -1);
+                }
+            }
+            d.n += n_emit;
+        }
+        return;
+    }
+    // ---- per-instruction truth accumulators ----
+    F.b_acc.reserve(8 * (size_t)ntot * A_COUNT);
+    g = make_ctx(F, seed);
+    FLAUNCH(k_instr_truth, (unsigned)ntot, 128, g, H->cfg, (uint32_t)ntot, (uint32_t)n_ph, (uint32_t)n_ph);
+    std::vector<int64_t> acc((size_t)ntot * A_COUNT);
+    WFS_CUDA_CHECK(cudaMemcpyAsync(acc.data(), F.b_acc.p, 8 * acc.size(), cudaMemcpyDeviceToHost, s));
+    WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+    // ---- host scheduler ----
+    SchedIn in;
+    in.n_prim = nprim;
+    in.rext = p.right_raw_extension;
+    in.save_full_truth = p.save_full_truth != 0;
+    in.v = p.drift_velocity_liquid;
+    in.stime.resize(ntot); in.type.resize(ntot); in.parent.assign(ntot, -1); in.pend.resize(ntot);
+    std::vector<int64_t> T(ntot);
+    for (int64_t j = 0; j < nprim; j++) {
+        in.stime[j] = P.stime[P.order[j0 + j]];
+        in.type[j] = (int8_t)h_type[j];
+        T[j] = h_time[j];
+    }
+    for (int64_t j = nprim; j < ntot; j++) {
+        in.type[j] = 4;
+        in.parent[j] = h_parent[j - nprim];
+        T[j] = sec_time[j - nprim];
+        in.stime[j] = signal_time(T[j], sec_z[j - nprim], 4, p.drift_velocity_liquid);
+    }
+    for (int64_t j = 0; j < ntot; j++) {
+        const int64_t tmax = acc[(size_t)j * A_COUNT + A_PTMAX];
+        if (tmax == LLONG_MIN) in.pend[j] = LLONG_MIN;
+        else {
+            int64_t q = tmax / p.dt; if (tmax % p.dt != 0 && tmax < 0) q--;
+            in.pend[j] = (q + p.pulse_right_margin) * p.dt;
+        }
+    }
+    for (int64_t c = bs.first_cluster; c < bs.last_cluster; c++)
+        in.clusters.push_back({(int32_t)(P.cluster_start[c] - j0), (int32_t)(P.cluster_start[c + 1] - j0)});
+    std::vector<Run> runs;
+    int32_t ngroups = 0;
+    schedule(in, runs, ngroups);
+    const int64_t nruns = (int64_t)runs.size();
+    const int64_t npc = 2 * nruns;
+    std::vector<int32_t> instr_run((size_t)ntot, -1), pc_group((size_t)std::max<int64_t>(npc, 1)),
+        pc_rank;
+    for (int64_t r = 0; r < nruns; r++) {
+        for (int32_t i : runs[r].instr) instr_run[i] = (int32_t)r;
+        pc_group[2 * r] = pc_group[2 * r + 1] = runs[r].group;
+    }
+    int32_t max_rank = 0;
+    pulse_call_ranks(pc_group.data(), npc, ngroups, pc_rank, max_rank);
+    F.b_irun.reserve(4 * (size_t)ntot);
+    F.b_pcgroup.reserve(4 * (size_t)std::max<int64_t>(npc, 1));
+    F.b_pcrank.reserve(4 * (size_t)std::max<int64_t>(npc, 1));
+    F.b_trig.reserve(4 * (size_t)std::max<int64_t>(2 * npc, 1));
+    up(F.b_irun, instr_run.data(), 4 * (size_t)ntot);
+    if (npc) {
+        up(F.b_pcgroup, pc_group.data(), 4 * (size_t)npc);
+        up(F.b_pcrank, pc_rank.data(), 4 * (size_t)npc);
+        WFS_CUDA_CHECK(cudaMemsetAsync(F.b_trig.p, 0, 4 * (size_t)(2 * npc), s));
+    }
+    // ---- back end ----
+    PhotonBatch b;
+    b.n = n_ph + n_ap;
+    b.t = F.b_pht.as<int64_t>(); b.channel = F.b_phch.as<int32_t>(); b.gain = F.b_phgain.as<double>();
+    b.pulse_call = F.b_phinstr.as<int32_t>();
+    b.instr_run = F.b_irun.as<int32_t>();
+    b.flags = F.b_phflags.as<uint8_t>();
+    b.trig_dpe_out = F.b_trig.as<int32_t>();
+    b.n_pulse_calls = npc;
+    b.pc_group = F.b_pcgroup.as<int32_t>(); b.pc_rank = F.b_pcrank.as<int32_t>();
+    b.max_rank = max_rank;
+    b.n_groups = ngroups;
+    b.seed = seed;
+    b.group_base = group_base;
+    BackendResult res;
+    wfs_outputs *out = so.out;
+    int64_t cap_here = 0;
+    uint8_t *d_rec = nullptr;
+    F.b_groups.reserve(sizeof(wfs_group_info) * (size_t)std::max<int32_t>(ngroups, 1));
+    if (so.resident) {
+        cap_here = (int64_t)(F.b_records.cap / WFS_RECORD_BYTES);
+        d_rec = F.b_records.as<uint8_t>();
+    } else {
+        cap_here = out && out->records ? std::max<int64_t>(out->cap_records - so.n_rec, 0) : 0;
+        if (so.overflow) cap_here = 0;
+        F.b_records.reserve((size_t)WFS_RECORD_BYTES * (size_t)std::max<int64_t>(cap_here, 1));
+        d_rec = F.b_records.as<uint8_t>();
+    }
+    if (ngroups > 0) {
+        H->backend->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res);
+        if (res.error) {
+            H->last_error = res.error == WFS_E_PULSE_CACHE_TOO_LONG ? "Pulse cache too long"
+                                                                    : "back end error (key bits)";
+            throw std::runtime_error(H->last_error);
+        }
+        if (so.resident && res.n_records > cap_here) {   // grow the resident buffer and redo the batch
+            F.b_records.reserve((size_t)WFS_RECORD_BYTES * (size_t)res.n_records);
+            cap_here = (int64_t)(F.b_records.cap / WFS_RECORD_BYTES);
+            WFS_CUDA_CHECK(cudaMemsetAsync(F.b_trig.p, 0, 4 * (size_t)std::max<int64_t>(2 * npc, 1), s));
+            H->backend->run(b, F.b_records.as<uint8_t>(), cap_here, F.b_groups.as<wfs_group_info>(), res);
+        }
+    }
+    // ---- outputs ----
+    wfs_counts *cn = so.counts;
+    const bool fits = res.n_records <= cap_here;
+    if (!so.resident) {
+        if (!fits) so.overflow = true;
+        if (fits && res.n_records > 0)
+            WFS_CUDA_CHECK(cudaMemcpyAsync(out->records + (size_t)so.n_rec * WFS_RECORD_BYTES, d_rec,
+                                           (size_t)res.n_records * WFS_RECORD_BYTES, cudaMemcpyDeviceToHost, s));
+    }
+    std::vector<wfs_group_info> h_groups((size_t)ngroups);
+    if (ngroups)
+        WFS_CUDA_CHECK(cudaMemcpyAsync(h_groups.data(), F.b_groups.p, sizeof(wfs_group_info) * ngroups,
+                                       cudaMemcpyDeviceToHost, s));
+    std::vector<int32_t> trig((size_t)std::max<int64_t>(2 * npc, 1), 0);
+    if (npc) WFS_CUDA_CHECK(cudaMemcpyAsync(trig.data(), F.b_trig.p, 4 * (size_t)(2 * npc), cudaMemcpyDeviceToHost, s));
+    WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (out && out->groups)
+        for (int32_t gi = 0; gi < ngroups; gi++)
+            if (so.n_groups + gi < out->cap_groups) out->groups[so.n_groups + gi] = h_groups[gi];
+    if (out && out->batch_records && so.n_batches < out->cap_batches)
+        for (int k = 0; k < 3; k++) out->batch_records[3 * so.n_batches + k] = fits ? res.n_rec_class[k] : 0;
+    // truth rows (rawdata.py:313-375), one per Pulse call
+    for (int64_t r = 0; r < nruns; r++) {
+        const Run &run = runs[r];
+        int64_t sum[A_COUNT];
+        for (int a = 0; a < A_COUNT; a++) sum[a] = 0;
+        sum[A_TMIN] = sum[A_ETMIN] = LLONG_MAX;
+        sum[A_TMAX] = sum[A_ETMAX] = LLONG_MIN;
+        for (int32_t i : run.instr) {
+            const int64_t *a = &acc[(size_t)i * A_COUNT];
+            for (int k = 0; k < A_COUNT; k++) {
+                if (k == A_TMIN || k == A_ETMIN) sum[k] = std::min(sum[k], a[k]);
+                else if (k == A_TMAX || k == A_ETMAX || k == A_PTMAX) sum[k] = std::max(sum[k], a[k]);
+                else sum[k] += a[k];
+            }
+        }
+        cn->n_pe += sum[A_NPH] + sum[A_NDPE];
+        if (sum[A_NPHALL] == 0 && run.type != 1 && run.type != 2) continue;   // rawdata.py:336-337
+        if (out && out->truth && so.n_truth < out->cap_truth) {
+            long double pm, psig, em, esig;
+            combine_moments(run.instr, T, acc.data(), A_NPHALL, A_SREL, A_SHI2, A_SHILO, A_SLO2, pm, psig);
+            combine_moments(run.instr, T, acc.data(), A_NE, A_ESREL, A_EHI2, A_EHILO, A_ELO2, em, esig);
+            const int32_t i0 = run.instr[0];
+            const int32_t root = i0 < nprim ? i0 : in.parent[i0];
+            const HostInstr &h0 = P.instr[P.order[j0 + root]];
+            float x, y, z; int32_t amp;
+            auto fx = [&](int32_t i) { return i < nprim ? h_x[i] : sec_x[i - nprim]; };
+            auto fy = [&](int32_t i) { return i < nprim ? h_y[i] : sec_y[i - nprim]; };
+            auto fz = [&](int32_t i) { return i < nprim ? h_z[i] : sec_z[i - nprim]; };
+            auto fa = [&](int32_t i) { return i < nprim ? h_amp[i] : sec_amp[i - nprim]; };
+            if (run.instr.size() > 1) {
+                float sx = 0, sy = 0, sz = 0; int64_t sa = 0;
+                for (int32_t i : run.instr) { sx += fx(i); sy += fy(i); sz += fz(i); sa += fa(i); }
+                const float nn = (float)run.instr.size();
+                x = sx / nn; y = sy / nn; z = sz / nn; amp = (int32_t)sa;
+            } else {
+                x = fx(i0); y = fy(i0); z = fz(i0); amp = fa(i0);
+            }
+            write_truth_row(out->truth + (size_t)so.n_truth * WFS_TRUTH_BYTES, h0, run.type, T[i0], x, y, z,
+                            amp, sum, pm, psig, em, esig, trig[4 * r], trig[4 * r + 1], p);
+        }
+        so.n_truth++;
+    }
+    so.n_rec += res.n_records;
+    so.n_groups += ngroups;
+    so.n_batches++;
+    group_base += ngroups;
+    for (int k = 0; k < 3; k++) cn->n_records[k] += fits ? res.n_rec_class[k] : 0;
+    cn->n_photons += res.n_valid_photons;
+    cn->n_pulses += res.n_pulses;
+    cn->n_windows += res.n_windows;
+    cn->n_intervals += res.n_intervals;
+    cn->n_samples += res.n_samples;
+    cn->n_pulse_calls += nruns;
+    cn->n_instructions += ntot;
+    cn->ms_digitize += res.ms_digitize;
+}
+
+static int run_plan(Handle *H, Plan &P, uint64_t seed, wfs_outputs *out, wfs_counts *counts, bool resident,
+                    PhotonDump *dump = nullptr) {
+    if (!H->frontend) throw std::runtime_error("front-end tables missing (SPE table is required for wfs_simulate)");
+    memset(counts, 0, sizeof(*counts));
+    const int64_t launches0 = H->launches.n;
+    SimOut so;
+    so.out = out;
+    so.counts = counts;
+    so.resident = resident;
+    so.dump = dump;
+    cudaStream_t s = H->stream;
+    WFS_CUDA_CHECK(cudaEventRecord(H->ev_a, s));
+    int64_t group_base = 0;
+    for (const BatchSpec &bs : P.batches) simulate_batch(H, P, bs, seed, so, group_base);
+    WFS_CUDA_CHECK(cudaEventRecord(H->ev_b, s));
+    WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+    float ms;
+    WFS_CUDA_CHECK(cudaEventElapsedTime(&ms, H->ev_a, H->ev_b));
+    counts->ms_total = ms;
+    counts->n_records_total = so.n_rec;
+    counts->n_truth = so.n_truth;
+    counts->n_groups = so.n_groups;
+    counts->n_batches = so.n_batches;
+    counts->need_records = so.n_rec;
+    counts->need_truth = so.n_truth;
+    counts->need_groups = so.n_groups;
+    counts->need_batches = so.n_batches;
+    counts->gpu_launches = H->launches.n - launches0;
+    bool cap = so.overflow;
+    if (out) {
+        if (out->truth && so.n_truth > out->cap_truth) cap = true;
+        if (out->groups && so.n_groups > out->cap_groups) cap = true;
+        if (out->batch_records && so.n_batches > out->cap_batches) cap = true;
+    }
+    if (cap) {
+        counts->n_records_total = 0;
+        for (int k = 0; k < 3; k++) counts->n_records[k] = 0;
+        return WFS_E_CAPACITY;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static T *upload_table(const T *host, size_t count, std::vector<void *> &owned) {
+    if (!host || count == 0) return nullptr;
+    T *d = nullptr;
+    WFS_CUDA_CHECK(cudaMalloc((void **)&d, count * sizeof(T)));
+    WFS_CUDA_CHECK(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    owned.push_back(d);
+    return d;
+}
+
+void Handle::frontend_init(const wfs_tables &t) {
+    frontend = nullptr;
+    if (!t.spe_ppf || !t.spe_row) return;   // deterministic entry only
+    Frontend *F = new Frontend(this);
+    F->prim.stream = stream;
+    F->prim.lc = &launches;
+    const wfs_params &p = cfg.p;
+    F->n_spe_rows = t.n_spe_rows; F->spe_len = t.spe_len;
+    F->spe_ppf = upload_table(t.spe_ppf, (size_t)t.n_spe_rows * t.spe_len, owned);
+    F->spe_row = upload_table(t.spe_row, (size_t)p.n_tpc_pmts, owned);
+    if (t.lum_cdf && t.lum_t && t.lum_len > 1) {
+        F->lum_cdf = upload_table(t.lum_cdf, (size_t)t.lum_len, owned);
+        F->lum_t = upload_table(t.lum_t, (size_t)t.lum_len, owned);
+        F->lum_len = t.lum_len;
+    }
+    F->n_ap = std::min<int32_t>(t.n_ap_elements, WFS_MAX_AP_ELEMENTS);
+    for (int e = 0; e < WFS_MAX_AP_ELEMENTS; e++) {
+        F->ap_is_uniform[e] = 0; F->ap_delay_cdf[e] = nullptr; F->ap_amp_cdf[e] = nullptr;
+        F->ap_delay_len[e] = F->ap_amp_len[e] = F->ap_amp_rows[e] = 0;
+        F->ap_delay_bin[e] = F->ap_amp_bin[e] = 0;
+    }
+    for (int e = 0; e < F->n_ap; e++) {
+        F->ap_is_uniform[e] = t.ap_is_uniform[e];
+        F->ap_delay_len[e] = t.ap_delay_len[e];
+        F->ap_delay_bin[e] = t.ap_delay_bin[e];
+        F->ap_delay_cdf[e] = upload_table(t.ap_delay_cdf[e], (size_t)p.n_tpc_pmts * t.ap_delay_len[e], owned);
+        F->ap_amp_len[e] = t.ap_amp_len[e];
+        F->ap_amp_rows[e] = t.ap_amp_rows[e];
+        F->ap_amp_bin[e] = t.ap_amp_bin[e];
+        if (t.ap_amp_cdf[e])
+            F->ap_amp_cdf[e] = upload_table(t.ap_amp_cdf[e], (size_t)std::max(1, t.ap_amp_rows[e]) * t.ap_amp_len[e], owned);
+    }
+    if (t.pi_coarse_time && t.pi_coarse_prob && t.pi_coarse_len > 0) {
+        F->pi_coarse_len = t.pi_coarse_len;
+        F->pi_coarse_time = upload_table(t.pi_coarse_time, (size_t)t.pi_coarse_len, owned);
+        F->pi_coarse_prob = upload_table(t.pi_coarse_prob, (size_t)t.pi_coarse_len, owned);
+        F->h_pi_coarse_time.assign(t.pi_coarse_time, t.pi_coarse_time + t.pi_coarse_len);
+    }
+    frontend = F;
+}
+
+void Handle::frontend_release() {
+    if (!frontend) return;
+    Frontend &F = *frontend;
+    DevBuf *all[] = {&F.b_itype, &F.b_itime, &F.b_ix, &F.b_iy, &F.b_iz, &F.b_iamp, &F.b_igidx, &F.b_ilce,
+                     &F.b_iscg, &F.b_icy, &F.b_ipat, &F.b_dmean, &F.b_dspread, &F.b_nemit, &F.b_emitoff,
+                     &F.b_nhits, &F.b_acc, &F.b_cdf, &F.b_cdfok, &F.b_pattern, &F.b_et, &F.b_einstr,
+                     &F.b_enph, &F.b_ephoff, &F.b_pht, &F.b_phch, &F.b_phgain, &F.b_phinstr, &F.b_phflags,
+                     &F.b_phnap, &F.b_apoff, &F.b_picount, &F.b_pioff, &F.b_irun, &F.b_pcgroup,
+                     &F.b_pcrank, &F.b_trig, &F.b_records, &F.b_groups, &F.b_scal};
+    for (DevBuf *b : all) b->release();
+    F.prim.release();
+    delete reinterpret_cast<Plan *>(staged_plan);
+    staged_plan = nullptr;
+    delete frontend;
+    frontend = nullptr;
+}
+
 }  // namespace wfs
 
 using namespace wfs;
 
+#define API_TRY(h)                                   \
+    Handle *H = reinterpret_cast<Handle *>(h);       \
+    if (!H) return WFS_E_ARG;                        \
+    try {                                            \
+        WFS_CUDA_CHECK(cudaSetDevice(H->device));
+
+#define API_CATCH                                                          \
+    } catch (const std::exception &e) {                                    \
+        H->last_error = e.what();                                          \
+        cudaGetLastError();                                                \
+        if (H->last_error == "Pulse cache too long") return WFS_E_PULSE_CACHE_TOO_LONG; \
+        return H->last_error.find("CUDA") != std::string::npos ? WFS_E_CUDA : WFS_E_ARG; \
+    }
+
 extern "C" {
-int wfs_simulate(void *handle, const uint8_t *, int64_t, const wfs_instr_maps *, uint64_t, uint8_t *,
-                 int64_t, uint8_t *, int64_t, wfs_group_info *, int64_t, wfs_counts *) {
-    if (handle) reinterpret_cast<Handle *>(handle)->last_error = "wfs_simulate: not built yet";
-    return WFS_E_ARG;
+
+int wfs_simulate(void *handle, const uint8_t *instructions, int64_t n_instructions,
+                 const wfs_instr_maps *maps, uint64_t seed, wfs_outputs *out, wfs_counts *counts) {
+    API_TRY(handle)
+    if (!counts) throw std::runtime_error("counts is required");
+    if (n_instructions < 0 || (n_instructions > 0 && !instructions)) throw std::runtime_error("bad instructions");
+    Plan P;
+    make_plan(H, instructions, n_instructions, maps, P);
+    return run_plan(H, P, seed, out, counts, false);
+    API_CATCH
 }
-int wfs_stage_instructions(void *handle, const uint8_t *, int64_t, const wfs_instr_maps *) {
-    if (handle) reinterpret_cast<Handle *>(handle)->last_error = "not built yet";
-    return WFS_E_ARG;
+
+int wfs_stage_instructions(void *handle, const uint8_t *instructions, int64_t n_instructions,
+                           const wfs_instr_maps *maps) {
+    API_TRY(handle)
+    if (!H->frontend) throw std::runtime_error("front-end tables missing");
+    Plan *P = new Plan();
+    make_plan(H, instructions, n_instructions, maps, *P);
+    delete reinterpret_cast<Plan *>(H->staged_plan);
+    H->staged_plan = P;
+    return 0;
+    API_CATCH
 }
-int wfs_run_staged(void *handle, uint64_t, wfs_counts *) {
-    if (handle) reinterpret_cast<Handle *>(handle)->last_error = "not built yet";
-    return WFS_E_ARG;
+
+int wfs_run_staged(void *handle, uint64_t seed, wfs_outputs *out, wfs_counts *counts) {
+    API_TRY(handle)
+    if (!H->staged_plan) throw std::runtime_error("nothing staged");
+    if (!counts) throw std::runtime_error("counts is required");
+    return run_plan(H, *reinterpret_cast<Plan *>(H->staged_plan), seed, out, counts, true);
+    API_CATCH
 }
-int wfs_sample_stage(void *handle, int, const uint8_t *, int64_t, const wfs_instr_maps *, uint64_t,
-                     void *, int64_t, int64_t *) {
-    if (handle) reinterpret_cast<Handle *>(handle)->last_error = "not built yet";
-    return WFS_E_ARG;
+
+int wfs_sample_stage(void *handle, int stage, const uint8_t *instructions, int64_t n_instructions,
+                     const wfs_instr_maps *maps, uint64_t seed, void *out, int64_t cap, int64_t *n_out) {
+    API_TRY(handle)
+    if (!n_out) throw std::runtime_error("n_out is required");
+    Plan P;
+    make_plan(H, instructions, n_instructions, maps, P);
+    PhotonDump d;
+    d.stage = stage;
+    d.out = reinterpret_cast<uint8_t *>(out);
+    d.cap = out ? cap : 0;
+    wfs_counts counts;
+    run_plan(H, P, seed, nullptr, &counts, false, &d);
+    *n_out = d.n;
+    return d.n > d.cap ? WFS_E_CAPACITY : 0;
+    API_CATCH
 }
-}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+// Sampling front end (Philox-driven S1/S2/afterpulse photon generation) + host scheduler.
+#pragma once
+#include "handle.cuh"
+
+namespace wfs {
+
+// Per-instruction truth accumulators (all int64, exact -> deterministic under atomics).
+enum Acc {
+    A_NPH = 0, A_NDPE, A_NTRIG, A_AREA, A_AREA_TRIG,             // pulse.py:259-266 (totals)
+    A_NPH_B, A_NDPE_B, A_NTRIG_B, A_AREA_B, A_AREA_TRIG_B,       // ... bottom array
+    A_NPHALL, A_TMIN, A_TMAX, A_SREL, A_SHI2, A_SHILO, A_SLO2,   // photon times, rawdata.py:325-332
+    A_NE, A_ETMIN, A_ETMAX, A_ESREL, A_EHI2, A_EHILO, A_ELO2,    // electron times
+    A_PTMAX,                                                     // last photon on a live PMT (incl. its PMT afterpulses)
+    A_NAP,
+    A_COUNT
+};
+
+constexpr double kAreaScale = 4294967296.0;   // fixed-point scale of the area accumulators
+
+// Instruction as parsed from the 70-byte rows (host side)
+struct HostInstr {
+    int32_t event_number;
+    int8_t type;
+    int64_t time;
+    float x, y, z;
+    int32_t amp;
+    int8_t recoil;
+    float e_dep, tot_e;
+    int32_t g4id, vol_id;
+    double local_field;
+    int32_t n_excitons;
+    float x_pri, y_pri, z_pri;
+};
+
+// One Pulse call of the reference scheduler (rawdata.py:102-145)
+struct Run {
+    int32_t type;                    // 1, 2, 4, 6
+    int32_t group;
+    std::vector<int32_t> instr;      // batch-local instruction indices
+};
+
+struct DeviceInstr {   // SoA views, batch-local
+    int32_t *type;
+    int64_t *time;
+    float *x, *y, *z;
+    int32_t *amp;
+    uint64_t *gidx;      // RNG identity of the instruction (independent of batching)
+    double *lce, *scgain, *cyextra;
+    int32_t *patrow;
+    // derived
+    double *dmean, *dspread;
+    uint32_t *nemit;     // emitters (S1: 0/1, S2-like: electrons)
+    uint32_t *emit_off;  // exclusive scan, [n+1]
+    int64_t *nhits;      // S1 detected photons
+    int64_t *acc;        // [A_COUNT][cap]
+};
+
+struct Frontend {
+    Handle *H;
+    // device tables
+    double *spe_ppf = nullptr;
+    int32_t *spe_row = nullptr;
+    int32_t n_spe_rows = 0, spe_len = 0;
+    double *lum_cdf = nullptr, *lum_t = nullptr;
+    int32_t lum_len = 0;
+    int32_t n_ap = 0;
+    int32_t ap_is_uniform[WFS_MAX_AP_ELEMENTS];
+    double *ap_delay_cdf[WFS_MAX_AP_ELEMENTS];
+    int32_t ap_delay_len[WFS_MAX_AP_ELEMENTS];
+    double ap_delay_bin[WFS_MAX_AP_ELEMENTS];
+    double *ap_amp_cdf[WFS_MAX_AP_ELEMENTS];
+    int32_t ap_amp_len[WFS_MAX_AP_ELEMENTS], ap_amp_rows[WFS_MAX_AP_ELEMENTS];
+    double ap_amp_bin[WFS_MAX_AP_ELEMENTS];
+    double *pi_coarse_time = nullptr, *pi_coarse_prob = nullptr;
+    int32_t pi_coarse_len = 0;
+    std::vector<double> h_pi_coarse_time;
+    Primitives prim;
+    // workspaces
+    DevBuf b_itype, b_itime, b_ix, b_iy, b_iz, b_iamp, b_igidx, b_ilce, b_iscg, b_icy, b_ipat,
+        b_dmean, b_dspread, b_nemit, b_emitoff, b_nhits, b_acc, b_cdf, b_cdfok, b_pattern,
+        b_et, b_einstr, b_enph, b_ephoff, b_pht, b_phch, b_phgain, b_phinstr, b_phflags, b_phnap,
+        b_apoff, b_picount, b_pioff, b_irun, b_pcgroup, b_pcrank, b_trig, b_records, b_groups,
+        b_scal;
+    int64_t *h_pin = nullptr;   // pinned scratch for small readbacks
+    // staged instructions (device-resident measurement mode)
+    std::vector<uint8_t> staged_instr;
+    std::vector<double> staged_lce, staged_scg, staged_cy;
+    std::vector<float> staged_pattern;
+    std::vector<int32_t> staged_patrow;
+    int64_t staged_n = 0, staged_pattern_rows = 0;
+    bool staged_has[5] = {false, false, false, false, false};
+
+    explicit Frontend(Handle *h) : H(h) {}
+};
+
+}  // namespace wfs

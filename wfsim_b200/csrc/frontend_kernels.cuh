@@ -1,0 +1,440 @@
+// Sampling kernels of the front end (included by frontend.cu only).
+//
+// Every random quantity is philox(seed, stream, instruction identity, draw) -- see philox.cuh --
+// so photons do not depend on batching or on which GPU simulates the instruction.
+#pragma once
+#include "frontend.cuh"
+#include "sampling.cuh"
+
+namespace wfs {
+
+struct GenCtx {
+    // instructions (batch-local SoA)
+    int32_t *i_type;
+    int64_t *i_time;
+    float *i_x, *i_y, *i_z;
+    int32_t *i_amp;
+    uint64_t *i_gidx;
+    double *i_lce, *i_scg, *i_cy;
+    int32_t *i_pat;
+    double *i_dmean, *i_dspread;
+    uint32_t *i_nemit, *i_emitoff;
+    int64_t *i_nhits;
+    int64_t *i_acc;
+    // pattern CDF rows
+    double *cdf;          // [rows][n_ch]
+    int32_t *cdf_ok;      // [rows]
+    // emitters
+    int64_t *e_t;
+    int32_t *e_instr;
+    uint32_t *e_nph, *e_phoff;
+    // photons
+    int64_t *ph_t;
+    int32_t *ph_ch;
+    double *ph_gain;
+    int32_t *ph_instr;
+    uint8_t *ph_flags, *ph_nap;
+    uint32_t *ap_off;
+    // tables
+    const double *spe_ppf;
+    const int32_t *spe_row;
+    int32_t spe_len;
+    const double *lum_cdf, *lum_t;
+    int32_t lum_len;
+    int32_t n_ap;
+    int32_t ap_is_uniform[WFS_MAX_AP_ELEMENTS];
+    const double *ap_delay_cdf[WFS_MAX_AP_ELEMENTS];
+    int32_t ap_delay_len[WFS_MAX_AP_ELEMENTS];
+    double ap_delay_bin[WFS_MAX_AP_ELEMENTS];
+    const double *ap_amp_cdf[WFS_MAX_AP_ELEMENTS];
+    int32_t ap_amp_len[WFS_MAX_AP_ELEMENTS], ap_amp_rows[WFS_MAX_AP_ELEMENTS];
+    double ap_amp_bin[WFS_MAX_AP_ELEMENTS];
+    const double *pi_time, *pi_prob;
+    int32_t pi_len;
+    uint64_t seed;
+};
+
+// first index in [0, n) with a[i] > key  (a ascending)
+template <typename T, typename K>
+__device__ __forceinline__ uint32_t upper_bound_dev(const T *a, uint32_t n, K key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] <= key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// first index in [0, n) with a[i] >= key
+template <typename T, typename K>
+__device__ __forceinline__ uint32_t lower_bound_dev(const T *a, uint32_t n, K key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void k_widen_u8(const uint8_t *a, uint32_t *b, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = a[i];
+}
+
+// Pattern row -> normalised CDF (np.random.choice(p=...) builds exactly this: cumsum, /= last;
+// s1.py:148-158, s2.py:646-677).  One thread per row.
+__global__ void k_pattern_cdf(int64_t rows, int n_ch, const float *pattern, const double *gains,
+                              double *cdf, int32_t *ok) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float *p = pattern + r * n_ch;
+    double *c = cdf + r * n_ch;
+    double s = 0.0;
+    bool bad = false;
+    for (int ch = 0; ch < n_ch; ch++) {
+        double v = gains[ch] != 0.0 ? (double)p[ch] : 0.0;   // turned-off PMTs get no photons
+        if (isnan(v)) bad = true;
+        s += v;
+        c[ch] = s;
+    }
+    if (bad || !(s > 0.0)) { ok[r] = 0; return; }
+    for (int ch = 0; ch < n_ch; ch++) c[ch] /= s;
+    ok[r] = 1;
+}
+
+// Per instruction: yields.  S1: s1.py:117-135.  S2-like: s2.py:157-179, 212-256.
+__global__ void k_instr(GenCtx g, wfs_params p, uint32_t i0, uint32_t i1) {
+    uint32_t i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i1) return;
+    const int type = g.i_type[i];
+    const int64_t amp = g.i_amp[i];
+    Rng rng(g.seed, RS_INSTR, g.i_gidx[i], 0);
+    uint32_t nemit = 0;
+    int64_t nhits = 0;
+    if (type == 1) {
+        double ly = g.i_lce[i] / (1.0 + p.p_double_pe_emision) * p.s1_detection_efficiency;
+        ly = fmin(fmax(ly, 0.0), 1.0);
+        nhits = sample_binomial(amp, ly, rng.ud53());
+        nemit = nhits > 0 ? 1u : 0u;
+    } else if (type == 2 || type == 4 || type == 6) {
+        const double z = (double)g.i_z[i];
+        double mean = -z / p.drift_velocity_liquid + p.drift_time_gate;
+        if (mean < 0.0) mean = 0.0;
+        double spread = sqrt(2.0 * p.diffusion_constant_longitudinal * mean) / p.drift_velocity_liquid;
+        double cy = p.electron_extraction_yield * exp(-mean / p.electron_lifetime_liquid) * g.i_cy[i];
+        cy = fmin(fmax(cy, 0.0), 1.0);
+        int64_t ne = sample_binomial(amp, cy, rng.ud53());
+        g.i_dmean[i] = mean;
+        g.i_dspread[i] = spread;
+        nemit = (uint32_t)ne;
+    }
+    g.i_nhits[i] = nhits;
+    g.i_nemit[i] = nemit;
+}
+
+// Per emitter: S1 -> the interaction itself; S2 -> one electron (s2.py:258-286, 300-310).
+__global__ void k_emitters(GenCtx g, wfs_params p, uint32_t n_instr, uint32_t e0, uint32_t e1) {
+    uint32_t e = e0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= e1) return;
+    uint32_t i = upper_bound_dev(g.i_emitoff, n_instr + 1, e) - 1;
+    const int type = g.i_type[i];
+    int64_t t = g.i_time[i];
+    int64_t nph;
+    if (type == 1) {
+        nph = g.i_nhits[i];
+    } else {
+        const uint32_t j = e - g.i_emitoff[i];
+        Rng rng(g.seed, RS_ELECTRON, g.i_gidx[i], j * 2u);
+        double tt = -log(1.0 - rng.ud53()) * p.electron_trapping_time;
+        tt += g.i_dmean[i] + g.i_dspread[i] * normal_d(rng);
+        t += (int64_t)tt;   // int(): truncation toward zero
+        nph = sample_poisson(g.i_scg[i], rng.ud53());
+        if (p.s2_gain_spread > 0.0) nph += (int64_t)(normal_d(rng) * p.s2_gain_spread);
+        if (nph < 0) nph = 0;
+    }
+    g.e_t[e] = t;
+    g.e_instr[e] = (int32_t)i;
+    g.e_nph[e] = (uint32_t)nph;
+}
+
+__device__ __forceinline__ double interp_table(const double *xp, const double *fp, int n, double x) {
+    // np.interp semantics for ascending xp
+    if (x <= xp[0]) return fp[0];
+    if (x >= xp[n - 1]) return fp[n - 1];
+    uint32_t j = upper_bound_dev(xp, (uint32_t)n, x) - 1;
+    double slope = (fp[j + 1] - fp[j]) / (xp[j + 1] - xp[j]);
+    return slope * (x - xp[j]) + fp[j];
+}
+
+// Per photon: channel (s1.py:138-159 / s2.py:616-682), arrival time (s1.py:162-238 /
+// s2.py:504-557, pulse.py:321-341), then the PMT stage (pulse.py:53-56,76-79,95-103).
+__global__ void __launch_bounds__(256)
+k_photons(GenCtx g, wfs_params p, const double *gains, int n_ch, uint32_t n_emit, uint32_t p0,
+          uint32_t p1) {
+    uint32_t ph = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (ph >= p1) return;
+    const uint32_t em = upper_bound_dev(g.e_phoff, n_emit + 1, ph) - 1;
+    const int32_t i = g.e_instr[em];
+    const uint32_t ord = ph - g.e_phoff[g.i_emitoff[i]];
+    const int type = g.i_type[i];
+    const uint64_t gidx = g.i_gidx[i];
+    const Philox4 w0 = philox4x32(g.seed, RS_PHOTON, gidx, ord * 3u);
+    const Philox4 w1 = philox4x32(g.seed, RS_PHOTON, gidx, ord * 3u + 1u);
+    const Philox4 w2 = philox4x32(g.seed, RS_PHOTON, gidx, ord * 3u + 2u);
+    // channel
+    int ch = -1;
+    const int row = g.i_pat[i];
+    if (g.cdf_ok[row]) {
+        const double u = u01_32(w0.v[0]);
+        ch = (int)upper_bound_dev(g.cdf + (int64_t)row * n_ch, (uint32_t)n_ch, u);
+        if (ch >= n_ch) ch = n_ch - 1;
+    }
+    float zs, zt;
+    normal_pair(w1.v[0], w1.v[1], zs, zt);
+    int64_t t = g.e_t[em];
+    if (type == 1) {
+        if (p.s1_model_simple) {
+            t += (int64_t)(exp1(w0.v[1]) * (float)p.s1_decay_time);
+            t += (int64_t)(zs * (float)p.s1_decay_spread);
+        }
+    } else {
+        if (p.s2_luminescence_model == 0 && g.lum_len > 0)
+            t += (int64_t)interp_table(g.lum_cdf, g.lum_t, g.lum_len, u01_32(w0.v[1]));
+        const double delay = u01_32(w0.v[2]) < p.singlet_fraction_gas ? p.singlet_lifetime_gas
+                                                                      : p.triplet_lifetime_gas;
+        t += (int64_t)((double)exp1(w0.v[3]) * delay);
+        if (p.s2_time_model == 0 && p.s2_time_spread > 0.0) t += (int64_t)(zs * (float)p.s2_time_spread);
+    }
+    // PMT transit time spread (FWHM -> sigma), truncated toward zero
+    t += (int64_t)(p.pmt_transit_time_mean + (double)zt * (p.pmt_transit_time_spread / 2.35482));
+    const bool dpe = u01_32(w1.v[2]) < p.p_double_pe_emision;
+    double gain = 0.0;
+    if (ch >= 0) {
+        const double *ppf = g.spe_ppf + (int64_t)g.spe_row[ch] * g.spe_len;
+        const double gch = gains[ch];
+        int k1 = (int)(((uint64_t)w1.v[3] * 2000u) >> 32) + 1;
+        gain = gch * ppf[k1];
+        if (dpe) {
+            int k2 = (int)(((uint64_t)w2.v[0] * 2000u) >> 32) + 1;
+            gain += gch * ppf[k2];
+        }
+    }
+    // PMT afterpulse selection (afterpulse.py:189-204): count children now, fill later
+    uint32_t nap = 0;
+    if (g.n_ap > 0 && ch >= 0) {
+        Rng ar(g.seed, RS_AP, gidx, ord * 2u);
+        for (int e = 0; e < g.n_ap; e++) {
+            double rU0 = (1.0 - ar.ud32()) / p.pmt_ap_modifier;
+            if (dpe) rU0 *= 0.5;
+            const double *dc = g.ap_delay_cdf[e] + (int64_t)ch * g.ap_delay_len[e];
+            if (rU0 <= dc[g.ap_delay_len[e] - 1]) nap++;
+        }
+    }
+    g.ph_t[ph] = t;
+    g.ph_ch[ph] = ch;
+    g.ph_gain[ph] = gain;
+    g.ph_instr[ph] = i;
+    g.ph_flags[ph] = dpe ? 1 : 0;
+    g.ph_nap[ph] = (uint8_t)nap;
+}
+
+// argmin(|cdf - x|) over an ascending row, first index on ties (np.argmin)
+__device__ __forceinline__ int nearest_index(const double *cdf, int n, double x) {
+    int j = (int)lower_bound_dev(cdf, (uint32_t)n, x);
+    if (j == 0) return 0;
+    if (j == n) j = n - 1;
+    double d1 = fabs(cdf[j] - x), d0 = fabs(cdf[j - 1] - x);
+    if (d0 <= d1) return (int)lower_bound_dev(cdf, (uint32_t)n, cdf[j - 1]);
+    return (int)lower_bound_dev(cdf, (uint32_t)n, cdf[j]);
+}
+
+// Fill the PMT-afterpulse photons behind the parents (afterpulse.py:206-243).
+__global__ void k_ap_fill(GenCtx g, wfs_params p, const double *gains, uint32_t n_emit, uint32_t n_ph,
+                          uint32_t out0) {
+    uint32_t ph = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ph >= n_ph || g.ph_nap[ph] == 0) return;
+    const int32_t i = g.ph_instr[ph];
+    const uint32_t em = upper_bound_dev(g.e_phoff, n_emit + 1, ph) - 1;
+    (void)em;
+    const uint32_t ord = ph - g.e_phoff[g.i_emitoff[i]];
+    const uint64_t gidx = g.i_gidx[i];
+    const int ch = g.ph_ch[ph];
+    const bool dpe = g.ph_flags[ph] & 1;
+    const int64_t tp = g.ph_t[ph];
+    uint32_t o = out0 + g.ap_off[ph];
+    Rng ar(g.seed, RS_AP, gidx, ord * 2u);
+    for (int e = 0; e < g.n_ap; e++) {
+        double rU0 = (1.0 - ar.ud32()) / p.pmt_ap_modifier;
+        if (dpe) rU0 *= 0.5;
+        const int len = g.ap_delay_len[e];
+        const double *dc = g.ap_delay_cdf[e] + (int64_t)ch * len;
+        if (!(rU0 <= dc[len - 1])) continue;
+        Rng er(g.seed, RS_AP + 100u + (uint32_t)e, gidx, ord);
+        const double rU1 = 1.0 - er.ud32();
+        double delay, amp;
+        if (g.ap_is_uniform[e]) {
+            double lo = dc[0], hi = dc[1];
+            delay = (lo + (hi - lo) * er.ud32()) * g.ap_delay_bin[e];
+            amp = 1.0;
+        } else {
+            delay = nearest_index(dc, len, rU0) * g.ap_delay_bin[e] - p.pmt_ap_t_modifier;
+            const int alen = g.ap_amp_len[e];
+            const double *ac = g.ap_amp_cdf[e] + (g.ap_amp_rows[e] > 1 ? (int64_t)ch * alen : 0);
+            amp = nearest_index(ac, alen, rU1) * g.ap_amp_bin[e];
+        }
+        g.ph_t[o] = (int64_t)((double)tp + delay);
+        g.ph_ch[o] = ch;
+        g.ph_gain[o] = gains[ch] * amp;
+        g.ph_instr[o] = i;
+        g.ph_flags[o] = 2;   // afterpulse photon
+        g.ph_nap[o] = 0;
+        o++;
+    }
+}
+
+// Per-instruction truth accumulators: one CTA per instruction, fixed reduction order.
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce(T v, T *sm, Op op) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    T r = sm[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = op(r, sm[w]);
+    return r;
+}
+
+struct OpAdd { __device__ int64_t operator()(int64_t a, int64_t b) const { return a + b; } };
+struct OpMin { __device__ int64_t operator()(int64_t a, int64_t b) const { return a < b ? a : b; } };
+struct OpMax { __device__ int64_t operator()(int64_t a, int64_t b) const { return a > b ? a : b; } };
+
+__device__ __forceinline__ void time_moments(int64_t rel, int64_t &s, int64_t &hi2, int64_t &hilo, int64_t &lo2) {
+    int64_t hi = rel >> 12, lo = rel & 4095;
+    s += rel; hi2 += hi * hi; hilo += hi * lo; lo2 += lo * lo;
+}
+
+__global__ void __launch_bounds__(128)
+k_instr_truth(GenCtx g, DeviceConfig c, uint32_t n_instr, uint32_t n_ph, uint32_t ap0) {
+    __shared__ int64_t sm[4];
+    const uint32_t i = blockIdx.x;
+    if (i >= n_instr) return;
+    const int64_t T0 = g.i_time[i];
+    const uint32_t e0 = g.i_emitoff[i], e1 = g.i_emitoff[i + 1];
+    const uint32_t q0 = g.e_phoff[e0], q1 = g.e_phoff[e1];
+    int64_t v[A_COUNT];
+#pragma unroll
+    for (int a = 0; a < A_COUNT; a++) v[a] = 0;
+    v[A_TMIN] = LLONG_MAX; v[A_TMAX] = LLONG_MIN; v[A_ETMIN] = LLONG_MAX; v[A_ETMAX] = LLONG_MIN;
+    v[A_PTMAX] = LLONG_MIN;
+    const int dt = c.p.dt;
+    for (uint32_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+        const int64_t t = g.ph_t[q];
+        const int ch = g.ph_ch[q];
+        v[A_NPHALL]++;
+        v[A_TMIN] = t < v[A_TMIN] ? t : v[A_TMIN];
+        v[A_TMAX] = t > v[A_TMAX] ? t : v[A_TMAX];
+        time_moments(t - T0, v[A_SREL], v[A_SHI2], v[A_SHILO], v[A_SLO2]);
+        if (ch < 0) continue;
+        const double gch = c.gains[ch];
+        if (gch == 0.0) continue;
+        v[A_PTMAX] = t > v[A_PTMAX] ? t : v[A_PTMAX];
+        const double gain = g.ph_gain[q];
+        const int dpe = g.ph_flags[q] & 1;
+        int64_t q_ = t / dt; int r = (int)(t - q_ * dt); if (r < 0) r += dt;
+        const double thr = (double)(c.p.baseline - 1 - c.zle_thr[ch]) - 0.5;
+        const bool above = gain * c.current_max[r] * c.p.current_2_adc > thr;
+        const int64_t area = llrint(gain / gch * kAreaScale);
+        const bool bottom = ch >= c.p.n_top_pmts;
+        v[A_NPH]++; v[A_NDPE] += dpe; v[A_AREA] += area;
+        if (above) { v[A_NTRIG]++; v[A_AREA_TRIG] += area; }
+        if (bottom) {
+            v[A_NPH_B]++; v[A_NDPE_B] += dpe; v[A_AREA_B] += area;
+            if (above) { v[A_NTRIG_B]++; v[A_AREA_TRIG_B] += area; }
+        }
+    }
+    if (g.i_type[i] != 1) {
+        for (uint32_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+            const int64_t t = g.e_t[e];
+            v[A_NE]++;
+            v[A_ETMIN] = t < v[A_ETMIN] ? t : v[A_ETMIN];
+            v[A_ETMAX] = t > v[A_ETMAX] ? t : v[A_ETMAX];
+            time_moments(t - T0, v[A_ESREL], v[A_EHI2], v[A_EHILO], v[A_ELO2]);
+        }
+    }
+    if (g.n_ap > 0 && q1 > q0) {   // PMT-afterpulse children extend the last pulse end
+        const uint32_t a0 = ap0 + g.ap_off[q0], a1 = ap0 + (q1 < n_ph ? g.ap_off[q1] : g.ap_off[n_ph]);
+        for (uint32_t a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
+            const int64_t t = g.ph_t[a];
+            v[A_NAP]++;
+            v[A_PTMAX] = t > v[A_PTMAX] ? t : v[A_PTMAX];
+        }
+    }
+    int64_t *out = g.i_acc + (int64_t)i * A_COUNT;
+#pragma unroll
+    for (int a = 0; a < A_COUNT; a++) {
+        int64_t r;
+        if (a == A_TMIN || a == A_ETMIN) r = block_reduce(v[a], sm, OpMin());
+        else if (a == A_TMAX || a == A_ETMAX || a == A_PTMAX) r = block_reduce(v[a], sm, OpMax());
+        else r = block_reduce(v[a], sm, OpAdd());
+        if (threadIdx.x == 0) out[a] = r;
+    }
+}
+
+// Photo-ionisation electrons (afterpulse.py:29-80): n_e ~ Poisson(n * N_photons * modifier) delays
+// drawn from the delay histogram and binned on the coarse grid == independent Poisson counts per
+// coarse bin with mean lambda * P(bin).  One warp per instruction; pass 0 counts, pass 1 fills.
+__global__ void __launch_bounds__(128)
+k_photoionization(GenCtx g, wfs_params p, uint32_t n_prim, int fill, uint32_t *count,
+                  const uint32_t *offset, uint32_t out0, int32_t *sec_parent) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n_prim) return;
+    uint32_t total = 0;
+    if (g.i_type[i] == 2) {
+        const uint32_t q0 = g.e_phoff[g.i_emitoff[i]], q1 = g.e_phoff[g.i_emitoff[i + 1]];
+        const uint32_t nph = q1 - q0;
+        if (nph > 0) {
+            const double lam = p.ele_ap_n * (double)nph * p.photoionization_modifier;
+            const uint64_t gidx = g.i_gidx[i];
+            uint32_t base = fill ? out0 + offset[i] : 0;
+            for (int b0 = 0; b0 < g.pi_len; b0 += 32) {
+                const int b = b0 + lane;
+                int64_t n = 0;
+                Philox4 w;
+                if (b < g.pi_len) {
+                    w = philox4x32(g.seed, RS_PI, gidx, (uint32_t)b * 2u);
+                    n = sample_poisson(lam * g.pi_prob[b], u01_53(w.v[0], w.v[1]));
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, n > 0);
+                if (fill && n > 0) {
+                    const uint32_t o = base + __popc(m & ((1u << lane) - 1u));
+                    const Philox4 w2 = philox4x32(g.seed, RS_PI, gidx, (uint32_t)b * 2u + 1u);
+                    // random parent photon as time zero (afterpulse.py:49-56)
+                    const uint32_t pick = q0 + (uint32_t)(((uint64_t)w.v[2] * nph) >> 32);
+                    const double t0 = (double)g.ph_t[pick];
+                    const double R = p.tpc_radius;
+                    const double r = sqrt(u01_53(w2.v[0], w2.v[1]) * R * R);
+                    const double ang = -3.141592653589793 + 6.283185307179586 * u01_32(w2.v[2]);
+                    g.i_type[o] = 4;
+                    g.i_time[o] = (int64_t)(t0 - p.drift_time_gate);
+                    g.i_x[o] = (float)(r * cos(ang));
+                    g.i_y[o] = (float)(r * sin(ang));
+                    g.i_z[o] = (float)(-g.pi_time[b] * p.drift_velocity_liquid);
+                    g.i_amp[o] = (int32_t)n;
+                    g.i_gidx[o] = (1ull << 40) + gidx * 4096ull + (uint64_t)b;
+                    g.i_lce[o] = 1.0;
+                    g.i_scg[o] = g.i_scg[i];     // see DESIGN.md: map value of the parent position
+                    g.i_cy[o] = g.i_cy[i];
+                    g.i_pat[o] = g.i_pat[i];
+                    sec_parent[o] = (int32_t)i;
+                }
+                total += __popc(m);
+                base += __popc(m);
+            }
+        }
+    }
+    if (!fill && lane == 0) count[i] = total;
+}
+
+}  // namespace wfs

@@ -17,6 +17,7 @@ struct Handle {
     Backend *backend = nullptr;
     Frontend *frontend = nullptr;
     std::string last_error;
+    void *staged_plan = nullptr;        // Plan of wfs_stage_instructions (frontend.cu)
     // staging for host-pointer calls
     DevBuf d_t, d_ch, d_gain, d_pc, d_pc_group, d_pc_rank, d_ix, d_records, d_groups;
 

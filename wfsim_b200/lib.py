@@ -56,13 +56,17 @@ class Tables(C.Structure):
         ('ap_delay_bin', f64 * MAX_AP_ELEMENTS),
         ('ap_amp_cdf', vp * MAX_AP_ELEMENTS), ('ap_amp_len', i32 * MAX_AP_ELEMENTS),
         ('ap_amp_rows', i32 * MAX_AP_ELEMENTS), ('ap_amp_bin', f64 * MAX_AP_ELEMENTS),
-        ('pi_delay_icdf', vp), ('pi_icdf_len', i32),
-        ('pi_coarse_time', vp), ('pi_coarse_len', i32)]
+        ('pi_coarse_time', vp), ('pi_coarse_prob', vp), ('pi_coarse_len', i32)]
 
 
 class InstrMaps(C.Structure):
     _fields_ = [('s1_lce', vp), ('s2_sc_gain', vp), ('s2_cy_extra', vp), ('pattern', vp),
-                ('pattern_row', vp), ('n_pattern_rows', i64)]
+                ('pattern_row', vp), ('n_pattern_rows', i64), ('s2_sc_gain_default', f64)]
+
+
+class Outputs(C.Structure):
+    _fields_ = [('records', vp), ('cap_records', i64), ('truth', vp), ('cap_truth', i64),
+                ('groups', vp), ('cap_groups', i64), ('batch_records', vp), ('cap_batches', i64)]
 
 
 class Counts(C.Structure):
@@ -70,7 +74,8 @@ class Counts(C.Structure):
                 + [(n, i64) for n in (
                     'n_records_total', 'n_truth', 'n_photons', 'n_pe', 'n_pulses', 'n_windows',
                     'n_intervals', 'n_samples', 'n_groups', 'n_pulse_calls', 'n_instructions',
-                    'n_batches', 'gpu_launches', 'need_records', 'need_truth')]
+                    'n_batches', 'gpu_launches', 'need_records', 'need_truth', 'need_groups',
+                    'need_batches')]
                 + [(n, f64) for n in ('ms_total', 'ms_digitize', 'ms_h2d', 'ms_d2h')])
 
     def as_dict(self):
@@ -118,16 +123,15 @@ def load():
         vp, i64, vp, vp, vp, vp, i64, vp, i64, vp, C.c_uint64, C.c_int, vp, i64, vp,
         C.POINTER(Counts)]
     lib.wfs_simulate.argtypes = [
-        vp, vp, i64, C.POINTER(InstrMaps), C.c_uint64, vp, i64, vp, i64, vp, i64,
-        C.POINTER(Counts)]
+        vp, vp, i64, C.POINTER(InstrMaps), C.c_uint64, C.POINTER(Outputs), C.POINTER(Counts)]
     lib.wfs_stage_instructions.argtypes = [vp, vp, i64, C.POINTER(InstrMaps)]
-    lib.wfs_run_staged.argtypes = [vp, C.c_uint64, C.POINTER(Counts)]
+    lib.wfs_run_staged.argtypes = [vp, C.c_uint64, C.POINTER(Outputs), C.POINTER(Counts)]
     lib.wfs_sample_stage.argtypes = [vp, C.c_int, vp, i64, C.POINTER(InstrMaps), C.c_uint64,
                                      vp, i64, C.POINTER(i64)]
-    sizes = (i64 * 5)()
+    sizes = (i64 * 6)()
     lib.wfs_struct_sizes(sizes)
     want = [C.sizeof(Params), C.sizeof(Tables), C.sizeof(InstrMaps), C.sizeof(Counts),
-            C.sizeof(GroupInfo)]
+            C.sizeof(GroupInfo), C.sizeof(Outputs)]
     if list(sizes) != want:
         raise LibraryMissing(f'struct layout mismatch between lib.py {want} and the .so {list(sizes)}')
     if lib.wfs_abi_version() != ABI_VERSION:

@@ -92,6 +92,12 @@ def build_params(cfg):
     return p
 
 
+def set_ele_ap_n(p, resource):
+    ele = getattr(resource, 'uniform_to_ele_ap', None) if not isinstance(resource, dict) else resource.get('uniform_to_ele_ap')
+    if ele is not None:
+        p.ele_ap_n = float(ele.n)
+
+
 def build_tables(cfg, resource=None):
     """`resource` is an object/dict with the optional attributes the reference's Resource
     carries (noise_data, photon_area_distribution or spe_ppf/spe_row, uniform_to_pmt_ap,
@@ -119,4 +125,43 @@ def build_tables(cfg, resource=None):
         spe_ppf = t.set('spe_ppf', spe_ppf, np.float64)
         t.set('spe_row', spe_row, np.int32)
         t.struct.n_spe_rows, t.struct.spe_len = spe_ppf.shape
+    # S2 luminescence ('simple' model, constant gas gap)
+    if cfg.get('s2_luminescence_model', 'simple') == 'simple' and not cfg.get('enable_gas_gap_warping', False) \
+            and 'elr_gas_gap_length' in cfg:
+        cdf, tt = wtab.luminescence_table(cfg)
+        t.set('lum_cdf', cdf, np.float64)
+        t.set('lum_t', tt, np.float64)
+        t.struct.lum_len = len(cdf)
+    # PMT afterpulse elements (afterpulse.py:155-159, 181-186)
+    ap = get('uniform_to_pmt_ap')
+    if cfg.get('enable_pmt_afterpulses', True) and ap:
+        names = list(ap.keys())
+        if len(names) > wlib.MAX_AP_ELEMENTS:
+            raise ValueError('too many PMT afterpulse elements')
+        t.struct.n_ap_elements = len(names)
+        for k, name in enumerate(names):
+            el = ap[name]
+            dc = np.asarray(el['delaytime_cdf'], dtype=np.float64)
+            if dc.ndim != 2 or dc.shape[0] < n_ch:
+                raise ValueError(f'afterpulse element {name}: delaytime_cdf must be [n_pmt, n]')
+            dc = t.set_elem('ap_delay_cdf', k, dc[:n_ch], np.float64)
+            t.struct.ap_delay_len[k] = dc.shape[1]
+            t.struct.ap_delay_bin[k] = float(el['delaytime_bin_size'])
+            t.struct.ap_is_uniform[k] = int('Uniform' in name)
+            ac = np.atleast_1d(np.asarray(el.get('amplitude_cdf', [0.0, 1.0]), dtype=np.float64))
+            if ac.ndim == 1:
+                ac = ac[None, :]
+            else:
+                ac = ac[:n_ch]
+            ac = t.set_elem('ap_amp_cdf', k, ac, np.float64)
+            t.struct.ap_amp_rows[k], t.struct.ap_amp_len[k] = ac.shape
+            t.struct.ap_amp_bin[k] = float(el.get('amplitude_bin_size', 1.0))
+    # photo-ionisation electrons (afterpulse.py:33-80)
+    ele = get('uniform_to_ele_ap')
+    if cfg.get('enable_electron_afterpulses', True) and ele is not None:
+        coarse = wtab.pi_coarse_grid(cfg, ele.bin_centers)
+        prob = wtab.pi_coarse_probabilities(coarse, ele.histogram, ele.bin_edges)
+        t.set('pi_coarse_time', coarse, np.float64)
+        t.set('pi_coarse_prob', prob, np.float64)
+        t.struct.pi_coarse_len = len(coarse)
     return t

@@ -5,7 +5,8 @@ import numpy as np
 
 from . import lib as wlib
 from . import params as wparams
-from .dtypes import raw_record_dtype
+from .dtypes import raw_record_dtype, instruction_dtype, truth_dtype
+from .resource import Resource, evaluate_instruction_maps
 
 
 class SimulatorError(RuntimeError):
@@ -51,7 +52,10 @@ class Simulator:
         if self.lib.wfs_device_count() <= 0:
             raise SimulatorError('no CUDA device visible: wfsim_b200 has no CPU fallback')
         self.config = config
+        self.resource = resource
         self.params = wparams.build_params(config)
+        if resource is not None:
+            wparams.set_ele_ap_n(self.params, resource)
         self.tables = wparams.build_tables(config, resource)
         h = C.c_void_p()
         rc = self.lib.wfs_create(C.byref(self.params), C.byref(self.tables.struct), device, C.byref(h))
@@ -124,3 +128,122 @@ class Simulator:
         out['groups'] = groups
         out['_pinned'] = holder
         return out
+
+    # -----------------------------------------------------------------------------------------
+    def _maps_struct(self, instructions, maps=None):
+        if maps is None:
+            if self.resource is None or isinstance(self.resource, dict):
+                raise SimulatorError('simulate() needs a Resource (maps) -- pass resource= to Simulator')
+            maps = evaluate_instruction_maps(self.config, self.resource, instructions)
+        keep = {k: np.ascontiguousarray(v, dtype=(np.float32 if k == 'pattern' else
+                                                   np.int32 if k == 'pattern_row' else np.float64))
+                for k, v in maps.items()}
+        m = wlib.InstrMaps()
+        m.s1_lce = _ptr(keep['s1_lce'])
+        m.s2_sc_gain = _ptr(keep['s2_sc_gain'])
+        m.s2_cy_extra = _ptr(keep['s2_cy_extra'])
+        m.pattern = _ptr(keep['pattern'])
+        m.pattern_row = _ptr(keep['pattern_row'])
+        m.n_pattern_rows = keep['pattern'].shape[0]
+        m.s2_sc_gain_default = 0.0
+        return m, keep
+
+    def simulate(self, instructions, seed=0, maps=None, cap_records=None, pinned=False):
+        """Full path for one set of instructions (see wfs_simulate in the header).
+
+        Returns dict(raw_records, raw_records_he, raw_records_aqmon, truth, groups); records of
+        each data type are sorted by (time, channel); truth rows are in Pulse-call execution
+        order with `time` still the instruction time (the chunker sets it to t_first_photon,
+        strax_interface.py:481-482)."""
+        instructions = np.ascontiguousarray(instructions)
+        if instructions.dtype.itemsize != 70:
+            raise ValueError('instructions must have the packed 70-byte instruction_dtype')
+        n = len(instructions)
+        m, keep = self._maps_struct(instructions, maps)
+        counts = wlib.Counts()
+        cap_rec = int(cap_records) if cap_records is not None else max(4096, 1500 * n)
+        cap_truth, cap_groups, cap_batches = 2 * n + 64, n + 64, 4096
+        tdt = truth_dtype()
+        gdt = np.dtype([('left', np.int64), ('right', np.int64), ('n_intervals', np.int64)])
+        while True:
+            holder = PinnedArray(self.lib, cap_rec, raw_record_dtype()) if pinned else None
+            rec = holder.array if pinned else np.empty(cap_rec, raw_record_dtype())
+            truth = np.zeros(cap_truth, tdt)
+            groups = np.zeros(cap_groups, gdt)
+            batch_records = np.zeros((cap_batches, 3), np.int64)
+            out = wlib.Outputs(_ptr(rec), cap_rec, _ptr(truth), cap_truth, _ptr(groups), cap_groups,
+                               _ptr(batch_records), cap_batches)
+            rc = self.lib.wfs_simulate(self.handle, _ptr(instructions.view(np.uint8)), n, C.byref(m),
+                                       int(seed), C.byref(out), C.byref(counts))
+            if rc == wlib.E_CAPACITY:
+                cap_rec = max(cap_rec, int(counts.need_records))
+                cap_truth = max(cap_truth, int(counts.need_truth))
+                cap_groups = max(cap_groups, int(counts.need_groups))
+                cap_batches = max(cap_batches, int(counts.need_batches))
+                if holder is not None:
+                    holder.free()
+                continue
+            if rc != 0:
+                self._raise(rc)
+            break
+        self.last_counts = counts.as_dict()
+        nb = counts.n_batches
+        br = batch_records[:nb]
+        total = int(counts.n_records_total)
+        rec = rec[:total]
+        if nb <= 1 or (br[:, 1:].sum() == 0):
+            n0 = int(br[:, 0].sum())
+            res = dict(raw_records=rec[:n0], raw_records_he=rec[n0:n0 + int(br[:, 1].sum())],
+                       raw_records_aqmon=rec[n0 + int(br[:, 1].sum()):total])
+        else:
+            offs = np.concatenate([[0], np.cumsum(br.sum(axis=1))])
+            parts = [[], [], []]
+            for b in range(nb):
+                o = offs[b]
+                for k in range(3):
+                    parts[k].append(rec[o:o + br[b, k]])
+                    o += br[b, k]
+            res = dict(zip(('raw_records', 'raw_records_he', 'raw_records_aqmon'),
+                           (np.concatenate(p) for p in parts)))
+        res['truth'] = truth[:counts.n_truth]
+        res['groups'] = groups[:counts.n_groups]
+        res['_pinned'] = holder
+        return res
+
+    def stage(self, instructions, maps=None):
+        instructions = np.ascontiguousarray(instructions)
+        m, keep = self._maps_struct(instructions, maps)
+        rc = self.lib.wfs_stage_instructions(self.handle, _ptr(instructions.view(np.uint8)),
+                                             len(instructions), C.byref(m))
+        if rc != 0:
+            self._raise(rc)
+
+    def run_staged(self, seed=0):
+        counts = wlib.Counts()
+        rc = self.lib.wfs_run_staged(self.handle, int(seed), None, C.byref(counts))
+        if rc != 0:
+            self._raise(rc)
+        self.last_counts = counts.as_dict()
+        return self.last_counts
+
+    PHOTON_DUMP_DTYPE = np.dtype([('t', np.int64), ('gain', np.float64), ('channel', np.int32),
+                                  ('instruction', np.int32), ('flags', np.int32), ('secondary', np.int32)])
+
+    def sample_stage(self, instructions, stage=0, seed=0, maps=None):
+        """Front-end only: photons (stage 0) or emitters/electrons (stage 1) as a structured array
+        (see wfs_sample_stage).  For the statistical parity tests."""
+        instructions = np.ascontiguousarray(instructions)
+        m, keep = self._maps_struct(instructions, maps)
+        n_out = C.c_int64()
+        cap = 1 << 16
+        while True:
+            out = np.zeros(cap, self.PHOTON_DUMP_DTYPE)
+            rc = self.lib.wfs_sample_stage(self.handle, int(stage), _ptr(instructions.view(np.uint8)),
+                                           len(instructions), C.byref(m), int(seed), _ptr(out), cap,
+                                           C.byref(n_out))
+            if rc == wlib.E_CAPACITY:
+                cap = int(n_out.value)
+                continue
+            if rc != 0:
+                self._raise(rc)
+            return out[:n_out.value]

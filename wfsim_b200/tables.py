@@ -82,3 +82,75 @@ def zle_thresholds(cfg, n_rows=N_ROWS):
         if 0 <= int(k) < n_rows:
             thr[int(k)] = cfg['digitizer_reference_baseline'] - v - 1
     return thr
+
+
+# pax unit system constants used by the S2 luminescence model (wfsim/units.py: cm, ns, eV, V)
+_ELECTRON_CHARGE_SI = 1.602176565e-19
+_BOLTZMANN = 1.3806488e-23 / _ELECTRON_CHARGE_SI      # eV / K
+_KV_PER_CM = 1000.0
+_BAR = 1e5 / _ELECTRON_CHARGE_SI / 100.0 / 100.0 ** 2
+
+
+def luminescence_table(cfg, gas_gap=None):
+    """Inverse-CDF table of the 'simple' S2 luminescence model for one gas gap.
+
+    The reference rebuilds these arrays for every instruction (s2.py:317-341); without gas-gap
+    warping the gap is a constant so one table serves all: emission = interp(U, cdf, t)."""
+    dG = float(cfg['elr_gas_gap_length'] if gas_gap is None else gas_gap)
+    number_density_gas = cfg['pressure'] / (_BOLTZMANN * cfg['temperature'])
+    alpha = cfg['gas_drift_velocity_slope'] / number_density_gas
+    pressure = cfg['pressure'] / _BAR
+    rA = cfg['anode_field_domination_distance']
+    rW = cfg['anode_wire_radius']
+    dL = cfg['gate_to_anode_distance'] - dG
+    VG = cfg['anode_voltage'] / (1 + dL / dG / cfg['lxe_dielectric_constant'])
+    E0 = VG / ((dG - rA) / rA + np.log(rA / rW))
+    dr = 0.0001
+    r = np.arange(dG, rW, -dr)
+    rr = np.clip(1 / r, 1 / rA, 1 / rW)
+    dt = dr / (alpha * E0 * rr)
+    dy = E0 * rr / _KV_PER_CM - 0.8 * pressure
+    avgt = np.sum(np.cumsum(dt) * dy) / np.sum(dy)
+    j = int(np.argmax(r <= dG))
+    t = np.cumsum(dt[j:]) - avgt
+    y = np.cumsum(dy[j:])
+    return y / y[-1], t
+
+
+def template_maxima(templates):
+    """current_max of pulse.py:32."""
+    return np.max(np.asarray(templates), axis=1)
+
+
+def pi_coarse_grid(cfg, bin_centers):
+    """Coarse delay grid of PhotoIonization_Electron._reduce_instruction_timing
+    (afterpulse.py:63-75)."""
+    bin_centers = np.asarray(bin_centers, dtype=np.float64)
+    spread = np.sqrt(2 * cfg['diffusion_constant_longitudinal'] * bin_centers)
+    spread /= cfg['drift_velocity_liquid']
+    coarse, cur = [], 100.0
+    while cur < bin_centers[-1]:
+        coarse.append(cur)
+        cur += spread[np.argmin(np.abs(cur - bin_centers))]
+    return np.array(coarse)
+
+
+def pi_coarse_probabilities(coarse, histogram, bin_edges):
+    """Probability that one delay drawn from the (piecewise-uniform) delay histogram
+    (multihist.Hist1d.get_random: pick a bin by weight, uniform inside it) lands in each coarse
+    bin of np.digitize(delay, coarse) -- i.e. index i collects coarse[i-1] <= delay < coarse[i],
+    index 0 collects delay < coarse[0]; delays >= coarse[-1] are dropped (afterpulse.py:77)."""
+    histogram = np.asarray(histogram, dtype=np.float64)
+    bin_edges = np.asarray(bin_edges, dtype=np.float64)
+    w = histogram / histogram.sum()
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+
+    def cdf(x):
+        x = np.clip(x, bin_edges[0], bin_edges[-1])
+        k = np.clip(np.searchsorted(bin_edges, x, side='right') - 1, 0, len(w) - 1)
+        frac = (x - bin_edges[k]) / (bin_edges[k + 1] - bin_edges[k])
+        return cum[k] + w[k] * frac
+    edges = np.concatenate([[-np.inf], coarse])
+    c = cdf(np.where(np.isinf(edges), bin_edges[0], edges))
+    c[0] = 0.0
+    return np.diff(c)
