@@ -21,6 +21,8 @@
 
 namespace wfs {
 
+constexpr int kBlk = 8;                 // samples per digitize thread
+
 enum Scalar {
     S_NVALID = 0, S_NPULSES, S_NWIN, S_NTILES, S_NITVSLOTS, S_NREC, S_MINSAMPLE, S_MAXSAMPLE,
     S_ERR, S_NITV, S_NSAMPLES, S_CLASS0, S_CLASS1, S_CLASS2, S_COUNT
@@ -33,7 +35,7 @@ struct WinMeta {
     int32_t group;
     int32_t mult;        // 1, or he_mult for HE rows
     int32_t p0, p1;      // pulses [p0, p1) contributing to this window
-    int32_t pad0, pad1;
+    uint32_t ph_lo, ph_hi;   // their photons [ph_lo, ph_hi) (contiguous in the sorted arrays)
 };
 
 struct Interval {
@@ -136,7 +138,7 @@ __global__ void k_build_keys(PhotonBatch b, DeviceConfig c, KeyLayout kl, const 
 // After the sort: gather time/gain into sorted order and flag pulse / window starts.
 __global__ void k_gather_flags(PhotonBatch b, KeyLayout kl, const uint64_t *keys,
                                const uint32_t *vals, int64_t *st, double *sg, uint64_t *flags,
-                               int64_t *scalars) {
+                               uint8_t *pstart, int64_t *scalars) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= b.n) return;
     uint64_t k = keys[i];
@@ -154,6 +156,7 @@ __global__ void k_gather_flags(PhotonBatch b, KeyLayout kl, const uint64_t *keys
         if (!next_valid) scalars[S_NVALID] = i + 1;
     }
     flags[i] = f;
+    pstart[i] = (uint8_t)(f & 1ull);
 }
 
 __global__ void k_emit_pulses(int64_t n, KeyLayout kl, const uint64_t *keys, const uint64_t *flags,
@@ -208,8 +211,21 @@ __global__ void k_window_extents(int64_t n_win, DeviceConfig c, const int64_t *s
     uint32_t key = win_key[w];
     int ch = key & ((1u << kChannelBits) - 1u);
     int g = key >> kChannelBits;
-    atomicMin((long long *)&group_lr[2 * g], (long long)lo);
-    atomicMax((long long *)&group_lr[2 * g + 1], (long long)hi);
+    {   // windows are ordered by (group, channel): aggregate the group extents inside the warp
+        const int lane = threadIdx.x & 31;
+        const unsigned act = __activemask();
+        const unsigned grp = __match_any_sync(act, g);
+        int64_t glo = lo, ghi = hi;
+        for (int o = 0; o < 32; o++) {
+            if (!((act >> o) & 1u)) continue;
+            int64_t olo = __shfl_sync(act, lo, o), ohi = __shfl_sync(act, hi, o);
+            if ((grp >> o) & 1u) { glo = olo < glo ? olo : glo; ghi = ohi > ghi ? ohi : ghi; }
+        }
+        if ((grp & ((1u << lane) - 1u)) == 0) {
+            atomicMin((long long *)&group_lr[2 * g], (long long)glo);
+            atomicMax((long long *)&group_lr[2 * g + 1], (long long)ghi);
+        }
+    }
     const int tw = c.p.trigger_window;
     WinMeta m;
     m.left = lo - tw;
@@ -224,17 +240,22 @@ __global__ void k_window_extents(int64_t n_win, DeviceConfig c, const int64_t *s
     m.mult = 1;
     m.p0 = (int32_t)p0;
     m.p1 = (int32_t)p1;
-    m.pad0 = m.pad1 = 0;
+    m.ph_lo = pulse_first[p0];
+    m.ph_hi = pulse_first[p1];
     meta[w] = m;
     const int holdoff = 2 * tw + 1;
-    uint64_t tiles = (uint64_t)((len + kTile - 1) / kTile);
+    uint64_t tiles = (uint64_t)((len + kBlk - 1) / kBlk);   // 8-sample blocks
     uint64_t icap = (uint64_t)(len / (holdoff + 1) + 2);
     win_scan_in[w] = tiles | (icap << 32);
-    atomicMin((long long *)&scalars[S_MINSAMPLE], (long long)m.left);
-    atomicMax((long long *)&scalars[S_MAXSAMPLE], (long long)(m.left + len));
-    // HE twin
+    // HE twin (rawdata.py:241-249).  With int(high_energy_deamplification_factor) == 0 the row is
+    // baseline (+ noise) only; it is materialised only if it can drop below its ZLE threshold.
     WinMeta h = m;
     bool he = he_rows && c.p.detector_nt && ch < c.p.n_top_pmts;
+    if (he) {
+        const int hch = c.p.he_first + ch;
+        const bool he_noise = c.p.enable_noise && c.noise_t != nullptr && hch < c.noise_nch;
+        he = c.p.he_mult != 0 || he_noise || c.zle_thr[hch] > c.p.baseline;
+    }
     if (he) {
         h.channel = c.p.he_first + ch;
         h.mult = c.p.he_mult;
@@ -283,6 +304,8 @@ __global__ void k_group_noise(int64_t n_groups, DeviceConfig c, const int64_t *g
     if (lo != LLONG_MAX) {
         int64_t left = lo - c.p.trigger_window, right = hi + c.p.trigger_window;
         if (right - left >= kMaxGroupSamples) scalars[S_ERR] = WFS_E_PULSE_CACHE_TOO_LONG;
+        atomicMin((long long *)&scalars[S_MINSAMPLE], (long long)left);
+        atomicMax((long long *)&scalars[S_MAXSAMPLE], (long long)(right + 1));
     }
     int64_t ix = 0;
     if (ix_in) {
@@ -301,19 +324,21 @@ __global__ void k_group_noise(int64_t n_groups, DeviceConfig c, const int64_t *g
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_digitize: one CTA per (window, tile).
+// k_digitize: ONE THREAD per block of 8 consecutive samples of a (group, channel) window.
+//   * the thread walks the photons of every pulse of its window in time order exactly like
+//     Pulse.add_current (pulse.py:301-318) -- equal-ns photons merged, then tap (s - q) of the
+//     template times the merged gain added to its samples, mul and add unfused;
+//   * one rounding per (pulse call, channel), integer sum over pulses (rawdata.py:236-239);
+//   * noise / baseline / clamp (rawdata.py:398-458), one 16-byte store of 8 int16 samples and one
+//     flag byte (sample < ZLE threshold, rawdata.py:290-296).
+// All lanes do distinct work (no warp-uniform control flow), nothing is staged in shared memory
+// except the 1.8 KB template table; the photons of a window are a few cache lines shared by the
+// ~40 threads of the window.
+// k_zle: ONE THREAD per window runs the hysteresis interval search (utils.py:13-58,
+// rawdata.py:296-308) on the flag bytes.
 // ---------------------------------------------------------------------------------------------
-constexpr int kChunk = 512;                     // photons staged per pass
-constexpr int kSPT = kTile / kDigiThreads;      // samples per thread
-
-__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *a, uint32_t n, uint64_t key) {
-    uint32_t lo = 0, hi = n;
-    while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        if ((uint64_t)a[mid] < key) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
+constexpr int kDigiThreads = 256;
+constexpr int kNeg = -(1 << 29);
 
 __device__ __forceinline__ int64_t lower_bound_i64(const int64_t *a, int64_t lo, int64_t hi, int64_t key) {
     while (lo < hi) {
@@ -323,165 +348,129 @@ __device__ __forceinline__ int64_t lower_bound_i64(const int64_t *a, int64_t lo,
     return lo;
 }
 
+__device__ __forceinline__ uint32_t udiv_dt(uint32_t x, int dt) {
+    return dt == 10 ? x / 10u : x / (uint32_t)dt;   // constant divisor -> multiply-high
+}
+
+// For every digitize CTA (kDigiThreads consecutive 8-sample blocks) the window owning its first
+// block, so the CTA needs no search.  One thread per window.
+__global__ void k_cta_index(int64_t n_wtot, const uint64_t *__restrict__ win_off, uint32_t *cta_first) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_wtot) return;
+    const int64_t b0 = (int64_t)(uint32_t)win_off[w], b1 = (int64_t)(uint32_t)win_off[w + 1];
+    if (b1 <= b0) return;
+    for (int64_t cta = (b0 + kDigiThreads - 1) / kDigiThreads; cta * kDigiThreads < b1; cta++)
+        cta_first[cta] = (uint32_t)w;
+}
+
 __global__ void __launch_bounds__(kDigiThreads)
-k_digitize(int64_t n_tiles, int64_t n_wtot, DeviceConfig c, const WinMeta *__restrict__ meta,
-           const uint64_t *__restrict__ win_off /* tiles in low 32 */, const int64_t *__restrict__ st,
-           const double *__restrict__ sg, const uint32_t *__restrict__ pulse_first,
-           const int64_t *__restrict__ pulse_lr, const int64_t *__restrict__ group_ix,
-           int16_t *__restrict__ dense, uint32_t *__restrict__ zflags) {
-    __shared__ int32_t acc[kTile];
-    __shared__ uint32_t s_key[kChunk];
-    __shared__ double s_gain[kChunk];
+k_digitize(int64_t n_blocks, int64_t n_wtot, DeviceConfig c, const WinMeta *__restrict__ meta,
+           const uint32_t *__restrict__ cta_first,
+           const uint64_t *__restrict__ win_off /* low 32: first 8-sample block */,
+           const int64_t *__restrict__ st, const double *__restrict__ sg,
+           const uint32_t *__restrict__ pulse_first, const int64_t *__restrict__ group_ix,
+           int16_t *__restrict__ dense, uint8_t *__restrict__ flag8) {
     __shared__ double s_tmpl[16 * 32];
-    __shared__ int64_t s_range[2];
-    const int tid = threadIdx.x;
+    __shared__ uint32_t s_woff[64];
     const int dt = c.p.dt, tlen = c.p.template_length;
-    for (int i = tid; i < dt * tlen; i += kDigiThreads) s_tmpl[i] = c.templates[i];
-
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // locate the window owning this tile
-        int64_t lo = 0, hi = n_wtot;
-        while (lo < hi) {   // last w with (uint32)win_off[w] <= tile
+    for (int i = threadIdx.x; i < dt * tlen; i += blockDim.x) s_tmpl[i] = c.templates[i];
+    const int64_t b0 = (int64_t)blockIdx.x * kDigiThreads;
+    const int64_t w0 = cta_first[blockIdx.x];
+    // block offsets of the windows this CTA can touch (windows are >= 28 blocks long unless empty)
+    if (threadIdx.x < 64) {
+        int64_t w = w0 + threadIdx.x;
+        s_woff[threadIdx.x] = w <= n_wtot ? (uint32_t)win_off[w] : 0xffffffffu;
+    }
+    __syncthreads();
+    const int64_t blk = b0 + threadIdx.x;
+    if (blk >= n_blocks) return;
+    int k = 0;
+    while (k + 1 < 64 && (int64_t)s_woff[k + 1] <= blk) k++;
+    int64_t w = w0 + k;
+    if (k == 63) {   // more than 63 (empty) windows inside one CTA span: fall back to a search
+        int64_t lo = w, hi = n_wtot;
+        while (lo < hi) {
             int64_t mid = (lo + hi + 1) >> 1;
-            if ((int64_t)(uint32_t)win_off[mid] <= tile) lo = mid; else hi = mid - 1;
+            if ((int64_t)(uint32_t)win_off[mid] <= blk) lo = mid; else hi = mid - 1;
         }
-        const int64_t w = lo;
-        const WinMeta m = meta[w];
-        const int64_t tile0 = (int64_t)(uint32_t)win_off[w];
-        const int tix = (int)(tile - tile0);
-        const int64_t a = m.left + (int64_t)tix * kTile;           // abs sample of tile start
-        const int nsamp = min(kTile, m.len - tix * kTile);
-        __syncthreads();
-        for (int i = tid; i < kTile; i += kDigiThreads) acc[i] = 0;
-        __syncthreads();
-
-        if (m.mult != 0) {
-            for (int p = m.p0; p < m.p1; p++) {
-                const int64_t pl = pulse_lr[2 * (int64_t)p], pr = pulse_lr[2 * (int64_t)p + 1];
-                if (pr < a || pl >= a + nsamp) continue;   // uniform across the CTA
-                if (tid == 0) {
-                    int64_t f0 = pulse_first[p], f1 = pulse_first[p + 1];
-                    // photons with q in [a - tlen + 1, a + nsamp - 1]
-                    s_range[0] = lower_bound_i64(st, f0, f1, (a - tlen + 1) * dt);
-                    s_range[1] = lower_bound_i64(st, f0, f1, (a + nsamp) * dt);
-                }
-                __syncthreads();
-                int64_t c0 = s_range[0];
-                const int64_t cend = s_range[1];
-                double cur[kSPT];
+        w = lo;
+    }
+    const WinMeta m = meta[w];
+    const int s0 = (int)(blk - (int64_t)(uint32_t)win_off[w]) * kBlk;     // first sample (window coords)
+    const int nvalid = min(kBlk, m.len - s0);
+    const int64_t a = m.left + s0;                                         // absolute sample index
+    const int64_t tbase = (a - tlen) * dt;
+    int acc[kBlk];
 #pragma unroll
-                for (int j = 0; j < kSPT; j++) cur[j] = 0.0;
-                while (c0 < cend) {
-                    int64_t c1 = c0 + kChunk < cend ? c0 + kChunk : cend;
-                    if (c1 < cend) {   // do not split a run of equal-ns photons (pulse.py:301-318)
-                        int64_t tb = st[c1];
-                        int64_t c1b = c1;
-                        while (c1b > c0 + 1 && st[c1b - 1] == tb) c1b--;
-                        if (c1b > c0 + 1 || st[c0] != tb) c1 = c1b;
-                    }
-                    const int nph = (int)(c1 - c0);
-                    __syncthreads();
-                    for (int i = tid; i < nph; i += kDigiThreads) {
-                        int64_t t = st[c0 + i];
-                        int64_t q = floordiv(t, dt);
-                        int r = (int)(t - q * dt);
-                        s_key[i] = (uint32_t)((q - a + tlen - 1) * dt + r);
-                        s_gain[i] = sg[c0 + i];
-                    }
-                    __syncthreads();
+    for (int i = 0; i < kBlk; i++) acc[i] = 0;
+    if (m.mult != 0) {
+        const double c2a = c.p.current_2_adc;
+        const int64_t t_lo = (a - tlen + 1) * dt, t_hi = (a + kBlk) * dt;   // photons that reach my samples
+        for (int p = m.p0; p < m.p1; p++) {
+            int64_t lo = pulse_first[p], hi = pulse_first[p + 1];
+            if (hi - lo > 16) {
+                const int64_t f0 = lo, f1 = hi;
+                lo = lower_bound_i64(st, f0, f1, t_lo);
+                hi = lower_bound_i64(st, lo, f1, t_hi);
+            }
+            double cur[kBlk];
 #pragma unroll
-                    for (int j = 0; j < kSPT; j++) {
-                        const int s = j * kDigiThreads + tid;
-                        if (s < nsamp) {
-                            uint32_t i = lower_bound_u32(s_key, nph, (uint64_t)s * dt);
-                            const uint32_t kend = (uint32_t)(s + tlen) * dt;
-                            double v = cur[j];
-                            while (i < (uint32_t)nph) {
-                                uint32_t kk = s_key[i];
-                                if (kk >= kend) break;
-                                double g = s_gain[i];
-                                i++;
-                                while (i < (uint32_t)nph && s_key[i] == kk) {
-                                    g = __dadd_rn(g, s_gain[i]);
-                                    i++;
-                                }
-                                int qs = kk / dt, r = kk - qs * dt;
-                                v = __dadd_rn(v, __dmul_rn(s_tmpl[r * tlen + (s - qs + tlen - 1)], g));
-                            }
-                            cur[j] = v;
-                        }
-                    }
-                    c0 = c1;
-                }
-                // one rounding per (pulse call, channel): rawdata.py:236-239
+            for (int i = 0; i < kBlk; i++) cur[i] = 0.0;
+            bool any = false;
+            int64_t i = lo;
+            while (i < hi) {
+                const int64_t t = st[i];
+                double g = sg[i];
+                i++;
+                while (i < hi && st[i] == t) { g = __dadd_rn(g, sg[i]); i++; }   // equal-ns merge
+                if (t < t_lo || t >= t_hi) continue;
+                const uint32_t rel = (uint32_t)(t - tbase);
+                const uint32_t q2 = udiv_dt(rel, dt);
+                const int r = (int)(rel - q2 * (uint32_t)dt);
+                const int first = (int)q2 - tlen;          // my sample index of template tap 0
+                const double *tm = s_tmpl + r * tlen;
+                any = true;
 #pragma unroll
-                for (int j = 0; j < kSPT; j++) {
-                    const int s = j * kDigiThreads + tid;
-                    const int64_t sa = a + s;
-                    if (s < nsamp && sa >= pl && sa <= pr) {
-                        long long adc = -(long long)rint(__dmul_rn(cur[j], c.p.current_2_adc));
-                        acc[s] += (int32_t)(adc * m.mult);
-                    }
+                for (int j = 0; j < kBlk; j++) {
+                    const int tap = j - first;
+                    if (tap >= 0 && tap < tlen) cur[j] = __dadd_rn(cur[j], __dmul_rn(tm[tap], g));
                 }
-                __syncthreads();
+            }
+            if (any) {   // one rounding per (pulse call, channel)
+#pragma unroll
+                for (int j = 0; j < kBlk; j++) acc[j] -= __double2int_rn(__dmul_rn(cur[j], c2a)) * m.mult;
             }
         }
-        // noise (rawdata.py:398-437), baseline (:439-447), clamp (:449-458), ZLE flag (:290-296)
-        const bool noisy = c.p.enable_noise && c.noise_t != nullptr && m.channel < c.noise_nch;
-        const int64_t ixr = noisy ? group_ix[m.group] : 0;
-        const int thr = c.zle_thr[m.channel];
-        int16_t *out = dense + tile * kTile;
-        uint32_t *fl = zflags + tile * (kTile / 32);
+    }
+    // noise, baseline, clamp, ZLE flag, packed int16 store
+    const bool noisy = c.p.enable_noise && c.noise_t != nullptr && m.channel < c.noise_nch;
+    const int thr = c.zle_thr[m.channel];
+    const int baseline = c.p.baseline;
+    int64_t ix = 0;
+    const double *noise_row = nullptr;
+    if (noisy) {
+        ix = group_ix[m.group] + s0;
+        noise_row = c.noise_t + (int64_t)m.channel * c.noise_len;
+        if (ix >= c.noise_len) ix -= c.noise_len * (ix / c.noise_len);
+    }
+    uint32_t flags = 0;
+    uint32_t packed[kBlk / 2];
 #pragma unroll
-        for (int j = 0; j < kSPT; j++) {
-            const int s = j * kDigiThreads + tid;
-            bool flag = false;
-            if (s < nsamp) {
-                long long v = acc[s];
-                if (noisy) {
-                    int64_t ix = ixr + (int64_t)tix * kTile + s;
-                    if (ix >= c.noise_len) ix -= c.noise_len * (ix / c.noise_len);
-                    v = (long long)((double)v + c.noise_t[(int64_t)m.channel * c.noise_len + ix]);
-                }
-                v += c.p.baseline;
-                if (v < 0) v = 0;
-                flag = v < thr;
-                out[s] = (int16_t)v;
-            }
-            unsigned word = __ballot_sync(0xffffffffu, flag);
-            if ((tid & 31) == 0) fl[(j * kDigiThreads + tid) >> 5] = word;
+    for (int j = 0; j < kBlk; j++) {
+        int v = acc[j];
+        if (noisy) {
+            v = __double2int_rz((double)v + noise_row[ix]);
+            if (++ix >= c.noise_len) ix = 0;
         }
+        v += baseline;
+        v = max(v, 0);
+        if (j < nvalid && v < thr) flags |= 1u << j;
+        if (j >= nvalid) v = 0;
+        const uint32_t h = (uint32_t)(uint16_t)(int16_t)v;
+        if (j & 1) packed[j >> 1] |= h << 16; else packed[j >> 1] = h;
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_zle: one warp per window.  An interval starts at a flagged sample whose previous flagged
-// sample is more than `holdoff` away and ends at the flagged sample before the next start
-// (equivalent to the sequential scan of utils.py:13-58); then +-tw, clip, even alignment in
-// channel-local coordinates (rawdata.py:303-308).
-// ---------------------------------------------------------------------------------------------
-constexpr int kNeg = -(1 << 29);
-
-__device__ __forceinline__ int warp_excl_max(int v, int lane) {
-    int incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int u = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl = max(incl, u);
-    }
-    int ex = __shfl_up_sync(0xffffffffu, incl, 1);
-    return lane == 0 ? kNeg : ex;
-}
-
-__device__ __forceinline__ int warp_excl_sum(int v, int lane, int *total) {
-    int incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int u = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += u;
-    }
-    *total = __shfl_sync(0xffffffffu, incl, 31);
-    return incl - v;
+    *reinterpret_cast<uint4 *>(dense + blk * kBlk) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    flag8[blk] = (uint8_t)flags;
 }
 
 __device__ __forceinline__ void emit_interval(int s, int e, const WinMeta &m, int tw, int64_t dense0,
@@ -504,76 +493,59 @@ __device__ __forceinline__ void emit_interval(int s, int e, const WinMeta &m, in
 
 __global__ void __launch_bounds__(128)
 k_zle(int64_t n_wtot, DeviceConfig c, const WinMeta *__restrict__ meta,
-      const uint64_t *__restrict__ win_off, const uint32_t *__restrict__ zflags, Interval *itv,
+      const uint64_t *__restrict__ win_off, const uint8_t *__restrict__ flag8, Interval *itv,
       uint32_t *itv_nrec, uint32_t *group_nitv, int64_t *scalars) {
-    const int lane = threadIdx.x & 31;
-    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= n_wtot) return;
-    const WinMeta m = meta[w];
-    const uint64_t off = win_off[w], off1 = win_off[w + 1];
-    const int64_t slot0 = (int64_t)(off >> 32);
-    const int cap = (int)((off1 >> 32) - (off >> 32));
-    if (m.len == 0) return;
-    const int64_t tile0 = (int64_t)(uint32_t)off;
-    const uint32_t *fw = zflags + tile0 * (kTile / 32);
-    const int64_t dense0 = tile0 * kTile;
-    const int nwords = (m.len + 31) >> 5;
-    const int H = 2 * c.p.trigger_window + 1, tw = c.p.trigger_window;
-    int carry_last = kNeg, carry_start = kNeg, n_emitted = 0;
-    for (int c0 = 0; c0 < nwords; c0 += 32) {
-        const int wi = c0 + lane;
-        const uint32_t word = wi < nwords ? fw[wi] : 0u;
-        const int base = wi * 32;
-        const int lastpos = word ? base + 31 - __clz(word) : kNeg;
-        int pl = max(warp_excl_max(lastpos, lane), carry_last);
-        // pass 1: breaks in this word
-        uint32_t rising = word & ~(word << 1);
-        int nbreak = 0, lastbreak = kNeg;
-        for (uint32_t rb = rising; rb; rb &= rb - 1) {
-            int b = __ffs(rb) - 1;
-            uint32_t below = word & ((1u << b) - 1u);
-            int prev = below ? base + 31 - __clz(below) : pl;
-            if (base + b - prev > H) { nbreak++; lastbreak = base + b; }
-        }
-        int ps = max(warp_excl_max(lastbreak, lane), carry_start);
-        // an emission happens at every break that closes an open interval
-        int nem = nbreak - ((word != 0u && pl == kNeg && nbreak > 0) ? 1 : 0);
-        int tot;
-        int eoff = warp_excl_sum(nem, lane, &tot) + n_emitted;
-        // pass 2: emit closed intervals
-        int cur_start = ps;
-        for (uint32_t rb = rising; rb; rb &= rb - 1) {
-            int b = __ffs(rb) - 1;
-            uint32_t below = word & ((1u << b) - 1u);
-            int prev = below ? base + 31 - __clz(below) : pl;
-            if (base + b - prev > H) {
-                if (prev != kNeg) {
-                    if (eoff < cap) emit_interval(cur_start, prev, m, tw, dense0, itv, itv_nrec, slot0 + eoff);
-                    eoff++;
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int n_emitted = 0, len = 0;
+    if (w < n_wtot) {
+        const WinMeta m = meta[w];
+        len = m.len;
+        if (m.len > 0) {
+            const uint64_t off = win_off[w], off1 = win_off[w + 1];
+            const int64_t blk0 = (int64_t)(uint32_t)off, slot0 = (int64_t)(off >> 32);
+            const int cap = (int)((off1 >> 32) - (off >> 32));
+            const int64_t dense0 = blk0 * kBlk;
+            const int nblk = (m.len + kBlk - 1) / kBlk;
+            const int tw = c.p.trigger_window, H = 2 * tw + 1;
+            int last = kNeg, start = kNeg;
+            const uint8_t *f = flag8 + blk0;
+            for (int b = 0; b < nblk; b++) {
+                uint32_t byte = f[b];
+                while (byte) {
+                    const int pos = b * kBlk + __ffs(byte) - 1;
+                    if (last == kNeg) start = pos;
+                    else if (pos - last > H) {
+                        if (n_emitted < cap) emit_interval(start, last, m, tw, dense0, itv, itv_nrec, slot0 + n_emitted);
+                        n_emitted++;
+                        start = pos;
+                    }
+                    // consecutive flagged samples never open an interval: jump to the run's end
+                    const uint32_t run = byte | (byte - 1);         // fill below the lowest set bit
+                    const uint32_t stop = ~run & (run + 1);         // lowest clear bit above the run
+                    const int run_end = stop > 0xffu || stop == 0 ? 7 : __ffs(stop) - 2;
+                    last = b * kBlk + run_end;
+                    byte &= ~((2u << run_end) - 1u);
                 }
-                cur_start = base + b;
             }
+            if (last != kNeg) {
+                if (n_emitted < cap) emit_interval(start, last, m, tw, dense0, itv, itv_nrec, slot0 + n_emitted);
+                n_emitted++;
+            }
+            if (n_emitted > cap) scalars[S_ERR] = WFS_E_ARG;   // cannot happen: cap is an upper bound
+            if (n_emitted) atomicAdd(&group_nitv[m.group], (uint32_t)n_emitted);
+            for (int k = n_emitted; k < cap; k++) itv_nrec[slot0 + k] = 0;   // unused slots
         }
-        n_emitted += tot;
-        // carries for the next chunk of 32 words
-        int incl_last = max(pl, lastpos), incl_start = max(ps, lastbreak);
-        carry_last = __shfl_sync(0xffffffffu, incl_last, 31);
-        carry_start = __shfl_sync(0xffffffffu, incl_start, 31);
     }
-    if (lane == 0) {
-        if (carry_last != kNeg) {   // close the last interval at the last flagged sample
-            if (n_emitted < cap) emit_interval(carry_start, carry_last, m, tw, dense0, itv, itv_nrec, slot0 + n_emitted);
-            n_emitted++;
-        }
-        if (n_emitted > cap) scalars[S_ERR] = WFS_E_ARG;   // cannot happen: cap is an upper bound
-        if (n_emitted) {
-            atomicAdd(&group_nitv[m.group], (uint32_t)n_emitted);
-            atomicAdd((unsigned long long *)&scalars[S_NITV], (unsigned long long)n_emitted);
-        }
-        atomicAdd((unsigned long long *)&scalars[S_NSAMPLES], (unsigned long long)m.len);
+    // block-level totals
+    unsigned long long ni = n_emitted, ns = len;
+    for (int o = 16; o > 0; o >>= 1) {
+        ni += __shfl_xor_sync(0xffffffffu, ni, o);
+        ns += __shfl_xor_sync(0xffffffffu, ns, o);
     }
-    // unused slots
-    for (int k = n_emitted + lane; k < cap; k += 32) itv_nrec[slot0 + k] = 0;
+    if ((threadIdx.x & 31) == 0 && ns) {
+        atomicAdd((unsigned long long *)&scalars[S_NITV], ni);
+        atomicAdd((unsigned long long *)&scalars[S_NSAMPLES], ns);
+    }
 }
 
 __device__ __forceinline__ int channel_class(int ch, const wfs_params &p) {
@@ -588,8 +560,7 @@ __device__ __forceinline__ int channel_class(int ch, const wfs_params &p) {
 
 __global__ void k_rec_keys(int64_t n_slots, DeviceConfig c, const Interval *itv,
                            const uint32_t *itv_nrec, const uint32_t *itv_rec0, int64_t min_sample,
-                           int time_bits, uint64_t *rec_keys, uint32_t *rec_vals, uint32_t *rec_itv,
-                           int64_t *scalars) {
+                           int time_bits, uint64_t *rec_keys, uint32_t *rec_vals, uint32_t *rec_itv) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_slots) return;
     uint32_t n = itv_nrec[s];
@@ -604,7 +575,19 @@ __global__ void k_rec_keys(int64_t n_slots, DeviceConfig c, const Interval *itv,
         rec_vals[r0 + i] = r0 + i;
         rec_itv[r0 + i] = (uint32_t)s;
     }
-    atomicAdd((unsigned long long *)&scalars[S_CLASS0 + cls], (unsigned long long)n);
+}
+
+// records per data type from the sorted keys (class is the top field of the key)
+__global__ void k_class_counts(int64_t n_rec, const uint64_t *keys, int class_shift, int64_t *scalars) {
+    if (blockIdx.x != 0 || threadIdx.x >= 2) return;
+    const uint64_t want = (uint64_t)(threadIdx.x + 1);
+    int64_t lo = 0, hi = n_rec;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if ((keys[mid] >> class_shift) < want) lo = mid + 1; else hi = mid;
+    }
+    // first index of class 1 and of class 2
+    scalars[threadIdx.x == 0 ? S_CLASS1 : S_CLASS2] = lo;
 }
 
 // One warp per output record, records written at their final sorted position.
@@ -690,8 +673,8 @@ Backend::~Backend() {
 void Backend::release() {
     DevBuf *all[] = {&keys_, &vals_, &st_, &sg_, &flags64_, &pulse_first_, &pulse_left_, &pulse_win_,
                      &win_first_pulse_, &win_meta_, &win_scan_, &group_tmin_, &group_lr_, &scalars_,
-                     &dense_, &zflags_, &itv_, &itv_nrec_, &itv_rec0_, &rec_keys_, &rec_vals_,
-                     &rec_itv_, &group_nitv_, &group_ix_};
+                     &dense_, &itv_, &itv_nrec_, &itv_rec0_, &rec_keys_, &rec_vals_,
+                     &rec_itv_, &group_nitv_, &group_ix_, &pstart_, &flag8_, &cta_first_};
     for (DevBuf *b : all) b->release();
     prim_.release();
 }
@@ -735,12 +718,13 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
         st_.reserve(sizeof(int64_t) * n);
         sg_.reserve(sizeof(double) * n);
         flags64_.reserve(sizeof(uint64_t) * (n + 1));
+        pstart_.reserve((size_t)n + 1);
         LAUNCH(k_group_tmin, div_up(n, T), T, b, c, group_tmin_.as<int64_t>());
         LAUNCH(k_build_keys, div_up(n, T), T, b, c, kl, group_tmin_.as<int64_t>(),
                keys_.as<uint64_t>(), vals_.as<uint32_t>(), scal);
         prim_.sort_pairs(keys_.as<uint64_t>(), vals_.as<uint32_t>(), n, kl.total_bits);
         LAUNCH(k_gather_flags, div_up(n, T), T, b, kl, keys_.as<uint64_t>(), vals_.as<uint32_t>(),
-               st_.as<int64_t>(), sg_.as<double>(), flags64_.as<uint64_t>(), scal);
+               st_.as<int64_t>(), sg_.as<double>(), flags64_.as<uint64_t>(), pstart_.as<uint8_t>(), scal);
         // positions: reuse the (now consumed) alt key buffer of the sort for the scan output
         DevBuf &posbuf = prim_.sort_keys_alt;
         posbuf.reserve(sizeof(uint64_t) * (n + 1));
@@ -799,21 +783,22 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
         min_sample = h_scalars_[S_MINSAMPLE];
         max_sample = h_scalars_[S_MAXSAMPLE];
         res.n_tiles = n_tiles;
-        dense_.reserve(sizeof(int16_t) * n_tiles * kTile);
-        zflags_.reserve(sizeof(uint32_t) * n_tiles * (kTile / 32));
+        dense_.reserve(sizeof(int16_t) * n_tiles * kBlk + 64);
+        flag8_.reserve((size_t)n_tiles + 64);
         itv_.reserve(sizeof(Interval) * n_slots);
         itv_nrec_.reserve(sizeof(uint32_t) * (n_slots + 1));
         itv_rec0_.reserve(sizeof(uint32_t) * (n_slots + 1));
         WFS_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
-        int grid = (int)std::min<int64_t>(n_tiles, (int64_t)kNumSMs * 64);
-        LAUNCH(k_digitize, grid, kDigiThreads, n_tiles, nwt, c, win_meta_.as<WinMeta>(),
-               win_scan_.as<uint64_t>(), st_.as<int64_t>(), sg_.as<double>(),
-               pulse_first_.as<uint32_t>(), pulse_left_.as<int64_t>(), group_ix_buf.as<int64_t>(),
-               dense_.as<int16_t>(), zflags_.as<uint32_t>());
+        cta_first_.reserve(sizeof(uint32_t) * (size_t)(div_up(n_tiles, kDigiThreads) + 1));
+        LAUNCH(k_cta_index, div_up(nwt, T), T, nwt, win_scan_.as<uint64_t>(), cta_first_.as<uint32_t>());
+        LAUNCH(k_digitize, div_up(n_tiles, kDigiThreads), kDigiThreads, n_tiles, nwt, c,
+               win_meta_.as<WinMeta>(), cta_first_.as<uint32_t>(), win_scan_.as<uint64_t>(), st_.as<int64_t>(), sg_.as<double>(),
+               pulse_first_.as<uint32_t>(), group_ix_buf.as<int64_t>(), dense_.as<int16_t>(),
+               flag8_.as<uint8_t>());
         WFS_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
-        LAUNCH(k_zle, div_up(nwt * 32, 128), 128, nwt, c, win_meta_.as<WinMeta>(),
-               win_scan_.as<uint64_t>(), zflags_.as<uint32_t>(), itv_.as<Interval>(),
-               itv_nrec_.as<uint32_t>(), group_nitv_.as<uint32_t>(), scal);
+        LAUNCH(k_zle, div_up(nwt, 128), 128, nwt, c, win_meta_.as<WinMeta>(), win_scan_.as<uint64_t>(),
+               flag8_.as<uint8_t>(), itv_.as<Interval>(), itv_nrec_.as<uint32_t>(),
+               group_nitv_.as<uint32_t>(), scal);
         prim_.exclusive_scan_u32(itv_nrec_.as<uint32_t>(), itv_rec0_.as<uint32_t>(), n_slots, true);
         uint32_t nrec32;
         WFS_CUDA_CHECK(cudaMemcpyAsync(&nrec32, itv_rec0_.as<uint32_t>() + n_slots, sizeof(uint32_t),
@@ -835,8 +820,9 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
         rec_itv_.reserve(sizeof(uint32_t) * nrec);
         LAUNCH(k_rec_keys, div_up(n_slots, T), T, n_slots, c, itv_.as<Interval>(),
                itv_nrec_.as<uint32_t>(), itv_rec0_.as<uint32_t>(), min_sample, time_bits,
-               rec_keys_.as<uint64_t>(), rec_vals_.as<uint32_t>(), rec_itv_.as<uint32_t>(), scal);
+               rec_keys_.as<uint64_t>(), rec_vals_.as<uint32_t>(), rec_itv_.as<uint32_t>());
         prim_.sort_pairs(rec_keys_.as<uint64_t>(), rec_vals_.as<uint32_t>(), nrec, key_bits);
+        LAUNCH(k_class_counts, 1, 32, nrec, rec_keys_.as<uint64_t>(), kChannelBits + time_bits, scal);
         LAUNCH(k_pack, div_up(nrec * 32, 256), 256, nrec, c, rec_vals_.as<uint32_t>(),
                rec_itv_.as<uint32_t>(), itv_rec0_.as<uint32_t>(), itv_.as<Interval>(),
                dense_.as<int16_t>(), reinterpret_cast<uint32_t *>(records_out));
@@ -849,7 +835,12 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
     res.n_intervals = h_scalars_[S_NITV];
     res.n_samples = h_scalars_[S_NSAMPLES];
     res.n_windows = nwt;
-    for (int k = 0; k < 3; k++) res.n_rec_class[k] = h_scalars_[S_CLASS0 + k];
+    if (nrec > 0 && nrec <= cap_records) {
+        const int64_t i1 = h_scalars_[S_CLASS1], i2 = h_scalars_[S_CLASS2];
+        res.n_rec_class[0] = i1;
+        res.n_rec_class[1] = i2 - i1;
+        res.n_rec_class[2] = nrec - i2;
+    }
 }
 
 }  // namespace wfs

@@ -5,8 +5,6 @@
 
 namespace wfs {
 
-constexpr int kTile = 512;          // samples per digitize tile (one CTA)
-constexpr int kDigiThreads = 128;
 constexpr int kRelTimeBits = 24;    // ns inside a digitisation group (< 1e6 samples * 10 ns)
 constexpr int kChannelBits = 10;
 constexpr int64_t kMaxGroupSamples = 1000000;  // rawdata.py:219
@@ -73,8 +71,8 @@ private:
     cudaEvent_t ev0_, ev1_;
     int64_t *h_scalars_ = nullptr;   // pinned readback area
     DevBuf keys_, vals_, st_, sg_, flags64_, pulse_first_, pulse_left_, pulse_win_, win_first_pulse_,
-        win_meta_, win_scan_, group_tmin_, group_lr_, scalars_, dense_, zflags_, itv_, itv_nrec_,
-        itv_rec0_, rec_keys_, rec_vals_, rec_itv_, group_nitv_, group_ix_;
+        win_meta_, win_scan_, group_tmin_, group_lr_, scalars_, dense_, itv_, itv_nrec_,
+        itv_rec0_, rec_keys_, rec_vals_, rec_itv_, group_nitv_, group_ix_, pstart_, flag8_, cta_first_;
 };
 
 }  // namespace wfs
