@@ -198,9 +198,11 @@ def run_b200(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms, ms_digi, launches = [], [], 0
+    phases = np.zeros(12)
     for k in range(args.steps):
         c = sim.run_staged(seed=1)
         ms.append(c['ms_total']); ms_digi.append(c['ms_digitize']); launches += c['gpu_launches']
+        phases += np.array(c['ms_phase'])
     barrier()
     clocks = sampler.stop()
     t_dev = float(np.sum(ms)) / 1e3
@@ -223,8 +225,6 @@ def run_b200(args, rank, world, local_rank):
     d2h = 0
     out = None
     for k in range(args.warmup + args.steps):
-        if out is not None and out['_pinned'] is not None:
-            out['_pinned'].free()
         barrier()
         t0 = time.perf_counter()
         out = sim.simulate(inst, seed=1, cap_records=cap, pinned=True)
@@ -240,8 +240,6 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_e2e = float(tt.item())
     e2e_value = n_pe_all * args.steps / t_e2e
-    if out['_pinned'] is not None:
-        out['_pinned'].free()
 
     if rank != 0:
         if world > 1:
@@ -267,6 +265,8 @@ def run_b200(args, rank, world, local_rank):
                 'd2h_bytes_per_step': int(d2h), 'ms_per_step': t_e2e / args.steps * 1e3,
                 'raw_records_gbs': n_rec_all * RECORD_BYTES * args.steps / t_e2e / 1e9},
         'gpu_launches': int(launches_all),
+        'ms_phase_per_step': dict(zip(['frontend', 'photon_sort', 'windows', 'digitize', 'zle', 'record_sort',
+                                       'record_pack', 'host_scheduler_truth'], (phases[:8] / args.steps).round(3).tolist())),
         'path_hbm': {'algorithmic_bytes_per_step': int(balg),
                      'achieved_gbs': balg / (t_dev / args.steps) / 1e9,
                      'frac_of_measured_peak': balg / (t_dev / args.steps) / 1e9 / peak},

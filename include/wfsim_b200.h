@@ -151,6 +151,10 @@ typedef struct wfs_counts {
     double ms_total;                /* CUDA-event time of the device work of this call */
     double ms_digitize;             /* of which: the digitize (superpose+ADC+noise+clip) kernel */
     double ms_h2d, ms_d2h;
+    /* device time per phase, summed over batches (CUDA events on the library stream):
+     * 0 sampling front end, 1 photon keys + sort, 2 pulses/windows, 3 digitize, 4 ZLE,
+     * 5 record keys + sort, 6 record pack, 7 host scheduler + truth (wall clock), 8 record D2H */
+    double ms_phase[12];
 } wfs_counts;
 
 /* Digitisation-group bookkeeping returned to the host-side chunker

@@ -238,6 +238,7 @@ int wfs_simulate_photons(void *handle, int64_t n_photons, const int64_t *t_ns, c
     WFS_CUDA_CHECK(cudaEventElapsedTime(&ms, H->ev_b, H->ev_c)); counts->ms_total = ms;
     WFS_CUDA_CHECK(cudaEventElapsedTime(&ms, H->ev_c, H->ev_d)); counts->ms_d2h = ms;
     counts->ms_digitize = r.ms_digitize;
+    for (int k = 1; k <= 6; k++) counts->ms_phase[k] = r.ms_phase[k];
     for (int k = 0; k < 3; k++) counts->n_records[k] = rc ? 0 : r.n_rec_class[k];
     counts->n_records_total = rc ? 0 : r.n_records;
     counts->n_photons = r.n_valid_photons;

@@ -36,6 +36,10 @@ struct WinMeta {
     int32_t mult;        // 1, or he_mult for HE rows
     int32_t p0, p1;      // pulses [p0, p1) contributing to this window
     uint32_t ph_lo, ph_hi;   // their photons [ph_lo, ph_hi) (contiguous in the sorted arrays)
+    uint32_t blk0;           // first 8-sample block of the window in the dense buffer
+    uint32_t slot0;          // first interval slot
+    int32_t s_first, s_last; // window-local sample range any photon of the window can touch
+    int32_t pad0, pad1;
 };
 
 struct Interval {
@@ -242,6 +246,11 @@ __global__ void k_window_extents(int64_t n_win, DeviceConfig c, const int64_t *s
     m.p1 = (int32_t)p1;
     m.ph_lo = pulse_first[p0];
     m.ph_hi = pulse_first[p1];
+    m.blk0 = m.slot0 = 0;
+    // pulse extents are [q_first - left_margin, q_last + right_margin]: recover the photon samples
+    m.s_first = (int32_t)((lo + c.p.pulse_left_margin) - m.left);
+    m.s_last = (int32_t)((hi - c.p.pulse_right_margin) - m.left) + c.p.template_length - 1;
+    m.pad0 = m.pad1 = 0;
     meta[w] = m;
     const int holdoff = 2 * tw + 1;
     uint64_t tiles = (uint64_t)((len + kBlk - 1) / kBlk);   // 8-sample blocks
@@ -352,83 +361,113 @@ __device__ __forceinline__ uint32_t udiv_dt(uint32_t x, int dt) {
     return dt == 10 ? x / 10u : x / (uint32_t)dt;   // constant divisor -> multiply-high
 }
 
-// For every digitize CTA (kDigiThreads consecutive 8-sample blocks) the window owning its first
-// block, so the CTA needs no search.  One thread per window.
-__global__ void k_cta_index(int64_t n_wtot, const uint64_t *__restrict__ win_off, uint32_t *cta_first) {
+// For every run of 32 consecutive 8-sample blocks (= one digitize warp) the window owning its
+// first block, so no thread needs a search.  One thread per window.
+__global__ void k_cta_index(int64_t n_wtot, const uint64_t *__restrict__ win_off, WinMeta *meta,
+                            uint32_t *cta_first) {
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_wtot) return;
     const int64_t b0 = (int64_t)(uint32_t)win_off[w], b1 = (int64_t)(uint32_t)win_off[w + 1];
+    meta[w].blk0 = (uint32_t)b0;
+    meta[w].slot0 = (uint32_t)(win_off[w] >> 32);
     if (b1 <= b0) return;
-    for (int64_t cta = (b0 + kDigiThreads - 1) / kDigiThreads; cta * kDigiThreads < b1; cta++)
-        cta_first[cta] = (uint32_t)w;
+    for (int64_t g = (b0 + 31) / 32; g * 32 < b1; g++) cta_first[g] = (uint32_t)w;
+}
+
+// Per sorted photon: window-local sample index + ns remainder packed into 32 bits, and -- for the
+// first photon of a run of equal-ns photons of one pulse -- the merged gain (pulse.py:301-318:
+// gains of coincident photons are summed before the template multiply).
+constexpr uint32_t kPhPulseStart = 1u << 31, kPhRunHead = 1u << 30, kPhQMask = (1u << 26) - 1u;
+
+__global__ void k_photon_prep(int64_t n_valid, DeviceConfig c, const int64_t *__restrict__ st,
+                              const double *__restrict__ sg, const uint8_t *__restrict__ pstart,
+                              const uint64_t *__restrict__ pos, const uint32_t *__restrict__ pulse_win,
+                              const WinMeta *__restrict__ meta, uint32_t *__restrict__ phq,
+                              double *__restrict__ gm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_valid) return;
+    const int64_t t = st[i];
+    const bool ps = pstart[i] != 0;
+    const bool head = ps || st[i - (i > 0)] != t || i == 0;
+    const uint32_t p = (uint32_t)pos[i] + (ps ? 1u : 0u) - 1u;
+    const int64_t left = meta[pulse_win[p]].left;
+    const int64_t q = floordiv(t, c.p.dt);
+    const uint32_t r = (uint32_t)(t - q * c.p.dt);
+    uint32_t v = (((uint32_t)(q - left) & kPhQMask) << 4) | r;
+    if (ps) v |= kPhPulseStart;
+    double g = 0.0;
+    if (head) {
+        v |= kPhRunHead;
+        g = sg[i];
+        for (int64_t j = i + 1; j < n_valid && !pstart[j] && st[j] == t; j++) g = __dadd_rn(g, sg[j]);
+    }
+    phq[i] = v;
+    gm[i] = g;
 }
 
 __global__ void __launch_bounds__(kDigiThreads)
 k_digitize(int64_t n_blocks, int64_t n_wtot, DeviceConfig c, const WinMeta *__restrict__ meta,
-           const uint32_t *__restrict__ cta_first,
-           const uint64_t *__restrict__ win_off /* low 32: first 8-sample block */,
-           const int64_t *__restrict__ st, const double *__restrict__ sg,
-           const uint32_t *__restrict__ pulse_first, const int64_t *__restrict__ group_ix,
-           int16_t *__restrict__ dense, uint8_t *__restrict__ flag8) {
+           const uint32_t *__restrict__ cta_first, const uint32_t *__restrict__ phq,
+           const double *__restrict__ gm, const uint32_t *__restrict__ pulse_first,
+           const int64_t *__restrict__ group_ix, int16_t *__restrict__ dense,
+           uint8_t *__restrict__ flag8) {
     __shared__ double s_tmpl[16 * 32];
-    __shared__ uint32_t s_woff[64];
     const int dt = c.p.dt, tlen = c.p.template_length;
     for (int i = threadIdx.x; i < dt * tlen; i += blockDim.x) s_tmpl[i] = c.templates[i];
-    const int64_t b0 = (int64_t)blockIdx.x * kDigiThreads;
-    const int64_t w0 = cta_first[blockIdx.x];
-    // block offsets of the windows this CTA can touch (windows are >= 28 blocks long unless empty)
-    if (threadIdx.x < 64) {
-        int64_t w = w0 + threadIdx.x;
-        s_woff[threadIdx.x] = w <= n_wtot ? (uint32_t)win_off[w] : 0xffffffffu;
-    }
     __syncthreads();
-    const int64_t blk = b0 + threadIdx.x;
+    const int64_t blk = (int64_t)blockIdx.x * kDigiThreads + threadIdx.x;
     if (blk >= n_blocks) return;
-    int k = 0;
-    while (k + 1 < 64 && (int64_t)s_woff[k + 1] <= blk) k++;
-    int64_t w = w0 + k;
-    if (k == 63) {   // more than 63 (empty) windows inside one CTA span: fall back to a search
-        int64_t lo = w, hi = n_wtot;
-        while (lo < hi) {
-            int64_t mid = (lo + hi + 1) >> 1;
-            if ((int64_t)(uint32_t)win_off[mid] <= blk) lo = mid; else hi = mid - 1;
-        }
-        w = lo;
-    }
-    const WinMeta m = meta[w];
-    const int s0 = (int)(blk - (int64_t)(uint32_t)win_off[w]) * kBlk;     // first sample (window coords)
+    // windows are >= 28 blocks long: the 32 blocks of a warp span at most 3 of them
+    int64_t w = cta_first[blk >> 5];
+    WinMeta m = meta[w];
+    while (blk >= (int64_t)m.blk0 + ((m.len + kBlk - 1) / kBlk) && w + 1 < n_wtot) m = meta[++w];
+    const int s0 = (int)(blk - (int64_t)m.blk0) * kBlk;     // first sample (window coords)
     const int nvalid = min(kBlk, m.len - s0);
-    const int64_t a = m.left + s0;                                         // absolute sample index
-    const int64_t tbase = (a - tlen) * dt;
     int acc[kBlk];
 #pragma unroll
     for (int i = 0; i < kBlk; i++) acc[i] = 0;
-    if (m.mult != 0) {
+    bool touched = false;
+    if (m.mult != 0 && s0 + kBlk > m.s_first && s0 <= m.s_last) {
         const double c2a = c.p.current_2_adc;
-        const int64_t t_lo = (a - tlen + 1) * dt, t_hi = (a + kBlk) * dt;   // photons that reach my samples
-        for (int p = m.p0; p < m.p1; p++) {
-            int64_t lo = pulse_first[p], hi = pulse_first[p + 1];
-            if (hi - lo > 16) {
-                const int64_t f0 = lo, f1 = hi;
-                lo = lower_bound_i64(st, f0, f1, t_lo);
-                hi = lower_bound_i64(st, lo, f1, t_hi);
-            }
-            double cur[kBlk];
+        const int q_lo = s0 - (tlen - 1), q_hi = s0 + kBlk - 1;   // photon samples that reach mine
+        double cur[kBlk];
 #pragma unroll
-            for (int i = 0; i < kBlk; i++) cur[i] = 0.0;
-            bool any = false;
-            int64_t i = lo;
-            while (i < hi) {
-                const int64_t t = st[i];
-                double g = sg[i];
-                i++;
-                while (i < hi && st[i] == t) { g = __dadd_rn(g, sg[i]); i++; }   // equal-ns merge
-                if (t < t_lo || t >= t_hi) continue;
-                const uint32_t rel = (uint32_t)(t - tbase);
-                const uint32_t q2 = udiv_dt(rel, dt);
-                const int r = (int)(rel - q2 * (uint32_t)dt);
-                const int first = (int)q2 - tlen;          // my sample index of template tap 0
-                const double *tm = s_tmpl + r * tlen;
+        for (int i = 0; i < kBlk; i++) cur[i] = 0.0;
+        bool any = false;
+        const bool small = (m.ph_hi - m.ph_lo) <= 64;
+        const int np = small ? 1 : (m.p1 - m.p0);
+        for (int pi = 0; pi < np; pi++) {
+            uint32_t lo = m.ph_lo, hi = m.ph_hi;
+            if (!small) {   // many photons: per pulse, jump to the first photon that can reach me
+                const uint32_t f0 = pulse_first[m.p0 + pi], f1 = pulse_first[m.p0 + pi + 1];
+                uint32_t a = f0, b = f1;
+                while (a < b) {
+                    const uint32_t mid = (a + b) >> 1;
+                    if ((int)((phq[mid] >> 4) & kPhQMask) < q_lo) a = mid + 1; else b = mid;
+                }
+                lo = a;
+                hi = f1;
+                // step back to the head of the run `lo` may sit in (same ns => same sample)
+                while (lo > f0 && !(phq[lo] & kPhRunHead)) lo--;
+            }
+            for (uint32_t i = lo; i < hi; i++) {
+                const uint32_t v = phq[i];
+                if ((v & kPhPulseStart) && any) {   // a new Pulse call starts: round the finished one
+#pragma unroll
+                    for (int j = 0; j < kBlk; j++) {
+                        acc[j] -= __double2int_rn(__dmul_rn(cur[j], c2a)) * m.mult;
+                        cur[j] = 0.0;
+                    }
+                    any = false;
+                    touched = true;
+                }
+                if (!(v & kPhRunHead)) continue;
+                const int q = (int)((v >> 4) & kPhQMask);
+                if (q > q_hi) { if (small) continue; else break; }
+                if (q < q_lo) continue;
+                const double g = gm[i];
+                const double *tm = s_tmpl + (v & 15u) * tlen;
+                const int first = q - s0;          // my sample index of template tap 0
                 any = true;
 #pragma unroll
                 for (int j = 0; j < kBlk; j++) {
@@ -436,16 +475,35 @@ k_digitize(int64_t n_blocks, int64_t n_wtot, DeviceConfig c, const WinMeta *__re
                     if (tap >= 0 && tap < tlen) cur[j] = __dadd_rn(cur[j], __dmul_rn(tm[tap], g));
                 }
             }
-            if (any) {   // one rounding per (pulse call, channel)
+            if (any && !small) {   // end of this pulse
 #pragma unroll
-                for (int j = 0; j < kBlk; j++) acc[j] -= __double2int_rn(__dmul_rn(cur[j], c2a)) * m.mult;
+                for (int j = 0; j < kBlk; j++) {
+                    acc[j] -= __double2int_rn(__dmul_rn(cur[j], c2a)) * m.mult;
+                    cur[j] = 0.0;
+                }
+                any = false;
+                touched = true;
             }
+        }
+        if (any) {   // one rounding per (pulse call, channel): rawdata.py:236-239
+            touched = true;
+#pragma unroll
+            for (int j = 0; j < kBlk; j++) acc[j] -= __double2int_rn(__dmul_rn(cur[j], c2a)) * m.mult;
         }
     }
     // noise, baseline, clamp, ZLE flag, packed int16 store
     const bool noisy = c.p.enable_noise && c.noise_t != nullptr && m.channel < c.noise_nch;
     const int thr = c.zle_thr[m.channel];
     const int baseline = c.p.baseline;
+    if (!touched && !noisy && nvalid == kBlk) {
+        // nothing but the baseline in these 8 samples
+        const int v = max(baseline, 0);
+        const uint32_t h = (uint32_t)(uint16_t)(int16_t)v;
+        const uint32_t pw = h | (h << 16);
+        *reinterpret_cast<uint4 *>(dense + blk * kBlk) = make_uint4(pw, pw, pw, pw);
+        flag8[blk] = v < thr ? 0xff : 0;
+        return;
+    }
     int64_t ix = 0;
     const double *noise_row = nullptr;
     if (noisy) {
@@ -558,9 +616,21 @@ __device__ __forceinline__ int channel_class(int ch, const wfs_params &p) {
     return 0;
 }
 
+struct RecDesc {      // everything k_pack needs for one record, 32 bytes
+    int64_t time;     // ns
+    int64_t src;      // first sample in the dense buffer
+    int32_t pulse_length;
+    int32_t length;
+    int16_t channel;
+    int16_t record_i;
+    int32_t pad;
+};
+
+// strax_interface.py:425-436 header fields + the (class, time, channel) sort key of
+// strax.sort_by_time, one thread per interval slot.
 __global__ void k_rec_keys(int64_t n_slots, DeviceConfig c, const Interval *itv,
                            const uint32_t *itv_nrec, const uint32_t *itv_rec0, int64_t min_sample,
-                           int time_bits, uint64_t *rec_keys, uint32_t *rec_vals, uint32_t *rec_itv) {
+                           int time_bits, uint64_t *rec_keys, uint32_t *rec_vals, RecDesc *desc) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_slots) return;
     uint32_t n = itv_nrec[s];
@@ -568,12 +638,22 @@ __global__ void k_rec_keys(int64_t n_slots, DeviceConfig c, const Interval *itv,
     const Interval it = itv[s];
     const uint32_t r0 = itv_rec0[s];
     const int cls = channel_class(it.channel, c.p);
+    const int spr = WFS_SAMPLES_PER_RECORD;
     for (uint32_t i = 0; i < n; i++) {
-        uint64_t trel = (uint64_t)(it.left + (int64_t)WFS_SAMPLES_PER_RECORD * i - min_sample);
+        const int64_t first = it.left + (int64_t)spr * i;
+        uint64_t trel = (uint64_t)(first - min_sample);
         rec_keys[r0 + i] = (uint64_t)it.channel | (trel << kChannelBits) |
                            ((uint64_t)cls << (kChannelBits + time_bits));
         rec_vals[r0 + i] = r0 + i;
-        rec_itv[r0 + i] = (uint32_t)s;
+        RecDesc d;
+        d.time = (int64_t)c.p.dt * first;
+        d.src = it.src + (int64_t)spr * i;
+        d.pulse_length = it.len;
+        d.length = min(it.len, spr * (int)(i + 1)) - spr * (int)i;
+        d.channel = (int16_t)it.channel;
+        d.record_i = (int16_t)i;
+        d.pad = 0;
+        desc[r0 + i] = d;
     }
 }
 
@@ -590,44 +670,62 @@ __global__ void k_class_counts(int64_t n_rec, const uint64_t *keys, int class_sh
     scalars[threadIdx.x == 0 ? S_CLASS1 : S_CLASS2] = lo;
 }
 
-// One warp per output record, records written at their final sorted position.
+// Record packing (strax_interface.py:425-436): 32 records per CTA (4 per warp), assembled in shared
+// memory and written as one contiguous, 16-byte-vectorised span at their final sorted position
+// (244 B = 61 words: 6 header words + 55 data words).
+constexpr int kPackRecs = 32;
 __global__ void __launch_bounds__(256)
 k_pack(int64_t n_rec, DeviceConfig c, const uint32_t *__restrict__ rec_vals,
-       const uint32_t *__restrict__ rec_itv, const uint32_t *__restrict__ itv_rec0,
-       const Interval *__restrict__ itv, const int16_t *__restrict__ dense, uint32_t *__restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (j >= n_rec) return;
-    const uint32_t r = rec_vals[j];
-    const uint32_t s = rec_itv[r];
-    const Interval it = itv[s];
-    const int i = (int)(r - itv_rec0[s]);
-    const int spr = WFS_SAMPLES_PER_RECORD;
-    const int length = min(it.len, spr * (i + 1)) - spr * i;
-    const int64_t time = (int64_t)c.p.dt * (it.left + (int64_t)spr * i);
-    uint32_t *o = out + j * (WFS_RECORD_BYTES / 4);
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(dense + it.src + (int64_t)spr * i);
+       const RecDesc *__restrict__ desc, const int16_t *__restrict__ dense, uint32_t *__restrict__ out) {
+    __shared__ __align__(16) uint32_t s_rec[kPackRecs * 61];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t j0 = (int64_t)blockIdx.x * kPackRecs;
+    const int nhere = (int)min((int64_t)kPackRecs, n_rec - j0);
+    // the 32 descriptors of this CTA are fetched by one warp, one lane each (32 independent
+    // dependent-load chains in flight), then every warp copies its 4 records
+    __shared__ RecDesc s_desc[kPackRecs];
+    if (warp == 0 && lane < nhere) s_desc[lane] = desc[rec_vals[j0 + lane]];
+    __syncthreads();
+    uint32_t v0[4], v1[4];
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
-        int wd = lane + 32 * k;
-        if (wd >= WFS_RECORD_BYTES / 4) break;
-        uint32_t v;
-        if (wd == 0) v = (uint32_t)(uint64_t)time;
-        else if (wd == 1) v = (uint32_t)((uint64_t)time >> 32);
-        else if (wd == 2) v = (uint32_t)length;
-        else if (wd == 3) v = ((uint32_t)(uint16_t)c.p.dt) | ((uint32_t)(uint16_t)it.channel << 16);
-        else if (wd == 4) v = (uint32_t)it.len;
-        else if (wd == 5) v = (uint32_t)(uint16_t)i;   // record_i, baseline = 0
-        else {
-            int s0 = 2 * (wd - 6);
-            v = 0;
-            if (s0 < length) {
-                v = src[wd - 6];
-                if (s0 + 1 >= length) v &= 0xffffu;
-            }
+    for (int k = 0; k < 4; k++) {
+        const int r = warp + 8 * k;
+        v0[k] = v1[k] = 0;
+        if (r < nhere) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(dense + s_desc[r].src);
+            const int length = s_desc[r].length;
+            if (2 * lane < length) v0[k] = src[lane];
+            if (lane + 32 < 55 && 2 * (lane + 32) < length) v1[k] = src[lane + 32];
         }
-        o[wd] = v;
     }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int r = warp + 8 * k;
+        if (r >= nhere) continue;
+        const RecDesc d = s_desc[r];
+        const int length = d.length;
+        uint32_t a0 = v0[k], a1 = v1[k];
+        if (2 * lane + 1 >= length) a0 &= 0xffffu;
+        if (2 * (lane + 32) + 1 >= length) a1 &= 0xffffu;
+        uint32_t h = 0;
+        if (lane == 0) h = (uint32_t)(uint64_t)d.time;
+        else if (lane == 1) h = (uint32_t)((uint64_t)d.time >> 32);
+        else if (lane == 2) h = (uint32_t)length;
+        else if (lane == 3) h = ((uint32_t)(uint16_t)c.p.dt) | ((uint32_t)(uint16_t)d.channel << 16);
+        else if (lane == 4) h = (uint32_t)d.pulse_length;
+        else if (lane == 5) h = (uint32_t)(uint16_t)d.record_i;   // record_i, baseline = 0
+        uint32_t *o = s_rec + r * 61;
+        if (lane < 6) o[lane] = h;
+        o[6 + lane] = a0;
+        if (lane + 32 < 55) o[6 + 32 + lane] = a1;
+    }
+    __syncthreads();
+    // contiguous span of nhere * 244 bytes starting at a 16-byte aligned address (32 * 244 = 488 * 16)
+    uint4 *dst = reinterpret_cast<uint4 *>(out + j0 * 61);
+    const uint4 *srcv = reinterpret_cast<const uint4 *>(s_rec);
+    const int nvec = (nhere * 61) / 4, rem = (nhere * 61) % 4;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = srcv[i];
+    if (threadIdx.x < rem) out[j0 * 61 + nvec * 4 + threadIdx.x] = s_rec[nvec * 4 + threadIdx.x];
 }
 
 __global__ void k_group_info(int64_t n_groups, DeviceConfig c, const int64_t *group_lr,
@@ -660,6 +758,7 @@ Backend::Backend(const DeviceConfig *cfg, cudaStream_t stream, LaunchCounter *lc
     prim_.lc = lc;
     WFS_CUDA_CHECK(cudaEventCreate(&ev0_));
     WFS_CUDA_CHECK(cudaEventCreate(&ev1_));
+    for (int i = 0; i < 8; i++) WFS_CUDA_CHECK(cudaEventCreate(&evp_[i]));
     WFS_CUDA_CHECK(cudaHostAlloc((void **)&h_scalars_, sizeof(int64_t) * S_COUNT, cudaHostAllocDefault));
 }
 
@@ -667,6 +766,7 @@ Backend::~Backend() {
     release();
     cudaEventDestroy(ev0_);
     cudaEventDestroy(ev1_);
+    for (int i = 0; i < 8; i++) cudaEventDestroy(evp_[i]);
     if (h_scalars_) cudaFreeHost(h_scalars_);
 }
 
@@ -674,7 +774,7 @@ void Backend::release() {
     DevBuf *all[] = {&keys_, &vals_, &st_, &sg_, &flags64_, &pulse_first_, &pulse_left_, &pulse_win_,
                      &win_first_pulse_, &win_meta_, &win_scan_, &group_tmin_, &group_lr_, &scalars_,
                      &dense_, &itv_, &itv_nrec_, &itv_rec0_, &rec_keys_, &rec_vals_,
-                     &rec_itv_, &group_nitv_, &group_ix_, &pstart_, &flag8_, &cta_first_};
+                     &rec_itv_, &group_nitv_, &group_ix_, &pstart_, &flag8_, &cta_first_, &phq_};
     for (DevBuf *b : all) b->release();
     prim_.release();
 }
@@ -712,6 +812,7 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
     LAUNCH(k_init, div_up(std::max<int64_t>(ng, S_COUNT), T), T, group_tmin_.as<int64_t>(),
            group_lr_.as<int64_t>(), group_nitv_.as<uint32_t>(), ng, scal);
     int64_t np = 0, nw = 0;
+    WFS_CUDA_CHECK(cudaEventRecord(evp_[0], stream_));
     if (n > 0) {
         keys_.reserve(sizeof(uint64_t) * n);
         vals_.reserve(sizeof(uint32_t) * n);
@@ -723,6 +824,7 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
         LAUNCH(k_build_keys, div_up(n, T), T, b, c, kl, group_tmin_.as<int64_t>(),
                keys_.as<uint64_t>(), vals_.as<uint32_t>(), scal);
         prim_.sort_pairs(keys_.as<uint64_t>(), vals_.as<uint32_t>(), n, kl.total_bits);
+        WFS_CUDA_CHECK(cudaEventRecord(evp_[1], stream_));
         LAUNCH(k_gather_flags, div_up(n, T), T, b, kl, keys_.as<uint64_t>(), vals_.as<uint32_t>(),
                st_.as<int64_t>(), sg_.as<double>(), flags64_.as<uint64_t>(), pstart_.as<uint8_t>(), scal);
         // positions: reuse the (now consumed) alt key buffer of the sort for the scan output
@@ -750,7 +852,7 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
     res.n_windows = 0;
     int64_t n_tiles = 0, n_slots = 0, min_sample = 0, max_sample = 0;
     const bool he_rows = c.p.detector_nt != 0;
-    static_assert(sizeof(WinMeta) == 40, "WinMeta layout");
+    static_assert(sizeof(WinMeta) == 64, "WinMeta layout");
     DevBuf &group_ix_buf = group_ix_;
     group_ix_buf.reserve(sizeof(int64_t) * ng);
     if (nw > 0) {
@@ -789,17 +891,29 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
         itv_nrec_.reserve(sizeof(uint32_t) * (n_slots + 1));
         itv_rec0_.reserve(sizeof(uint32_t) * (n_slots + 1));
         WFS_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
-        cta_first_.reserve(sizeof(uint32_t) * (size_t)(div_up(n_tiles, kDigiThreads) + 1));
-        LAUNCH(k_cta_index, div_up(nwt, T), T, nwt, win_scan_.as<uint64_t>(), cta_first_.as<uint32_t>());
+        WFS_CUDA_CHECK(cudaEventRecord(evp_[2], stream_));
+        cta_first_.reserve(sizeof(uint32_t) * (size_t)(div_up(n_tiles, 32) + 1));
+        LAUNCH(k_cta_index, div_up(nwt, T), T, nwt, win_scan_.as<uint64_t>(), win_meta_.as<WinMeta>(),
+               cta_first_.as<uint32_t>());
+        phq_.reserve(sizeof(uint32_t) * (size_t)(n + 1));
+        {
+            const int64_t nv = res.n_valid_photons;
+            if (nv > 0)
+                LAUNCH(k_photon_prep, div_up(nv, T), T, nv, c, st_.as<int64_t>(), sg_.as<double>(),
+                       pstart_.as<uint8_t>(), prim_.sort_keys_alt.as<uint64_t>(), pulse_win_.as<uint32_t>(),
+                       win_meta_.as<WinMeta>(), phq_.as<uint32_t>(), reinterpret_cast<double *>(flags64_.p));
+        }
         LAUNCH(k_digitize, div_up(n_tiles, kDigiThreads), kDigiThreads, n_tiles, nwt, c,
-               win_meta_.as<WinMeta>(), cta_first_.as<uint32_t>(), win_scan_.as<uint64_t>(), st_.as<int64_t>(), sg_.as<double>(),
-               pulse_first_.as<uint32_t>(), group_ix_buf.as<int64_t>(), dense_.as<int16_t>(),
-               flag8_.as<uint8_t>());
+               win_meta_.as<WinMeta>(), cta_first_.as<uint32_t>(), phq_.as<uint32_t>(),
+               reinterpret_cast<const double *>(flags64_.p), pulse_first_.as<uint32_t>(),
+               group_ix_buf.as<int64_t>(), dense_.as<int16_t>(), flag8_.as<uint8_t>());
         WFS_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
+        WFS_CUDA_CHECK(cudaEventRecord(evp_[3], stream_));
         LAUNCH(k_zle, div_up(nwt, 128), 128, nwt, c, win_meta_.as<WinMeta>(), win_scan_.as<uint64_t>(),
                flag8_.as<uint8_t>(), itv_.as<Interval>(), itv_nrec_.as<uint32_t>(),
                group_nitv_.as<uint32_t>(), scal);
         prim_.exclusive_scan_u32(itv_nrec_.as<uint32_t>(), itv_rec0_.as<uint32_t>(), n_slots, true);
+        WFS_CUDA_CHECK(cudaEventRecord(evp_[4], stream_));
         uint32_t nrec32;
         WFS_CUDA_CHECK(cudaMemcpyAsync(&nrec32, itv_rec0_.as<uint32_t>() + n_slots, sizeof(uint32_t),
                                        cudaMemcpyDeviceToHost, stream_));
@@ -817,20 +931,27 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
         if (key_bits > 64) { res.error = WFS_E_KEYBITS; return; }
         rec_keys_.reserve(sizeof(uint64_t) * nrec);
         rec_vals_.reserve(sizeof(uint32_t) * nrec);
-        rec_itv_.reserve(sizeof(uint32_t) * nrec);
+        rec_itv_.reserve(sizeof(RecDesc) * nrec);
         LAUNCH(k_rec_keys, div_up(n_slots, T), T, n_slots, c, itv_.as<Interval>(),
                itv_nrec_.as<uint32_t>(), itv_rec0_.as<uint32_t>(), min_sample, time_bits,
-               rec_keys_.as<uint64_t>(), rec_vals_.as<uint32_t>(), rec_itv_.as<uint32_t>());
+               rec_keys_.as<uint64_t>(), rec_vals_.as<uint32_t>(), rec_itv_.as<RecDesc>());
         prim_.sort_pairs(rec_keys_.as<uint64_t>(), rec_vals_.as<uint32_t>(), nrec, key_bits);
         LAUNCH(k_class_counts, 1, 32, nrec, rec_keys_.as<uint64_t>(), kChannelBits + time_bits, scal);
-        LAUNCH(k_pack, div_up(nrec * 32, 256), 256, nrec, c, rec_vals_.as<uint32_t>(),
-               rec_itv_.as<uint32_t>(), itv_rec0_.as<uint32_t>(), itv_.as<Interval>(),
-               dense_.as<int16_t>(), reinterpret_cast<uint32_t *>(records_out));
+        WFS_CUDA_CHECK(cudaEventRecord(evp_[5], stream_));
+        LAUNCH(k_pack, div_up(nrec, kPackRecs), 256, nrec, c, rec_vals_.as<uint32_t>(),
+               rec_itv_.as<RecDesc>(), dense_.as<int16_t>(), reinterpret_cast<uint32_t *>(records_out));
     }
+    WFS_CUDA_CHECK(cudaEventRecord(evp_[6], stream_));
     WFS_CUDA_CHECK(cudaMemcpyAsync(h_scalars_, scal, sizeof(int64_t) * S_COUNT,
                                    cudaMemcpyDeviceToHost, stream_));
     WFS_CUDA_CHECK(cudaStreamSynchronize(stream_));
     WFS_CUDA_CHECK(cudaGetLastError());
+    {
+        const bool full = nw > 0 && nrec > 0 && nrec <= cap_records;
+        auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, evp_[a], evp_[b]); return ms; };
+        if (n > 0 && nw > 0) { res.ms_phase[1] = el(0, 1); res.ms_phase[2] = el(1, 2); res.ms_phase[3] = el(2, 3); res.ms_phase[4] = el(3, 4); }
+        if (full) { res.ms_phase[5] = el(4, 5); res.ms_phase[6] = el(5, 6); }
+    }
     if (h_scalars_[S_ERR]) res.error = (int)h_scalars_[S_ERR];
     res.n_intervals = h_scalars_[S_NITV];
     res.n_samples = h_scalars_[S_NSAMPLES];

@@ -48,6 +48,7 @@ struct BackendResult {
     int64_t n_intervals = 0, n_records = 0, n_samples = 0;
     int64_t n_rec_class[3] = {0, 0, 0};
     float ms_digitize = 0.f;
+    float ms_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 1 sort, 2 windows, 3 digitize, 4 zle, 5 rec sort, 6 pack
     int error = 0;
 };
 
@@ -69,10 +70,11 @@ private:
     LaunchCounter *lc_;
     Primitives prim_;
     cudaEvent_t ev0_, ev1_;
+    cudaEvent_t evp_[8];
     int64_t *h_scalars_ = nullptr;   // pinned readback area
     DevBuf keys_, vals_, st_, sg_, flags64_, pulse_first_, pulse_left_, pulse_win_, win_first_pulse_,
         win_meta_, win_scan_, group_tmin_, group_lr_, scalars_, dense_, itv_, itv_nrec_,
-        itv_rec0_, rec_keys_, rec_vals_, rec_itv_, group_nitv_, group_ix_, pstart_, flag8_, cta_first_;
+        itv_rec0_, rec_keys_, rec_vals_, rec_itv_, group_nitv_, group_ix_, pstart_, flag8_, cta_first_, phq_;
 };
 
 }  // namespace wfs

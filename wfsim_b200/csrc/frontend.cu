@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <chrono>
 #include <limits>
 #include <unordered_map>
 
@@ -470,6 +471,7 @@ static void simulate_batch(Handle *H, Plan &P, const BatchSpec &bs, uint64_t see
     FLAUNCH(k_pattern_cdf, div_up(nrows, 64), 64, nrows, n_ch, F.b_pattern.as<float>(), H->cfg.gains,
             F.b_cdf.as<double>(), F.b_cdfok.as<int32_t>());
     // ---- pass A: primaries ----
+    WFS_CUDA_CHECK(cudaEventRecord(H->ev_c, s));
     int64_t n_emit = 0, n_ph = 0;
     generate(H, F, seed, 0, nprim, n_emit, n_ph);
     // ---- secondaries: photo-ionisation electrons of the S2 calls (rawdata.py:193-197) ----
@@ -586,9 +588,16 @@ static void simulate_batch(Handle *H, Plan &P, const BatchSpec &bs, uint64_t see
     F.b_acc.reserve(8 * (size_t)ntot * A_COUNT);
     g = make_ctx(F, seed);
     FLAUNCH(k_instr_truth, (unsigned)ntot, 128, g, H->cfg, (uint32_t)ntot, (uint32_t)n_ph, (uint32_t)n_ph);
+    WFS_CUDA_CHECK(cudaEventRecord(H->ev_d, s));
     std::vector<int64_t> acc((size_t)ntot * A_COUNT);
     WFS_CUDA_CHECK(cudaMemcpyAsync(acc.data(), F.b_acc.p, 8 * acc.size(), cudaMemcpyDeviceToHost, s));
     WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+    {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, H->ev_c, H->ev_d);
+        so.counts->ms_phase[0] += ms;
+    }
+    const auto host_t0 = std::chrono::steady_clock::now();
     // ---- host scheduler ----
     SchedIn in;
     in.n_prim = nprim;
@@ -641,6 +650,7 @@ static void simulate_batch(Handle *H, Plan &P, const BatchSpec &bs, uint64_t see
         up(F.b_pcrank, pc_rank.data(), 4 * (size_t)npc);
         WFS_CUDA_CHECK(cudaMemsetAsync(F.b_trig.p, 0, 4 * (size_t)(2 * npc), s));
     }
+    so.counts->ms_phase[7] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
     // ---- back end ----
     PhotonBatch b;
     b.n = n_ph + n_ap;
@@ -666,8 +676,19 @@ static void simulate_batch(Handle *H, Plan &P, const BatchSpec &bs, uint64_t see
     } else {
         cap_here = out && out->records ? std::max<int64_t>(out->cap_records - so.n_rec, 0) : 0;
         if (so.overflow) cap_here = 0;
-        F.b_records.reserve((size_t)WFS_RECORD_BYTES * (size_t)std::max<int64_t>(cap_here, 1));
-        d_rec = F.b_records.as<uint8_t>();
+        // two device buffers: batch k is copied to the host on the copy stream while batch k+1 runs
+        const int par = (int)(so.n_batches & 1);
+        DevBuf &rb = par ? F.b_records2 : F.b_records;
+        if (F.copy_pending[par]) {
+            WFS_CUDA_CHECK(cudaEventSynchronize(F.ev_copy[par]));
+            F.copy_pending[par] = false;
+        }
+        // a batch cannot produce more records than samples / 2; size by a generous estimate and
+        // let the capacity protocol of Backend::run handle the rest
+        const int64_t want = std::min<int64_t>(cap_here, std::max<int64_t>(4 * (n_ph + n_ap) + 65536, (int64_t)(rb.cap / WFS_RECORD_BYTES)));
+        rb.reserve((size_t)WFS_RECORD_BYTES * (size_t)std::max<int64_t>(want, 1));
+        cap_here = std::min<int64_t>(cap_here, (int64_t)(rb.cap / WFS_RECORD_BYTES));
+        d_rec = rb.as<uint8_t>();
     }
     if (ngroups > 0) {
         H->backend->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res);
@@ -676,11 +697,16 @@ static void simulate_batch(Handle *H, Plan &P, const BatchSpec &bs, uint64_t see
                                                                     : "back end error (key bits)";
             throw std::runtime_error(H->last_error);
         }
-        if (so.resident && res.n_records > cap_here) {   // grow the resident buffer and redo the batch
-            F.b_records.reserve((size_t)WFS_RECORD_BYTES * (size_t)res.n_records);
-            cap_here = (int64_t)(F.b_records.cap / WFS_RECORD_BYTES);
+        const int64_t user_room = so.resident ? (int64_t(1) << 40)
+                                               : (out && out->records && !so.overflow ? out->cap_records - so.n_rec : 0);
+        if (res.n_records > cap_here && res.n_records <= user_room) {
+            // the device buffer was too small (not the caller's): grow it and redo the back end
+            DevBuf &rb = so.resident ? F.b_records : ((so.n_batches & 1) ? F.b_records2 : F.b_records);
+            rb.reserve((size_t)WFS_RECORD_BYTES * (size_t)res.n_records);
+            cap_here = std::min<int64_t>(user_room, (int64_t)(rb.cap / WFS_RECORD_BYTES));
+            d_rec = rb.as<uint8_t>();
             WFS_CUDA_CHECK(cudaMemsetAsync(F.b_trig.p, 0, 4 * (size_t)std::max<int64_t>(2 * npc, 1), s));
-            H->backend->run(b, F.b_records.as<uint8_t>(), cap_here, F.b_groups.as<wfs_group_info>(), res);
+            H->backend->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res);
         }
     }
     // ---- outputs ----
@@ -688,9 +714,21 @@ static void simulate_batch(Handle *H, Plan &P, const BatchSpec &bs, uint64_t see
     const bool fits = res.n_records <= cap_here;
     if (!so.resident) {
         if (!fits) so.overflow = true;
-        if (fits && res.n_records > 0)
+        if (fits && res.n_records > 0) {
+            const int par = (int)(so.n_batches & 1);
+            if (!F.ev_ready) {
+                WFS_CUDA_CHECK(cudaEventCreateWithFlags(&F.ev_ready, cudaEventDisableTiming));
+                WFS_CUDA_CHECK(cudaEventCreateWithFlags(&F.ev_copy[0], cudaEventDisableTiming));
+                WFS_CUDA_CHECK(cudaEventCreateWithFlags(&F.ev_copy[1], cudaEventDisableTiming));
+            }
+            WFS_CUDA_CHECK(cudaEventRecord(F.ev_ready, s));
+            WFS_CUDA_CHECK(cudaStreamWaitEvent(H->copy_stream, F.ev_ready, 0));
             WFS_CUDA_CHECK(cudaMemcpyAsync(out->records + (size_t)so.n_rec * WFS_RECORD_BYTES, d_rec,
-                                           (size_t)res.n_records * WFS_RECORD_BYTES, cudaMemcpyDeviceToHost, s));
+                                           (size_t)res.n_records * WFS_RECORD_BYTES, cudaMemcpyDeviceToHost,
+                                           H->copy_stream));
+            WFS_CUDA_CHECK(cudaEventRecord(F.ev_copy[par], H->copy_stream));
+            F.copy_pending[par] = true;
+        }
     }
     std::vector<wfs_group_info> h_groups((size_t)ngroups);
     if (ngroups)
@@ -759,6 +797,7 @@ static void simulate_batch(Handle *H, Plan &P, const BatchSpec &bs, uint64_t see
     cn->n_pulse_calls += nruns;
     cn->n_instructions += ntot;
     cn->ms_digitize += res.ms_digitize;
+    for (int k = 1; k <= 6; k++) cn->ms_phase[k] += res.ms_phase[k];
 }
 
 static int run_plan(Handle *H, Plan &P, uint64_t seed, wfs_outputs *out, wfs_counts *counts, bool resident,
@@ -777,6 +816,8 @@ static int run_plan(Handle *H, Plan &P, uint64_t seed, wfs_outputs *out, wfs_cou
     for (const BatchSpec &bs : P.batches) simulate_batch(H, P, bs, seed, so, group_base);
     WFS_CUDA_CHECK(cudaEventRecord(H->ev_b, s));
     WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+    WFS_CUDA_CHECK(cudaStreamSynchronize(H->copy_stream));
+    H->frontend->copy_pending[0] = H->frontend->copy_pending[1] = false;
     float ms;
     WFS_CUDA_CHECK(cudaEventElapsedTime(&ms, H->ev_a, H->ev_b));
     counts->ms_total = ms;
@@ -863,7 +904,7 @@ void Handle::frontend_release() {
                      &F.b_nhits, &F.b_acc, &F.b_cdf, &F.b_cdfok, &F.b_pattern, &F.b_et, &F.b_einstr,
                      &F.b_enph, &F.b_ephoff, &F.b_pht, &F.b_phch, &F.b_phgain, &F.b_phinstr, &F.b_phflags,
                      &F.b_phnap, &F.b_apoff, &F.b_picount, &F.b_pioff, &F.b_irun, &F.b_pcgroup,
-                     &F.b_pcrank, &F.b_trig, &F.b_records, &F.b_groups, &F.b_scal};
+                     &F.b_pcrank, &F.b_trig, &F.b_records, &F.b_records2, &F.b_groups, &F.b_scal};
     for (DevBuf *b : all) b->release();
     F.prim.release();
     delete reinterpret_cast<Plan *>(staged_plan);

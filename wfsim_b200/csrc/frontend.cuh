@@ -79,8 +79,10 @@ struct Frontend {
     DevBuf b_itype, b_itime, b_ix, b_iy, b_iz, b_iamp, b_igidx, b_ilce, b_iscg, b_icy, b_ipat,
         b_dmean, b_dspread, b_nemit, b_emitoff, b_nhits, b_acc, b_cdf, b_cdfok, b_pattern,
         b_et, b_einstr, b_enph, b_ephoff, b_pht, b_phch, b_phgain, b_phinstr, b_phflags, b_phnap,
-        b_apoff, b_picount, b_pioff, b_irun, b_pcgroup, b_pcrank, b_trig, b_records, b_groups,
-        b_scal;
+        b_apoff, b_picount, b_pioff, b_irun, b_pcgroup, b_pcrank, b_trig, b_records, b_records2,
+        b_groups, b_scal;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_ready = nullptr;
+    bool copy_pending[2] = {false, false};
     int64_t *h_pin = nullptr;   // pinned scratch for small readbacks
     // staged instructions (device-resident measurement mode)
     std::vector<uint8_t> staged_instr;

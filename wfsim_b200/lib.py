@@ -76,11 +76,13 @@ class Counts(C.Structure):
                     'n_intervals', 'n_samples', 'n_groups', 'n_pulse_calls', 'n_instructions',
                     'n_batches', 'gpu_launches', 'need_records', 'need_truth', 'need_groups',
                     'need_batches')]
-                + [(n, f64) for n in ('ms_total', 'ms_digitize', 'ms_h2d', 'ms_d2h')])
+                + [(n, f64) for n in ('ms_total', 'ms_digitize', 'ms_h2d', 'ms_d2h')]
+                + [('ms_phase', f64 * 12)])
 
     def as_dict(self):
-        d = {n: getattr(self, n) for n, _ in self._fields_ if n != 'n_records'}
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n not in ('n_records', 'ms_phase')}
         d['n_records'] = list(self.n_records)
+        d['ms_phase'] = list(self.ms_phase)
         return d
 
 

@@ -64,8 +64,12 @@ class Simulator:
         self.handle = h
         self.device = device
         self.last_counts = None
+        self._pinned_cache = None      # reusable pinned record buffer (pinning is slow)
 
     def close(self):
+        if getattr(self, '_pinned_cache', None) is not None:
+            self._pinned_cache.free()
+            self._pinned_cache = None
         if getattr(self, 'handle', None):
             self.lib.wfs_destroy(self.handle)
             self.handle = None
@@ -148,6 +152,16 @@ class Simulator:
         m.s2_sc_gain_default = 0.0
         return m, keep
 
+    def _pinned_records(self, cap):
+        """Pinned host buffer for `cap` records, reused across calls (grow-only).  The arrays
+        returned by simulate(pinned=True) are views into it and are overwritten by the next call."""
+        c = self._pinned_cache
+        if c is None or len(c.array) < cap:
+            if c is not None:
+                c.free()
+            self._pinned_cache = c = PinnedArray(self.lib, int(cap * 1.05) + 1024, raw_record_dtype())
+        return c
+
     def simulate(self, instructions, seed=0, maps=None, cap_records=None, pinned=False):
         """Full path for one set of instructions (see wfs_simulate in the header).
 
@@ -166,8 +180,9 @@ class Simulator:
         tdt = truth_dtype()
         gdt = np.dtype([('left', np.int64), ('right', np.int64), ('n_intervals', np.int64)])
         while True:
-            holder = PinnedArray(self.lib, cap_rec, raw_record_dtype()) if pinned else None
+            holder = self._pinned_records(cap_rec) if pinned else None
             rec = holder.array if pinned else np.empty(cap_rec, raw_record_dtype())
+            cap_rec = len(rec)
             truth = np.zeros(cap_truth, tdt)
             groups = np.zeros(cap_groups, gdt)
             batch_records = np.zeros((cap_batches, 3), np.int64)
@@ -180,8 +195,6 @@ class Simulator:
                 cap_truth = max(cap_truth, int(counts.need_truth))
                 cap_groups = max(cap_groups, int(counts.need_groups))
                 cap_batches = max(cap_batches, int(counts.need_batches))
-                if holder is not None:
-                    holder.free()
                 continue
             if rc != 0:
                 self._raise(rc)
@@ -207,7 +220,7 @@ class Simulator:
                            (np.concatenate(p) for p in parts)))
         res['truth'] = truth[:counts.n_truth]
         res['groups'] = groups[:counts.n_groups]
-        res['_pinned'] = holder
+        res['_pinned'] = None
         return res
 
     def stage(self, instructions, maps=None):
