@@ -64,6 +64,12 @@ def widened_spe_hook(path, fmt):
         cols = {str(i): df['0'] for i in range(1, 494)}
         df = pd.concat([df, pd.DataFrame(cols)], axis=1)
         return df
+    if fmt == 'json.gz' and 'synthetic_ap' in path:
+        from tests.golden.synth_tables import pmt_ap_tables
+        return pmt_ap_tables()
+    if fmt == 'dill' and 'synthetic_ele_ap' in path:
+        from tests.golden.synth_tables import EleApHist
+        return EleApHist()
     return None
 
 
@@ -207,6 +213,12 @@ def main():
                                  'special_thresholds': {'7': 40, '255': 5},
                                  'zle_threshold': 10})
         make_det_case(ref, 'det_noise', seed=13, n_groups=3, with_noise=True)
+    if 'ap' in which:
+        from tests.golden import make_golden_ap
+        make_golden_ap.main(ref, c0_config)
+    if 'chunks' in which:
+        from tests.golden import make_golden_chunks
+        make_golden_chunks.main(ref, c0_config)
     if 'stoch' in which:
         from tests.golden import make_golden_stoch
         make_golden_stoch.main(ref, c0_config)

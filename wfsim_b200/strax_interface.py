@@ -1,0 +1,322 @@
+"""Drop-in host side of the hot path: the interface of wfsim/strax_interface.py with the
+simulator swapped for the B200 library.
+
+Mirrors (names, argument meaning, error behaviour; citations relative to the reference):
+* `ChunkRawRecords`        strax_interface.py:353-504   (chunk cutting, truth selection)
+* `SimulatorPlugin`        strax_interface.py:506-663   (options, set_config, _sort_check, is_ready)
+* `RawRecordsFromFaxNT`    strax_interface.py:665-714   (provides, _setup, check_instructions, compute)
+* `instruction_from_csv`   strax_interface.py:336-350
+* dtypes                   strax_interface.py:25-116     (wfsim_b200/dtypes.py)
+
+With strax/straxen installed the plugin classes derive from strax.Plugin and register in a
+strax.Context exactly like the reference's; without them (this build container) a minimal
+stand-in base class is used so the same compute loop can be exercised by the tests.
+The simulation itself always runs in libwfsim_b200.so (ctypes); there is no CPU fallback.
+"""
+import logging
+
+import numpy as np
+
+from . import config as wcfg
+from .dtypes import (RECORD_LENGTH, extra_truth_dtype_per_pmt, instruction_dtype, raw_record_dtype,
+                     truth_extra_dtype)
+from .resource import Resource
+
+log = logging.getLogger('wfsim_b200.interface')
+
+try:                                    # pragma: no cover - depends on the deployment
+    import strax
+    import straxen
+    HAVE_STRAX = True
+except ImportError:
+    strax = straxen = None
+    HAVE_STRAX = False
+
+__all__ = ['instruction_dtype', 'truth_extra_dtype', 'extra_truth_dtype_per_pmt', 'ChunkRawRecords',
+           'SimulatorPlugin', 'RawRecordsFromFaxNT', 'instruction_from_csv', 'chunk_boundaries']
+
+
+def instruction_from_csv(filename):
+    """Return wfsim instructions from a csv (strax_interface.py:336-350)."""
+    import pandas as pd
+    df = pd.read_csv(filename)
+    recs = np.zeros(len(df), dtype=instruction_dtype)
+    for column in df.columns:
+        recs[column] = df[column]
+    expected_dtype = np.dtype(instruction_dtype)
+    assert recs.dtype == expected_dtype, \
+        f"CSV {filename} produced wrong dtype. Got {recs.dtype}, expected {expected_dtype}."
+    return recs
+
+
+def chunk_boundaries(config, t_min_instruction, groups, time_zero=None):
+    """The chunk_time bookkeeping of ChunkRawRecords.__call__ (strax_interface.py:378-440).
+
+    `groups` holds, per digitisation group in time order, (left, right, n_intervals) -- what the
+    reference reads from RawData.left / RawData.right while iterating the ZLE intervals.  Returns
+    [(chunk_time_pre, chunk_time), ...] in the order the reference yields its chunks."""
+    dt = config['sample_duration']
+    rext = int(config['right_raw_extension'])
+    cksz = int(config['chunk_size'] * 1e9)
+    pre = (time_zero - rext) if time_zero else (int(t_min_instruction) - rext)
+    ct = pre + cksz
+    cur_right = last_right = 0
+    out = []
+    for left, right, n_itv in groups:
+        for _ in range(max(int(n_itv), 0)):
+            if right != cur_right:
+                last_right, cur_right = cur_right, right
+            if left * dt > ct + rext:
+                if (last_right + 1) * dt > ct:
+                    ct += (last_right + 1) * dt - ct
+                out.append((pre, ct))
+                pre = ct
+                ct += cksz
+            else:
+                break
+    last_right = cur_right
+    ct = max((last_right + 1) * dt, pre + dt)
+    out.append((pre, ct))
+    return out
+
+
+class ChunkRawRecords(object):
+    """Same protocol as the reference class: calling the object with the instructions returns a
+    generator of dict(raw_records, raw_records_he, raw_records_aqmon, truth); `chunk_time_pre`
+    and `chunk_time` hold the bounds of the chunk just yielded; `source_finished()`."""
+
+    def __init__(self, config, rawdata_generator=None, resource=None, device=0, seed=None, **kwargs):
+        from .simulator import Simulator
+        self.config = config
+        if resource is None:
+            resource = Resource(config, **{k: kwargs[k] for k in list(kwargs) if k in (
+                'spe_ppf', 'spe_row', 'photon_area_distribution', 'noise_data', 'uniform_to_pmt_ap',
+                'uniform_to_ele_ap')})
+        self.simulator = rawdata_generator(config, resource=resource, device=device) \
+            if rawdata_generator is not None else Simulator(config, resource=resource, device=device)
+        truth_per_n_pmts = self._n_channels if config.get('per_pmt_truth') else False
+        if truth_per_n_pmts:
+            raise NotImplementedError('per_pmt_truth is not produced by the device path yet')
+        self.truth_dtype = extra_truth_dtype_per_pmt(truth_per_n_pmts)
+        self.seed = int(seed if seed is not None else (config.get('seed') or 0))
+        self._finished = False
+        self.chunk_time_pre = self.chunk_time = 0
+
+    def __call__(self, instructions, time_zero=None, **kwargs):
+        samples_per_record = RECORD_LENGTH
+        if len(instructions) == 0:      # Empty (strax_interface.py:374-377)
+            yield from np.array([], dtype=raw_record_dtype(samples_per_record=samples_per_record))
+            self._finished = True
+            return
+        cfg = self.config
+        out = self.simulator.simulate(instructions, seed=self.seed)
+        chunks = chunk_boundaries(cfg, np.min(instructions['time']), out['groups'], time_zero)
+        truth = out['truth']
+        done = {k: 0 for k in ('raw_records', 'raw_records_he', 'raw_records_aqmon')}
+        truth_left = np.ones(len(truth), bool)
+        tdt = np.dtype(instruction_dtype + self.truth_dtype)
+        for i, (pre, ct) in enumerate(chunks):
+            self.chunk_time_pre, self.chunk_time = pre, ct
+            res = {}
+            for k in done:
+                rec = out[k]
+                stop = done[k] + int(np.searchsorted(rec['time'][done[k]:], ct, side='right'))
+                res[k] = rec[done[k]:stop]          # already sorted by (time, channel)
+                done[k] = stop
+            # truth rows of this chunk (strax_interface.py:458-483)
+            tfp = truth['t_first_photon']
+            sel = truth_left & ((tfp <= ct) | (np.isnan(tfp) & (truth['time'] <= ct)))
+            truth_left &= ~sel
+            t = truth[sel]
+            t = t[np.argsort(t['time'], kind='stable')]
+            _truth = np.zeros(len(t), dtype=tdt)
+            for name in _truth.dtype.names:
+                _truth[name] = t[name]
+            has = ~np.isnan(_truth['t_first_photon'])
+            _truth['time'][has] = _truth['t_first_photon'][has].astype(int)
+            _truth = _truth[np.argsort(_truth['time'], kind='stable')]
+            res['truth'] = _truth
+            if i == len(chunks) - 1:
+                self._finished = True
+            if cfg['detector'] in ('XENON1T', 'XENONnT_neutron_veto'):
+                yield dict(raw_records=res['raw_records'], truth=_truth)
+            else:
+                yield res
+
+    def source_finished(self):
+        return self._finished
+
+    @property
+    def _n_channels(self):
+        return len(self.config.get('gains', np.arange(wcfg.N_TPC_PMTS)))
+
+
+# --------------------------------------------------------------------------------------------------
+# plugin layer
+# --------------------------------------------------------------------------------------------------
+_OPTION_DEFAULTS = dict(
+    detector='XENONnT', event_rate=1000, chunk_size=100, n_chunk=10, per_pmt_truth=False,
+    fax_file=None, fax_config='fax_config_nt_design.json', fax_config_override=None,
+    fax_config_override_from_cmt=None, channel_map=None, n_tpc_pmts=wcfg.N_TPC_PMTS,
+    n_top_pmts=wcfg.N_TOP_PMTS, right_raw_extension=100000, seed=False)
+
+if HAVE_STRAX:                                                          # pragma: no cover
+    _PluginBase = strax.Plugin
+
+    def _takes_config(cls):
+        from immutabledict import immutabledict
+        opts = [strax.Option(k, default=v, track=k in ('detector', 'per_pmt_truth'), infer_type=False)
+                for k, v in _OPTION_DEFAULTS.items() if k not in ('channel_map', 'n_tpc_pmts', 'n_top_pmts')]
+        opts += [strax.Option('channel_map', track=False, type=immutabledict),
+                 strax.Option('n_tpc_pmts', track=False, infer_type=False),
+                 strax.Option('n_top_pmts', track=False, infer_type=False)]
+        return strax.takes_config(*opts)(cls)
+else:
+    class _PluginBase:
+        """Tiny stand-in for strax.Plugin: a config dict and `chunk()` returning a plain dict."""
+        provides = tuple()
+
+        def __init__(self, config=None, run_id='0'):
+            self.config = dict(_OPTION_DEFAULTS)
+            self.config.update(config or {})
+            self.run_id = run_id
+
+        def chunk(self, *, start, end, data, data_type=None):
+            return dict(start=start, end=end, data=data, data_type=data_type)
+
+    def _takes_config(cls):
+        return cls
+
+
+@_takes_config
+class SimulatorPlugin(_PluginBase):
+    compressor = 'zstd'
+    depends_on = tuple()
+    rechunk_on_save = False     # Cannot arbitrarily rechunk records inside events
+    parallel = False            # the simulator is a stateful generator (strax_interface.py:544-546)
+    last_chunk_time = -999999999999999
+    input_timeout = 3600
+    gain_model_mc = None        # to_pe per channel; straxen.URLConfig in a straxen deployment
+
+    def setup(self):
+        self.set_config()
+        self.get_instructions()
+        self.check_instructions()
+        self._setup()
+
+    def set_config(self):
+        fax = self.config['fax_config']
+        if isinstance(fax, str):
+            fax = straxen.get_resource(fax, fmt='json') if HAVE_STRAX else wcfg.load_fax_config(fax)
+        to_pe = self.config.get('gain_model_mc', self.gain_model_mc)
+        if to_pe is None or isinstance(to_pe, str):
+            raise ValueError('gain_model_mc must resolve to the to_pe array of the TPC PMTs')
+        self.to_pe = np.asarray(to_pe, dtype=np.float64)
+        opts = {k: self.config[k] for k in _OPTION_DEFAULTS
+                if k in self.config and k not in ('channel_map', 'fax_config', 'fax_config_override')}
+        if self.config.get('channel_map'):
+            opts['channel_map'] = dict(self.config['channel_map'])
+        merged = wcfg.plugin_config(fax, overrides=self.config.get('fax_config_override'), to_pe=self.to_pe,
+                                    **opts)
+        for k, v in self.config.items():
+            merged.setdefault(k, v)
+        self.config = merged
+        if self.config['seed']:
+            np.random.seed(self.config['seed'])
+        if self.config.get('fax_config_override_from_cmt') is not None:
+            raise NotImplementedError('CMT overrides need straxen.get_correction_from_cmt')
+
+    def _setup(self):
+        pass
+
+    def get_instructions(self):
+        pass
+
+    def check_instructions(self):
+        pass
+
+    def _sort_check(self, results):
+        if not isinstance(results, list):
+            results = [results]
+        last_chunk_time = self.last_chunk_time
+        for result in results:
+            if len(result) == 0:
+                continue
+            if result['time'][0] < self.last_chunk_time + 1000:
+                raise RuntimeError(
+                    "Simulator returned chunks with insufficient spacing. "
+                    f"Last chunk's max time was {self.last_chunk_time}, "
+                    f"this chunk's first time is {result['time'][0]}.")
+            if len(result) == 1:
+                continue
+            if np.diff(result['time']).min() < 0:
+                raise RuntimeError("Simulator returned non-sorted records!")
+            last_chunk_time = max(result['time'].max(), self.last_chunk_time)
+        self.last_chunk_time = last_chunk_time
+
+    def is_ready(self, chunk_i):
+        """Flip-flop: False to check source finished, True to get the next chunk."""
+        if 'ready' not in self.__dict__:
+            self.ready = False
+        self.ready ^= True
+        return self.ready
+
+    def source_finished(self):
+        return self.sim.source_finished()
+
+    @property
+    def _n_channels(self):
+        return len(self.config.get('gains', np.arange(wcfg.N_TPC_PMTS)))
+
+    @property
+    def _truth_dtype(self):
+        truth_per_n_pmts = self._n_channels if self.config.get('per_pmt_truth') else False
+        return extra_truth_dtype_per_pmt(truth_per_n_pmts)
+
+
+class RawRecordsFromFaxNT(SimulatorPlugin):
+    provides = ('raw_records', 'raw_records_he', 'raw_records_aqmon', 'truth')
+    data_kind = dict(zip(provides, provides))
+    resource_overrides = None    # extra Resource pieces (spe table, noise, afterpulse tables)
+    device = 0
+
+    def _setup(self):
+        self.sim = ChunkRawRecords(self.config, device=self.device, **(self.resource_overrides or {}))
+        self.sim_iter = self.sim(self.instructions)
+
+    def get_instructions(self):
+        if self.config['fax_file']:
+            assert not self.config['fax_file'].endswith('root'), \
+                'None optical g4 input is deprecated use EPIX instead'
+            assert self.config['fax_file'].endswith('csv'), 'Only csv input is supported'
+            self.instructions = instruction_from_csv(self.config['fax_file'])
+        elif getattr(self, 'instructions', None) is None:
+            raise RuntimeError('rand_instructions needs nestpy (third party); pass instructions or a csv fax_file')
+
+    def check_instructions(self):
+        # Let below cathode S1 instructions pass but remove S2 instructions
+        m = (self.instructions['z'] < - self.config['tpc_length']) & (self.instructions['type'] == 2)
+        self.instructions = self.instructions[~m]
+        r_instr = np.sqrt(self.instructions['x']**2 + self.instructions['y']**2)
+        assert np.all((r_instr < self.config['tpc_radius']) | np.isclose(r_instr, self.config['tpc_radius'])), \
+            "Interaction is outside the TPC (radius)"
+        assert np.all(self.instructions['z'] < 0.25), "Interaction is outside the TPC (in Z)"
+        assert np.all(self.instructions['amp'] > 0), "Interaction has zero size"
+
+    def infer_dtype(self):
+        dtype = {data_type: raw_record_dtype(samples_per_record=RECORD_LENGTH)
+                 for data_type in self.provides if data_type != 'truth'}
+        dtype['truth'] = instruction_dtype + self._truth_dtype
+        return dtype
+
+    def compute(self):
+        try:
+            result = next(self.sim_iter)
+        except StopIteration:
+            raise RuntimeError("Bug in chunk count computation")
+        self._sort_check(result[self.provides[0]])
+        return {data_type: self.chunk(
+            start=self.sim.chunk_time_pre,
+            end=self.sim.chunk_time,
+            data=result[data_type],
+            data_type=data_type) for data_type in self.provides}
