@@ -292,7 +292,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--events', type=int, default=int(os.environ.get('WFS_BENCH_EVENTS', 100000)))
-    ap.add_argument('--ref-events', type=int, default=int(os.environ.get('WFS_BENCH_REF_EVENTS', 100)),
+    ap.add_argument('--ref-events', type=int, default=int(os.environ.get('WFS_BENCH_REF_EVENTS', 1500)),
                     help='events per worker process and step of the CPU baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

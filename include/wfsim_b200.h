@@ -127,6 +127,9 @@ typedef struct wfs_instr_maps {
     const int32_t *pattern_row;     /* [n_instr] row of `pattern` for the instruction; NULL -> row 0 */
     int64_t n_pattern_rows;
     double s2_sc_gain_default;      /* used when s2_sc_gain is NULL */
+    const uint64_t *rng_id;         /* [n_instr] Philox identity of each instruction; NULL -> its index.
+                                     * Shards of one instruction set pass the global indices so that the
+                                     * result does not depend on the sharding. */
 } wfs_instr_maps;
 
 typedef struct wfs_counts {

@@ -159,6 +159,7 @@ struct Plan {
     std::vector<double> lce, scg, cy;
     std::vector<float> pattern;
     std::vector<int32_t> patrow;
+    std::vector<uint64_t> rng_id;
     int64_t pattern_rows = 0;
     double scg_default = 0.0;
 };
@@ -194,6 +195,8 @@ static void make_plan(Handle *H, const uint8_t *rows, int64_t n, const wfs_instr
     P.scg.assign((size_t)n, P.scg_default);
     P.cy.assign((size_t)n, 1.0);
     P.patrow.assign((size_t)n, 0);
+    P.rng_id.resize((size_t)n);
+    for (int64_t i = 0; i < n; i++) P.rng_id[i] = maps && maps->rng_id ? maps->rng_id[i] : (uint64_t)i;
     if (maps && maps->s1_lce) std::copy(maps->s1_lce, maps->s1_lce + n, P.lce.begin());
     if (maps && maps->s2_sc_gain) std::copy(maps->s2_sc_gain, maps->s2_sc_gain + n, P.scg.begin());
     if (maps && maps->s2_cy_extra) std::copy(maps->s2_cy_extra, maps->s2_cy_extra + n, P.cy.begin());
@@ -441,7 +444,7 @@ static void simulate_batch(Handle *H, Plan &P, const BatchSpec &bs, uint64_t see
         const HostInstr &h = P.instr[gi];
         h_type[j] = h.type; h_amp[j] = h.amp; h_time[j] = h.time;
         h_x[j] = h.x; h_y[j] = h.y; h_z[j] = h.z;
-        h_gidx[j] = (uint64_t)gi;
+        h_gidx[j] = P.rng_id[gi];
         h_lce[j] = P.lce[gi]; h_scg[j] = P.scg[gi]; h_cy[j] = P.cy[gi];
         auto it = rowmap.find(P.patrow[gi]);
         if (it == rowmap.end()) {

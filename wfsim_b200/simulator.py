@@ -134,7 +134,7 @@ class Simulator:
         return out
 
     # -----------------------------------------------------------------------------------------
-    def _maps_struct(self, instructions, maps=None):
+    def _maps_struct(self, instructions, maps=None, rng_id=None):
         if maps is None:
             if self.resource is None or isinstance(self.resource, dict):
                 raise SimulatorError('simulate() needs a Resource (maps) -- pass resource= to Simulator')
@@ -150,6 +150,11 @@ class Simulator:
         m.pattern_row = _ptr(keep['pattern_row'])
         m.n_pattern_rows = keep['pattern'].shape[0]
         m.s2_sc_gain_default = 0.0
+        if rng_id is not None:
+            keep['rng_id'] = np.ascontiguousarray(rng_id, np.uint64)
+            if len(keep['rng_id']) != len(instructions):
+                raise ValueError('rng_id needs one entry per instruction')
+            m.rng_id = _ptr(keep['rng_id'])
         return m, keep
 
     def _pinned_records(self, cap):
@@ -162,7 +167,7 @@ class Simulator:
             self._pinned_cache = c = PinnedArray(self.lib, int(cap * 1.05) + 1024, raw_record_dtype())
         return c
 
-    def simulate(self, instructions, seed=0, maps=None, cap_records=None, pinned=False):
+    def simulate(self, instructions, seed=0, maps=None, cap_records=None, pinned=False, rng_id=None):
         """Full path for one set of instructions (see wfs_simulate in the header).
 
         Returns dict(raw_records, raw_records_he, raw_records_aqmon, truth, groups); records of
@@ -173,7 +178,7 @@ class Simulator:
         if instructions.dtype.itemsize != 70:
             raise ValueError('instructions must have the packed 70-byte instruction_dtype')
         n = len(instructions)
-        m, keep = self._maps_struct(instructions, maps)
+        m, keep = self._maps_struct(instructions, maps, rng_id)
         counts = wlib.Counts()
         cap_rec = int(cap_records) if cap_records is not None else max(4096, 1500 * n)
         cap_truth, cap_groups, cap_batches = 2 * n + 64, n + 64, 4096
