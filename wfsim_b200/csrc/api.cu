@@ -34,6 +34,10 @@ Handle::Handle(const wfs_params &p, const wfs_tables &t, int dev) : device(dev) 
         throw std::runtime_error("unsupported sample_duration / template length");
     if (p.n_tpc_pmts <= 0 || p.n_tpc_pmts >= (1 << kChannelBits) || p.n_rows > (1 << kChannelBits))
         throw std::runtime_error("unsupported channel count");
+    // Pulse.add_current writes template_length samples from (photon sample - pulse left); the pulse
+    // array (pulse.py:118-128) only holds them if the right margin covers the template
+    if (p.template_length > p.pulse_right_margin + 1 || p.pulse_left_margin < 0 || p.trigger_window < 0)
+        throw std::runtime_error("template longer than the stored pulse margin (samples_to_store_after)");
     if (!t.templates || !t.gains || !t.zle_thresholds)
         throw std::runtime_error("templates, gains and zle_thresholds tables are required");
     cfg.templates = upload(t.templates, (size_t)p.dt * p.template_length, owned);

@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <limits.h>
+#include <stdlib.h>
 
 namespace wfs {
 
@@ -333,51 +334,74 @@ __global__ void k_group_noise(int64_t n_groups, DeviceConfig c, const int64_t *g
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_digitize: ONE THREAD per block of 8 consecutive samples of a (group, channel) window.
-//   * the thread walks the photons of every pulse of its window in time order exactly like
-//     Pulse.add_current (pulse.py:301-318) -- equal-ns photons merged, then tap (s - q) of the
-//     template times the merged gain added to its samples, mul and add unfused;
-//   * one rounding per (pulse call, channel), integer sum over pulses (rawdata.py:236-239);
-//   * noise / baseline / clamp (rawdata.py:398-458), one 16-byte store of 8 int16 samples and one
-//     flag byte (sample < ZLE threshold, rawdata.py:290-296).
-// All lanes do distinct work (no warp-uniform control flow), nothing is staged in shared memory
-// except the 1.8 KB template table; the photons of a window are a few cache lines shared by the
-// ~40 threads of the window.
+// k_digitize: persistent CTAs, each looping over TILES of the dense buffer (up to 256 consecutive
+// 8-sample blocks = 2048 samples; the dense buffer is window-contiguous, so a tile covers a few
+// whole windows or a slice of a long one).
+//   setup   warp 0: the windows overlapping the tile -> s_win (ballot-ordered), photon prefix;
+//   sparse  (<= kStageCap photons in those windows, the common case): one thread per photon
+//           stages it in shared memory (tile-local sample position, merged gain) and marks the
+//           8-sample blocks its template reaches.  An ISLAND is a run of photons of one Pulse
+//           call whose 22-tap templates overlap; every sample of an island is OWNED by the first
+//           photon whose template covers it, and the owner's index is scattered into byte l of
+//           the sample's word (layer l = pulse ordinal in the window mod 4, so overlapping Pulse
+//           calls do not collide; a collision is detected by the atomicOr and sends the tile to
+//           the dense path).  Then one thread per sample of the touched blocks: for each layer,
+//           walk the island from the owner and sum template x merged gain in time order exactly
+//           like Pulse.add_current (pulse.py:301-318, mul and add unfused), round once per Pulse
+//           call (rawdata.py:236-239) and add the integers.
+//   dense   (many photons): one thread per 8 samples gathers the photons that reach it, per
+//           pulse, with a binary search for the first one (all lanes busy: high photon density);
+//   finish  untouched blocks (nothing but the baseline) are one constant 16-byte store; touched
+//           blocks: noise, baseline, clamp (rawdata.py:398-458), int16 pack, ZLE flag bits
+//           (sample < threshold, rawdata.py:290-296).
 // k_zle: ONE THREAD per window runs the hysteresis interval search (utils.py:13-58,
 // rawdata.py:296-308) on the flag bytes.
 // ---------------------------------------------------------------------------------------------
-constexpr int kDigiThreads = 256;
+constexpr int kDigiThreads = 128;
+constexpr int kDigiWarps = kDigiThreads / 32;
+constexpr int kDigiCtasPerSm = 9;
 constexpr int kNeg = -(1 << 29);
+constexpr int kTileBlkMax = 256;                 // 8-sample blocks per tile
+constexpr int kTileSmpMax = kTileBlkMax * kBlk;
+constexpr int kTileWinMax = 32;                  // windows overlapping one tile (host sizes the tile)
+constexpr int kStageCap = 255;                   // photons staged in shared memory per tile (byte index + 1)
+constexpr int kLayers = 4;
 
-__device__ __forceinline__ int64_t lower_bound_i64(const int64_t *a, int64_t lo, int64_t hi, int64_t key) {
-    while (lo < hi) {
-        int64_t mid = (lo + hi) >> 1;
-        if (a[mid] < key) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
+struct TileWin {
+    int32_t off;             // tile-local sample index of window sample 0 (negative: starts before)
+    int32_t len;
+    int32_t mult;
+    int32_t thr;
+    int32_t channel;         // -1: no noise row
+    int32_t ixbase;          // noise start index of window sample 0, already modulo noise_len
+    uint32_t ph_lo, ph_cnt;
+    int32_t p0, p1;
+    int32_t s_first, s_last;
+    uint32_t stage0;
+    int32_t all_touched;     // every block needs the full finish (noise, or baseline below threshold)
+};
 
-__device__ __forceinline__ uint32_t udiv_dt(uint32_t x, int dt) {
-    return dt == 10 ? x / 10u : x / (uint32_t)dt;   // constant divisor -> multiply-high
-}
-
-// For every run of 32 consecutive 8-sample blocks (= one digitize warp) the window owning its
-// first block, so no thread needs a search.  One thread per window.
-__global__ void k_cta_index(int64_t n_wtot, const uint64_t *__restrict__ win_off, WinMeta *meta,
-                            uint32_t *cta_first) {
+// For every tile the window owning its first block, so no CTA needs a search.  One thread per window.
+__global__ void k_tile_index(int64_t n_wtot, int tile_blk, const uint64_t *__restrict__ win_off,
+                             WinMeta *meta, uint32_t *tile_first) {
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_wtot) return;
     const int64_t b0 = (int64_t)(uint32_t)win_off[w], b1 = (int64_t)(uint32_t)win_off[w + 1];
     meta[w].blk0 = (uint32_t)b0;
     meta[w].slot0 = (uint32_t)(win_off[w] >> 32);
     if (b1 <= b0) return;
-    for (int64_t g = (b0 + 31) / 32; g * 32 < b1; g++) cta_first[g] = (uint32_t)w;
+    for (int64_t g = (b0 + tile_blk - 1) / tile_blk; g * tile_blk < b1; g++) tile_first[g] = (uint32_t)w;
 }
 
-// Per sorted photon: window-local sample index + ns remainder packed into 32 bits, and -- for the
+// Per sorted photon, packed into 32 bits: ns remainder [0,4), window-local sample index [4,24),
+// ordinal of its Pulse call inside the window [24,29) (31 = 31 or more), flags (island start,
+// run head, alone = an island of one photon); and -- for the
 // first photon of a run of equal-ns photons of one pulse -- the merged gain (pulse.py:301-318:
-// gains of coincident photons are summed before the template multiply).
-constexpr uint32_t kPhPulseStart = 1u << 31, kPhRunHead = 1u << 30, kPhQMask = (1u << 26) - 1u;
+// gains of coincident photons are summed before the template multiply).  kPhIsland marks the first
+// photon of an island: a new Pulse call, or a photon whose template cannot overlap the previous one's.
+constexpr uint32_t kPhAlone = 1u << 31, kPhRunHead = 1u << 30, kPhIsland = 1u << 29,
+                   kPhQMask = (1u << 20) - 1u, kPhOrdShift = 24, kPhOrdMask = 31u;
+static_assert(kMaxGroupSamples + 1 <= (int64_t)kPhQMask, "window-local sample index must fit");
 
 __global__ void k_photon_prep(int64_t n_valid, DeviceConfig c, const int64_t *__restrict__ st,
                               const double *__restrict__ sg, const uint8_t *__restrict__ pstart,
@@ -387,14 +411,21 @@ __global__ void k_photon_prep(int64_t n_valid, DeviceConfig c, const int64_t *__
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_valid) return;
     const int64_t t = st[i];
-    const bool ps = pstart[i] != 0;
-    const bool head = ps || st[i - (i > 0)] != t || i == 0;
-    const uint32_t p = (uint32_t)pos[i] + (ps ? 1u : 0u) - 1u;
-    const int64_t left = meta[pulse_win[p]].left;
+    const bool ps = pstart[i] != 0 || i == 0;
+    const int64_t tprev = st[i - (i > 0)];
+    const bool head = ps || tprev != t;
+    const uint32_t p = (uint32_t)pos[i] + (pstart[i] != 0 ? 1u : 0u) - 1u;
+    const WinMeta *m = meta + pulse_win[p];
+    const int64_t left = m->left;
+    const uint32_t ord = min(p - (uint32_t)m->p0, kPhOrdMask);
     const int64_t q = floordiv(t, c.p.dt);
     const uint32_t r = (uint32_t)(t - q * c.p.dt);
-    uint32_t v = (((uint32_t)(q - left) & kPhQMask) << 4) | r;
-    if (ps) v |= kPhPulseStart;
+    uint32_t v = (((uint32_t)(q - left) & kPhQMask) << 4) | r | (ord << kPhOrdShift);
+    if (ps || q - floordiv(tprev, c.p.dt) >= c.p.template_length) {
+        v |= kPhIsland;
+        // single-photon island: the next photon (if any) starts an island of its own
+        if (i + 1 >= n_valid || pstart[i + 1] || floordiv(st[i + 1], c.p.dt) - q >= c.p.template_length) v |= kPhAlone;
+    }
     double g = 0.0;
     if (head) {
         v |= kPhRunHead;
@@ -405,130 +436,307 @@ __global__ void k_photon_prep(int64_t n_valid, DeviceConfig c, const int64_t *__
     gm[i] = g;
 }
 
-__global__ void __launch_bounds__(kDigiThreads)
-k_digitize(int64_t n_blocks, int64_t n_wtot, DeviceConfig c, const WinMeta *__restrict__ meta,
-           const uint32_t *__restrict__ cta_first, const uint32_t *__restrict__ phq,
-           const double *__restrict__ gm, const uint32_t *__restrict__ pulse_first,
-           const int64_t *__restrict__ group_ix, int16_t *__restrict__ dense,
-           uint8_t *__restrict__ flag8) {
-    __shared__ double s_tmpl[16 * 32];
-    const int dt = c.p.dt, tlen = c.p.template_length;
-    for (int i = threadIdx.x; i < dt * tlen; i += blockDim.x) s_tmpl[i] = c.templates[i];
-    __syncthreads();
-    const int64_t blk = (int64_t)blockIdx.x * kDigiThreads + threadIdx.x;
-    if (blk >= n_blocks) return;
-    // windows are >= 28 blocks long: the 32 blocks of a warp span at most 3 of them
-    int64_t w = cta_first[blk >> 5];
-    WinMeta m = meta[w];
-    while (blk >= (int64_t)m.blk0 + ((m.len + kBlk - 1) / kBlk) && w + 1 < n_wtot) m = meta[++w];
-    const int s0 = (int)(blk - (int64_t)m.blk0) * kBlk;     // first sample (window coords)
-    const int nvalid = min(kBlk, m.len - s0);
-    int acc[kBlk];
+__device__ __forceinline__ int ph_q(uint32_t v) { return (int)((v >> 4) & kPhQMask); }
+
+// dense path: the 8 samples [s0, s0 + 8) of window `m`, gathered per pulse
+__device__ __forceinline__ void gather_block(const TileWin &m, int s0, int tlen, double c2a,
+                                             const double *s_tmpl, const uint32_t *__restrict__ phq,
+                                             const double *__restrict__ gm,
+                                             const uint32_t *__restrict__ pulse_first, int acc[kBlk]) {
 #pragma unroll
     for (int i = 0; i < kBlk; i++) acc[i] = 0;
-    bool touched = false;
-    if (m.mult != 0 && s0 + kBlk > m.s_first && s0 <= m.s_last) {
-        const double c2a = c.p.current_2_adc;
-        const int q_lo = s0 - (tlen - 1), q_hi = s0 + kBlk - 1;   // photon samples that reach mine
-        double cur[kBlk];
+    if (m.mult == 0 || s0 + kBlk <= m.s_first || s0 > m.s_last) return;
+    const int q_lo = s0 - (tlen - 1), q_hi = s0 + kBlk - 1;   // photon samples that reach mine
+    double cur[kBlk];
 #pragma unroll
-        for (int i = 0; i < kBlk; i++) cur[i] = 0.0;
+    for (int i = 0; i < kBlk; i++) cur[i] = 0.0;
+    for (int p = m.p0; p < m.p1; p++) {
+        const uint32_t f0 = pulse_first[p], f1 = pulse_first[p + 1];
+        uint32_t a = f0, b = f1;
+        while (a < b) {   // first photon of the pulse that can reach me (a run head, see k_photon_prep)
+            const uint32_t mid = (a + b) >> 1;
+            if (ph_q(phq[mid]) < q_lo) a = mid + 1; else b = mid;
+        }
         bool any = false;
-        const bool small = (m.ph_hi - m.ph_lo) <= 64;
-        const int np = small ? 1 : (m.p1 - m.p0);
-        for (int pi = 0; pi < np; pi++) {
-            uint32_t lo = m.ph_lo, hi = m.ph_hi;
-            if (!small) {   // many photons: per pulse, jump to the first photon that can reach me
-                const uint32_t f0 = pulse_first[m.p0 + pi], f1 = pulse_first[m.p0 + pi + 1];
-                uint32_t a = f0, b = f1;
-                while (a < b) {
-                    const uint32_t mid = (a + b) >> 1;
-                    if ((int)((phq[mid] >> 4) & kPhQMask) < q_lo) a = mid + 1; else b = mid;
-                }
-                lo = a;
-                hi = f1;
-                // step back to the head of the run `lo` may sit in (same ns => same sample)
-                while (lo > f0 && !(phq[lo] & kPhRunHead)) lo--;
-            }
-            for (uint32_t i = lo; i < hi; i++) {
-                const uint32_t v = phq[i];
-                if ((v & kPhPulseStart) && any) {   // a new Pulse call starts: round the finished one
+        for (uint32_t i = a; i < f1; i++) {
+            const uint32_t v = phq[i];
+            if (!(v & kPhRunHead)) continue;
+            const int q = ph_q(v);
+            if (q > q_hi) break;
+            const double g = gm[i];
+            const double *tm = s_tmpl + (v & 15u) * tlen;
+            const int first = q - s0;          // my sample index of template tap 0
+            any = true;
 #pragma unroll
-                    for (int j = 0; j < kBlk; j++) {
-                        acc[j] -= __double2int_rn(__dmul_rn(cur[j], c2a)) * m.mult;
-                        cur[j] = 0.0;
-                    }
-                    any = false;
-                    touched = true;
-                }
-                if (!(v & kPhRunHead)) continue;
-                const int q = (int)((v >> 4) & kPhQMask);
-                if (q > q_hi) { if (small) continue; else break; }
-                if (q < q_lo) continue;
-                const double g = gm[i];
-                const double *tm = s_tmpl + (v & 15u) * tlen;
-                const int first = q - s0;          // my sample index of template tap 0
-                any = true;
-#pragma unroll
-                for (int j = 0; j < kBlk; j++) {
-                    const int tap = j - first;
-                    if (tap >= 0 && tap < tlen) cur[j] = __dadd_rn(cur[j], __dmul_rn(tm[tap], g));
-                }
-            }
-            if (any && !small) {   // end of this pulse
-#pragma unroll
-                for (int j = 0; j < kBlk; j++) {
-                    acc[j] -= __double2int_rn(__dmul_rn(cur[j], c2a)) * m.mult;
-                    cur[j] = 0.0;
-                }
-                any = false;
-                touched = true;
+            for (int j = 0; j < kBlk; j++) {
+                const int tap = j - first;
+                if (tap >= 0 && tap < tlen) cur[j] = __dadd_rn(cur[j], __dmul_rn(tm[tap], g));
             }
         }
         if (any) {   // one rounding per (pulse call, channel): rawdata.py:236-239
-            touched = true;
 #pragma unroll
-            for (int j = 0; j < kBlk; j++) acc[j] -= __double2int_rn(__dmul_rn(cur[j], c2a)) * m.mult;
+            for (int j = 0; j < kBlk; j++) {
+                acc[j] -= __double2int_rn(__dmul_rn(cur[j], c2a)) * m.mult;
+                cur[j] = 0.0;
+            }
         }
     }
-    // noise, baseline, clamp, ZLE flag, packed int16 store
-    const bool noisy = c.p.enable_noise && c.noise_t != nullptr && m.channel < c.noise_nch;
-    const int thr = c.zle_thr[m.channel];
-    const int baseline = c.p.baseline;
-    if (!touched && !noisy && nvalid == kBlk) {
-        // nothing but the baseline in these 8 samples
-        const int v = max(baseline, 0);
-        const uint32_t h = (uint32_t)(uint16_t)(int16_t)v;
-        const uint32_t pw = h | (h << 16);
-        *reinterpret_cast<uint4 *>(dense + blk * kBlk) = make_uint4(pw, pw, pw, pw);
-        flag8[blk] = v < thr ? 0xff : 0;
-        return;
-    }
-    int64_t ix = 0;
-    const double *noise_row = nullptr;
-    if (noisy) {
-        ix = group_ix[m.group] + s0;
-        noise_row = c.noise_t + (int64_t)m.channel * c.noise_len;
-        if (ix >= c.noise_len) ix -= c.noise_len * (ix / c.noise_len);
-    }
-    uint32_t flags = 0;
-    uint32_t packed[kBlk / 2];
+}
+
+// staged photon: s_rf = ns remainder | run head << 4 | island start << 5 | layer << 6 | window slot << 8 | alone << 13
+constexpr uint32_t kRfHead = 16u, kRfIsland = 32u, kRfAlone = 1u << 13;
+
+// noise, baseline, clamp, ZLE flags, one 16-byte store of 8 int16 samples + one flag byte
+__device__ __forceinline__ void finish_block(int v[kBlk], const TileWin &m, int S, const DeviceConfig &c,
+                                             uint4 *out, uint8_t *flag) {
+    if (m.channel >= 0) {
+        const double *row = c.noise_t + (int64_t)m.channel * c.noise_len;
+        int64_t ix = ((int64_t)m.ixbase + S) % c.noise_len;
 #pragma unroll
-    for (int j = 0; j < kBlk; j++) {
-        int v = acc[j];
-        if (noisy) {
-            v = __double2int_rz((double)v + noise_row[ix]);
+        for (int j = 0; j < kBlk; j++) {
+            v[j] = __double2int_rz((double)v[j] + row[ix]);
             if (++ix >= c.noise_len) ix = 0;
         }
-        v += baseline;
-        v = max(v, 0);
-        if (j < nvalid && v < thr) flags |= 1u << j;
-        if (j >= nvalid) v = 0;
-        const uint32_t h = (uint32_t)(uint16_t)(int16_t)v;
-        if (j & 1) packed[j >> 1] |= h << 16; else packed[j >> 1] = h;
     }
-    *reinterpret_cast<uint4 *>(dense + blk * kBlk) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-    flag8[blk] = (uint8_t)flags;
+    const int nvalid = min(kBlk, m.len - S), thr = m.thr, baseline = c.p.baseline;
+    uint32_t flags = 0, h[kBlk];
+#pragma unroll
+    for (int j = 0; j < kBlk; j++) {
+        int x = max(v[j] + baseline, 0);
+        if (x < thr) flags |= 1u << j;
+        if (j >= nvalid) x = 0;
+        h[j] = (uint32_t)(uint16_t)(int16_t)x;
+    }
+    flags &= (1u << nvalid) - 1u;
+    *out = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+    *flag = (uint8_t)flags;
+}
+
+__global__ void __launch_bounds__(kDigiThreads)
+k_digitize(int64_t n_blocks, int tile_blk, int n_tiles, int64_t n_wtot, DeviceConfig c,
+           const WinMeta *__restrict__ meta, const uint64_t *__restrict__ win_off,
+           const uint32_t *__restrict__ tile_first, const uint32_t *__restrict__ phq,
+           const double *__restrict__ gm, const uint32_t *__restrict__ pulse_first,
+           const int64_t *__restrict__ group_ix, int16_t *__restrict__ dense,
+           uint8_t *__restrict__ flag8, int64_t *scalars) {
+    __shared__ __align__(16) uint32_t s_own[kTileSmpMax];   // per sample: owner index + 1 of layer l in byte l; then the ADC sum
+    __shared__ double s_tmpl[16 * 32];
+    __shared__ double s_gm[kStageCap + 1];
+    __shared__ int s_T[kStageCap + 1];
+    __shared__ TileWin s_win[kTileWinMax];
+    __shared__ uint16_t s_rf[kStageCap + 1];
+    __shared__ uint16_t s_tb[kTileBlkMax];
+    __shared__ uint8_t s_blkwin[kTileBlkMax];
+    __shared__ uint32_t s_touch[kTileBlkMax / 32];
+    __shared__ int s_nwin, s_total, s_ntb, s_fallback, s_mult1;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int dt = c.p.dt, tlen = c.p.template_length;
+    const bool noise_on = c.p.enable_noise && c.noise_t != nullptr;
+    const double c2a = c.p.current_2_adc;
+    const int base_clamped = max(c.p.baseline, 0);
+    const uint32_t base_h = (uint32_t)(uint16_t)(int16_t)base_clamped;
+    const uint32_t base_pw = base_h | (base_h << 16);
+    for (int i = tid; i < dt * tlen; i += kDigiThreads) s_tmpl[i] = c.templates[i];
+    for (int i = tid; i < kTileSmpMax; i += kDigiThreads) s_own[i] = 0;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t B0 = (int64_t)tile * tile_blk;
+        const int nblk = (int)min((int64_t)tile_blk, n_blocks - B0);
+        const int nsmp = nblk * kBlk;
+        uint4 *out = reinterpret_cast<uint4 *>(dense + B0 * kBlk);
+        __syncthreads();   // previous tile fully written; tables initialised
+        if (tid < kTileBlkMax / 32) s_touch[tid] = 0;
+        if (tid == 32) { s_ntb = 0; s_fallback = 0; }
+        // ---- setup (warp 0): the windows overlapping this tile, in window order ----
+        if (warp == 0) {
+            int n = 0;
+            for (int64_t base = tile_first[tile];; base += 32) {
+                const int64_t w = base + lane;
+                bool past = w >= n_wtot, take = false;
+                int64_t b0 = 0;
+                if (!past) {
+                    b0 = (int64_t)(uint32_t)win_off[w];
+                    const int64_t b1 = (int64_t)(uint32_t)win_off[w + 1];
+                    past = b0 >= B0 + nblk;
+                    take = !past && b1 > b0 && b1 > B0;
+                }
+                const uint32_t tm = __ballot_sync(0xffffffffu, take);
+                const int slot = n + __popc(tm & lt);
+                if (take && slot < kTileWinMax) {
+                    const WinMeta m = meta[w];
+                    TileWin t;
+                    t.off = (int32_t)(b0 - B0) * kBlk;
+                    t.len = m.len;
+                    t.mult = m.mult;
+                    t.thr = c.zle_thr[m.channel];
+                    const bool noisy = noise_on && m.channel < c.noise_nch;
+                    t.channel = noisy ? m.channel : -1;
+                    t.ixbase = noisy ? (int32_t)(group_ix[m.group] % c.noise_len) : 0;
+                    t.ph_lo = m.ph_lo;
+                    t.ph_cnt = m.mult != 0 ? m.ph_hi - m.ph_lo : 0u;
+                    t.p0 = m.p0; t.p1 = m.p1;
+                    t.s_first = m.s_first; t.s_last = m.s_last;
+                    t.stage0 = 0;
+                    t.all_touched = (noisy || base_clamped < t.thr) ? 1 : 0;
+                    s_win[slot] = t;
+                }
+                n += __popc(tm);
+                if (__ballot_sync(0xffffffffu, past)) break;
+            }
+            if (n > kTileWinMax) {   // cannot happen: the host sizes tile_blk from the minimum window length
+                if (lane == 0) scalars[S_ERR] = WFS_E_ARG;
+                n = kTileWinMax;
+            }
+            __syncwarp();
+            // exclusive prefix of the photon counts over the (<= 32) slots
+            const uint32_t c0 = lane < n ? min(s_win[lane].ph_cnt, 1u << 24) : 0u;
+            uint32_t i0 = c0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t a0 = __shfl_up_sync(0xffffffffu, i0, o);
+                if (lane >= o) i0 += a0;
+            }
+            if (lane < n) s_win[lane].stage0 = i0 - c0;
+            const uint32_t notone = __ballot_sync(0xffffffffu, lane < n && s_win[lane].mult != 1);
+            if (lane == 31) { s_nwin = n; s_total = (int)i0; s_mult1 = notone == 0; }
+        }
+        __syncthreads();
+        const int nwin = s_nwin, total = s_total;
+        const bool mult1 = s_mult1 != 0;
+        bool sparse = total <= kStageCap;
+        if (sparse) {
+            // ---- stage the photons (one thread each); mark the blocks their templates reach ----
+            if (tid < nwin) {
+                const TileWin &m = s_win[tid];
+                const int blk_lo = max(m.off / kBlk, 0), blk_end = (m.off + m.len + kBlk - 1) / kBlk;
+                if (m.all_touched) {
+                    for (int b = blk_lo; b < min(blk_end, nblk); b++) {
+                        s_blkwin[b] = (uint8_t)tid;
+                        atomicOr(&s_touch[b >> 5], 1u << (b & 31));
+                    }
+                } else if ((m.len & (kBlk - 1)) && blk_end <= nblk) {   // partial last block
+                    s_blkwin[blk_end - 1] = (uint8_t)tid;
+                    atomicOr(&s_touch[(blk_end - 1) >> 5], 1u << ((blk_end - 1) & 31));
+                }
+            }
+            for (int i = tid; i < total; i += kDigiThreads) {
+                int slot = 0;   // last slot with stage0 <= i
+#pragma unroll
+                for (int step = kTileWinMax / 2; step > 0; step >>= 1)
+                    if (slot + step < nwin && (int)s_win[slot + step].stage0 <= i) slot += step;
+                const uint32_t src = s_win[slot].ph_lo + (uint32_t)(i - (int)s_win[slot].stage0);
+                const uint32_t v = phq[src];
+                const int off = s_win[slot].off;
+                const int T0 = off + ph_q(v);
+                const uint32_t ord = (v >> kPhOrdShift) & kPhOrdMask;
+                s_gm[i] = gm[src];
+                s_T[i] = T0;
+                s_rf[i] = (uint16_t)((v & 15u) | ((v & kPhRunHead) ? kRfHead : 0u) |
+                                     ((v & kPhIsland) ? kRfIsland : 0u) | ((ord & (kLayers - 1)) << 6) |
+                                     ((uint32_t)slot << 8) | ((v & kPhAlone) ? kRfAlone : 0u));
+                if (ord == kPhOrdMask) s_fallback = 1;
+                if (v & kPhRunHead) {
+                    const int t_hi = min(T0 + tlen - 1, nsmp - 1);
+                    for (int b = max(T0, 0) >> 3; b <= (t_hi >> 3); b++) {
+                        s_blkwin[b] = (uint8_t)slot;
+                        atomicOr(&s_touch[b >> 5], 1u << (b & 31));
+                    }
+                    // the samples this photon owns: its template's reach minus the previous photon's
+                    int lo = T0;
+                    if (!(v & kPhIsland)) lo = max(lo, off + ph_q(phq[src - 1]) + tlen);
+                    lo = max(lo, 0);
+                    const int sh = (int)(ord & (kLayers - 1)) * 8;
+                    bool clash = false;
+                    for (int T = lo; T <= t_hi; T++) {
+                        const uint32_t old = atomicOr(&s_own[T], (uint32_t)(i + 1) << sh);
+                        clash |= ((old >> sh) & 0xffu) != 0;
+                    }
+                    if (clash) s_fallback = 1;   // two Pulse calls on one layer overlap
+                }
+            }
+            __syncthreads();
+            if (s_fallback) {   // rare: clear the owner tables and take the dense path
+                __syncthreads();
+                for (int i = tid; i < kTileSmpMax; i += kDigiThreads) s_own[i] = 0;
+                sparse = false;
+            }
+        }
+        if (sparse) {
+            // ---- untouched blocks: constant stores; touched blocks: compacted list ----
+            for (int wd = warp; wd * 32 < nblk; wd += kDigiWarps) {
+                const uint32_t word = s_touch[wd];
+                const int b = wd * 32 + lane;
+                int base = 0;
+                if (lane == 0 && word) base = atomicAdd(&s_ntb, __popc(word));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if ((word >> lane) & 1u) {
+                    s_tb[base + __popc(word & lt)] = (uint16_t)b;
+                } else if (b < nblk) {          // nothing but the baseline in these 8 samples
+                    out[b] = make_uint4(base_pw, base_pw, base_pw, base_pw);
+                    flag8[B0 + b] = 0;
+                }
+            }
+            __syncthreads();
+            const int ntb = s_ntb;
+            // ---- touched samples (one thread each): gather from the owners, round per Pulse call ----
+            for (int e = tid; e < ntb * kBlk; e += kDigiThreads) {
+                const int b = s_tb[e >> 3];
+                const int T = b * kBlk + (e & (kBlk - 1));
+                uint32_t ow = s_own[T];
+                if (!ow) continue;
+                const int mult = mult1 ? 1 : s_win[s_blkwin[b]].mult;
+                int v = 0;
+                do {   // one owner per layer (byte), usually a single one
+                    const int sh = (31 - __clz(ow)) & ~7;
+                    const int o = (int)((ow >> sh) & 0xffu);
+                    ow &= ~(0xffu << sh);
+                    const uint32_t r0 = s_rf[o - 1];
+                    double cur;
+                    if (r0 & kRfAlone) {
+                        cur = __dmul_rn(s_tmpl[(r0 & 15u) * tlen + (T - s_T[o - 1])], s_gm[o - 1]);
+                    } else {
+                        cur = 0.0;
+                        for (int k = o - 1; k < total; k++) {
+                            const uint32_t rk = s_rf[k];
+                            if (k >= o && (rk & kRfIsland)) break;
+                            const int tap = T - s_T[k];
+                            if (tap < 0) break;
+                            if (rk & kRfHead) cur = __dadd_rn(cur, __dmul_rn(s_tmpl[(rk & 15u) * tlen + tap], s_gm[k]));
+                        }
+                    }
+                    v -= __double2int_rn(__dmul_rn(cur, c2a)) * mult;
+                } while (ow);
+                s_own[T] = (uint32_t)v;
+            }
+            __syncthreads();
+            // ---- touched blocks: finish ----
+            for (int j = tid; j < ntb; j += kDigiThreads) {
+                const int b = s_tb[j];
+                const TileWin &m = s_win[s_blkwin[b]];
+                int4 *acc = reinterpret_cast<int4 *>(&s_own[b * kBlk]);
+                const int4 a0 = acc[0], a1 = acc[1];
+                acc[0] = acc[1] = make_int4(0, 0, 0, 0);
+                int v[kBlk] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                finish_block(v, m, b * kBlk - m.off, c, &out[b], &flag8[B0 + b]);
+            }
+        } else {
+            // ---- dense path ----
+            for (int slot = warp; slot < nwin; slot += kDigiWarps) {
+                const int lo = max(s_win[slot].off / kBlk, 0);
+                const int hi = min((s_win[slot].off + s_win[slot].len + kBlk - 1) / kBlk, nblk);
+                for (int b = lo + lane; b < hi; b += 32) s_blkwin[b] = (uint8_t)slot;
+            }
+            __syncthreads();
+            for (int b = tid; b < nblk; b += kDigiThreads) {
+                const TileWin &m = s_win[s_blkwin[b]];
+                int v[kBlk];
+                gather_block(m, b * kBlk - m.off, tlen, c2a, s_tmpl, phq, gm, pulse_first, v);
+                finish_block(v, m, b * kBlk - m.off, c, &out[b], &flag8[B0 + b]);
+            }
+        }
+    }
 }
 
 __device__ __forceinline__ void emit_interval(int s, int e, const WinMeta &m, int tw, int64_t dense0,
@@ -892,8 +1100,13 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
         itv_rec0_.reserve(sizeof(uint32_t) * (n_slots + 1));
         WFS_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
         WFS_CUDA_CHECK(cudaEventRecord(evp_[2], stream_));
-        cta_first_.reserve(sizeof(uint32_t) * (size_t)(div_up(n_tiles, 32) + 1));
-        LAUNCH(k_cta_index, div_up(nwt, T), T, nwt, win_scan_.as<uint64_t>(), win_meta_.as<WinMeta>(),
+        // tile size: at most kTileWinMax windows may overlap a tile (every window is at least
+        // left margin + right margin + 1 + 2 trigger windows long)
+        const int min_blk = std::max(1, (c.p.pulse_left_margin + c.p.pulse_right_margin + 1 + 2 * c.p.trigger_window) / kBlk);
+        const int tile_blk = std::min(kTileBlkMax, (kTileWinMax - 4) * min_blk);
+        const int n_cta = div_up(n_tiles, tile_blk);
+        cta_first_.reserve(sizeof(uint32_t) * (size_t)(n_cta + 1));
+        LAUNCH(k_tile_index, div_up(nwt, T), T, nwt, tile_blk, win_scan_.as<uint64_t>(), win_meta_.as<WinMeta>(),
                cta_first_.as<uint32_t>());
         phq_.reserve(sizeof(uint32_t) * (size_t)(n + 1));
         {
@@ -903,10 +1116,12 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
                        pstart_.as<uint8_t>(), prim_.sort_keys_alt.as<uint64_t>(), pulse_win_.as<uint32_t>(),
                        win_meta_.as<WinMeta>(), phq_.as<uint32_t>(), reinterpret_cast<double *>(flags64_.p));
         }
-        LAUNCH(k_digitize, div_up(n_tiles, kDigiThreads), kDigiThreads, n_tiles, nwt, c,
-               win_meta_.as<WinMeta>(), cta_first_.as<uint32_t>(), phq_.as<uint32_t>(),
-               reinterpret_cast<const double *>(flags64_.p), pulse_first_.as<uint32_t>(),
-               group_ix_buf.as<int64_t>(), dense_.as<int16_t>(), flag8_.as<uint8_t>());
+        static const int ctas_per_sm = getenv("WFS_DIGI_CTAS") ? atoi(getenv("WFS_DIGI_CTAS")) : kDigiCtasPerSm;
+        LAUNCH(k_digitize, std::min(n_cta, kNumSMs * ctas_per_sm), kDigiThreads, n_tiles, tile_blk, n_cta, nwt, c,
+               win_meta_.as<WinMeta>(), win_scan_.as<uint64_t>(), cta_first_.as<uint32_t>(),
+               phq_.as<uint32_t>(), reinterpret_cast<const double *>(flags64_.p),
+               pulse_first_.as<uint32_t>(), group_ix_buf.as<int64_t>(), dense_.as<int16_t>(),
+               flag8_.as<uint8_t>(), scal);
         WFS_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
         WFS_CUDA_CHECK(cudaEventRecord(evp_[3], stream_));
         LAUNCH(k_zle, div_up(nwt, 128), 128, nwt, c, win_meta_.as<WinMeta>(), win_scan_.as<uint64_t>(),
