@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 #include <stdexcept>
+#include <atomic>
 
 #define WFS_CUDA_CHECK(expr)                                                              \
     do {                                                                                  \
@@ -59,7 +60,7 @@ struct DevBuf {
 };
 
 struct LaunchCounter {
-    int64_t n = 0;
+    std::atomic<int64_t> n{0};   // lanes launch from their own host threads
 };
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -10,6 +10,10 @@
 #include <chrono>
 #include <limits>
 #include <unordered_map>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <exception>
 
 namespace wfs {
 
@@ -248,6 +252,33 @@ static void make_plan(Handle *H, const uint8_t *rows, int64_t n, const wfs_instr
 }
 
 // ---------------------------------------------------------------------------------------------
+// Lanes: device batches are independent units (closed sets of instruction clusters), so batch k
+// runs on lane k % n_lanes -- a stream, a workspace set and a host thread of its own.  While one
+// lane's host thread replays the scheduler or waits for a count, the other lane's kernels keep
+// the GPU busy.  Group numbering (noise RNG identity) and output offsets are published in batch
+// order through `Order`, so results do not depend on the number of lanes.
+struct Lane {
+    int id = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_c = nullptr, ev_d = nullptr, ev_done = nullptr;
+    Frontend *F = nullptr;
+    Backend *B = nullptr;
+    int64_t local_batches = 0;
+};
+
+struct Order {
+    std::mutex mu;
+    std::condition_variable cv;
+    int64_t sched_done = 0;      // batches [0, sched_done) have published their group count
+    int64_t group_base = 0;      // number of digitisation groups in those batches
+    int64_t out_done = 0;        // batches [0, out_done) have reserved their output ranges
+    bool abort = false;
+};
+
+struct LaneAborted : std::runtime_error {
+    LaneAborted() : std::runtime_error("another lane failed") {}
+};
+
 struct PhotonDump {     // wfs_sample_stage
     int stage = 0;
     uint8_t *out = nullptr;
@@ -316,9 +347,8 @@ static void grow_photons(Frontend &F, int64_t n_new, int64_t n_old, cudaStream_t
 }
 
 // Generate emitters and photons of instructions [i0, i1); arrays are appended.
-static void generate(Handle *H, Frontend &F, uint64_t seed, int64_t i0, int64_t i1, int64_t &n_emit,
-                     int64_t &n_ph) {
-    cudaStream_t s = H->stream;
+static void generate(Handle *H, Frontend &F, cudaStream_t s, uint64_t seed, int64_t i0, int64_t i1,
+                     int64_t &n_emit, int64_t &n_ph) {
     const wfs_params &p = H->cfg.p;
     if (i1 <= i0) return;
     GenCtx g = make_ctx(F, seed);
@@ -423,10 +453,10 @@ static void combine_moments(const std::vector<int32_t> &set, const std::vector<i
     sigma = sqrtl(var);
 }
 
-static void simulate_batch(Handle *H, Plan &P, const BatchSpec &bs, uint64_t seed, SimOut &so,
-                           int64_t &group_base) {
-    Frontend &F = *H->frontend;
-    cudaStream_t s = H->stream;
+static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, const BatchSpec &bs,
+                           uint64_t seed, SimOut &so, Order &ord) {
+    Frontend &F = *L.F;
+    cudaStream_t s = L.stream;
     const wfs_params &p = H->cfg.p;
     const int n_ch = p.n_tpc_pmts;
     const int64_t j0 = P.cluster_start[bs.first_cluster], j1 = P.cluster_start[bs.last_cluster];
@@ -474,9 +504,9 @@ static void simulate_batch(Handle *H, Plan &P, const BatchSpec &bs, uint64_t see
     FLAUNCH(k_pattern_cdf, div_up(nrows, 64), 64, nrows, n_ch, F.b_pattern.as<float>(), H->cfg.gains,
             F.b_cdf.as<double>(), F.b_cdfok.as<int32_t>());
     // ---- pass A: primaries ----
-    WFS_CUDA_CHECK(cudaEventRecord(H->ev_c, s));
+    WFS_CUDA_CHECK(cudaEventRecord(L.ev_c, s));
     int64_t n_emit = 0, n_ph = 0;
-    generate(H, F, seed, 0, nprim, n_emit, n_ph);
+    generate(H, F, s, seed, 0, nprim, n_emit, n_ph);
     // ---- secondaries: photo-ionisation electrons of the S2 calls (rawdata.py:193-197) ----
     int64_t ntot = nprim;
     std::vector<int32_t> h_parent;
@@ -515,7 +545,7 @@ static void simulate_batch(Handle *H, Plan &P, const BatchSpec &bs, uint64_t see
             down(sec_amp.data(), F.b_iamp.as<int32_t>() + nprim, 4 * (size_t)nsec);
             WFS_CUDA_CHECK(cudaStreamSynchronize(s));
             d_parent.release();
-            generate(H, F, seed, nprim, ntot, n_emit, n_ph);   // pass B
+            generate(H, F, s, seed, nprim, ntot, n_emit, n_ph);   // pass B
         }
     }
     // ---- PMT afterpulses of every photon (rawdata.py:176-178) ----
@@ -591,15 +621,12 @@ static void simulate_batch(Handle *H, Plan &P, const BatchSpec &bs, uint64_t see
     F.b_acc.reserve(8 * (size_t)ntot * A_COUNT);
     g = make_ctx(F, seed);
     FLAUNCH(k_instr_truth, (unsigned)ntot, 128, g, H->cfg, (uint32_t)ntot, (uint32_t)n_ph, (uint32_t)n_ph);
-    WFS_CUDA_CHECK(cudaEventRecord(H->ev_d, s));
+    WFS_CUDA_CHECK(cudaEventRecord(L.ev_d, s));
     std::vector<int64_t> acc((size_t)ntot * A_COUNT);
     WFS_CUDA_CHECK(cudaMemcpyAsync(acc.data(), F.b_acc.p, 8 * acc.size(), cudaMemcpyDeviceToHost, s));
     WFS_CUDA_CHECK(cudaStreamSynchronize(s));
-    {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, H->ev_c, H->ev_d);
-        so.counts->ms_phase[0] += ms;
-    }
+    float ms_front = 0;
+    cudaEventElapsedTime(&ms_front, L.ev_c, L.ev_d);
     const auto host_t0 = std::chrono::steady_clock::now();
     // ---- host scheduler ----
     SchedIn in;
@@ -653,7 +680,18 @@ static void simulate_batch(Handle *H, Plan &P, const BatchSpec &bs, uint64_t see
         up(F.b_pcrank, pc_rank.data(), 4 * (size_t)npc);
         WFS_CUDA_CHECK(cudaMemsetAsync(F.b_trig.p, 0, 4 * (size_t)(2 * npc), s));
     }
-    so.counts->ms_phase[7] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+    const double ms_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+    // ---- group numbering, in batch order ----
+    int64_t group_base = 0;
+    {
+        std::unique_lock<std::mutex> lk(ord.mu);
+        ord.cv.wait(lk, [&] { return ord.abort || ord.sched_done == batch_index; });
+        if (ord.abort) throw LaneAborted();
+        group_base = ord.group_base;
+        ord.group_base += ngroups;
+        ord.sched_done = batch_index + 1;
+    }
+    ord.cv.notify_all();
     // ---- back end ----
     PhotonBatch b;
     b.n = n_ph + n_ap;
@@ -670,67 +708,34 @@ static void simulate_batch(Handle *H, Plan &P, const BatchSpec &bs, uint64_t see
     b.group_base = group_base;
     BackendResult res;
     wfs_outputs *out = so.out;
-    int64_t cap_here = 0;
-    uint8_t *d_rec = nullptr;
     F.b_groups.reserve(sizeof(wfs_group_info) * (size_t)std::max<int32_t>(ngroups, 1));
-    if (so.resident) {
-        cap_here = (int64_t)(F.b_records.cap / WFS_RECORD_BYTES);
-        d_rec = F.b_records.as<uint8_t>();
-    } else {
-        cap_here = out && out->records ? std::max<int64_t>(out->cap_records - so.n_rec, 0) : 0;
-        if (so.overflow) cap_here = 0;
-        // two device buffers: batch k is copied to the host on the copy stream while batch k+1 runs
-        const int par = (int)(so.n_batches & 1);
-        DevBuf &rb = par ? F.b_records2 : F.b_records;
-        if (F.copy_pending[par]) {
-            WFS_CUDA_CHECK(cudaEventSynchronize(F.ev_copy[par]));
-            F.copy_pending[par] = false;
-        }
-        // a batch cannot produce more records than samples / 2; size by a generous estimate and
-        // let the capacity protocol of Backend::run handle the rest
-        const int64_t want = std::min<int64_t>(cap_here, std::max<int64_t>(4 * (n_ph + n_ap) + 65536, (int64_t)(rb.cap / WFS_RECORD_BYTES)));
-        rb.reserve((size_t)WFS_RECORD_BYTES * (size_t)std::max<int64_t>(want, 1));
-        cap_here = std::min<int64_t>(cap_here, (int64_t)(rb.cap / WFS_RECORD_BYTES));
-        d_rec = rb.as<uint8_t>();
+    // records are produced in a device buffer of the lane; with host outputs two buffers alternate:
+    // batch k is copied to the host on the copy stream while the lane's next batch runs
+    const int par = so.resident ? 0 : (int)(L.local_batches & 1);
+    DevBuf &rb = par ? F.b_records2 : F.b_records;
+    if (!so.resident && F.copy_pending[par]) {
+        WFS_CUDA_CHECK(cudaEventSynchronize(F.ev_copy[par]));
+        F.copy_pending[par] = false;
     }
+    const bool want_records = so.resident || (out && out->records);
+    if (want_records)
+        rb.reserve((size_t)WFS_RECORD_BYTES * (size_t)std::max<int64_t>(2 * (n_ph + n_ap) + 65536, 1));
+    int64_t cap_here = want_records ? (int64_t)(rb.cap / WFS_RECORD_BYTES) : 0;
+    uint8_t *d_rec = rb.as<uint8_t>();
     if (ngroups > 0) {
-        H->backend->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res);
+        L.B->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res);
         if (res.error) {
             H->last_error = res.error == WFS_E_PULSE_CACHE_TOO_LONG ? "Pulse cache too long"
                                                                     : "back end error (key bits)";
             throw std::runtime_error(H->last_error);
         }
-        const int64_t user_room = so.resident ? (int64_t(1) << 40)
-                                               : (out && out->records && !so.overflow ? out->cap_records - so.n_rec : 0);
-        if (res.n_records > cap_here && res.n_records <= user_room) {
-            // the device buffer was too small (not the caller's): grow it and redo the back end
-            DevBuf &rb = so.resident ? F.b_records : ((so.n_batches & 1) ? F.b_records2 : F.b_records);
+        if (want_records && res.n_records > cap_here) {
+            // the device buffer was too small: grow it and redo the back end
             rb.reserve((size_t)WFS_RECORD_BYTES * (size_t)res.n_records);
-            cap_here = std::min<int64_t>(user_room, (int64_t)(rb.cap / WFS_RECORD_BYTES));
+            cap_here = (int64_t)(rb.cap / WFS_RECORD_BYTES);
             d_rec = rb.as<uint8_t>();
             WFS_CUDA_CHECK(cudaMemsetAsync(F.b_trig.p, 0, 4 * (size_t)std::max<int64_t>(2 * npc, 1), s));
-            H->backend->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res);
-        }
-    }
-    // ---- outputs ----
-    wfs_counts *cn = so.counts;
-    const bool fits = res.n_records <= cap_here;
-    if (!so.resident) {
-        if (!fits) so.overflow = true;
-        if (fits && res.n_records > 0) {
-            const int par = (int)(so.n_batches & 1);
-            if (!F.ev_ready) {
-                WFS_CUDA_CHECK(cudaEventCreateWithFlags(&F.ev_ready, cudaEventDisableTiming));
-                WFS_CUDA_CHECK(cudaEventCreateWithFlags(&F.ev_copy[0], cudaEventDisableTiming));
-                WFS_CUDA_CHECK(cudaEventCreateWithFlags(&F.ev_copy[1], cudaEventDisableTiming));
-            }
-            WFS_CUDA_CHECK(cudaEventRecord(F.ev_ready, s));
-            WFS_CUDA_CHECK(cudaStreamWaitEvent(H->copy_stream, F.ev_ready, 0));
-            WFS_CUDA_CHECK(cudaMemcpyAsync(out->records + (size_t)so.n_rec * WFS_RECORD_BYTES, d_rec,
-                                           (size_t)res.n_records * WFS_RECORD_BYTES, cudaMemcpyDeviceToHost,
-                                           H->copy_stream));
-            WFS_CUDA_CHECK(cudaEventRecord(F.ev_copy[par], H->copy_stream));
-            F.copy_pending[par] = true;
+            L.B->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res);
         }
     }
     std::vector<wfs_group_info> h_groups((size_t)ngroups);
@@ -740,15 +745,13 @@ static void simulate_batch(Handle *H, Plan &P, const BatchSpec &bs, uint64_t see
     std::vector<int32_t> trig((size_t)std::max<int64_t>(2 * npc, 1), 0);
     if (npc) WFS_CUDA_CHECK(cudaMemcpyAsync(trig.data(), F.b_trig.p, 4 * (size_t)(2 * npc), cudaMemcpyDeviceToHost, s));
     WFS_CUDA_CHECK(cudaStreamSynchronize(s));
-    if (out && out->groups)
-        for (int32_t gi = 0; gi < ngroups; gi++)
-            if (so.n_groups + gi < out->cap_groups) out->groups[so.n_groups + gi] = h_groups[gi];
-    if (out && out->batch_records && so.n_batches < out->cap_batches)
-        for (int k = 0; k < 3; k++) out->batch_records[3 * so.n_batches + k] = fits ? res.n_rec_class[k] : 0;
-    // truth rows (rawdata.py:313-375), one per Pulse call
+    // truth rows of this batch (rawdata.py:313-375), one per Pulse call
+    struct RunSum { int64_t sum[A_COUNT]; bool row; };
+    std::vector<RunSum> rsum((size_t)nruns);
+    int64_t n_pe = 0, n_truth_here = 0;
     for (int64_t r = 0; r < nruns; r++) {
         const Run &run = runs[r];
-        int64_t sum[A_COUNT];
+        int64_t *sum = rsum[r].sum;
         for (int a = 0; a < A_COUNT; a++) sum[a] = 0;
         sum[A_TMIN] = sum[A_ETMIN] = LLONG_MAX;
         sum[A_TMAX] = sum[A_ETMAX] = LLONG_MIN;
@@ -760,9 +763,62 @@ static void simulate_batch(Handle *H, Plan &P, const BatchSpec &bs, uint64_t see
                 else sum[k] += a[k];
             }
         }
-        cn->n_pe += sum[A_NPH] + sum[A_NDPE];
-        if (sum[A_NPHALL] == 0 && run.type != 1 && run.type != 2) continue;   // rawdata.py:336-337
-        if (out && out->truth && so.n_truth < out->cap_truth) {
+        n_pe += sum[A_NPH] + sum[A_NDPE];
+        rsum[r].row = !(sum[A_NPHALL] == 0 && run.type != 1 && run.type != 2);   // rawdata.py:336-337
+        n_truth_here += rsum[r].row ? 1 : 0;
+    }
+    // ---- output ranges, in batch order ----
+    wfs_counts *cn = so.counts;
+    int64_t rec0 = 0, truth0 = 0, groups0 = 0;
+    bool fits = false;
+    {
+        std::unique_lock<std::mutex> lk(ord.mu);
+        ord.cv.wait(lk, [&] { return ord.abort || ord.out_done == batch_index; });
+        if (ord.abort) throw LaneAborted();
+        rec0 = so.n_rec; truth0 = so.n_truth; groups0 = so.n_groups;
+        const int64_t user_room = so.resident ? (int64_t(1) << 40)
+                                               : (out && out->records && !so.overflow ? out->cap_records - so.n_rec : 0);
+        fits = res.n_records <= cap_here && res.n_records <= user_room;
+        if (!so.resident && !fits) so.overflow = true;
+        so.n_rec += res.n_records;
+        so.n_truth += n_truth_here;
+        so.n_groups += ngroups;
+        so.n_batches = std::max(so.n_batches, batch_index + 1);
+        for (int k = 0; k < 3; k++) cn->n_records[k] += fits ? res.n_rec_class[k] : 0;
+        cn->n_pe += n_pe;
+        cn->n_photons += res.n_valid_photons;
+        cn->n_pulses += res.n_pulses;
+        cn->n_windows += res.n_windows;
+        cn->n_intervals += res.n_intervals;
+        cn->n_samples += res.n_samples;
+        cn->n_pulse_calls += nruns;
+        cn->n_instructions += ntot;
+        cn->ms_digitize += res.ms_digitize;
+        cn->ms_phase[0] += ms_front;
+        cn->ms_phase[7] += ms_host;
+        for (int k = 1; k <= 6; k++) cn->ms_phase[k] += res.ms_phase[k];
+        ord.out_done = batch_index + 1;
+    }
+    ord.cv.notify_all();
+    if (!so.resident && fits && res.n_records > 0) {
+        WFS_CUDA_CHECK(cudaEventRecord(F.ev_ready, s));
+        WFS_CUDA_CHECK(cudaStreamWaitEvent(L.copy_stream, F.ev_ready, 0));
+        WFS_CUDA_CHECK(cudaMemcpyAsync(out->records + (size_t)rec0 * WFS_RECORD_BYTES, d_rec,
+                                       (size_t)res.n_records * WFS_RECORD_BYTES, cudaMemcpyDeviceToHost,
+                                       L.copy_stream));
+        WFS_CUDA_CHECK(cudaEventRecord(F.ev_copy[par], L.copy_stream));
+        F.copy_pending[par] = true;
+    }
+    if (out && out->groups)
+        for (int32_t gi = 0; gi < ngroups; gi++)
+            if (groups0 + gi < out->cap_groups) out->groups[groups0 + gi] = h_groups[gi];
+    if (out && out->batch_records && batch_index < out->cap_batches)
+        for (int k = 0; k < 3; k++) out->batch_records[3 * batch_index + k] = fits ? res.n_rec_class[k] : 0;
+    int64_t trow = truth0;
+    for (int64_t r = 0; r < nruns; r++) {
+        if (!rsum[r].row) continue;
+        const Run &run = runs[r];
+        if (out && out->truth && trow < out->cap_truth) {
             long double pm, psig, em, esig;
             combine_moments(run.instr, T, acc.data(), A_NPHALL, A_SREL, A_SHI2, A_SHILO, A_SLO2, pm, psig);
             combine_moments(run.instr, T, acc.data(), A_NE, A_ESREL, A_EHI2, A_EHILO, A_ELO2, em, esig);
@@ -782,25 +838,90 @@ static void simulate_batch(Handle *H, Plan &P, const BatchSpec &bs, uint64_t see
             } else {
                 x = fx(i0); y = fy(i0); z = fz(i0); amp = fa(i0);
             }
-            write_truth_row(out->truth + (size_t)so.n_truth * WFS_TRUTH_BYTES, h0, run.type, T[i0], x, y, z,
-                            amp, sum, pm, psig, em, esig, trig[4 * r], trig[4 * r + 1], p);
+            write_truth_row(out->truth + (size_t)trow * WFS_TRUTH_BYTES, h0, run.type, T[i0], x, y, z,
+                            amp, rsum[r].sum, pm, psig, em, esig, trig[4 * r], trig[4 * r + 1], p);
         }
-        so.n_truth++;
+        trow++;
     }
-    so.n_rec += res.n_records;
-    so.n_groups += ngroups;
-    so.n_batches++;
-    group_base += ngroups;
-    for (int k = 0; k < 3; k++) cn->n_records[k] += fits ? res.n_rec_class[k] : 0;
-    cn->n_photons += res.n_valid_photons;
-    cn->n_pulses += res.n_pulses;
-    cn->n_windows += res.n_windows;
-    cn->n_intervals += res.n_intervals;
-    cn->n_samples += res.n_samples;
-    cn->n_pulse_calls += nruns;
-    cn->n_instructions += ntot;
-    cn->ms_digitize += res.ms_digitize;
-    for (int k = 1; k <= 6; k++) cn->ms_phase[k] += res.ms_phase[k];
+    L.local_batches++;
+}
+
+// Lane 0 is the handle's own stream / back end / front end; further lanes get their own stream and
+// workspaces and share the device tables.
+static void clone_tables(const Frontend &a, Frontend &b) {
+    b.spe_ppf = a.spe_ppf; b.spe_row = a.spe_row; b.n_spe_rows = a.n_spe_rows; b.spe_len = a.spe_len;
+    b.lum_cdf = a.lum_cdf; b.lum_t = a.lum_t; b.lum_len = a.lum_len;
+    b.n_ap = a.n_ap;
+    for (int e = 0; e < WFS_MAX_AP_ELEMENTS; e++) {
+        b.ap_is_uniform[e] = a.ap_is_uniform[e];
+        b.ap_delay_cdf[e] = a.ap_delay_cdf[e]; b.ap_delay_len[e] = a.ap_delay_len[e];
+        b.ap_delay_bin[e] = a.ap_delay_bin[e];
+        b.ap_amp_cdf[e] = a.ap_amp_cdf[e]; b.ap_amp_len[e] = a.ap_amp_len[e];
+        b.ap_amp_rows[e] = a.ap_amp_rows[e]; b.ap_amp_bin[e] = a.ap_amp_bin[e];
+    }
+    b.pi_coarse_time = a.pi_coarse_time; b.pi_coarse_prob = a.pi_coarse_prob; b.pi_coarse_len = a.pi_coarse_len;
+    b.h_pi_coarse_time = a.h_pi_coarse_time;
+}
+
+static void init_copy_events(Frontend &F) {
+    if (F.ev_ready) return;
+    WFS_CUDA_CHECK(cudaEventCreateWithFlags(&F.ev_ready, cudaEventDisableTiming));
+    WFS_CUDA_CHECK(cudaEventCreateWithFlags(&F.ev_copy[0], cudaEventDisableTiming));
+    WFS_CUDA_CHECK(cudaEventCreateWithFlags(&F.ev_copy[1], cudaEventDisableTiming));
+}
+
+static void ensure_lanes(Handle *H, int n) {
+    while ((int)H->lanes.size() < n) {
+        Lane *L = new Lane();
+        L->id = (int)H->lanes.size();
+        if (L->id == 0) {
+            L->stream = H->stream; L->copy_stream = H->copy_stream;
+            L->F = H->frontend; L->B = H->backend;
+        } else {
+            WFS_CUDA_CHECK(cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
+            WFS_CUDA_CHECK(cudaStreamCreateWithFlags(&L->copy_stream, cudaStreamNonBlocking));
+            L->F = new Frontend(H);
+            clone_tables(*H->frontend, *L->F);
+            L->F->prim.stream = L->stream;
+            L->F->prim.lc = &H->launches;
+            L->B = new Backend(&H->cfg, L->stream, &H->launches);
+        }
+        WFS_CUDA_CHECK(cudaEventCreate(&L->ev_c));
+        WFS_CUDA_CHECK(cudaEventCreate(&L->ev_d));
+        WFS_CUDA_CHECK(cudaEventCreateWithFlags(&L->ev_done, cudaEventDisableTiming));
+        init_copy_events(*L->F);
+        H->lanes.push_back(L);
+    }
+}
+
+static void release_frontend_buffers(Frontend &F) {
+    DevBuf *all[] = {&F.b_itype, &F.b_itime, &F.b_ix, &F.b_iy, &F.b_iz, &F.b_iamp, &F.b_igidx, &F.b_ilce,
+                     &F.b_iscg, &F.b_icy, &F.b_ipat, &F.b_dmean, &F.b_dspread, &F.b_nemit, &F.b_emitoff,
+                     &F.b_nhits, &F.b_acc, &F.b_cdf, &F.b_cdfok, &F.b_pattern, &F.b_et, &F.b_einstr,
+                     &F.b_enph, &F.b_ephoff, &F.b_pht, &F.b_phch, &F.b_phgain, &F.b_phinstr, &F.b_phflags,
+                     &F.b_phnap, &F.b_apoff, &F.b_picount, &F.b_pioff, &F.b_irun, &F.b_pcgroup,
+                     &F.b_pcrank, &F.b_trig, &F.b_records, &F.b_records2, &F.b_groups, &F.b_scal};
+    for (DevBuf *b : all) b->release();
+    F.prim.release();
+    if (F.ev_ready) {
+        cudaEventDestroy(F.ev_ready); cudaEventDestroy(F.ev_copy[0]); cudaEventDestroy(F.ev_copy[1]);
+        F.ev_ready = nullptr;
+    }
+}
+
+void Handle::lanes_release() {
+    for (Lane *L : lanes) {
+        cudaEventDestroy(L->ev_c); cudaEventDestroy(L->ev_d); cudaEventDestroy(L->ev_done);
+        if (L->id != 0) {
+            release_frontend_buffers(*L->F);
+            delete L->F;
+            delete L->B;
+            cudaStreamDestroy(L->stream);
+            cudaStreamDestroy(L->copy_stream);
+        }
+        delete L;
+    }
+    lanes.clear();
 }
 
 static int run_plan(Handle *H, Plan &P, uint64_t seed, wfs_outputs *out, wfs_counts *counts, bool resident,
@@ -813,14 +934,52 @@ static int run_plan(Handle *H, Plan &P, uint64_t seed, wfs_outputs *out, wfs_cou
     so.counts = counts;
     so.resident = resident;
     so.dump = dump;
+    const int64_t nb = (int64_t)P.batches.size();
+    const int n_lanes = dump ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(env_i64("WFS_LANES", 2), nb));
+    ensure_lanes(H, std::max(n_lanes, 1));
     cudaStream_t s = H->stream;
     WFS_CUDA_CHECK(cudaEventRecord(H->ev_a, s));
-    int64_t group_base = 0;
-    for (const BatchSpec &bs : P.batches) simulate_batch(H, P, bs, seed, so, group_base);
+    Order ord;
+    std::exception_ptr failure[8] = {};
+    auto lane_loop = [&](int li) {
+        try {
+            WFS_CUDA_CHECK(cudaSetDevice(H->device));
+            for (int64_t k = li; k < nb; k += n_lanes) simulate_batch(H, *H->lanes[li], P, k, P.batches[k], seed, so, ord);
+        } catch (const LaneAborted &) {
+        } catch (...) {
+            failure[li] = std::current_exception();
+            {
+                std::lock_guard<std::mutex> lk(ord.mu);
+                ord.abort = true;
+            }
+            ord.cv.notify_all();
+        }
+    };
+    {
+        std::vector<std::thread> workers;
+        for (int li = 1; li < n_lanes; li++) workers.emplace_back(lane_loop, li);
+        lane_loop(0);
+        for (auto &t : workers) t.join();
+    }
+    for (int li = 0; li < n_lanes; li++)
+        if (failure[li]) {
+            for (int lj = 0; lj < n_lanes; lj++) {   // drain before reporting
+                cudaStreamSynchronize(H->lanes[lj]->stream);
+                cudaStreamSynchronize(H->lanes[lj]->copy_stream);
+                H->lanes[lj]->F->copy_pending[0] = H->lanes[lj]->F->copy_pending[1] = false;
+            }
+            std::rethrow_exception(failure[li]);
+        }
+    for (int li = 1; li < n_lanes; li++) {   // the closing event on lane 0 covers every lane
+        WFS_CUDA_CHECK(cudaEventRecord(H->lanes[li]->ev_done, H->lanes[li]->stream));
+        WFS_CUDA_CHECK(cudaStreamWaitEvent(s, H->lanes[li]->ev_done, 0));
+    }
     WFS_CUDA_CHECK(cudaEventRecord(H->ev_b, s));
-    WFS_CUDA_CHECK(cudaStreamSynchronize(s));
-    WFS_CUDA_CHECK(cudaStreamSynchronize(H->copy_stream));
-    H->frontend->copy_pending[0] = H->frontend->copy_pending[1] = false;
+    for (int li = 0; li < n_lanes; li++) {
+        WFS_CUDA_CHECK(cudaStreamSynchronize(H->lanes[li]->stream));
+        WFS_CUDA_CHECK(cudaStreamSynchronize(H->lanes[li]->copy_stream));
+        H->lanes[li]->F->copy_pending[0] = H->lanes[li]->F->copy_pending[1] = false;
+    }
     float ms;
     WFS_CUDA_CHECK(cudaEventElapsedTime(&ms, H->ev_a, H->ev_b));
     counts->ms_total = ms;
@@ -900,16 +1059,9 @@ void Handle::frontend_init(const wfs_tables &t) {
 }
 
 void Handle::frontend_release() {
+    lanes_release();
     if (!frontend) return;
-    Frontend &F = *frontend;
-    DevBuf *all[] = {&F.b_itype, &F.b_itime, &F.b_ix, &F.b_iy, &F.b_iz, &F.b_iamp, &F.b_igidx, &F.b_ilce,
-                     &F.b_iscg, &F.b_icy, &F.b_ipat, &F.b_dmean, &F.b_dspread, &F.b_nemit, &F.b_emitoff,
-                     &F.b_nhits, &F.b_acc, &F.b_cdf, &F.b_cdfok, &F.b_pattern, &F.b_et, &F.b_einstr,
-                     &F.b_enph, &F.b_ephoff, &F.b_pht, &F.b_phch, &F.b_phgain, &F.b_phinstr, &F.b_phflags,
-                     &F.b_phnap, &F.b_apoff, &F.b_picount, &F.b_pioff, &F.b_irun, &F.b_pcgroup,
-                     &F.b_pcrank, &F.b_trig, &F.b_records, &F.b_records2, &F.b_groups, &F.b_scal};
-    for (DevBuf *b : all) b->release();
-    F.prim.release();
+    release_frontend_buffers(*frontend);
     delete reinterpret_cast<Plan *>(staged_plan);
     staged_plan = nullptr;
     delete frontend;

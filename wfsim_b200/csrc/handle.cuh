@@ -5,6 +5,7 @@
 namespace wfs {
 
 struct Frontend;   // sampling stages + host scheduler (frontend.cu)
+struct Lane;       // stream + workspaces + host thread processing every n-th device batch (frontend.cu)
 
 struct Handle {
     int device = 0;
@@ -16,6 +17,7 @@ struct Handle {
     LaunchCounter launches;
     Backend *backend = nullptr;
     Frontend *frontend = nullptr;
+    std::vector<Lane *> lanes;          // lane 0 = (stream, backend, frontend) above
     std::string last_error;
     void *staged_plan = nullptr;        // Plan of wfs_stage_instructions (frontend.cu)
     // staging for host-pointer calls
@@ -25,6 +27,7 @@ struct Handle {
     ~Handle();
     void frontend_init(const wfs_tables &t);
     void frontend_release();
+    void lanes_release();
 };
 
 void pulse_call_ranks(const int32_t *group_of, int64_t n_pc, int64_t n_groups,
