@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define WFS_ABI_VERSION 1
+#define WFS_ABI_VERSION 2
 #define WFS_E_CAPACITY 1
 #define WFS_E_CUDA (-1)
 #define WFS_E_ARG (-2)
@@ -79,7 +79,15 @@ typedef struct wfs_params {
     double photoionization_modifier;           /* afterpulse.py:39 */
     double photoelectric_modifier, photoelectric_p, photoelectric_t_center, photoelectric_t_spread; /* afterpulse.py:108-115 */
     double ele_ap_n;                /* uniform_to_ele_ap.n, afterpulse.py:37 */
-    double s2_aft_sigma, s2_aft_skewness; /* s2.py:630-631 */
+    double s2_aft_sigma, s2_aft_skewness; /* s2.py:630-631 (applied on the host, per-instruction pattern rows) */
+    /* S1 'custom' model (s1.py:201-217, 263-337): timing by recoil type (NestId, s1.py:19-30) */
+    int32_t s1_model_custom;        /* 'custom' in s1_model_type */
+    int32_t gf_avgt;                /* int(np.average(s2_luminescence['t'])), s2.py:408 */
+    double singlet_lifetime_liquid, triplet_lifetime_liquid;   /* pulse.py:331-333 */
+    double s1_ER_alpha_singlet_fraction, s1_NR_singlet_fraction, led_pulse_length; /* s1.py:271,279,337 */
+    /* S2 'garfield' luminescence (s2.py:381-409) */
+    double anode_xaxis_angle, anode_pitch;      /* defaults pi/4, 0.5 */
+    double s2_garfield_confine_position;        /* <= 0: distance to the nearest anode wire from xy */
 } wfs_params;
 
 /* Tables (host pointers, copied to the device at wfs_create).  A NULL pointer means "absent". */
@@ -114,6 +122,19 @@ typedef struct wfs_tables {
     const double *pi_coarse_time;   /* [pi_coarse_len] */
     const double *pi_coarse_prob;   /* [pi_coarse_len] */
     int32_t pi_coarse_len;
+    /* optical propagation delays (resource.s1/s2_optical_propagation_spline, regular grids with
+     * linear interpolation / extrapolation as scipy's RegularGridInterpolator(fill_value=None)):
+     * S1: delay(z, U) per array (s1.py:241-260); S2: delay(U) per array (s2.py:486-501) */
+    const double *s1_op_top, *s1_op_bottom;     /* [s1_op_nz][s1_op_nu] */
+    int32_t s1_op_nz, s1_op_nu;
+    double s1_op_z0, s1_op_z1, s1_op_u0, s1_op_u1;
+    const double *s2_op_top, *s2_op_bottom;     /* [s2_op_nu] */
+    int32_t s2_op_nu;
+    double s2_op_u0, s2_op_u1;
+    /* S2 'garfield' luminescence (resource.s2_luminescence, s2.py:381-409) */
+    const int32_t *gf_t;            /* [gf_rows][gf_cols] emission times */
+    const double *gf_x;             /* [gf_rows] distance to the anode wire of each row */
+    int32_t gf_rows, gf_cols;
 } wfs_tables;
 
 /* Per-instruction map values evaluated on the host with the reference's own map objects
@@ -130,6 +151,13 @@ typedef struct wfs_instr_maps {
     const uint64_t *rng_id;         /* [n_instr] Philox identity of each instruction; NULL -> its index.
                                      * Shards of one instruction set pass the global indices so that the
                                      * result does not depend on the sharding. */
+    /* field dependencies (s2.py:139-179): per-instruction drift velocity [cm/ns] and longitudinal
+     * diffusion constant [cm^2/ns]; NULL -> the config constants */
+    const double *drift_velocity;
+    const double *diffusion_long;
+    /* observed S2 position after the field-distortion model (s2.py:80-87); used by the garfield
+     * luminescence model for the distance to the anode wires; NULL -> the instruction's x, y */
+    const double *x_obs, *y_obs;
 } wfs_instr_maps;
 
 typedef struct wfs_counts {

@@ -222,6 +222,9 @@ def main():
     if 'stoch' in which:
         from tests.golden import make_golden_stoch
         make_golden_stoch.main(ref, c0_config)
+    if 'models' in which:
+        from tests.golden import make_golden_models
+        make_golden_models.main(ref, c0_config)
 
 
 if __name__ == '__main__':

@@ -1,0 +1,63 @@
+"""Synthetic regular-grid maps / tables standing in for the XENON resource files that are not
+public (optical-propagation splines, garfield luminescence table, field maps).  The same objects
+are injected into the unmodified reference (golden generation) and into wfsim_b200 (tests)."""
+import numpy as np
+
+from wfsim_b200.resource import GridMap
+
+
+def s1_optical_spline():
+    z = np.linspace(-150.0, 0.0, 16)
+    u = np.linspace(0.0, 1.0, 65)
+    zz, uu = np.meshgrid(z, u, indexing='ij')
+    top = 4.0 + 60.0 * uu ** 2 * (1.0 + (-zz) / 150.0)
+    bottom = 2.0 + 35.0 * uu * (1.0 + (150.0 + zz) / 300.0)
+    return GridMap([(-150.0, 0.0, 16), (0.0, 1.0, 65)], dict(top=top, bottom=bottom))
+
+
+def s2_optical_spline():
+    u = np.linspace(0.0, 1.0, 129)
+    return GridMap([(0.0, 1.0, 129)], dict(top=3.0 + 40.0 * u ** 3, bottom=5.0 + 70.0 * u ** 2))
+
+
+def garfield_table():
+    rng = np.random.default_rng(2024)
+    x = np.linspace(-0.25, 0.25, 11)
+    t = np.stack([np.sort(rng.exponential(120.0 + 600.0 * abs(xx), 400)) + 200.0 * abs(xx) for xx in x])
+    return dict(x=x, t=np.round(t).astype(np.int64))
+
+
+def fdc_3d_map():
+    """r-correction dr(x, y, z) [cm] on a coarse 3-D grid."""
+    ax = [(-60.0, 60.0, 13), (-60.0, 60.0, 13), (-155.0, 5.0, 9)]
+    g = [np.linspace(lo, hi, n) for lo, hi, n in ax]
+    X, Y, Z = np.meshgrid(*g, indexing='ij')
+    R = np.sqrt(X ** 2 + Y ** 2)
+    return GridMap(ax, dict(map=0.02 * R * (-Z) / 150.0))
+
+
+def fd_comsol_map():
+    ax = [(0.0, 70.0, 15), (-155.0, 5.0, 9)]
+    g = [np.linspace(lo, hi, n) for lo, hi, n in ax]
+    R, Z = np.meshgrid(*g, indexing='ij')
+    return GridMap(ax, dict(r_distortion_map=R * (1.0 - 0.05 * (-Z) / 150.0)))
+
+
+class FieldDependencies:
+    """resource.field_dependencies_map / diffusion_longitudinal_map take (z, xy) (load_resource.py:335-338)."""
+
+    def __init__(self):
+        ax = [(0.0, 70.0, 8), (-155.0, 5.0, 9)]
+        g = [np.linspace(lo, hi, n) for lo, hi, n in ax]
+        R, Z = np.meshgrid(*g, indexing='ij')
+        self.m = GridMap(ax, dict(drift_speed_map=0.9 + 0.5 * (-Z) / 150.0 + 0.002 * R,      # mm/us
+                                  survival_probability_map=np.clip(1.05 - 0.004 * R, 0, 1.2),
+                                  diffusion=(20.0 + 0.2 * R + 0.05 * (-Z)) * 1e-9))          # cm^2/ns
+
+    def field_dependencies_map(self, z, xy, map_name):
+        r = np.sqrt(xy[:, 0] ** 2 + xy[:, 1] ** 2)
+        return self.m(np.array([r, z]).T, map_name=map_name)
+
+    def diffusion_longitudinal_map(self, z, xy):
+        r = np.sqrt(xy[:, 0] ** 2 + xy[:, 1] ** 2)
+        return self.m(np.array([r, z]).T, map_name='diffusion')

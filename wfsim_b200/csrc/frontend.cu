@@ -161,6 +161,7 @@ struct Plan {
     std::vector<BatchSpec> batches;
     // map values
     std::vector<double> lce, scg, cy;
+    std::vector<double> vd, dl, xo, yo;      // optional (empty = absent)
     std::vector<float> pattern;
     std::vector<int32_t> patrow;
     std::vector<uint64_t> rng_id;
@@ -204,6 +205,21 @@ static void make_plan(Handle *H, const uint8_t *rows, int64_t n, const wfs_instr
     if (maps && maps->s1_lce) std::copy(maps->s1_lce, maps->s1_lce + n, P.lce.begin());
     if (maps && maps->s2_sc_gain) std::copy(maps->s2_sc_gain, maps->s2_sc_gain + n, P.scg.begin());
     if (maps && maps->s2_cy_extra) std::copy(maps->s2_cy_extra, maps->s2_cy_extra + n, P.cy.begin());
+    P.vd.clear(); P.dl.clear(); P.xo.clear(); P.yo.clear();
+    if (maps && maps->drift_velocity) P.vd.assign(maps->drift_velocity, maps->drift_velocity + n);
+    if (maps && maps->diffusion_long) P.dl.assign(maps->diffusion_long, maps->diffusion_long + n);
+    if (maps && maps->x_obs && maps->y_obs) {
+        P.xo.assign(maps->x_obs, maps->x_obs + n);
+        P.yo.assign(maps->y_obs, maps->y_obs + n);
+    }
+    if (p.s1_model_custom)
+        for (int64_t i = 0; i < n; i++) {
+            const HostInstr &h = P.instr[i];
+            if (h.type == 1 && !(h.recoil == 0 || h.recoil == 6 || h.recoil == 20))
+                // s1.py:205-217: ER goes to S1.er, which fails in the reference (undefined `units`);
+                // anything else raises AttributeError there
+                throw std::runtime_error("Recoil type must be ER, NR, alpha or LED (custom S1 model: only NR, alpha and LED are usable)");
+        }
     if (maps && maps->pattern && maps->n_pattern_rows > 0) {
         P.pattern_rows = maps->n_pattern_rows;
         P.pattern.assign(maps->pattern, maps->pattern + maps->n_pattern_rows * n_ch);
@@ -219,8 +235,11 @@ static void make_plan(Handle *H, const uint8_t *rows, int64_t n, const wfs_instr
     const int64_t sample_budget = env_i64("WFS_BATCH_SAMPLES", 1500000000);
     const int64_t instr_budget = env_i64("WFS_BATCH_INSTRUCTIONS", 400000);
     const bool secondaries = p.enable_electron_afterpulses && H->frontend && H->frontend->pi_coarse_len > 0;
-    const double quiet = (double)p.right_raw_extension +
-                         (secondaries ? H->frontend->h_pi_coarse_time.back() + 50000.0 : 0.0);
+    double quiet = (double)p.right_raw_extension +
+                   (secondaries ? H->frontend->h_pi_coarse_time.back() + 50000.0 : 0.0);
+    if (p.enable_gate_afterpulses && p.photoelectric_p > 0.0)
+        quiet = std::max(quiet, (double)p.right_raw_extension + p.photoelectric_t_center + p.drift_time_gate +
+                                    6.0 * p.photoelectric_t_spread + 50000.0);
     const int64_t n_cl = (int64_t)P.cluster_start.size() - 1;
     P.batches.clear();
     int64_t c0 = 0;
@@ -240,7 +259,7 @@ static void make_plan(Handle *H, const uint8_t *rows, int64_t n, const wfs_instr
         bool over2 = ph > 2 * ph_budget || smp > 2 * sample_budget || ni > 2 * instr_budget;
         if (over && c + 1 < n_cl) {
             double gap = (double)(P.stime[P.order[P.cluster_start[c + 1]]] - P.stime[P.order[P.cluster_start[c + 1] - 1]]);
-            if (gap > quiet || over2) {
+            if (gap > quiet || over2) {   // `secondaries` only documents why quiet is long
                 P.batches.push_back({c0, c + 1});
                 c0 = c + 1;
                 ph = smp = 0;
@@ -302,6 +321,12 @@ static GenCtx make_ctx(Frontend &F, uint64_t seed) {
     g.i_amp = F.b_iamp.as<int32_t>(); g.i_gidx = F.b_igidx.as<uint64_t>();
     g.i_lce = F.b_ilce.as<double>(); g.i_scg = F.b_iscg.as<double>(); g.i_cy = F.b_icy.as<double>();
     g.i_pat = F.b_ipat.as<int32_t>();
+    g.i_vd = F.has_vd ? F.b_ivd.as<double>() : nullptr;
+    g.i_dl = F.has_dl ? F.b_idl.as<double>() : nullptr;
+    g.i_xo = F.has_xy ? F.b_ixo.as<double>() : nullptr;
+    g.i_yo = F.has_xy ? F.b_iyo.as<double>() : nullptr;
+    g.i_recoil = F.b_irecoil.as<int32_t>();
+    g.i_lrow = F.b_ilrow.as<int32_t>();
     g.i_dmean = F.b_dmean.as<double>(); g.i_dspread = F.b_dspread.as<double>();
     g.i_nemit = F.b_nemit.as<uint32_t>(); g.i_emitoff = F.b_emitoff.as<uint32_t>();
     g.i_nhits = F.b_nhits.as<int64_t>(); g.i_acc = F.b_acc.as<int64_t>();
@@ -322,6 +347,11 @@ static GenCtx make_ctx(Frontend &F, uint64_t seed) {
         g.ap_amp_rows[e] = F.ap_amp_rows[e]; g.ap_amp_bin[e] = F.ap_amp_bin[e];
     }
     g.pi_time = F.pi_coarse_time; g.pi_prob = F.pi_coarse_prob; g.pi_len = F.pi_coarse_len;
+    g.s1_op_top = F.s1_op_top; g.s1_op_bottom = F.s1_op_bottom; g.s2_op_top = F.s2_op_top; g.s2_op_bottom = F.s2_op_bottom;
+    g.s1_op_nz = F.s1_op_nz; g.s1_op_nu = F.s1_op_nu; g.s2_op_nu = F.s2_op_nu;
+    g.s1_op_z0 = F.s1_op_z0; g.s1_op_z1 = F.s1_op_z1; g.s1_op_u0 = F.s1_op_u0; g.s1_op_u1 = F.s1_op_u1;
+    g.s2_op_u0 = F.s2_op_u0; g.s2_op_u1 = F.s2_op_u1;
+    g.gf_t = F.gf_t; g.gf_x = F.gf_x; g.gf_rows = F.gf_rows; g.gf_cols = F.gf_cols;
     g.seed = seed;
     return g;
 }
@@ -337,6 +367,7 @@ static void grow_instr(Frontend &F, int64_t n_new, int64_t n_old, cudaStream_t s
     g(F.b_itype, 4); g(F.b_itime, 8); g(F.b_ix, 4); g(F.b_iy, 4); g(F.b_iz, 4); g(F.b_iamp, 4);
     g(F.b_igidx, 8); g(F.b_ilce, 8); g(F.b_iscg, 8); g(F.b_icy, 8); g(F.b_ipat, 4);
     g(F.b_dmean, 8); g(F.b_dspread, 8); g(F.b_nemit, 4); g(F.b_nhits, 8);
+    g(F.b_ivd, 8); g(F.b_idl, 8); g(F.b_ixo, 8); g(F.b_iyo, 8); g(F.b_irecoil, 4); g(F.b_ilrow, 4);
     F.b_emitoff.reserve_keep(4 * (size_t)(n_new + 1), 4 * (size_t)(n_old + 1), s);
     F.b_irun.reserve_keep(4 * (size_t)n_new, 0, s);
 }
@@ -467,6 +498,10 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     std::vector<float> h_x(nprim), h_y(nprim), h_z(nprim);
     std::vector<uint64_t> h_gidx(nprim);
     std::vector<double> h_lce(nprim), h_scg(nprim), h_cy(nprim);
+    std::vector<int32_t> h_recoil(nprim);
+    F.has_vd = !P.vd.empty(); F.has_dl = !P.dl.empty(); F.has_xy = !P.xo.empty();
+    std::vector<double> h_vd(F.has_vd ? nprim : 0), h_dl(F.has_dl ? nprim : 0), h_xo(F.has_xy ? nprim : 0),
+        h_yo(F.has_xy ? nprim : 0);
     std::unordered_map<int32_t, int32_t> rowmap;
     std::vector<int32_t> rows_used;
     for (int64_t j = 0; j < nprim; j++) {
@@ -476,6 +511,10 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         h_x[j] = h.x; h_y[j] = h.y; h_z[j] = h.z;
         h_gidx[j] = P.rng_id[gi];
         h_lce[j] = P.lce[gi]; h_scg[j] = P.scg[gi]; h_cy[j] = P.cy[gi];
+        h_recoil[j] = h.recoil;
+        if (F.has_vd) h_vd[j] = P.vd[gi];
+        if (F.has_dl) h_dl[j] = P.dl[gi];
+        if (F.has_xy) { h_xo[j] = P.xo[gi]; h_yo[j] = P.yo[gi]; }
         auto it = rowmap.find(P.patrow[gi]);
         if (it == rowmap.end()) {
             it = rowmap.emplace(P.patrow[gi], (int32_t)rows_used.size()).first;
@@ -492,6 +531,10 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     up(F.b_iamp, h_amp.data(), 4 * nprim); up(F.b_igidx, h_gidx.data(), 8 * nprim);
     up(F.b_ilce, h_lce.data(), 8 * nprim); up(F.b_iscg, h_scg.data(), 8 * nprim);
     up(F.b_icy, h_cy.data(), 8 * nprim); up(F.b_ipat, h_pat.data(), 4 * nprim);
+    up(F.b_irecoil, h_recoil.data(), 4 * nprim);
+    if (F.has_vd) up(F.b_ivd, h_vd.data(), 8 * nprim);
+    if (F.has_dl) up(F.b_idl, h_dl.data(), 8 * nprim);
+    if (F.has_xy) { up(F.b_ixo, h_xo.data(), 8 * nprim); up(F.b_iyo, h_yo.data(), 8 * nprim); }
     // pattern rows of this batch -> CDF rows
     const int64_t nrows = (int64_t)rows_used.size();
     std::vector<float> h_rows((size_t)nrows * n_ch);
@@ -513,27 +556,46 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     std::vector<int64_t> sec_time;
     std::vector<float> sec_x, sec_y, sec_z;
     std::vector<int32_t> sec_amp;
-    if (p.enable_gate_afterpulses) throw std::runtime_error("enable_gate_afterpulses is not supported yet");
-    if (p.enable_electron_afterpulses && F.pi_coarse_len > 0 && n_ph > 0) {
-        F.b_picount.reserve(4 * (size_t)(nprim + 1));
-        F.b_pioff.reserve(4 * (size_t)(nprim + 1));
+    std::vector<int32_t> sec_type;
+    {
+        // pass 0: how many secondaries does every S2 primary spawn (photo-ionisation: type 4,
+        // rawdata.py:193-197; photo-electric / gate: type 6, rawdata.py:198-201)
+        const bool do_pi = p.enable_electron_afterpulses && F.pi_coarse_len > 0 && n_ph > 0;
+        const bool do_pe = p.enable_gate_afterpulses && p.photoelectric_p > 0.0 && n_ph > 0;
+        uint32_t nsec_pi = 0, nsec_pe = 0;
         GenCtx g = make_ctx(F, seed);
-        FLAUNCH(k_photoionization, div_up(nprim * 32, 128), 128, g, p, (uint32_t)nprim, 0,
-                F.b_picount.as<uint32_t>(), nullptr, 0u, nullptr);
-        F.prim.exclusive_scan_u32(F.b_picount.as<uint32_t>(), F.b_pioff.as<uint32_t>(), nprim, true);
-        uint32_t nsec;
-        WFS_CUDA_CHECK(cudaMemcpyAsync(&nsec, F.b_pioff.as<uint32_t>() + nprim, 4, cudaMemcpyDeviceToHost, s));
-        WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (do_pi) {
+            F.b_picount.reserve(4 * (size_t)(nprim + 1));
+            F.b_pioff.reserve(4 * (size_t)(nprim + 1));
+            FLAUNCH(k_photoionization, div_up(nprim * 32, 128), 128, g, p, (uint32_t)nprim, 0,
+                    F.b_picount.as<uint32_t>(), nullptr, 0u, nullptr);
+            F.prim.exclusive_scan_u32(F.b_picount.as<uint32_t>(), F.b_pioff.as<uint32_t>(), nprim, true);
+            WFS_CUDA_CHECK(cudaMemcpyAsync(&nsec_pi, F.b_pioff.as<uint32_t>() + nprim, 4, cudaMemcpyDeviceToHost, s));
+        }
+        if (do_pe) {
+            F.b_pecount.reserve(4 * (size_t)(nprim + 1));
+            F.b_peoff.reserve(4 * (size_t)(nprim + 1));
+            FLAUNCH(k_photoelectric, div_up(nprim * 32, 128), 128, g, p, (uint32_t)nprim, 0,
+                    F.b_pecount.as<uint32_t>(), nullptr, 0u, nullptr);
+            F.prim.exclusive_scan_u32(F.b_pecount.as<uint32_t>(), F.b_peoff.as<uint32_t>(), nprim, true);
+            WFS_CUDA_CHECK(cudaMemcpyAsync(&nsec_pe, F.b_peoff.as<uint32_t>() + nprim, 4, cudaMemcpyDeviceToHost, s));
+        }
+        if (do_pi || do_pe) WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+        const int64_t nsec = (int64_t)nsec_pi + nsec_pe;
         if (nsec > 0) {
             ntot = nprim + nsec;
             grow_instr(F, ntot, nprim, s);
             DevBuf d_parent;
             d_parent.reserve(4 * (size_t)ntot);
             g = make_ctx(F, seed);
-            FLAUNCH(k_photoionization, div_up(nprim * 32, 128), 128, g, p, (uint32_t)nprim, 1, nullptr,
-                    F.b_pioff.as<uint32_t>(), (uint32_t)nprim, d_parent.as<int32_t>());
+            if (nsec_pi)
+                FLAUNCH(k_photoionization, div_up(nprim * 32, 128), 128, g, p, (uint32_t)nprim, 1, nullptr,
+                        F.b_pioff.as<uint32_t>(), (uint32_t)nprim, d_parent.as<int32_t>());
+            if (nsec_pe)
+                FLAUNCH(k_photoelectric, div_up(nprim * 32, 128), 128, g, p, (uint32_t)nprim, 1, nullptr,
+                        F.b_peoff.as<uint32_t>(), (uint32_t)(nprim + nsec_pi), d_parent.as<int32_t>());
             h_parent.resize(nsec); sec_time.resize(nsec); sec_x.resize(nsec); sec_y.resize(nsec);
-            sec_z.resize(nsec); sec_amp.resize(nsec);
+            sec_z.resize(nsec); sec_amp.resize(nsec); sec_type.resize(nsec);
             auto down = [&](void *dst, const void *src, size_t bytes) {
                 WFS_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
             };
@@ -543,6 +605,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
             down(sec_y.data(), F.b_iy.as<float>() + nprim, 4 * (size_t)nsec);
             down(sec_z.data(), F.b_iz.as<float>() + nprim, 4 * (size_t)nsec);
             down(sec_amp.data(), F.b_iamp.as<int32_t>() + nprim, 4 * (size_t)nsec);
+            down(sec_type.data(), F.b_itype.as<int32_t>() + nprim, 4 * (size_t)nsec);
             WFS_CUDA_CHECK(cudaStreamSynchronize(s));
             d_parent.release();
             generate(H, F, s, seed, nprim, ntot, n_emit, n_ph);   // pass B
@@ -595,6 +658,23 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
                 }
             }
             d.n += m;
+        } else if (d.stage >= 2) {
+            // secondary instructions (photo-ionisation type 4, photo-electric type 6):
+            // t = time, gain = z (stage 2) or x^2 + y^2 (stage 3), channel = amp, flags = type
+            const int64_t nsec = ntot - nprim;
+            for (int64_t q = 0; q < nsec; q++) {
+                if (base + q < d.cap) {
+                    uint8_t *r = d.out + (base + q) * 32;
+                    const double x = sec_x[q], y = sec_y[q];
+                    wr<int64_t>(r, sec_time[q]);
+                    wr<double>(r + 8, d.stage == 2 ? (double)sec_z[q] : x * x + y * y);
+                    wr<int32_t>(r + 16, sec_amp[q]);
+                    wr<int32_t>(r + 20, (int32_t)P.order[j0 + h_parent[q]]);
+                    wr<int32_t>(r + 24, sec_type[q]);
+                    wr<int32_t>(r + 28, (int32_t)q);
+                }
+            }
+            d.n += nsec;
         } else {
             std::vector<int64_t> t(n_emit); std::vector<int32_t> in_(n_emit); std::vector<uint32_t> np_(n_emit);
             WFS_CUDA_CHECK(cudaMemcpyAsync(t.data(), F.b_et.p, 8 * n_emit, cudaMemcpyDeviceToHost, s));
@@ -642,7 +722,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         T[j] = h_time[j];
     }
     for (int64_t j = nprim; j < ntot; j++) {
-        in.type[j] = 4;
+        in.type[j] = (int8_t)sec_type[j - nprim];
         in.parent[j] = h_parent[j - nprim];
         T[j] = sec_time[j - nprim];
         in.stime[j] = signal_time(T[j], sec_z[j - nprim], 4, p.drift_velocity_liquid);
@@ -861,6 +941,11 @@ static void clone_tables(const Frontend &a, Frontend &b) {
     }
     b.pi_coarse_time = a.pi_coarse_time; b.pi_coarse_prob = a.pi_coarse_prob; b.pi_coarse_len = a.pi_coarse_len;
     b.h_pi_coarse_time = a.h_pi_coarse_time;
+    b.s1_op_top = a.s1_op_top; b.s1_op_bottom = a.s1_op_bottom; b.s2_op_top = a.s2_op_top; b.s2_op_bottom = a.s2_op_bottom;
+    b.s1_op_nz = a.s1_op_nz; b.s1_op_nu = a.s1_op_nu; b.s2_op_nu = a.s2_op_nu;
+    b.s1_op_z0 = a.s1_op_z0; b.s1_op_z1 = a.s1_op_z1; b.s1_op_u0 = a.s1_op_u0; b.s1_op_u1 = a.s1_op_u1;
+    b.s2_op_u0 = a.s2_op_u0; b.s2_op_u1 = a.s2_op_u1;
+    b.gf_t = a.gf_t; b.gf_x = a.gf_x; b.gf_rows = a.gf_rows; b.gf_cols = a.gf_cols;
 }
 
 static void init_copy_events(Frontend &F) {
@@ -896,10 +981,10 @@ static void ensure_lanes(Handle *H, int n) {
 
 static void release_frontend_buffers(Frontend &F) {
     DevBuf *all[] = {&F.b_itype, &F.b_itime, &F.b_ix, &F.b_iy, &F.b_iz, &F.b_iamp, &F.b_igidx, &F.b_ilce,
-                     &F.b_iscg, &F.b_icy, &F.b_ipat, &F.b_dmean, &F.b_dspread, &F.b_nemit, &F.b_emitoff,
+                     &F.b_iscg, &F.b_icy, &F.b_ipat, &F.b_ivd, &F.b_idl, &F.b_ixo, &F.b_iyo, &F.b_irecoil, &F.b_ilrow, &F.b_dmean, &F.b_dspread, &F.b_nemit, &F.b_emitoff,
                      &F.b_nhits, &F.b_acc, &F.b_cdf, &F.b_cdfok, &F.b_pattern, &F.b_et, &F.b_einstr,
                      &F.b_enph, &F.b_ephoff, &F.b_pht, &F.b_phch, &F.b_phgain, &F.b_phinstr, &F.b_phflags,
-                     &F.b_phnap, &F.b_apoff, &F.b_picount, &F.b_pioff, &F.b_irun, &F.b_pcgroup,
+                     &F.b_phnap, &F.b_apoff, &F.b_picount, &F.b_pioff, &F.b_pecount, &F.b_peoff, &F.b_irun, &F.b_pcgroup,
                      &F.b_pcrank, &F.b_trig, &F.b_records, &F.b_records2, &F.b_groups, &F.b_scal};
     for (DevBuf *b : all) b->release();
     F.prim.release();
@@ -1054,6 +1139,32 @@ void Handle::frontend_init(const wfs_tables &t) {
         F->pi_coarse_time = upload_table(t.pi_coarse_time, (size_t)t.pi_coarse_len, owned);
         F->pi_coarse_prob = upload_table(t.pi_coarse_prob, (size_t)t.pi_coarse_len, owned);
         F->h_pi_coarse_time.assign(t.pi_coarse_time, t.pi_coarse_time + t.pi_coarse_len);
+    }
+    if (p.s1_model_optical) {
+        if (!t.s1_op_top || !t.s1_op_bottom || t.s1_op_nz < 2 || t.s1_op_nu < 2)
+            throw std::runtime_error("s1_model_type contains optical_propagation but no s1_optical_propagation_spline grid was given");
+        F->s1_op_top = upload_table(t.s1_op_top, (size_t)t.s1_op_nz * t.s1_op_nu, owned);
+        F->s1_op_bottom = upload_table(t.s1_op_bottom, (size_t)t.s1_op_nz * t.s1_op_nu, owned);
+        F->s1_op_nz = t.s1_op_nz; F->s1_op_nu = t.s1_op_nu;
+        F->s1_op_z0 = t.s1_op_z0; F->s1_op_z1 = t.s1_op_z1; F->s1_op_u0 = t.s1_op_u0; F->s1_op_u1 = t.s1_op_u1;
+    }
+    if (p.s2_time_model == 2) {
+        if (!t.s2_op_top || !t.s2_op_bottom || t.s2_op_nu < 2)
+            throw std::runtime_error("s2_time_model is optical_propagation but no s2_optical_propagation_spline grid was given");
+        F->s2_op_top = upload_table(t.s2_op_top, (size_t)t.s2_op_nu, owned);
+        F->s2_op_bottom = upload_table(t.s2_op_bottom, (size_t)t.s2_op_nu, owned);
+        F->s2_op_nu = t.s2_op_nu; F->s2_op_u0 = t.s2_op_u0; F->s2_op_u1 = t.s2_op_u1;
+    }
+    if (p.s2_luminescence_model == 1) {
+        if (!t.gf_t || !t.gf_x || t.gf_rows < 1 || t.gf_cols < 1)
+            throw std::runtime_error("s2_luminescence model not found");   // s2.py:391
+        F->gf_t = upload_table(t.gf_t, (size_t)t.gf_rows * t.gf_cols, owned);
+        F->gf_x = upload_table(t.gf_x, (size_t)t.gf_rows, owned);
+        F->gf_rows = t.gf_rows; F->gf_cols = t.gf_cols;
+    } else if (p.s2_luminescence_model == 2) {
+        throw std::runtime_error("s2_luminescence_model 'garfield_gas_gap' is not built yet (DESIGN.md, next rows)");
+    } else if (p.s2_luminescence_model == 0 && F->lum_len <= 0) {
+        throw std::runtime_error("s2_luminescence_model 'simple' with enable_gas_gap_warping needs per-position gas gaps: not built yet; set enable_gas_gap_warping=False");
     }
     frontend = F;
 }

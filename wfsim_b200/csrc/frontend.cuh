@@ -74,15 +74,24 @@ struct Frontend {
     double *pi_coarse_time = nullptr, *pi_coarse_prob = nullptr;
     int32_t pi_coarse_len = 0;
     std::vector<double> h_pi_coarse_time;
+    // optical propagation grids and the garfield luminescence table
+    double *s1_op_top = nullptr, *s1_op_bottom = nullptr, *s2_op_top = nullptr, *s2_op_bottom = nullptr;
+    int32_t s1_op_nz = 0, s1_op_nu = 0, s2_op_nu = 0;
+    double s1_op_z0 = 0, s1_op_z1 = 1, s1_op_u0 = 0, s1_op_u1 = 1, s2_op_u0 = 0, s2_op_u1 = 1;
+    int32_t *gf_t = nullptr;
+    double *gf_x = nullptr;
+    int32_t gf_rows = 0, gf_cols = 0;
     Primitives prim;
     // workspaces
     DevBuf b_itype, b_itime, b_ix, b_iy, b_iz, b_iamp, b_igidx, b_ilce, b_iscg, b_icy, b_ipat,
+        b_ivd, b_idl, b_ixo, b_iyo, b_irecoil, b_ilrow,
         b_dmean, b_dspread, b_nemit, b_emitoff, b_nhits, b_acc, b_cdf, b_cdfok, b_pattern,
         b_et, b_einstr, b_enph, b_ephoff, b_pht, b_phch, b_phgain, b_phinstr, b_phflags, b_phnap,
-        b_apoff, b_picount, b_pioff, b_irun, b_pcgroup, b_pcrank, b_trig, b_records, b_records2,
+        b_apoff, b_picount, b_pioff, b_pecount, b_peoff, b_irun, b_pcgroup, b_pcrank, b_trig, b_records, b_records2,
         b_groups, b_scal;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_ready = nullptr;
     bool copy_pending[2] = {false, false};
+    bool has_vd = false, has_dl = false, has_xy = false;   // optional per-instruction arrays of the current batch
     int64_t *h_pin = nullptr;   // pinned scratch for small readbacks
     // staged instructions (device-resident measurement mode)
     std::vector<uint8_t> staged_instr;

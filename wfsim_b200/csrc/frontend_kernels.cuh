@@ -17,6 +17,10 @@ struct GenCtx {
     uint64_t *i_gidx;
     double *i_lce, *i_scg, *i_cy;
     int32_t *i_pat;
+    double *i_vd, *i_dl;          // per-instruction drift velocity / longitudinal diffusion, or nullptr
+    double *i_xo, *i_yo;          // observed xy (field distortion), or nullptr
+    int32_t *i_recoil;
+    int32_t *i_lrow;              // garfield luminescence: table row of the instruction
     double *i_dmean, *i_dspread;
     uint32_t *i_nemit, *i_emitoff;
     int64_t *i_nhits;
@@ -51,8 +55,37 @@ struct GenCtx {
     double ap_amp_bin[WFS_MAX_AP_ELEMENTS];
     const double *pi_time, *pi_prob;
     int32_t pi_len;
+    const double *s1_op_top, *s1_op_bottom, *s2_op_top, *s2_op_bottom;
+    int32_t s1_op_nz, s1_op_nu, s2_op_nu;
+    double s1_op_z0, s1_op_z1, s1_op_u0, s1_op_u1, s2_op_u0, s2_op_u1;
+    const int32_t *gf_t;
+    const double *gf_x;
+    int32_t gf_rows, gf_cols;
     uint64_t seed;
 };
+
+// Linear interpolation on a regular grid, extrapolating linearly outside it (what scipy's
+// RegularGridInterpolator(method='linear', bounds_error=False, fill_value=None) returns).
+__device__ __forceinline__ void grid_cell(double x, double lo, double hi, int n, int &i, double &w) {
+    const double f = (x - lo) / (hi - lo) * (double)(n - 1);
+    i = (int)floor(f);
+    i = max(0, min(i, n - 2));
+    w = f - (double)i;
+}
+__device__ __forceinline__ double grid_interp1(const double *tab, int n, double lo, double hi, double x) {
+    if (n < 2) return tab[0];
+    int i; double w;
+    grid_cell(x, lo, hi, n, i, w);
+    return tab[i] * (1.0 - w) + tab[i + 1] * w;
+}
+__device__ __forceinline__ double grid_interp2(const double *tab, int n0, int n1, double lo0, double hi0,
+                                               double lo1, double hi1, double x0, double x1) {
+    int i, j; double wi, wj;
+    grid_cell(x0, lo0, hi0, n0, i, wi);
+    grid_cell(x1, lo1, hi1, n1, j, wj);
+    const double *r0 = tab + (int64_t)i * n1, *r1 = r0 + n1;
+    return (r0[j] * (1.0 - wj) + r0[j + 1] * wj) * (1.0 - wi) + (r1[j] * (1.0 - wj) + r1[j + 1] * wj) * wi;
+}
 
 // first index in [0, n) with a[i] > key  (a ascending)
 template <typename T, typename K>
@@ -117,9 +150,31 @@ __global__ void k_instr(GenCtx g, wfs_params p, uint32_t i0, uint32_t i1) {
         nemit = nhits > 0 ? 1u : 0u;
     } else if (type == 2 || type == 4 || type == 6) {
         const double z = (double)g.i_z[i];
-        double mean = -z / p.drift_velocity_liquid + p.drift_time_gate;
+        const double vd = g.i_vd ? g.i_vd[i] : p.drift_velocity_liquid;       // s2.py:139-155
+        const double dl = g.i_dl ? g.i_dl[i] : p.diffusion_constant_longitudinal;
+        double mean = -z / vd + p.drift_time_gate;
         if (mean < 0.0) mean = 0.0;
-        double spread = sqrt(2.0 * p.diffusion_constant_longitudinal * mean) / p.drift_velocity_liquid;
+        double spread = sqrt(2.0 * dl * mean) / vd;
+        if (p.s2_luminescence_model == 1 && g.gf_rows > 0) {
+            // distance to the nearest anode wire -> nearest row of the garfield table (s2.py:396-404)
+            double d;
+            if (p.s2_garfield_confine_position > 0.0) {
+                d = (2.0 * rng.ud53() - 1.0) * p.s2_garfield_confine_position;
+            } else {
+                const double x = g.i_xo ? g.i_xo[i] : (double)g.i_x[i], y = g.i_yo ? g.i_yo[i] : (double)g.i_y[i];
+                const double rel = -x * sin(p.anode_xaxis_angle) + y * cos(p.anode_xaxis_angle);
+                double m = fmod(rel + 0.5 * p.anode_pitch, p.anode_pitch);
+                if (m < 0.0) m += p.anode_pitch;           // python modulo
+                d = m - 0.5 * p.anode_pitch;
+            }
+            int best = 0;
+            double bd = fabs(d - g.gf_x[0]);
+            for (int r = 1; r < g.gf_rows; r++) {
+                const double dd = fabs(d - g.gf_x[r]);
+                if (dd < bd) { bd = dd; best = r; }
+            }
+            g.i_lrow[i] = best;
+        }
         double cy = p.electron_extraction_yield * exp(-mean / p.electron_lifetime_liquid) * g.i_cy[i];
         cy = fmin(fmax(cy, 0.0), 1.0);
         int64_t ne = sample_binomial(amp, cy, rng.ud53());
@@ -191,18 +246,39 @@ k_photons(GenCtx g, wfs_params p, const double *gains, int n_ch, uint32_t n_emit
     float zs, zt;
     normal_pair(w1.v[0], w1.v[1], zs, zt);
     int64_t t = g.e_t[em];
+    const bool top = ch >= 0 && ch < p.n_top_pmts;
     if (type == 1) {
+        if (p.s1_model_optical && g.s1_op_top && ch >= 0)      // s1.py:186-189, 241-260
+            t += (int64_t)grid_interp2(top ? g.s1_op_top : g.s1_op_bottom, g.s1_op_nz, g.s1_op_nu, g.s1_op_z0,
+                                       g.s1_op_z1, g.s1_op_u0, g.s1_op_u1, (double)g.i_z[i], u01_32(w2.v[1]));
         if (p.s1_model_simple) {
             t += (int64_t)(exp1(w0.v[1]) * (float)p.s1_decay_time);
             t += (int64_t)(zs * (float)p.s1_decay_spread);
         }
+        if (p.s1_model_custom) {                                // s1.py:201-217, 263-337
+            const int rc = g.i_recoil[i];
+            if (rc == 20) {                                     // LED: uniform in the pulse length
+                t += (int64_t)(u01_32(w0.v[2]) * p.led_pulse_length);
+            } else {                                            // NR (0) / alpha (6): singlet / triplet decay
+                const double fs = rc == 0 ? p.s1_NR_singlet_fraction : p.s1_ER_alpha_singlet_fraction;
+                const double delay = u01_32(w0.v[2]) < fs ? p.singlet_lifetime_liquid : p.triplet_lifetime_liquid;
+                t += (int64_t)((double)exp1(w0.v[3]) * delay);
+            }
+        }
     } else {
         if (p.s2_luminescence_model == 0 && g.lum_len > 0)
             t += (int64_t)interp_table(g.lum_cdf, g.lum_t, g.lum_len, u01_32(w0.v[1]));
+        else if (p.s2_luminescence_model == 1 && g.gf_rows > 0) {   // s2.py:405-409
+            const int col = (int)(((uint64_t)w0.v[1] * (uint32_t)g.gf_cols) >> 32);
+            t += (int64_t)g.gf_t[(int64_t)g.i_lrow[i] * g.gf_cols + col] - (int64_t)p.gf_avgt;
+        }
         const double delay = u01_32(w0.v[2]) < p.singlet_fraction_gas ? p.singlet_lifetime_gas
                                                                       : p.triplet_lifetime_gas;
         t += (int64_t)((double)exp1(w0.v[3]) * delay);
-        if (p.s2_time_model == 0 && p.s2_time_spread > 0.0) t += (int64_t)(zs * (float)p.s2_time_spread);
+        if (p.s2_time_model == 2 && g.s2_op_top && ch >= 0)    // s2.py:486-501, 542-544
+            t += (int64_t)grid_interp1(top ? g.s2_op_top : g.s2_op_bottom, g.s2_op_nu, g.s2_op_u0, g.s2_op_u1,
+                                       u01_32(w2.v[1]));
+        else if (p.s2_time_model == 0 && p.s2_time_spread > 0.0) t += (int64_t)(zs * (float)p.s2_time_spread);
     }
     // PMT transit time spread (FWHM -> sigma), truncated toward zero
     t += (int64_t)(p.pmt_transit_time_mean + (double)zt * (p.pmt_transit_time_spread / 2.35482));
@@ -427,6 +503,10 @@ k_photoionization(GenCtx g, wfs_params p, uint32_t n_prim, int fill, uint32_t *c
                     g.i_scg[o] = g.i_scg[i];     // see DESIGN.md: map value of the parent position
                     g.i_cy[o] = g.i_cy[i];
                     g.i_pat[o] = g.i_pat[i];
+                    g.i_recoil[o] = g.i_recoil[i];
+                    if (g.i_vd) g.i_vd[o] = g.i_vd[i];
+                    if (g.i_dl) g.i_dl[o] = g.i_dl[i];
+                    if (g.i_xo) { g.i_xo[o] = r * cos(ang); g.i_yo[o] = r * sin(ang); }
                     sec_parent[o] = (int32_t)i;
                 }
                 total += __popc(m);
@@ -435,6 +515,62 @@ k_photoionization(GenCtx g, wfs_params p, uint32_t n_prim, int fill, uint32_t *c
         }
     }
     if (!fill && lane == 0) count[i] = total;
+}
+
+// Photo-electric (gate) electrons (afterpulse.py:105-135): n_e ~ Poisson(p * N_photons * modifier)
+// single-electron instructions of type 6, delayed by N(t_center + gate, t_spread) clipped at 0
+// behind a random photon of the S2.  One warp per primary instruction; pass 0 counts, pass 1 fills.
+__global__ void __launch_bounds__(128)
+k_photoelectric(GenCtx g, wfs_params p, uint32_t n_prim, int fill, uint32_t *count,
+                const uint32_t *offset, uint32_t out0, int32_t *sec_parent) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n_prim) return;
+    uint32_t n = 0;
+    uint32_t q0 = 0, nph = 0;
+    if (g.i_type[i] == 2) {
+        q0 = g.e_phoff[g.i_emitoff[i]];
+        nph = g.e_phoff[g.i_emitoff[i + 1]] - q0;
+        if (nph > 0) {
+            const Philox4 w = philox4x32(g.seed, RS_PE, g.i_gidx[i], 0u);
+            const int64_t k = sample_poisson(p.photoelectric_p * (double)nph * p.photoelectric_modifier,
+                                             u01_53(w.v[0], w.v[1]));
+            n = (uint32_t)min((int64_t)(1 << 24) - 1, k);
+        }
+    }
+    if (!fill) {
+        if (lane == 0) count[i] = n;
+        return;
+    }
+    const uint64_t gidx = g.i_gidx[i];
+    for (uint32_t j = lane; j < n; j += 32) {
+        const uint32_t o = out0 + offset[i] + j;
+        const Philox4 a = philox4x32(g.seed, RS_PE, gidx, 1u + 2u * j), b = philox4x32(g.seed, RS_PE, gidx, 2u + 2u * j);
+        const double u1 = 1.0 - u01_53(a.v[0], a.v[1]), u2 = u01_32(a.v[2]);
+        const double nrm = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+        double delay = p.photoelectric_t_center + p.drift_time_gate + p.photoelectric_t_spread * nrm;
+        if (delay < 0.0) delay = 0.0;
+        const uint32_t pick = q0 + (uint32_t)(((uint64_t)a.v[3] * nph) >> 32);
+        const double R = p.tpc_radius;
+        const double r = sqrt(u01_53(b.v[0], b.v[1]) * R * R);
+        const double ang = -3.141592653589793 + 6.283185307179586 * u01_32(b.v[2]);
+        g.i_type[o] = 6;
+        g.i_time[o] = (int64_t)((double)g.ph_t[pick] + p.drift_time_gate);
+        g.i_x[o] = (float)(r * cos(ang));
+        g.i_y[o] = (float)(r * sin(ang));
+        g.i_z[o] = (float)(-delay * p.drift_velocity_liquid);
+        g.i_amp[o] = 1;
+        g.i_gidx[o] = (1ull << 62) | (gidx << 24) | (uint64_t)j;
+        g.i_lce[o] = 1.0;
+        g.i_scg[o] = g.i_scg[i];
+        g.i_cy[o] = g.i_cy[i];
+        g.i_pat[o] = g.i_pat[i];
+        g.i_recoil[o] = g.i_recoil[i];
+        if (g.i_vd) g.i_vd[o] = g.i_vd[i];
+        if (g.i_dl) g.i_dl[o] = g.i_dl[i];
+        if (g.i_xo) { g.i_xo[o] = r * cos(ang); g.i_yo[o] = r * sin(ang); }
+        sec_parent[o] = (int32_t)i;
+    }
 }
 
 }  // namespace wfs

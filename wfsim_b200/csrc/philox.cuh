@@ -48,7 +48,7 @@ enum : uint32_t {
     RS_PHOTON = 4,      // per photon: channel, timing terms, TTS, DPE, SPE
     RS_AP = 5,          // per parent photon: PMT afterpulses (afterpulse.py:189-217)
     RS_PI = 6,          // per S2 pulse call: photo-ionisation (afterpulse.py:37-59)
-    RS_PE = 7,          // per S2 pulse call: photo-electric (afterpulse.py:108-128)
+    RS_PE = 7,          // per S2 pulse call: photo-electric (gate) electrons (afterpulse.py:105-135)
 };
 
 // uniform in [0,1) with 53 bits from two words

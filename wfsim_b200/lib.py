@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'csrc', 'libwfsim_b200.so')
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 E_CAPACITY = 1
 E_CUDA = -1
 E_ARG = -2
@@ -42,7 +42,12 @@ class Params(C.Structure):
             'tpc_radius', 'tpc_length', 'pmt_ap_modifier', 'pmt_ap_t_modifier',
             'photoionization_modifier', 'photoelectric_modifier', 'photoelectric_p',
             'photoelectric_t_center', 'photoelectric_t_spread', 'ele_ap_n',
-            's2_aft_sigma', 's2_aft_skewness')])
+            's2_aft_sigma', 's2_aft_skewness')]
+        + [('s1_model_custom', i32), ('gf_avgt', i32)]
+        + [(n, f64) for n in (
+            'singlet_lifetime_liquid', 'triplet_lifetime_liquid', 's1_ER_alpha_singlet_fraction',
+            's1_NR_singlet_fraction', 'led_pulse_length', 'anode_xaxis_angle', 'anode_pitch',
+            's2_garfield_confine_position')])
 
 
 class Tables(C.Structure):
@@ -56,13 +61,18 @@ class Tables(C.Structure):
         ('ap_delay_bin', f64 * MAX_AP_ELEMENTS),
         ('ap_amp_cdf', vp * MAX_AP_ELEMENTS), ('ap_amp_len', i32 * MAX_AP_ELEMENTS),
         ('ap_amp_rows', i32 * MAX_AP_ELEMENTS), ('ap_amp_bin', f64 * MAX_AP_ELEMENTS),
-        ('pi_coarse_time', vp), ('pi_coarse_prob', vp), ('pi_coarse_len', i32)]
+        ('pi_coarse_time', vp), ('pi_coarse_prob', vp), ('pi_coarse_len', i32),
+        ('s1_op_top', vp), ('s1_op_bottom', vp), ('s1_op_nz', i32), ('s1_op_nu', i32),
+        ('s1_op_z0', f64), ('s1_op_z1', f64), ('s1_op_u0', f64), ('s1_op_u1', f64),
+        ('s2_op_top', vp), ('s2_op_bottom', vp), ('s2_op_nu', i32),
+        ('s2_op_u0', f64), ('s2_op_u1', f64),
+        ('gf_t', vp), ('gf_x', vp), ('gf_rows', i32), ('gf_cols', i32)]
 
 
 class InstrMaps(C.Structure):
     _fields_ = [('s1_lce', vp), ('s2_sc_gain', vp), ('s2_cy_extra', vp), ('pattern', vp),
                 ('pattern_row', vp), ('n_pattern_rows', i64), ('s2_sc_gain_default', f64),
-                ('rng_id', vp)]
+                ('rng_id', vp), ('drift_velocity', vp), ('diffusion_long', vp), ('x_obs', vp), ('y_obs', vp)]
 
 
 class Outputs(C.Structure):

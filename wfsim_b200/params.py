@@ -89,7 +89,26 @@ def build_params(cfg):
     p.photoelectric_t_spread = float(cfg.get('photoelectric_t_spread', 0))
     p.s2_aft_sigma = float(cfg.get('s2_aft_sigma', 0.0))
     p.s2_aft_skewness = float(cfg.get('s2_aft_skewness', 0.0))
+    if 'nest' in s1m:
+        # s1.py:222-234 calls nestpy.GetPhotonTimes (third-party, not in this image)
+        raise NotImplementedError("s1_model_type 'nest' needs nestpy, which the device path does not bind")
+    p.s1_model_custom = int('custom' in s1m)
+    for name in ('singlet_lifetime_liquid', 'triplet_lifetime_liquid', 's1_ER_alpha_singlet_fraction',
+                 's1_NR_singlet_fraction', 'led_pulse_length'):
+        setattr(p, name, float(cfg.get(name, 0.0)))
+    p.anode_xaxis_angle = float(cfg.get('anode_xaxis_angle', np.pi / 4))
+    p.anode_pitch = float(cfg.get('anode_pitch', 0.5))
+    cp = cfg.get('s2_garfield_confine_position', 0.0)
+    p.s2_garfield_confine_position = float(cp) if isinstance(cp, float) and cp > 0.0 else 0.0
     return p
+
+
+def set_resource_scalars(p, cfg, resource):
+    """Scalars that depend on resource tables."""
+    set_ele_ap_n(p, resource)
+    lum = getattr(resource, 's2_luminescence', None) if not isinstance(resource, dict) else resource.get('s2_luminescence')
+    if cfg.get('s2_luminescence_model', 'simple') == 'garfield' and lum is not None:
+        p.gf_avgt = int(np.average(lum['t']).astype(int))      # s2.py:408
 
 
 def set_ele_ap_n(p, resource):
@@ -156,6 +175,39 @@ def build_tables(cfg, resource=None):
             ac = t.set_elem('ap_amp_cdf', k, ac, np.float64)
             t.struct.ap_amp_rows[k], t.struct.ap_amp_len[k] = ac.shape
             t.struct.ap_amp_bin[k] = float(el.get('amplitude_bin_size', 1.0))
+    # optical propagation grids (s1.py:241-260, s2.py:486-501)
+    if 'optical_propagation' in cfg.get('s1_model_type', 'simple'):
+        m = get('s1_optical_propagation_spline')
+        if m is None or not hasattr(m, 'grid'):
+            raise ValueError("s1_model_type 'optical_propagation' needs resource.s1_optical_propagation_spline "
+                             "as a wfsim_b200.resource.GridMap with maps 'top' and 'bottom' over (z, U)")
+        axes, top = m.grid('top')
+        _, bot = m.grid('bottom')
+        t.set('s1_op_top', top, np.float64)
+        t.set('s1_op_bottom', bot, np.float64)
+        t.struct.s1_op_nz, t.struct.s1_op_nu = axes[0][2], axes[1][2]
+        t.struct.s1_op_z0, t.struct.s1_op_z1 = axes[0][0], axes[0][1]
+        t.struct.s1_op_u0, t.struct.s1_op_u1 = axes[1][0], axes[1][1]
+    if 'optical_propagation' in cfg.get('s2_time_model', ''):
+        m = get('s2_optical_propagation_spline')
+        if m is None or not hasattr(m, 'grid'):
+            raise ValueError("s2_time_model 'optical_propagation' needs resource.s2_optical_propagation_spline "
+                             "as a wfsim_b200.resource.GridMap with maps 'top' and 'bottom' over (U,)")
+        axes, top = m.grid('top')
+        _, bot = m.grid('bottom')
+        t.set('s2_op_top', top, np.float64)
+        t.set('s2_op_bottom', bot, np.float64)
+        t.struct.s2_op_nu = axes[0][2]
+        t.struct.s2_op_u0, t.struct.s2_op_u1 = axes[0][0], axes[0][1]
+    # garfield luminescence table (s2.py:381-409)
+    if cfg.get('s2_luminescence_model', 'simple') == 'garfield':
+        lum = get('s2_luminescence')
+        assert lum is not None, 's2_luminescence model not found'
+        tt = np.asarray(lum['t'])
+        assert len(tt.shape) == 2, 'Timing data is expected to have D2'
+        tt = t.set('gf_t', tt, np.int32)
+        t.set('gf_x', lum['x'], np.float64)
+        t.struct.gf_rows, t.struct.gf_cols = tt.shape
     # photo-ionisation electrons (afterpulse.py:33-80)
     ele = get('uniform_to_ele_ap')
     if cfg.get('enable_electron_afterpulses', True) and ele is not None:

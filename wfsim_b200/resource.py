@@ -18,6 +18,50 @@ class DummyMap:
         return np.ones([len(x)] + list(self.shape)) * self.const
 
 
+class GridMap:
+    """Named value arrays on one regular grid, evaluated with multilinear interpolation and
+    linear extrapolation outside the grid -- the arithmetic of
+    scipy.interpolate.RegularGridInterpolator(method='linear', bounds_error=False, fill_value=None),
+    which is what straxen.InterpolatingMap(method='RegularGridInterpolator') (third party, used
+    by load_resource.py:399,433) wraps.  The same grids are uploaded to the device for the
+    per-photon maps (optical propagation), so host and device evaluate identical tables.
+
+    axes: [(lo, hi, n), ...] one per coordinate; maps: {name: array of shape (n0, n1, ...[, k])}."""
+
+    def __init__(self, axes, maps):
+        self.axes = [(float(lo), float(hi), int(n)) for lo, hi, n in axes]
+        self.maps = {k: np.asarray(v, dtype=np.float64) for k, v in maps.items()}
+        for k, v in self.maps.items():
+            if tuple(v.shape[:len(self.axes)]) != tuple(n for _, _, n in self.axes):
+                raise ValueError(f'map {k}: shape {v.shape} does not match the grid')
+
+    def grid(self, map_name='map'):
+        return self.axes, self.maps[map_name]
+
+    def __call__(self, points, map_name='map'):
+        v = self.maps[map_name]
+        pts = np.asarray(points, dtype=np.float64)
+        if pts.ndim == 1:
+            pts = pts[:, None]
+        nd = len(self.axes)
+        idx, w = [], []
+        for d, (lo, hi, n) in enumerate(self.axes):
+            f = (pts[:, d] - lo) / (hi - lo) * (n - 1)
+            i = np.clip(np.floor(f).astype(np.int64), 0, n - 2)
+            idx.append(i)
+            w.append(f - i)
+        out = 0.0
+        for corner in range(1 << nd):
+            sel, wt = [], 1.0
+            for d in range(nd):
+                bit = (corner >> (nd - 1 - d)) & 1
+                sel.append(idx[d] + bit)
+                wt = wt * (w[d] if bit else 1.0 - w[d])
+            val = v[tuple(sel)]
+            out = out + (wt[(...,) + (None,) * (val.ndim - 1)] * val)
+        return out
+
+
 def _make_map(spec, name):
     if callable(spec):
         return spec
@@ -59,9 +103,14 @@ class Resource:
             pm = self.s1_pattern_map
             self.s1_lce_correction_map = DummyMap(pm.const * (pm.shape[-1] if pm.shape else 1), ())
         for name in ('photon_area_distribution', 'spe_ppf', 'spe_row', 'noise_data',
-                     'uniform_to_pmt_ap', 'uniform_to_ele_ap'):
+                     'uniform_to_pmt_ap', 'uniform_to_ele_ap',
+                     # load_resource.py:262-330: timing splines, luminescence tables, field maps
+                     's1_optical_propagation_spline', 's2_optical_propagation_spline', 's2_luminescence',
+                     'fdc_3d', 'fd_comsol', 'diffusion_longitudinal_map', 'drift_velocity_scaling'):
             if name in overrides:
                 setattr(self, name, overrides[name])
+        if not hasattr(self, 'drift_velocity_scaling'):
+            self.drift_velocity_scaling = 1.0
 
 
 def _rz_wrapper(m):
@@ -71,11 +120,38 @@ def _rz_wrapper(m):
     return rz_map
 
 
-def evaluate_instruction_maps(config, resource, instructions):
+def inverse_field_distortion_correction(x, y, z, resource):
+    """s2.py:30-53: six fixed-point iterations of the fdc_3d map."""
+    positions = np.array([x, y, z]).T
+    dr_pre = None
+    for i_iter in range(6):
+        dr = np.asarray(resource.fdc_3d(positions), dtype=np.float64).reshape(-1)
+        if i_iter > 0:
+            dr = 0.5 * dr + 0.5 * dr_pre
+        dr_pre = dr
+        r_obs = np.sqrt(x ** 2 + y ** 2) - dr
+        x_obs = x * r_obs / (r_obs + dr)
+        y_obs = y * r_obs / (r_obs + dr)
+        z_obs = -np.sqrt(z ** 2 + dr ** 2)
+        positions = np.array([x_obs, y_obs, z_obs]).T
+    return z_obs, np.array([x_obs, y_obs]).T
+
+
+def field_distortion_comsol(x, y, z, resource):
+    """s2.py:56-71."""
+    positions = np.array([np.sqrt(x ** 2 + y ** 2), z]).T
+    theta = np.arctan2(y, x)
+    r_obs = np.asarray(resource.fd_comsol(positions, map_name='r_distortion_map'), dtype=np.float64).reshape(-1)
+    return z, np.array([r_obs * np.cos(theta), r_obs * np.sin(theta)]).T
+
+
+def evaluate_instruction_maps(config, resource, instructions, seed=0):
     """Per-instruction map values handed to the device (struct wfs_instr_maps):
-    S1 light yield (s1.py:125), S2 secondary-scintillation gain (s2.py:182-209), the survival /
-    extraction factor of the electron yield (s2.py:227-252) and the un-normalised PMT patterns
-    (s1.py:148, s2.py:637-644)."""
+    S1 light yield (s1.py:125), observed S2 positions after the field-distortion model
+    (s2.py:80-87), S2 secondary-scintillation gain (s2.py:182-209), the survival / extraction
+    factor of the electron yield (s2.py:227-252), drift velocity / longitudinal diffusion from the
+    field-dependency maps (s2.py:139-179) and the un-normalised PMT patterns (s1.py:148,
+    s2.py:637-665, with the optional area-fraction-top smearing)."""
     n = len(instructions)
     n_ch = len(config['gains'])
     typ = instructions['type']
@@ -86,17 +162,27 @@ def evaluate_instruction_maps(config, resource, instructions):
     s1_lce = np.ones(n)
     sc_gain = np.zeros(n)
     cy_extra = np.ones(n)
+    out = {}
     p_dpe = config['p_double_pe_emision']
+    efd = config.get('enable_field_dependencies', {})
     if is_s1.any():
         ly = np.asarray(resource.s1_lce_correction_map(xyz[is_s1]), dtype=np.float64)
         if ly.ndim != 1:
             ly = np.squeeze(ly, axis=-1)
         s1_lce[is_s1] = ly
+    pos_obs = xy.copy()            # observed xy of the S2-like instructions
     if is_s2.any():
-        if config.get('field_distortion_model', 'none') not in ('none', None):
-            raise NotImplementedError('field distortion models are evaluated by the reference map '
-                                      'objects; not wired for the device path yet')
-        pos = xy[is_s2]
+        x, y, z = xyz[is_s2, 0], xyz[is_s2, 1], xyz[is_s2, 2]
+        fdm = config.get('field_distortion_model', 'none')
+        if fdm == 'inverse_fdc':
+            _, pos = inverse_field_distortion_correction(x, y, z, resource)
+        elif fdm == 'comsol':
+            _, pos = field_distortion_comsol(x, y, z, resource)
+        else:
+            pos = xy[is_s2]
+        pos_obs[is_s2] = pos
+        if fdm in ('inverse_fdc', 'comsol'):
+            out['x_obs'], out['y_obs'] = pos_obs[:, 0].copy(), pos_obs[:, 1].copy()
         if config.get('se_gain_from_map', False):
             g = np.asarray(resource.se_gain_map(pos), dtype=np.float64)
         else:
@@ -111,33 +197,63 @@ def evaluate_instruction_maps(config, resource, instructions):
             se = (np.asarray(resource.se_gain_map(pos)).flatten() if config.get('se_gain_from_map', False)
                   else rel * config['s2_secondary_sc_gain'])
             cy_extra[is_s2] = config['g2_mean'] * rel / se / config['electron_extraction_yield']
-        if config['enable_field_dependencies']['survival_probability_map']:
+        # survival probability / drift maps are in TRUE coordinates (s2.py:91-93)
+        if efd.get('survival_probability_map'):
             ps = np.asarray(resource.field_dependencies_map(
-                xyz[is_s2, 2], pos, map_name='survival_probability_map'), dtype=np.float64).reshape(-1)
+                z, xy[is_s2], map_name='survival_probability_map'), dtype=np.float64).reshape(-1)
             cy_extra[is_s2] *= np.clip(ps, 0, 1)
-        for k in ('drift_speed_map', 'diffusion_longitudinal_map'):
-            if config['enable_field_dependencies'].get(k):
-                raise NotImplementedError(f'field dependency {k} is not wired for the device path yet')
+        if efd.get('drift_speed_map'):
+            v = np.asarray(resource.field_dependencies_map(z, xy[is_s2], map_name='drift_speed_map'),
+                           dtype=np.float64).reshape(-1) * 1e-4 * resource.drift_velocity_scaling
+            vd = np.full(n, float(config['drift_velocity_liquid']))
+            vd[is_s2] = v
+            out['drift_velocity'] = vd
+        if efd.get('diffusion_longitudinal_map'):
+            d = np.asarray(resource.diffusion_longitudinal_map(z, xy[is_s2]), dtype=np.float64).reshape(-1)
+            dl = np.full(n, float(config['diffusion_constant_longitudinal']))
+            dl[is_s2] = d
+            out['diffusion_long'] = dl
     # patterns: constant maps share one row per signal type
     s1m, s2m = getattr(resource, 's1_pattern_map', None), getattr(resource, 's2_pattern_map', None)
     rows, row_of = [], np.zeros(n, np.int32)
+    aft_sigma = config.get('s2_aft_sigma', 0.0)
 
-    def add_rows(mask, m, pad_bottom):
+    def add_rows(mask, m, is_s2_map):
         if not mask.any():
             return
-        if isinstance(m, DummyMap):
+        smear = is_s2_map and aft_sigma != 0
+        if isinstance(m, DummyMap) and not smear:
             pat = np.asarray(m(np.zeros((1, 2))), dtype=np.float64).reshape(1, -1)
             idx = np.zeros(mask.sum(), np.int64)
         else:
-            pat = np.asarray(m(xyz[mask] if not pad_bottom else xy[mask]), dtype=np.float64)
+            # s2_pattern_map_diffuse (s2.py:560-613) evaluates the map at the undiffused position
+            # unless the transverse-diffusion field map is enabled
+            if is_s2_map and efd.get('diffusion_transverse_map'):
+                raise NotImplementedError('diffusion_transverse_map: per-electron pattern averaging is not built')
+            pat = np.asarray(m(pos_obs[mask] if is_s2_map else xyz[mask]), dtype=np.float64)
+            pat = pat.reshape(mask.sum(), -1)
             idx = np.arange(mask.sum())
-        if pad_bottom and pat.shape[1] < n_ch:        # top-only S2 map: s2.py:642-644
+        if is_s2_map and pat.shape[1] < n_ch:        # top-only S2 map: s2.py:642-644
             pat = np.pad(pat, [[0, 0], [0, n_ch - pat.shape[1]]], 'constant', constant_values=1)
+        if smear:                                    # s2.py:660-665
+            from scipy.stats import skewnorm
+            rng = np.random.default_rng([int(seed) & 0xffffffff, 0xAF7])
+            n_top = int(config['n_top_pmts'])
+            pat = pat.copy()
+            pat[:, np.asarray(config['gains']) == 0] = 0
+            tot = pat.sum(axis=1, keepdims=True)
+            pat = np.divide(pat, tot, out=np.zeros_like(pat), where=tot != 0)
+            cur = pat[:, :n_top].sum(axis=1) / pat.sum(axis=1)
+            new = np.clip(cur * skewnorm.rvs(loc=1.0, scale=aft_sigma, a=config.get('s2_aft_skewness', 0.0),
+                                             size=len(cur), random_state=rng), 0, 1)
+            pat[:, :n_top] *= (new / cur)[:, None]
+            pat[:, n_top:] *= ((1 - new) / (1 - cur))[:, None]
         base = sum(len(r) for r in rows)
         rows.append(pat.astype(np.float32))
         row_of[mask] = base + idx
     add_rows(is_s1, s1m, False)
     add_rows(is_s2, s2m, True)
     pattern = np.concatenate(rows) if rows else np.ones((1, n_ch), np.float32)
-    return dict(s1_lce=s1_lce, s2_sc_gain=sc_gain, s2_cy_extra=cy_extra,
-                pattern=np.ascontiguousarray(pattern), pattern_row=row_of)
+    out.update(s1_lce=s1_lce, s2_sc_gain=sc_gain, s2_cy_extra=cy_extra,
+               pattern=np.ascontiguousarray(pattern), pattern_row=row_of)
+    return out

@@ -55,7 +55,7 @@ class Simulator:
         self.resource = resource
         self.params = wparams.build_params(config)
         if resource is not None:
-            wparams.set_ele_ap_n(self.params, resource)
+            wparams.set_resource_scalars(self.params, config, resource)
         self.tables = wparams.build_tables(config, resource)
         h = C.c_void_p()
         rc = self.lib.wfs_create(C.byref(self.params), C.byref(self.tables.struct), device, C.byref(h))
@@ -134,11 +134,11 @@ class Simulator:
         return out
 
     # -----------------------------------------------------------------------------------------
-    def _maps_struct(self, instructions, maps=None, rng_id=None):
+    def _maps_struct(self, instructions, maps=None, rng_id=None, seed=0):
         if maps is None:
             if self.resource is None or isinstance(self.resource, dict):
                 raise SimulatorError('simulate() needs a Resource (maps) -- pass resource= to Simulator')
-            maps = evaluate_instruction_maps(self.config, self.resource, instructions)
+            maps = evaluate_instruction_maps(self.config, self.resource, instructions, seed=seed)
         keep = {k: np.ascontiguousarray(v, dtype=(np.float32 if k == 'pattern' else
                                                    np.int32 if k == 'pattern_row' else np.float64))
                 for k, v in maps.items()}
@@ -150,6 +150,9 @@ class Simulator:
         m.pattern_row = _ptr(keep['pattern_row'])
         m.n_pattern_rows = keep['pattern'].shape[0]
         m.s2_sc_gain_default = 0.0
+        for k in ('drift_velocity', 'diffusion_long', 'x_obs', 'y_obs'):
+            if k in keep:
+                setattr(m, k, _ptr(keep[k]))
         if rng_id is not None:
             keep['rng_id'] = np.ascontiguousarray(rng_id, np.uint64)
             if len(keep['rng_id']) != len(instructions):
@@ -178,7 +181,7 @@ class Simulator:
         if instructions.dtype.itemsize != 70:
             raise ValueError('instructions must have the packed 70-byte instruction_dtype')
         n = len(instructions)
-        m, keep = self._maps_struct(instructions, maps, rng_id)
+        m, keep = self._maps_struct(instructions, maps, rng_id, seed=seed)
         counts = wlib.Counts()
         cap_rec = int(cap_records) if cap_records is not None else max(4096, 1500 * n)
         cap_truth, cap_groups, cap_batches = 2 * n + 64, n + 64, 4096
@@ -251,7 +254,7 @@ class Simulator:
         """Front-end only: photons (stage 0) or emitters/electrons (stage 1) as a structured array
         (see wfs_sample_stage).  For the statistical parity tests."""
         instructions = np.ascontiguousarray(instructions)
-        m, keep = self._maps_struct(instructions, maps)
+        m, keep = self._maps_struct(instructions, maps, seed=seed)
         n_out = C.c_int64()
         cap = 1 << 16
         while True:
