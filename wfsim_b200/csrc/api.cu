@@ -30,7 +30,7 @@ Handle::Handle(const wfs_params &p, const wfs_tables &t, int dev) : device(dev) 
     WFS_CUDA_CHECK(cudaEventCreate(&ev_c));
     WFS_CUDA_CHECK(cudaEventCreate(&ev_d));
     cfg.p = p;
-    if (p.dt <= 0 || p.dt > 16 || p.template_length <= 0 || p.template_length > 32)
+    if (p.dt <= 0 || p.dt > 16 || p.template_length <= 0 || p.template_length > 32 || p.dt * p.template_length > 352)
         throw std::runtime_error("unsupported sample_duration / template length");
     if (p.n_tpc_pmts <= 0 || p.n_tpc_pmts >= (1 << kChannelBits) || p.n_rows > (1 << kChannelBits))
         throw std::runtime_error("unsupported channel count");

@@ -334,11 +334,13 @@ __global__ void k_group_noise(int64_t n_groups, DeviceConfig c, const int64_t *g
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_digitize: persistent CTAs, each looping over TILES of the dense buffer (up to 256 consecutive
-// 8-sample blocks = 2048 samples; the dense buffer is window-contiguous, so a tile covers a few
-// whole windows or a slice of a long one).
-//   setup   warp 0: the windows overlapping the tile -> s_win (ballot-ordered), photon prefix;
-//   sparse  (<= kStageCap photons in those windows, the common case): one thread per photon
+// k_digitize: persistent WARPS, each looping over TILES of the dense buffer (up to 128 consecutive
+// 8-sample blocks = 1024 samples; the dense buffer is window-contiguous, so a tile covers a few
+// whole windows or a slice of a long one).  A warp runs a tile from start to finish with
+// __syncwarp only -- no CTA barrier after the template load -- so ~28 independent tiles are in
+// flight per SM and the dependent metadata / photon loads of one hide behind the others.
+//   setup   the windows overlapping the tile -> W.win (ballot-ordered), photon prefix by shuffles;
+//   sparse  (<= kStageCap photons in those windows, the common case): one lane per photon
 //           stages it in shared memory (tile-local sample position, merged gain) and marks the
 //           8-sample blocks its template reaches.  An ISLAND is a run of photons of one Pulse
 //           call whose 22-tap templates overlap; every sample of an island is OWNED by the first
@@ -359,13 +361,14 @@ __global__ void k_group_noise(int64_t n_groups, DeviceConfig c, const int64_t *g
 // ---------------------------------------------------------------------------------------------
 constexpr int kDigiThreads = 128;
 constexpr int kDigiWarps = kDigiThreads / 32;
-constexpr int kDigiCtasPerSm = 9;
+constexpr int kDigiCtasPerSm = 7;
 constexpr int kNeg = -(1 << 29);
-constexpr int kTileBlkMax = 256;                 // 8-sample blocks per tile
+constexpr int kTileBlkMax = 128;                 // 8-sample blocks per tile (one tile per warp)
 constexpr int kTileSmpMax = kTileBlkMax * kBlk;
-constexpr int kTileWinMax = 32;                  // windows overlapping one tile (host sizes the tile)
-constexpr int kStageCap = 255;                   // photons staged in shared memory per tile (byte index + 1)
+constexpr int kTileWinMax = 16;                  // windows overlapping one tile (host sizes the tile)
+constexpr int kStageCap = 127;                   // photons staged in shared memory per tile (byte index + 1)
 constexpr int kLayers = 4;
+constexpr int kTmplMax = 352;                    // dt * template_length doubles staged per CTA (checked at wfs_create)
 
 struct TileWin {
     int32_t off;             // tile-local sample index of window sample 0 (negative: starts before)
@@ -512,6 +515,18 @@ __device__ __forceinline__ void finish_block(int v[kBlk], const TileWin &m, int 
     *flag = (uint8_t)flags;
 }
 
+// Per-warp working set of one tile.
+struct __align__(16) WarpTile {
+    uint32_t own[kTileSmpMax];      // per sample: owner index + 1 of layer l in byte l; then the ADC sum
+    double gm[kStageCap + 1];
+    int T[kStageCap + 1];
+    TileWin win[kTileWinMax];
+    uint16_t rf[kStageCap + 1];
+    uint8_t tb[kTileBlkMax];        // touched blocks, compacted
+    uint8_t blkwin[kTileBlkMax];
+    uint32_t touch[kTileBlkMax / 32];
+};
+
 __global__ void __launch_bounds__(kDigiThreads)
 k_digitize(int64_t n_blocks, int tile_blk, int n_tiles, int64_t n_wtot, DeviceConfig c,
            const WinMeta *__restrict__ meta, const uint64_t *__restrict__ win_off,
@@ -519,16 +534,8 @@ k_digitize(int64_t n_blocks, int tile_blk, int n_tiles, int64_t n_wtot, DeviceCo
            const double *__restrict__ gm, const uint32_t *__restrict__ pulse_first,
            const int64_t *__restrict__ group_ix, int16_t *__restrict__ dense,
            uint8_t *__restrict__ flag8, int64_t *scalars) {
-    __shared__ __align__(16) uint32_t s_own[kTileSmpMax];   // per sample: owner index + 1 of layer l in byte l; then the ADC sum
-    __shared__ double s_tmpl[16 * 32];
-    __shared__ double s_gm[kStageCap + 1];
-    __shared__ int s_T[kStageCap + 1];
-    __shared__ TileWin s_win[kTileWinMax];
-    __shared__ uint16_t s_rf[kStageCap + 1];
-    __shared__ uint16_t s_tb[kTileBlkMax];
-    __shared__ uint8_t s_blkwin[kTileBlkMax];
-    __shared__ uint32_t s_touch[kTileBlkMax / 32];
-    __shared__ int s_nwin, s_total, s_ntb, s_fallback, s_mult1;
+    __shared__ double s_tmpl[kTmplMax];
+    __shared__ WarpTile s_wt[kDigiWarps];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u;
@@ -538,184 +545,180 @@ k_digitize(int64_t n_blocks, int tile_blk, int n_tiles, int64_t n_wtot, DeviceCo
     const int base_clamped = max(c.p.baseline, 0);
     const uint32_t base_h = (uint32_t)(uint16_t)(int16_t)base_clamped;
     const uint32_t base_pw = base_h | (base_h << 16);
+    WarpTile &W = s_wt[warp];
     for (int i = tid; i < dt * tlen; i += kDigiThreads) s_tmpl[i] = c.templates[i];
-    for (int i = tid; i < kTileSmpMax; i += kDigiThreads) s_own[i] = 0;
+    for (int i = lane; i < kTileSmpMax; i += 32) W.own[i] = 0;
+    __syncthreads();   // the only CTA-wide barrier: from here on every warp works on tiles of its own
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int n_warps = gridDim.x * kDigiWarps;
+    for (int tile = blockIdx.x * kDigiWarps + warp; tile < n_tiles; tile += n_warps) {
         const int64_t B0 = (int64_t)tile * tile_blk;
         const int nblk = (int)min((int64_t)tile_blk, n_blocks - B0);
         const int nsmp = nblk * kBlk;
         uint4 *out = reinterpret_cast<uint4 *>(dense + B0 * kBlk);
-        __syncthreads();   // previous tile fully written; tables initialised
-        if (tid < kTileBlkMax / 32) s_touch[tid] = 0;
-        if (tid == 32) { s_ntb = 0; s_fallback = 0; }
-        // ---- setup (warp 0): the windows overlapping this tile, in window order ----
-        if (warp == 0) {
-            int n = 0;
-            for (int64_t base = tile_first[tile];; base += 32) {
-                const int64_t w = base + lane;
-                bool past = w >= n_wtot, take = false;
-                int64_t b0 = 0;
-                if (!past) {
-                    b0 = (int64_t)(uint32_t)win_off[w];
-                    const int64_t b1 = (int64_t)(uint32_t)win_off[w + 1];
-                    past = b0 >= B0 + nblk;
-                    take = !past && b1 > b0 && b1 > B0;
-                }
-                const uint32_t tm = __ballot_sync(0xffffffffu, take);
-                const int slot = n + __popc(tm & lt);
-                if (take && slot < kTileWinMax) {
-                    const WinMeta m = meta[w];
-                    TileWin t;
-                    t.off = (int32_t)(b0 - B0) * kBlk;
-                    t.len = m.len;
-                    t.mult = m.mult;
-                    t.thr = c.zle_thr[m.channel];
-                    const bool noisy = noise_on && m.channel < c.noise_nch;
-                    t.channel = noisy ? m.channel : -1;
-                    t.ixbase = noisy ? (int32_t)(group_ix[m.group] % c.noise_len) : 0;
-                    t.ph_lo = m.ph_lo;
-                    t.ph_cnt = m.mult != 0 ? m.ph_hi - m.ph_lo : 0u;
-                    t.p0 = m.p0; t.p1 = m.p1;
-                    t.s_first = m.s_first; t.s_last = m.s_last;
-                    t.stage0 = 0;
-                    t.all_touched = (noisy || base_clamped < t.thr) ? 1 : 0;
-                    s_win[slot] = t;
-                }
-                n += __popc(tm);
-                if (__ballot_sync(0xffffffffu, past)) break;
+        __syncwarp();
+        if (lane < kTileBlkMax / 32) W.touch[lane] = 0;
+        // ---- setup: the windows overlapping this tile, in window order ----
+        int n = 0;
+        for (int64_t base = tile_first[tile];; base += 32) {
+            const int64_t w = base + lane;
+            bool past = w >= n_wtot, take = false;
+            int64_t b0 = 0;
+            if (!past) {
+                b0 = (int64_t)(uint32_t)win_off[w];
+                const int64_t b1 = (int64_t)(uint32_t)win_off[w + 1];
+                past = b0 >= B0 + nblk;
+                take = !past && b1 > b0 && b1 > B0;
             }
-            if (n > kTileWinMax) {   // cannot happen: the host sizes tile_blk from the minimum window length
-                if (lane == 0) scalars[S_ERR] = WFS_E_ARG;
-                n = kTileWinMax;
+            const uint32_t tm = __ballot_sync(0xffffffffu, take);
+            const int slot = n + __popc(tm & lt);
+            if (take && slot < kTileWinMax) {
+                const WinMeta m = meta[w];
+                TileWin t;
+                t.off = (int32_t)(b0 - B0) * kBlk;
+                t.len = m.len;
+                t.mult = m.mult;
+                t.thr = c.zle_thr[m.channel];
+                const bool noisy = noise_on && m.channel < c.noise_nch;
+                t.channel = noisy ? m.channel : -1;
+                t.ixbase = noisy ? (int32_t)(group_ix[m.group] % c.noise_len) : 0;
+                t.ph_lo = m.ph_lo;
+                t.ph_cnt = m.mult != 0 ? m.ph_hi - m.ph_lo : 0u;
+                t.p0 = m.p0; t.p1 = m.p1;
+                t.s_first = m.s_first; t.s_last = m.s_last;
+                t.stage0 = 0;
+                t.all_touched = (noisy || base_clamped < t.thr) ? 1 : 0;
+                W.win[slot] = t;
             }
-            __syncwarp();
-            // exclusive prefix of the photon counts over the (<= 32) slots
-            const uint32_t c0 = lane < n ? min(s_win[lane].ph_cnt, 1u << 24) : 0u;
-            uint32_t i0 = c0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t a0 = __shfl_up_sync(0xffffffffu, i0, o);
-                if (lane >= o) i0 += a0;
-            }
-            if (lane < n) s_win[lane].stage0 = i0 - c0;
-            const uint32_t notone = __ballot_sync(0xffffffffu, lane < n && s_win[lane].mult != 1);
-            if (lane == 31) { s_nwin = n; s_total = (int)i0; s_mult1 = notone == 0; }
+            n += __popc(tm);
+            if (__ballot_sync(0xffffffffu, past)) break;
         }
-        __syncthreads();
-        const int nwin = s_nwin, total = s_total;
-        const bool mult1 = s_mult1 != 0;
+        if (n > kTileWinMax) {   // cannot happen: the host sizes tile_blk from the minimum window length
+            if (lane == 0) scalars[S_ERR] = WFS_E_ARG;
+            n = kTileWinMax;
+        }
+        __syncwarp();
+        // exclusive prefix of the photon counts over the slots
+        const uint32_t c0 = lane < n ? min(W.win[lane].ph_cnt, 1u << 24) : 0u;
+        uint32_t i0 = c0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t a0 = __shfl_up_sync(0xffffffffu, i0, o);
+            if (lane >= o) i0 += a0;
+        }
+        if (lane < n) W.win[lane].stage0 = i0 - c0;
+        const int total = (int)__shfl_sync(0xffffffffu, i0, 31);
+        const bool mult1 = __ballot_sync(0xffffffffu, lane < n && W.win[lane].mult != 1) == 0;
+        const int nwin = n;
         bool sparse = total <= kStageCap;
+        __syncwarp();
         if (sparse) {
-            // ---- stage the photons (one thread each); mark the blocks their templates reach ----
-            if (tid < nwin) {
-                const TileWin &m = s_win[tid];
+            // ---- stage the photons (one lane each); mark the blocks their templates reach ----
+            bool clash = false;
+            if (lane < nwin) {
+                const TileWin &m = W.win[lane];
                 const int blk_lo = max(m.off / kBlk, 0), blk_end = (m.off + m.len + kBlk - 1) / kBlk;
                 if (m.all_touched) {
                     for (int b = blk_lo; b < min(blk_end, nblk); b++) {
-                        s_blkwin[b] = (uint8_t)tid;
-                        atomicOr(&s_touch[b >> 5], 1u << (b & 31));
+                        W.blkwin[b] = (uint8_t)lane;
+                        atomicOr(&W.touch[b >> 5], 1u << (b & 31));
                     }
                 } else if ((m.len & (kBlk - 1)) && blk_end <= nblk) {   // partial last block
-                    s_blkwin[blk_end - 1] = (uint8_t)tid;
-                    atomicOr(&s_touch[(blk_end - 1) >> 5], 1u << ((blk_end - 1) & 31));
+                    W.blkwin[blk_end - 1] = (uint8_t)lane;
+                    atomicOr(&W.touch[(blk_end - 1) >> 5], 1u << ((blk_end - 1) & 31));
                 }
             }
-            for (int i = tid; i < total; i += kDigiThreads) {
+            for (int i = lane; i < total; i += 32) {
                 int slot = 0;   // last slot with stage0 <= i
 #pragma unroll
                 for (int step = kTileWinMax / 2; step > 0; step >>= 1)
-                    if (slot + step < nwin && (int)s_win[slot + step].stage0 <= i) slot += step;
-                const uint32_t src = s_win[slot].ph_lo + (uint32_t)(i - (int)s_win[slot].stage0);
+                    if (slot + step < nwin && (int)W.win[slot + step].stage0 <= i) slot += step;
+                const uint32_t src = W.win[slot].ph_lo + (uint32_t)(i - (int)W.win[slot].stage0);
                 const uint32_t v = phq[src];
-                const int off = s_win[slot].off;
+                const int off = W.win[slot].off;
                 const int T0 = off + ph_q(v);
                 const uint32_t ord = (v >> kPhOrdShift) & kPhOrdMask;
-                s_gm[i] = gm[src];
-                s_T[i] = T0;
-                s_rf[i] = (uint16_t)((v & 15u) | ((v & kPhRunHead) ? kRfHead : 0u) |
+                W.gm[i] = gm[src];
+                W.T[i] = T0;
+                W.rf[i] = (uint16_t)((v & 15u) | ((v & kPhRunHead) ? kRfHead : 0u) |
                                      ((v & kPhIsland) ? kRfIsland : 0u) | ((ord & (kLayers - 1)) << 6) |
                                      ((uint32_t)slot << 8) | ((v & kPhAlone) ? kRfAlone : 0u));
-                if (ord == kPhOrdMask) s_fallback = 1;
+                if (ord == kPhOrdMask) clash = true;
                 if (v & kPhRunHead) {
                     const int t_hi = min(T0 + tlen - 1, nsmp - 1);
                     for (int b = max(T0, 0) >> 3; b <= (t_hi >> 3); b++) {
-                        s_blkwin[b] = (uint8_t)slot;
-                        atomicOr(&s_touch[b >> 5], 1u << (b & 31));
+                        W.blkwin[b] = (uint8_t)slot;
+                        atomicOr(&W.touch[b >> 5], 1u << (b & 31));
                     }
                     // the samples this photon owns: its template's reach minus the previous photon's
                     int lo = T0;
                     if (!(v & kPhIsland)) lo = max(lo, off + ph_q(phq[src - 1]) + tlen);
                     lo = max(lo, 0);
                     const int sh = (int)(ord & (kLayers - 1)) * 8;
-                    bool clash = false;
                     for (int T = lo; T <= t_hi; T++) {
-                        const uint32_t old = atomicOr(&s_own[T], (uint32_t)(i + 1) << sh);
-                        clash |= ((old >> sh) & 0xffu) != 0;
+                        const uint32_t old = atomicOr(&W.own[T], (uint32_t)(i + 1) << sh);
+                        clash |= ((old >> sh) & 0xffu) != 0;   // two Pulse calls on one layer overlap
                     }
-                    if (clash) s_fallback = 1;   // two Pulse calls on one layer overlap
                 }
             }
-            __syncthreads();
-            if (s_fallback) {   // rare: clear the owner tables and take the dense path
-                __syncthreads();
-                for (int i = tid; i < kTileSmpMax; i += kDigiThreads) s_own[i] = 0;
+            __syncwarp();
+            if (__any_sync(0xffffffffu, clash)) {   // rare: clear the owner table and take the dense path
+                for (int i = lane; i < kTileSmpMax; i += 32) W.own[i] = 0;
                 sparse = false;
+                __syncwarp();
             }
         }
         if (sparse) {
             // ---- untouched blocks: constant stores; touched blocks: compacted list ----
-            for (int wd = warp; wd * 32 < nblk; wd += kDigiWarps) {
-                const uint32_t word = s_touch[wd];
+            int ntb = 0;
+            for (int wd = 0; wd * 32 < nblk; wd++) {
+                const uint32_t word = W.touch[wd];
                 const int b = wd * 32 + lane;
-                int base = 0;
-                if (lane == 0 && word) base = atomicAdd(&s_ntb, __popc(word));
-                base = __shfl_sync(0xffffffffu, base, 0);
                 if ((word >> lane) & 1u) {
-                    s_tb[base + __popc(word & lt)] = (uint16_t)b;
+                    W.tb[ntb + __popc(word & lt)] = (uint8_t)b;
                 } else if (b < nblk) {          // nothing but the baseline in these 8 samples
                     out[b] = make_uint4(base_pw, base_pw, base_pw, base_pw);
                     flag8[B0 + b] = 0;
                 }
+                ntb += __popc(word);
             }
-            __syncthreads();
-            const int ntb = s_ntb;
-            // ---- touched samples (one thread each): gather from the owners, round per Pulse call ----
-            for (int e = tid; e < ntb * kBlk; e += kDigiThreads) {
-                const int b = s_tb[e >> 3];
+            __syncwarp();
+            // ---- touched samples (one lane each): gather from the owners, round per Pulse call ----
+            for (int e = lane; e < ntb * kBlk; e += 32) {
+                const int b = W.tb[e >> 3];
                 const int T = b * kBlk + (e & (kBlk - 1));
-                uint32_t ow = s_own[T];
+                uint32_t ow = W.own[T];
                 if (!ow) continue;
-                const int mult = mult1 ? 1 : s_win[s_blkwin[b]].mult;
+                const int mult = mult1 ? 1 : W.win[W.blkwin[b]].mult;
                 int v = 0;
                 do {   // one owner per layer (byte), usually a single one
                     const int sh = (31 - __clz(ow)) & ~7;
                     const int o = (int)((ow >> sh) & 0xffu);
                     ow &= ~(0xffu << sh);
-                    const uint32_t r0 = s_rf[o - 1];
+                    const uint32_t r0 = W.rf[o - 1];
                     double cur;
                     if (r0 & kRfAlone) {
-                        cur = __dmul_rn(s_tmpl[(r0 & 15u) * tlen + (T - s_T[o - 1])], s_gm[o - 1]);
+                        cur = __dmul_rn(s_tmpl[(r0 & 15u) * tlen + (T - W.T[o - 1])], W.gm[o - 1]);
                     } else {
                         cur = 0.0;
                         for (int k = o - 1; k < total; k++) {
-                            const uint32_t rk = s_rf[k];
+                            const uint32_t rk = W.rf[k];
                             if (k >= o && (rk & kRfIsland)) break;
-                            const int tap = T - s_T[k];
+                            const int tap = T - W.T[k];
                             if (tap < 0) break;
-                            if (rk & kRfHead) cur = __dadd_rn(cur, __dmul_rn(s_tmpl[(rk & 15u) * tlen + tap], s_gm[k]));
+                            if (rk & kRfHead) cur = __dadd_rn(cur, __dmul_rn(s_tmpl[(rk & 15u) * tlen + tap], W.gm[k]));
                         }
                     }
                     v -= __double2int_rn(__dmul_rn(cur, c2a)) * mult;
                 } while (ow);
-                s_own[T] = (uint32_t)v;
+                W.own[T] = (uint32_t)v;
             }
-            __syncthreads();
+            __syncwarp();
             // ---- touched blocks: finish ----
-            for (int j = tid; j < ntb; j += kDigiThreads) {
-                const int b = s_tb[j];
-                const TileWin &m = s_win[s_blkwin[b]];
-                int4 *acc = reinterpret_cast<int4 *>(&s_own[b * kBlk]);
+            for (int j = lane; j < ntb; j += 32) {
+                const int b = W.tb[j];
+                const TileWin &m = W.win[W.blkwin[b]];
+                int4 *acc = reinterpret_cast<int4 *>(&W.own[b * kBlk]);
                 const int4 a0 = acc[0], a1 = acc[1];
                 acc[0] = acc[1] = make_int4(0, 0, 0, 0);
                 int v[kBlk] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
@@ -723,14 +726,14 @@ k_digitize(int64_t n_blocks, int tile_blk, int n_tiles, int64_t n_wtot, DeviceCo
             }
         } else {
             // ---- dense path ----
-            for (int slot = warp; slot < nwin; slot += kDigiWarps) {
-                const int lo = max(s_win[slot].off / kBlk, 0);
-                const int hi = min((s_win[slot].off + s_win[slot].len + kBlk - 1) / kBlk, nblk);
-                for (int b = lo + lane; b < hi; b += 32) s_blkwin[b] = (uint8_t)slot;
+            for (int slot = 0; slot < nwin; slot++) {
+                const int lo = max(W.win[slot].off / kBlk, 0);
+                const int hi = min((W.win[slot].off + W.win[slot].len + kBlk - 1) / kBlk, nblk);
+                for (int b = lo + lane; b < hi; b += 32) W.blkwin[b] = (uint8_t)slot;
             }
-            __syncthreads();
-            for (int b = tid; b < nblk; b += kDigiThreads) {
-                const TileWin &m = s_win[s_blkwin[b]];
+            __syncwarp();
+            for (int b = lane; b < nblk; b += 32) {
+                const TileWin &m = W.win[W.blkwin[b]];
                 int v[kBlk];
                 gather_block(m, b * kBlk - m.off, tlen, c2a, s_tmpl, phq, gm, pulse_first, v);
                 finish_block(v, m, b * kBlk - m.off, c, &out[b], &flag8[B0 + b]);
@@ -1117,7 +1120,7 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
                        win_meta_.as<WinMeta>(), phq_.as<uint32_t>(), reinterpret_cast<double *>(flags64_.p));
         }
         static const int ctas_per_sm = getenv("WFS_DIGI_CTAS") ? atoi(getenv("WFS_DIGI_CTAS")) : kDigiCtasPerSm;
-        LAUNCH(k_digitize, std::min(n_cta, kNumSMs * ctas_per_sm), kDigiThreads, n_tiles, tile_blk, n_cta, nwt, c,
+        LAUNCH(k_digitize, std::min(div_up(n_cta, kDigiWarps), kNumSMs * ctas_per_sm), kDigiThreads, n_tiles, tile_blk, n_cta, nwt, c,
                win_meta_.as<WinMeta>(), win_scan_.as<uint64_t>(), cta_first_.as<uint32_t>(),
                phq_.as<uint32_t>(), reinterpret_cast<const double *>(flags64_.p),
                pulse_first_.as<uint32_t>(), group_ix_buf.as<int64_t>(), dense_.as<int16_t>(),
