@@ -103,3 +103,29 @@ def test_linearity_and_idempotence():
     cat = np.concatenate(parts)
     assert cat.tobytes() == a.tobytes()
     sim.close()
+
+
+@pytest.mark.parametrize('n_calls,n_ch_used', [(6, 3), (40, 5)])
+def test_many_overlapping_pulse_calls(n_calls, n_ch_used):
+    """Several Pulse calls of one digitisation group overlapping on the same samples of the same
+    channels (pile-up, G4-style inputs): every call is rounded on its own and the integers add
+    (rawdata.py:236-239).  Exercises the layer-collision and >= 31-calls paths of k_digitize."""
+    from oracle import wfsim_oracle as orc
+    cfg = load_c0_config()
+    gains = cfg['gains']
+    rng = np.random.default_rng(300 + n_calls)
+    pcall, ch, t, g = [], [], [], []
+    for pc in range(n_calls):
+        n = int(rng.integers(3, 30))
+        pcall.append(np.full(n, pc))
+        c = rng.integers(0, n_ch_used, n) * 50 + 3
+        ch.append(c)
+        t.append(2_000_000 + rng.integers(0, 1500, n))
+        g.append(gains[c] * (0.3 + rng.exponential(0.7, n)))
+    pcall, ch, t, g = (np.concatenate(x) for x in (pcall, ch, t, g))
+    group_of = np.zeros(n_calls, np.int32)
+    want = orc.simulate_photons(cfg, pcall.astype(np.int32), ch.astype(np.int32), t.astype(np.int64), g, group_of)
+    sim = make_sim(cfg)
+    out = sim.simulate_photons(t, ch, g, pcall, group_of)
+    assert_records_equal(out['raw_records'], want['raw_records'], 'tpc')
+    sim.close()
