@@ -883,9 +883,13 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     if (!so.resident && fits && res.n_records > 0) {
         WFS_CUDA_CHECK(cudaEventRecord(F.ev_ready, s));
         WFS_CUDA_CHECK(cudaStreamWaitEvent(L.copy_stream, F.ev_ready, 0));
-        WFS_CUDA_CHECK(cudaMemcpyAsync(out->records + (size_t)rec0 * WFS_RECORD_BYTES, d_rec,
-                                       (size_t)res.n_records * WFS_RECORD_BYTES, cudaMemcpyDeviceToHost,
-                                       L.copy_stream));
+        // in pieces: the copy engine serves streams in FIFO order, and the other lane's 4-byte count
+        // readbacks must not queue behind a gigabyte of records
+        const size_t total_bytes = (size_t)res.n_records * WFS_RECORD_BYTES, piece = size_t(8) << 20;
+        uint8_t *dst = out->records + (size_t)rec0 * WFS_RECORD_BYTES;
+        for (size_t o = 0; o < total_bytes; o += piece)
+            WFS_CUDA_CHECK(cudaMemcpyAsync(dst + o, d_rec + o, std::min(piece, total_bytes - o),
+                                           cudaMemcpyDeviceToHost, L.copy_stream));
         WFS_CUDA_CHECK(cudaEventRecord(F.ev_copy[par], L.copy_stream));
         F.copy_pending[par] = true;
     }
