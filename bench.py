@@ -220,7 +220,7 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- end-to-end leg: public API, host buffers, H2D + D2H inside the timed region ----------
     cap = int(c['n_records_total'] * 1.02) + 1024
-    e2e_ms = []
+    e2e_ms, e2e_lib = [], []
     h2d = inst.nbytes + 494 * 4 * 2 + len(inst) * (8 * 3 + 4)
     d2h = 0
     out = None
@@ -232,7 +232,10 @@ def run_b200(args, rank, world, local_rank):
         dt = time.perf_counter() - t0
         if k >= args.warmup:
             e2e_ms.append(dt * 1e3)
-        d2h = (sim.last_counts['n_records_total'] * RECORD_BYTES + sim.last_counts['n_truth'] * TRUTH_BYTES
+            e2e_lib.append([sim.last_counts['ms_total']] + list(sim.last_counts['ms_phase'][8:10]))
+        # record bytes that crossed PCIe (compact transport: headers + non-baseline sample blocks,
+        # expanded to 244-byte records by the library's host threads) + truth rows + group info
+        d2h = (sim.last_counts['d2h_bytes'] + sim.last_counts['n_truth'] * TRUTH_BYTES
                + sim.last_counts['n_groups'] * 24)
     t_e2e = float(np.sum(e2e_ms)) / 1e3
     if world > 1:
@@ -263,7 +266,12 @@ def run_b200(args, rank, world, local_rank):
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': 'pe/s', 'h2d_bytes_per_step': int(h2d),
                 'd2h_bytes_per_step': int(d2h), 'ms_per_step': t_e2e / args.steps * 1e3,
-                'raw_records_gbs': n_rec_all * RECORD_BYTES * args.steps / t_e2e / 1e9},
+                'raw_records_gbs': n_rec_all * RECORD_BYTES * args.steps / t_e2e / 1e9,
+                # inside the call (rank 0, per step): device work of all batches; wall clock summed over
+                # batches of (batch shipped -> its compact D2H done) and (D2H done -> expanded by host threads)
+                'ms_device': float(np.mean([x[0] for x in e2e_lib])),
+                'ms_batches_d2h': float(np.mean([x[1] for x in e2e_lib])),
+                'ms_batches_expand': float(np.mean([x[2] for x in e2e_lib]))},
         'gpu_launches': int(launches_all),
         'ms_phase_per_step': dict(zip(['frontend', 'photon_sort', 'windows', 'digitize', 'zle', 'record_sort',
                                        'record_pack', 'host_scheduler_truth'], (phases[:8] / args.steps).round(3).tolist())),

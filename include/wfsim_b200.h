@@ -179,12 +179,14 @@ typedef struct wfs_counts {
     int64_t need_truth;
     int64_t need_groups;
     int64_t need_batches;
+    int64_t d2h_bytes;              /* record bytes that crossed PCIe (compact transport or 244 B/record) */
     double ms_total;                /* CUDA-event time of the device work of this call */
     double ms_digitize;             /* of which: the digitize (superpose+ADC+noise+clip) kernel */
     double ms_h2d, ms_d2h;
     /* device time per phase, summed over batches (CUDA events on the library stream):
      * 0 sampling front end, 1 photon keys + sort, 2 pulses/windows, 3 digitize, 4 ZLE,
-     * 5 record keys + sort, 6 record pack, 7 host scheduler + truth (wall clock), 8 record D2H */
+     * 5 record keys + sort, 6 record pack, 7 host scheduler + truth (wall clock); compact transport
+     * (wall clock): 8 batch shipped -> its D2H copies complete, 9 copies complete -> expanded */
     double ms_phase[12];
 } wfs_counts;
 
@@ -206,6 +208,16 @@ int wfs_device_count(void);
 /* Pinned host memory for output buffers (so device->host copies are plain DMA). */
 void *wfs_host_alloc(int64_t bytes);
 void wfs_host_free(void *p);
+
+/* Host half of the compact record transport (csrc/transport.cuh): when the destination of the records
+ * is host memory they cross PCIe as 24-byte headers + the 16-byte sample blocks that differ from the
+ * fill pattern (baseline below `length`, 0 behind it) and are expanded into 244-byte raw_records
+ * (strax_interface.py:425-436) by host threads.  wfs_simulate / wfs_simulate_photons do this
+ * internally; this entry expands a compact batch the caller holds (and lets the expander be tested
+ * without a GPU).  hdr: n_records x {i64 time, i32 pulse_length, i16 channel, i16 record_i,
+ * u32 first block, u16 block mask, u16 length}; blocks: 16 bytes each.  Returns 0. */
+int wfs_expand_compact(const void *hdr, const void *blocks, int64_t n_records, uint8_t *records,
+                       int fill, int dt, int n_threads);
 
 /* Deterministic entry: photons in, records out.
  * Replaces Pulse.__call__ with preset gains (pulse.py:82-144) + Pulse.add_current (:276-318) +

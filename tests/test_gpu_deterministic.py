@@ -129,3 +129,34 @@ def test_many_overlapping_pulse_calls(n_calls, n_ch_used):
     out = sim.simulate_photons(t, ch, g, pcall, group_of)
     assert_records_equal(out['raw_records'], want['raw_records'], 'tpc')
     sim.close()
+
+
+@pytest.mark.parametrize('noise', [False, True])
+def test_compact_transport_equals_plain_copy(noise, monkeypatch):
+    """Records that cross PCIe in the compact form (k_pack<true> + host expansion, transport.cuh)
+    are byte-identical to the plain 244-byte copy -- with a constant baseline (few blocks in the
+    stream) and with noise (every block in the stream)."""
+    from tests.golden.synth import synth_photons
+    cfg = load_c0_config()
+    noise_data = None
+    if noise:
+        cfg['enable_noise'] = True
+        noise_data = np.round(np.random.default_rng(3).normal(0, 2, (4096, 494)))
+    rng = np.random.default_rng(11)
+    pcall, ch, t, g, group_of = synth_photons(cfg, rng, 10, big=True)
+    ix = np.arange(int(group_of.max()) + 1, dtype=np.int64) * 7
+    outs = {}
+    for mode in ('0', '2'):
+        monkeypatch.setenv('WFS_COMPACT', mode)
+        sim = make_sim(cfg, noise_data)
+        outs[mode] = sim.simulate_photons(t, ch, g, pcall, group_of, ix_rand=ix if noise else None)
+        d2h = sim.last_counts['d2h_bytes']
+        n = sim.last_counts['n_records_total']
+        assert n > 0
+        if mode == '0':
+            assert d2h == 244 * n
+        elif not noise:
+            assert d2h < 0.8 * 244 * n
+        sim.close()
+    for k in ('raw_records', 'raw_records_he'):
+        assert outs['0'][k].tobytes() == outs['2'][k].tobytes()

@@ -1,5 +1,6 @@
 // C-ABI of libwfsim_b200.so (declared in include/wfsim_b200.h).
 #include "handle.cuh"
+#include <stdlib.h>
 
 #include <string.h>
 #include <algorithm>
@@ -61,6 +62,7 @@ Handle::Handle(const wfs_params &p, const wfs_tables &t, int dev) : device(dev) 
         cfg.noise_len = t.noise_len;
         cfg.noise_nch = t.noise_nch;
     }
+    if (const char *e = getenv("WFS_COMPACT")) compact_mode = atoi(e);
     backend = new Backend(&cfg, stream, &launches);
     frontend_init(t);
 }
@@ -68,6 +70,8 @@ Handle::Handle(const wfs_params &p, const wfs_tables &t, int dev) : device(dev) 
 Handle::~Handle() {
     cudaSetDevice(device);
     frontend_release();
+    cstage.release();
+    delete pool;
     delete backend;
     for (void *p : owned) cudaFree(p);
     DevBuf *bufs[] = {&d_t, &d_ch, &d_gain, &d_pc, &d_pc_group, &d_pc_rank, &d_ix, &d_records, &d_groups};
@@ -160,6 +164,27 @@ void *wfs_host_alloc(int64_t bytes) {
 
 void wfs_host_free(void *p) { if (p) cudaFreeHost(p); }
 
+int wfs_expand_compact(const void *hdr, const void *blocks, int64_t n_records, uint8_t *records,
+                       int fill, int dt, int n_threads) {
+    if (n_records < 0 || (n_records > 0 && (!hdr || !records))) return WFS_E_ARG;
+    if (n_records == 0) return 0;
+    const CompactHdr *h = reinterpret_cast<const CompactHdr *>(hdr);
+    const uint8_t *b = reinterpret_cast<const uint8_t *>(blocks);
+    if (n_threads <= 1) {
+        expand_records(h, b, 0, n_records, records, (int16_t)fill, (int16_t)dt);
+        return 0;
+    }
+    HostPool pool(n_threads);
+    ExpandJob job;
+    job.pool = &pool;
+    job.hdr = h; job.blocks = b; job.n_rec = n_records; job.dst = records;
+    job.fill = (int16_t)fill; job.dt = (int16_t)dt;
+    job.arm((int)std::min<int64_t>(4 * n_threads, n_records));
+    pool.enqueue(&job);
+    job.wait();
+    return 0;
+}
+
 int wfs_simulate_photons(void *handle, int64_t n_photons, const int64_t *t_ns, const int32_t *channel,
                          const double *gain, const int32_t *pulse_call, int64_t n_pulse_calls,
                          const int32_t *group_of, int64_t n_groups, const int64_t *ix_rand,
@@ -195,6 +220,8 @@ int wfs_simulate_photons(void *handle, int64_t n_photons, const int64_t *t_ns, c
         b.ix_rand = H->d_ix.as<int64_t>();
     }
     uint8_t *d_rec = records;
+    // host destination: the records cross PCIe in the compact form and are expanded by host threads
+    const bool compact = !on_device && H->use_compact();
     if (on_device) {
         b.t = t_ns; b.channel = channel; b.gain = gain; b.pulse_call = pulse_call;
     } else {
@@ -208,8 +235,16 @@ int wfs_simulate_photons(void *handle, int64_t n_photons, const int64_t *t_ns, c
         WFS_CUDA_CHECK(cudaMemcpyAsync(H->d_pc.p, pulse_call, sizeof(int32_t) * n_photons, cudaMemcpyHostToDevice, s));
         b.t = H->d_t.as<int64_t>(); b.channel = H->d_ch.as<int32_t>();
         b.gain = H->d_gain.as<double>(); b.pulse_call = H->d_pc.as<int32_t>();
-        H->d_records.reserve((size_t)WFS_RECORD_BYTES * std::max<int64_t>(cap_records, 1));
-        d_rec = H->d_records.as<uint8_t>();
+        if (!compact) {
+            H->d_records.reserve((size_t)WFS_RECORD_BYTES * std::max<int64_t>(cap_records, 1));
+            d_rec = H->d_records.as<uint8_t>();
+        }
+    }
+    CompactOut co;
+    if (compact) {
+        H->cstage.job.wait();
+        H->cstage.reserve_device(std::max<int64_t>(cap_records, 1));
+        co = H->cstage.out();
     }
     wfs_group_info *d_groups = nullptr;
     if (groups && n_groups > 0) {
@@ -218,7 +253,7 @@ int wfs_simulate_photons(void *handle, int64_t n_photons, const int64_t *t_ns, c
     }
     WFS_CUDA_CHECK(cudaEventRecord(H->ev_b, s));
     BackendResult r;
-    H->backend->run(b, d_rec, cap_records, d_groups, r);
+    H->backend->run(b, d_rec, cap_records, d_groups, r, compact ? &co : nullptr);
     WFS_CUDA_CHECK(cudaEventRecord(H->ev_c, s));
     if (r.error) {
         H->last_error = r.error == WFS_E_PULSE_CACHE_TOO_LONG ? "Pulse cache too long" :
@@ -230,13 +265,18 @@ int wfs_simulate_photons(void *handle, int64_t n_photons, const int64_t *t_ns, c
     counts->need_records = r.n_records;
     if (r.n_records > cap_records) {
         rc = WFS_E_CAPACITY;
+    } else if (compact && r.n_records > 0) {
+        H->cstage.ship(H->host_pool(), s, r.n_records, r.n_blocks, records, H->record_fill(), (int16_t)H->cfg.p.dt);
+        counts->d2h_bytes = (int64_t)sizeof(CompactHdr) * r.n_records + 16 * r.n_blocks;
     } else if (!on_device && r.n_records > 0) {
         WFS_CUDA_CHECK(cudaMemcpyAsync(records, d_rec, (size_t)WFS_RECORD_BYTES * r.n_records, cudaMemcpyDeviceToHost, s));
+        counts->d2h_bytes = (int64_t)WFS_RECORD_BYTES * r.n_records;
     }
     if (d_groups)
         WFS_CUDA_CHECK(cudaMemcpyAsync(groups, d_groups, sizeof(wfs_group_info) * n_groups, cudaMemcpyDeviceToHost, s));
     WFS_CUDA_CHECK(cudaEventRecord(H->ev_d, s));
     WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+    H->cstage.job.wait();
     float ms;
     WFS_CUDA_CHECK(cudaEventElapsedTime(&ms, H->ev_a, H->ev_b)); counts->ms_h2d = ms;
     WFS_CUDA_CHECK(cudaEventElapsedTime(&ms, H->ev_b, H->ev_c)); counts->ms_total = ms;

@@ -26,7 +26,7 @@ constexpr int kBlk = 8;                 // samples per digitize thread
 
 enum Scalar {
     S_NVALID = 0, S_NPULSES, S_NWIN, S_NTILES, S_NITVSLOTS, S_NREC, S_MINSAMPLE, S_MAXSAMPLE,
-    S_ERR, S_NITV, S_NSAMPLES, S_CLASS0, S_CLASS1, S_CLASS2, S_COUNT
+    S_ERR, S_NITV, S_NSAMPLES, S_CLASS0, S_CLASS1, S_CLASS2, S_NBLOCKS, S_COUNT
 };
 
 struct WinMeta {
@@ -884,11 +884,18 @@ __global__ void k_class_counts(int64_t n_rec, const uint64_t *keys, int class_sh
 // Record packing (strax_interface.py:425-436): 32 records per CTA (4 per warp), assembled in shared
 // memory and written as one contiguous, 16-byte-vectorised span at their final sorted position
 // (244 B = 61 words: 6 header words + 55 data words).
+// kCompact: the records leave in the compact transport form instead (transport.cuh): a 24-byte
+// header per record at its final sorted position and only the 8-sample blocks that differ from the
+// fill pattern (baseline below `length`, zero behind it), appended to a block stream through one
+// atomic per CTA (the header carries the offset, so the stream order does not matter).
 constexpr int kPackRecs = 32;
+template <bool kCompact>
 __global__ void __launch_bounds__(256)
 k_pack(int64_t n_rec, DeviceConfig c, const uint32_t *__restrict__ rec_vals,
-       const RecDesc *__restrict__ desc, const int16_t *__restrict__ dense, uint32_t *__restrict__ out) {
+       const RecDesc *__restrict__ desc, const int16_t *__restrict__ dense, uint32_t *__restrict__ out,
+       uint32_t *__restrict__ chdr, uint4 *__restrict__ cblk, int64_t *scalars) {
     __shared__ __align__(16) uint32_t s_rec[kPackRecs * 61];
+    __shared__ uint32_t s_mask[kPackRecs], s_off[kPackRecs];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t j0 = (int64_t)blockIdx.x * kPackRecs;
     const int nhere = (int)min((int64_t)kPackRecs, n_rec - j0);
@@ -896,6 +903,7 @@ k_pack(int64_t n_rec, DeviceConfig c, const uint32_t *__restrict__ rec_vals,
     // dependent-load chains in flight), then every warp copies its 4 records
     __shared__ RecDesc s_desc[kPackRecs];
     if (warp == 0 && lane < nhere) s_desc[lane] = desc[rec_vals[j0 + lane]];
+    if (kCompact && threadIdx.x < kPackRecs) s_mask[threadIdx.x] = 0;
     __syncthreads();
     uint32_t v0[4], v1[4];
 #pragma unroll
@@ -931,12 +939,64 @@ k_pack(int64_t n_rec, DeviceConfig c, const uint32_t *__restrict__ rec_vals,
         if (lane + 32 < 55) o[6 + 32 + lane] = a1;
     }
     __syncthreads();
-    // contiguous span of nhere * 244 bytes starting at a 16-byte aligned address (32 * 244 = 488 * 16)
-    uint4 *dst = reinterpret_cast<uint4 *>(out + j0 * 61);
-    const uint4 *srcv = reinterpret_cast<const uint4 *>(s_rec);
-    const int nvec = (nhere * 61) / 4, rem = (nhere * 61) % 4;
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = srcv[i];
-    if (threadIdx.x < rem) out[j0 * 61 + nvec * 4 + threadIdx.x] = s_rec[nvec * 4 + threadIdx.x];
+    if (!kCompact) {
+        // contiguous span of nhere * 244 bytes starting at a 16-byte aligned address (32 * 244 = 488 * 16)
+        uint4 *dst = reinterpret_cast<uint4 *>(out + j0 * 61);
+        const uint4 *srcv = reinterpret_cast<const uint4 *>(s_rec);
+        const int nvec = (nhere * 61) / 4, rem = (nhere * 61) % 4;
+        for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = srcv[i];
+        if (threadIdx.x < rem) out[j0 * 61 + nvec * 4 + threadIdx.x] = s_rec[nvec * 4 + threadIdx.x];
+        return;
+    }
+    // ---- compact form ----
+    const uint32_t fill_h = (uint32_t)(uint16_t)(int16_t)max(c.p.baseline, 0);
+    for (int idx = threadIdx.x; idx < nhere * kBlocksPerRecord; idx += blockDim.x) {
+        const int r = idx / kBlocksPerRecord, b = idx - r * kBlocksPerRecord;
+        const int length = s_desc[r].length;
+        const uint32_t *w = s_rec + r * 61 + 6 + 4 * b;
+        const int nw = b == kBlocksPerRecord - 1 ? 3 : 4;
+        bool diff = false;
+        for (int k = 0; k < nw; k++) {
+            const int s = 8 * b + 2 * k;
+            const uint32_t expect = (s < length ? fill_h : 0u) | ((s + 1 < length ? fill_h : 0u) << 16);
+            diff |= w[k] != expect;
+        }
+        if (diff) atomicOr(&s_mask[r], 1u << b);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t cnt = lane < nhere ? __popc(s_mask[lane]) : 0u;
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += a;
+        }
+        unsigned long long base = 0;
+        if (lane == 31 && inc) base = atomicAdd((unsigned long long *)&scalars[S_NBLOCKS], (unsigned long long)inc);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        s_off[lane] = (uint32_t)base + inc - cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x < nhere * 6) {
+        const int r = threadIdx.x / 6, k = threadIdx.x - r * 6;
+        const uint32_t *o = s_rec + r * 61;
+        uint32_t h;
+        if (k < 2) h = o[k];                                             // time
+        else if (k == 2) h = o[4];                                       // pulse_length
+        else if (k == 3) h = (o[3] >> 16) | ((o[5] & 0xffffu) << 16);    // channel, record_i
+        else if (k == 4) h = s_off[r];
+        else h = s_mask[r] | (o[2] << 16);                               // mask, length
+        chdr[(j0 + r) * 6 + k] = h;
+    }
+    for (int idx = threadIdx.x; idx < nhere * kBlocksPerRecord; idx += blockDim.x) {
+        const int r = idx / kBlocksPerRecord, b = idx - r * kBlocksPerRecord;
+        const uint32_t m = s_mask[r];
+        if (!((m >> b) & 1u)) continue;
+        const uint32_t *w = s_rec + r * 61 + 6 + 4 * b;
+        cblk[s_off[r] + __popc(m & ((1u << b) - 1u))] =
+            make_uint4(w[0], w[1], w[2], b == kBlocksPerRecord - 1 ? 0u : w[3]);
+    }
 }
 
 __global__ void k_group_info(int64_t n_groups, DeviceConfig c, const int64_t *group_lr,
@@ -997,7 +1057,7 @@ void Backend::release() {
     } while (0)
 
 void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_records,
-                  wfs_group_info *group_info_out, BackendResult &res) {
+                  wfs_group_info *group_info_out, BackendResult &res, const CompactOut *compact) {
     const DeviceConfig &c = *cfg_;
     res = BackendResult();
     const int64_t n = b.n, ng = b.n_groups;
@@ -1156,8 +1216,16 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
         prim_.sort_pairs(rec_keys_.as<uint64_t>(), rec_vals_.as<uint32_t>(), nrec, key_bits);
         LAUNCH(k_class_counts, 1, 32, nrec, rec_keys_.as<uint64_t>(), kChannelBits + time_bits, scal);
         WFS_CUDA_CHECK(cudaEventRecord(evp_[5], stream_));
-        LAUNCH(k_pack, div_up(nrec, kPackRecs), 256, nrec, c, rec_vals_.as<uint32_t>(),
-               rec_itv_.as<RecDesc>(), dense_.as<int16_t>(), reinterpret_cast<uint32_t *>(records_out));
+        if (compact) {
+            if ((uint64_t)nrec * kBlocksPerRecord >= (uint64_t(1) << 32)) { res.error = WFS_E_KEYBITS; return; }
+            LAUNCH(k_pack<true>, div_up(nrec, kPackRecs), 256, nrec, c, rec_vals_.as<uint32_t>(),
+                   rec_itv_.as<RecDesc>(), dense_.as<int16_t>(), nullptr,
+                   reinterpret_cast<uint32_t *>(compact->hdr), compact->blocks, scal);
+        } else {
+            LAUNCH(k_pack<false>, div_up(nrec, kPackRecs), 256, nrec, c, rec_vals_.as<uint32_t>(),
+                   rec_itv_.as<RecDesc>(), dense_.as<int16_t>(), reinterpret_cast<uint32_t *>(records_out),
+                   nullptr, nullptr, scal);
+        }
     }
     WFS_CUDA_CHECK(cudaEventRecord(evp_[6], stream_));
     WFS_CUDA_CHECK(cudaMemcpyAsync(h_scalars_, scal, sizeof(int64_t) * S_COUNT,
@@ -1173,6 +1241,7 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
     if (h_scalars_[S_ERR]) res.error = (int)h_scalars_[S_ERR];
     res.n_intervals = h_scalars_[S_NITV];
     res.n_samples = h_scalars_[S_NSAMPLES];
+    res.n_blocks = h_scalars_[S_NBLOCKS];
     res.n_windows = nwt;
     if (nrec > 0 && nrec <= cap_records) {
         const int64_t i1 = h_scalars_[S_CLASS1], i2 = h_scalars_[S_CLASS2];

@@ -1,6 +1,7 @@
 // Deterministic back end: photons -> pulses -> windows -> ADC samples -> ZLE -> raw_records.
 #pragma once
 #include "common.cuh"
+#include "transport.cuh"
 #include "../../include/wfsim_b200.h"
 
 namespace wfs {
@@ -46,6 +47,7 @@ struct PhotonBatch {
 struct BackendResult {
     int64_t n_valid_photons = 0, n_pulses = 0, n_windows = 0, n_tiles = 0;
     int64_t n_intervals = 0, n_records = 0, n_samples = 0;
+    int64_t n_blocks = 0;            // compact transport: 16-byte blocks in the stream
     int64_t n_rec_class[3] = {0, 0, 0};
     float ms_digitize = 0.f;
     float ms_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 1 sort, 2 windows, 3 digitize, 4 zle, 5 rec sort, 6 pack
@@ -60,8 +62,11 @@ public:
     // `records_out` (device pointer, capacity cap_records rows): [tpc | he | aqmon] segments each
     // sorted by (time, channel).  group_info_out: device pointer [n_groups] or nullptr.
     // If cap_records is too small, res.n_records holds the need and nothing is written.
+    // With `compact` the records leave in the compact transport form (transport.cuh) instead:
+    // headers at compact->hdr[0 .. n_records), res.n_blocks blocks at compact->blocks; cap_records
+    // then bounds those buffers and records_out is unused.
     void run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_records,
-             wfs_group_info *group_info_out, BackendResult &res);
+             wfs_group_info *group_info_out, BackendResult &res, const CompactOut *compact = nullptr);
     void release();
 
 private:

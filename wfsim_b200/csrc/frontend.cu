@@ -790,20 +790,36 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     wfs_outputs *out = so.out;
     F.b_groups.reserve(sizeof(wfs_group_info) * (size_t)std::max<int32_t>(ngroups, 1));
     // records are produced in a device buffer of the lane; with host outputs two buffers alternate:
-    // batch k is copied to the host on the copy stream while the lane's next batch runs
+    // batch k travels to the host on the copy stream while the lane's next batch runs.  Host
+    // destinations get the compact transport form (transport.cuh) unless it is switched off.
     const int par = so.resident ? 0 : (int)(L.local_batches & 1);
     DevBuf &rb = par ? F.b_records2 : F.b_records;
-    if (!so.resident && F.copy_pending[par]) {
-        WFS_CUDA_CHECK(cudaEventSynchronize(F.ev_copy[par]));
-        F.copy_pending[par] = false;
+    CompactStage &cs = F.cstage[par];
+    if (!so.resident) {
+        if (F.copy_pending[par]) {
+            WFS_CUDA_CHECK(cudaEventSynchronize(F.ev_copy[par]));
+            F.copy_pending[par] = false;
+        }
+        cs.job.wait();
     }
     const bool want_records = so.resident || (out && out->records);
-    if (want_records)
-        rb.reserve((size_t)WFS_RECORD_BYTES * (size_t)std::max<int64_t>(2 * (n_ph + n_ap) + 65536, 1));
-    int64_t cap_here = want_records ? (int64_t)(rb.cap / WFS_RECORD_BYTES) : 0;
+    const bool compact = !so.resident && want_records && H->use_compact();
+    CompactOut co;
+    int64_t cap_here = 0;
+    auto reserve_records = [&](int64_t n_rec) {
+        if (compact) {
+            cs.reserve_device(n_rec);
+            cap_here = cs.cap_records();
+            co = cs.out();
+        } else if (want_records) {
+            rb.reserve((size_t)WFS_RECORD_BYTES * (size_t)n_rec);
+            cap_here = (int64_t)(rb.cap / WFS_RECORD_BYTES);
+        }
+    };
+    reserve_records(std::max<int64_t>(2 * (n_ph + n_ap) + 65536, 1));
     uint8_t *d_rec = rb.as<uint8_t>();
     if (ngroups > 0) {
-        L.B->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res);
+        L.B->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res, compact ? &co : nullptr);
         if (res.error) {
             H->last_error = res.error == WFS_E_PULSE_CACHE_TOO_LONG ? "Pulse cache too long"
                                                                     : "back end error (key bits)";
@@ -811,11 +827,10 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         }
         if (want_records && res.n_records > cap_here) {
             // the device buffer was too small: grow it and redo the back end
-            rb.reserve((size_t)WFS_RECORD_BYTES * (size_t)res.n_records);
-            cap_here = (int64_t)(rb.cap / WFS_RECORD_BYTES);
+            reserve_records(res.n_records);
             d_rec = rb.as<uint8_t>();
             WFS_CUDA_CHECK(cudaMemsetAsync(F.b_trig.p, 0, 4 * (size_t)std::max<int64_t>(2 * npc, 1), s));
-            L.B->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res);
+            L.B->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res, compact ? &co : nullptr);
         }
     }
     std::vector<wfs_group_info> h_groups((size_t)ngroups);
@@ -865,6 +880,9 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         so.n_groups += ngroups;
         so.n_batches = std::max(so.n_batches, batch_index + 1);
         for (int k = 0; k < 3; k++) cn->n_records[k] += fits ? res.n_rec_class[k] : 0;
+        if (!so.resident && fits)
+            cn->d2h_bytes += compact ? (int64_t)sizeof(CompactHdr) * res.n_records + 16 * res.n_blocks
+                                     : (int64_t)WFS_RECORD_BYTES * res.n_records;
         cn->n_pe += n_pe;
         cn->n_photons += res.n_valid_photons;
         cn->n_pulses += res.n_pulses;
@@ -887,11 +905,16 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         // readbacks must not queue behind a gigabyte of records
         const size_t total_bytes = (size_t)res.n_records * WFS_RECORD_BYTES, piece = size_t(8) << 20;
         uint8_t *dst = out->records + (size_t)rec0 * WFS_RECORD_BYTES;
-        for (size_t o = 0; o < total_bytes; o += piece)
-            WFS_CUDA_CHECK(cudaMemcpyAsync(dst + o, d_rec + o, std::min(piece, total_bytes - o),
-                                           cudaMemcpyDeviceToHost, L.copy_stream));
-        WFS_CUDA_CHECK(cudaEventRecord(F.ev_copy[par], L.copy_stream));
-        F.copy_pending[par] = true;
+        if (compact) {
+            cs.ship(H->host_pool(), L.copy_stream, res.n_records, res.n_blocks, dst, H->record_fill(),
+                    (int16_t)p.dt, &H->tstats);
+        } else {
+            for (size_t o = 0; o < total_bytes; o += piece)
+                WFS_CUDA_CHECK(cudaMemcpyAsync(dst + o, d_rec + o, std::min(piece, total_bytes - o),
+                                               cudaMemcpyDeviceToHost, L.copy_stream));
+            WFS_CUDA_CHECK(cudaEventRecord(F.ev_copy[par], L.copy_stream));
+            F.copy_pending[par] = true;
+        }
     }
     if (out && out->groups)
         for (int32_t gi = 0; gi < ngroups; gi++)
@@ -991,6 +1014,7 @@ static void release_frontend_buffers(Frontend &F) {
                      &F.b_phnap, &F.b_apoff, &F.b_picount, &F.b_pioff, &F.b_pecount, &F.b_peoff, &F.b_irun, &F.b_pcgroup,
                      &F.b_pcrank, &F.b_trig, &F.b_records, &F.b_records2, &F.b_groups, &F.b_scal};
     for (DevBuf *b : all) b->release();
+    for (CompactStage &cs : F.cstage) cs.release();
     F.prim.release();
     if (F.ev_ready) {
         cudaEventDestroy(F.ev_ready); cudaEventDestroy(F.ev_copy[0]); cudaEventDestroy(F.ev_copy[1]);
@@ -1018,6 +1042,8 @@ static int run_plan(Handle *H, Plan &P, uint64_t seed, wfs_outputs *out, wfs_cou
     if (!H->frontend) throw std::runtime_error("front-end tables missing (SPE table is required for wfs_simulate)");
     memset(counts, 0, sizeof(*counts));
     const int64_t launches0 = H->launches.n;
+    H->tstats.ns_copy = 0;
+    H->tstats.ns_expand = 0;
     SimOut so;
     so.out = out;
     so.counts = counts;
@@ -1054,8 +1080,11 @@ static int run_plan(Handle *H, Plan &P, uint64_t seed, wfs_outputs *out, wfs_cou
         if (failure[li]) {
             for (int lj = 0; lj < n_lanes; lj++) {   // drain before reporting
                 cudaStreamSynchronize(H->lanes[lj]->stream);
-                cudaStreamSynchronize(H->lanes[lj]->copy_stream);
+                const bool copies_ok = cudaStreamSynchronize(H->lanes[lj]->copy_stream) == cudaSuccess;
                 H->lanes[lj]->F->copy_pending[0] = H->lanes[lj]->F->copy_pending[1] = false;
+                for (CompactStage &cs : H->lanes[lj]->F->cstage) {
+                    if (copies_ok) cs.job.wait(); else cs.job.abandon();
+                }
             }
             std::rethrow_exception(failure[li]);
         }
@@ -1068,10 +1097,13 @@ static int run_plan(Handle *H, Plan &P, uint64_t seed, wfs_outputs *out, wfs_cou
         WFS_CUDA_CHECK(cudaStreamSynchronize(H->lanes[li]->stream));
         WFS_CUDA_CHECK(cudaStreamSynchronize(H->lanes[li]->copy_stream));
         H->lanes[li]->F->copy_pending[0] = H->lanes[li]->F->copy_pending[1] = false;
+        for (CompactStage &cs : H->lanes[li]->F->cstage) cs.job.wait();   // expansion into the caller's array
     }
     float ms;
     WFS_CUDA_CHECK(cudaEventElapsedTime(&ms, H->ev_a, H->ev_b));
     counts->ms_total = ms;
+    counts->ms_phase[8] = H->tstats.ns_copy.load() * 1e-6;
+    counts->ms_phase[9] = H->tstats.ns_expand.load() * 1e-6;
     counts->n_records_total = so.n_rec;
     counts->n_truth = so.n_truth;
     counts->n_groups = so.n_groups;

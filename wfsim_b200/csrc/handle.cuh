@@ -22,6 +22,20 @@ struct Handle {
     void *staged_plan = nullptr;        // Plan of wfs_stage_instructions (frontend.cu)
     // staging for host-pointer calls
     DevBuf d_t, d_ch, d_gain, d_pc, d_pc_group, d_pc_rank, d_ix, d_records, d_groups;
+    // compact record transport (transport.cuh): expansion threads + the stage of wfs_simulate_photons
+    HostPool *pool = nullptr;
+    CompactStage cstage;
+    TransportStats tstats;
+    int compact_mode = 1;               // WFS_COMPACT: 0 off, 1 on unless noise is enabled, 2 always
+
+    bool use_compact() const {
+        return compact_mode == 2 || (compact_mode == 1 && !(cfg.p.enable_noise && cfg.noise_t));
+    }
+    HostPool *host_pool() {
+        if (!pool) pool = new HostPool(HostPool::default_threads());
+        return pool;
+    }
+    int16_t record_fill() const { return (int16_t)std::max(cfg.p.baseline, 0); }
 
     Handle(const wfs_params &p, const wfs_tables &t, int dev);
     ~Handle();

@@ -1,0 +1,159 @@
+// Host side of the compact record transport (see transport.cuh): pinned staging, the expansion
+// thread pool and the record expander.  The reference builds each record with numpy slicing
+// (strax_interface.py:425-436); here the same 244 bytes are produced from the compact form.
+#include "transport.cuh"
+#include "../../include/wfsim_b200.h"
+
+#include <algorithm>
+#include <chrono>
+#include <stdlib.h>
+#include <string.h>
+
+namespace wfs {
+
+static_assert(WFS_RECORD_BYTES == 244 && WFS_SAMPLES_PER_RECORD == 110, "record layout");
+
+typedef void (*ExpandFn)(const CompactHdr *, const uint8_t *, int64_t, int64_t, uint8_t *, int16_t, int16_t);
+
+static ExpandFn pick_expander() {
+    const char *e = getenv("WFS_EXPAND_ISA");
+    const std::string want = e ? e : "";
+    __builtin_cpu_init();
+    const bool avx2 = __builtin_cpu_supports("avx2");
+    const bool avx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
+    if (want == "sse2") return expand_records_sse2;
+    if (want == "avx2" && avx2) return expand_records_avx2;
+    if (want == "avx512" && avx512) return expand_records_avx512;
+    return avx512 ? expand_records_avx512 : avx2 ? expand_records_avx2 : expand_records_sse2;
+}
+
+void expand_records(const CompactHdr *hdr, const uint8_t *blocks, int64_t j0, int64_t j1,
+                    uint8_t *dst_base, int16_t fill, int16_t dt) {
+    static const ExpandFn fn = pick_expander();
+    fn(hdr, blocks, j0, j1, dst_base, fill, dt);
+}
+
+// ---------------------------------------------------------------------------------------------
+void ExpandJob::arm(int n_slices) {
+    std::lock_guard<std::mutex> lk(mu);
+    slices = n_slices;
+    remaining = n_slices;
+    pending = true;
+}
+
+void ExpandJob::wait() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return !pending; });
+}
+
+void ExpandJob::abandon() {
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        pending = false;
+    }
+    cv.notify_all();
+}
+
+int HostPool::default_threads() {
+    if (const char *e = getenv("WFS_EXPAND_THREADS")) return std::max(1, atoi(e));
+    const int hw = (int)std::thread::hardware_concurrency();
+    return std::max(1, std::min(16, hw - 2));
+}
+
+HostPool::HostPool(int n_threads) {
+    for (int i = 0; i < std::max(1, n_threads); i++) threads_.emplace_back([this] { worker(); });
+}
+
+HostPool::~HostPool() {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto &t : threads_) t.join();
+}
+
+void HostPool::enqueue(ExpandJob *job) {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (int k = 0; k < job->slices; k++) queue_.push_back(Task{job, k});
+    }
+    cv_.notify_all();
+}
+
+static int64_t now_ns() {
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+void CUDART_CB HostPool::stream_callback(void *p) {
+    ExpandJob *job = reinterpret_cast<ExpandJob *>(p);
+    job->t_callback = now_ns();
+    job->pool->enqueue(job);
+}
+
+void HostPool::worker() {
+    for (;;) {
+        Task t;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return stop_ || !queue_.empty(); });
+            if (queue_.empty()) return;     // stop requested and nothing left
+            t = queue_.front();
+            queue_.pop_front();
+        }
+        ExpandJob *job = t.job;
+        const int64_t per = (job->n_rec + job->slices - 1) / job->slices;
+        const int64_t j0 = std::min(job->n_rec, per * t.k), j1 = std::min(job->n_rec, per * (t.k + 1));
+        if (j1 > j0) expand_records(job->hdr, job->blocks, j0, j1, job->dst, job->fill, job->dt);
+        bool last;
+        {
+            std::lock_guard<std::mutex> lk(job->mu);
+            last = --job->remaining == 0;
+            if (last) {
+                if (job->stats) {
+                    job->stats->ns_copy += job->t_callback - job->t_ship;
+                    job->stats->ns_expand += now_ns() - job->t_callback;
+                }
+                job->pending = false;
+            }
+        }
+        if (last) job->cv.notify_all();
+    }
+}
+
+void CompactStage::ship(HostPool *pool, cudaStream_t copy_stream, int64_t n_rec, int64_t n_blocks,
+                        uint8_t *dst, int16_t fill, int16_t dt, TransportStats *stats) {
+    const size_t hdr_bytes = sizeof(CompactHdr) * (size_t)n_rec, blk_bytes = (size_t)16 * (size_t)n_blocks;
+    job.wait();
+    h_hdr.reserve(hdr_bytes);
+    h_blk.reserve(blk_bytes + 16);
+    // in pieces: the copy engine serves streams in FIFO order, and small count readbacks of other
+    // lanes must not queue behind hundreds of megabytes
+    const size_t piece = size_t(8) << 20;
+    for (size_t o = 0; o < hdr_bytes; o += piece)
+        WFS_CUDA_CHECK(cudaMemcpyAsync((uint8_t *)h_hdr.p + o, d_hdr.as<uint8_t>() + o, std::min(piece, hdr_bytes - o),
+                                       cudaMemcpyDeviceToHost, copy_stream));
+    for (size_t o = 0; o < blk_bytes; o += piece)
+        WFS_CUDA_CHECK(cudaMemcpyAsync((uint8_t *)h_blk.p + o, d_blk.as<uint8_t>() + o, std::min(piece, blk_bytes - o),
+                                       cudaMemcpyDeviceToHost, copy_stream));
+    job.pool = pool;
+    job.stats = stats;
+    job.t_ship = now_ns();
+    job.hdr = reinterpret_cast<const CompactHdr *>(h_hdr.p);
+    job.blocks = reinterpret_cast<const uint8_t *>(h_blk.p);
+    job.n_rec = n_rec;
+    job.dst = dst;
+    job.fill = fill;
+    job.dt = dt;
+    // slices of at least 16k records: small batches are not worth a wake-up per thread
+    job.arm((int)std::max<int64_t>(1, std::min<int64_t>(4 * pool->size(), n_rec / 16384)));
+    if (cudaLaunchHostFunc(copy_stream, HostPool::stream_callback, &job) != cudaSuccess) {
+        {
+            std::lock_guard<std::mutex> lk(job.mu);
+            job.pending = false;
+        }
+        throw std::runtime_error("CUDA error: cudaLaunchHostFunc failed");
+    }
+}
+
+}  // namespace wfs

@@ -1,0 +1,126 @@
+// Record transport from HBM to the caller's host array.
+//
+// raw_records are 244 bytes each, most of them the constant baseline (and zero padding behind
+// `length`): copying them as they are makes the PCIe link the bottleneck of the whole path
+// (30 GB per 1e5 low-energy events).  The pack kernel can therefore emit a COMPACT form instead:
+//   CompactHdr[n_rec]   24 B: the header fields of strax_interface.py:425-436 that are not constant,
+//                       a 14-bit mask of the 8-sample blocks that differ from the fill pattern
+//                       (baseline for samples < length, 0 behind it) and the offset of the first one;
+//   blocks[n_blocks]    16 B per differing block (block 13 holds 6 samples + 2 pad).
+// Both streams are copied to pinned staging memory and a pool of host threads expands them into the
+// caller's array (header, fill pattern, patched blocks) with streaming stores, so the destination
+// needs neither pinning nor alignment.  Records are bit-identical to what k_pack<false> writes.
+#pragma once
+#include "common.cuh"
+#include "compact_format.h"
+
+#include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+
+namespace wfs {
+
+struct CompactOut {      // device pointers handed to Backend::run
+    CompactHdr *hdr = nullptr;
+    uint4 *blocks = nullptr;
+};
+
+// Expands records [j0, j1) of a compact batch into dst (dst = address of record 0 of the batch);
+// dispatches to the widest expander the CPU supports (WFS_EXPAND_ISA=sse2|avx2|avx512 overrides).
+void expand_records(const CompactHdr *hdr, const uint8_t *blocks, int64_t j0, int64_t j1,
+                    uint8_t *dst, int16_t fill, int16_t dt);
+
+class HostPool;
+
+struct TransportStats {          // wall clock, summed over the batches of one call
+    std::atomic<int64_t> ns_copy{0};      // ship -> copies complete (waits for the stream included)
+    std::atomic<int64_t> ns_expand{0};    // copies complete -> last slice expanded
+};
+
+// One batch in flight: filled in by the producer, enqueued (from a stream callback) when its D2H
+// copies have completed, executed in slices by the pool.
+struct ExpandJob {
+    HostPool *pool = nullptr;
+    const CompactHdr *hdr = nullptr;
+    const uint8_t *blocks = nullptr;
+    int64_t n_rec = 0;
+    uint8_t *dst = nullptr;
+    int16_t fill = 0, dt = 0;
+    int slices = 0;
+    TransportStats *stats = nullptr;
+    int64_t t_ship = 0, t_callback = 0;
+    // completion
+    std::mutex mu;
+    std::condition_variable cv;
+    int remaining = 0;
+    bool pending = false;
+
+    void arm(int n_slices);      // before the stream callback is queued
+    void wait();                 // until every slice has run (no-op if nothing is pending)
+    void abandon();              // the stream failed before the callback could run: nothing will come
+};
+
+class HostPool {
+public:
+    explicit HostPool(int n_threads);
+    ~HostPool();
+    int size() const { return (int)threads_.size(); }
+    void enqueue(ExpandJob *job);            // callable from a CUDA host function
+    static void CUDART_CB stream_callback(void *job);   // cudaLaunchHostFunc target
+    static int default_threads();
+
+private:
+    struct Task { ExpandJob *job; int k; };
+    void worker();
+    std::vector<std::thread> threads_;
+    std::deque<Task> queue_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    bool stop_ = false;
+};
+
+// Grow-only pinned host buffer.
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) WFS_CUDA_CHECK(cudaFreeHost(p));
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 4096;
+        WFS_CUDA_CHECK(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// Device buffers + pinned staging + job of one compact batch in flight.
+struct CompactStage {
+    DevBuf d_hdr, d_blk;
+    PinnedBuf h_hdr, h_blk;
+    ExpandJob job;
+    int64_t cap_records() const {
+        return (int64_t)std::min(d_hdr.cap / sizeof(CompactHdr), d_blk.cap / (16 * (size_t)kBlocksPerRecord));
+    }
+    void reserve_device(int64_t n_rec) {
+        d_hdr.reserve(sizeof(CompactHdr) * (size_t)n_rec);
+        d_blk.reserve((size_t)16 * kBlocksPerRecord * (size_t)n_rec);
+    }
+    CompactOut out() { return CompactOut{d_hdr.as<CompactHdr>(), d_blk.as<uint4>()}; }
+    // Queues the D2H copies of (n_rec headers, n_blocks blocks) on `copy_stream` and, behind them,
+    // the expansion into dst.  The caller must job.wait() before touching the stage again.
+    void ship(HostPool *pool, cudaStream_t copy_stream, int64_t n_rec, int64_t n_blocks, uint8_t *dst,
+              int16_t fill, int16_t dt, TransportStats *stats = nullptr);
+    void release() {
+        d_hdr.release(); d_blk.release(); h_hdr.release(); h_blk.release();
+    }
+};
+
+}  // namespace wfs

@@ -86,7 +86,7 @@ class Counts(C.Structure):
                     'n_records_total', 'n_truth', 'n_photons', 'n_pe', 'n_pulses', 'n_windows',
                     'n_intervals', 'n_samples', 'n_groups', 'n_pulse_calls', 'n_instructions',
                     'n_batches', 'gpu_launches', 'need_records', 'need_truth', 'need_groups',
-                    'need_batches')]
+                    'need_batches', 'd2h_bytes')]
                 + [(n, f64) for n in ('ms_total', 'ms_digitize', 'ms_h2d', 'ms_d2h')]
                 + [('ms_phase', f64 * 12)])
 
@@ -103,7 +103,8 @@ class GroupInfo(C.Structure):
 
 EXPORTS = ['wfs_create', 'wfs_destroy', 'wfs_last_error', 'wfs_abi_version', 'wfs_struct_sizes',
            'wfs_device_count', 'wfs_host_alloc', 'wfs_host_free', 'wfs_simulate_photons',
-           'wfs_simulate', 'wfs_stage_instructions', 'wfs_run_staged', 'wfs_sample_stage']
+           'wfs_simulate', 'wfs_stage_instructions', 'wfs_run_staged', 'wfs_sample_stage',
+           'wfs_expand_compact']
 
 _lib = None
 
@@ -131,6 +132,7 @@ def load():
     lib.wfs_host_alloc.argtypes = [i64]
     lib.wfs_host_free.argtypes = [vp]
     lib.wfs_destroy.argtypes = [vp]
+    lib.wfs_expand_compact.argtypes = [vp, vp, i64, vp, C.c_int, C.c_int, C.c_int]
     lib.wfs_create.argtypes = [C.POINTER(Params), C.POINTER(Tables), C.c_int, C.POINTER(vp)]
     lib.wfs_simulate_photons.argtypes = [
         vp, i64, vp, vp, vp, vp, i64, vp, i64, vp, C.c_uint64, C.c_int, vp, i64, vp,
