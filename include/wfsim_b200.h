@@ -210,12 +210,13 @@ void *wfs_host_alloc(int64_t bytes);
 void wfs_host_free(void *p);
 
 /* Host half of the compact record transport (csrc/transport.cuh): when the destination of the records
- * is host memory they cross PCIe as 24-byte headers + the 16-byte sample blocks that differ from the
+ * is host memory they cross PCIe as 24-byte headers + the 8-byte (4-sample) blocks that differ from the
  * fill pattern (baseline below `length`, 0 behind it) and are expanded into 244-byte raw_records
  * (strax_interface.py:425-436) by host threads.  wfs_simulate / wfs_simulate_photons do this
  * internally; this entry expands a compact batch the caller holds (and lets the expander be tested
  * without a GPU).  hdr: n_records x {i64 time, i32 pulse_length, i16 channel, i16 record_i,
- * u32 first block, u16 block mask, u16 length}; blocks: 16 bytes each.  Returns 0. */
+ * u32 first block, u32 block mask} (length = min(pulse_length - 110 record_i, 110)); blocks: 8 bytes
+ * each.  Returns 0. */
 int wfs_expand_compact(const void *hdr, const void *blocks, int64_t n_records, uint8_t *records,
                        int fill, int dt, int n_threads);
 

@@ -267,7 +267,7 @@ int wfs_simulate_photons(void *handle, int64_t n_photons, const int64_t *t_ns, c
         rc = WFS_E_CAPACITY;
     } else if (compact && r.n_records > 0) {
         H->cstage.ship(H->host_pool(), s, r.n_records, r.n_blocks, records, H->record_fill(), (int16_t)H->cfg.p.dt);
-        counts->d2h_bytes = (int64_t)sizeof(CompactHdr) * r.n_records + 16 * r.n_blocks;
+        counts->d2h_bytes = (int64_t)sizeof(CompactHdr) * r.n_records + kBlockBytes * r.n_blocks;
     } else if (!on_device && r.n_records > 0) {
         WFS_CUDA_CHECK(cudaMemcpyAsync(records, d_rec, (size_t)WFS_RECORD_BYTES * r.n_records, cudaMemcpyDeviceToHost, s));
         counts->d2h_bytes = (int64_t)WFS_RECORD_BYTES * r.n_records;

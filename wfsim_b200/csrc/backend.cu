@@ -885,7 +885,7 @@ __global__ void k_class_counts(int64_t n_rec, const uint64_t *keys, int class_sh
 // memory and written as one contiguous, 16-byte-vectorised span at their final sorted position
 // (244 B = 61 words: 6 header words + 55 data words).
 // kCompact: the records leave in the compact transport form instead (transport.cuh): a 24-byte
-// header per record at its final sorted position and only the 8-sample blocks that differ from the
+// header per record at its final sorted position and only the 4-sample blocks that differ from the
 // fill pattern (baseline below `length`, zero behind it), appended to a block stream through one
 // atomic per CTA (the header carries the offset, so the stream order does not matter).
 constexpr int kPackRecs = 32;
@@ -893,7 +893,7 @@ template <bool kCompact>
 __global__ void __launch_bounds__(256)
 k_pack(int64_t n_rec, DeviceConfig c, const uint32_t *__restrict__ rec_vals,
        const RecDesc *__restrict__ desc, const int16_t *__restrict__ dense, uint32_t *__restrict__ out,
-       uint32_t *__restrict__ chdr, uint4 *__restrict__ cblk, int64_t *scalars) {
+       uint32_t *__restrict__ chdr, uint2 *__restrict__ cblk, int64_t *scalars) {
     __shared__ __align__(16) uint32_t s_rec[kPackRecs * 61];
     __shared__ uint32_t s_mask[kPackRecs], s_off[kPackRecs];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -953,11 +953,11 @@ k_pack(int64_t n_rec, DeviceConfig c, const uint32_t *__restrict__ rec_vals,
     for (int idx = threadIdx.x; idx < nhere * kBlocksPerRecord; idx += blockDim.x) {
         const int r = idx / kBlocksPerRecord, b = idx - r * kBlocksPerRecord;
         const int length = s_desc[r].length;
-        const uint32_t *w = s_rec + r * 61 + 6 + 4 * b;
-        const int nw = b == kBlocksPerRecord - 1 ? 3 : 4;
+        const uint32_t *w = s_rec + r * 61 + 6 + 2 * b;
+        const int nw = b == kBlocksPerRecord - 1 ? 1 : 2;
         bool diff = false;
         for (int k = 0; k < nw; k++) {
-            const int s = 8 * b + 2 * k;
+            const int s = 4 * b + 2 * k;
             const uint32_t expect = (s < length ? fill_h : 0u) | ((s + 1 < length ? fill_h : 0u) << 16);
             diff |= w[k] != expect;
         }
@@ -986,16 +986,15 @@ k_pack(int64_t n_rec, DeviceConfig c, const uint32_t *__restrict__ rec_vals,
         else if (k == 2) h = o[4];                                       // pulse_length
         else if (k == 3) h = (o[3] >> 16) | ((o[5] & 0xffffu) << 16);    // channel, record_i
         else if (k == 4) h = s_off[r];
-        else h = s_mask[r] | (o[2] << 16);                               // mask, length
+        else h = s_mask[r];
         chdr[(j0 + r) * 6 + k] = h;
     }
     for (int idx = threadIdx.x; idx < nhere * kBlocksPerRecord; idx += blockDim.x) {
         const int r = idx / kBlocksPerRecord, b = idx - r * kBlocksPerRecord;
         const uint32_t m = s_mask[r];
         if (!((m >> b) & 1u)) continue;
-        const uint32_t *w = s_rec + r * 61 + 6 + 4 * b;
-        cblk[s_off[r] + __popc(m & ((1u << b) - 1u))] =
-            make_uint4(w[0], w[1], w[2], b == kBlocksPerRecord - 1 ? 0u : w[3]);
+        const uint32_t *w = s_rec + r * 61 + 6 + 2 * b;
+        cblk[s_off[r] + __popc(m & ((1u << b) - 1u))] = make_uint2(w[0], b == kBlocksPerRecord - 1 ? 0u : w[1]);
     }
 }
 

@@ -881,7 +881,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         so.n_batches = std::max(so.n_batches, batch_index + 1);
         for (int k = 0; k < 3; k++) cn->n_records[k] += fits ? res.n_rec_class[k] : 0;
         if (!so.resident && fits)
-            cn->d2h_bytes += compact ? (int64_t)sizeof(CompactHdr) * res.n_records + 16 * res.n_blocks
+            cn->d2h_bytes += compact ? (int64_t)sizeof(CompactHdr) * res.n_records + kBlockBytes * res.n_blocks
                                      : (int64_t)WFS_RECORD_BYTES * res.n_records;
         cn->n_pe += n_pe;
         cn->n_photons += res.n_valid_photons;

@@ -20,7 +20,8 @@ static ExpandFn pick_expander() {
     const std::string want = e ? e : "";
     __builtin_cpu_init();
     const bool avx2 = __builtin_cpu_supports("avx2");
-    const bool avx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
+    const bool avx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
+                        __builtin_cpu_supports("bmi2") && __builtin_cpu_supports("popcnt");
     if (want == "sse2") return expand_records_sse2;
     if (want == "avx2" && avx2) return expand_records_avx2;
     if (want == "avx512" && avx512) return expand_records_avx512;
@@ -123,10 +124,10 @@ void HostPool::worker() {
 
 void CompactStage::ship(HostPool *pool, cudaStream_t copy_stream, int64_t n_rec, int64_t n_blocks,
                         uint8_t *dst, int16_t fill, int16_t dt, TransportStats *stats) {
-    const size_t hdr_bytes = sizeof(CompactHdr) * (size_t)n_rec, blk_bytes = (size_t)16 * (size_t)n_blocks;
+    const size_t hdr_bytes = sizeof(CompactHdr) * (size_t)n_rec, blk_bytes = (size_t)kBlockBytes * (size_t)n_blocks;
     job.wait();
     h_hdr.reserve(hdr_bytes);
-    h_blk.reserve(blk_bytes + 16);
+    h_blk.reserve(blk_bytes + 64);
     // in pieces: the copy engine serves streams in FIFO order, and small count readbacks of other
     // lanes must not queue behind hundreds of megabytes
     const size_t piece = size_t(8) << 20;

@@ -3,10 +3,10 @@
 // raw_records are 244 bytes each, most of them the constant baseline (and zero padding behind
 // `length`): copying them as they are makes the PCIe link the bottleneck of the whole path
 // (30 GB per 1e5 low-energy events).  The pack kernel can therefore emit a COMPACT form instead:
-//   CompactHdr[n_rec]   24 B: the header fields of strax_interface.py:425-436 that are not constant,
-//                       a 14-bit mask of the 8-sample blocks that differ from the fill pattern
-//                       (baseline for samples < length, 0 behind it) and the offset of the first one;
-//   blocks[n_blocks]    16 B per differing block (block 13 holds 6 samples + 2 pad).
+//   CompactHdr[n_rec]   24 B: the header fields of strax_interface.py:425-436 that are neither constant
+//                       nor derivable, a 28-bit mask of the 4-sample blocks that differ from the fill
+//                       pattern (baseline for samples < length, 0 behind it) and the offset of the first;
+//   blocks[n_blocks]    8 B per differing block (block 27 holds 2 samples + 2 pad).
 // Both streams are copied to pinned staging memory and a pool of host threads expands them into the
 // caller's array (header, fill pattern, patched blocks) with streaming stores, so the destination
 // needs neither pinning nor alignment.  Records are bit-identical to what k_pack<false> writes.
@@ -24,7 +24,7 @@ namespace wfs {
 
 struct CompactOut {      // device pointers handed to Backend::run
     CompactHdr *hdr = nullptr;
-    uint4 *blocks = nullptr;
+    uint2 *blocks = nullptr;
 };
 
 // Expands records [j0, j1) of a compact batch into dst (dst = address of record 0 of the batch);
@@ -107,13 +107,13 @@ struct CompactStage {
     PinnedBuf h_hdr, h_blk;
     ExpandJob job;
     int64_t cap_records() const {
-        return (int64_t)std::min(d_hdr.cap / sizeof(CompactHdr), d_blk.cap / (16 * (size_t)kBlocksPerRecord));
+        return (int64_t)std::min(d_hdr.cap / sizeof(CompactHdr), d_blk.cap / ((size_t)kBlockBytes * kBlocksPerRecord));
     }
     void reserve_device(int64_t n_rec) {
         d_hdr.reserve(sizeof(CompactHdr) * (size_t)n_rec);
-        d_blk.reserve((size_t)16 * kBlocksPerRecord * (size_t)n_rec);
+        d_blk.reserve((size_t)kBlockBytes * kBlocksPerRecord * (size_t)n_rec);
     }
-    CompactOut out() { return CompactOut{d_hdr.as<CompactHdr>(), d_blk.as<uint4>()}; }
+    CompactOut out() { return CompactOut{d_hdr.as<CompactHdr>(), d_blk.as<uint2>()}; }
     // Queues the D2H copies of (n_rec headers, n_blocks blocks) on `copy_stream` and, behind them,
     // the expansion into dst.  The caller must job.wait() before touching the stage again.
     void ship(HostPool *pool, cudaStream_t copy_stream, int64_t n_rec, int64_t n_blocks, uint8_t *dst,
