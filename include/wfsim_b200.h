@@ -186,7 +186,8 @@ typedef struct wfs_counts {
     /* device time per phase, summed over batches (CUDA events on the library stream):
      * 0 sampling front end, 1 photon keys + sort, 2 pulses/windows, 3 digitize, 4 ZLE,
      * 5 record keys + sort, 6 record pack, 7 host scheduler + truth (wall clock); compact transport
-     * (wall clock): 8 batch shipped -> its D2H copies complete, 9 copies complete -> expanded */
+     * (wall clock): 8 batch shipped -> its D2H copies complete, 9 copies complete -> expanded;
+     * 10 / 11: number of batches whose photons / records were ordered per group in shared memory */
     double ms_phase[12];
 } wfs_counts;
 

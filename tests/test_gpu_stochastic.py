@@ -174,3 +174,31 @@ def test_sharding_invariance(sim):
     order = np.argsort(whole['truth']['time'], kind='stable')
     order2 = np.argsort(merged['truth']['time'], kind='stable')
     assert whole['truth'][order].tobytes() == merged['truth'][order2].tobytes()
+
+
+def test_group_local_photon_order_equals_device_wide_sort(monkeypatch):
+    """Low-energy events: every digitisation group is a short contiguous photon range, which the
+    back end orders per group in shared memory (Primitives::segment_sort_pairs).  Same bytes as
+    the device-wide radix sort, and the records equal the oracle's on the generated photons."""
+    from oracle import wfsim_oracle as orc
+    from tests.golden.synth_instructions import c1_like
+    s, cfg = make_sim()
+    inst = c1_like(300, seed=12)
+    outs = {}
+    for mode in ('0', '1'):
+        monkeypatch.setenv('WFS_SEGMENT_SORT', mode)
+        outs[mode] = s.simulate(inst, seed=33)
+        outs[mode] = {k: np.array(v) for k, v in outs[mode].items() if k != '_pinned'}
+    for k in ('raw_records', 'raw_records_he', 'truth', 'groups'):
+        assert outs['0'][k].tobytes() == outs['1'][k].tobytes(), k
+    assert len(outs['1']['raw_records']) > 1000
+    out = outs['1']
+    ph = s.sample_stage(inst, stage=0, seed=33)
+    ph = ph[ph['channel'] >= 0]
+    pcall = ph['instruction'] * 2 + ((ph['flags'] >> 1) & 1)
+    uniq, pc = np.unique(pcall, return_inverse=True)
+    group_of = np.zeros(len(uniq), np.int32)
+    group_of[pc] = group_of_photons(ph, out['groups'], cfg)
+    want = orc.simulate_photons(cfg, pc.astype(np.int32), ph['channel'], ph['t'], ph['gain'], group_of)
+    assert out['raw_records'].tobytes() == want['raw_records'].tobytes()
+    s.close()

@@ -94,7 +94,7 @@ __device__ __forceinline__ bool photon_valid(int32_t ch, int32_t pc, const Devic
     return ch >= 0 && ch < c.p.n_tpc_pmts && pc >= 0 && pc < n_pc && c.gains[ch] != 0.0;
 }
 
-__global__ void k_group_tmin(PhotonBatch b, DeviceConfig c, int64_t *group_tmin) {
+__global__ void k_group_tmin(PhotonBatch b, DeviceConfig c, int64_t *group_tmin, uint32_t *group_nvalid) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = false;
     int g = -1;
@@ -115,7 +115,16 @@ __global__ void k_group_tmin(PhotonBatch b, DeviceConfig c, int64_t *group_tmin)
         int64_t other = __shfl_sync(0xffffffffu, t, o);
         if ((m >> o) & 1u) mn = other < mn ? other : mn;
     }
-    if (valid && (m & ((1u << lane) - 1u)) == 0) atomicMin((long long *)&group_tmin[g], (long long)mn);
+    if (valid && (m & ((1u << lane) - 1u)) == 0) {
+        atomicMin((long long *)&group_tmin[g], (long long)mn);
+        if (group_nvalid) atomicAdd(&group_nvalid[g], (uint32_t)__popc(m));   // invalid lanes carry g = -1
+    }
+}
+
+// keys behind the valid photons of a segment-sorted batch read as "invalid" (they sort last)
+__global__ void k_fill_invalid_tail(int64_t n, const uint32_t *n_valid, uint64_t invalid_key, uint64_t *keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && i >= (int64_t)*n_valid) keys[i] = invalid_key;
 }
 
 __global__ void k_build_keys(PhotonBatch b, DeviceConfig c, KeyLayout kl, const int64_t *group_tmin,
@@ -1044,7 +1053,8 @@ void Backend::release() {
     DevBuf *all[] = {&keys_, &vals_, &st_, &sg_, &flags64_, &pulse_first_, &pulse_left_, &pulse_win_,
                      &win_first_pulse_, &win_meta_, &win_scan_, &group_tmin_, &group_lr_, &scalars_,
                      &dense_, &itv_, &itv_nrec_, &itv_rec0_, &rec_keys_, &rec_vals_,
-                     &rec_itv_, &group_nitv_, &group_ix_, &pstart_, &flag8_, &cta_first_, &phq_};
+                     &rec_itv_, &group_nitv_, &group_ix_, &pstart_, &flag8_, &cta_first_, &phq_,
+                     &group_nvalid_, &group_out_};
     for (DevBuf *b : all) b->release();
     prim_.release();
 }
@@ -1090,10 +1100,36 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
         sg_.reserve(sizeof(double) * n);
         flags64_.reserve(sizeof(uint64_t) * (n + 1));
         pstart_.reserve((size_t)n + 1);
-        LAUNCH(k_group_tmin, div_up(n, T), T, b, c, group_tmin_.as<int64_t>());
+        const bool seg_sort_on = !(getenv("WFS_SEGMENT_SORT") && atoi(getenv("WFS_SEGMENT_SORT")) == 0);
+        const bool by_group = seg_sort_on && b.group_start != nullptr && b.max_group_photons <= kSegSortMax &&
+                              kl.shift_group + 1 + 13 <= 64;
+        if (by_group) {
+            group_nvalid_.reserve(sizeof(uint32_t) * (ng + 1));
+            group_out_.reserve(sizeof(uint32_t) * (ng + 1));
+            WFS_CUDA_CHECK(cudaMemsetAsync(group_nvalid_.p, 0, sizeof(uint32_t) * (ng + 1), stream_));
+        }
+        LAUNCH(k_group_tmin, div_up(n, T), T, b, c, group_tmin_.as<int64_t>(),
+               by_group ? group_nvalid_.as<uint32_t>() : nullptr);
         LAUNCH(k_build_keys, div_up(n, T), T, b, c, kl, group_tmin_.as<int64_t>(),
                keys_.as<uint64_t>(), vals_.as<uint32_t>(), scal);
-        prim_.sort_pairs(keys_.as<uint64_t>(), vals_.as<uint32_t>(), n, kl.total_bits);
+        res.segment_sorted_photons = by_group ? 1 : 0;
+        if (by_group) {
+            // photons arrive group by group: order each group by (channel, pulse call, time) in
+            // shared memory, dropping the invalid ones (dead PMT, no pattern)
+            prim_.exclusive_scan_u32(group_nvalid_.as<uint32_t>(), group_out_.as<uint32_t>(), ng, true);
+            prim_.sort_keys_alt.reserve((size_t)(n + 1) * sizeof(uint64_t));
+            prim_.sort_vals_alt.reserve((size_t)(n + 1) * sizeof(uint32_t));
+            const uint64_t invalid_key = (uint64_t)ng << kl.shift_group;
+            prim_.segment_sort_pairs(keys_.as<uint64_t>(), vals_.as<uint32_t>(), prim_.sort_keys_alt.as<uint64_t>(),
+                                     prim_.sort_vals_alt.as<uint32_t>(), b.group_start, group_out_.as<uint32_t>(),
+                                     ng, b.max_group_photons, kl.shift_group, invalid_key);
+            LAUNCH(k_fill_invalid_tail, div_up(n, T), T, n, group_out_.as<uint32_t>() + ng, invalid_key,
+                   prim_.sort_keys_alt.as<uint64_t>());
+            std::swap(keys_, prim_.sort_keys_alt);
+            std::swap(vals_, prim_.sort_vals_alt);
+        } else {
+            prim_.sort_pairs(keys_.as<uint64_t>(), vals_.as<uint32_t>(), n, kl.total_bits);
+        }
         WFS_CUDA_CHECK(cudaEventRecord(evp_[1], stream_));
         LAUNCH(k_gather_flags, div_up(n, T), T, b, kl, keys_.as<uint64_t>(), vals_.as<uint32_t>(),
                st_.as<int64_t>(), sg_.as<double>(), flags64_.as<uint64_t>(), pstart_.as<uint8_t>(), scal);

@@ -42,6 +42,12 @@ struct PhotonBatch {
     const int64_t *ix_rand = nullptr;      // [n_groups] or nullptr -> Philox(seed, group_base + g)
     uint64_t seed = 0;
     int64_t group_base = 0;                // global index of group 0 of this batch (RNG counter)
+    // Optional: the photons of group g are the contiguous range [group_start[g], group_start[g+1])
+    // of the arrays above (device array, [n_groups+1]) and no group holds more than
+    // max_group_photons of them -> the ordering is done per group in shared memory
+    // (Primitives::segment_sort_pairs) instead of by the device-wide radix sort.
+    const uint32_t *group_start = nullptr;
+    int64_t max_group_photons = 0;
 };
 
 struct BackendResult {
@@ -52,6 +58,7 @@ struct BackendResult {
     float ms_digitize = 0.f;
     float ms_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 1 sort, 2 windows, 3 digitize, 4 zle, 5 rec sort, 6 pack
     int error = 0;
+    int segment_sorted_photons = 0, segment_sorted_records = 0;   // 1: ordered per group in shared memory
 };
 
 class Backend {
@@ -79,7 +86,8 @@ private:
     int64_t *h_scalars_ = nullptr;   // pinned readback area
     DevBuf keys_, vals_, st_, sg_, flags64_, pulse_first_, pulse_left_, pulse_win_, win_first_pulse_,
         win_meta_, win_scan_, group_tmin_, group_lr_, scalars_, dense_, itv_, itv_nrec_,
-        itv_rec0_, rec_keys_, rec_vals_, rec_itv_, group_nitv_, group_ix_, pstart_, flag8_, cta_first_, phq_;
+        itv_rec0_, rec_keys_, rec_vals_, rec_itv_, group_nitv_, group_ix_, pstart_, flag8_, cta_first_, phq_,
+        group_nvalid_, group_out_;
 };
 
 }  // namespace wfs

@@ -65,6 +65,8 @@ struct LaunchCounter {
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+constexpr int kSegSortMax = 8192;   // items per segment of Primitives::segment_sort_pairs
+
 // ---------------------------------------------------------------------------------------------
 // Device-wide primitives (implemented in primitives.cu)
 // ---------------------------------------------------------------------------------------------
@@ -72,6 +74,7 @@ struct Primitives {
     cudaStream_t stream = nullptr;
     LaunchCounter *lc = nullptr;
     DevBuf scan_tmp, sort_hist, sort_keys_alt, sort_vals_alt, red_tmp;
+    bool seg_attr_set = false;
 
     // out[i] = sum_{j<i} in[j] (exclusive); out may alias in.  Returns nothing; total is
     // written to out[n] when `write_total` (out must then hold n+1 entries).
@@ -81,6 +84,17 @@ struct Primitives {
     // Stable LSD radix sort of (key, value) pairs on bits [0, key_bits).  Sorted result ends in
     // keys/vals (ping-pong handled inside).
     void sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, int key_bits);
+
+    // Stable sort of (key, value) pairs INSIDE segments: segment s holds items
+    // [seg_start[s], seg_start[s+1]) of keys_in/vals_in (device arrays), each at most kSegSortMax
+    // items (max_seg = the largest one, sizes the shared memory).  Ordered by bits [0, key_bits) of
+    // the key -- the bits above must be equal inside a segment; items with key >= drop_from are
+    // dropped.  Segment s is written to keys_out/vals_out at out_start[s] (or seg_start[s] when
+    // out_start is null).  One CTA per segment, everything in shared memory: one read and one
+    // write of the data instead of one per digit.
+    void segment_sort_pairs(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *keys_out,
+                            uint32_t *vals_out, const uint32_t *seg_start, const uint32_t *out_start,
+                            int64_t n_seg, int64_t max_seg, int key_bits, uint64_t drop_from);
 
     void release() {
         scan_tmp.release(); sort_hist.release(); sort_keys_alt.release();

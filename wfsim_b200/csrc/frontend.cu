@@ -362,6 +362,13 @@ static GenCtx make_ctx(Frontend &F, uint64_t seed) {
         H->launches.n++;                                           \
     } while (0)
 
+// first photon of every instruction (photons are laid out instruction by instruction): [n + 1]
+__global__ void k_instr_ph_start(uint32_t n, const uint32_t *__restrict__ emit_off,
+                                 const uint32_t *__restrict__ e_phoff, uint32_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) out[i] = e_phoff[emit_off[i]];
+}
+
 static void grow_instr(Frontend &F, int64_t n_new, int64_t n_old, cudaStream_t s) {
     auto g = [&](DevBuf &b, size_t el) { b.reserve_keep(el * (size_t)n_new, el * (size_t)n_old, s); };
     g(F.b_itype, 4); g(F.b_itime, 8); g(F.b_ix, 4); g(F.b_iy, 4); g(F.b_iz, 4); g(F.b_iamp, 4);
@@ -704,6 +711,13 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     WFS_CUDA_CHECK(cudaEventRecord(L.ev_d, s));
     std::vector<int64_t> acc((size_t)ntot * A_COUNT);
     WFS_CUDA_CHECK(cudaMemcpyAsync(acc.data(), F.b_acc.p, 8 * acc.size(), cudaMemcpyDeviceToHost, s));
+    std::vector<uint32_t> ph_start((size_t)ntot + 1, 0u);
+    if (n_ph > 0) {
+        F.b_phstart.reserve(4 * (size_t)(ntot + 1));
+        FLAUNCH(k_instr_ph_start, div_up(ntot + 1, 256), 256, (uint32_t)ntot, g.i_emitoff, g.e_phoff,
+                F.b_phstart.as<uint32_t>());
+        WFS_CUDA_CHECK(cudaMemcpyAsync(ph_start.data(), F.b_phstart.p, 4 * (size_t)(ntot + 1), cudaMemcpyDeviceToHost, s));
+    }
     WFS_CUDA_CHECK(cudaStreamSynchronize(s));
     float ms_front = 0;
     cudaEventElapsedTime(&ms_front, L.ev_c, L.ev_d);
@@ -760,6 +774,40 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         up(F.b_pcrank, pc_rank.data(), 4 * (size_t)npc);
         WFS_CUDA_CHECK(cudaMemsetAsync(F.b_trig.p, 0, 4 * (size_t)(2 * npc), s));
     }
+    // Photons are laid out instruction by instruction.  If the groups the scheduler formed are runs
+    // of consecutive instructions (the common case: no secondaries, no PMT afterpulses behind the
+    // primaries) every group is a contiguous photon range and the back end can order it in shared memory.
+    std::vector<uint32_t> gstart;
+    int64_t max_group_photons = 0;
+    {
+        bool contiguous = n_ap == 0 && n_ph > 0 && ngroups > 0;
+        if (contiguous) {
+            gstart.assign((size_t)ngroups + 1, UINT32_MAX);
+            int32_t last_group = -1;
+            for (int64_t i = 0; i < ntot && contiguous; i++) {
+                if (ph_start[i + 1] == ph_start[i] || instr_run[i] < 0) continue;   // no photons / in no Pulse call
+                const int32_t gi = runs[instr_run[i]].group;
+                if (gi < last_group) contiguous = false;
+                else if (gi > last_group) { gstart[gi] = ph_start[i]; last_group = gi; }
+            }
+        }
+        if (contiguous) {
+            gstart[ngroups] = (uint32_t)n_ph;
+            for (int32_t gi = ngroups - 1; gi >= 0; gi--)
+                if (gstart[gi] == UINT32_MAX) gstart[gi] = gstart[gi + 1];        // group without photons
+            gstart[0] = 0;     // photons in front of the first group belong to no Pulse call: dropped as invalid
+            for (int32_t gi = 0; gi < ngroups; gi++)
+                max_group_photons = std::max<int64_t>(max_group_photons, gstart[gi + 1] - gstart[gi]);
+            F.b_gstart.reserve(4 * (size_t)(ngroups + 1));
+            up(F.b_gstart, gstart.data(), 4 * (size_t)(ngroups + 1));
+        } else {
+            gstart.clear();
+        }
+        if (getenv("WFS_DEBUG_SEG"))
+            fprintf(stderr, "[wfs] batch %lld: n_ph %lld n_ap %lld groups %d contiguous %d max_group_photons %lld\n",
+                    (long long)batch_index, (long long)n_ph, (long long)n_ap, ngroups, (int)contiguous,
+                    (long long)max_group_photons);
+    }
     const double ms_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
     // ---- group numbering, in batch order ----
     int64_t group_base = 0;
@@ -786,6 +834,10 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     b.n_groups = ngroups;
     b.seed = seed;
     b.group_base = group_base;
+    if (!gstart.empty()) {
+        b.group_start = F.b_gstart.as<uint32_t>();
+        b.max_group_photons = max_group_photons;
+    }
     BackendResult res;
     wfs_outputs *out = so.out;
     F.b_groups.reserve(sizeof(wfs_group_info) * (size_t)std::max<int32_t>(ngroups, 1));
@@ -895,6 +947,8 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         cn->ms_phase[0] += ms_front;
         cn->ms_phase[7] += ms_host;
         for (int k = 1; k <= 6; k++) cn->ms_phase[k] += res.ms_phase[k];
+        cn->ms_phase[10] += res.segment_sorted_photons;
+        cn->ms_phase[11] += res.segment_sorted_records;
         ord.out_done = batch_index + 1;
     }
     ord.cv.notify_all();
@@ -1012,7 +1066,8 @@ static void release_frontend_buffers(Frontend &F) {
                      &F.b_nhits, &F.b_acc, &F.b_cdf, &F.b_cdfok, &F.b_pattern, &F.b_et, &F.b_einstr,
                      &F.b_enph, &F.b_ephoff, &F.b_pht, &F.b_phch, &F.b_phgain, &F.b_phinstr, &F.b_phflags,
                      &F.b_phnap, &F.b_apoff, &F.b_picount, &F.b_pioff, &F.b_pecount, &F.b_peoff, &F.b_irun, &F.b_pcgroup,
-                     &F.b_pcrank, &F.b_trig, &F.b_records, &F.b_records2, &F.b_groups, &F.b_scal};
+                     &F.b_pcrank, &F.b_trig, &F.b_records, &F.b_records2, &F.b_groups, &F.b_scal, &F.b_phstart,
+                     &F.b_gstart};
     for (DevBuf *b : all) b->release();
     for (CompactStage &cs : F.cstage) cs.release();
     F.prim.release();

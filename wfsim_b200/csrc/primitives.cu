@@ -3,6 +3,9 @@
 // and raw_record ordering by (time, channel) (strax.sort_by_time, strax_interface.py:453).
 #include "common.cuh"
 
+#include <algorithm>
+#include <stdlib.h>
+
 namespace wfs {
 
 // ---------------------------------------------------------------------------------------------
@@ -130,6 +133,20 @@ void Primitives::exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n
 // radix sort: 8-bit digits; per pass: upsweep (block digit histograms) -> scan -> downsweep
 // (stable in-block ranking via warp match_any, warp-striped item order)
 // ---------------------------------------------------------------------------------------------
+// Lanes of the warp holding the same 8-bit digit (among the lanes of `valid`).  Eight ballots:
+// match.any walks the distinct values of the warp one by one and random digits are almost all
+// distinct, which made it the dominant cost of every ranking loop.
+__device__ __forceinline__ unsigned match_digit8(uint32_t d, unsigned valid) {
+    unsigned m = valid;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const bool bit = (d >> b) & 1u;
+        const unsigned bal = __ballot_sync(0xffffffffu, bit);
+        m &= bit ? bal : ~bal;
+    }
+    return m;
+}
+
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortIPT = 8;
@@ -149,7 +166,7 @@ k_radix_upsweep(const uint64_t *__restrict__ keys, uint32_t *__restrict__ hist, 
         bool valid = i < n;
         uint32_t d = valid ? (uint32_t)((keys[i] >> shift) & 255u) : 0u;
         unsigned vm = __ballot_sync(0xffffffffu, valid);
-        unsigned m = __match_any_sync(0xffffffffu, d) & vm;
+        unsigned m = match_digit8(d, vm);
         if (valid && (m & ((1u << lane) - 1u)) == 0) atomicAdd(&h[d], __popc(m));
     }
     __syncthreads();
@@ -182,7 +199,7 @@ k_radix_downsweep(const uint64_t *__restrict__ keys_in, const uint32_t *__restri
         bool valid = i < n;
         uint32_t d = (uint32_t)((key[k] >> shift) & 255u);
         unsigned vm = __ballot_sync(0xffffffffu, valid);
-        unsigned m = __match_any_sync(0xffffffffu, d) & vm;
+        unsigned m = match_digit8(d, vm);
         uint32_t r = __popc(m & ((1u << lane) - 1u));
         uint32_t old = valid ? wcount[warp][d] : 0u;
         __syncwarp();
@@ -242,6 +259,174 @@ void Primitives::sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, int key_b
                                        cudaMemcpyDeviceToDevice, stream));
         WFS_CUDA_CHECK(cudaMemcpyAsync(vals, v_in, (size_t)n * sizeof(uint32_t),
                                        cudaMemcpyDeviceToDevice, stream));
+    }
+    WFS_CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
+// segmented sort: one CTA per segment, LSD radix on 8-bit digits entirely in shared memory.
+// Items are packed as (dropped | key bits | index in segment) in one 64-bit word; digits on which
+// all items of the segment agree are skipped (high time bits, pulse-call rank, ... are often constant).
+// ---------------------------------------------------------------------------------------------
+constexpr int kSegThreads = 256;
+constexpr int kSegWarps = kSegThreads / 32;
+constexpr int kSegIdxBits = 13;
+static_assert((1 << kSegIdxBits) >= kSegSortMax, "segment index bits");
+
+// Processes the segments with n_lo < n <= cap (the host launches one size class after the other, so
+// that the many short segments run at high occupancy).  Shared memory: [2][cap] packed items + [cap] ranks.
+template <int kRoundsMax>
+__global__ void __launch_bounds__(kSegThreads)
+k_segment_sort(int n_seg, const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ out_start,
+               const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+               uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int key_bits,
+               uint64_t drop_from, int n_lo, int cap) {
+    extern __shared__ uint64_t s_buf[];                 // [2][cap] items
+    __shared__ uint32_t wcount[kSegWarps][256];
+    __shared__ uint32_t dbase[256];
+    __shared__ uint32_t s_wsum[kSegWarps];
+    __shared__ unsigned long long s_diff;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint64_t kmask = (uint64_t(1) << key_bits) - 1u;
+    for (int seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
+        const uint32_t a = seg_start[seg];
+        const int n = (int)(seg_start[seg + 1] - a);
+        if (n <= n_lo || n > cap) continue;
+        const uint32_t o = out_start ? out_start[seg] : a;
+        uint64_t *cur = s_buf, *alt = s_buf + cap;
+        __syncthreads();
+        if (tid == 0) s_diff = 0ull;
+        __syncthreads();
+        {
+            uint64_t diff = 0, x0 = 0;
+            {
+                const uint64_t k = keys_in[a];
+                x0 = ((k >= drop_from ? (uint64_t(1) << key_bits) : 0ull) | (k & kmask)) << kSegIdxBits;
+            }
+            for (int i = tid; i < n; i += kSegThreads) {
+                const uint64_t k = keys_in[a + i];
+                const uint64_t x = (((k >= drop_from ? (uint64_t(1) << key_bits) : 0ull) | (k & kmask)) << kSegIdxBits) |
+                                   (uint64_t)i;
+                cur[i] = x;
+                diff |= (x ^ x0) >> kSegIdxBits;
+            }
+            const uint32_t dlo = __reduce_or_sync(0xffffffffu, (uint32_t)diff);
+            const uint32_t dhi = __reduce_or_sync(0xffffffffu, (uint32_t)(diff >> 32));
+            if (lane == 0 && (dlo | dhi)) atomicOr(&s_diff, ((unsigned long long)dhi << 32) | dlo);
+        }
+        __syncthreads();
+        const uint64_t diffbits = (uint64_t)s_diff << kSegIdxBits;
+        // warp w ranks the contiguous chunk [w * chunk, (w + 1) * chunk) in rounds of 32 items
+        const int rounds = (n + kSegThreads - 1) / kSegThreads;
+        const int chunk = rounds * 32;
+        for (int shift = kSegIdxBits; shift < kSegIdxBits + key_bits + 1; shift += 8) {
+            if (((diffbits >> shift) & 255u) == 0) continue;     // every item has the same digit
+            for (int i = tid; i < kSegWarps * 256; i += kSegThreads) (&wcount[0][0])[i] = 0;
+            __syncthreads();
+            // ranks stay in registers; the loop is unrolled so that the shared-memory loads and the
+            // ballots of several rounds are in flight while the per-digit counters are updated in order
+            uint64_t xs[kRoundsMax];
+            uint16_t rank[kRoundsMax];
+#pragma unroll
+            for (int k = 0; k < kRoundsMax; k++) {
+                if (k < rounds) {
+                    const int i = warp * chunk + k * 32 + lane;
+                    const bool valid = i < n;
+                    const uint64_t x = valid ? cur[i] : ~0ull;
+                    xs[k] = x;
+                    const uint32_t d = (uint32_t)(x >> shift) & 255u;
+                    const unsigned vm = __ballot_sync(0xffffffffu, valid);
+                    const unsigned m = __match_any_sync(0xffffffffu, d) & vm;
+                    const uint32_t r = __popc(m & lt);
+                    const uint32_t old = valid ? wcount[warp][d] : 0u;
+                    __syncwarp();
+                    if (valid && r == 0) wcount[warp][d] = old + __popc(m);
+                    __syncwarp();
+                    rank[k] = (uint16_t)(old + r);
+                }
+            }
+            __syncthreads();
+            {   // digit tid: exclusive prefix over the warps, then over the digits
+                uint32_t run = 0;
+#pragma unroll
+                for (int w = 0; w < kSegWarps; w++) {
+                    const uint32_t c = wcount[w][tid];
+                    wcount[w][tid] = run;
+                    run += c;
+                }
+                uint32_t inc = run;
+#pragma unroll
+                for (int s = 1; s < 32; s <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, inc, s);
+                    if (lane >= s) inc += u;
+                }
+                if (lane == 31) s_wsum[warp] = inc;
+                __syncthreads();
+                uint32_t wbase = 0;
+                for (int w = 0; w < warp; w++) wbase += s_wsum[w];
+                dbase[tid] = wbase + inc - run;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < kRoundsMax; k++) {
+                if (k < rounds) {
+                    const int i = warp * chunk + k * 32 + lane;
+                    if (i < n) {
+                        const uint64_t x = xs[k];
+                        const uint32_t d = (uint32_t)(x >> shift) & 255u;
+                        alt[dbase[d] + wcount[warp][d] + rank[k]] = x;
+                    }
+                }
+            }
+            __syncthreads();
+            uint64_t *t = cur; cur = alt; alt = t;
+        }
+        for (int i = tid; i < n; i += kSegThreads) {
+            const uint64_t x = cur[i];
+            if ((x >> (kSegIdxBits + key_bits)) & 1ull) continue;     // dropped (they sort behind the kept ones)
+            const uint32_t src = a + (uint32_t)(x & ((1u << kSegIdxBits) - 1u));
+            keys_out[o + i] = keys_in[src];
+            vals_out[o + i] = vals_in[src];
+        }
+    }
+}
+
+void Primitives::segment_sort_pairs(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *keys_out,
+                                    uint32_t *vals_out, const uint32_t *seg_start, const uint32_t *out_start,
+                                    int64_t n_seg, int64_t max_seg, int key_bits, uint64_t drop_from) {
+    if (n_seg <= 0) return;
+    if (max_seg > kSegSortMax || key_bits + 1 + kSegIdxBits > 64)
+        throw std::runtime_error("segment_sort_pairs: segment too large / key too wide");
+    auto smem_of = [](int cap) { return (size_t)cap * 2 * sizeof(uint64_t); };
+    if (!seg_attr_set) {
+        WFS_CUDA_CHECK(cudaFuncSetAttribute(k_segment_sort<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem_of(kSegSortMax)));
+        seg_attr_set = true;
+    }
+    // optionally two size classes (WFS_SEG_SPLIT): measured on B200 (C1 groups, 30-4800 photons) one
+    // launch over all sizes is as fast as any split -- the kernel is bound by the dependent
+    // rank/count chains of each pass, not by occupancy
+    const int split = getenv("WFS_SEG_SPLIT") ? atoi(getenv("WFS_SEG_SPLIT")) : 0;
+    const int cap_all = (int)((max_seg + 255) / 256 * 256);
+    auto launch = [&](int lo, int cap) {
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)200 * 1024 / (smem_of(cap) + 10 * 1024)));
+        const int grid = (int)std::min<int64_t>(n_seg, (int64_t)kNumSMs * per_sm);
+        if (cap <= 8 * kSegThreads)
+            k_segment_sort<8><<<grid, kSegThreads, smem_of(cap), stream>>>((int)n_seg, seg_start, out_start, keys_in,
+                                                                         vals_in, keys_out, vals_out, key_bits,
+                                                                         drop_from, lo, cap);
+        else
+            k_segment_sort<32><<<grid, kSegThreads, smem_of(cap), stream>>>((int)n_seg, seg_start, out_start, keys_in,
+                                                                          vals_in, keys_out, vals_out, key_bits,
+                                                                          drop_from, lo, cap);
+        lc->n++;
+    };
+    if (split >= 256 && split <= 8 * kSegThreads && cap_all > split) {
+        launch(0, split);
+        launch(split, cap_all);
+    } else {
+        launch(0, cap_all);
     }
     WFS_CUDA_CHECK(cudaGetLastError());
 }
