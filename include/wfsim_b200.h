@@ -249,6 +249,11 @@ typedef struct wfs_outputs {
     int64_t cap_groups;
     int64_t *batch_records;         /* [cap_batches][3]: records per data type of each batch */
     int64_t cap_batches;
+    /* per_pmt_truth (strax_interface.py:77-116, pulse.py:257-269): per truth row and PMT the four
+     * counters n_photon, n_pe, n_photon_trigger, n_pe_trigger and the two areas raw_area,
+     * raw_area_trigger of Pulse.add_truth.  NULL -> not produced. */
+    int32_t *truth_pmt_counts;      /* [cap_truth][4][n_tpc_pmts] */
+    double *truth_pmt_areas;        /* [cap_truth][2][n_tpc_pmts] */
 } wfs_outputs;
 
 /* Full path: instructions in, records + truth out.

@@ -202,3 +202,38 @@ def test_group_local_photon_order_equals_device_wide_sort(monkeypatch):
     want = orc.simulate_photons(cfg, pc.astype(np.int32), ph['channel'], ph['t'], ph['gain'], group_of)
     assert out['raw_records'].tobytes() == want['raw_records'].tobytes()
     s.close()
+
+
+def test_per_pmt_truth(sim):
+    """per_pmt_truth (strax_interface.py:77-116, pulse.py:257-269): the per-PMT counters add up to the
+    totals (the identity the reference's own test asserts, tests/test_wfsim.py:140-142), the bottom
+    PMTs add up to the `*_bottom` fields of the default mode, and n_photon_per_pmt is the channel
+    histogram of the photons the GPU generated for that Pulse call."""
+    cfg = sim.config
+    inst = c0_like(10, seed=17)
+    plain = sim.simulate(inst, seed=5)['truth']
+    t = sim.simulate(inst, seed=5, per_pmt_truth=True)['truth']
+    n_pmt = len(cfg['gains'])
+    assert len(t) == len(plain) and t['n_photon_per_pmt'].shape == (len(t), n_pmt)
+    assert 'n_photon_bottom' not in t.dtype.names
+    for f in ('n_photon', 'n_pe', 'n_photon_trigger', 'n_pe_trigger'):
+        np.testing.assert_array_equal(t[f], plain[f])
+        np.testing.assert_array_equal(t[f + '_per_pmt'].sum(axis=1), t[f], err_msg=f)
+        bottom = t[f + '_per_pmt'][:, cfg['channels_bottom']].sum(axis=1)
+        np.testing.assert_array_equal(bottom, plain[f + '_bottom'], err_msg=f + '_bottom')
+    for f in ('raw_area', 'raw_area_trigger'):
+        np.testing.assert_allclose(t[f + '_per_pmt'].sum(axis=1), t[f], rtol=1e-12)
+        np.testing.assert_allclose(t[f + '_per_pmt'][:, cfg['channels_bottom']].sum(axis=1), plain[f + '_bottom'],
+                                   rtol=1e-12)
+    assert t['n_photon'].sum() > 1000 and (t['n_pe'] >= t['n_photon']).all()
+    # channel histogram of the generated photons (save_full_truth: one Pulse call per instruction)
+    ph = sim.sample_stage(inst, stage=0, seed=5)
+    live = (ph['channel'] >= 0) & ((ph['flags'] >> 1) & 1 == 0)
+    live &= np.asarray(cfg['gains'])[np.clip(ph['channel'], 0, n_pmt - 1)] != 0
+    ph = ph[live]
+    order = np.argsort(inst['time'], kind='stable')     # truth rows are in execution (time) order
+    assert len(t) == len(inst)
+    for row, i in enumerate(order[:6]):
+        h = np.bincount(ph['channel'][ph['instruction'] == i], minlength=n_pmt)
+        if t['type'][row] == inst['type'][i] and t['amp'][row] == inst['amp'][i]:
+            np.testing.assert_array_equal(t['n_photon_per_pmt'][row], h)

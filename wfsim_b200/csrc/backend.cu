@@ -295,11 +295,11 @@ __global__ void k_truth_pulses(int64_t n_pulses, PhotonBatch b, DeviceConfig c, 
     if (p >= n_pulses) return;
     uint32_t a = pulse_first[p], e = pulse_first[p + 1];
     int32_t pc = pc_of(b, vals[a]);
-    if (pc & 1) return;   // PMT-afterpulse calls carry preset gains: n_double_pe = 0 (pulse.py:106)
+    if (pc & 1) return;   // PMT-afterpulse calls carry preset gains: n_double_pe = 0 (pulse.py:106);
+                          // their truth buffer is not the one get_truth reads (rawdata.py:317-318)
     int ch = win_key[pulse_win[p]] & ((1u << kChannelBits) - 1u);
     uint32_t ndpe = 0;
     for (uint32_t i = a; i < e; i++) ndpe += b.flags[vals[i]] & 1u;
-    if (!ndpe) return;
     const double thr = (double)(c.p.baseline - 1 - c.zle_thr[ch]) - 0.5;
     int trig = 0;
     for (uint32_t i = a; i < a + ndpe; i++) {
@@ -310,6 +310,28 @@ __global__ void k_truth_pulses(int64_t n_pulses, PhotonBatch b, DeviceConfig c, 
     if (trig) {
         atomicAdd(&b.trig_dpe_out[2 * pc], trig);
         if (ch >= c.p.n_top_pmts) atomicAdd(&b.trig_dpe_out[2 * pc + 1], trig);
+    }
+    if (b.pmt_counts) {   // per_pmt_truth: this thread owns (pulse call, channel)
+        const double gch = c.gains[ch];
+        int n_trig = 0;
+        int64_t area = 0, area_trig = 0;
+        for (uint32_t i = a; i < e; i++) {
+            const int64_t t = st[i];
+            const int r = (int)(t - floordiv(t, c.p.dt) * c.p.dt);
+            const bool above = sg[i] * c.current_max[r] * c.p.current_2_adc > thr;
+            const int64_t ar = llrint(sg[i] / gch * 4294967296.0);   // same fixed point as the totals (k_instr_truth)
+            area += ar;
+            if (above) { n_trig++; area_trig += ar; }
+        }
+        const int64_t npmt = c.p.n_tpc_pmts;
+        int32_t *cnt = b.pmt_counts + ((int64_t)(pc >> 1) * 4) * npmt + ch;
+        int64_t *ar_out = b.pmt_areas + ((int64_t)(pc >> 1) * 2) * npmt + ch;
+        cnt[0] = (int32_t)(e - a);
+        cnt[npmt] = (int32_t)(e - a + ndpe);
+        cnt[2 * npmt] = n_trig;
+        cnt[3 * npmt] = n_trig + trig;
+        ar_out[0] = area;
+        ar_out[npmt] = area_trig;
     }
 }
 

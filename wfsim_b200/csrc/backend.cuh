@@ -48,6 +48,10 @@ struct PhotonBatch {
     // (Primitives::segment_sort_pairs) instead of by the device-wide radix sort.
     const uint32_t *group_start = nullptr;
     int64_t max_group_photons = 0;
+    // Optional per-PMT truth (generate mode): per Pulse call r = pulse-call id >> 1 and PMT, written
+    // by the thread that owns the (pulse call, channel) pulse -- pulse.py:257-269 with per_pmt_truth.
+    int32_t *pmt_counts = nullptr;         // [n_pulse_calls / 2][4][n_tpc_pmts] n_photon, n_pe, n_photon_trigger, n_pe_trigger
+    int64_t *pmt_areas = nullptr;          // [n_pulse_calls / 2][2][n_tpc_pmts] raw_area, raw_area_trigger (x 2^32)
 };
 
 struct BackendResult {

@@ -838,6 +838,15 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         b.group_start = F.b_gstart.as<uint32_t>();
         b.max_group_photons = max_group_photons;
     }
+    const bool per_pmt = so.out && so.out->truth_pmt_counts && so.out->truth_pmt_areas && nruns > 0;
+    if (per_pmt) {
+        F.b_pmtcnt.reserve(sizeof(int32_t) * 4 * (size_t)n_ch * (size_t)nruns);
+        F.b_pmtarea.reserve(sizeof(int64_t) * 2 * (size_t)n_ch * (size_t)nruns);
+        WFS_CUDA_CHECK(cudaMemsetAsync(F.b_pmtcnt.p, 0, sizeof(int32_t) * 4 * (size_t)n_ch * (size_t)nruns, s));
+        WFS_CUDA_CHECK(cudaMemsetAsync(F.b_pmtarea.p, 0, sizeof(int64_t) * 2 * (size_t)n_ch * (size_t)nruns, s));
+        b.pmt_counts = F.b_pmtcnt.as<int32_t>();
+        b.pmt_areas = F.b_pmtarea.as<int64_t>();
+    }
     BackendResult res;
     wfs_outputs *out = so.out;
     F.b_groups.reserve(sizeof(wfs_group_info) * (size_t)std::max<int32_t>(ngroups, 1));
@@ -882,7 +891,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
             reserve_records(res.n_records);
             d_rec = rb.as<uint8_t>();
             WFS_CUDA_CHECK(cudaMemsetAsync(F.b_trig.p, 0, 4 * (size_t)std::max<int64_t>(2 * npc, 1), s));
-            L.B->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res, compact ? &co : nullptr);
+            L.B->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res, compact ? &co : nullptr);   // per-PMT truth: plain stores, safe to redo
         }
     }
     std::vector<wfs_group_info> h_groups((size_t)ngroups);
@@ -891,6 +900,14 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
                                        cudaMemcpyDeviceToHost, s));
     std::vector<int32_t> trig((size_t)std::max<int64_t>(2 * npc, 1), 0);
     if (npc) WFS_CUDA_CHECK(cudaMemcpyAsync(trig.data(), F.b_trig.p, 4 * (size_t)(2 * npc), cudaMemcpyDeviceToHost, s));
+    std::vector<int32_t> pmt_cnt;
+    std::vector<int64_t> pmt_area;
+    if (per_pmt) {
+        pmt_cnt.resize((size_t)4 * n_ch * nruns);
+        pmt_area.resize((size_t)2 * n_ch * nruns);
+        WFS_CUDA_CHECK(cudaMemcpyAsync(pmt_cnt.data(), F.b_pmtcnt.p, sizeof(int32_t) * pmt_cnt.size(), cudaMemcpyDeviceToHost, s));
+        WFS_CUDA_CHECK(cudaMemcpyAsync(pmt_area.data(), F.b_pmtarea.p, sizeof(int64_t) * pmt_area.size(), cudaMemcpyDeviceToHost, s));
+    }
     WFS_CUDA_CHECK(cudaStreamSynchronize(s));
     // truth rows of this batch (rawdata.py:313-375), one per Pulse call
     struct RunSum { int64_t sum[A_COUNT]; bool row; };
@@ -1001,6 +1018,13 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
             }
             write_truth_row(out->truth + (size_t)trow * WFS_TRUTH_BYTES, h0, run.type, T[i0], x, y, z,
                             amp, rsum[r].sum, pm, psig, em, esig, trig[4 * r], trig[4 * r + 1], p);
+            if (per_pmt) {
+                memcpy(out->truth_pmt_counts + (size_t)trow * 4 * n_ch, &pmt_cnt[(size_t)r * 4 * n_ch],
+                       sizeof(int32_t) * 4 * (size_t)n_ch);
+                double *dst = out->truth_pmt_areas + (size_t)trow * 2 * n_ch;
+                const int64_t *src = &pmt_area[(size_t)r * 2 * n_ch];
+                for (int k = 0; k < 2 * n_ch; k++) dst[k] = (double)src[k] / kAreaScale;
+            }
         }
         trow++;
     }
@@ -1067,7 +1091,7 @@ static void release_frontend_buffers(Frontend &F) {
                      &F.b_enph, &F.b_ephoff, &F.b_pht, &F.b_phch, &F.b_phgain, &F.b_phinstr, &F.b_phflags,
                      &F.b_phnap, &F.b_apoff, &F.b_picount, &F.b_pioff, &F.b_pecount, &F.b_peoff, &F.b_irun, &F.b_pcgroup,
                      &F.b_pcrank, &F.b_trig, &F.b_records, &F.b_records2, &F.b_groups, &F.b_scal, &F.b_phstart,
-                     &F.b_gstart};
+                     &F.b_gstart, &F.b_pmtcnt, &F.b_pmtarea};
     for (DevBuf *b : all) b->release();
     for (CompactStage &cs : F.cstage) cs.release();
     F.prim.release();

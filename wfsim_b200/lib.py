@@ -77,7 +77,8 @@ class InstrMaps(C.Structure):
 
 class Outputs(C.Structure):
     _fields_ = [('records', vp), ('cap_records', i64), ('truth', vp), ('cap_truth', i64),
-                ('groups', vp), ('cap_groups', i64), ('batch_records', vp), ('cap_batches', i64)]
+                ('groups', vp), ('cap_groups', i64), ('batch_records', vp), ('cap_batches', i64),
+                ('truth_pmt_counts', vp), ('truth_pmt_areas', vp)]
 
 
 class Counts(C.Structure):

@@ -170,13 +170,18 @@ class Simulator:
             self._pinned_cache = c = PinnedArray(self.lib, int(cap * 1.05) + 1024, raw_record_dtype())
         return c
 
-    def simulate(self, instructions, seed=0, maps=None, cap_records=None, pinned=False, rng_id=None):
+    def simulate(self, instructions, seed=0, maps=None, cap_records=None, pinned=False, rng_id=None,
+                 per_pmt_truth=None):
         """Full path for one set of instructions (see wfs_simulate in the header).
 
         Returns dict(raw_records, raw_records_he, raw_records_aqmon, truth, groups); records of
         each data type are sorted by (time, channel); truth rows are in Pulse-call execution
         order with `time` still the instruction time (the chunker sets it to t_first_photon,
-        strax_interface.py:481-482)."""
+        strax_interface.py:481-482).  With per_pmt_truth (default: config['per_pmt_truth']) the
+        truth rows carry the `*_per_pmt` fields of extra_truth_dtype_per_pmt instead of `*_bottom`."""
+        if per_pmt_truth is None:
+            per_pmt_truth = bool(self.config.get('per_pmt_truth', False))
+        n_pmt = int(self.params.n_tpc_pmts)
         instructions = np.ascontiguousarray(instructions)
         if instructions.dtype.itemsize != 70:
             raise ValueError('instructions must have the packed 70-byte instruction_dtype')
@@ -194,8 +199,10 @@ class Simulator:
             truth = np.zeros(cap_truth, tdt)
             groups = np.zeros(cap_groups, gdt)
             batch_records = np.zeros((cap_batches, 3), np.int64)
+            pmt_counts = np.zeros((cap_truth, 4, n_pmt), np.int32) if per_pmt_truth else None
+            pmt_areas = np.zeros((cap_truth, 2, n_pmt), np.float64) if per_pmt_truth else None
             out = wlib.Outputs(_ptr(rec), cap_rec, _ptr(truth), cap_truth, _ptr(groups), cap_groups,
-                               _ptr(batch_records), cap_batches)
+                               _ptr(batch_records), cap_batches, _ptr(pmt_counts), _ptr(pmt_areas))
             rc = self.lib.wfs_simulate(self.handle, _ptr(instructions.view(np.uint8)), n, C.byref(m),
                                        int(seed), C.byref(out), C.byref(counts))
             if rc == wlib.E_CAPACITY:
@@ -226,7 +233,18 @@ class Simulator:
                     o += br[b, k]
             res = dict(zip(('raw_records', 'raw_records_he', 'raw_records_aqmon'),
                            (np.concatenate(p) for p in parts)))
-        res['truth'] = truth[:counts.n_truth]
+        truth = truth[:counts.n_truth]
+        if per_pmt_truth:
+            full = np.zeros(len(truth), truth_dtype(n_pmt))
+            for name in full.dtype.names:
+                if name in truth.dtype.names:
+                    full[name] = truth[name]
+            for k, f in enumerate(('n_photon', 'n_pe', 'n_photon_trigger', 'n_pe_trigger')):
+                full[f + '_per_pmt'] = pmt_counts[:len(truth), k]
+            for k, f in enumerate(('raw_area', 'raw_area_trigger')):
+                full[f + '_per_pmt'] = pmt_areas[:len(truth), k]
+            truth = full
+        res['truth'] = truth
         res['groups'] = groups[:counts.n_groups]
         res['_pinned'] = None
         return res

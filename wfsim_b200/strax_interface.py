@@ -95,8 +95,6 @@ class ChunkRawRecords(object):
         self.simulator = rawdata_generator(config, resource=resource, device=device) \
             if rawdata_generator is not None else Simulator(config, resource=resource, device=device)
         truth_per_n_pmts = self._n_channels if config.get('per_pmt_truth') else False
-        if truth_per_n_pmts:
-            raise NotImplementedError('per_pmt_truth is not produced by the device path yet')
         self.truth_dtype = extra_truth_dtype_per_pmt(truth_per_n_pmts)
         self.seed = int(seed if seed is not None else (config.get('seed') or 0))
         self._finished = False
