@@ -810,6 +810,12 @@ k_zle(int64_t n_wtot, DeviceConfig c, const WinMeta *__restrict__ meta,
             int last = kNeg, start = kNeg;
             const uint8_t *f = flag8 + blk0;
             for (int b = 0; b < nblk; b++) {
+                // most flag bytes are zero (baseline): skip them eight at a time
+                if (((reinterpret_cast<uintptr_t>(f + b) & 7) == 0) && b + 8 <= nblk &&
+                    *reinterpret_cast<const unsigned long long *>(f + b) == 0ull) {
+                    b += 7;
+                    continue;
+                }
                 uint32_t byte = f[b];
                 while (byte) {
                     const int pos = b * kBlk + __ffs(byte) - 1;
@@ -912,49 +918,51 @@ __global__ void k_class_counts(int64_t n_rec, const uint64_t *keys, int class_sh
     scalars[threadIdx.x == 0 ? S_CLASS1 : S_CLASS2] = lo;
 }
 
-// Record packing (strax_interface.py:425-436): 32 records per CTA (4 per warp), assembled in shared
-// memory and written as one contiguous, 16-byte-vectorised span at their final sorted position
-// (244 B = 61 words: 6 header words + 55 data words).
+// Record packing (strax_interface.py:425-436): every WARP assembles 8 records in its own slice of
+// shared memory and writes them as one contiguous, 16-byte-vectorised span at their final sorted
+// position (244 B = 61 words: 6 header words + 55 data words; 8 records = 122 x 16 B).  Warps never
+// wait for each other (no CTA barrier): the dependent chain rec_vals -> descriptor -> samples of one
+// warp hides behind the other warps of the SM.
 // kCompact: the records leave in the compact transport form instead (transport.cuh): a 24-byte
 // header per record at its final sorted position and only the 4-sample blocks that differ from the
 // fill pattern (baseline below `length`, zero behind it), appended to a block stream through one
-// atomic per CTA (the header carries the offset, so the stream order does not matter).
-constexpr int kPackRecs = 32;
+// atomic per warp (the header carries the offset, so the stream order does not matter).
+constexpr int kPackWarpRecs = 8, kPackWarps = 4, kPackRecs = kPackWarpRecs * kPackWarps;
 template <bool kCompact>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kPackWarps * 32)
 k_pack(int64_t n_rec, DeviceConfig c, const uint32_t *__restrict__ rec_vals,
        const RecDesc *__restrict__ desc, const int16_t *__restrict__ dense, uint32_t *__restrict__ out,
        uint32_t *__restrict__ chdr, uint2 *__restrict__ cblk, int64_t *scalars) {
-    __shared__ __align__(16) uint32_t s_rec[kPackRecs * 61];
-    __shared__ uint32_t s_mask[kPackRecs], s_off[kPackRecs];
+    __shared__ __align__(16) uint32_t s_rec_all[kPackWarps][kPackWarpRecs * 61];
+    __shared__ RecDesc s_desc_all[kPackWarps][kPackWarpRecs];
+    __shared__ uint32_t s_mask_all[kPackWarps][kPackWarpRecs], s_off_all[kPackWarps][kPackWarpRecs];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t j0 = (int64_t)blockIdx.x * kPackRecs;
-    const int nhere = (int)min((int64_t)kPackRecs, n_rec - j0);
-    // the 32 descriptors of this CTA are fetched by one warp, one lane each (32 independent
-    // dependent-load chains in flight), then every warp copies its 4 records
-    __shared__ RecDesc s_desc[kPackRecs];
-    if (warp == 0 && lane < nhere) s_desc[lane] = desc[rec_vals[j0 + lane]];
-    if (kCompact && threadIdx.x < kPackRecs) s_mask[threadIdx.x] = 0;
-    __syncthreads();
-    uint32_t v0[4], v1[4];
+    const int64_t j0 = ((int64_t)blockIdx.x * kPackWarps + warp) * kPackWarpRecs;
+    const int nhere = (int)min((int64_t)kPackWarpRecs, n_rec - j0);
+    if (nhere <= 0) return;
+    uint32_t *s_rec = s_rec_all[warp];
+    RecDesc *s_desc = s_desc_all[warp];
+    uint32_t *s_mask = s_mask_all[warp], *s_off = s_off_all[warp];
+    if (lane < nhere) s_desc[lane] = desc[rec_vals[j0 + lane]];
+    if (kCompact && lane < kPackWarpRecs) s_mask[lane] = 0;
+    __syncwarp();
+    uint32_t v0[kPackWarpRecs], v1[kPackWarpRecs];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int r = warp + 8 * k;
-        v0[k] = v1[k] = 0;
+    for (int r = 0; r < kPackWarpRecs; r++) {
+        v0[r] = v1[r] = 0;
         if (r < nhere) {
             const uint32_t *src = reinterpret_cast<const uint32_t *>(dense + s_desc[r].src);
             const int length = s_desc[r].length;
-            if (2 * lane < length) v0[k] = src[lane];
-            if (lane + 32 < 55 && 2 * (lane + 32) < length) v1[k] = src[lane + 32];
+            if (2 * lane < length) v0[r] = src[lane];
+            if (lane + 32 < 55 && 2 * (lane + 32) < length) v1[r] = src[lane + 32];
         }
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int r = warp + 8 * k;
+    for (int r = 0; r < kPackWarpRecs; r++) {
         if (r >= nhere) continue;
         const RecDesc d = s_desc[r];
         const int length = d.length;
-        uint32_t a0 = v0[k], a1 = v1[k];
+        uint32_t a0 = v0[r], a1 = v1[r];
         if (2 * lane + 1 >= length) a0 &= 0xffffu;
         if (2 * (lane + 32) + 1 >= length) a1 &= 0xffffu;
         uint32_t h = 0;
@@ -969,19 +977,19 @@ k_pack(int64_t n_rec, DeviceConfig c, const uint32_t *__restrict__ rec_vals,
         o[6 + lane] = a0;
         if (lane + 32 < 55) o[6 + 32 + lane] = a1;
     }
-    __syncthreads();
+    __syncwarp();
     if (!kCompact) {
-        // contiguous span of nhere * 244 bytes starting at a 16-byte aligned address (32 * 244 = 488 * 16)
+        // contiguous span of nhere * 244 bytes starting at a 16-byte aligned address (8 * 244 = 122 * 16)
         uint4 *dst = reinterpret_cast<uint4 *>(out + j0 * 61);
         const uint4 *srcv = reinterpret_cast<const uint4 *>(s_rec);
         const int nvec = (nhere * 61) / 4, rem = (nhere * 61) % 4;
-        for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = srcv[i];
-        if (threadIdx.x < rem) out[j0 * 61 + nvec * 4 + threadIdx.x] = s_rec[nvec * 4 + threadIdx.x];
+        for (int i = lane; i < nvec; i += 32) dst[i] = srcv[i];
+        if (lane < rem) out[j0 * 61 + nvec * 4 + lane] = s_rec[nvec * 4 + lane];
         return;
     }
     // ---- compact form ----
     const uint32_t fill_h = (uint32_t)(uint16_t)(int16_t)max(c.p.baseline, 0);
-    for (int idx = threadIdx.x; idx < nhere * kBlocksPerRecord; idx += blockDim.x) {
+    for (int idx = lane; idx < nhere * kBlocksPerRecord; idx += 32) {
         const int r = idx / kBlocksPerRecord, b = idx - r * kBlocksPerRecord;
         const int length = s_desc[r].length;
         const uint32_t *w = s_rec + r * 61 + 6 + 2 * b;
@@ -994,23 +1002,24 @@ k_pack(int64_t n_rec, DeviceConfig c, const uint32_t *__restrict__ rec_vals,
         }
         if (diff) atomicOr(&s_mask[r], 1u << b);
     }
-    __syncthreads();
-    if (warp == 0) {
+    __syncwarp();
+    {
         const uint32_t cnt = lane < nhere ? __popc(s_mask[lane]) : 0u;
         uint32_t inc = cnt;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
+        for (int o = 1; o < kPackWarpRecs; o <<= 1) {
             const uint32_t a = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += a;
         }
+        const uint32_t total = __shfl_sync(0xffffffffu, inc, kPackWarpRecs - 1);
         unsigned long long base = 0;
-        if (lane == 31 && inc) base = atomicAdd((unsigned long long *)&scalars[S_NBLOCKS], (unsigned long long)inc);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        s_off[lane] = (uint32_t)base + inc - cnt;
+        if (lane == 0 && total) base = atomicAdd((unsigned long long *)&scalars[S_NBLOCKS], (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < kPackWarpRecs) s_off[lane] = (uint32_t)base + inc - cnt;
     }
-    __syncthreads();
-    if (threadIdx.x < nhere * 6) {
-        const int r = threadIdx.x / 6, k = threadIdx.x - r * 6;
+    __syncwarp();
+    for (int idx = lane; idx < nhere * 6; idx += 32) {
+        const int r = idx / 6, k = idx - r * 6;
         const uint32_t *o = s_rec + r * 61;
         uint32_t h;
         if (k < 2) h = o[k];                                             // time
@@ -1020,7 +1029,7 @@ k_pack(int64_t n_rec, DeviceConfig c, const uint32_t *__restrict__ rec_vals,
         else h = s_mask[r];
         chdr[(j0 + r) * 6 + k] = h;
     }
-    for (int idx = threadIdx.x; idx < nhere * kBlocksPerRecord; idx += blockDim.x) {
+    for (int idx = lane; idx < nhere * kBlocksPerRecord; idx += 32) {
         const int r = idx / kBlocksPerRecord, b = idx - r * kBlocksPerRecord;
         const uint32_t m = s_mask[r];
         if (!((m >> b) & 1u)) continue;
@@ -1275,11 +1284,11 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
         WFS_CUDA_CHECK(cudaEventRecord(evp_[5], stream_));
         if (compact) {
             if ((uint64_t)nrec * kBlocksPerRecord >= (uint64_t(1) << 32)) { res.error = WFS_E_KEYBITS; return; }
-            LAUNCH(k_pack<true>, div_up(nrec, kPackRecs), 256, nrec, c, rec_vals_.as<uint32_t>(),
+            LAUNCH(k_pack<true>, div_up(nrec, kPackRecs), kPackWarps * 32, nrec, c, rec_vals_.as<uint32_t>(),
                    rec_itv_.as<RecDesc>(), dense_.as<int16_t>(), nullptr,
                    reinterpret_cast<uint32_t *>(compact->hdr), compact->blocks, scal);
         } else {
-            LAUNCH(k_pack<false>, div_up(nrec, kPackRecs), 256, nrec, c, rec_vals_.as<uint32_t>(),
+            LAUNCH(k_pack<false>, div_up(nrec, kPackRecs), kPackWarps * 32, nrec, c, rec_vals_.as<uint32_t>(),
                    rec_itv_.as<RecDesc>(), dense_.as<int16_t>(), reinterpret_cast<uint32_t *>(records_out),
                    nullptr, nullptr, scal);
         }

@@ -92,6 +92,8 @@ struct Frontend {
     CompactStage cstage[2];     // compact record transport: batch k ships while batch k+1 runs
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_ready = nullptr;
     bool copy_pending[2] = {false, false};
+    int64_t cdf_rows = -1;      // pattern CDF rows resident in b_cdf (few-row case only) and their hash
+    uint64_t cdf_hash = 0;
     bool has_vd = false, has_dl = false, has_xy = false;   // optional per-instruction arrays of the current batch
     int64_t *h_pin = nullptr;   // pinned scratch for small readbacks
     // staged instructions (device-resident measurement mode)

@@ -392,7 +392,7 @@ __device__ __forceinline__ void time_moments(int64_t rel, int64_t &s, int64_t &h
 
 __global__ void __launch_bounds__(128)
 k_instr_truth(GenCtx g, DeviceConfig c, uint32_t n_instr, uint32_t n_ph, uint32_t ap0) {
-    __shared__ int64_t sm[4];
+    __shared__ int64_t sm[4][A_COUNT];
     const uint32_t i = blockIdx.x;
     if (i >= n_instr) return;
     const int64_t T0 = g.i_time[i];
@@ -446,14 +446,30 @@ k_instr_truth(GenCtx g, DeviceConfig c, uint32_t n_instr, uint32_t n_ph, uint32_
             v[A_PTMAX] = t > v[A_PTMAX] ? t : v[A_PTMAX];
         }
     }
-    int64_t *out = g.i_acc + (int64_t)i * A_COUNT;
+    // warp partials of all accumulators, ONE barrier, then accumulator a is combined by thread a
+    // (integer sums / min / max: the order does not matter, the result is deterministic)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int a = 0; a < A_COUNT; a++) {
-        int64_t r;
-        if (a == A_TMIN || a == A_ETMIN) r = block_reduce(v[a], sm, OpMin());
-        else if (a == A_TMAX || a == A_ETMAX || a == A_PTMAX) r = block_reduce(v[a], sm, OpMax());
-        else r = block_reduce(v[a], sm, OpAdd());
-        if (threadIdx.x == 0) out[a] = r;
+        int64_t r = v[a];
+        const bool is_min = a == A_TMIN || a == A_ETMIN, is_max = a == A_TMAX || a == A_ETMAX || a == A_PTMAX;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int64_t u = __shfl_xor_sync(0xffffffffu, r, o);
+            r = is_min ? (u < r ? u : r) : is_max ? (u > r ? u : r) : r + u;
+        }
+        if (lane == 0) sm[warp][a] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < A_COUNT) {
+        const int a = threadIdx.x;
+        const bool is_min = a == A_TMIN || a == A_ETMIN, is_max = a == A_TMAX || a == A_ETMAX || a == A_PTMAX;
+        int64_t r = sm[0][a];
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) {
+            const int64_t u = sm[w][a];
+            r = is_min ? (u < r ? u : r) : is_max ? (u > r ? u : r) : r + u;
+        }
+        g.i_acc[(int64_t)i * A_COUNT + a] = r;
     }
 }
 

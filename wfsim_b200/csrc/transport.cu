@@ -57,7 +57,9 @@ void ExpandJob::abandon() {
 
 int HostPool::default_threads() {
     if (const char *e = getenv("WFS_EXPAND_THREADS")) return std::max(1, atoi(e));
-    const int hw = (int)std::thread::hardware_concurrency();
+    // one process per GPU shares the host with LOCAL_WORLD_SIZE - 1 others (torchrun sets it)
+    int hw = (int)std::thread::hardware_concurrency();
+    if (const char *w = getenv("LOCAL_WORLD_SIZE")) hw /= std::max(1, atoi(w));
     return std::max(1, std::min(16, hw - 2));
 }
 
