@@ -46,6 +46,16 @@ def workload(n_events, seed):
     return c1_like(n_events, seed=seed)
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (None if there is none)."""
+    path = os.path.join(ROOT, 'profiles', f'r1n_{kernel}_ncu.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)['dram_bytes_per_launch'])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def algorithmic_bytes(c):
     """every compulsory stream counted once."""
     return (PHOTON_BYTES * c['n_photons'] + RECORD_BYTES * c['n_records_total']
@@ -282,7 +292,12 @@ def run_b200(args, rank, world, local_rank):
                      'achieved': digi_bytes / (digi_ms / 1e3) / 1e9 if digi_ms > 0 else None,
                      'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
                      'frac': (digi_bytes / (digi_ms / 1e3) / 1e9 / peak) if digi_ms > 0 else None,
-                     'traffic': None,
+                     # DRAM bytes per launch (read + write) of the committed ncu --set full capture
+                     'traffic': ncu_traffic('k_digitize'),
+                     'traffic_source': 'profiles/r1n_k_digitize_ncu.json (one launch = one device batch of the same '
+                                       'size class as here; dram__bytes_read.sum + dram__bytes_write.sum)',
+                     'launches_per_step': int(c['n_batches']),
+                     'algorithmic_bytes_per_launch': int(digi_bytes / max(int(c['n_batches']), 1)),
                      'algorithmic_bytes_per_step': int(digi_bytes), 'kernel_ms_per_step': digi_ms},
     }
     if world == 1 and not args.no_cpu_baseline:
