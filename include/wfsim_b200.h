@@ -135,6 +135,19 @@ typedef struct wfs_tables {
     const int32_t *gf_t;            /* [gf_rows][gf_cols] emission times */
     const double *gf_x;             /* [gf_rows] distance to the anode wire of each row */
     int32_t gf_rows, gf_cols;
+    /* PMT pattern maps on regular grids (resource.s1_pattern_map over (x, y, z), s1.py:148;
+     * resource.s2_pattern_map over the observed (x, y), s2.py:637-645), evaluated on the device for
+     * every instruction whose wfs_instr_maps.pattern_row is negative: multilinear interpolation with
+     * linear extrapolation outside the grid, the arithmetic of scipy's RegularGridInterpolator
+     * (fill_value=None) that straxen.InterpolatingMap wraps (load_resource.py:399,433), result
+     * rounded to float32 like the host-evaluated rows.  An S2 map with fewer than n_tpc_pmts columns
+     * (top array only) is padded with ones (s2.py:642-644).  NULL -> host rows only. */
+    const double *s1_pat_grid;      /* [n0][n1][n2][s1_pat_npmt] */
+    int32_t s1_pat_n[3], s1_pat_npmt;
+    double s1_pat_lo[3], s1_pat_hi[3];
+    const double *s2_pat_grid;      /* [n0][n1][s2_pat_npmt] */
+    int32_t s2_pat_n[2], s2_pat_npmt, s2_pat_pad;
+    double s2_pat_lo[2], s2_pat_hi[2];
 } wfs_tables;
 
 /* Per-instruction map values evaluated on the host with the reference's own map objects
@@ -145,7 +158,8 @@ typedef struct wfs_instr_maps {
     const double *s2_sc_gain;       /* get_s2_light_yield(positions) incl. /(1+p_dpe), s2.py:182-209 */
     const double *s2_cy_extra;      /* p_surv (and map-driven extraction yield) factor, s2.py:227-252; NULL -> 1 */
     const float *pattern;           /* [n_pattern_rows][n_tpc_pmts] un-normalised per-PMT pattern */
-    const int32_t *pattern_row;     /* [n_instr] row of `pattern` for the instruction; NULL -> row 0 */
+    const int32_t *pattern_row;     /* [n_instr] row of `pattern` for the instruction; NULL -> row 0;
+                                     * negative -> evaluate the device-resident pattern grid (wfs_tables) */
     int64_t n_pattern_rows;
     double s2_sc_gain_default;      /* used when s2_sc_gain is NULL */
     const uint64_t *rng_id;         /* [n_instr] Philox identity of each instruction; NULL -> its index.

@@ -223,13 +223,13 @@ static void make_plan(Handle *H, const uint8_t *rows, int64_t n, const wfs_instr
     if (maps && maps->pattern && maps->n_pattern_rows > 0) {
         P.pattern_rows = maps->n_pattern_rows;
         P.pattern.assign(maps->pattern, maps->pattern + maps->n_pattern_rows * n_ch);
-        if (maps->pattern_row) std::copy(maps->pattern_row, maps->pattern_row + n, P.patrow.begin());
-        for (int64_t i = 0; i < n; i++)
-            if (P.patrow[i] < 0 || P.patrow[i] >= P.pattern_rows) throw std::runtime_error("pattern_row out of range");
     } else {
         P.pattern_rows = 1;
         P.pattern.assign((size_t)n_ch, 1.0f);
     }
+    if (maps && maps->pattern_row) std::copy(maps->pattern_row, maps->pattern_row + n, P.patrow.begin());
+    for (int64_t i = 0; i < n; i++)     // negative: evaluated on the device from the pattern grid
+        if (P.patrow[i] >= P.pattern_rows) throw std::runtime_error("pattern_row out of range");
     // batches: contiguous cluster ranges under a photon / sample budget
     const int64_t ph_budget = env_i64("WFS_BATCH_PHOTONS", 48000000);
     const int64_t sample_budget = env_i64("WFS_BATCH_SAMPLES", 1500000000);
@@ -510,7 +510,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     std::vector<double> h_vd(F.has_vd ? nprim : 0), h_dl(F.has_dl ? nprim : 0), h_xo(F.has_xy ? nprim : 0),
         h_yo(F.has_xy ? nprim : 0);
     std::unordered_map<int32_t, int32_t> rowmap;
-    std::vector<int32_t> rows_used;
+    std::vector<int32_t> rows_used, dev_rows;
     for (int64_t j = 0; j < nprim; j++) {
         const int64_t gi = P.order[j0 + j];
         const HostInstr &h = P.instr[gi];
@@ -522,12 +522,23 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         if (F.has_vd) h_vd[j] = P.vd[gi];
         if (F.has_dl) h_dl[j] = P.dl[gi];
         if (F.has_xy) { h_xo[j] = P.xo[gi]; h_yo[j] = P.yo[gi]; }
+        if (P.patrow[gi] < 0) {          // pattern evaluated on the device from the uploaded grid
+            dev_rows.push_back((int32_t)j);
+            continue;
+        }
         auto it = rowmap.find(P.patrow[gi]);
         if (it == rowmap.end()) {
             it = rowmap.emplace(P.patrow[gi], (int32_t)rows_used.size()).first;
             rows_used.push_back(P.patrow[gi]);
         }
         h_pat[j] = it->second;
+    }
+    const int64_t n_host_rows = (int64_t)rows_used.size();
+    for (size_t k = 0; k < dev_rows.size(); k++) {
+        const int32_t j = dev_rows[k];
+        const PatGrid &g = h_type[j] == 1 ? F.s1_pat : F.s2_pat;
+        if (!g.v) throw std::runtime_error("pattern_row < 0 but no pattern grid was given for this signal type (wfs_tables)");
+        h_pat[j] = (int32_t)(n_host_rows + (int64_t)k);
     }
     grow_instr(F, std::max<int64_t>(nprim, 1), 0, s);
     auto up = [&](DevBuf &b, const void *src, size_t bytes) {
@@ -543,9 +554,9 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     if (F.has_dl) up(F.b_idl, h_dl.data(), 8 * nprim);
     if (F.has_xy) { up(F.b_ixo, h_xo.data(), 8 * nprim); up(F.b_iyo, h_yo.data(), 8 * nprim); }
     // pattern rows of this batch -> CDF rows
-    const int64_t nrows = (int64_t)rows_used.size();
-    std::vector<float> h_rows((size_t)nrows * n_ch);
-    for (int64_t r = 0; r < nrows; r++)
+    const int64_t nrows = n_host_rows + (int64_t)dev_rows.size();
+    std::vector<float> h_rows((size_t)n_host_rows * n_ch);
+    for (int64_t r = 0; r < n_host_rows; r++)
         memcpy(&h_rows[(size_t)r * n_ch], &P.pattern[(size_t)rows_used[r] * n_ch], sizeof(float) * n_ch);
     // few rows (dummy / constant maps): one thread per row is a long serial chain on the critical
     // path -- keep the CDF rows of the previous batch if the pattern rows are bit-identical
@@ -554,15 +565,20 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         const uint8_t *bytes = reinterpret_cast<const uint8_t *>(h_rows.data());
         for (size_t k = 0; k < sizeof(float) * h_rows.size(); k++) rows_hash = (rows_hash ^ bytes[k]) * 1099511628211ull;
     }
-    const bool cdf_cached = nrows > 0 && nrows <= 16 && F.cdf_rows == nrows && F.cdf_hash == rows_hash;
+    const bool cdf_cached = dev_rows.empty() && nrows > 0 && nrows <= 16 && F.cdf_rows == nrows && F.cdf_hash == rows_hash;
     if (!cdf_cached) {
-        F.b_pattern.reserve(sizeof(float) * h_rows.size());
-        F.b_cdf.reserve(sizeof(double) * h_rows.size());
+        F.b_pattern.reserve(sizeof(float) * (size_t)nrows * n_ch);
+        F.b_cdf.reserve(sizeof(double) * (size_t)nrows * n_ch);
         F.b_cdfok.reserve(sizeof(int32_t) * nrows);
-        up(F.b_pattern, h_rows.data(), sizeof(float) * h_rows.size());
+        if (n_host_rows) up(F.b_pattern, h_rows.data(), sizeof(float) * h_rows.size());
+        if (!dev_rows.empty())
+            FLAUNCH(k_pattern_eval, div_up(nprim * 32, 128), 128, (uint32_t)nprim, (int32_t)n_host_rows,
+                    F.b_itype.as<int32_t>(), F.b_ix.as<float>(), F.b_iy.as<float>(), F.b_iz.as<float>(),
+                    F.has_xy ? F.b_ixo.as<double>() : nullptr, F.has_xy ? F.b_iyo.as<double>() : nullptr,
+                    F.b_ipat.as<int32_t>(), F.s1_pat, F.s2_pat, n_ch, F.b_pattern.as<float>());
         FLAUNCH(k_pattern_cdf, div_up(nrows, 64), 64, nrows, n_ch, F.b_pattern.as<float>(), H->cfg.gains,
                 F.b_cdf.as<double>(), F.b_cdfok.as<int32_t>());
-        F.cdf_rows = nrows <= 16 ? nrows : -1;
+        F.cdf_rows = (dev_rows.empty() && nrows <= 16) ? nrows : -1;
         F.cdf_hash = rows_hash;
     }
     // ---- pass A: primaries ----
@@ -1063,6 +1079,7 @@ static void clone_tables(const Frontend &a, Frontend &b) {
     b.s1_op_z0 = a.s1_op_z0; b.s1_op_z1 = a.s1_op_z1; b.s1_op_u0 = a.s1_op_u0; b.s1_op_u1 = a.s1_op_u1;
     b.s2_op_u0 = a.s2_op_u0; b.s2_op_u1 = a.s2_op_u1;
     b.gf_t = a.gf_t; b.gf_x = a.gf_x; b.gf_rows = a.gf_rows; b.gf_cols = a.gf_cols;
+    b.s1_pat = a.s1_pat; b.s2_pat = a.s2_pat;
 }
 
 static void init_copy_events(Frontend &F) {
@@ -1282,6 +1299,22 @@ void Handle::frontend_init(const wfs_tables &t) {
         F->s2_op_top = upload_table(t.s2_op_top, (size_t)t.s2_op_nu, owned);
         F->s2_op_bottom = upload_table(t.s2_op_bottom, (size_t)t.s2_op_nu, owned);
         F->s2_op_nu = t.s2_op_nu; F->s2_op_u0 = t.s2_op_u0; F->s2_op_u1 = t.s2_op_u1;
+    }
+    if (t.s1_pat_grid) {
+        if (t.s1_pat_npmt != p.n_tpc_pmts || t.s1_pat_n[0] < 2 || t.s1_pat_n[1] < 2 || t.s1_pat_n[2] < 2)
+            throw std::runtime_error("s1 pattern grid: needs >= 2 points per axis and n_tpc_pmts columns");
+        F->s1_pat.nd = 3; F->s1_pat.npmt = t.s1_pat_npmt;
+        size_t cells = 1;
+        for (int d = 0; d < 3; d++) { F->s1_pat.n[d] = t.s1_pat_n[d]; F->s1_pat.lo[d] = t.s1_pat_lo[d]; F->s1_pat.hi[d] = t.s1_pat_hi[d]; cells *= (size_t)t.s1_pat_n[d]; }
+        F->s1_pat.v = upload_table(t.s1_pat_grid, cells * (size_t)t.s1_pat_npmt, owned);
+    }
+    if (t.s2_pat_grid) {
+        if (t.s2_pat_npmt < 1 || t.s2_pat_npmt > p.n_tpc_pmts || t.s2_pat_n[0] < 2 || t.s2_pat_n[1] < 2)
+            throw std::runtime_error("s2 pattern grid: needs >= 2 points per axis and at most n_tpc_pmts columns");
+        F->s2_pat.nd = 2; F->s2_pat.npmt = t.s2_pat_npmt;
+        size_t cells = 1;
+        for (int d = 0; d < 2; d++) { F->s2_pat.n[d] = t.s2_pat_n[d]; F->s2_pat.lo[d] = t.s2_pat_lo[d]; F->s2_pat.hi[d] = t.s2_pat_hi[d]; cells *= (size_t)t.s2_pat_n[d]; }
+        F->s2_pat.v = upload_table(t.s2_pat_grid, cells * (size_t)t.s2_pat_npmt, owned);
     }
     if (p.s2_luminescence_model == 1) {
         if (!t.gf_t || !t.gf_x || t.gf_rows < 1 || t.gf_cols < 1)

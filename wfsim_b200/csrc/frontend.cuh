@@ -55,8 +55,17 @@ struct DeviceInstr {   // SoA views, batch-local
     int64_t *acc;        // [A_COUNT][cap]
 };
 
+// Pattern map on a regular grid, resident on the device (wfs_tables.s1_pat_* / s2_pat_*)
+struct PatGrid {
+    const double *v = nullptr;     // [n0][n1]([n2])[npmt]
+    int32_t nd = 0, npmt = 0;
+    int32_t n[3] = {1, 1, 1};
+    double lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+};
+
 struct Frontend {
     Handle *H;
+    PatGrid s1_pat, s2_pat;
     // device tables
     double *spe_ppf = nullptr;
     int32_t *spe_row = nullptr;

@@ -134,6 +134,58 @@ __global__ void k_pattern_cdf(int64_t rows, int n_ch, const float *pattern, cons
     ok[r] = 1;
 }
 
+// Pattern rows of the instructions whose map lives on the device as a regular grid (rows >=
+// first_dev_row): multilinear interpolation, linear extrapolation outside the grid -- the arithmetic of
+// scipy's RegularGridInterpolator(fill_value=None) behind straxen.InterpolatingMap, in the operation
+// order of wfsim_b200.resource.GridMap so that host- and device-evaluated rows are bit-identical.
+// S1 (s1.py:148): (x, y, z); S2-like (s2.py:637-645): observed (x, y), top-only maps padded with ones.
+// One warp per instruction, lanes over the PMTs (coalesced reads of the grid rows).
+__global__ void __launch_bounds__(128)
+k_pattern_eval(uint32_t n_instr, int32_t first_dev_row, const int32_t *__restrict__ i_type,
+               const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
+               const double *__restrict__ xo, const double *__restrict__ yo,
+               const int32_t *__restrict__ i_pat, PatGrid g1, PatGrid g2, int n_ch, float *__restrict__ pattern) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n_instr) return;
+    const int32_t row = i_pat[i];
+    if (row < first_dev_row) return;
+    const bool is_s1 = i_type[i] == 1;
+    const PatGrid &g = is_s1 ? g1 : g2;
+    double p[3] = {0.0, 0.0, 0.0};
+    if (is_s1) { p[0] = (double)x[i]; p[1] = (double)y[i]; p[2] = (double)z[i]; }
+    else { p[0] = xo ? xo[i] : (double)x[i]; p[1] = yo ? yo[i] : (double)y[i]; }
+    int64_t idx[3] = {0, 0, 0};
+    double w[3] = {0.0, 0.0, 0.0};
+    for (int d = 0; d < g.nd; d++) {
+        const double f = (p[d] - g.lo[d]) / (g.hi[d] - g.lo[d]) * (double)(g.n[d] - 1);
+        double fl = floor(f);
+        int64_t i0 = isnan(fl) ? 0 : (fl < -1e18 ? (int64_t)-1000000000000000000ll : (fl > 1e18 ? (int64_t)1000000000000000000ll : (int64_t)fl));
+        i0 = i0 < 0 ? 0 : (i0 > g.n[d] - 2 ? g.n[d] - 2 : i0);
+        idx[d] = i0;
+        w[d] = f - (double)i0;
+    }
+    const int nd = g.nd, ncorner = 1 << nd;
+    float *out = pattern + (int64_t)row * n_ch;
+    for (int ch = lane; ch < n_ch; ch += 32) {
+        double acc = 1.0;                 // columns the map does not have (bottom array of a top-only S2 map)
+        if (ch < g.npmt) {
+            acc = 0.0;
+            for (int corner = 0; corner < ncorner; corner++) {
+                double wt = 1.0;
+                int64_t flat = 0;
+                for (int d = 0; d < nd; d++) {
+                    const int bit = (corner >> (nd - 1 - d)) & 1;
+                    flat = flat * g.n[d] + idx[d] + bit;
+                    wt = wt * (bit ? w[d] : 1.0 - w[d]);
+                }
+                acc = acc + wt * g.v[flat * g.npmt + ch];
+            }
+        }
+        out[ch] = (float)acc;
+    }
+}
+
 // Per instruction: yields.  S1: s1.py:117-135.  S2-like: s2.py:157-179, 212-256.
 __global__ void k_instr(GenCtx g, wfs_params p, uint32_t i0, uint32_t i1) {
     uint32_t i = i0 + blockIdx.x * blockDim.x + threadIdx.x;

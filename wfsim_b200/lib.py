@@ -66,7 +66,10 @@ class Tables(C.Structure):
         ('s1_op_z0', f64), ('s1_op_z1', f64), ('s1_op_u0', f64), ('s1_op_u1', f64),
         ('s2_op_top', vp), ('s2_op_bottom', vp), ('s2_op_nu', i32),
         ('s2_op_u0', f64), ('s2_op_u1', f64),
-        ('gf_t', vp), ('gf_x', vp), ('gf_rows', i32), ('gf_cols', i32)]
+        ('gf_t', vp), ('gf_x', vp), ('gf_rows', i32), ('gf_cols', i32),
+        ('s1_pat_grid', vp), ('s1_pat_n', i32 * 3), ('s1_pat_npmt', i32), ('s1_pat_lo', f64 * 3), ('s1_pat_hi', f64 * 3),
+        ('s2_pat_grid', vp), ('s2_pat_n', i32 * 2), ('s2_pat_npmt', i32), ('s2_pat_pad', i32),
+        ('s2_pat_lo', f64 * 2), ('s2_pat_hi', f64 * 2)]
 
 
 class InstrMaps(C.Structure):

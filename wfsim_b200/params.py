@@ -208,6 +208,22 @@ def build_tables(cfg, resource=None):
         tt = t.set('gf_t', tt, np.int32)
         t.set('gf_x', lum['x'], np.float64)
         t.struct.gf_rows, t.struct.gf_cols = tt.shape
+    # pattern maps on regular grids: evaluated on the device (resource.GridMap with map 'map')
+    for key, nd in (('s1', 3), ('s2', 2)):
+        m = get(key + '_pattern_map')
+        if m is None or not hasattr(m, 'grid') or 'map' not in getattr(m, 'maps', {}):
+            continue
+        axes, vals = m.grid('map')
+        if len(axes) != nd or vals.ndim != nd + 1 or vals.shape[-1] > n_ch or min(a[2] for a in axes) < 2:
+            continue            # unusual layout: the host evaluates this map
+        if key == 's1' and vals.shape[-1] != n_ch:
+            continue
+        t.set(key + '_pat_grid', vals, np.float64)
+        setattr(t.struct, key + '_pat_npmt', vals.shape[-1])
+        for d, (lo, hi, n) in enumerate(axes):
+            getattr(t.struct, key + '_pat_n')[d] = n
+            getattr(t.struct, key + '_pat_lo')[d] = lo
+            getattr(t.struct, key + '_pat_hi')[d] = hi
     # photo-ionisation electrons (afterpulse.py:33-80)
     ele = get('uniform_to_ele_ap')
     if cfg.get('enable_electron_afterpulses', True) and ele is not None:

@@ -145,7 +145,16 @@ def field_distortion_comsol(x, y, z, resource):
     return z, np.array([r_obs * np.cos(theta), r_obs * np.sin(theta)]).T
 
 
-def evaluate_instruction_maps(config, resource, instructions, seed=0):
+def _on_device(m, nd, n_ch, need_full):
+    """Is this pattern map a regular grid the library evaluates on the device (params.build_tables)?"""
+    if not hasattr(m, 'grid') or 'map' not in getattr(m, 'maps', {}):
+        return False
+    axes, vals = m.grid('map')
+    ok = len(axes) == nd and vals.ndim == nd + 1 and vals.shape[-1] <= n_ch and min(a[2] for a in axes) >= 2
+    return ok and (vals.shape[-1] == n_ch or not need_full)
+
+
+def evaluate_instruction_maps(config, resource, instructions, seed=0, device_patterns=True):
     """Per-instruction map values handed to the device (struct wfs_instr_maps):
     S1 light yield (s1.py:125), observed S2 positions after the field-distortion model
     (s2.py:80-87), S2 secondary-scintillation gain (s2.py:182-209), the survival / extraction
@@ -222,6 +231,10 @@ def evaluate_instruction_maps(config, resource, instructions, seed=0):
         if not mask.any():
             return
         smear = is_s2_map and aft_sigma != 0
+        if device_patterns and not smear and _on_device(m, 2 if is_s2_map else 3, n_ch, not is_s2_map) \
+                and not (is_s2_map and efd.get('diffusion_transverse_map')):
+            row_of[mask] = -1        # evaluated on the device from the uploaded grid
+            return
         if isinstance(m, DummyMap) and not smear:
             pat = np.asarray(m(np.zeros((1, 2))), dtype=np.float64).reshape(1, -1)
             idx = np.zeros(mask.sum(), np.int64)
