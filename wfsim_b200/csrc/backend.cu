@@ -26,7 +26,7 @@ constexpr int kBlk = 8;                 // samples per digitize thread
 
 enum Scalar {
     S_NVALID = 0, S_NPULSES, S_NWIN, S_NTILES, S_NITVSLOTS, S_NREC, S_MINSAMPLE, S_MAXSAMPLE,
-    S_ERR, S_NITV, S_NSAMPLES, S_CLASS0, S_CLASS1, S_CLASS2, S_NBLOCKS, S_COUNT
+    S_ERR, S_NITV, S_NSAMPLES, S_CLASS0, S_CLASS1, S_CLASS2, S_NBLOCKS, S_RECSEG_MAX, S_GROUPS_OVERLAP, S_COUNT
 };
 
 struct WinMeta {
@@ -874,6 +874,48 @@ struct RecDesc {      // everything k_pack needs for one record, 32 bytes
     int32_t pad;
 };
 
+// Record segments.  Interval slots follow the window order -- all base windows by (group, channel),
+// then all high-energy twins by (group, channel) -- so the records of one (data type, group) are a
+// contiguous range of the record list.  When the digitisation windows of consecutive groups do not
+// overlap in time (what the scheduler produces), sorting every segment by (time, channel) IS the
+// global (class, time, channel) order and can be done per segment in shared memory.
+__global__ void k_group_first_window(int64_t n_win, const uint32_t *__restrict__ win_key, uint32_t *group_win) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_win) return;
+    const uint32_t g = win_key[w] >> kChannelBits;
+    if (w == 0 || (win_key[w - 1] >> kChannelBits) != g) group_win[g] = (uint32_t)w;
+}
+
+__global__ void k_rec_segments(int64_t n_groups, int64_t n_win, DeviceConfig c, const uint32_t *__restrict__ group_win,
+                               const uint64_t *__restrict__ win_off, const uint32_t *__restrict__ itv_rec0,
+                               const int64_t *__restrict__ group_lr, uint32_t *rec_seg, int64_t *scalars) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > 2 * n_groups) return;
+    auto start_of = [&](int64_t seg) -> uint32_t {
+        int64_t w = 2 * n_win;                       // behind the last window: the record total
+        if (seg < 2 * n_groups) {
+            const int64_t cls = seg / n_groups;
+            w = (cls + 1) * n_win;
+            for (int64_t g = seg - cls * n_groups; g < n_groups; g++)
+                if (group_win[g] != 0xffffffffu) { w = cls * n_win + group_win[g]; break; }
+        }
+        return itv_rec0[win_off[w] >> 32];
+    };
+    const uint32_t a = start_of(s);
+    rec_seg[s] = a;
+    if (s == 2 * n_groups) return;
+    const uint32_t e = start_of(s + 1);
+    if (e > a) atomicMax((long long *)&scalars[S_RECSEG_MAX], (long long)(e - a));
+    if (s < n_groups && group_lr[2 * s] != LLONG_MAX) {     // my window against the next non-empty group's
+        for (int64_t g = s + 1; g < n_groups; g++) {
+            if (group_lr[2 * g] == LLONG_MAX) continue;
+            if (group_lr[2 * s + 1] + c.p.trigger_window >= group_lr[2 * g] - c.p.trigger_window)
+                scalars[S_GROUPS_OVERLAP] = 1;
+            break;
+        }
+    }
+}
+
 // strax_interface.py:425-436 header fields + the (class, time, channel) sort key of
 // strax.sort_by_time, one thread per interval slot.
 __global__ void k_rec_keys(int64_t n_slots, DeviceConfig c, const Interval *itv,
@@ -1085,7 +1127,7 @@ void Backend::release() {
                      &win_first_pulse_, &win_meta_, &win_scan_, &group_tmin_, &group_lr_, &scalars_,
                      &dense_, &itv_, &itv_nrec_, &itv_rec0_, &rec_keys_, &rec_vals_,
                      &rec_itv_, &group_nitv_, &group_ix_, &pstart_, &flag8_, &cta_first_, &phq_,
-                     &group_nvalid_, &group_out_};
+                     &group_nvalid_, &group_out_, &group_win_, &rec_seg_};
     for (DevBuf *b : all) b->release();
     prim_.release();
 }
@@ -1187,7 +1229,8 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
     res.n_pulses = np;
     const int64_t nwt = 2 * nw;
     res.n_windows = 0;
-    int64_t n_tiles = 0, n_slots = 0, min_sample = 0, max_sample = 0;
+    int64_t n_tiles = 0, n_slots = 0, min_sample = 0, max_sample = 0, rec_seg_max = 0;
+    bool rec_groups_disjoint = false;
     const bool he_rows = c.p.detector_nt != 0;
     static_assert(sizeof(WinMeta) == 64, "WinMeta layout");
     DevBuf &group_ix_buf = group_ix_;
@@ -1258,11 +1301,23 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
                group_nitv_.as<uint32_t>(), scal);
         prim_.exclusive_scan_u32(itv_nrec_.as<uint32_t>(), itv_rec0_.as<uint32_t>(), n_slots, true);
         WFS_CUDA_CHECK(cudaEventRecord(evp_[4], stream_));
+        // (data type, group) segments of the record list, their largest size, and whether the groups'
+        // windows are disjoint in time
+        group_win_.reserve(sizeof(uint32_t) * ng);
+        rec_seg_.reserve(sizeof(uint32_t) * (2 * ng + 1));
+        WFS_CUDA_CHECK(cudaMemsetAsync(group_win_.p, 0xff, sizeof(uint32_t) * ng, stream_));
+        LAUNCH(k_group_first_window, div_up(nw, T), T, nw, prim_.sort_vals_alt.as<uint32_t>(), group_win_.as<uint32_t>());
+        LAUNCH(k_rec_segments, div_up(2 * ng + 1, T), T, ng, nw, c, group_win_.as<uint32_t>(),
+               win_scan_.as<uint64_t>(), itv_rec0_.as<uint32_t>(), group_lr_.as<int64_t>(),
+               rec_seg_.as<uint32_t>(), scal);
         uint32_t nrec32;
         WFS_CUDA_CHECK(cudaMemcpyAsync(&nrec32, itv_rec0_.as<uint32_t>() + n_slots, sizeof(uint32_t),
                                        cudaMemcpyDeviceToHost, stream_));
+        WFS_CUDA_CHECK(cudaMemcpyAsync(h_scalars_, scal, sizeof(int64_t) * S_COUNT, cudaMemcpyDeviceToHost, stream_));
         WFS_CUDA_CHECK(cudaStreamSynchronize(stream_));
         res.n_records = nrec32;
+        rec_seg_max = h_scalars_[S_RECSEG_MAX];
+        rec_groups_disjoint = h_scalars_[S_GROUPS_OVERLAP] == 0;
         WFS_CUDA_CHECK(cudaEventElapsedTime(&res.ms_digitize, ev0_, ev1_));
     }
     if (group_info_out)
@@ -1279,7 +1334,21 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
         LAUNCH(k_rec_keys, div_up(n_slots, T), T, n_slots, c, itv_.as<Interval>(),
                itv_nrec_.as<uint32_t>(), itv_rec0_.as<uint32_t>(), min_sample, time_bits,
                rec_keys_.as<uint64_t>(), rec_vals_.as<uint32_t>(), rec_itv_.as<RecDesc>());
-        prim_.sort_pairs(rec_keys_.as<uint64_t>(), rec_vals_.as<uint32_t>(), nrec, key_bits);
+        const bool seg_on = !(getenv("WFS_SEGMENT_SORT") && atoi(getenv("WFS_SEGMENT_SORT")) == 0);
+        if (seg_on && rec_groups_disjoint && rec_seg_max <= kSegSortMax && kChannelBits + time_bits + 1 + 13 <= 64) {
+            // every (data type, group) segment ordered by (time, channel) in shared memory
+            prim_.sort_keys_alt.reserve((size_t)nrec * sizeof(uint64_t));
+            prim_.sort_vals_alt.reserve((size_t)nrec * sizeof(uint32_t));
+            prim_.segment_sort_pairs(rec_keys_.as<uint64_t>(), rec_vals_.as<uint32_t>(),
+                                     prim_.sort_keys_alt.as<uint64_t>(), prim_.sort_vals_alt.as<uint32_t>(),
+                                     rec_seg_.as<uint32_t>(), nullptr, 2 * ng, rec_seg_max, kChannelBits + time_bits,
+                                     ~0ull);
+            std::swap(rec_keys_, prim_.sort_keys_alt);
+            std::swap(rec_vals_, prim_.sort_vals_alt);
+            res.segment_sorted_records = 1;
+        } else {
+            prim_.sort_pairs(rec_keys_.as<uint64_t>(), rec_vals_.as<uint32_t>(), nrec, key_bits);
+        }
         LAUNCH(k_class_counts, 1, 32, nrec, rec_keys_.as<uint64_t>(), kChannelBits + time_bits, scal);
         WFS_CUDA_CHECK(cudaEventRecord(evp_[5], stream_));
         if (compact) {

@@ -91,7 +91,7 @@ private:
     DevBuf keys_, vals_, st_, sg_, flags64_, pulse_first_, pulse_left_, pulse_win_, win_first_pulse_,
         win_meta_, win_scan_, group_tmin_, group_lr_, scalars_, dense_, itv_, itv_nrec_,
         itv_rec0_, rec_keys_, rec_vals_, rec_itv_, group_nitv_, group_ix_, pstart_, flag8_, cta_first_, phq_,
-        group_nvalid_, group_out_;
+        group_nvalid_, group_out_, group_win_, rec_seg_;
 };
 
 }  // namespace wfs
