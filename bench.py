@@ -230,12 +230,16 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- kernel-alone pass for the roofline: one lane, so that the CUDA events around k_digitize
     # bracket that kernel only (with two lanes the other lane's kernels share the GPU with it) ----
+    lanes_before = os.environ.get('WFS_LANES')
     os.environ['WFS_LANES'] = '1'
     try:
         sim.run_staged(seed=1)
         ms_digi_alone = [sim.run_staged(seed=1)['ms_digitize'] for _ in range(args.steps)]
     finally:
-        del os.environ['WFS_LANES']
+        if lanes_before is None:
+            del os.environ['WFS_LANES']
+        else:
+            os.environ['WFS_LANES'] = lanes_before
     barrier()
 
     # ---- end-to-end leg: public API, host buffers, H2D + D2H inside the timed region ----------

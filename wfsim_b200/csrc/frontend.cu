@@ -1159,7 +1159,7 @@ static int run_plan(Handle *H, Plan &P, uint64_t seed, wfs_outputs *out, wfs_cou
     so.resident = resident;
     so.dump = dump;
     const int64_t nb = (int64_t)P.batches.size();
-    const int n_lanes = dump ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(env_i64("WFS_LANES", 2), nb));
+    const int n_lanes = dump ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(env_i64("WFS_LANES", 3), 8), nb));
     ensure_lanes(H, std::max(n_lanes, 1));
     cudaStream_t s = H->stream;
     WFS_CUDA_CHECK(cudaEventRecord(H->ev_a, s));
