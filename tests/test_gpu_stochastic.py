@@ -237,3 +237,20 @@ def test_per_pmt_truth(sim):
         h = np.bincount(ph['channel'][ph['instruction'] == i], minlength=n_pmt)
         if t['type'][row] == inst['type'][i] and t['amp'][row] == inst['amp'][i]:
             np.testing.assert_array_equal(t['n_photon_per_pmt'][row], h)
+
+
+def test_caller_owned_record_buffer(sim):
+    """records_out: the records land in the caller's (pageable, here deliberately misaligned) array."""
+    from wfsim_b200.dtypes import raw_record_dtype
+    inst = c0_like(6, seed=2)
+    a = sim.simulate(inst, seed=3)
+    n = len(a['raw_records']) + len(a['raw_records_he'])
+    raw = np.zeros(244 * (n + 10) + 8, np.uint8)
+    buf = raw[4:4 + 244 * (n + 10)].view(raw_record_dtype())
+    b = sim.simulate(inst, seed=3, records_out=buf)
+    assert np.shares_memory(b['raw_records'], raw)
+    for k in ('raw_records', 'raw_records_he'):
+        assert np.array(a[k]).tobytes() == np.array(b[k]).tobytes()
+    small = np.zeros(10, raw_record_dtype())          # too small: the call falls back to its own buffer
+    c = sim.simulate(inst, seed=3, records_out=small)
+    assert np.array(c['raw_records']).tobytes() == np.array(a['raw_records']).tobytes()

@@ -171,14 +171,16 @@ class Simulator:
         return c
 
     def simulate(self, instructions, seed=0, maps=None, cap_records=None, pinned=False, rng_id=None,
-                 per_pmt_truth=None):
+                 per_pmt_truth=None, records_out=None):
         """Full path for one set of instructions (see wfs_simulate in the header).
 
         Returns dict(raw_records, raw_records_he, raw_records_aqmon, truth, groups); records of
         each data type are sorted by (time, channel); truth rows are in Pulse-call execution
         order with `time` still the instruction time (the chunker sets it to t_first_photon,
         strax_interface.py:481-482).  With per_pmt_truth (default: config['per_pmt_truth']) the
-        truth rows carry the `*_per_pmt` fields of extra_truth_dtype_per_pmt instead of `*_bottom`."""
+        truth rows carry the `*_per_pmt` fields of extra_truth_dtype_per_pmt instead of `*_bottom`.
+        `records_out`: a caller-owned raw_record array the records are written into (any host
+        memory; the returned record arrays are views of it) -- grown if it turns out too small."""
         if per_pmt_truth is None:
             per_pmt_truth = bool(self.config.get('per_pmt_truth', False))
         n_pmt = int(self.params.n_tpc_pmts)
@@ -188,13 +190,19 @@ class Simulator:
         n = len(instructions)
         m, keep = self._maps_struct(instructions, maps, rng_id, seed=seed)
         counts = wlib.Counts()
-        cap_rec = int(cap_records) if cap_records is not None else max(4096, 1500 * n)
+        cap_rec = int(cap_records) if cap_records is not None else \
+            (len(records_out) if records_out is not None else max(4096, 1500 * n))
         cap_truth, cap_groups, cap_batches = 2 * n + 64, n + 64, 4096
         tdt = truth_dtype()
         gdt = np.dtype([('left', np.int64), ('right', np.int64), ('n_intervals', np.int64)])
         while True:
             holder = self._pinned_records(cap_rec) if pinned else None
-            rec = holder.array if pinned else np.empty(cap_rec, raw_record_dtype())
+            if records_out is not None and len(records_out) >= cap_rec:
+                if records_out.dtype != raw_record_dtype() or not records_out.flags['C_CONTIGUOUS']:
+                    raise ValueError('records_out must be a C-contiguous raw_record_dtype array')
+                rec = records_out
+            else:
+                rec = holder.array if pinned else np.empty(cap_rec, raw_record_dtype())
             cap_rec = len(rec)
             truth = np.zeros(cap_truth, tdt)
             groups = np.zeros(cap_groups, gdt)
