@@ -221,7 +221,7 @@ int wfs_simulate_photons(void *handle, int64_t n_photons, const int64_t *t_ns, c
     }
     uint8_t *d_rec = records;
     // host destination: the records cross PCIe in the compact form and are expanded by host threads
-    const bool compact = !on_device && H->use_compact();
+    const bool compact = !on_device && records && H->use_compact(records);
     if (on_device) {
         b.t = t_ns; b.channel = channel; b.gain = gain; b.pulse_call = pulse_call;
     } else {

@@ -26,7 +26,7 @@ constexpr int kBlk = 8;                 // samples per digitize thread
 
 enum Scalar {
     S_NVALID = 0, S_NPULSES, S_NWIN, S_NTILES, S_NITVSLOTS, S_NREC, S_MINSAMPLE, S_MAXSAMPLE,
-    S_ERR, S_NITV, S_NSAMPLES, S_CLASS0, S_CLASS1, S_CLASS2, S_NBLOCKS, S_RECSEG_MAX, S_GROUPS_OVERLAP, S_COUNT
+    S_ERR, S_NITV, S_NSAMPLES, S_CLASS0, S_CLASS1, S_CLASS2, S_NBLOCKS, S_RECSEG_MAX, S_GROUPS_OVERLAP, S_DENSE_TILES, S_COUNT
 };
 
 struct WinMeta {
@@ -757,6 +757,7 @@ k_digitize(int64_t n_blocks, int tile_blk, int n_tiles, int64_t n_wtot, DeviceCo
             }
         } else {
             // ---- dense path ----
+            if (lane == 0) atomicAdd((unsigned long long *)&scalars[S_DENSE_TILES], 1ull);
             for (int slot = 0; slot < nwin; slot++) {
                 const int lo = max(W.win[slot].off / kBlk, 0);
                 const int hi = min((W.win[slot].off + W.win[slot].len + kBlk - 1) / kBlk, nblk);
@@ -1377,6 +1378,7 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
     res.n_intervals = h_scalars_[S_NITV];
     res.n_samples = h_scalars_[S_NSAMPLES];
     res.n_blocks = h_scalars_[S_NBLOCKS];
+    res.n_dense_tiles = h_scalars_[S_DENSE_TILES];
     res.n_windows = nwt;
     if (nrec > 0 && nrec <= cap_records) {
         const int64_t i1 = h_scalars_[S_CLASS1], i2 = h_scalars_[S_CLASS2];

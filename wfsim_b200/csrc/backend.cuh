@@ -58,6 +58,7 @@ struct BackendResult {
     int64_t n_valid_photons = 0, n_pulses = 0, n_windows = 0, n_tiles = 0;
     int64_t n_intervals = 0, n_records = 0, n_samples = 0;
     int64_t n_blocks = 0;            // compact transport: 8-byte blocks in the stream
+    int64_t n_dense_tiles = 0;       // digitize tiles that took the gather (dense) path
     int64_t n_rec_class[3] = {0, 0, 0};
     float ms_digitize = 0.f;
     float ms_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 1 sort, 2 windows, 3 digitize, 4 zle, 5 rec sort, 6 pack

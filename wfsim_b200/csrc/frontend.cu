@@ -311,6 +311,7 @@ struct SimOut {
     bool resident = false;
     int64_t n_rec = 0, n_truth = 0, n_groups = 0, n_batches = 0;
     bool overflow = false;
+    bool compact = false;        // records travel in the compact transport form (decided once per call)
 };
 
 static GenCtx make_ctx(Frontend &F, uint64_t seed) {
@@ -892,7 +893,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         cs.job.wait();
     }
     const bool want_records = so.resident || (out && out->records);
-    const bool compact = !so.resident && want_records && H->use_compact();
+    const bool compact = !so.resident && want_records && so.compact;
     CompactOut co;
     int64_t cap_here = 0;
     auto reserve_records = [&](int64_t n_rec) {
@@ -1158,6 +1159,7 @@ static int run_plan(Handle *H, Plan &P, uint64_t seed, wfs_outputs *out, wfs_cou
     so.counts = counts;
     so.resident = resident;
     so.dump = dump;
+    so.compact = !resident && out && out->records && H->use_compact(out->records);
     const int64_t nb = (int64_t)P.batches.size();
     const int n_lanes = dump ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(env_i64("WFS_LANES", 3), 8), nb));
     ensure_lanes(H, std::max(n_lanes, 1));

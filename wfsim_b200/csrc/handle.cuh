@@ -26,10 +26,18 @@ struct Handle {
     HostPool *pool = nullptr;
     CompactStage cstage;
     TransportStats tstats;
-    int compact_mode = 1;               // WFS_COMPACT: 0 off, 1 on unless noise is enabled, 2 always
+    int compact_mode = 1;               // WFS_COMPACT: 0 never, 1 (default) see use_compact, 2 always
 
-    bool use_compact() const {
-        return compact_mode == 2 || (compact_mode == 1 && !(cfg.p.enable_noise && cfg.noise_t));
+    // Compact transport + host expansion, or a plain DMA of the 244-byte rows?  With the noise on
+    // nothing is compressible (the compact form is 248 B per record), but a plain copy is only fast
+    // into page-locked memory: into an ordinary numpy array the driver stages it at a few GB/s, while
+    // the expansion threads write it at the host's memory bandwidth.
+    bool use_compact(const void *dst) const {
+        if (compact_mode != 1) return compact_mode == 2;
+        if (!(cfg.p.enable_noise && cfg.noise_t)) return true;
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, dst) != cudaSuccess) { cudaGetLastError(); return true; }
+        return attr.type != cudaMemoryTypeHost;      // pinned destination: plain DMA straight into it
     }
     HostPool *host_pool() {
         if (!pool) pool = new HostPool(HostPool::default_threads());
