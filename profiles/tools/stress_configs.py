@@ -31,6 +31,8 @@ inst = heavy_s2_events(n2, seed=5, n_e=(10_000, 100_000))
 for k in range(2):
     run('C2', sim, cfg, inst)
 sim.close()
+if n3 <= 0:
+    sys.exit(0)
 # C3: mixed stream (95 % low energy, 5 % heavy), noise + ZLE
 rng = np.random.default_rng(3)
 noise = np.round(rng.normal(0, 2.0, (1 << 16, 494)))

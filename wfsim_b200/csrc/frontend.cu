@@ -363,6 +363,16 @@ static GenCtx make_ctx(Frontend &F, uint64_t seed) {
         H->launches.n++;                                           \
     } while (0)
 
+// largest number of photons of one instruction in [i0, i1) -> *out (atomicMax; preset to 0)
+__global__ void k_max_instr_photons(uint32_t i0, uint32_t i1, const uint32_t *__restrict__ emit_off,
+                                    const uint32_t *__restrict__ e_phoff, uint32_t *out) {
+    const uint32_t i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = 0;
+    if (i < i1) n = e_phoff[emit_off[i + 1]] - e_phoff[emit_off[i]];
+    n = __reduce_max_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31) == 0 && n) atomicMax(out, n);
+}
+
 // first photon of every instruction (photons are laid out instruction by instruction): [n + 1]
 __global__ void k_instr_ph_start(uint32_t n, const uint32_t *__restrict__ emit_off,
                                  const uint32_t *__restrict__ e_phoff, uint32_t *__restrict__ out) {
@@ -387,7 +397,7 @@ static void grow_photons(Frontend &F, int64_t n_new, int64_t n_old, cudaStream_t
 
 // Generate emitters and photons of instructions [i0, i1); arrays are appended.
 static void generate(Handle *H, Frontend &F, cudaStream_t s, uint64_t seed, int64_t i0, int64_t i1,
-                     int64_t &n_emit, int64_t &n_ph) {
+                     int64_t &n_emit, int64_t &n_ph, int64_t *max_instr_photons = nullptr) {
     const wfs_params &p = H->cfg.p;
     if (i1 <= i0) return;
     GenCtx g = make_ctx(F, seed);
@@ -406,7 +416,16 @@ static void generate(Handle *H, Frontend &F, cudaStream_t s, uint64_t seed, int6
     if (e1 > e0) FLAUNCH(k_emitters, div_up(e1 - e0, 128), 128, g, p, (uint32_t)i1, (uint32_t)e0, (uint32_t)e1);
     F.prim.exclusive_scan_u32(g.e_nph, g.e_phoff, e1, true);
     WFS_CUDA_CHECK(cudaMemcpyAsync(&tot, g.e_phoff + e1, 4, cudaMemcpyDeviceToHost, s));
+    uint32_t max_ph = 0;
+    if (max_instr_photons) {
+        F.b_scal.reserve(64);
+        WFS_CUDA_CHECK(cudaMemsetAsync(F.b_scal.p, 0, 4, s));
+        FLAUNCH(k_max_instr_photons, div_up(i1 - i0, 256), 256, (uint32_t)i0, (uint32_t)i1, g.i_emitoff, g.e_phoff,
+                F.b_scal.as<uint32_t>());
+        WFS_CUDA_CHECK(cudaMemcpyAsync(&max_ph, F.b_scal.p, 4, cudaMemcpyDeviceToHost, s));
+    }
     WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (max_instr_photons) *max_instr_photons = std::max<int64_t>(*max_instr_photons, max_ph);
     const int64_t p0 = n_ph, p1 = tot;
     if (p1 >= (int64_t(1) << 30)) throw std::runtime_error("photon batch too large; lower WFS_BATCH_PHOTONS");
     grow_photons(F, std::max<int64_t>(p1, 1), p0, s);
@@ -584,8 +603,8 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     }
     // ---- pass A: primaries ----
     WFS_CUDA_CHECK(cudaEventRecord(L.ev_c, s));
-    int64_t n_emit = 0, n_ph = 0;
-    generate(H, F, s, seed, 0, nprim, n_emit, n_ph);
+    int64_t n_emit = 0, n_ph = 0, max_instr_photons = 0;
+    generate(H, F, s, seed, 0, nprim, n_emit, n_ph, &max_instr_photons);
     // ---- secondaries: photo-ionisation electrons of the S2 calls (rawdata.py:193-197) ----
     int64_t ntot = nprim;
     std::vector<int32_t> h_parent;
@@ -644,7 +663,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
             down(sec_type.data(), F.b_itype.as<int32_t>() + nprim, 4 * (size_t)nsec);
             WFS_CUDA_CHECK(cudaStreamSynchronize(s));
             d_parent.release();
-            generate(H, F, s, seed, nprim, ntot, n_emit, n_ph);   // pass B
+            generate(H, F, s, seed, nprim, ntot, n_emit, n_ph, &max_instr_photons);   // pass B
         }
     }
     // ---- PMT afterpulses of every photon (rawdata.py:176-178) ----
@@ -736,7 +755,12 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     // ---- per-instruction truth accumulators ----
     F.b_acc.reserve(8 * (size_t)ntot * A_COUNT);
     g = make_ctx(F, seed);
-    FLAUNCH(k_instr_truth, (unsigned)ntot, 128, g, H->cfg, (uint32_t)ntot, (uint32_t)n_ph, (uint32_t)n_ph);
+    {
+        // heavy instructions (S2s with 1e5..1e6 photons) are split over several CTAs
+        const unsigned ny = (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, max_instr_photons / 16384));
+        if (ny > 1) FLAUNCH(k_acc_init, div_up(ntot * A_COUNT, 256), 256, ntot * (int64_t)A_COUNT, F.b_acc.as<int64_t>());
+        FLAUNCH(k_instr_truth, dim3((unsigned)ntot, ny), 128, g, H->cfg, (uint32_t)ntot, (uint32_t)n_ph, (uint32_t)n_ph);
+    }
     WFS_CUDA_CHECK(cudaEventRecord(L.ev_d, s));
     std::vector<int64_t> acc((size_t)ntot * A_COUNT);
     WFS_CUDA_CHECK(cudaMemcpyAsync(acc.data(), F.b_acc.p, 8 * acc.size(), cudaMemcpyDeviceToHost, s));

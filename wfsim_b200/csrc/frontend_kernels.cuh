@@ -442,14 +442,36 @@ __device__ __forceinline__ void time_moments(int64_t rel, int64_t &s, int64_t &h
     s += rel; hi2 += hi * hi; hilo += hi * lo; lo2 += lo * lo;
 }
 
+// neutral elements of the accumulators, for the multi-CTA (atomic) form of k_instr_truth
+__global__ void k_acc_init(int64_t n, int64_t *acc) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int a = (int)(k % A_COUNT);
+    acc[k] = (a == A_TMIN || a == A_ETMIN) ? LLONG_MAX : (a == A_TMAX || a == A_ETMAX || a == A_PTMAX) ? LLONG_MIN : 0;
+}
+
+// grid (n_instr, ny): CTA (i, y) takes the y-th slice of the photons / electrons / afterpulses of
+// instruction i.  ny == 1: plain stores; ny > 1 (heavy S2 instructions with millions of photons, which
+// one CTA would walk alone): integer atomics into accumulators preset by k_acc_init -- sums, minima and
+// maxima of integers, so the result does not depend on the order.
 __global__ void __launch_bounds__(128)
 k_instr_truth(GenCtx g, DeviceConfig c, uint32_t n_instr, uint32_t n_ph, uint32_t ap0) {
     __shared__ int64_t sm[4][A_COUNT];
     const uint32_t i = blockIdx.x;
     if (i >= n_instr) return;
+    const uint32_t ny = gridDim.y, yi = blockIdx.y;
     const int64_t T0 = g.i_time[i];
-    const uint32_t e0 = g.i_emitoff[i], e1 = g.i_emitoff[i + 1];
-    const uint32_t q0 = g.e_phoff[e0], q1 = g.e_phoff[e1];
+    const uint32_t e0_all = g.i_emitoff[i], e1_all = g.i_emitoff[i + 1];
+    const uint32_t q0_all = g.e_phoff[e0_all], q1_all = g.e_phoff[e1_all];
+    auto slice = [&](uint32_t lo, uint32_t hi, uint32_t &a, uint32_t &b) {
+        const uint64_t n = hi - lo;
+        a = lo + (uint32_t)(n * yi / ny);
+        b = lo + (uint32_t)(n * (yi + 1) / ny);
+    };
+    uint32_t e0, e1, q0, q1;
+    slice(e0_all, e1_all, e0, e1);
+    slice(q0_all, q1_all, q0, q1);
+    if (ny > 1 && yi > 0 && e1 == e0 && q1 == q0) return;   // nothing in this slice (CTA 0 still reports)
     int64_t v[A_COUNT];
 #pragma unroll
     for (int a = 0; a < A_COUNT; a++) v[a] = 0;
@@ -490,7 +512,7 @@ k_instr_truth(GenCtx g, DeviceConfig c, uint32_t n_instr, uint32_t n_ph, uint32_
             time_moments(t - T0, v[A_ESREL], v[A_EHI2], v[A_EHILO], v[A_ELO2]);
         }
     }
-    if (g.n_ap > 0 && q1 > q0) {   // PMT-afterpulse children extend the last pulse end
+    if (g.n_ap > 0 && q1 > q0) {   // PMT-afterpulse children (of my photons) extend the last pulse end
         const uint32_t a0 = ap0 + g.ap_off[q0], a1 = ap0 + (q1 < n_ph ? g.ap_off[q1] : g.ap_off[n_ph]);
         for (uint32_t a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
             const int64_t t = g.ph_t[a];
@@ -521,7 +543,11 @@ k_instr_truth(GenCtx g, DeviceConfig c, uint32_t n_instr, uint32_t n_ph, uint32_
             const int64_t u = sm[w][a];
             r = is_min ? (u < r ? u : r) : is_max ? (u > r ? u : r) : r + u;
         }
-        g.i_acc[(int64_t)i * A_COUNT + a] = r;
+        int64_t *out = &g.i_acc[(int64_t)i * A_COUNT + a];
+        if (ny == 1) *out = r;
+        else if (is_min) atomicMin((long long *)out, (long long)r);
+        else if (is_max) atomicMax((long long *)out, (long long)r);
+        else if (r) atomicAdd((unsigned long long *)out, (unsigned long long)r);
     }
 }
 
