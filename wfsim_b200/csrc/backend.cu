@@ -287,51 +287,96 @@ __global__ void k_window_extents(int64_t n_win, DeviceConfig c, const int64_t *s
 
 // Truth quirk of Pulse.add_truth (pulse.py:251-255): `trigger_dpe` counts the above-threshold
 // photons among the FIRST n_double_pe photons of the channel slice, whichever they are.
-// One thread per pulse, photons in their sorted (time) order.
-__global__ void k_truth_pulses(int64_t n_pulses, PhotonBatch b, DeviceConfig c, const uint32_t *vals,
-                               const int64_t *st, const double *sg, const uint32_t *pulse_first,
-                               const uint32_t *pulse_win, const uint32_t *win_key) {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pulses) return;
-    uint32_t a = pulse_first[p], e = pulse_first[p + 1];
-    int32_t pc = pc_of(b, vals[a]);
-    if (pc & 1) return;   // PMT-afterpulse calls carry preset gains: n_double_pe = 0 (pulse.py:106);
-                          // their truth buffer is not the one get_truth reads (rawdata.py:317-318)
-    int ch = win_key[pulse_win[p]] & ((1u << kChannelBits) - 1u);
+// Photons in their sorted (time) order.  One thread per pulse for short pulses; pulses of more than 32
+// photons (heavy S2s: thousands per PMT) are handed to the whole warp, one after the other, so that
+// no single thread walks them alone.  Everything summed is an integer: the order does not matter.
+struct PulseTruth {
     uint32_t ndpe = 0;
-    for (uint32_t i = a; i < e; i++) ndpe += b.flags[vals[i]] & 1u;
+    int trig = 0, n_trig = 0;
+    int64_t area = 0, area_trig = 0;
+};
+
+template <bool kWarp>
+__device__ __forceinline__ PulseTruth pulse_truth(uint32_t a, uint32_t e, int ch, bool per_pmt, const PhotonBatch &b,
+                                                  const DeviceConfig &c, const uint32_t *vals, const int64_t *st,
+                                                  const double *sg) {
+    const int lane = kWarp ? (int)(threadIdx.x & 31) : 0, step = kWarp ? 32 : 1;
+    PulseTruth r;
+    for (uint32_t i = a + lane; i < e; i += step) r.ndpe += b.flags[vals[i]] & 1u;
+    if (kWarp) r.ndpe = __reduce_add_sync(0xffffffffu, r.ndpe);
     const double thr = (double)(c.p.baseline - 1 - c.zle_thr[ch]) - 0.5;
-    int trig = 0;
-    for (uint32_t i = a; i < a + ndpe; i++) {
-        int64_t t = st[i];
-        int r = (int)(t - floordiv(t, c.p.dt) * c.p.dt);
-        if (sg[i] * c.current_max[r] * c.p.current_2_adc > thr) trig++;
-    }
-    if (trig) {
-        atomicAdd(&b.trig_dpe_out[2 * pc], trig);
-        if (ch >= c.p.n_top_pmts) atomicAdd(&b.trig_dpe_out[2 * pc + 1], trig);
-    }
-    if (b.pmt_counts) {   // per_pmt_truth: this thread owns (pulse call, channel)
-        const double gch = c.gains[ch];
-        int n_trig = 0;
-        int64_t area = 0, area_trig = 0;
-        for (uint32_t i = a; i < e; i++) {
-            const int64_t t = st[i];
-            const int r = (int)(t - floordiv(t, c.p.dt) * c.p.dt);
-            const bool above = sg[i] * c.current_max[r] * c.p.current_2_adc > thr;
+    const double gch = c.gains[ch];
+    const uint32_t stop = per_pmt ? e : a + r.ndpe;
+    for (uint32_t i = a + lane; i < stop; i += step) {
+        const int64_t t = st[i];
+        const int rem = (int)(t - floordiv(t, c.p.dt) * c.p.dt);
+        const bool above = sg[i] * c.current_max[rem] * c.p.current_2_adc > thr;
+        if (above && i < a + r.ndpe) r.trig++;
+        if (per_pmt) {
             const int64_t ar = llrint(sg[i] / gch * 4294967296.0);   // same fixed point as the totals (k_instr_truth)
-            area += ar;
-            if (above) { n_trig++; area_trig += ar; }
+            r.area += ar;
+            if (above) { r.n_trig++; r.area_trig += ar; }
         }
+    }
+    if (kWarp) {
+        r.trig = __reduce_add_sync(0xffffffffu, r.trig);
+        r.n_trig = __reduce_add_sync(0xffffffffu, r.n_trig);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            r.area += __shfl_xor_sync(0xffffffffu, r.area, o);
+            r.area_trig += __shfl_xor_sync(0xffffffffu, r.area_trig, o);
+        }
+    }
+    return r;
+}
+
+__device__ __forceinline__ void store_pulse_truth(const PulseTruth &r, uint32_t a, uint32_t e, int32_t pc, int ch,
+                                                  const PhotonBatch &b, const DeviceConfig &c) {
+    if (r.trig) {
+        atomicAdd(&b.trig_dpe_out[2 * pc], r.trig);
+        if (ch >= c.p.n_top_pmts) atomicAdd(&b.trig_dpe_out[2 * pc + 1], r.trig);
+    }
+    if (b.pmt_counts) {   // per_pmt_truth: one writer per (pulse call, channel)
         const int64_t npmt = c.p.n_tpc_pmts;
         int32_t *cnt = b.pmt_counts + ((int64_t)(pc >> 1) * 4) * npmt + ch;
         int64_t *ar_out = b.pmt_areas + ((int64_t)(pc >> 1) * 2) * npmt + ch;
         cnt[0] = (int32_t)(e - a);
-        cnt[npmt] = (int32_t)(e - a + ndpe);
-        cnt[2 * npmt] = n_trig;
-        cnt[3 * npmt] = n_trig + trig;
-        ar_out[0] = area;
-        ar_out[npmt] = area_trig;
+        cnt[npmt] = (int32_t)(e - a + r.ndpe);
+        cnt[2 * npmt] = r.n_trig;
+        cnt[3 * npmt] = r.n_trig + r.trig;
+        ar_out[0] = r.area;
+        ar_out[npmt] = r.area_trig;
+    }
+}
+
+__global__ void k_truth_pulses(int64_t n_pulses, PhotonBatch b, DeviceConfig c, const uint32_t *vals,
+                               const int64_t *st, const double *sg, const uint32_t *pulse_first,
+                               const uint32_t *pulse_win, const uint32_t *win_key) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool per_pmt = b.pmt_counts != nullptr;
+    uint32_t a = 0, e = 0;
+    int32_t pc = 1;
+    int ch = 0;
+    if (p < n_pulses) {
+        a = pulse_first[p]; e = pulse_first[p + 1];
+        pc = pc_of(b, vals[a]);
+        ch = win_key[pulse_win[p]] & ((1u << kChannelBits) - 1u);
+    }
+    // PMT-afterpulse calls (odd ids) carry preset gains: n_double_pe = 0 (pulse.py:106); their truth
+    // buffer is not the one get_truth reads (rawdata.py:317-318)
+    const bool mine = p < n_pulses && !(pc & 1);
+    const bool big = mine && e - a > 32u;
+    if (mine && !big) store_pulse_truth(pulse_truth<false>(a, e, ch, per_pmt, b, c, vals, st, sg), a, e, pc, ch, b, c);
+    unsigned todo = __ballot_sync(0xffffffffu, big);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t a2 = __shfl_sync(0xffffffffu, a, src), e2 = __shfl_sync(0xffffffffu, e, src);
+        const int ch2 = __shfl_sync(0xffffffffu, ch, src);
+        const int32_t pc2 = __shfl_sync(0xffffffffu, pc, src);
+        const PulseTruth r = pulse_truth<true>(a2, e2, ch2, per_pmt, b, c, vals, st, sg);
+        if (lane == 0) store_pulse_truth(r, a2, e2, pc2, ch2, b, c);
     }
 }
 
