@@ -1,15 +1,19 @@
 // Deterministic back end of the WFSim hot path on B200 (sm_100a).
 //
 //   photons (t_ns, channel, gain, pulse call) resident in HBM
-//     -> ordered by (digitisation group, channel, pulse call, time)      [radix sort, primitives.cu]
+//     -> ordered by (digitisation group, channel, pulse call, time)      [per-group sort in shared memory
+//                                                                          or device radix sort, primitives.cu]
 //     -> pulses  = runs of equal (group, channel, pulse call)            Pulse.__call__ pulse.py:82-144
 //     -> windows = runs of equal (group, channel)                        rawdata.py:231-235,258-259
-//     -> k_digitize: per (window, 512-sample tile) CTA: template superposition in fp64 with the
-//        reference's summation order, one rounding per pulse, integer sum over pulses, noise,
-//        baseline, clamp, int16 store + ZLE flag bits   pulse.py:276-318, rawdata.py:236-272,392-458
+//     -> k_digitize: one warp per 1024-sample tile of the window-contiguous dense buffer: template
+//        superposition in fp64 with the reference's summation order, one rounding per pulse, integer
+//        sum over pulses, noise, baseline, clamp, int16 store + ZLE flag bits
+//                                                        pulse.py:276-318, rawdata.py:236-272,392-458
 //     -> k_zle: hysteresis interval finding on the flag bits             utils.py:13-58, rawdata.py:296-308
-//     -> record keys (class, time, channel) -> radix sort                strax.sort_by_time
-//     -> k_pack: 244-byte raw_records written at their final position    strax_interface.py:425-436
+//     -> record keys (class, time, channel) -> per-(data type, group) sort in shared memory or
+//        device radix sort                                               strax.sort_by_time
+//     -> k_pack: 244-byte raw_records written at their final position, or the compact transport
+//        form for host destinations (transport.cuh)                      strax_interface.py:425-436
 //
 // HBM-bound integer/byte work: no tensor cores.  Accumulation is fp64 (B200 has full-rate FP64
 // FMA pipes; the mul/add are issued unfused to match the reference bit for bit).
