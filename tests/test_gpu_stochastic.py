@@ -254,3 +254,46 @@ def test_caller_owned_record_buffer(sim):
     small = np.zeros(10, raw_record_dtype())          # too small: the call falls back to its own buffer
     c = sim.simulate(inst, seed=3, records_out=small)
     assert np.array(c['raw_records']).tobytes() == np.array(a['raw_records']).tobytes()
+
+
+def test_save_full_truth_false_merges_instructions_into_one_pulse_call():
+    """save_full_truth=False (rawdata.py:110-123): S1 instructions within 100 ns and S2 instructions
+    within int(0.2 / v) ns of signal time share ONE Pulse call -- one truth row summarising them
+    (rawdata.py:355-372) and, in the records, one rounding per channel for the whole set.  Exact check
+    of the records against the oracle's deterministic back end with Pulse call = instruction set."""
+    from oracle import wfsim_oracle as orc
+    s, cfg = make_sim(save_full_truth=False)
+    v = cfg['drift_velocity_liquid']
+    base = c0_like(6, seed=31, e_range=(1, 10))
+    rows = []
+    for ev in range(6):
+        s1, s2 = base[2 * ev], base[2 * ev + 1]
+        for k, dt in enumerate((0, 40, 90, 400)):          # three S1 inside 100 ns gaps, one 310 ns later
+            r = s1.copy(); r['time'] += dt; r['amp'] = 200 + 50 * k; rows.append(r)
+        for k, dt in enumerate((0, 700, 1300, 9000)):      # S2: int(0.2 / v) = 1498 ns with v = 1.335e-4
+            r = s2.copy(); r['time'] += dt; r['amp'] = 30 + 10 * k; rows.append(r)
+    inst = np.array(rows, dtype=base.dtype)
+    out = s.simulate(inst, seed=13)
+    truth = out['truth']
+    # expected instruction sets per event: S1 {0, 40, 90} + {400}; S2 {0, 700, 1300} + {9000}
+    assert int(0.2 / v) == 1498
+    assert len(truth) == 6 * 4
+    t1 = truth[truth['type'] == 1]
+    np.testing.assert_array_equal(np.sort(t1['amp'].reshape(6, 2), axis=1), np.tile([350, 750], (6, 1)))
+    t2 = truth[truth['type'] == 2]
+    np.testing.assert_array_equal(np.sort(t2['amp'].reshape(6, 2), axis=1), np.tile([60, 120], (6, 1)))
+    ph = s.sample_stage(inst, stage=0, seed=13)
+    ph = ph[ph['channel'] >= 0]
+    assert truth['n_photon'].sum() == len(ph)
+    set_of = np.repeat(np.arange(12), 4) * 2 + np.tile([0, 0, 0, 1, 0, 0, 0, 1], 6)    # instruction -> set id
+    pcall = set_of[ph['instruction']]
+    uniq, pc = np.unique(pcall, return_inverse=True)
+    group_of = np.zeros(len(uniq), np.int32)
+    group_of[pc] = group_of_photons(ph, out['groups'], cfg)
+    want = orc.simulate_photons(cfg, pc.astype(np.int32), ph['channel'], ph['t'], ph['gain'], group_of)
+    assert out['raw_records'].tobytes() == want['raw_records'].tobytes()
+    # and it differs from the per-instruction rounding of the default mode
+    s2_, _ = make_sim()
+    full = s2_.simulate(inst, seed=13)
+    assert len(full['truth']) == len(inst)
+    s.close(); s2_.close()
