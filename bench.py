@@ -59,15 +59,8 @@ def ncu_traffic(kernel):
 def host_array(n, dtype):
     """Ordinary pageable host array for the records (what a plugin would allocate), on transparent
     huge pages where the kernel offers them, touched once so that page faults are not timed."""
-    import mmap
-    dtype = np.dtype(dtype)
-    nbytes = max(n * dtype.itemsize, 1)
-    m = mmap.mmap(-1, nbytes)
-    try:
-        m.madvise(mmap.MADV_HUGEPAGE)
-    except (AttributeError, OSError, ValueError):
-        pass
-    a = np.frombuffer(m, dtype=dtype, count=n)
+    from wfsim_b200.simulator import host_records
+    a = host_records(n, dtype)
     a.view(np.uint8)[::4096] = 0
     return a
 

@@ -172,6 +172,10 @@ typedef struct wfs_instr_maps {
     /* observed S2 position after the field-distortion model (s2.py:80-87); used by the garfield
      * luminescence model for the distance to the anode wires; NULL -> the instruction's x, y */
     const double *x_obs, *y_obs;
+    /* Index of the first digitisation group of this call in the caller's numbering: the noise start
+     * offset of group g is a Philox draw keyed by group_base + g (rawdata.py:407-417), so a run
+     * simulated in several calls draws what the single call would.  0 for a call of its own. */
+    int64_t group_base;
 } wfs_instr_maps;
 
 typedef struct wfs_counts {

@@ -201,3 +201,37 @@ def test_plugin_compute_loop_and_chunks():
     p2.set_config()
     with pytest.raises(AssertionError, match='Interaction has zero size'):
         p2.check_instructions()
+
+
+@pytest.mark.parametrize('noise', [False, True])
+def test_chunker_streams_the_run_piece_by_piece(noise):
+    """ChunkRawRecords simulates the run in pieces of `b200_piece_instructions` instructions (bounded
+    host memory) and yields chunks as they complete: same chunks, records and truth as the whole run
+    in one piece -- with noise too (the noise draw is keyed by the running group number)."""
+    from wfsim_b200.resource import Resource
+    from wfsim_b200.strax_interface import ChunkRawRecords
+    uniq, row = spe()
+    extra = {}
+    cfg = load_c0_config(chunk_size=1.5, enable_noise=noise)
+    if noise:
+        extra['noise_data'] = np.round(np.random.default_rng(8).normal(0, 2, (8192, 494)))
+    res = Resource(cfg, spe_ppf=uniq, spe_row=row, **extra)
+    inst = c0_like(14, seed=16, event_rate=2.0, e_range=(1, 30))
+    runs = {}
+    for piece in (6, 10 ** 9):
+        c = dict(cfg, b200_piece_instructions=piece)
+        sim = ChunkRawRecords(c, resource=res, seed=77)
+        chunks = []
+        for ch in sim(inst):
+            chunks.append((sim.chunk_time_pre, sim.chunk_time, ch))
+        assert sim.source_finished()
+        runs[piece] = chunks
+        sim.simulator.close()
+    a, b = runs[6], runs[10 ** 9]
+    assert len(a) == len(b) >= 3
+    for (pre1, ct1, c1), (pre2, ct2, c2) in zip(a, b):
+        assert (pre1, ct1) == (pre2, ct2)
+        for k in ('raw_records', 'raw_records_he', 'truth'):
+            assert np.asarray(c1[k]).tobytes() == np.asarray(c2[k]).tobytes(), k
+    assert sum(len(c[2]['raw_records']) for c in a) > 1000
+    assert sum(len(c[2]['truth']) for c in a) == len(inst)

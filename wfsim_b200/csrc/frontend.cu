@@ -154,6 +154,7 @@ struct BatchSpec {
 };
 
 struct Plan {
+    int64_t group_base = 0;      // wfs_instr_maps.group_base
     std::vector<HostInstr> instr;            // as given
     std::vector<int64_t> stime;              // signal time per instruction
     std::vector<int64_t> order;              // instruction indices ordered by signal time
@@ -200,6 +201,7 @@ static void make_plan(Handle *H, const uint8_t *rows, int64_t n, const wfs_instr
     P.scg.assign((size_t)n, P.scg_default);
     P.cy.assign((size_t)n, 1.0);
     P.patrow.assign((size_t)n, 0);
+    P.group_base = maps ? maps->group_base : 0;
     P.rng_id.resize((size_t)n);
     for (int64_t i = 0; i < n; i++) P.rng_id[i] = maps && maps->rng_id ? maps->rng_id[i] : (uint64_t)i;
     if (maps && maps->s1_lce) std::copy(maps->s1_lce, maps->s1_lce + n, P.lce.begin());
@@ -1190,6 +1192,7 @@ static int run_plan(Handle *H, Plan &P, uint64_t seed, wfs_outputs *out, wfs_cou
     cudaStream_t s = H->stream;
     WFS_CUDA_CHECK(cudaEventRecord(H->ev_a, s));
     Order ord;
+    ord.group_base = P.group_base;
     std::exception_ptr failure[8] = {};
     auto lane_loop = [&](int li) {
         try {

@@ -75,7 +75,8 @@ class Tables(C.Structure):
 class InstrMaps(C.Structure):
     _fields_ = [('s1_lce', vp), ('s2_sc_gain', vp), ('s2_cy_extra', vp), ('pattern', vp),
                 ('pattern_row', vp), ('n_pattern_rows', i64), ('s2_sc_gain_default', f64),
-                ('rng_id', vp), ('drift_velocity', vp), ('diffusion_long', vp), ('x_obs', vp), ('y_obs', vp)]
+                ('rng_id', vp), ('drift_velocity', vp), ('diffusion_long', vp), ('x_obs', vp), ('y_obs', vp),
+                ('group_base', i64)]
 
 
 class Outputs(C.Structure):

@@ -17,6 +17,23 @@ def _ptr(a):
     return a.ctypes.data if a is not None else None
 
 
+def host_records(n, dtype=None):
+    """Uninitialised host array for `n` records on transparent huge pages where the kernel offers
+    them: the library's expansion threads touch every page of a fresh output array, and with 4 KiB
+    pages the page faults cost more than the writes (30 GB per 1e5 low-energy events)."""
+    import mmap
+    dtype = np.dtype(raw_record_dtype() if dtype is None else dtype)
+    nbytes = int(n) * dtype.itemsize
+    if nbytes < (64 << 20) or not hasattr(mmap, 'MADV_HUGEPAGE'):
+        return np.empty(int(n), dtype)
+    m = mmap.mmap(-1, nbytes)
+    try:
+        m.madvise(mmap.MADV_HUGEPAGE)
+    except (OSError, ValueError):
+        pass
+    return np.frombuffer(m, dtype=dtype, count=int(n))
+
+
 class PinnedArray:
     """numpy view over pinned host memory obtained from the library (plain DMA target)."""
 
@@ -134,7 +151,7 @@ class Simulator:
         return out
 
     # -----------------------------------------------------------------------------------------
-    def _maps_struct(self, instructions, maps=None, rng_id=None, seed=0):
+    def _maps_struct(self, instructions, maps=None, rng_id=None, seed=0, group_base=0):
         if maps is None:
             if self.resource is None or isinstance(self.resource, dict):
                 raise SimulatorError('simulate() needs a Resource (maps) -- pass resource= to Simulator')
@@ -150,6 +167,7 @@ class Simulator:
         m.pattern_row = _ptr(keep['pattern_row'])
         m.n_pattern_rows = keep['pattern'].shape[0]
         m.s2_sc_gain_default = 0.0
+        m.group_base = int(group_base)
         for k in ('drift_velocity', 'diffusion_long', 'x_obs', 'y_obs'):
             if k in keep:
                 setattr(m, k, _ptr(keep[k]))
@@ -171,7 +189,7 @@ class Simulator:
         return c
 
     def simulate(self, instructions, seed=0, maps=None, cap_records=None, pinned=False, rng_id=None,
-                 per_pmt_truth=None, records_out=None):
+                 per_pmt_truth=None, records_out=None, group_base=0):
         """Full path for one set of instructions (see wfs_simulate in the header).
 
         Returns dict(raw_records, raw_records_he, raw_records_aqmon, truth, groups); records of
@@ -188,7 +206,7 @@ class Simulator:
         if instructions.dtype.itemsize != 70:
             raise ValueError('instructions must have the packed 70-byte instruction_dtype')
         n = len(instructions)
-        m, keep = self._maps_struct(instructions, maps, rng_id, seed=seed)
+        m, keep = self._maps_struct(instructions, maps, rng_id, seed=seed, group_base=group_base)
         counts = wlib.Counts()
         cap_rec = int(cap_records) if cap_records is not None else \
             (len(records_out) if records_out is not None else max(4096, 1500 * n))
@@ -202,7 +220,7 @@ class Simulator:
                     raise ValueError('records_out must be a C-contiguous raw_record_dtype array')
                 rec = records_out
             else:
-                rec = holder.array if pinned else np.empty(cap_rec, raw_record_dtype())
+                rec = holder.array if pinned else host_records(cap_rec)
             cap_rec = len(rec)
             truth = np.zeros(cap_truth, tdt)
             groups = np.zeros(cap_groups, gdt)

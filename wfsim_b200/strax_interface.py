@@ -33,7 +33,7 @@ except ImportError:
     HAVE_STRAX = False
 
 __all__ = ['instruction_dtype', 'truth_extra_dtype', 'extra_truth_dtype_per_pmt', 'ChunkRawRecords',
-           'SimulatorPlugin', 'RawRecordsFromFaxNT', 'instruction_from_csv', 'chunk_boundaries']
+           'SimulatorPlugin', 'RawRecordsFromFaxNT', 'instruction_from_csv', 'chunk_boundaries', 'ChunkClock']
 
 
 def instruction_from_csv(filename):
@@ -49,34 +49,51 @@ def instruction_from_csv(filename):
     return recs
 
 
-def chunk_boundaries(config, t_min_instruction, groups, time_zero=None):
-    """The chunk_time bookkeeping of ChunkRawRecords.__call__ (strax_interface.py:378-440).
+class ChunkClock:
+    """The chunk_time bookkeeping of ChunkRawRecords.__call__ (strax_interface.py:378-440) as a state
+    machine that is fed the digitisation groups piece by piece.
 
-    `groups` holds, per digitisation group in time order, (left, right, n_intervals) -- what the
-    reference reads from RawData.left / RawData.right while iterating the ZLE intervals.  Returns
-    [(chunk_time_pre, chunk_time), ...] in the order the reference yields its chunks."""
-    dt = config['sample_duration']
-    rext = int(config['right_raw_extension'])
-    cksz = int(config['chunk_size'] * 1e9)
-    pre = (time_zero - rext) if time_zero else (int(t_min_instruction) - rext)
-    ct = pre + cksz
-    cur_right = last_right = 0
-    out = []
-    for left, right, n_itv in groups:
-        for _ in range(max(int(n_itv), 0)):
-            if right != cur_right:
-                last_right, cur_right = cur_right, right
-            if left * dt > ct + rext:
-                if (last_right + 1) * dt > ct:
-                    ct += (last_right + 1) * dt - ct
-                out.append((pre, ct))
-                pre = ct
-                ct += cksz
-            else:
-                break
-    last_right = cur_right
-    ct = max((last_right + 1) * dt, pre + dt)
-    out.append((pre, ct))
+    `feed(groups)` takes (left, right, n_intervals) per group in time order -- what the reference
+    reads from RawData.left / RawData.right while iterating the ZLE intervals -- and returns the
+    chunks [(chunk_time_pre, chunk_time), ...] that became complete; `finish()` returns the last one."""
+
+    def __init__(self, config, t_min_instruction, time_zero=None):
+        self.dt = config['sample_duration']
+        self.rext = int(config['right_raw_extension'])
+        self.cksz = int(config['chunk_size'] * 1e9)
+        self.pre = (time_zero - self.rext) if time_zero else (int(t_min_instruction) - self.rext)
+        self.ct = self.pre + self.cksz
+        self.cur_right = self.last_right = 0
+
+    def feed(self, groups):
+        out = []
+        dt, rext = self.dt, self.rext
+        for left, right, n_itv in groups:
+            for _ in range(max(int(n_itv), 0)):
+                if right != self.cur_right:
+                    self.last_right, self.cur_right = self.cur_right, right
+                if left * dt > self.ct + rext:
+                    if (self.last_right + 1) * dt > self.ct:
+                        self.ct += (self.last_right + 1) * dt - self.ct
+                    out.append((self.pre, self.ct))
+                    self.pre = self.ct
+                    self.ct += self.cksz
+                else:
+                    break
+        return out
+
+    def finish(self):
+        self.last_right = self.cur_right
+        self.ct = max((self.last_right + 1) * self.dt, self.pre + self.dt)
+        return (self.pre, self.ct)
+
+
+def chunk_boundaries(config, t_min_instruction, groups, time_zero=None):
+    """All chunks of one run: [(chunk_time_pre, chunk_time), ...] in the order the reference yields
+    them (see ChunkClock)."""
+    clock = ChunkClock(config, t_min_instruction, time_zero)
+    out = clock.feed(groups)
+    out.append(clock.finish())
     return out
 
 
@@ -107,39 +124,62 @@ class ChunkRawRecords(object):
             self._finished = True
             return
         cfg = self.config
-        out = self.simulator.simulate(instructions, seed=self.seed)
-        chunks = chunk_boundaries(cfg, np.min(instructions['time']), out['groups'], time_zero)
-        truth = out['truth']
-        done = {k: 0 for k in ('raw_records', 'raw_records_he', 'raw_records_aqmon')}
-        truth_left = np.ones(len(truth), bool)
+        # The run is simulated PIECE BY PIECE (contiguous in signal time, cut only at quiet gaps, so the
+        # pieces are independent) and the chunks are yielded as soon as they are complete: host memory is
+        # bounded by one piece (config 'b200_piece_instructions', default 40000) instead of the whole run.
+        # Philox identities are the instruction indices and the noise draws are keyed by the running
+        # group number, so the records do not depend on how the run is cut.
+        from .sharding import shard_instructions
+        piece = max(int(cfg.get('b200_piece_instructions', 40000)), 1)
+        parts = [p for p in shard_instructions(instructions, -(-len(instructions) // piece), cfg) if len(p)]
+        clock = ChunkClock(cfg, np.min(instructions['time']), time_zero)
+        keys = ('raw_records', 'raw_records_he', 'raw_records_aqmon')
+        held = {k: np.zeros(0, raw_record_dtype(samples_per_record=samples_per_record)) for k in keys}
         tdt = np.dtype(instruction_dtype + self.truth_dtype)
-        for i, (pre, ct) in enumerate(chunks):
-            self.chunk_time_pre, self.chunk_time = pre, ct
+        held_truth = None
+        n_groups = 0
+
+        def cut(ct, last):
+            """Records and truth rows up to chunk time `ct` leave the held arrays."""
+            nonlocal held_truth
             res = {}
-            for k in done:
-                rec = out[k]
-                stop = done[k] + int(np.searchsorted(rec['time'][done[k]:], ct, side='right'))
-                res[k] = rec[done[k]:stop]          # already sorted by (time, channel)
-                done[k] = stop
+            for k in keys:
+                rec = held[k]               # sorted by (time, channel)
+                stop = len(rec) if last else int(np.searchsorted(rec['time'], ct, side='right'))
+                res[k], held[k] = rec[:stop], rec[stop:]
             # truth rows of this chunk (strax_interface.py:458-483)
+            truth = held_truth
             tfp = truth['t_first_photon']
-            sel = truth_left & ((tfp <= ct) | (np.isnan(tfp) & (truth['time'] <= ct)))
-            truth_left &= ~sel
-            t = truth[sel]
+            sel = (tfp <= ct) | (np.isnan(tfp) & (truth['time'] <= ct))
+            t, held_truth = truth[sel], truth[~sel]
             t = t[np.argsort(t['time'], kind='stable')]
             _truth = np.zeros(len(t), dtype=tdt)
             for name in _truth.dtype.names:
                 _truth[name] = t[name]
             has = ~np.isnan(_truth['t_first_photon'])
             _truth['time'][has] = _truth['t_first_photon'][has].astype(int)
-            _truth = _truth[np.argsort(_truth['time'], kind='stable')]
-            res['truth'] = _truth
-            if i == len(chunks) - 1:
-                self._finished = True
+            res['truth'] = _truth[np.argsort(_truth['time'], kind='stable')]
+            return res
+
+        def deliver(res):
             if cfg['detector'] in ('XENON1T', 'XENONnT_neutron_veto'):
-                yield dict(raw_records=res['raw_records'], truth=_truth)
-            else:
-                yield res
+                return dict(raw_records=res['raw_records'], truth=res['truth'])
+            return res
+
+        for i_part, idx in enumerate(parts):
+            out = self.simulator.simulate(instructions[idx], seed=self.seed, rng_id=idx.astype(np.uint64),
+                                          group_base=n_groups)
+            n_groups += len(out['groups'])
+            for k in keys:
+                held[k] = np.concatenate([held[k], out[k]]) if len(held[k]) else np.asarray(out[k])
+            held_truth = out['truth'] if held_truth is None or not len(held_truth) \
+                else np.concatenate([held_truth, out['truth']])
+            for pre, ct in clock.feed(out['groups']):
+                self.chunk_time_pre, self.chunk_time = pre, ct
+                yield deliver(cut(ct, last=False))
+        self.chunk_time_pre, self.chunk_time = clock.finish()
+        self._finished = True
+        yield deliver(cut(self.chunk_time, last=True))
 
     def source_finished(self):
         return self._finished
