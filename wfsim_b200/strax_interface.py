@@ -134,19 +134,22 @@ class ChunkRawRecords(object):
         parts = [p for p in shard_instructions(instructions, -(-len(instructions) // piece), cfg) if len(p)]
         clock = ChunkClock(cfg, np.min(instructions['time']), time_zero)
         keys = ('raw_records', 'raw_records_he', 'raw_records_aqmon')
-        held = {k: np.zeros(0, raw_record_dtype(samples_per_record=samples_per_record)) for k in keys}
+        held = {k: [] for k in keys}        # per data type: arrays of the pieces not yet delivered, in time order
         tdt = np.dtype(instruction_dtype + self.truth_dtype)
         held_truth = None
         n_groups = 0
+        empty = np.zeros(0, raw_record_dtype(samples_per_record=samples_per_record))
 
         def cut(ct, last):
             """Records and truth rows up to chunk time `ct` leave the held arrays."""
             nonlocal held_truth
             res = {}
             for k in keys:
-                rec = held[k]               # sorted by (time, channel)
+                # the pieces are disjoint in time and each is sorted by (time, channel): one copy per chunk
+                parts_k = [a for a in held[k] if len(a)]
+                rec = empty if not parts_k else parts_k[0] if len(parts_k) == 1 else np.concatenate(parts_k)
                 stop = len(rec) if last else int(np.searchsorted(rec['time'], ct, side='right'))
-                res[k], held[k] = rec[:stop], rec[stop:]
+                res[k], held[k] = rec[:stop], [rec[stop:]]
             # truth rows of this chunk (strax_interface.py:458-483)
             truth = held_truth
             tfp = truth['t_first_photon']
@@ -171,7 +174,7 @@ class ChunkRawRecords(object):
                                           group_base=n_groups)
             n_groups += len(out['groups'])
             for k in keys:
-                held[k] = np.concatenate([held[k], out[k]]) if len(held[k]) else np.asarray(out[k])
+                held[k].append(np.asarray(out[k]))
             held_truth = out['truth'] if held_truth is None or not len(held_truth) \
                 else np.concatenate([held_truth, out['truth']])
             for pre, ct in clock.feed(out['groups']):
