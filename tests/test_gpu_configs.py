@@ -165,3 +165,26 @@ def test_c4_superposition_microbench_properties():
     assert abs(total - area) <= 0.5 * touched + 1
     assert abs(total - area) / area < 2e-3
     sim.close()
+
+
+def test_group_local_order_with_afterpulses_and_secondaries(monkeypatch):
+    """With PMT afterpulses and photo-ionisation electrons a group's photons sit in up to four runs of
+    the photon array (primaries, secondaries, afterpulse children of either); the per-group
+    shared-memory sort gathers them and gives the bytes of the device-wide radix sort."""
+    from tests.golden.synth_instructions import c1_like
+    sim, cfg = make_sim(dict(uniform_to_pmt_ap=pmt_ap_tables(494), uniform_to_ele_ap=EleApHist()),
+                        enable_pmt_afterpulses=True, enable_electron_afterpulses=True)
+    inst = c1_like(400, seed=19)
+    outs = {}
+    for mode in ('0', '1'):
+        monkeypatch.setenv('WFS_SEGMENT_SORT', mode)
+        o = sim.simulate(inst, seed=44)
+        outs[mode] = {k: np.array(v) for k, v in o.items() if k != '_pinned'}
+        seg_batches = sim.last_counts['ms_phase'][10]
+        assert (seg_batches > 0) == (mode == '1')
+    for k in ('raw_records', 'raw_records_he', 'truth', 'groups'):
+        assert outs['0'][k].tobytes() == outs['1'][k].tobytes(), k
+    check_records_sorted_and_consistent(outs['1'], cfg)
+    ph = sim.sample_stage(inst, stage=0, seed=44)
+    assert ((ph['flags'] >> 1) & 1).sum() > 100          # afterpulse photons are there
+    sim.close()

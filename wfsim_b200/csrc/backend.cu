@@ -1245,7 +1245,7 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
             const uint64_t invalid_key = (uint64_t)ng << kl.shift_group;
             prim_.segment_sort_pairs(keys_.as<uint64_t>(), vals_.as<uint32_t>(), prim_.sort_keys_alt.as<uint64_t>(),
                                      prim_.sort_vals_alt.as<uint32_t>(), b.group_start, group_out_.as<uint32_t>(),
-                                     ng, b.max_group_photons, kl.shift_group, invalid_key);
+                                     ng, b.max_group_photons, kl.shift_group, invalid_key, b.group_ranges);
             LAUNCH(k_fill_invalid_tail, div_up(n, T), T, n, group_out_.as<uint32_t>() + ng, invalid_key,
                    prim_.sort_keys_alt.as<uint64_t>());
             std::swap(keys_, prim_.sort_keys_alt);

@@ -42,11 +42,14 @@ struct PhotonBatch {
     const int64_t *ix_rand = nullptr;      // [n_groups] or nullptr -> Philox(seed, group_base + g)
     uint64_t seed = 0;
     int64_t group_base = 0;                // global index of group 0 of this batch (RNG counter)
-    // Optional: the photons of group g are the contiguous range [group_start[g], group_start[g+1])
-    // of the arrays above (device array, [n_groups+1]) and no group holds more than
-    // max_group_photons of them -> the ordering is done per group in shared memory
-    // (Primitives::segment_sort_pairs) instead of by the device-wide radix sort.
+    // Optional: the photons of group g are the ranges [group_start[r][g], group_start[r][g+1]),
+    // r < group_ranges, of the arrays above (device array, [group_ranges][n_groups+1]; the generate
+    // path has up to four runs: photons of the primaries, of the secondaries, and the PMT-afterpulse
+    // children of either) and no group holds more than max_group_photons of them -> the ordering is
+    // done per group in shared memory (Primitives::segment_sort_pairs) instead of by the device-wide
+    // radix sort.
     const uint32_t *group_start = nullptr;
+    int group_ranges = 1;
     int64_t max_group_photons = 0;
     // Optional per-PMT truth (generate mode): per Pulse call r = pulse-call id >> 1 and PMT, written
     // by the thread that owns the (pulse call, channel) pulse -- pulse.py:257-269 with per_pmt_truth.

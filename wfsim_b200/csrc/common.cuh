@@ -86,15 +86,16 @@ struct Primitives {
     void sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, int key_bits);
 
     // Stable sort of (key, value) pairs INSIDE segments: segment s holds items
-    // [seg_start[s], seg_start[s+1]) of keys_in/vals_in (device arrays), each at most kSegSortMax
-    // items (max_seg = the largest one, sizes the shared memory).  Ordered by bits [0, key_bits) of
+    // [seg_start[s], seg_start[s+1]) of keys_in/vals_in (device arrays) -- or, with n_ranges > 1, the
+    // concatenation of that range of each of the n_ranges tables seg_start[r][n_seg + 1] (at most
+    // four) -- each at most kSegSortMax items (max_seg = the largest one, sizes the shared memory).  Ordered by bits [0, key_bits) of
     // the key -- the bits above must be equal inside a segment; items with key >= drop_from are
     // dropped.  Segment s is written to keys_out/vals_out at out_start[s] (or seg_start[s] when
     // out_start is null).  One CTA per segment, everything in shared memory: one read and one
     // write of the data instead of one per digit.
     void segment_sort_pairs(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *keys_out,
                             uint32_t *vals_out, const uint32_t *seg_start, const uint32_t *out_start,
-                            int64_t n_seg, int64_t max_seg, int key_bits, uint64_t drop_from);
+                            int64_t n_seg, int64_t max_seg, int key_bits, uint64_t drop_from, int n_ranges = 1);
 
     void release() {
         scan_tmp.release(); sort_hist.release(); sort_keys_alt.release();

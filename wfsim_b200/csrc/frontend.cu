@@ -376,10 +376,15 @@ __global__ void k_max_instr_photons(uint32_t i0, uint32_t i1, const uint32_t *__
 }
 
 // first photon of every instruction (photons are laid out instruction by instruction): [n + 1]
+// ... and the first PMT-afterpulse child of the instruction's photons (children follow the parent order)
 __global__ void k_instr_ph_start(uint32_t n, const uint32_t *__restrict__ emit_off,
-                                 const uint32_t *__restrict__ e_phoff, uint32_t *__restrict__ out) {
+                                 const uint32_t *__restrict__ e_phoff, const uint32_t *__restrict__ ap_off,
+                                 uint32_t *__restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i <= n) out[i] = e_phoff[emit_off[i]];
+    if (i > n) return;
+    const uint32_t q = e_phoff[emit_off[i]];
+    out[i] = q;
+    out[n + 1 + i] = ap_off[q];
 }
 
 static void grow_instr(Frontend &F, int64_t n_new, int64_t n_old, cudaStream_t s) {
@@ -766,12 +771,12 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     WFS_CUDA_CHECK(cudaEventRecord(L.ev_d, s));
     std::vector<int64_t> acc((size_t)ntot * A_COUNT);
     WFS_CUDA_CHECK(cudaMemcpyAsync(acc.data(), F.b_acc.p, 8 * acc.size(), cudaMemcpyDeviceToHost, s));
-    std::vector<uint32_t> ph_start((size_t)ntot + 1, 0u);
+    std::vector<uint32_t> ph_start(2 * ((size_t)ntot + 1), 0u);     // [ntot + 1] photon starts, [ntot + 1] afterpulse starts
     if (n_ph > 0) {
-        F.b_phstart.reserve(4 * (size_t)(ntot + 1));
-        FLAUNCH(k_instr_ph_start, div_up(ntot + 1, 256), 256, (uint32_t)ntot, g.i_emitoff, g.e_phoff,
+        F.b_phstart.reserve(4 * ph_start.size());
+        FLAUNCH(k_instr_ph_start, div_up(ntot + 1, 256), 256, (uint32_t)ntot, g.i_emitoff, g.e_phoff, g.ap_off,
                 F.b_phstart.as<uint32_t>());
-        WFS_CUDA_CHECK(cudaMemcpyAsync(ph_start.data(), F.b_phstart.p, 4 * (size_t)(ntot + 1), cudaMemcpyDeviceToHost, s));
+        WFS_CUDA_CHECK(cudaMemcpyAsync(ph_start.data(), F.b_phstart.p, 4 * ph_start.size(), cudaMemcpyDeviceToHost, s));
     }
     WFS_CUDA_CHECK(cudaStreamSynchronize(s));
     float ms_front = 0;
@@ -829,32 +834,46 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         up(F.b_pcrank, pc_rank.data(), 4 * (size_t)npc);
         WFS_CUDA_CHECK(cudaMemsetAsync(F.b_trig.p, 0, 4 * (size_t)(2 * npc), s));
     }
-    // Photons are laid out instruction by instruction.  If the groups the scheduler formed are runs
-    // of consecutive instructions (the common case: no secondaries, no PMT afterpulses behind the
-    // primaries) every group is a contiguous photon range and the back end can order it in shared memory.
+    // Photons are laid out instruction by instruction in up to four runs: photons of the primaries, of
+    // the secondaries, and behind them the PMT-afterpulse children of either (in parent order).  If in
+    // every run the groups the scheduler formed follow each other (the common case), every group is the
+    // concatenation of one range per run and the back end can order it in shared memory.
     std::vector<uint32_t> gstart;
     int64_t max_group_photons = 0;
+    const int n_ranges = 4;
     {
-        bool contiguous = n_ap == 0 && n_ph > 0 && ngroups > 0;
+        bool contiguous = n_ph > 0 && ngroups > 0;
+        const uint32_t *ap_start = ph_start.data() + (ntot + 1);
         if (contiguous) {
-            gstart.assign((size_t)ngroups + 1, UINT32_MAX);
-            int32_t last_group = -1;
-            for (int64_t i = 0; i < ntot && contiguous; i++) {
-                if (ph_start[i + 1] == ph_start[i] || instr_run[i] < 0) continue;   // no photons / in no Pulse call
-                const int32_t gi = runs[instr_run[i]].group;
-                if (gi < last_group) contiguous = false;
-                else if (gi > last_group) { gstart[gi] = ph_start[i]; last_group = gi; }
+            gstart.assign((size_t)n_ranges * (ngroups + 1), UINT32_MAX);
+            for (int cls = 0; cls < n_ranges && contiguous; cls++) {
+                const int64_t i0 = (cls & 1) ? nprim : 0, i1 = (cls & 1) ? ntot : nprim;
+                auto first_of = [&](int64_t i) -> uint32_t {
+                    return cls < 2 ? ph_start[i] : (uint32_t)n_ph + ap_start[i];
+                };
+                uint32_t *gs = &gstart[(size_t)cls * (ngroups + 1)];
+                int32_t last_group = -1;
+                for (int64_t i = i0; i < i1 && contiguous; i++) {
+                    if (first_of(i + 1) == first_of(i) || instr_run[i] < 0) continue;   // nothing / in no Pulse call
+                    const int32_t gi = runs[instr_run[i]].group;
+                    if (gi < last_group) contiguous = false;
+                    else if (gi > last_group) { gs[gi] = first_of(i); last_group = gi; }
+                }
+                gs[ngroups] = first_of(i1);
+                for (int32_t gi = ngroups - 1; gi >= 0; gi--)
+                    if (gs[gi] == UINT32_MAX) gs[gi] = gs[gi + 1];                     // group without photons in this run
+                gs[0] = first_of(i0);     // photons in front of the first group belong to no Pulse call: dropped as invalid
             }
         }
         if (contiguous) {
-            gstart[ngroups] = (uint32_t)n_ph;
-            for (int32_t gi = ngroups - 1; gi >= 0; gi--)
-                if (gstart[gi] == UINT32_MAX) gstart[gi] = gstart[gi + 1];        // group without photons
-            gstart[0] = 0;     // photons in front of the first group belong to no Pulse call: dropped as invalid
-            for (int32_t gi = 0; gi < ngroups; gi++)
-                max_group_photons = std::max<int64_t>(max_group_photons, gstart[gi + 1] - gstart[gi]);
-            F.b_gstart.reserve(4 * (size_t)(ngroups + 1));
-            up(F.b_gstart, gstart.data(), 4 * (size_t)(ngroups + 1));
+            for (int32_t gi = 0; gi < ngroups; gi++) {
+                int64_t cnt = 0;
+                for (int cls = 0; cls < n_ranges; cls++)
+                    cnt += gstart[(size_t)cls * (ngroups + 1) + gi + 1] - gstart[(size_t)cls * (ngroups + 1) + gi];
+                max_group_photons = std::max(max_group_photons, cnt);
+            }
+            F.b_gstart.reserve(4 * gstart.size());
+            up(F.b_gstart, gstart.data(), 4 * gstart.size());
         } else {
             gstart.clear();
         }
@@ -891,6 +910,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     b.group_base = group_base;
     if (!gstart.empty()) {
         b.group_start = F.b_gstart.as<uint32_t>();
+        b.group_ranges = n_ranges;
         b.max_group_photons = max_group_photons;
     }
     const bool per_pmt = so.out && so.out->truth_pmt_counts && so.out->truth_pmt_areas && nruns > 0;

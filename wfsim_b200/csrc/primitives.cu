@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(kSegThreads)
 k_segment_sort(int n_seg, const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ out_start,
                const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int key_bits,
-               uint64_t drop_from, int n_lo, int cap) {
+               uint64_t drop_from, int n_lo, int cap, int n_ranges) {
     extern __shared__ uint64_t s_buf[];                 // [2][cap] items
     __shared__ uint32_t wcount[kSegWarps][256];
     __shared__ uint32_t dbase[256];
@@ -290,9 +290,24 @@ k_segment_sort(int n_seg, const uint32_t *__restrict__ seg_start, const uint32_t
     const uint32_t lt = (1u << lane) - 1u;
     const uint64_t kmask = (uint64_t(1) << key_bits) - 1u;
     for (int seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
-        const uint32_t a = seg_start[seg];
-        const int n = (int)(seg_start[seg + 1] - a);
+        // a segment is the concatenation of up to four ranges of the input (seg_start is [n_ranges][n_seg + 1])
+        uint32_t ra[4] = {0, 0, 0, 0}, rc[4] = {0, 0, 0, 0};
+        int n = 0;
+        for (int r = 0; r < n_ranges; r++) {
+            ra[r] = seg_start[(size_t)r * (n_seg + 1) + seg];
+            rc[r] = seg_start[(size_t)r * (n_seg + 1) + seg + 1] - ra[r];
+            n += (int)rc[r];
+        }
         if (n <= n_lo || n > cap) continue;
+        auto src_of = [&](uint32_t i) -> uint32_t {
+            if (i < rc[0]) return ra[0] + i;
+            i -= rc[0];
+            if (i < rc[1]) return ra[1] + i;
+            i -= rc[1];
+            if (i < rc[2]) return ra[2] + i;
+            return ra[3] + (i - rc[2]);
+        };
+        const uint32_t a = src_of(0);
         const uint32_t o = out_start ? out_start[seg] : a;
         uint64_t *cur = s_buf, *alt = s_buf + cap;
         __syncthreads();
@@ -305,7 +320,7 @@ k_segment_sort(int n_seg, const uint32_t *__restrict__ seg_start, const uint32_t
                 x0 = ((k >= drop_from ? (uint64_t(1) << key_bits) : 0ull) | (k & kmask)) << kSegIdxBits;
             }
             for (int i = tid; i < n; i += kSegThreads) {
-                const uint64_t k = keys_in[a + i];
+                const uint64_t k = keys_in[src_of((uint32_t)i)];
                 const uint64_t x = (((k >= drop_from ? (uint64_t(1) << key_bits) : 0ull) | (k & kmask)) << kSegIdxBits) |
                                    (uint64_t)i;
                 cur[i] = x;
@@ -385,7 +400,7 @@ k_segment_sort(int n_seg, const uint32_t *__restrict__ seg_start, const uint32_t
         for (int i = tid; i < n; i += kSegThreads) {
             const uint64_t x = cur[i];
             if ((x >> (kSegIdxBits + key_bits)) & 1ull) continue;     // dropped (they sort behind the kept ones)
-            const uint32_t src = a + (uint32_t)(x & ((1u << kSegIdxBits) - 1u));
+            const uint32_t src = src_of((uint32_t)(x & ((1u << kSegIdxBits) - 1u)));
             keys_out[o + i] = keys_in[src];
             vals_out[o + i] = vals_in[src];
         }
@@ -394,9 +409,9 @@ k_segment_sort(int n_seg, const uint32_t *__restrict__ seg_start, const uint32_t
 
 void Primitives::segment_sort_pairs(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *keys_out,
                                     uint32_t *vals_out, const uint32_t *seg_start, const uint32_t *out_start,
-                                    int64_t n_seg, int64_t max_seg, int key_bits, uint64_t drop_from) {
+                                    int64_t n_seg, int64_t max_seg, int key_bits, uint64_t drop_from, int n_ranges) {
     if (n_seg <= 0) return;
-    if (max_seg > kSegSortMax || key_bits + 1 + kSegIdxBits > 64)
+    if (max_seg > kSegSortMax || key_bits + 1 + kSegIdxBits > 64 || n_ranges < 1 || n_ranges > 4)
         throw std::runtime_error("segment_sort_pairs: segment too large / key too wide");
     auto smem_of = [](int cap) { return (size_t)cap * 2 * sizeof(uint64_t); };
     if (!seg_attr_set) {
@@ -415,11 +430,11 @@ void Primitives::segment_sort_pairs(const uint64_t *keys_in, const uint32_t *val
         if (cap <= 8 * kSegThreads)
             k_segment_sort<8><<<grid, kSegThreads, smem_of(cap), stream>>>((int)n_seg, seg_start, out_start, keys_in,
                                                                          vals_in, keys_out, vals_out, key_bits,
-                                                                         drop_from, lo, cap);
+                                                                         drop_from, lo, cap, n_ranges);
         else
             k_segment_sort<32><<<grid, kSegThreads, smem_of(cap), stream>>>((int)n_seg, seg_start, out_start, keys_in,
                                                                           vals_in, keys_out, vals_out, key_bits,
-                                                                          drop_from, lo, cap);
+                                                                          drop_from, lo, cap, n_ranges);
         lc->n++;
     };
     if (split >= 256 && split <= 8 * kSegThreads && cap_all > split) {
