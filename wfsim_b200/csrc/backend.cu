@@ -631,7 +631,12 @@ k_digitize(int64_t n_blocks, int tile_blk, int n_tiles, int64_t n_wtot, DeviceCo
     __syncthreads();   // the only CTA-wide barrier: from here on every warp works on tiles of its own
 
     const int n_warps = gridDim.x * kDigiWarps;
+    // the window rows of the NEXT tile of this warp are pulled towards the SM while the current tile is
+    // worked on: tile -> first window -> window offsets / rows -> photons is a chain of dependent loads
+    int64_t w_first = blockIdx.x * kDigiWarps + warp < n_tiles ? tile_first[blockIdx.x * kDigiWarps + warp] : 0;
     for (int tile = blockIdx.x * kDigiWarps + warp; tile < n_tiles; tile += n_warps) {
+        const int64_t w_here = w_first;
+        if (tile + n_warps < n_tiles) w_first = tile_first[tile + n_warps];
         const int64_t B0 = (int64_t)tile * tile_blk;
         const int nblk = (int)min((int64_t)tile_blk, n_blocks - B0);
         const int nsmp = nblk * kBlk;
@@ -640,7 +645,7 @@ k_digitize(int64_t n_blocks, int tile_blk, int n_tiles, int64_t n_wtot, DeviceCo
         if (lane < kTileBlkMax / 32) W.touch[lane] = 0;
         // ---- setup: the windows overlapping this tile, in window order ----
         int n = 0;
-        for (int64_t base = tile_first[tile];; base += 32) {
+        for (int64_t base = w_here;; base += 32) {
             const int64_t w = base + lane;
             bool past = w >= n_wtot, take = false;
             int64_t b0 = 0;
@@ -749,6 +754,10 @@ k_digitize(int64_t n_blocks, int tile_blk, int n_tiles, int64_t n_wtot, DeviceCo
             }
         }
         if (sparse) {
+            if (tile + n_warps < n_tiles && w_first + lane < n_wtot) {   // next tile's window rows and offsets
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(meta + w_first + lane));
+                if (lane < 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(win_off + w_first + 8 * lane));
+            }
             // ---- untouched blocks: constant stores; touched blocks: compacted list ----
             int ntb = 0;
             for (int wd = 0; wd * 32 < nblk; wd++) {
