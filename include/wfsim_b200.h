@@ -176,6 +176,18 @@ typedef struct wfs_instr_maps {
      * offset of group g is a Philox draw keyed by group_base + g (rawdata.py:407-417), so a run
      * simulated in several calls draws what the single call would.  0 for a call of its own. */
     int64_t group_base;
+    /* Externally supplied photons (RawDataOptical.sim_primary, rawdata.py:478-495: G4 optical output,
+     * neutron-veto style inputs): a type-1 instruction with opt_last[i] > opt_first[i] takes its photons
+     * from the lists below instead of sampling them -- channel opt_channels[k], arrival time
+     * instruction time + opt_timings[k], k in [opt_first[i], opt_last[i]); photons with a timing < 0
+     * or >= opt_time_cutoff (config nveto_time_max_cutoff) are dropped.  Transit-time spread, double
+     * photo-electrons and SPE gains are sampled for them as for any photon (Pulse.__call__).  All NULL /
+     * 0 -> none. */
+    const int64_t *opt_first, *opt_last;    /* [n_instr] (the `_first`, `_last` columns) */
+    const int32_t *opt_channels;            /* [n_opt] */
+    const int64_t *opt_timings;             /* [n_opt] ns relative to the instruction time */
+    int64_t n_opt;
+    int64_t opt_time_cutoff;
 } wfs_instr_maps;
 
 typedef struct wfs_counts {

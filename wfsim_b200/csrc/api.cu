@@ -74,7 +74,8 @@ Handle::~Handle() {
     delete pool;
     delete backend;
     for (void *p : owned) cudaFree(p);
-    DevBuf *bufs[] = {&d_t, &d_ch, &d_gain, &d_pc, &d_pc_group, &d_pc_rank, &d_ix, &d_records, &d_groups};
+    DevBuf *bufs[] = {&d_t, &d_ch, &d_gain, &d_pc, &d_pc_group, &d_pc_rank, &d_ix, &d_records, &d_groups,
+                      &d_opt_ch, &d_opt_t};
     for (DevBuf *b : bufs) b->release();
     cudaEventDestroy(ev_a); cudaEventDestroy(ev_b); cudaEventDestroy(ev_c); cudaEventDestroy(ev_d);
     cudaStreamDestroy(stream);

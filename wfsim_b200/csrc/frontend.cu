@@ -155,6 +155,11 @@ struct BatchSpec {
 
 struct Plan {
     int64_t group_base = 0;      // wfs_instr_maps.group_base
+    std::vector<int64_t> opt_first;   // externally supplied photons: first list index / count per instruction
+    std::vector<int32_t> opt_n;       // (empty: the call has none)
+    const int32_t *opt_channels = nullptr;
+    const int64_t *opt_timings = nullptr;
+    int64_t n_opt = 0, opt_cutoff = 0;
     std::vector<HostInstr> instr;            // as given
     std::vector<int64_t> stime;              // signal time per instruction
     std::vector<int64_t> order;              // instruction indices ordered by signal time
@@ -202,6 +207,22 @@ static void make_plan(Handle *H, const uint8_t *rows, int64_t n, const wfs_instr
     P.cy.assign((size_t)n, 1.0);
     P.patrow.assign((size_t)n, 0);
     P.group_base = maps ? maps->group_base : 0;
+    if (maps && maps->opt_first && maps->opt_last && maps->n_opt > 0) {
+        if (!maps->opt_channels || !maps->opt_timings) throw std::runtime_error("opt_channels / opt_timings missing");
+        P.opt_first.assign((size_t)n, 0);
+        P.opt_n.assign((size_t)n, 0);
+        for (int64_t i = 0; i < n; i++) {
+            const int64_t a = maps->opt_first[i], b = maps->opt_last[i];
+            if (b <= a) continue;
+            if (a < 0 || b > maps->n_opt || b - a > INT32_MAX) throw std::runtime_error("opt_first / opt_last out of range");
+            P.opt_first[i] = a;
+            P.opt_n[i] = (int32_t)(b - a);
+        }
+        P.opt_channels = maps->opt_channels;
+        P.opt_timings = maps->opt_timings;
+        P.n_opt = maps->n_opt;
+        P.opt_cutoff = maps->opt_time_cutoff > 0 ? maps->opt_time_cutoff : 1000000;   // nveto_time_max_cutoff default
+    }
     P.rng_id.resize((size_t)n);
     for (int64_t i = 0; i < n; i++) P.rng_id[i] = maps && maps->rng_id ? maps->rng_id[i] : (uint64_t)i;
     if (maps && maps->s1_lce) std::copy(maps->s1_lce, maps->s1_lce + n, P.lce.begin());
@@ -252,6 +273,7 @@ static void make_plan(Handle *H, const uint8_t *rows, int64_t n, const wfs_instr
             const HostInstr &h = P.instr[P.order[j]];
             double e = h.type == 1 ? h.amp * P.lce[P.order[j]] * p.s1_detection_efficiency
                                    : (double)h.amp * P.scg[P.order[j]] * 1.1;
+            if (!P.opt_n.empty() && P.opt_n[P.order[j]] > 0) e = (double)P.opt_n[P.order[j]];   // supplied photons
             if (p.enable_pmt_afterpulses) e *= 1.1;
             ph += e;
             smp += std::min(e, (double)n_ch) * 450.0 * (p.detector_nt ? 1.5 : 1.0);
@@ -329,6 +351,11 @@ static GenCtx make_ctx(Frontend &F, uint64_t seed) {
     g.i_xo = F.has_xy ? F.b_ixo.as<double>() : nullptr;
     g.i_yo = F.has_xy ? F.b_iyo.as<double>() : nullptr;
     g.i_recoil = F.b_irecoil.as<int32_t>();
+    g.i_optfirst = F.has_opt ? F.b_ioptfirst.as<int64_t>() : nullptr;
+    g.i_optn = F.has_opt ? F.b_ioptn.as<int32_t>() : nullptr;
+    g.opt_ch = F.H->d_opt_ch.as<int32_t>();
+    g.opt_t = F.H->d_opt_t.as<int64_t>();
+    g.opt_cutoff = F.H->opt_cutoff;
     g.i_lrow = F.b_ilrow.as<int32_t>();
     g.i_dmean = F.b_dmean.as<double>(); g.i_dspread = F.b_dspread.as<double>();
     g.i_nemit = F.b_nemit.as<uint32_t>(); g.i_emitoff = F.b_emitoff.as<uint32_t>();
@@ -393,6 +420,7 @@ static void grow_instr(Frontend &F, int64_t n_new, int64_t n_old, cudaStream_t s
     g(F.b_igidx, 8); g(F.b_ilce, 8); g(F.b_iscg, 8); g(F.b_icy, 8); g(F.b_ipat, 4);
     g(F.b_dmean, 8); g(F.b_dspread, 8); g(F.b_nemit, 4); g(F.b_nhits, 8);
     g(F.b_ivd, 8); g(F.b_idl, 8); g(F.b_ixo, 8); g(F.b_iyo, 8); g(F.b_irecoil, 4); g(F.b_ilrow, 4);
+    g(F.b_ioptfirst, 8); g(F.b_ioptn, 4);
     F.b_emitoff.reserve_keep(4 * (size_t)(n_new + 1), 4 * (size_t)(n_old + 1), s);
     F.b_irun.reserve_keep(4 * (size_t)n_new, 0, s);
 }
@@ -533,6 +561,9 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     std::vector<uint64_t> h_gidx(nprim);
     std::vector<double> h_lce(nprim), h_scg(nprim), h_cy(nprim);
     std::vector<int32_t> h_recoil(nprim);
+    F.has_opt = !P.opt_n.empty();
+    std::vector<int64_t> h_optfirst(F.has_opt ? nprim : 0);
+    std::vector<int32_t> h_optn(F.has_opt ? nprim : 0);
     F.has_vd = !P.vd.empty(); F.has_dl = !P.dl.empty(); F.has_xy = !P.xo.empty();
     std::vector<double> h_vd(F.has_vd ? nprim : 0), h_dl(F.has_dl ? nprim : 0), h_xo(F.has_xy ? nprim : 0),
         h_yo(F.has_xy ? nprim : 0);
@@ -546,6 +577,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         h_gidx[j] = P.rng_id[gi];
         h_lce[j] = P.lce[gi]; h_scg[j] = P.scg[gi]; h_cy[j] = P.cy[gi];
         h_recoil[j] = h.recoil;
+        if (F.has_opt) { h_optfirst[j] = P.opt_first[gi]; h_optn[j] = P.opt_n[gi]; }
         if (F.has_vd) h_vd[j] = P.vd[gi];
         if (F.has_dl) h_dl[j] = P.dl[gi];
         if (F.has_xy) { h_xo[j] = P.xo[gi]; h_yo[j] = P.yo[gi]; }
@@ -577,6 +609,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     up(F.b_ilce, h_lce.data(), 8 * nprim); up(F.b_iscg, h_scg.data(), 8 * nprim);
     up(F.b_icy, h_cy.data(), 8 * nprim); up(F.b_ipat, h_pat.data(), 4 * nprim);
     up(F.b_irecoil, h_recoil.data(), 4 * nprim);
+    if (F.has_opt) { up(F.b_ioptfirst, h_optfirst.data(), 8 * nprim); up(F.b_ioptn, h_optn.data(), 4 * nprim); }
     if (F.has_vd) up(F.b_ivd, h_vd.data(), 8 * nprim);
     if (F.has_dl) up(F.b_idl, h_dl.data(), 8 * nprim);
     if (F.has_xy) { up(F.b_ixo, h_xo.data(), 8 * nprim); up(F.b_iyo, h_yo.data(), 8 * nprim); }
@@ -1162,7 +1195,7 @@ static void ensure_lanes(Handle *H, int n) {
 
 static void release_frontend_buffers(Frontend &F) {
     DevBuf *all[] = {&F.b_itype, &F.b_itime, &F.b_ix, &F.b_iy, &F.b_iz, &F.b_iamp, &F.b_igidx, &F.b_ilce,
-                     &F.b_iscg, &F.b_icy, &F.b_ipat, &F.b_ivd, &F.b_idl, &F.b_ixo, &F.b_iyo, &F.b_irecoil, &F.b_ilrow, &F.b_dmean, &F.b_dspread, &F.b_nemit, &F.b_emitoff,
+                     &F.b_iscg, &F.b_icy, &F.b_ipat, &F.b_ivd, &F.b_idl, &F.b_ixo, &F.b_iyo, &F.b_irecoil, &F.b_ilrow, &F.b_ioptfirst, &F.b_ioptn, &F.b_dmean, &F.b_dspread, &F.b_nemit, &F.b_emitoff,
                      &F.b_nhits, &F.b_acc, &F.b_cdf, &F.b_cdfok, &F.b_pattern, &F.b_et, &F.b_einstr,
                      &F.b_enph, &F.b_ephoff, &F.b_pht, &F.b_phch, &F.b_phgain, &F.b_phinstr, &F.b_phflags,
                      &F.b_phnap, &F.b_apoff, &F.b_picount, &F.b_pioff, &F.b_pecount, &F.b_peoff, &F.b_irun, &F.b_pcgroup,
@@ -1197,6 +1230,13 @@ static int run_plan(Handle *H, Plan &P, uint64_t seed, wfs_outputs *out, wfs_cou
                     PhotonDump *dump = nullptr) {
     if (!H->frontend) throw std::runtime_error("front-end tables missing (SPE table is required for wfs_simulate)");
     memset(counts, 0, sizeof(*counts));
+    if (P.n_opt > 0) {      // the caller's photon lists, resident for the whole call (all lanes read them)
+        H->d_opt_ch.reserve(sizeof(int32_t) * (size_t)P.n_opt);
+        H->d_opt_t.reserve(sizeof(int64_t) * (size_t)P.n_opt);
+        WFS_CUDA_CHECK(cudaMemcpy(H->d_opt_ch.p, P.opt_channels, sizeof(int32_t) * (size_t)P.n_opt, cudaMemcpyHostToDevice));
+        WFS_CUDA_CHECK(cudaMemcpy(H->d_opt_t.p, P.opt_timings, sizeof(int64_t) * (size_t)P.n_opt, cudaMemcpyHostToDevice));
+        H->opt_cutoff = P.opt_cutoff;
+    }
     const int64_t launches0 = H->launches.n;
     H->tstats.ns_copy = 0;
     H->tstats.ns_expand = 0;

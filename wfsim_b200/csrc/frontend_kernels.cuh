@@ -21,6 +21,13 @@ struct GenCtx {
     double *i_xo, *i_yo;          // observed xy (field distortion), or nullptr
     int32_t *i_recoil;
     int32_t *i_lrow;              // garfield luminescence: table row of the instruction
+    // externally supplied photons (wfs_instr_maps.opt_*): first list index / count per instruction
+    // (count 0: sampled as usual), the lists, the cutoff; all nullptr when the call has none
+    const int64_t *i_optfirst;
+    const int32_t *i_optn;
+    const int32_t *opt_ch;
+    const int64_t *opt_t;
+    int64_t opt_cutoff;
     double *i_dmean, *i_dspread;
     uint32_t *i_nemit, *i_emitoff;
     int64_t *i_nhits;
@@ -195,7 +202,10 @@ __global__ void k_instr(GenCtx g, wfs_params p, uint32_t i0, uint32_t i1) {
     Rng rng(g.seed, RS_INSTR, g.i_gidx[i], 0);
     uint32_t nemit = 0;
     int64_t nhits = 0;
-    if (type == 1) {
+    if (type == 1 && g.i_optn && g.i_optn[i] > 0) {      // photons supplied by the caller (rawdata.py:478-495)
+        nhits = g.i_optn[i];
+        nemit = 1u;
+    } else if (type == 1) {
         double ly = g.i_lce[i] / (1.0 + p.p_double_pe_emision) * p.s1_detection_efficiency;
         ly = fmin(fmax(ly, 0.0), 1.0);
         nhits = sample_binomial(amp, ly, rng.ud53());
@@ -298,8 +308,17 @@ k_photons(GenCtx g, wfs_params p, const double *gains, int n_ch, uint32_t n_emit
     float zs, zt;
     normal_pair(w1.v[0], w1.v[1], zs, zt);
     int64_t t = g.e_t[em];
+    const bool external = type == 1 && g.i_optn && g.i_optn[i] > 0;
+    if (external) {                                            // channel and time come from the lists
+        const int64_t k = g.i_optfirst[i] + ord;
+        const int64_t dt_k = g.opt_t[k];
+        ch = g.opt_ch[k];
+        if (dt_k < 0 || dt_k >= g.opt_cutoff || ch < 0 || ch >= n_ch) ch = -1;   // dropped (rawdata.py:484-487)
+        t += dt_k;
+    }
     const bool top = ch >= 0 && ch < p.n_top_pmts;
-    if (type == 1) {
+    if (external) {
+    } else if (type == 1) {
         if (p.s1_model_optical && g.s1_op_top && ch >= 0)      // s1.py:186-189, 241-260
             t += (int64_t)grid_interp2(top ? g.s1_op_top : g.s1_op_bottom, g.s1_op_nz, g.s1_op_nu, g.s1_op_z0,
                                        g.s1_op_z1, g.s1_op_u0, g.s1_op_u1, (double)g.i_z[i], u01_32(w2.v[1]));

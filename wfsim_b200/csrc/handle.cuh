@@ -22,6 +22,8 @@ struct Handle {
     void *staged_plan = nullptr;        // Plan of wfs_stage_instructions (frontend.cu)
     // staging for host-pointer calls
     DevBuf d_t, d_ch, d_gain, d_pc, d_pc_group, d_pc_rank, d_ix, d_records, d_groups;
+    DevBuf d_opt_ch, d_opt_t;           // externally supplied photons of the current wfs_simulate call
+    int64_t opt_cutoff = 0;
     // compact record transport (transport.cuh): expansion threads + the stage of wfs_simulate_photons
     HostPool *pool = nullptr;
     CompactStage cstage;

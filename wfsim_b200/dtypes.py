@@ -66,6 +66,12 @@ truth_extra_dtype = (
     + _TRUTH_TAIL)
 
 
+# strax_interface.py:44-45: optical (externally supplied photons) instructions carry the index range of
+# their photons in the channel / timing lists
+optical_extra_dtype = [(('first optical input index', '_first'), np.int32),
+                       (('last optical input index +1', '_last'), np.int32)]
+
+
 def extra_truth_dtype_per_pmt(n_pmt):
     """Truth layout; total/bottom split when `n_pmt` is falsy, per-PMT arrays otherwise."""
     if not n_pmt:

@@ -76,7 +76,8 @@ class InstrMaps(C.Structure):
     _fields_ = [('s1_lce', vp), ('s2_sc_gain', vp), ('s2_cy_extra', vp), ('pattern', vp),
                 ('pattern_row', vp), ('n_pattern_rows', i64), ('s2_sc_gain_default', f64),
                 ('rng_id', vp), ('drift_velocity', vp), ('diffusion_long', vp), ('x_obs', vp), ('y_obs', vp),
-                ('group_base', i64)]
+                ('group_base', i64), ('opt_first', vp), ('opt_last', vp), ('opt_channels', vp), ('opt_timings', vp),
+                ('n_opt', i64), ('opt_time_cutoff', i64)]
 
 
 class Outputs(C.Structure):

@@ -151,7 +151,7 @@ class Simulator:
         return out
 
     # -----------------------------------------------------------------------------------------
-    def _maps_struct(self, instructions, maps=None, rng_id=None, seed=0, group_base=0):
+    def _maps_struct(self, instructions, maps=None, rng_id=None, seed=0, group_base=0, optical=None):
         if maps is None:
             if self.resource is None or isinstance(self.resource, dict):
                 raise SimulatorError('simulate() needs a Resource (maps) -- pass resource= to Simulator')
@@ -168,6 +168,22 @@ class Simulator:
         m.n_pattern_rows = keep['pattern'].shape[0]
         m.s2_sc_gain_default = 0.0
         m.group_base = int(group_base)
+        if optical is not None:
+            # externally supplied photons (RawDataOptical, rawdata.py:461-495): optical = (first, last,
+            # channels, timings); `first` / `last` are the `_first` / `_last` columns of the instructions
+            first, last, channels, timings = optical
+            keep['opt_first'] = np.ascontiguousarray(first, np.int64)
+            keep['opt_last'] = np.ascontiguousarray(last, np.int64)
+            keep['opt_channels'] = np.ascontiguousarray(channels, np.int32)
+            keep['opt_timings'] = np.ascontiguousarray(timings, np.int64)
+            if len(keep['opt_first']) != len(instructions) or len(keep['opt_last']) != len(instructions):
+                raise ValueError('optical first / last need one entry per instruction')
+            if len(keep['opt_channels']) != len(keep['opt_timings']):
+                raise ValueError('optical channels and timings must have equal length')
+            m.opt_first, m.opt_last = _ptr(keep['opt_first']), _ptr(keep['opt_last'])
+            m.opt_channels, m.opt_timings = _ptr(keep['opt_channels']), _ptr(keep['opt_timings'])
+            m.n_opt = len(keep['opt_channels'])
+            m.opt_time_cutoff = int(self.config.get('nveto_time_max_cutoff', int(1e6)))
         for k in ('drift_velocity', 'diffusion_long', 'x_obs', 'y_obs'):
             if k in keep:
                 setattr(m, k, _ptr(keep[k]))
@@ -189,7 +205,7 @@ class Simulator:
         return c
 
     def simulate(self, instructions, seed=0, maps=None, cap_records=None, pinned=False, rng_id=None,
-                 per_pmt_truth=None, records_out=None, group_base=0):
+                 per_pmt_truth=None, records_out=None, group_base=0, optical=None):
         """Full path for one set of instructions (see wfs_simulate in the header).
 
         Returns dict(raw_records, raw_records_he, raw_records_aqmon, truth, groups); records of
@@ -202,11 +218,11 @@ class Simulator:
         if per_pmt_truth is None:
             per_pmt_truth = bool(self.config.get('per_pmt_truth', False))
         n_pmt = int(self.params.n_tpc_pmts)
-        instructions = np.ascontiguousarray(instructions)
+        instructions, optical = self._split_optical(instructions, optical)
         if instructions.dtype.itemsize != 70:
             raise ValueError('instructions must have the packed 70-byte instruction_dtype')
         n = len(instructions)
-        m, keep = self._maps_struct(instructions, maps, rng_id, seed=seed, group_base=group_base)
+        m, keep = self._maps_struct(instructions, maps, rng_id, seed=seed, group_base=group_base, optical=optical)
         counts = wlib.Counts()
         cap_rec = int(cap_records) if cap_records is not None else \
             (len(records_out) if records_out is not None else max(4096, 1500 * n))
@@ -275,6 +291,22 @@ class Simulator:
         res['_pinned'] = None
         return res
 
+    @staticmethod
+    def _split_optical(instructions, optical):
+        """Instructions with the optical extra columns (`_first`, `_last`, strax_interface.py:44-45) plus
+        optical=(channels, timings) -> plain 70-byte instructions + (first, last, channels, timings)."""
+        instructions = np.ascontiguousarray(instructions)
+        if optical is not None and len(optical) == 2:
+            if '_first' not in (instructions.dtype.names or ()):
+                raise ValueError("optical photons need instructions with the '_first' / '_last' columns")
+            optical = (instructions['_first'], instructions['_last'], optical[0], optical[1])
+        if instructions.dtype.names and '_first' in instructions.dtype.names:
+            plain = np.zeros(len(instructions), instruction_dtype)
+            for name in plain.dtype.names:
+                plain[name] = instructions[name]
+            instructions = plain
+        return instructions, optical
+
     def stage(self, instructions, maps=None):
         instructions = np.ascontiguousarray(instructions)
         m, keep = self._maps_struct(instructions, maps)
@@ -294,11 +326,11 @@ class Simulator:
     PHOTON_DUMP_DTYPE = np.dtype([('t', np.int64), ('gain', np.float64), ('channel', np.int32),
                                   ('instruction', np.int32), ('flags', np.int32), ('secondary', np.int32)])
 
-    def sample_stage(self, instructions, stage=0, seed=0, maps=None):
+    def sample_stage(self, instructions, stage=0, seed=0, maps=None, optical=None):
         """Front-end only: photons (stage 0) or emitters/electrons (stage 1) as a structured array
         (see wfs_sample_stage).  For the statistical parity tests."""
-        instructions = np.ascontiguousarray(instructions)
-        m, keep = self._maps_struct(instructions, maps, seed=seed)
+        instructions, optical = self._split_optical(instructions, optical)
+        m, keep = self._maps_struct(instructions, maps, seed=seed, optical=optical)
         n_out = C.c_int64()
         cap = 1 << 16
         while True:

@@ -18,7 +18,7 @@ import logging
 import numpy as np
 
 from . import config as wcfg
-from .dtypes import (RECORD_LENGTH, extra_truth_dtype_per_pmt, instruction_dtype, raw_record_dtype,
+from .dtypes import (RECORD_LENGTH, extra_truth_dtype_per_pmt, instruction_dtype, optical_extra_dtype, raw_record_dtype,
                      truth_extra_dtype)
 from .resource import Resource
 
@@ -33,7 +33,8 @@ except ImportError:
     HAVE_STRAX = False
 
 __all__ = ['instruction_dtype', 'truth_extra_dtype', 'extra_truth_dtype_per_pmt', 'ChunkRawRecords',
-           'SimulatorPlugin', 'RawRecordsFromFaxNT', 'instruction_from_csv', 'chunk_boundaries', 'ChunkClock']
+           'SimulatorPlugin', 'RawRecordsFromFaxNT', 'RawRecordsFromFaxOpticalNT', 'optical_extra_dtype',
+           'instruction_from_csv', 'chunk_boundaries', 'ChunkClock']
 
 
 def instruction_from_csv(filename):
@@ -97,6 +98,24 @@ def chunk_boundaries(config, t_min_instruction, groups, time_zero=None):
     return out
 
 
+def _with_optical_columns(truth, instructions, dtype):
+    """Truth rows of optical instructions get the `_first` / `_last` columns of the instruction they
+    describe (one Pulse call per instruction; matched on the copied instruction fields)."""
+    out = np.zeros(len(truth), dtype=dtype)
+    for n in truth.dtype.names:
+        out[n] = truth[n]
+    key = ('time', 'type', 'amp', 'event_number', 'x', 'y', 'z')
+    where = {}
+    for j, row in enumerate(instructions):
+        where.setdefault(tuple(row[k].item() for k in key), []).append(j)
+    for i, row in enumerate(truth):
+        js = where.get(tuple(row[k].item() for k in key))
+        if js:
+            j = js.pop(0) if len(js) > 1 else js[0]
+            out['_first'][i], out['_last'][i] = instructions['_first'][j], instructions['_last'][j]
+    return out
+
+
 class ChunkRawRecords(object):
     """Same protocol as the reference class: calling the object with the instructions returns a
     generator of dict(raw_records, raw_records_he, raw_records_aqmon, truth); `chunk_time_pre`
@@ -113,6 +132,11 @@ class ChunkRawRecords(object):
             if rawdata_generator is not None else Simulator(config, resource=resource, device=device)
         truth_per_n_pmts = self._n_channels if config.get('per_pmt_truth') else False
         self.truth_dtype = extra_truth_dtype_per_pmt(truth_per_n_pmts)
+        # externally supplied photons (ChunkRawRecords(..., rawdata_generator=RawDataOptical, channels=,
+        # timings=), strax_interface.py:726-729): the instructions then carry `_first` / `_last`
+        self.channels, self.timings = kwargs.get('channels'), kwargs.get('timings')
+        if self.channels is not None:
+            self.truth_dtype = optical_extra_dtype + self.truth_dtype
         self.seed = int(seed if seed is not None else (config.get('seed') or 0))
         self._finished = False
         self.chunk_time_pre = self.chunk_time = 0
@@ -170,8 +194,11 @@ class ChunkRawRecords(object):
             return res
 
         for i_part, idx in enumerate(parts):
+            optical = None if self.channels is None else (self.channels, self.timings)
             out = self.simulator.simulate(instructions[idx], seed=self.seed, rng_id=idx.astype(np.uint64),
-                                          group_base=n_groups)
+                                          group_base=n_groups, optical=optical)
+            if optical is not None:
+                out['truth'] = _with_optical_columns(out['truth'], instructions[idx], tdt)
             n_groups += len(out['groups'])
             for k in keys:
                 held[k].append(np.asarray(out[k]))
@@ -361,3 +388,27 @@ class RawRecordsFromFaxNT(SimulatorPlugin):
             end=self.sim.chunk_time,
             data=result[data_type],
             data_type=data_type) for data_type in self.provides}
+
+
+class RawRecordsFromFaxOpticalNT(RawRecordsFromFaxNT):
+    """Mirror of strax_interface.py:722-751: photons (channel, arrival time) come from outside -- G4 optical
+    output, neutron-veto style inputs -- and only the PMT stage (transit time, double photo-electrons, SPE
+    gains, afterpulses), the digitiser and the ZLE are simulated.  Set `instructions` (instruction_dtype +
+    optical_extra_dtype, `_first` / `_last` indexing the lists), `channels` and `timings` before setup();
+    reading the G4 files themselves (`read_optical`, uproot) is not part of this package."""
+
+    def _setup(self):
+        self.sim = ChunkRawRecords(self.config, device=self.device, channels=self.channels, timings=self.timings,
+                                   **(self.resource_overrides or {}))
+        self.sim_iter = self.sim(self.instructions)
+
+    def get_instructions(self):
+        if getattr(self, 'instructions', None) is None or getattr(self, 'channels', None) is None \
+                or getattr(self, 'timings', None) is None:
+            raise RuntimeError('optical input: set instructions (with _first/_last), channels and timings; '
+                               'reading G4 optical files needs uproot (third party)')
+
+    def infer_dtype(self):
+        dtype = super().infer_dtype()
+        dtype['truth'] = instruction_dtype + optical_extra_dtype + self._truth_dtype
+        return dtype
