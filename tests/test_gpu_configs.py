@@ -188,3 +188,40 @@ def test_group_local_order_with_afterpulses_and_secondaries(monkeypatch):
     ph = sim.sample_stage(inst, stage=0, seed=44)
     assert ((ph['flags'] >> 1) & 1).sum() > 100          # afterpulse photons are there
     sim.close()
+
+
+def test_c1_large_run_properties(monkeypatch):
+    """BASELINE config [1] at 2e4 events (a fifth of the bench size; 2.7e7 photons, 2.5e7 records, 6 GB):
+    size-independent properties instead of an oracle run -- every data type sorted by (time, channel),
+    fragments consistent, truth photon sum equal to the photons superposed, the same bytes from a
+    second run, and the same bytes when the device batches are cut differently."""
+    import zlib
+    from tests.golden.synth_instructions import c1_like
+    sim, cfg = make_sim()
+    inst = c1_like(20_000, seed=100)
+
+    def run():
+        out = sim.simulate(inst, seed=1)
+        c = dict(sim.last_counts)
+        rr = out['raw_records']
+        key = rr['time'] * 1024 + rr['channel']
+        assert (np.diff(key) >= 0).all()
+        assert (rr['length'] > 0).all() and (rr['length'] <= 110).all() and (rr['dt'] == cfg['sample_duration']).all()
+        first = rr[rr['record_i'] == 0]
+        assert (first['pulse_length'] >= first['length']).all()
+        # a record is full unless it is the last fragment of its pulse
+        assert ((rr['length'] == 110) | (rr['pulse_length'] - 110 * rr['record_i'].astype(np.int64) == rr['length'])).all()
+        assert out['truth']['n_photon'].sum() == c['n_photons']
+        assert len(out['truth']) == len(inst)
+        crc = zlib.crc32(rr.view(np.uint8)[:len(rr) * 244:1].tobytes()) if len(rr) < 4_000_000 else \
+            zlib.crc32(np.ascontiguousarray(rr[::17]).tobytes())
+        return crc, len(rr), int(rr['data'].astype(np.int64)[::101].sum()), c['n_batches']
+
+    a = run()
+    b = run()
+    assert a == b
+    monkeypatch.setenv('WFS_BATCH_SAMPLES', '300000000')
+    c = run()
+    assert c[3] > a[3] and c[:3] == a[:3]
+    assert a[1] > 2e7
+    sim.close()
