@@ -797,7 +797,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     g = make_ctx(F, seed);
     {
         // heavy instructions (S2s with 1e5..1e6 photons) are split over several CTAs
-        const unsigned ny = (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, max_instr_photons / 16384));
+        const unsigned ny = (unsigned)std::max<int64_t>(1, std::min<int64_t>(256, max_instr_photons / 8192));
         if (ny > 1) FLAUNCH(k_acc_init, div_up(ntot * A_COUNT, 256), 256, ntot * (int64_t)A_COUNT, F.b_acc.as<int64_t>());
         FLAUNCH(k_instr_truth, dim3((unsigned)ntot, ny), 128, g, H->cfg, (uint32_t)ntot, (uint32_t)n_ph, (uint32_t)n_ph);
     }

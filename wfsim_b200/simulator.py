@@ -18,20 +18,10 @@ def _ptr(a):
 
 
 def host_records(n, dtype=None):
-    """Uninitialised host array for `n` records on transparent huge pages where the kernel offers
-    them: the library's expansion threads touch every page of a fresh output array, and with 4 KiB
-    pages the page faults cost more than the writes (30 GB per 1e5 low-energy events)."""
-    import mmap
-    dtype = np.dtype(raw_record_dtype() if dtype is None else dtype)
-    nbytes = int(n) * dtype.itemsize
-    if nbytes < (64 << 20) or not hasattr(mmap, 'MADV_HUGEPAGE'):
-        return np.empty(int(n), dtype)
-    m = mmap.mmap(-1, nbytes)
-    try:
-        m.madvise(mmap.MADV_HUGEPAGE)
-    except (OSError, ValueError):
-        pass
-    return np.frombuffer(m, dtype=dtype, count=int(n))
+    """Uninitialised host array for `n` records.  (Asking for transparent huge pages here was tried:
+    the GPU boxes of this pool do not grant them and every page fault of a madvise(MADV_HUGEPAGE) range
+    then also pays for a compaction attempt -- 0.47 s instead of 0.34 s for a 1.9 GB output.)"""
+    return np.empty(int(n), np.dtype(raw_record_dtype() if dtype is None else dtype))
 
 
 class PinnedArray:
