@@ -98,6 +98,37 @@ def chunk_boundaries(config, t_min_instruction, groups, time_zero=None):
     return out
 
 
+def _pieces(instructions, config, piece_max, time_zero=None):
+    """Index arrays of the pieces the run is simulated in: contiguous in signal time, cut only at quiet
+    gaps (sharding.shard_instructions explains which), first where the chunk clock will cut -- so that the
+    records of a chunk come from one library call and are handed on without a copy -- then further down to
+    at most ~piece_max instructions."""
+    from .sharding import signal_time
+    n = len(instructions)
+    st = signal_time(instructions, config['drift_velocity_liquid'])
+    order = np.argsort(st, kind='stable')
+    sts = st[order]
+    min_gap = int(config.get('right_raw_extension', 100000))
+    if config.get('enable_electron_afterpulses', False):
+        min_gap += int(config.get('tpc_length', 150) / config['drift_velocity_liquid']) + 100000
+    cut_ok = np.flatnonzero(np.diff(sts) > min_gap) + 1
+    cuts = set()
+    if len(cut_ok):
+        rext, cksz = int(config['right_raw_extension']), int(config['chunk_size'] * 1e9)
+        t0 = (time_zero - rext) if time_zero else int(np.min(instructions['time'])) - rext
+        for t_cut in np.arange(t0 + cksz, sts[-1], max(cksz, 1)):
+            j = np.searchsorted(cut_ok, np.searchsorted(sts, t_cut + rext, side='right'))
+            if j < len(cut_ok):
+                cuts.add(int(cut_ok[j]))
+        edges = [0] + sorted(cuts) + [n]
+        for a, b in zip(edges[:-1], edges[1:]):            # pieces that are still too big
+            for k in range(1, -(-(b - a) // piece_max)):
+                j = int(np.argmin(np.abs(cut_ok - (a + k * (b - a) // -(-(b - a) // piece_max)))))
+                if a < cut_ok[j] < b:
+                    cuts.add(int(cut_ok[j]))
+    return [p for p in np.split(order, sorted(cuts)) if len(p)]
+
+
 def _with_optical_columns(truth, instructions, dtype):
     """Truth rows of optical instructions get the `_first` / `_last` columns of the instruction they
     describe (one Pulse call per instruction; matched on the copied instruction fields)."""
@@ -153,9 +184,8 @@ class ChunkRawRecords(object):
         # bounded by one piece (config 'b200_piece_instructions', default 40000) instead of the whole run.
         # Philox identities are the instruction indices and the noise draws are keyed by the running
         # group number, so the records do not depend on how the run is cut.
-        from .sharding import shard_instructions
         piece = max(int(cfg.get('b200_piece_instructions', 40000)), 1)
-        parts = [p for p in shard_instructions(instructions, -(-len(instructions) // piece), cfg) if len(p)]
+        parts = _pieces(instructions, cfg, piece, time_zero)
         clock = ChunkClock(cfg, np.min(instructions['time']), time_zero)
         keys = ('raw_records', 'raw_records_he', 'raw_records_aqmon')
         held = {k: [] for k in keys}        # per data type: arrays of the pieces not yet delivered, in time order
