@@ -83,6 +83,19 @@ class ChunkClock:
                     break
         return out
 
+    def peek(self, t_next):
+        """Every group still to come starts after `t_next` [ns]: if the first of them is going to close the
+        current chunk, close it now (same bounds: they depend on the groups seen so far only) so that its
+        records can leave before the next piece is simulated."""
+        if t_next <= self.ct + self.rext:
+            return []
+        if (self.cur_right + 1) * self.dt > self.ct:      # cur_right is what last_right will be by then
+            self.ct += (self.cur_right + 1) * self.dt - self.ct
+        out = [(self.pre, self.ct)]
+        self.pre = self.ct
+        self.ct += self.cksz
+        return out
+
     def finish(self):
         self.last_right = self.cur_right
         self.ct = max((self.last_right + 1) * self.dt, self.pre + self.dt)
@@ -96,6 +109,27 @@ def chunk_boundaries(config, t_min_instruction, groups, time_zero=None):
     out = clock.feed(groups)
     out.append(clock.finish())
     return out
+
+
+class _ArenaPool:
+    """Record arenas of one chunker.  take(n) hands out an arena of at least n records: one of its own
+    that nobody else references any more (the consumer dropped every chunk view into it), else a new one."""
+
+    def __init__(self):
+        self.arenas = []
+
+    def take(self, n, dtype):
+        import sys
+        # an arena is free when the list slot is the only reference left (+ the call argument)
+        free = [i for i in range(len(self.arenas)) if sys.getrefcount(self.arenas[i]) <= 2]
+        fit = [i for i in free if len(self.arenas[i]) >= n]
+        if fit:
+            chosen = self.arenas[fit[0]]
+            self.arenas = [x for i, x in enumerate(self.arenas) if i == fit[0] or i not in free]
+            return chosen
+        self.arenas = [x for i, x in enumerate(self.arenas) if i not in free]      # too small: let them go
+        self.arenas.append(np.empty(int(n), dtype))
+        return self.arenas[-1]
 
 
 def _pieces(instructions, config, piece_max, time_zero=None):
@@ -169,6 +203,7 @@ class ChunkRawRecords(object):
         if self.channels is not None:
             self.truth_dtype = optical_extra_dtype + self.truth_dtype
         self.seed = int(seed if seed is not None else (config.get('seed') or 0))
+        self._arena_pool = _ArenaPool()
         self._finished = False
         self.chunk_time_pre = self.chunk_time = 0
 
@@ -188,22 +223,49 @@ class ChunkRawRecords(object):
         parts = _pieces(instructions, cfg, piece, time_zero)
         clock = ChunkClock(cfg, np.min(instructions['time']), time_zero)
         keys = ('raw_records', 'raw_records_he', 'raw_records_aqmon')
-        held = {k: [] for k in keys}        # per data type: arrays of the pieces not yet delivered, in time order
+        side = {k: [] for k in keys[1:]}    # he / aqmon records not yet delivered (few): arrays in time order
         tdt = np.dtype(instruction_dtype + self.truth_dtype)
+        rdt = raw_record_dtype(samples_per_record=samples_per_record)
         held_truth = None
         n_groups = 0
-        empty = np.zeros(0, raw_record_dtype(samples_per_record=samples_per_record))
+        empty = np.zeros(0, rdt)
+        # TPC records live in an ARENA: every piece is simulated straight behind the records still held
+        # (records_out = arena[used:]), chunks are views arena[a0:a0 + stop] -- no concatenation, no copy.
+        # Arenas whose views the consumer has dropped are recycled (already-touched pages: the first-touch
+        # page faults of fresh memory cost ten times the simulation).
+        pool = self._arena_pool
+        arena, a0, used = None, 0, 0
+        per_instr = None                     # records per instruction, learnt from the pieces
+
+        # one arena per chunk: it is changed right after a chunk has left (little to carry over), sized for
+        # the instructions of one chunk; should the estimate prove too small it is doubled on the way
+        span = float(np.max(instructions['time']) - np.min(instructions['time'])) + 1.0
+        instr_per_chunk = int(len(instructions) * min(1.0, cfg['chunk_size'] * 1e9 / span)) + 1
+
+        def room_for(n_instr, fresh=False):
+            nonlocal arena, a0, used
+            need = int((per_instr or 700.0) * n_instr * 1.3) + 65536
+            if arena is not None and not fresh and len(arena) - used >= need:
+                return
+            held_n = used - a0
+            new = pool.take(held_n + need if fresh else max(2 * held_n + need, 2 * need), rdt)
+            if held_n:
+                new[:held_n] = arena[a0:used]
+            arena, a0, used = new, 0, held_n
 
         def cut(ct, last):
             """Records and truth rows up to chunk time `ct` leave the held arrays."""
-            nonlocal held_truth
+            nonlocal held_truth, a0
             res = {}
-            for k in keys:
-                # the pieces are disjoint in time and each is sorted by (time, channel): one copy per chunk
-                parts_k = [a for a in held[k] if len(a)]
+            rec = arena[a0:used] if arena is not None else empty
+            stop = len(rec) if last else int(np.searchsorted(rec['time'], ct, side='right'))
+            res['raw_records'] = rec[:stop]
+            a0 += stop
+            for k in keys[1:]:
+                parts_k = [x for x in side[k] if len(x)]
                 rec = empty if not parts_k else parts_k[0] if len(parts_k) == 1 else np.concatenate(parts_k)
                 stop = len(rec) if last else int(np.searchsorted(rec['time'], ct, side='right'))
-                res[k], held[k] = rec[:stop], [rec[stop:]]
+                res[k], side[k] = rec[:stop], [rec[stop:]]
             # truth rows of this chunk (strax_interface.py:458-483)
             truth = held_truth
             tfp = truth['t_first_photon']
@@ -223,20 +285,43 @@ class ChunkRawRecords(object):
                 return dict(raw_records=res['raw_records'], truth=res['truth'])
             return res
 
+        delivered = True
+        from .sharding import signal_time
+        next_start = [signal_time(instructions[p[:1]], cfg['drift_velocity_liquid'])[0] for p in parts]
         for i_part, idx in enumerate(parts):
             optical = None if self.channels is None else (self.channels, self.timings)
+            room_for(max(instr_per_chunk, len(idx)) if delivered else len(idx), fresh=delivered and arena is not None)
+            delivered = False
             out = self.simulator.simulate(instructions[idx], seed=self.seed, rng_id=idx.astype(np.uint64),
-                                          group_base=n_groups, optical=optical)
+                                          group_base=n_groups, optical=optical, records_out=arena[used:])
             if optical is not None:
                 out['truth'] = _with_optical_columns(out['truth'], instructions[idx], tdt)
             n_groups += len(out['groups'])
-            for k in keys:
-                held[k].append(np.asarray(out[k]))
+            rr = out['raw_records']
+            in_arena = len(rr) == 0 or \
+                arena.ctypes.data <= rr.ctypes.data < arena.ctypes.data + arena.nbytes
+            if not in_arena:                                     # the estimate was too small: the call used
+                per_instr = max(per_instr or 0.0, len(rr) / max(len(idx), 1))        # a buffer of its own
+                room_for(len(idx))
+                arena[used:used + len(rr)] = rr
+            else:
+                per_instr = max(0.7 * (per_instr or 0.0), len(rr) / max(len(idx), 1))
+                for k in keys[1:]:          # they sit behind the TPC records in the arena: move them out
+                    out[k] = np.array(out[k])
+            used += len(rr)
+            for k in keys[1:]:
+                side[k].append(np.asarray(out[k]))
             held_truth = out['truth'] if held_truth is None or not len(held_truth) \
                 else np.concatenate([held_truth, out['truth']])
-            for pre, ct in clock.feed(out['groups']):
+            done = clock.feed(out['groups'])
+            if i_part + 1 < len(parts) and n_groups:
+                # nothing of the next piece can start before its first signal time minus the longest
+                # backward reach of a pulse (left margin, trigger window, diffusion of the drift)
+                done += clock.peek(int(next_start[i_part + 1]) - 200000)
+            for pre, ct in done:
                 self.chunk_time_pre, self.chunk_time = pre, ct
                 yield deliver(cut(ct, last=False))
+                delivered = True
         self.chunk_time_pre, self.chunk_time = clock.finish()
         self._finished = True
         yield deliver(cut(self.chunk_time, last=True))
