@@ -128,7 +128,10 @@ class _ArenaPool:
             self.arenas = [x for i, x in enumerate(self.arenas) if i == fit[0] or i not in free]
             return chosen
         self.arenas = [x for i, x in enumerate(self.arenas) if i not in free]      # too small: let them go
-        self.arenas.append(np.empty(int(n), dtype))
+        # generous, quantised sizes: the estimates move a little from chunk to chunk and an arena that is
+        # released and allocated again pays for unmapping and for the page faults of fresh memory
+        quantum = 1 << 22
+        self.arenas.append(np.empty((int(n * 1.25) // quantum + 1) * quantum, dtype))
         return self.arenas[-1]
 
 
