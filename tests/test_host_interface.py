@@ -150,3 +150,30 @@ def test_plugin_set_config_and_check_instructions():
     r['time'] += 500
     with pytest.raises(RuntimeError, match='insufficient spacing'):
         q._sort_check(r)
+
+
+def test_chunk_clock_fed_in_pieces_with_peek_gives_the_reference_bounds():
+    """ChunkClock: feeding the groups piece by piece and closing chunks early with peek() (a lower bound on
+    where the next piece starts) gives the bounds of the one-pass bookkeeping, i.e. the reference's
+    (tests/golden/chunks.json), however the run is cut."""
+    from wfsim_b200.strax_interface import ChunkClock
+    with open(os.path.join(GOLDEN, 'chunks.json')) as f:
+        cases = json.load(f)
+    rng = np.random.default_rng(5)
+    for name, c in cases.items():
+        cfg = load_c0_config()
+        cfg['chunk_size'] = c['chunk_size']
+        groups = [tuple(g) for g in c['groups']]
+        for trial in range(20):
+            cuts = sorted(set(rng.integers(1, max(len(groups), 2), rng.integers(0, 6)).tolist()))
+            pieces = [groups[a:b] for a, b in zip([0] + cuts, cuts + [len(groups)])]
+            clock = ChunkClock(cfg, c['t_min_instruction'])
+            got = []
+            for k, piece in enumerate(pieces):
+                got += clock.feed(piece)
+                if k + 1 < len(pieces) and pieces[k + 1]:
+                    # the next piece starts at its first group's left edge; any earlier time is a valid bound
+                    t_next = pieces[k + 1][0][0] * cfg['sample_duration'] - int(rng.integers(0, 50000))
+                    got += clock.peek(t_next)
+            got.append(clock.finish())
+            assert [list(b) for b in got] == c['bounds'], (name, cuts)
