@@ -48,7 +48,7 @@ def workload(n_events, seed):
 
 def ncu_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu capture (None if there is none)."""
-    path = os.path.join(ROOT, 'profiles', f'r1o_{kernel}_ncu.json')
+    path = os.path.join(ROOT, 'profiles', f'r1p_{kernel}_ncu.json')
     try:
         with open(path) as f:
             return float(json.load(f)['dram_bytes_per_launch'])
@@ -321,7 +321,7 @@ def run_b200(args, rank, world, local_rank):
                      'frac': (digi_bytes / (digi_ms / 1e3) / 1e9 / peak) if digi_ms > 0 else None,
                      # DRAM bytes per launch (read + write) of the committed ncu --set full capture
                      'traffic': ncu_traffic('k_digitize'),
-                     'traffic_source': 'profiles/r1o_k_digitize_ncu.json (one launch = one device batch of the same '
+                     'traffic_source': 'profiles/r1p_k_digitize_ncu.json (one launch = one device batch of the same '
                                        'size class as here; dram__bytes_read.sum + dram__bytes_write.sum)',
                      'launches_per_step': int(c['n_batches']),
                      'algorithmic_bytes_per_launch': int(digi_bytes / max(int(c['n_batches']), 1)),
