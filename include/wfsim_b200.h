@@ -135,6 +135,10 @@ typedef struct wfs_tables {
     const int32_t *gf_t;            /* [gf_rows][gf_cols] emission times */
     const double *gf_x;             /* [gf_rows] distance to the anode wire of each row */
     int32_t gf_rows, gf_cols;
+    /* S2 'garfield_gas_gap' luminescence (resource.s2_luminescence_gg['timing_inv_cdf'], s2.py:411-483):
+     * inverse CDFs of the excitation time, one row per tabulated gas gap */
+    const double *gg_cdf;           /* [gg_rows][gg_len] */
+    int32_t gg_rows, gg_len;
     /* PMT pattern maps on regular grids (resource.s1_pattern_map over (x, y, z), s1.py:148;
      * resource.s2_pattern_map over the observed (x, y), s2.py:637-645), evaluated on the device for
      * every instruction whose wfs_instr_maps.pattern_row is negative: multilinear interpolation with
@@ -188,6 +192,12 @@ typedef struct wfs_instr_maps {
     const int64_t *opt_timings;             /* [n_opt] ns relative to the instruction time */
     int64_t n_opt;
     int64_t opt_time_cutoff;
+    /* 'garfield_gas_gap' luminescence (s2.py:460-483), per S2-like instruction from
+     * resource.garfield_gas_gap_map at the observed position: the two rows of gg_cdf the gas gap lies
+     * between (np.digitize - 1 and the row above, clipped; python's negative index included) and
+     * (gas gap - gas_gap[row]) / row spacing.  Required when s2_luminescence_model == 2. */
+    const int32_t *gg_lo_row, *gg_hi_row;
+    const double *gg_frac;
 } wfs_instr_maps;
 
 typedef struct wfs_counts {

@@ -225,6 +225,9 @@ def main():
     if 'models' in which:
         from tests.golden import make_golden_models
         make_golden_models.main(ref, c0_config)
+    if 'gg' in which:
+        from tests.golden import make_golden_gg
+        make_golden_gg.main(ref, c0_config)
 
 
 if __name__ == '__main__':

@@ -61,3 +61,21 @@ class FieldDependencies:
     def diffusion_longitudinal_map(self, z, xy):
         r = np.sqrt(xy[:, 0] ** 2 + xy[:, 1] ** 2)
         return self.m(np.array([r, z]).T, map_name='diffusion')
+
+
+def garfield_gas_gap_table():
+    """resource.s2_luminescence_gg stand-in (load_resource.py:286-290): inverse CDFs of the excitation
+    time [ns] on 10 gas gaps 0.1 mm apart (s2.py:411-483); the last entries are the 'strange tail' the
+    reference does not sample from."""
+    gas_gap = np.round(np.linspace(0.24, 0.33, 10), 3)
+    u = np.linspace(0.0, 1.0, 203)
+    rows = [(300.0 + 4000.0 * (g - 0.24)) * (-np.log(1.0 - 0.995 * u)) ** 0.8 + 50.0 * g for g in gas_gap]
+    return dict(gas_gap=gas_gap, timing_inv_cdf=np.stack(rows))
+
+
+class GasGapMap:
+    """resource.garfield_gas_gap_map stand-in: gas gap [cm] growing with the radius."""
+
+    def __call__(self, xy, **kw):
+        xy = np.asarray(xy, dtype=np.float64)
+        return 0.243 + 0.085 * np.hypot(xy[:, 0], xy[:, 1]) / 70.0

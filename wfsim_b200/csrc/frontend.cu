@@ -155,6 +155,8 @@ struct BatchSpec {
 
 struct Plan {
     int64_t group_base = 0;      // wfs_instr_maps.group_base
+    std::vector<int32_t> gg_lo, gg_hi;   // 'garfield_gas_gap' luminescence rows / fraction per instruction
+    std::vector<double> gg_frac;
     std::vector<int64_t> opt_first;   // externally supplied photons: first list index / count per instruction
     std::vector<int32_t> opt_n;       // (empty: the call has none)
     const int32_t *opt_channels = nullptr;
@@ -207,6 +209,18 @@ static void make_plan(Handle *H, const uint8_t *rows, int64_t n, const wfs_instr
     P.cy.assign((size_t)n, 1.0);
     P.patrow.assign((size_t)n, 0);
     P.group_base = maps ? maps->group_base : 0;
+    P.gg_lo.clear(); P.gg_hi.clear(); P.gg_frac.clear();
+    if (p.s2_luminescence_model == 2) {
+        if (!maps || !maps->gg_lo_row || !maps->gg_hi_row || !maps->gg_frac)
+            throw std::runtime_error("s2_luminescence_model 'garfield_gas_gap' needs gg_lo_row / gg_hi_row / gg_frac per instruction");
+        const int rows = H->frontend ? H->frontend->gg_rows : 0;
+        P.gg_lo.assign(maps->gg_lo_row, maps->gg_lo_row + n);
+        P.gg_hi.assign(maps->gg_hi_row, maps->gg_hi_row + n);
+        P.gg_frac.assign(maps->gg_frac, maps->gg_frac + n);
+        for (int64_t i = 0; i < n; i++)
+            if (P.gg_lo[i] < 0 || P.gg_lo[i] >= rows || P.gg_hi[i] < 0 || P.gg_hi[i] >= rows)
+                throw std::runtime_error("gg_lo_row / gg_hi_row out of range");
+    }
     if (maps && maps->opt_first && maps->opt_last && maps->n_opt > 0) {
         if (!maps->opt_channels || !maps->opt_timings) throw std::runtime_error("opt_channels / opt_timings missing");
         P.opt_first.assign((size_t)n, 0);
@@ -351,6 +365,11 @@ static GenCtx make_ctx(Frontend &F, uint64_t seed) {
     g.i_xo = F.has_xy ? F.b_ixo.as<double>() : nullptr;
     g.i_yo = F.has_xy ? F.b_iyo.as<double>() : nullptr;
     g.i_recoil = F.b_irecoil.as<int32_t>();
+    g.gg_cdf = F.gg_cdf; g.gg_rows = F.gg_rows; g.gg_len = F.gg_len;
+    g.i_gglo = F.has_gg ? F.b_igglo.as<int32_t>() : nullptr;
+    g.i_gghi = F.has_gg ? F.b_igghi.as<int32_t>() : nullptr;
+    g.i_ggfrac = F.has_gg ? F.b_iggfrac.as<double>() : nullptr;
+    g.i_ggmean = F.has_gg ? F.b_iggmean.as<double>() : nullptr;
     g.i_optfirst = F.has_opt ? F.b_ioptfirst.as<int64_t>() : nullptr;
     g.i_optn = F.has_opt ? F.b_ioptn.as<int32_t>() : nullptr;
     g.opt_ch = F.H->d_opt_ch.as<int32_t>();
@@ -421,6 +440,7 @@ static void grow_instr(Frontend &F, int64_t n_new, int64_t n_old, cudaStream_t s
     g(F.b_dmean, 8); g(F.b_dspread, 8); g(F.b_nemit, 4); g(F.b_nhits, 8);
     g(F.b_ivd, 8); g(F.b_idl, 8); g(F.b_ixo, 8); g(F.b_iyo, 8); g(F.b_irecoil, 4); g(F.b_ilrow, 4);
     g(F.b_ioptfirst, 8); g(F.b_ioptn, 4);
+    g(F.b_igglo, 4); g(F.b_igghi, 4); g(F.b_iggfrac, 8); g(F.b_iggmean, 8);
     F.b_emitoff.reserve_keep(4 * (size_t)(n_new + 1), 4 * (size_t)(n_old + 1), s);
     F.b_irun.reserve_keep(4 * (size_t)n_new, 0, s);
 }
@@ -465,6 +485,13 @@ static void generate(Handle *H, Frontend &F, cudaStream_t s, uint64_t seed, int6
     if (p1 >= (int64_t(1) << 30)) throw std::runtime_error("photon batch too large; lower WFS_BATCH_PHOTONS");
     grow_photons(F, std::max<int64_t>(p1, 1), p0, s);
     g = make_ctx(F, seed);
+    if (p1 > p0 && p.s2_luminescence_model == 2 && F.has_gg) {
+        // 'garfield_gas_gap': the mean excitation time of every instruction is subtracted (s2.py:450-451)
+        const int ny = (int)std::max<int64_t>(1, std::min<int64_t>(64, (p1 - p0) / (std::max<int64_t>(i1 - i0, 1) * 4096)));
+        F.b_ggpartial.reserve(sizeof(double) * (size_t)(i1 - i0) * ny);
+        FLAUNCH(k_gg_sum, dim3((unsigned)(i1 - i0), (unsigned)ny), 128, g, (uint32_t)i0, (uint32_t)i1, F.b_ggpartial.as<double>());
+        FLAUNCH(k_gg_mean, div_up(i1 - i0, 128), 128, g, (uint32_t)i0, (uint32_t)i1, ny, F.b_ggpartial.as<double>());
+    }
     if (p1 > p0)
         FLAUNCH(k_photons, div_up(p1 - p0, 256), 256, g, p, H->cfg.gains, p.n_tpc_pmts, (uint32_t)e1,
                 (uint32_t)p0, (uint32_t)p1);
@@ -561,6 +588,9 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     std::vector<uint64_t> h_gidx(nprim);
     std::vector<double> h_lce(nprim), h_scg(nprim), h_cy(nprim);
     std::vector<int32_t> h_recoil(nprim);
+    F.has_gg = !P.gg_lo.empty();
+    std::vector<int32_t> h_gglo(F.has_gg ? nprim : 0), h_gghi(F.has_gg ? nprim : 0);
+    std::vector<double> h_ggfrac(F.has_gg ? nprim : 0);
     F.has_opt = !P.opt_n.empty();
     std::vector<int64_t> h_optfirst(F.has_opt ? nprim : 0);
     std::vector<int32_t> h_optn(F.has_opt ? nprim : 0);
@@ -578,6 +608,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         h_lce[j] = P.lce[gi]; h_scg[j] = P.scg[gi]; h_cy[j] = P.cy[gi];
         h_recoil[j] = h.recoil;
         if (F.has_opt) { h_optfirst[j] = P.opt_first[gi]; h_optn[j] = P.opt_n[gi]; }
+        if (F.has_gg) { h_gglo[j] = P.gg_lo[gi]; h_gghi[j] = P.gg_hi[gi]; h_ggfrac[j] = P.gg_frac[gi]; }
         if (F.has_vd) h_vd[j] = P.vd[gi];
         if (F.has_dl) h_dl[j] = P.dl[gi];
         if (F.has_xy) { h_xo[j] = P.xo[gi]; h_yo[j] = P.yo[gi]; }
@@ -610,6 +641,10 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     up(F.b_icy, h_cy.data(), 8 * nprim); up(F.b_ipat, h_pat.data(), 4 * nprim);
     up(F.b_irecoil, h_recoil.data(), 4 * nprim);
     if (F.has_opt) { up(F.b_ioptfirst, h_optfirst.data(), 8 * nprim); up(F.b_ioptn, h_optn.data(), 4 * nprim); }
+    if (F.has_gg) {
+        up(F.b_igglo, h_gglo.data(), 4 * nprim); up(F.b_igghi, h_gghi.data(), 4 * nprim);
+        up(F.b_iggfrac, h_ggfrac.data(), 8 * nprim);
+    }
     if (F.has_vd) up(F.b_ivd, h_vd.data(), 8 * nprim);
     if (F.has_dl) up(F.b_idl, h_dl.data(), 8 * nprim);
     if (F.has_xy) { up(F.b_ixo, h_xo.data(), 8 * nprim); up(F.b_iyo, h_yo.data(), 8 * nprim); }
@@ -1159,6 +1194,7 @@ static void clone_tables(const Frontend &a, Frontend &b) {
     b.s1_op_z0 = a.s1_op_z0; b.s1_op_z1 = a.s1_op_z1; b.s1_op_u0 = a.s1_op_u0; b.s1_op_u1 = a.s1_op_u1;
     b.s2_op_u0 = a.s2_op_u0; b.s2_op_u1 = a.s2_op_u1;
     b.gf_t = a.gf_t; b.gf_x = a.gf_x; b.gf_rows = a.gf_rows; b.gf_cols = a.gf_cols;
+    b.gg_cdf = a.gg_cdf; b.gg_rows = a.gg_rows; b.gg_len = a.gg_len;
     b.s1_pat = a.s1_pat; b.s2_pat = a.s2_pat;
 }
 
@@ -1195,7 +1231,8 @@ static void ensure_lanes(Handle *H, int n) {
 
 static void release_frontend_buffers(Frontend &F) {
     DevBuf *all[] = {&F.b_itype, &F.b_itime, &F.b_ix, &F.b_iy, &F.b_iz, &F.b_iamp, &F.b_igidx, &F.b_ilce,
-                     &F.b_iscg, &F.b_icy, &F.b_ipat, &F.b_ivd, &F.b_idl, &F.b_ixo, &F.b_iyo, &F.b_irecoil, &F.b_ilrow, &F.b_ioptfirst, &F.b_ioptn, &F.b_dmean, &F.b_dspread, &F.b_nemit, &F.b_emitoff,
+                     &F.b_iscg, &F.b_icy, &F.b_ipat, &F.b_ivd, &F.b_idl, &F.b_ixo, &F.b_iyo, &F.b_irecoil, &F.b_ilrow, &F.b_ioptfirst, &F.b_ioptn,
+                     &F.b_igglo, &F.b_igghi, &F.b_iggfrac, &F.b_iggmean, &F.b_ggpartial, &F.b_dmean, &F.b_dspread, &F.b_nemit, &F.b_emitoff,
                      &F.b_nhits, &F.b_acc, &F.b_cdf, &F.b_cdfok, &F.b_pattern, &F.b_et, &F.b_einstr,
                      &F.b_enph, &F.b_ephoff, &F.b_pht, &F.b_phch, &F.b_phgain, &F.b_phinstr, &F.b_phflags,
                      &F.b_phnap, &F.b_apoff, &F.b_picount, &F.b_pioff, &F.b_pecount, &F.b_peoff, &F.b_irun, &F.b_pcgroup,
@@ -1412,7 +1449,10 @@ void Handle::frontend_init(const wfs_tables &t) {
         F->gf_x = upload_table(t.gf_x, (size_t)t.gf_rows, owned);
         F->gf_rows = t.gf_rows; F->gf_cols = t.gf_cols;
     } else if (p.s2_luminescence_model == 2) {
-        throw std::runtime_error("s2_luminescence_model 'garfield_gas_gap' is not built yet (DESIGN.md, next rows)");
+        if (!t.gg_cdf || t.gg_rows < 1 || t.gg_len < 3)
+            throw std::runtime_error("s2_luminescence_gg model not found");   // s2.py:471
+        F->gg_cdf = upload_table(t.gg_cdf, (size_t)t.gg_rows * t.gg_len, owned);
+        F->gg_rows = t.gg_rows; F->gg_len = t.gg_len;
     } else if (p.s2_luminescence_model == 0 && F->lum_len <= 0) {
         throw std::runtime_error("s2_luminescence_model 'simple' with enable_gas_gap_warping needs per-position gas gaps: not built yet; set enable_gas_gap_warping=False");
     }

@@ -90,10 +90,13 @@ struct Frontend {
     int32_t *gf_t = nullptr;
     double *gf_x = nullptr;
     int32_t gf_rows = 0, gf_cols = 0;
+    double *gg_cdf = nullptr;       // 'garfield_gas_gap' luminescence table
+    int32_t gg_rows = 0, gg_len = 0;
     Primitives prim;
     // workspaces
     DevBuf b_itype, b_itime, b_ix, b_iy, b_iz, b_iamp, b_igidx, b_ilce, b_iscg, b_icy, b_ipat,
-        b_ivd, b_idl, b_ixo, b_iyo, b_irecoil, b_ilrow, b_ioptfirst, b_ioptn,
+        b_ivd, b_idl, b_ixo, b_iyo, b_irecoil, b_ilrow, b_ioptfirst, b_ioptn, b_igglo, b_igghi, b_iggfrac, b_iggmean,
+        b_ggpartial,
         b_dmean, b_dspread, b_nemit, b_emitoff, b_nhits, b_acc, b_cdf, b_cdfok, b_pattern,
         b_et, b_einstr, b_enph, b_ephoff, b_pht, b_phch, b_phgain, b_phinstr, b_phflags, b_phnap,
         b_apoff, b_picount, b_pioff, b_pecount, b_peoff, b_irun, b_pcgroup, b_pcrank, b_trig, b_records, b_records2,
@@ -101,6 +104,7 @@ struct Frontend {
     CompactStage cstage[2];     // compact record transport: batch k ships while batch k+1 runs
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_ready = nullptr;
     bool copy_pending[2] = {false, false};
+    bool has_gg = false;        // the current call carries the per-instruction gas-gap rows
     bool has_opt = false;       // the current call supplies photons (wfs_instr_maps.opt_*)
     int64_t cdf_rows = -1;      // pattern CDF rows resident in b_cdf (few-row case only) and their hash
     uint64_t cdf_hash = 0;

@@ -21,6 +21,12 @@ struct GenCtx {
     double *i_xo, *i_yo;          // observed xy (field distortion), or nullptr
     int32_t *i_recoil;
     int32_t *i_lrow;              // garfield luminescence: table row of the instruction
+    // 'garfield_gas_gap' luminescence (s2.py:411-483): table, per-instruction rows / fraction, and the
+    // per-instruction mean of the drawn excitation times (filled by k_gg_sum + k_gg_mean)
+    const double *gg_cdf;
+    int32_t gg_rows, gg_len;
+    int32_t *i_gglo, *i_gghi;
+    double *i_ggfrac, *i_ggmean;
     // externally supplied photons (wfs_instr_maps.opt_*): first list index / count per instruction
     // (count 0: sampled as usual), the lists, the cutoff; all nullptr when the call has none
     const int64_t *i_optfirst;
@@ -282,6 +288,57 @@ __device__ __forceinline__ double interp_table(const double *xp, const double *f
     return slope * (x - xp[j]) + fp[j];
 }
 
+// Excitation time of one photon in the 'garfield_gas_gap' model (s2.py:441-449): the inverse CDF is the
+// linear blend of the two rows around the local gas gap, sampled at U(0, len - 2) with linear
+// interpolation between neighbouring entries.
+__device__ __forceinline__ double gg_time(const GenCtx &g, int lo_row, int hi_row, double frac, uint32_t u32) {
+    const double s = u01_32(u32) * (double)(g.gg_len - 2);
+    const double fl = floor(s);
+    const int k0 = (int)fl, k1 = (int)ceil(s);
+    const double *lo = g.gg_cdf + (int64_t)lo_row * g.gg_len, *hi = g.gg_cdf + (int64_t)hi_row * g.gg_len;
+    const double t1 = (hi[k0] - lo[k0]) * frac + lo[k0];
+    const double t2 = (hi[k1] - lo[k1]) * frac + lo[k1];
+    return (t2 - t1) * (s - fl) + t1;
+}
+
+// Sum of the excitation times of the photons of every S2-like instruction, in a FIXED order (thread-strided
+// partial sums, shuffle tree, warps in order), so that the mean subtracted in k_photons (s2.py:450-451) --
+// and with it every photon time -- is reproducible.  grid (instructions, slices); one partial per slice.
+__global__ void __launch_bounds__(128)
+k_gg_sum(GenCtx g, uint32_t i0, uint32_t i1, double *partial) {
+    __shared__ double sm[4];
+    const uint32_t i = i0 + blockIdx.x;
+    if (i >= i1) return;
+    const uint32_t ny = gridDim.y, yi = blockIdx.y;
+    double acc = 0.0;
+    if (g.i_type[i] != 1) {
+        const uint32_t q0 = g.e_phoff[g.i_emitoff[i]], q1 = g.e_phoff[g.i_emitoff[i + 1]];
+        const uint64_t n = q1 - q0;
+        const uint32_t a = (uint32_t)(n * yi / ny), b = (uint32_t)(n * (yi + 1) / ny);
+        const int lo = g.i_gglo[i], hi = g.i_gghi[i];
+        const double frac = g.i_ggfrac[i];
+        const uint64_t gidx = g.i_gidx[i];
+        for (uint32_t ord = a + threadIdx.x; ord < b; ord += blockDim.x) {
+            const Philox4 w0 = philox4x32(g.seed, RS_PHOTON, gidx, ord * 3u);
+            acc += gg_time(g, lo, hi, frac, w0.v[1]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) partial[(int64_t)(i - i0) * ny + yi] = ((sm[0] + sm[1]) + sm[2]) + sm[3];
+}
+
+__global__ void k_gg_mean(GenCtx g, uint32_t i0, uint32_t i1, int ny, const double *partial) {
+    const uint32_t i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i1) return;
+    double s = 0.0;
+    for (int y = 0; y < ny; y++) s += partial[(int64_t)(i - i0) * ny + y];
+    const uint32_t n = g.e_phoff[g.i_emitoff[i + 1]] - g.e_phoff[g.i_emitoff[i]];
+    g.i_ggmean[i] = n ? s / (double)n : 0.0;
+}
+
 // Per photon: channel (s1.py:138-159 / s2.py:616-682), arrival time (s1.py:162-238 /
 // s2.py:504-557, pulse.py:321-341), then the PMT stage (pulse.py:53-56,76-79,95-103).
 __global__ void __launch_bounds__(256)
@@ -342,6 +399,8 @@ k_photons(GenCtx g, wfs_params p, const double *gains, int n_ch, uint32_t n_emit
         else if (p.s2_luminescence_model == 1 && g.gf_rows > 0) {   // s2.py:405-409
             const int col = (int)(((uint64_t)w0.v[1] * (uint32_t)g.gf_cols) >> 32);
             t += (int64_t)g.gf_t[(int64_t)g.i_lrow[i] * g.gf_cols + col] - (int64_t)p.gf_avgt;
+        } else if (p.s2_luminescence_model == 2 && g.gg_cdf) {      // s2.py:441-451, astype(int64) at :532
+            t += (int64_t)(gg_time(g, g.i_gglo[i], g.i_gghi[i], g.i_ggfrac[i], w0.v[1]) - g.i_ggmean[i]);
         }
         const double delay = u01_32(w0.v[2]) < p.singlet_fraction_gas ? p.singlet_lifetime_gas
                                                                       : p.triplet_lifetime_gas;
@@ -617,6 +676,7 @@ k_photoionization(GenCtx g, wfs_params p, uint32_t n_prim, int fill, uint32_t *c
                     g.i_cy[o] = g.i_cy[i];
                     g.i_pat[o] = g.i_pat[i];
                     g.i_recoil[o] = g.i_recoil[i];
+                    if (g.i_gglo) { g.i_gglo[o] = g.i_gglo[i]; g.i_gghi[o] = g.i_gghi[i]; g.i_ggfrac[o] = g.i_ggfrac[i]; }
                     if (g.i_vd) g.i_vd[o] = g.i_vd[i];
                     if (g.i_dl) g.i_dl[o] = g.i_dl[i];
                     if (g.i_xo) { g.i_xo[o] = r * cos(ang); g.i_yo[o] = r * sin(ang); }
@@ -679,6 +739,7 @@ k_photoelectric(GenCtx g, wfs_params p, uint32_t n_prim, int fill, uint32_t *cou
         g.i_cy[o] = g.i_cy[i];
         g.i_pat[o] = g.i_pat[i];
         g.i_recoil[o] = g.i_recoil[i];
+        if (g.i_gglo) { g.i_gglo[o] = g.i_gglo[i]; g.i_gghi[o] = g.i_gghi[i]; g.i_ggfrac[o] = g.i_ggfrac[i]; }
         if (g.i_vd) g.i_vd[o] = g.i_vd[i];
         if (g.i_dl) g.i_dl[o] = g.i_dl[i];
         if (g.i_xo) { g.i_xo[o] = r * cos(ang); g.i_yo[o] = r * sin(ang); }

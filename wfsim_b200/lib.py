@@ -67,6 +67,7 @@ class Tables(C.Structure):
         ('s2_op_top', vp), ('s2_op_bottom', vp), ('s2_op_nu', i32),
         ('s2_op_u0', f64), ('s2_op_u1', f64),
         ('gf_t', vp), ('gf_x', vp), ('gf_rows', i32), ('gf_cols', i32),
+        ('gg_cdf', vp), ('gg_rows', i32), ('gg_len', i32),
         ('s1_pat_grid', vp), ('s1_pat_n', i32 * 3), ('s1_pat_npmt', i32), ('s1_pat_lo', f64 * 3), ('s1_pat_hi', f64 * 3),
         ('s2_pat_grid', vp), ('s2_pat_n', i32 * 2), ('s2_pat_npmt', i32), ('s2_pat_pad', i32),
         ('s2_pat_lo', f64 * 2), ('s2_pat_hi', f64 * 2)]
@@ -77,7 +78,7 @@ class InstrMaps(C.Structure):
                 ('pattern_row', vp), ('n_pattern_rows', i64), ('s2_sc_gain_default', f64),
                 ('rng_id', vp), ('drift_velocity', vp), ('diffusion_long', vp), ('x_obs', vp), ('y_obs', vp),
                 ('group_base', i64), ('opt_first', vp), ('opt_last', vp), ('opt_channels', vp), ('opt_timings', vp),
-                ('n_opt', i64), ('opt_time_cutoff', i64)]
+                ('n_opt', i64), ('opt_time_cutoff', i64), ('gg_lo_row', vp), ('gg_hi_row', vp), ('gg_frac', vp)]
 
 
 class Outputs(C.Structure):

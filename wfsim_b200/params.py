@@ -208,6 +208,13 @@ def build_tables(cfg, resource=None):
         tt = t.set('gf_t', tt, np.int32)
         t.set('gf_x', lum['x'], np.float64)
         t.struct.gf_rows, t.struct.gf_cols = tt.shape
+    # garfield luminescence per gas gap (s2.py:411-483)
+    if cfg.get('s2_luminescence_model', 'simple') == 'garfield_gas_gap':
+        gg = get('s2_luminescence_gg')
+        assert gg is not None, 's2_luminescence_gg model not found'          # s2.py:471
+        cdf = t.set('gg_cdf', np.asarray(gg['timing_inv_cdf']), np.float64)
+        assert cdf.ndim == 2 and cdf.shape[1] >= 3 and cdf.shape[0] == len(gg['gas_gap'])
+        t.struct.gg_rows, t.struct.gg_len = cdf.shape
     # pattern maps on regular grids: evaluated on the device (resource.GridMap with map 'map')
     for key, nd in (('s1', 3), ('s2', 2)):
         m = get(key + '_pattern_map')

@@ -106,7 +106,8 @@ class Resource:
                      'uniform_to_pmt_ap', 'uniform_to_ele_ap',
                      # load_resource.py:262-330: timing splines, luminescence tables, field maps
                      's1_optical_propagation_spline', 's2_optical_propagation_spline', 's2_luminescence',
-                     'fdc_3d', 'fd_comsol', 'diffusion_longitudinal_map', 'drift_velocity_scaling'):
+                     'fdc_3d', 'fd_comsol', 'diffusion_longitudinal_map', 'drift_velocity_scaling',
+                     's2_luminescence_gg', 'garfield_gas_gap_map'):
             if name in overrides:
                 setattr(self, name, overrides[name])
         if not hasattr(self, 'drift_velocity_scaling'):
@@ -222,6 +223,19 @@ def evaluate_instruction_maps(config, resource, instructions, seed=0, device_pat
             dl = np.full(n, float(config['diffusion_constant_longitudinal']))
             dl[is_s2] = d
             out['diffusion_long'] = dl
+    if config.get('s2_luminescence_model', 'simple') == 'garfield_gas_gap' and is_s2.any():
+        # s2.py:460-483: the excitation-time inverse CDF is interpolated between the two tabulated gas gaps
+        # around the local one (np.digitize - 1: below the first gap python's index -1 picks the LAST row)
+        gg = resource.s2_luminescence_gg
+        gaps = np.asarray(gg['gas_gap'], dtype=np.float64)
+        n_rows = len(gaps)
+        cont = np.asarray(resource.garfield_gas_gap_map(pos_obs[is_s2]), dtype=np.float64).reshape(-1)
+        draw = np.digitize(cont, gaps) - 1
+        lo = np.zeros(n, np.int32); hi = np.zeros(n, np.int32); frac = np.zeros(n)
+        lo[is_s2] = np.where(draw < 0, draw + n_rows, draw)
+        hi[is_s2] = np.clip(draw + 1, 0, n_rows - 1)
+        frac[is_s2] = (cont - gaps[draw]) / (gaps[1] - gaps[0])
+        out['gg_lo_row'], out['gg_hi_row'], out['gg_frac'] = lo, hi, frac
     # patterns: constant maps share one row per signal type
     s1m, s2m = getattr(resource, 's1_pattern_map', None), getattr(resource, 's2_pattern_map', None)
     rows, row_of = [], np.zeros(n, np.int32)

@@ -147,7 +147,8 @@ class Simulator:
                 raise SimulatorError('simulate() needs a Resource (maps) -- pass resource= to Simulator')
             maps = evaluate_instruction_maps(self.config, self.resource, instructions, seed=seed)
         keep = {k: np.ascontiguousarray(v, dtype=(np.float32 if k == 'pattern' else
-                                                   np.int32 if k == 'pattern_row' else np.float64))
+                                                   np.int32 if k in ('pattern_row', 'gg_lo_row', 'gg_hi_row')
+                                                   else np.float64))
                 for k, v in maps.items()}
         m = wlib.InstrMaps()
         m.s1_lce = _ptr(keep['s1_lce'])
@@ -174,7 +175,7 @@ class Simulator:
             m.opt_channels, m.opt_timings = _ptr(keep['opt_channels']), _ptr(keep['opt_timings'])
             m.n_opt = len(keep['opt_channels'])
             m.opt_time_cutoff = int(self.config.get('nveto_time_max_cutoff', int(1e6)))
-        for k in ('drift_velocity', 'diffusion_long', 'x_obs', 'y_obs'):
+        for k in ('drift_velocity', 'diffusion_long', 'x_obs', 'y_obs', 'gg_lo_row', 'gg_hi_row', 'gg_frac'):
             if k in keep:
                 setattr(m, k, _ptr(keep[k]))
         if rng_id is not None:
