@@ -9,7 +9,13 @@ from tests.test_gpu_stochastic import make_sim, group_of_photons
 from tests.test_gpu_configs import check_records_sorted_and_consistent
 from wfsim_b200.dtypes import instruction_dtype
 
-sim, cfg = make_sim()
+if os.environ.get('FUZZ_AP'):        # PMT afterpulses + photo-ionisation secondaries
+    from tests.test_gpu_configs import make_sim as make_sim_res
+    from tests.golden.synth_tables import EleApHist, pmt_ap_tables
+    sim, cfg = make_sim_res(dict(uniform_to_pmt_ap=pmt_ap_tables(494), uniform_to_ele_ap=EleApHist()),
+                            enable_pmt_afterpulses=True, enable_electron_afterpulses=True)
+else:
+    sim, cfg = make_sim()
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 n_iter = int(sys.argv[2]) if len(sys.argv) > 2 else 150
 bad = 0
@@ -26,7 +32,8 @@ for it in range(n_iter):
     inst['local_field'] = 82.0
     inst['event_number'] = np.arange(n)
     inst = inst[inst['amp'] > 0]
-    os.environ['WFS_BATCH_INSTRUCTIONS'] = str(int(rng.choice([3, 7, 400000])))
+    # forced batch cuts are a documented deviation once secondaries exist: keep the default there
+    os.environ['WFS_BATCH_INSTRUCTIONS'] = str(int(rng.choice([3, 7, 400000]))) if not os.environ.get('FUZZ_AP') else '400000'
     try:
         out = sim.simulate(inst, seed=it)
         check_records_sorted_and_consistent(out, cfg)
@@ -35,15 +42,24 @@ for it in range(n_iter):
             continue
         ph = sim.sample_stage(inst, stage=0, seed=it)
         ph = ph[ph['channel'] >= 0]
-        assert out['truth']['n_photon'].sum() == len(ph), (out['truth']['n_photon'].sum(), len(ph))
+        prim = ph[(ph['flags'] >> 1) & 1 == 0]
+        assert out['truth']['n_photon'].sum() == len(prim), (out['truth']['n_photon'].sum(), len(prim))
         if it % 3 == 0 and len(ph) and len(out['groups']):
-            pcall = ph['instruction'] * 2 + ((ph['flags'] >> 1) & 1)
+            g_of_ph = group_of_photons(ph, out['groups'], cfg)
+            # Pulse-call identity: (primary instruction | secondary cluster = its group) x afterpulse flag
+            base = np.where((ph['flags'] & 4) != 0, 10_000_000 + g_of_ph, ph['instruction'])
+            pcall = base * 2 + ((ph['flags'] >> 1) & 1)
             uniq, pc = np.unique(pcall, return_inverse=True)
             group_of = np.zeros(len(uniq), np.int32)
-            group_of[pc] = group_of_photons(ph, out['groups'][out['groups']['n_intervals'] >= 0], cfg) if False else \
-                group_of_photons(ph, out['groups'], cfg)
+            group_of[pc] = g_of_ph
             want = orc.simulate_photons(cfg, pc.astype(np.int32), ph['channel'], ph['t'], ph['gain'], group_of)
             if out['raw_records'].tobytes() != want['raw_records'].tobytes():
+                if os.environ.get('FUZZ_AP'):
+                    # with secondaries the Pulse-call identity is only approximated here (all type-4 photons of a
+                    # group = one call; the scheduler makes one call per instruction cluster): piled-up
+                    # secondaries can legitimately differ.  The exact AP + PI case is tests/test_gpu_afterpulse_plugin.py
+                    print('unverified (approximate Pulse-call reconstruction) at iteration', it, flush=True)
+                    continue
                 bad += 1
                 print('MISMATCH at iteration', it, len(inst), len(ph), len(out['raw_records']), len(want['raw_records']), flush=True)
     except Exception as e:      # noqa

@@ -266,6 +266,19 @@ class Simulator:
                     o += br[b, k]
             res = dict(zip(('raw_records', 'raw_records_he', 'raw_records_aqmon'),
                            (np.concatenate(p) for p in parts)))
+        # Device batches are cut at quiet gaps, so their records follow each other in time.  Only when the
+        # stream has no quiet gap within twice the batch budget (far beyond physical TPC rates) is a cut
+        # forced, and delayed secondaries of one batch may then lie behind the start of the next: restore
+        # the (time, channel) order the consumer relies on (strax_interface.py:453, 622-640).
+        if nb > 1:
+            starts = np.cumsum(br, axis=0)
+            for k, name in enumerate(('raw_records', 'raw_records_he', 'raw_records_aqmon')):
+                r = res[name]
+                cuts = starts[:-1, k]
+                cuts = cuts[(cuts > 0) & (cuts < len(r))]
+                if len(cuts) and (r['time'][cuts] < r['time'][cuts - 1]).any():
+                    order = np.lexsort((r['channel'], r['time']))
+                    res[name] = r[order]
         truth = truth[:counts.n_truth]
         if per_pmt_truth:
             full = np.zeros(len(truth), truth_dtype(n_pmt))
