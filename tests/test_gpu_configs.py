@@ -225,3 +225,21 @@ def test_c1_large_run_properties(monkeypatch):
     assert c[3] > a[3] and c[:3] == a[:3]
     assert a[1] > 2e7
     sim.close()
+
+
+def test_forced_batch_cuts_keep_the_records_sorted(monkeypatch):
+    """A dense stream with photo-ionisation secondaries and a batch budget of three instructions: cuts are
+    forced where no quiet gap exists, delayed secondaries of one batch reach behind the start of the next,
+    and simulate() hands the records out in (time, channel) order all the same."""
+    sim, cfg = make_sim(dict(uniform_to_pmt_ap=pmt_ap_tables(494), uniform_to_ele_ap=EleApHist()),
+                        enable_pmt_afterpulses=True, enable_electron_afterpulses=True)
+    inst = c0_like(60, seed=23, event_rate=3000.0, e_range=(1, 8))      # one event every 333 us: clusters, but no quiet gap
+    monkeypatch.setenv('WFS_BATCH_INSTRUCTIONS', '3')
+    out = sim.simulate(inst, seed=2)
+    assert sim.last_counts['n_batches'] > 5
+    check_records_sorted_and_consistent(out, cfg)
+    monkeypatch.delenv('WFS_BATCH_INSTRUCTIONS')
+    one = sim.simulate(inst, seed=2)
+    assert sim.last_counts['n_batches'] == 1
+    check_records_sorted_and_consistent(one, cfg)
+    sim.close()
