@@ -276,7 +276,7 @@ int wfs_simulate_photons(void *handle, int64_t n_photons, const int64_t *t_ns, c
     if (d_groups)
         WFS_CUDA_CHECK(cudaMemcpyAsync(groups, d_groups, sizeof(wfs_group_info) * n_groups, cudaMemcpyDeviceToHost, s));
     WFS_CUDA_CHECK(cudaEventRecord(H->ev_d, s));
-    WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+    WFS_CUDA_CHECK(stream_sync(s));
     H->cstage.job.wait();
     float ms;
     WFS_CUDA_CHECK(cudaEventElapsedTime(&ms, H->ev_a, H->ev_b)); counts->ms_h2d = ms;

@@ -1279,7 +1279,7 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
                pulse_win_.as<uint32_t>(), win_first_pulse_.as<uint32_t>(), winkey.as<uint32_t>(), scal);
         WFS_CUDA_CHECK(cudaMemcpyAsync(h_scalars_, scal, sizeof(int64_t) * S_COUNT,
                                        cudaMemcpyDeviceToHost, stream_));
-        WFS_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        WFS_CUDA_CHECK(stream_sync(stream_));
         if (h_scalars_[S_ERR]) { res.error = (int)h_scalars_[S_ERR]; return; }
         res.n_valid_photons = h_scalars_[S_NVALID];
         np = h_scalars_[S_NPULSES];
@@ -1317,7 +1317,7 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
                                        cudaMemcpyDeviceToHost, stream_));
         WFS_CUDA_CHECK(cudaMemcpyAsync(&tot, win_scan_.as<uint64_t>() + nwt, sizeof(uint64_t),
                                        cudaMemcpyDeviceToHost, stream_));
-        WFS_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        WFS_CUDA_CHECK(stream_sync(stream_));
         if (h_scalars_[S_ERR]) { res.error = (int)h_scalars_[S_ERR]; return; }
         n_tiles = (int64_t)(uint32_t)tot;
         n_slots = (int64_t)(tot >> 32);
@@ -1373,7 +1373,7 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
         WFS_CUDA_CHECK(cudaMemcpyAsync(&nrec32, itv_rec0_.as<uint32_t>() + n_slots, sizeof(uint32_t),
                                        cudaMemcpyDeviceToHost, stream_));
         WFS_CUDA_CHECK(cudaMemcpyAsync(h_scalars_, scal, sizeof(int64_t) * S_COUNT, cudaMemcpyDeviceToHost, stream_));
-        WFS_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        WFS_CUDA_CHECK(stream_sync(stream_));
         res.n_records = nrec32;
         rec_seg_max = h_scalars_[S_RECSEG_MAX];
         rec_groups_disjoint = h_scalars_[S_GROUPS_OVERLAP] == 0;
@@ -1424,7 +1424,7 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
     WFS_CUDA_CHECK(cudaEventRecord(evp_[6], stream_));
     WFS_CUDA_CHECK(cudaMemcpyAsync(h_scalars_, scal, sizeof(int64_t) * S_COUNT,
                                    cudaMemcpyDeviceToHost, stream_));
-    WFS_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    WFS_CUDA_CHECK(stream_sync(stream_));
     WFS_CUDA_CHECK(cudaGetLastError());
     {
         const bool full = nw > 0 && nrec > 0 && nrec <= cap_records;

@@ -65,6 +65,10 @@ struct LaunchCounter {
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Wait for the work queued on a stream: cudaStreamSynchronize (spinning), or with WFS_BLOCKING_SYNC=1 a
+// sleep on a blocking event (for hosts with very few cores per GPU; slower everywhere it was measured).
+cudaError_t stream_sync(cudaStream_t s);
+
 constexpr int kSegSortMax = 8192;   // items per segment of Primitives::segment_sort_pairs
 
 // ---------------------------------------------------------------------------------------------

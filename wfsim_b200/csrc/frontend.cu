@@ -460,7 +460,7 @@ static void generate(Handle *H, Frontend &F, cudaStream_t s, uint64_t seed, int6
     F.prim.exclusive_scan_u32(g.i_nemit, g.i_emitoff, i1, true);
     uint32_t tot;
     WFS_CUDA_CHECK(cudaMemcpyAsync(&tot, g.i_emitoff + i1, 4, cudaMemcpyDeviceToHost, s));
-    WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+    WFS_CUDA_CHECK(stream_sync(s));
     const int64_t e0 = n_emit, e1 = tot;
     if (e1 >= (int64_t(1) << 31)) throw std::runtime_error("emitter batch too large");
     F.b_et.reserve_keep(8 * (size_t)std::max<int64_t>(e1, 1), 8 * (size_t)e0, s);
@@ -479,7 +479,7 @@ static void generate(Handle *H, Frontend &F, cudaStream_t s, uint64_t seed, int6
                 F.b_scal.as<uint32_t>());
         WFS_CUDA_CHECK(cudaMemcpyAsync(&max_ph, F.b_scal.p, 4, cudaMemcpyDeviceToHost, s));
     }
-    WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+    WFS_CUDA_CHECK(stream_sync(s));
     if (max_instr_photons) *max_instr_photons = std::max<int64_t>(*max_instr_photons, max_ph);
     const int64_t p0 = n_ph, p1 = tot;
     if (p1 >= (int64_t(1) << 30)) throw std::runtime_error("photon batch too large; lower WFS_BATCH_PHOTONS");
@@ -710,7 +710,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
             F.prim.exclusive_scan_u32(F.b_pecount.as<uint32_t>(), F.b_peoff.as<uint32_t>(), nprim, true);
             WFS_CUDA_CHECK(cudaMemcpyAsync(&nsec_pe, F.b_peoff.as<uint32_t>() + nprim, 4, cudaMemcpyDeviceToHost, s));
         }
-        if (do_pi || do_pe) WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (do_pi || do_pe) WFS_CUDA_CHECK(stream_sync(s));
         const int64_t nsec = (int64_t)nsec_pi + nsec_pe;
         if (nsec > 0) {
             ntot = nprim + nsec;
@@ -736,7 +736,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
             down(sec_z.data(), F.b_iz.as<float>() + nprim, 4 * (size_t)nsec);
             down(sec_amp.data(), F.b_iamp.as<int32_t>() + nprim, 4 * (size_t)nsec);
             down(sec_type.data(), F.b_itype.as<int32_t>() + nprim, 4 * (size_t)nsec);
-            WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+            WFS_CUDA_CHECK(stream_sync(s));
             d_parent.release();
             generate(H, F, s, seed, nprim, ntot, n_emit, n_ph, &max_instr_photons);   // pass B
         }
@@ -751,7 +751,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         F.prim.exclusive_scan_u32(g.ap_off, g.ap_off, n_ph, true);
         uint32_t tot;
         WFS_CUDA_CHECK(cudaMemcpyAsync(&tot, g.ap_off + n_ph, 4, cudaMemcpyDeviceToHost, s));
-        WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+        WFS_CUDA_CHECK(stream_sync(s));
         n_ap = tot;
         if (n_ap > 0) {
             grow_photons(F, n_ph + n_ap, n_ph, s);
@@ -774,7 +774,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
             WFS_CUDA_CHECK(cudaMemcpyAsync(ch.data(), F.b_phch.p, 4 * m, cudaMemcpyDeviceToHost, s));
             WFS_CUDA_CHECK(cudaMemcpyAsync(in_.data(), F.b_phinstr.p, 4 * m, cudaMemcpyDeviceToHost, s));
             WFS_CUDA_CHECK(cudaMemcpyAsync(fl.data(), F.b_phflags.p, m, cudaMemcpyDeviceToHost, s));
-            WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+            WFS_CUDA_CHECK(stream_sync(s));
             for (int64_t q = 0; q < m; q++) {
                 if (base + q < d.cap) {
                     uint8_t *r = d.out + (base + q) * 32;
@@ -810,7 +810,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
             WFS_CUDA_CHECK(cudaMemcpyAsync(t.data(), F.b_et.p, 8 * n_emit, cudaMemcpyDeviceToHost, s));
             WFS_CUDA_CHECK(cudaMemcpyAsync(in_.data(), F.b_einstr.p, 4 * n_emit, cudaMemcpyDeviceToHost, s));
             WFS_CUDA_CHECK(cudaMemcpyAsync(np_.data(), F.b_enph.p, 4 * n_emit, cudaMemcpyDeviceToHost, s));
-            WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+            WFS_CUDA_CHECK(stream_sync(s));
             for (int64_t q = 0; q < n_emit; q++) {
                 if (base + q < d.cap) {
                     uint8_t *r = d.out + (base + q) * 32;
@@ -846,7 +846,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
                 F.b_phstart.as<uint32_t>());
         WFS_CUDA_CHECK(cudaMemcpyAsync(ph_start.data(), F.b_phstart.p, 4 * ph_start.size(), cudaMemcpyDeviceToHost, s));
     }
-    WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+    WFS_CUDA_CHECK(stream_sync(s));
     float ms_front = 0;
     cudaEventElapsedTime(&ms_front, L.ev_c, L.ev_d);
     const auto host_t0 = std::chrono::steady_clock::now();
@@ -1051,7 +1051,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         WFS_CUDA_CHECK(cudaMemcpyAsync(pmt_cnt.data(), F.b_pmtcnt.p, sizeof(int32_t) * pmt_cnt.size(), cudaMemcpyDeviceToHost, s));
         WFS_CUDA_CHECK(cudaMemcpyAsync(pmt_area.data(), F.b_pmtarea.p, sizeof(int64_t) * pmt_area.size(), cudaMemcpyDeviceToHost, s));
     }
-    WFS_CUDA_CHECK(cudaStreamSynchronize(s));
+    WFS_CUDA_CHECK(stream_sync(s));
     // truth rows of this batch (rawdata.py:313-375), one per Pulse call
     struct RunSum { int64_t sum[A_COUNT]; bool row; };
     std::vector<RunSum> rsum((size_t)nruns);
@@ -1314,8 +1314,8 @@ static int run_plan(Handle *H, Plan &P, uint64_t seed, wfs_outputs *out, wfs_cou
     for (int li = 0; li < n_lanes; li++)
         if (failure[li]) {
             for (int lj = 0; lj < n_lanes; lj++) {   // drain before reporting
-                cudaStreamSynchronize(H->lanes[lj]->stream);
-                const bool copies_ok = cudaStreamSynchronize(H->lanes[lj]->copy_stream) == cudaSuccess;
+                stream_sync(H->lanes[lj]->stream);
+                const bool copies_ok = stream_sync(H->lanes[lj]->copy_stream) == cudaSuccess;
                 H->lanes[lj]->F->copy_pending[0] = H->lanes[lj]->F->copy_pending[1] = false;
                 for (CompactStage &cs : H->lanes[lj]->F->cstage) {
                     if (copies_ok) cs.job.wait(); else cs.job.abandon();
@@ -1329,8 +1329,8 @@ static int run_plan(Handle *H, Plan &P, uint64_t seed, wfs_outputs *out, wfs_cou
     }
     WFS_CUDA_CHECK(cudaEventRecord(H->ev_b, s));
     for (int li = 0; li < n_lanes; li++) {
-        WFS_CUDA_CHECK(cudaStreamSynchronize(H->lanes[li]->stream));
-        WFS_CUDA_CHECK(cudaStreamSynchronize(H->lanes[li]->copy_stream));
+        WFS_CUDA_CHECK(stream_sync(H->lanes[li]->stream));
+        WFS_CUDA_CHECK(stream_sync(H->lanes[li]->copy_stream));
         H->lanes[li]->F->copy_pending[0] = H->lanes[li]->F->copy_pending[1] = false;
         for (CompactStage &cs : H->lanes[li]->F->cstage) cs.job.wait();   // expansion into the caller's array
     }

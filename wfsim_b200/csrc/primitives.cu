@@ -8,6 +8,31 @@
 
 namespace wfs {
 
+static bool blocking_sync_mode() {
+    // measured on a 4-GPU box with 8 cores per rank: sleeping on a blocking event costs more (144 ms per
+    // step) than the spinning waits take from the other ranks (119 ms): off unless asked for
+    if (const char *e = getenv("WFS_BLOCKING_SYNC")) return atoi(e) != 0;
+    return false;
+}
+
+cudaError_t stream_sync(cudaStream_t s) {
+    static const bool blocking = blocking_sync_mode();
+    if (!blocking) return cudaStreamSynchronize(s);
+    // one blocking event per (thread, device)
+    thread_local cudaEvent_t ev[16] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 16) return cudaStreamSynchronize(s);
+    if (!ev[dev]) {
+        e = cudaEventCreateWithFlags(&ev[dev], cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    e = cudaEventRecord(ev[dev], s);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ev[dev]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // scan: 3-phase (block reduce, recursive scan of block sums, block scan + offset)
 // ---------------------------------------------------------------------------------------------
