@@ -203,8 +203,8 @@ def test_plugin_compute_loop_and_chunks():
         p2.check_instructions()
 
 
-@pytest.mark.parametrize('noise', [False, True])
-def test_chunker_streams_the_run_piece_by_piece(noise):
+@pytest.mark.parametrize('noise,he', [(False, False), (True, False), (False, True)])
+def test_chunker_streams_the_run_piece_by_piece(noise, he):
     """ChunkRawRecords simulates the run in pieces of `b200_piece_instructions` instructions (bounded
     host memory) and yields chunks as they complete: same chunks, records and truth as the whole run
     in one piece -- with noise too (the noise draw is keyed by the running group number)."""
@@ -212,7 +212,8 @@ def test_chunker_streams_the_run_piece_by_piece(noise):
     from wfsim_b200.strax_interface import ChunkRawRecords
     uniq, row = spe()
     extra = {}
-    cfg = load_c0_config(chunk_size=1.5, enable_noise=noise)
+    cfg = load_c0_config(chunk_size=1.5, enable_noise=noise,
+                         **({'high_energy_deamplification_factor': 2.0} if he else {}))
     if noise:
         extra['noise_data'] = np.round(np.random.default_rng(8).normal(0, 2, (8192, 494)))
     res = Resource(cfg, spe_ppf=uniq, spe_row=row, **extra)
@@ -235,3 +236,4 @@ def test_chunker_streams_the_run_piece_by_piece(noise):
             assert np.asarray(c1[k]).tobytes() == np.asarray(c2[k]).tobytes(), k
     assert sum(len(c[2]['raw_records']) for c in a) > 1000
     assert sum(len(c[2]['truth']) for c in a) == len(inst)
+    assert (sum(len(c[2]['raw_records_he']) for c in a) > 100) == he
