@@ -198,6 +198,13 @@ typedef struct wfs_instr_maps {
      * (gas gap - gas_gap[row]) / row spacing.  Required when s2_luminescence_model == 2. */
     const int32_t *gg_lo_row, *gg_hi_row;
     const double *gg_frac;
+    /* Transverse diffusion of the S2 hit pattern (S2.s2_pattern_map_diffuse, s2.py:560-613, with
+     * enable_field_dependencies.diffusion_transverse_map): per S2-like instruction the sigma [cm] of the
+     * radial and azimuthal displacement of one electron at the liquid surface,
+     * sqrt(2 * D_radial|azimuthal * drift_time_mean).  The pattern of the instruction is then the average
+     * of the device-resident S2 pattern grid over its electrons' displaced positions inside tpc_radius
+     * (requires pattern_row < 0 for these instructions).  Both NULL -> pattern at the observed position. */
+    const double *hdiff_sigma_r, *hdiff_sigma_a;
 } wfs_instr_maps;
 
 typedef struct wfs_counts {

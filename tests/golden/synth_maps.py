@@ -52,7 +52,11 @@ class FieldDependencies:
         R, Z = np.meshgrid(*g, indexing='ij')
         self.m = GridMap(ax, dict(drift_speed_map=0.9 + 0.5 * (-Z) / 150.0 + 0.002 * R,      # mm/us
                                   survival_probability_map=np.clip(1.05 - 0.004 * R, 0, 1.2),
-                                  diffusion=(20.0 + 0.2 * R + 0.05 * (-Z)) * 1e-9))          # cm^2/ns
+                                  diffusion=(20.0 + 0.2 * R + 0.05 * (-Z)) * 1e-9,           # cm^2/ns
+                                  # transverse diffusion [cm^2/s], far larger than in xenon so that the
+                                  # smearing is visible on the coarse synthetic pattern grid
+                                  diffusion_radial_map=3000.0 + 20.0 * R + 4.0 * (-Z),
+                                  diffusion_azimuthal_map=800.0 + 5.0 * R + 1.0 * (-Z)))
 
     def field_dependencies_map(self, z, xy, map_name):
         r = np.sqrt(xy[:, 0] ** 2 + xy[:, 1] ** 2)
@@ -79,3 +83,21 @@ class GasGapMap:
     def __call__(self, xy, **kw):
         xy = np.asarray(xy, dtype=np.float64)
         return 0.243 + 0.085 * np.hypot(xy[:, 0], xy[:, 1]) / 70.0
+
+
+def s2_pattern_grid(n_top, seed=4):
+    """S2 hit-pattern map over (x, y), top array only (the layout of the XENONnT map; the bottom array is
+    padded with ones, s2.py:642-644): strongly peaked values so that neighbouring cells differ a lot."""
+    rng = np.random.default_rng(seed)
+    return GridMap([(-55, 55, 12), (-55, 55, 11)], {'map': 40.0 * rng.random((12, 11, n_top)) ** 4 + 0.04})
+
+
+class ReferencePatternMap:
+    """What the reference reads of straxen.InterpolatingMap: a callable with .data['map'] (s2.py:601-604)."""
+
+    def __init__(self, grid_map):
+        self.g = grid_map
+        self.data = {'map': grid_map.maps['map']}
+
+    def __call__(self, points, **kw):
+        return self.g(points, **kw)

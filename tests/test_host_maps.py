@@ -2,6 +2,7 @@
 import os
 
 import numpy as np
+import pytest
 
 from tests.conftest import GOLDEN, load_c0_config
 from tests.golden import synth_maps as SM
@@ -55,3 +56,39 @@ def test_instruction_maps_field_models():
     assert np.allclose([mean, spread], g['fdep_mean_spread'], rtol=1e-12)      # s2.py:157-179
     r_obs = np.hypot(m['x_obs'][0], m['y_obs'][0])
     assert np.isclose(r_obs, 25.0 * (1 - 0.05 * 80.0 / 150.0), rtol=1e-9)
+
+
+def test_transverse_diffusion_sigmas_match_reference_displacements():
+    """diffusion_transverse_map (s2.py:560-613): the per-instruction sigmas handed to the device are the
+    spreads of the displacements the unmodified reference draws (tests/golden/stoch_diffuse.npz,
+    make_golden_diffuse.py: positions read back through an identity "pattern map")."""
+    from scipy import stats
+    from tests.golden.make_golden_diffuse import CASES
+    from tests.golden.make_golden_stoch import fixed_rows
+    from wfsim_b200.dtypes import instruction_dtype
+    g = np.load(os.path.join(GOLDEN, 'stoch_diffuse.npz'))
+    fd = SM.FieldDependencies()
+    efd = dict(survival_probability_map=False, drift_speed_map=True, diffusion_longitudinal_map=False,
+               diffusion_transverse_map=True)
+    cfg = load_c0_config(enable_field_dependencies=efd, diffusion_constant_transverse=1.0)
+    n_top = int(cfg['n_top_pmts'])
+    res = R.Resource(cfg, field_dependencies_map=fd.field_dependencies_map, s2_pattern_map=SM.s2_pattern_grid(n_top))
+    for name, (x, y, z) in CASES.items():
+        rows = fixed_rows(np.dtype(instruction_dtype), 2, 40, 2, z)
+        rows['x'], rows['y'] = x, y
+        rows['type'][1] = 1                     # an S1 row gets no sigma
+        rows['z'][1] = -10.0
+        m = R.evaluate_instruction_maps(cfg, res, rows)
+        assert m['pattern_row'][0] == -1        # averaged on the device from the grid
+        assert m['hdiff_sigma_r'][1] == 0 and m['hdiff_sigma_a'][1] == 0
+        if name == 'edge':
+            continue                            # truncated by the tpc_radius cut in the golden sample
+        for key, sig in (('radial', m['hdiff_sigma_r'][0]), ('azimuthal', m['hdiff_sigma_a'][0])):
+            assert stats.kstest(g[f'diff_{name}_{key}'].astype(np.float64) / sig, 'norm').pvalue > 0.01, (name, key)
+    # off without the config constant (s2.py:636-640), and not available for maps that are not grids
+    m = R.evaluate_instruction_maps(dict(cfg, diffusion_constant_transverse=0), res, rows)
+    assert 'hdiff_sigma_r' not in m
+    res2 = R.Resource(cfg, field_dependencies_map=fd.field_dependencies_map,
+                      s2_pattern_map=lambda p, **kw: np.ones((len(p), n_top)))
+    with pytest.raises(NotImplementedError):
+        R.evaluate_instruction_maps(cfg, res2, rows)

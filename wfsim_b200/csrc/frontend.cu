@@ -170,6 +170,7 @@ struct Plan {
     // map values
     std::vector<double> lce, scg, cy;
     std::vector<double> vd, dl, xo, yo;      // optional (empty = absent)
+    std::vector<double> hsr, hsa;            // transverse-diffusion sigmas (radial, azimuthal); empty = off
     std::vector<float> pattern;
     std::vector<int32_t> patrow;
     std::vector<uint64_t> rng_id;
@@ -242,7 +243,11 @@ static void make_plan(Handle *H, const uint8_t *rows, int64_t n, const wfs_instr
     if (maps && maps->s1_lce) std::copy(maps->s1_lce, maps->s1_lce + n, P.lce.begin());
     if (maps && maps->s2_sc_gain) std::copy(maps->s2_sc_gain, maps->s2_sc_gain + n, P.scg.begin());
     if (maps && maps->s2_cy_extra) std::copy(maps->s2_cy_extra, maps->s2_cy_extra + n, P.cy.begin());
-    P.vd.clear(); P.dl.clear(); P.xo.clear(); P.yo.clear();
+    P.vd.clear(); P.dl.clear(); P.xo.clear(); P.yo.clear(); P.hsr.clear(); P.hsa.clear();
+    if (maps && maps->hdiff_sigma_r && maps->hdiff_sigma_a) {
+        P.hsr.assign(maps->hdiff_sigma_r, maps->hdiff_sigma_r + n);
+        P.hsa.assign(maps->hdiff_sigma_a, maps->hdiff_sigma_a + n);
+    }
     if (maps && maps->drift_velocity) P.vd.assign(maps->drift_velocity, maps->drift_velocity + n);
     if (maps && maps->diffusion_long) P.dl.assign(maps->diffusion_long, maps->diffusion_long + n);
     if (maps && maps->x_obs && maps->y_obs) {
@@ -364,6 +369,8 @@ static GenCtx make_ctx(Frontend &F, uint64_t seed) {
     g.i_dl = F.has_dl ? F.b_idl.as<double>() : nullptr;
     g.i_xo = F.has_xy ? F.b_ixo.as<double>() : nullptr;
     g.i_yo = F.has_xy ? F.b_iyo.as<double>() : nullptr;
+    g.i_hsr = F.has_hd ? F.b_ihsr.as<double>() : nullptr;
+    g.i_hsa = F.has_hd ? F.b_ihsa.as<double>() : nullptr;
     g.i_recoil = F.b_irecoil.as<int32_t>();
     g.gg_cdf = F.gg_cdf; g.gg_rows = F.gg_rows; g.gg_len = F.gg_len;
     g.i_gglo = F.has_gg ? F.b_igglo.as<int32_t>() : nullptr;
@@ -441,6 +448,7 @@ static void grow_instr(Frontend &F, int64_t n_new, int64_t n_old, cudaStream_t s
     g(F.b_ivd, 8); g(F.b_idl, 8); g(F.b_ixo, 8); g(F.b_iyo, 8); g(F.b_irecoil, 4); g(F.b_ilrow, 4);
     g(F.b_ioptfirst, 8); g(F.b_ioptn, 4);
     g(F.b_igglo, 4); g(F.b_igghi, 4); g(F.b_iggfrac, 8); g(F.b_iggmean, 8);
+    g(F.b_ihsr, 8); g(F.b_ihsa, 8);
     F.b_emitoff.reserve_keep(4 * (size_t)(n_new + 1), 4 * (size_t)(n_old + 1), s);
     F.b_irun.reserve_keep(4 * (size_t)n_new, 0, s);
 }
@@ -463,6 +471,17 @@ static void generate(Handle *H, Frontend &F, cudaStream_t s, uint64_t seed, int6
     WFS_CUDA_CHECK(stream_sync(s));
     const int64_t e0 = n_emit, e1 = tot;
     if (e1 >= (int64_t(1) << 31)) throw std::runtime_error("emitter batch too large");
+    if (F.has_hd && i0 == 0 && F.n_pattern_rows > F.first_dev_row) {
+        // transverse diffusion (s2.py:560-613): the rows of the S2 primaries become the average of the
+        // pattern grid over their electrons' displaced positions, now that the electron counts are
+        // known; secondaries (pass B) inherit the row of their parent
+        if (!F.s2_pat.v || F.s2_pat.nd != 2 || F.s2_pat.npmt > 128 * kDiffuseMaxPerThread)
+            throw std::runtime_error("hdiff_sigma_* need a 2-D device-resident S2 pattern grid of at most 1024 PMTs");
+        FLAUNCH(k_pattern_diffuse, (unsigned)(i1 - i0), 128, g, (int32_t)F.first_dev_row, F.s2_pat, (int)p.n_tpc_pmts,
+                p.tpc_radius, F.b_pattern.as<float>());
+        FLAUNCH(k_pattern_cdf, div_up(F.n_pattern_rows, 64), 64, F.n_pattern_rows, (int)p.n_tpc_pmts,
+                F.b_pattern.as<float>(), H->cfg.gains, F.b_cdf.as<double>(), F.b_cdfok.as<int32_t>());
+    }
     F.b_et.reserve_keep(8 * (size_t)std::max<int64_t>(e1, 1), 8 * (size_t)e0, s);
     F.b_einstr.reserve_keep(4 * (size_t)std::max<int64_t>(e1, 1), 4 * (size_t)e0, s);
     F.b_enph.reserve_keep(4 * (size_t)std::max<int64_t>(e1, 1), 4 * (size_t)e0, s);
@@ -597,6 +616,8 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     F.has_vd = !P.vd.empty(); F.has_dl = !P.dl.empty(); F.has_xy = !P.xo.empty();
     std::vector<double> h_vd(F.has_vd ? nprim : 0), h_dl(F.has_dl ? nprim : 0), h_xo(F.has_xy ? nprim : 0),
         h_yo(F.has_xy ? nprim : 0);
+    F.has_hd = !P.hsr.empty();
+    std::vector<double> h_hsr(F.has_hd ? nprim : 0), h_hsa(F.has_hd ? nprim : 0);
     std::unordered_map<int32_t, int32_t> rowmap;
     std::vector<int32_t> rows_used, dev_rows;
     for (int64_t j = 0; j < nprim; j++) {
@@ -612,6 +633,11 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         if (F.has_vd) h_vd[j] = P.vd[gi];
         if (F.has_dl) h_dl[j] = P.dl[gi];
         if (F.has_xy) { h_xo[j] = P.xo[gi]; h_yo[j] = P.yo[gi]; }
+        if (F.has_hd) {
+            h_hsr[j] = P.hsr[gi]; h_hsa[j] = P.hsa[gi];
+            if (h.type != 1 && P.patrow[gi] >= 0)
+                throw std::runtime_error("hdiff_sigma_* need the device-resident S2 pattern grid (pattern_row < 0)");
+        }
         if (P.patrow[gi] < 0) {          // pattern evaluated on the device from the uploaded grid
             dev_rows.push_back((int32_t)j);
             continue;
@@ -648,6 +674,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     if (F.has_vd) up(F.b_ivd, h_vd.data(), 8 * nprim);
     if (F.has_dl) up(F.b_idl, h_dl.data(), 8 * nprim);
     if (F.has_xy) { up(F.b_ixo, h_xo.data(), 8 * nprim); up(F.b_iyo, h_yo.data(), 8 * nprim); }
+    if (F.has_hd) { up(F.b_ihsr, h_hsr.data(), 8 * nprim); up(F.b_ihsa, h_hsa.data(), 8 * nprim); }
     // pattern rows of this batch -> CDF rows
     const int64_t nrows = n_host_rows + (int64_t)dev_rows.size();
     std::vector<float> h_rows((size_t)n_host_rows * n_ch);
@@ -676,6 +703,8 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         F.cdf_rows = (dev_rows.empty() && nrows <= 16) ? nrows : -1;
         F.cdf_hash = rows_hash;
     }
+    F.first_dev_row = n_host_rows;
+    F.n_pattern_rows = nrows;
     // ---- pass A: primaries ----
     WFS_CUDA_CHECK(cudaEventRecord(L.ev_c, s));
     int64_t n_emit = 0, n_ph = 0, max_instr_photons = 0;

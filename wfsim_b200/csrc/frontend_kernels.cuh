@@ -19,6 +19,7 @@ struct GenCtx {
     int32_t *i_pat;
     double *i_vd, *i_dl;          // per-instruction drift velocity / longitudinal diffusion, or nullptr
     double *i_xo, *i_yo;          // observed xy (field distortion), or nullptr
+    double *i_hsr, *i_hsa;        // transverse-diffusion sigma (radial, azimuthal) [cm], or nullptr
     int32_t *i_recoil;
     int32_t *i_lrow;              // garfield luminescence: table row of the instruction
     // 'garfield_gas_gap' luminescence (s2.py:411-483): table, per-instruction rows / fraction, and the
@@ -197,6 +198,91 @@ k_pattern_eval(uint32_t n_instr, int32_t first_dev_row, const int32_t *__restric
         }
         out[ch] = (float)acc;
     }
+}
+
+// Transverse diffusion of the S2 hit pattern (S2.s2_pattern_map_diffuse, s2.py:560-613): the pattern of an
+// S2 instruction is the average of the pattern map over its electrons, each displaced by
+// N(0, sigma_r) along the radius and N(0, sigma_a) along the azimuth (rotated by theta = atan2(y, x),
+// s2.py:588-594); electrons displaced beyond tpc_radius are left out of the average (s2.py:597-599), none
+// left -> NaN row (np.average of nothing), whose photons get channel -1.  One CTA per instruction: the
+// threads draw 128 electrons at a time into shared memory (grid cell + weights), then every thread
+// accumulates its PMTs over them in electron order -- a fixed order, so the row is reproducible.
+// Interpolation arithmetic as in k_pattern_eval.  Rows of instructions without electrons keep the
+// pattern at the observed position (they emit nothing).
+constexpr int kDiffuseMaxPerThread = 8;
+__global__ void __launch_bounds__(128)
+k_pattern_diffuse(GenCtx g, int32_t first_dev_row, PatGrid pg, int n_ch, double tpc_radius,
+                  float *__restrict__ pattern) {
+    __shared__ int32_t s_i0[128], s_i1[128];
+    __shared__ double s_w0[128], s_w1[128];
+    const uint32_t i = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int32_t row = g.i_pat[i];
+    const uint32_t ne = g.i_nemit[i];
+    if (g.i_type[i] == 1 || row < first_dev_row || ne == 0) return;
+    const double x0 = g.i_xo ? g.i_xo[i] : (double)g.i_x[i], y0 = g.i_yo ? g.i_yo[i] : (double)g.i_y[i];
+    const double theta = atan2(y0, x0);
+    const double ct = cos(theta), st = sin(theta);
+    const double sr = g.i_hsr[i], sa = g.i_hsa[i];
+    const uint64_t gidx = g.i_gidx[i];
+    double acc[kDiffuseMaxPerThread];
+#pragma unroll
+    for (int k = 0; k < kDiffuseMaxPerThread; k++) acc[k] = 0.0;
+    uint32_t n_in = 0;
+    for (uint32_t base = 0; base < ne; base += 128) {
+        const uint32_t e = base + tid;
+        if (e < ne) {
+            Rng rng(g.seed, RS_HDIFF, gidx, e * 2u);
+            const double hr = normal_d(rng) * sr, ha = normal_d(rng) * sa;
+            const double pos[2] = {x0 + (ct * hr - st * ha), y0 + (st * hr + ct * ha)};
+            int32_t cell[2];
+            double w[2];
+            for (int d = 0; d < 2; d++) {
+                const double f = (pos[d] - pg.lo[d]) / (pg.hi[d] - pg.lo[d]) * (double)(pg.n[d] - 1);
+                const double fl = floor(f);
+                int64_t c = isnan(fl) ? 0 : (fl < -1e9 ? (int64_t)-1000000000 : (fl > 1e9 ? (int64_t)1000000000 : (int64_t)fl));
+                c = c < 0 ? 0 : (c > pg.n[d] - 2 ? pg.n[d] - 2 : c);
+                cell[d] = (int32_t)c;
+                w[d] = f - (double)c;
+            }
+            const bool inside = pos[0] * pos[0] + pos[1] * pos[1] <= tpc_radius * tpc_radius;
+            s_i0[tid] = inside ? cell[0] : -1;
+            s_i1[tid] = cell[1];
+            s_w0[tid] = w[0];
+            s_w1[tid] = w[1];
+        }
+        __syncthreads();
+        const uint32_t m = min(128u, ne - base);
+        for (uint32_t k = 0; k < m; k++) {
+            const int32_t c0 = s_i0[k];
+            if (c0 < 0) continue;
+            const int32_t c1 = s_i1[k];
+            const double w0 = s_w0[k], w1 = s_w1[k];
+            const double *v00 = pg.v + ((int64_t)c0 * pg.n[1] + c1) * pg.npmt;
+            const double *v10 = v00 + (int64_t)pg.n[1] * pg.npmt;
+            n_in++;
+#pragma unroll
+            for (int q = 0; q < kDiffuseMaxPerThread; q++) {
+                const int ch = tid + 128 * q;
+                if (ch < pg.npmt) {
+                    double a = 0.0;
+                    a = a + ((1.0 - w0) * (1.0 - w1)) * v00[ch];
+                    a = a + ((1.0 - w0) * w1) * v00[pg.npmt + ch];
+                    a = a + (w0 * (1.0 - w1)) * v10[ch];
+                    a = a + (w0 * w1) * v10[pg.npmt + ch];
+                    acc[q] += a;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    float *out = pattern + (int64_t)row * n_ch;
+#pragma unroll
+    for (int q = 0; q < kDiffuseMaxPerThread; q++) {
+        const int ch = tid + 128 * q;
+        if (ch < pg.npmt) out[ch] = (float)(acc[q] / (double)n_in);      // n_in == 0 -> NaN
+    }
+    for (int ch = pg.npmt + tid; ch < n_ch; ch += 128) out[ch] = 1.0f;      // top-only map: s2.py:642-644
 }
 
 // Per instruction: yields.  S1: s1.py:117-135.  S2-like: s2.py:157-179, 212-256.

@@ -49,6 +49,7 @@ enum : uint32_t {
     RS_AP = 5,          // per parent photon: PMT afterpulses (afterpulse.py:189-217)
     RS_PI = 6,          // per S2 pulse call: photo-ionisation (afterpulse.py:37-59)
     RS_PE = 7,          // per S2 pulse call: photo-electric (gate) electrons (afterpulse.py:105-135)
+    RS_HDIFF = 8,       // per electron: transverse displacement for the hit pattern (s2.py:588-589)
 };
 
 // uniform in [0,1) with 53 bits from two words

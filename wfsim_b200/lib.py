@@ -78,7 +78,8 @@ class InstrMaps(C.Structure):
                 ('pattern_row', vp), ('n_pattern_rows', i64), ('s2_sc_gain_default', f64),
                 ('rng_id', vp), ('drift_velocity', vp), ('diffusion_long', vp), ('x_obs', vp), ('y_obs', vp),
                 ('group_base', i64), ('opt_first', vp), ('opt_last', vp), ('opt_channels', vp), ('opt_timings', vp),
-                ('n_opt', i64), ('opt_time_cutoff', i64), ('gg_lo_row', vp), ('gg_hi_row', vp), ('gg_frac', vp)]
+                ('n_opt', i64), ('opt_time_cutoff', i64), ('gg_lo_row', vp), ('gg_hi_row', vp), ('gg_frac', vp),
+                ('hdiff_sigma_r', vp), ('hdiff_sigma_a', vp)]
 
 
 class Outputs(C.Structure):

@@ -185,11 +185,11 @@ def evaluate_instruction_maps(config, resource, instructions, seed=0, device_pat
         x, y, z = xyz[is_s2, 0], xyz[is_s2, 1], xyz[is_s2, 2]
         fdm = config.get('field_distortion_model', 'none')
         if fdm == 'inverse_fdc':
-            _, pos = inverse_field_distortion_correction(x, y, z, resource)
+            z_obs, pos = inverse_field_distortion_correction(x, y, z, resource)
         elif fdm == 'comsol':
-            _, pos = field_distortion_comsol(x, y, z, resource)
+            z_obs, pos = field_distortion_comsol(x, y, z, resource)
         else:
-            pos = xy[is_s2]
+            z_obs, pos = z, xy[is_s2]
         pos_obs[is_s2] = pos
         if fdm in ('inverse_fdc', 'comsol'):
             out['x_obs'], out['y_obs'] = pos_obs[:, 0].copy(), pos_obs[:, 1].copy()
@@ -223,6 +223,24 @@ def evaluate_instruction_maps(config, resource, instructions, seed=0, device_pat
             dl = np.full(n, float(config['diffusion_constant_longitudinal']))
             dl[is_s2] = d
             out['diffusion_long'] = dl
+    diffuse = bool(efd.get('diffusion_transverse_map')) and config.get('diffusion_constant_transverse', 0) > 0
+    if diffuse and is_s2.any():
+        # s2_pattern_map_diffuse (s2.py:560-613): sigma of one electron's radial / azimuthal displacement,
+        # from the maps at the OBSERVED position (photon_channels gets z_obs, positions: s2.py:112-117);
+        # the per-electron averaging of the pattern runs on the device (k_pattern_diffuse)
+        assert np.all(z_obs < 0), 'All S2 in liquid should have z < 0'
+        if efd.get('drift_speed_map'):                  # get_avg_drift_velocity, s2.py:139-155
+            v_avg = np.asarray(resource.field_dependencies_map(z_obs, pos, map_name='drift_speed_map'),
+                               dtype=np.float64).reshape(-1) * 1e-4 * resource.drift_velocity_scaling
+        else:
+            v_avg = float(config['drift_velocity_liquid'])
+        t_mean = -z_obs / v_avg
+        sr, sa = np.zeros(n), np.zeros(n)
+        for dst, name in ((sr, 'diffusion_radial_map'), (sa, 'diffusion_azimuthal_map')):
+            d = np.asarray(resource.field_dependencies_map(z_obs, pos, map_name=name),
+                           dtype=np.float64).reshape(-1) * 1e-9          # cm^2/s -> cm^2/ns
+            dst[is_s2] = np.sqrt(2 * d * t_mean)
+        out['hdiff_sigma_r'], out['hdiff_sigma_a'] = sr, sa
     if config.get('s2_luminescence_model', 'simple') == 'garfield_gas_gap' and is_s2.any():
         # s2.py:460-483: the excitation-time inverse CDF is interpolated between the two tabulated gas gaps
         # around the local one (np.digitize - 1: below the first gap python's index -1 picks the LAST row)
@@ -245,8 +263,15 @@ def evaluate_instruction_maps(config, resource, instructions, seed=0, device_pat
         if not mask.any():
             return
         smear = is_s2_map and aft_sigma != 0
-        if device_patterns and not smear and _on_device(m, 2 if is_s2_map else 3, n_ch, not is_s2_map) \
-                and not (is_s2_map and efd.get('diffusion_transverse_map')):
+        if is_s2_map and diffuse:
+            # the average over the electrons' displaced positions needs the electron counts, which are
+            # drawn on the device: only a device-resident grid can serve it
+            if smear or not _on_device(m, 2, n_ch, False):
+                raise NotImplementedError('diffusion_transverse_map needs s2_pattern_map as a regular 2-D grid '
+                                          '(resource.GridMap) and no s2_aft_sigma smearing')
+            row_of[mask] = -1
+            return
+        if device_patterns and not smear and _on_device(m, 2 if is_s2_map else 3, n_ch, not is_s2_map):
             row_of[mask] = -1        # evaluated on the device from the uploaded grid
             return
         if isinstance(m, DummyMap) and not smear:
@@ -254,9 +279,7 @@ def evaluate_instruction_maps(config, resource, instructions, seed=0, device_pat
             idx = np.zeros(mask.sum(), np.int64)
         else:
             # s2_pattern_map_diffuse (s2.py:560-613) evaluates the map at the undiffused position
-            # unless the transverse-diffusion field map is enabled
-            if is_s2_map and efd.get('diffusion_transverse_map'):
-                raise NotImplementedError('diffusion_transverse_map: per-electron pattern averaging is not built')
+            # unless the transverse-diffusion field map is enabled (handled above)
             pat = np.asarray(m(pos_obs[mask] if is_s2_map else xyz[mask]), dtype=np.float64)
             pat = pat.reshape(mask.sum(), -1)
             idx = np.arange(mask.sum())

@@ -175,7 +175,8 @@ class Simulator:
             m.opt_channels, m.opt_timings = _ptr(keep['opt_channels']), _ptr(keep['opt_timings'])
             m.n_opt = len(keep['opt_channels'])
             m.opt_time_cutoff = int(self.config.get('nveto_time_max_cutoff', int(1e6)))
-        for k in ('drift_velocity', 'diffusion_long', 'x_obs', 'y_obs', 'gg_lo_row', 'gg_hi_row', 'gg_frac'):
+        for k in ('drift_velocity', 'diffusion_long', 'x_obs', 'y_obs', 'gg_lo_row', 'gg_hi_row', 'gg_frac',
+                  'hdiff_sigma_r', 'hdiff_sigma_a'):
             if k in keep:
                 setattr(m, k, _ptr(keep[k]))
         if rng_id is not None:
