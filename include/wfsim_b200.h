@@ -152,6 +152,12 @@ typedef struct wfs_tables {
     const double *s2_pat_grid;      /* [n0][n1][s2_pat_npmt] */
     int32_t s2_pat_n[2], s2_pat_npmt, s2_pat_pad;
     double s2_pat_lo[2], s2_pat_hi[2];
+    /* 'simple' S2 luminescence with enable_gas_gap_warping (s2.py:317-378 with resource.gas_gap_length):
+     * scalars of the field model between liquid surface and anode wire -- alpha =
+     * gas_drift_velocity_slope / number density, uE = kV/cm, pressure in bar, anode_field_domination_distance,
+     * anode_wire_radius, radial step (0.0001 cm).  Used with wfs_instr_maps.lum_gap / lum_e0;
+     * lumw_dr == 0 -> not available. */
+    double lumw_alpha, lumw_ue, lumw_pressure, lumw_ra, lumw_rw, lumw_dr;
 } wfs_tables;
 
 /* Per-instruction map values evaluated on the host with the reference's own map objects
@@ -205,6 +211,10 @@ typedef struct wfs_instr_maps {
      * of the device-resident S2 pattern grid over its electrons' displaced positions inside tpc_radius
      * (requires pattern_row < 0 for these instructions).  Both NULL -> pattern at the observed position. */
     const double *hdiff_sigma_r, *hdiff_sigma_a;
+    /* 'simple' luminescence with enable_gas_gap_warping: per S2-like instruction the local gas gap dG
+     * [cm] (resource.gas_gap_length(xy), s2.py:361-362) and the field scale E0 [V/cm] derived from it
+     * (s2.py:365-370).  Required when s2_luminescence_model == 0 and no constant-gap table was given. */
+    const double *lum_gap, *lum_e0;
 } wfs_instr_maps;
 
 typedef struct wfs_counts {

@@ -228,6 +228,9 @@ def main():
     if 'gg' in which:
         from tests.golden import make_golden_gg
         make_golden_gg.main(ref, c0_config)
+    if 'lumw' in which:
+        from tests.golden import make_golden_lumw
+        make_golden_lumw.main(ref, c0_config)
     if 'diffuse' in which:
         from tests.golden import make_golden_diffuse
         make_golden_diffuse.main(ref, c0_config)

@@ -101,3 +101,12 @@ class ReferencePatternMap:
 
     def __call__(self, points, **kw):
         return self.g(points, **kw)
+
+
+class GasGapLength:
+    """resource.gas_gap_length stand-in (load_resource.py:319-321, the sagging anode: `lookup(x, y)` of the
+    warping map): gas gap [cm] shrinking towards the centre of the TPC."""
+
+    def __call__(self, xy, **kw):
+        xy = np.asarray(xy, dtype=np.float64)
+        return 0.215 + 0.075 * (np.hypot(xy[:, 0], xy[:, 1]) / 50.0) ** 2

@@ -92,3 +92,29 @@ def test_transverse_diffusion_sigmas_match_reference_displacements():
                       s2_pattern_map=lambda p, **kw: np.ones((len(p), n_top)))
     with pytest.raises(NotImplementedError):
         R.evaluate_instruction_maps(cfg, res2, rows)
+
+
+def test_gas_gap_warping_map_values():
+    """enable_gas_gap_warping with the 'simple' luminescence model: per-instruction gas gap from
+    resource.gas_gap_length at the observed position and the field scale E0 of s2.py:365-370; the field
+    scalars replace the constant-gap table in wfs_tables."""
+    from tests.golden.make_golden_stoch import fixed_rows
+    from wfsim_b200 import params, tables
+    from wfsim_b200.dtypes import instruction_dtype
+    cfg = load_c0_config(enable_gas_gap_warping=True)
+    res = R.Resource(cfg, gas_gap_length=SM.GasGapLength())
+    rows = fixed_rows(np.dtype(instruction_dtype), 2, 40, 3, -30.0)
+    rows['x'], rows['y'] = [3.0, 20.0, 0.0], [-4.0, 22.5, 0.0]
+    rows['type'][2] = 1
+    m = R.evaluate_instruction_maps(cfg, res, rows)
+    assert np.allclose(m['lum_gap'], [0.215 + 0.075 * 25 / 2500, 0.215 + 0.075 * (20 ** 2 + 22.5 ** 2) / 2500, 0])
+    dG = m['lum_gap'][:2]
+    VG = cfg['anode_voltage'] / (1 + (cfg['gate_to_anode_distance'] - dG) / dG / cfg['lxe_dielectric_constant'])
+    rA, rW = cfg['anode_field_domination_distance'], cfg['anode_wire_radius']
+    assert np.allclose(m['lum_e0'][:2], VG / ((dG - rA) / rA + np.log(rA / rW)), rtol=1e-14) and m['lum_e0'][2] == 0
+    t = params.build_tables(cfg, res)
+    assert t.struct.lum_len == 0 and t.struct.lumw_dr == 0.0001 and t.struct.lumw_ra == rA and t.struct.lumw_rw == rW
+    # constant gap: E0 of the table builder is the same formula
+    t0 = params.build_tables(load_c0_config(), R.Resource(load_c0_config()))
+    assert t0.struct.lum_len > 0 and t0.struct.lumw_dr == 0
+    assert 'lum_gap' not in R.evaluate_instruction_maps(load_c0_config(), R.Resource(load_c0_config()), rows)

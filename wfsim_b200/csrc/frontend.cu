@@ -171,6 +171,7 @@ struct Plan {
     std::vector<double> lce, scg, cy;
     std::vector<double> vd, dl, xo, yo;      // optional (empty = absent)
     std::vector<double> hsr, hsa;            // transverse-diffusion sigmas (radial, azimuthal); empty = off
+    std::vector<double> lgap, lgapmax, le0;  // warped gas gap: own, largest of the instruction's S2 call, E0; empty = off
     std::vector<float> pattern;
     std::vector<int32_t> patrow;
     std::vector<uint64_t> rng_id;
@@ -253,6 +254,25 @@ static void make_plan(Handle *H, const uint8_t *rows, int64_t n, const wfs_instr
     if (maps && maps->x_obs && maps->y_obs) {
         P.xo.assign(maps->x_obs, maps->x_obs + n);
         P.yo.assign(maps->y_obs, maps->y_obs + n);
+    }
+    P.lgap.clear(); P.lgapmax.clear(); P.le0.clear();
+    if (maps && maps->lum_gap && maps->lum_e0) {
+        P.lgap.assign(maps->lum_gap, maps->lum_gap + n);
+        P.le0.assign(maps->lum_e0, maps->lum_e0 + n);
+        // the reference lays its radial grid from the LARGEST gap of the S2 call down to the wire
+        // (s2.py:372-373), i.e. of the type-2 instructions of one cluster (rawdata.py:102-150)
+        P.lgapmax.assign((size_t)n, 0.0);
+        for (size_t c = 0; c + 1 < P.cluster_start.size(); c++) {
+            double mx = 0.0;
+            for (int64_t j = P.cluster_start[c]; j < P.cluster_start[c + 1]; j++)
+                if (P.instr[P.order[j]].type == 2) mx = std::max(mx, P.lgap[P.order[j]]);
+            for (int64_t j = P.cluster_start[c]; j < P.cluster_start[c + 1]; j++)
+                P.lgapmax[P.order[j]] = std::max(mx, P.lgap[P.order[j]]);
+        }
+    } else if (p.s2_luminescence_model == 0 && H->frontend && H->frontend->lum_len <= 0) {
+        for (int64_t i = 0; i < n; i++)
+            if (P.instr[i].type != 1)
+                throw std::runtime_error("s2_luminescence_model 'simple' with enable_gas_gap_warping needs wfs_instr_maps.lum_gap / lum_e0");
     }
     if (p.s1_model_custom)
         for (int64_t i = 0; i < n; i++) {
@@ -369,6 +389,12 @@ static GenCtx make_ctx(Frontend &F, uint64_t seed) {
     g.i_dl = F.has_dl ? F.b_idl.as<double>() : nullptr;
     g.i_xo = F.has_xy ? F.b_ixo.as<double>() : nullptr;
     g.i_yo = F.has_xy ? F.b_iyo.as<double>() : nullptr;
+    g.i_lgap = F.has_lw ? F.b_ilgap.as<double>() : nullptr;
+    g.i_lgapmax = F.has_lw ? F.b_ilgapmax.as<double>() : nullptr;
+    g.i_le0 = F.has_lw ? F.b_ile0.as<double>() : nullptr;
+    g.i_lavgt = F.has_lw ? F.b_ilavgt.as<double>() : nullptr;
+    g.lumw_alpha = F.lumw_alpha; g.lumw_ue = F.lumw_ue; g.lumw_pressure = F.lumw_pressure;
+    g.lumw_ra = F.lumw_ra; g.lumw_rw = F.lumw_rw; g.lumw_dr = F.lumw_dr;
     g.i_hsr = F.has_hd ? F.b_ihsr.as<double>() : nullptr;
     g.i_hsa = F.has_hd ? F.b_ihsa.as<double>() : nullptr;
     g.i_recoil = F.b_irecoil.as<int32_t>();
@@ -449,6 +475,7 @@ static void grow_instr(Frontend &F, int64_t n_new, int64_t n_old, cudaStream_t s
     g(F.b_ioptfirst, 8); g(F.b_ioptn, 4);
     g(F.b_igglo, 4); g(F.b_igghi, 4); g(F.b_iggfrac, 8); g(F.b_iggmean, 8);
     g(F.b_ihsr, 8); g(F.b_ihsa, 8);
+    g(F.b_ilgap, 8); g(F.b_ilgapmax, 8); g(F.b_ile0, 8); g(F.b_ilavgt, 8);
     F.b_emitoff.reserve_keep(4 * (size_t)(n_new + 1), 4 * (size_t)(n_old + 1), s);
     F.b_irun.reserve_keep(4 * (size_t)n_new, 0, s);
 }
@@ -618,6 +645,9 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         h_yo(F.has_xy ? nprim : 0);
     F.has_hd = !P.hsr.empty();
     std::vector<double> h_hsr(F.has_hd ? nprim : 0), h_hsa(F.has_hd ? nprim : 0);
+    F.has_lw = !P.lgap.empty();
+    if (F.has_lw && !(F.lumw_dr > 0.0)) throw std::runtime_error("lum_gap / lum_e0 given but wfs_tables.lumw_* is not set");
+    std::vector<double> h_lgap(F.has_lw ? nprim : 0), h_lgapmax(F.has_lw ? nprim : 0), h_le0(F.has_lw ? nprim : 0);
     std::unordered_map<int32_t, int32_t> rowmap;
     std::vector<int32_t> rows_used, dev_rows;
     for (int64_t j = 0; j < nprim; j++) {
@@ -633,6 +663,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         if (F.has_vd) h_vd[j] = P.vd[gi];
         if (F.has_dl) h_dl[j] = P.dl[gi];
         if (F.has_xy) { h_xo[j] = P.xo[gi]; h_yo[j] = P.yo[gi]; }
+        if (F.has_lw) { h_lgap[j] = P.lgap[gi]; h_lgapmax[j] = P.lgapmax[gi]; h_le0[j] = P.le0[gi]; }
         if (F.has_hd) {
             h_hsr[j] = P.hsr[gi]; h_hsa[j] = P.hsa[gi];
             if (h.type != 1 && P.patrow[gi] >= 0)
@@ -675,6 +706,10 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     if (F.has_dl) up(F.b_idl, h_dl.data(), 8 * nprim);
     if (F.has_xy) { up(F.b_ixo, h_xo.data(), 8 * nprim); up(F.b_iyo, h_yo.data(), 8 * nprim); }
     if (F.has_hd) { up(F.b_ihsr, h_hsr.data(), 8 * nprim); up(F.b_ihsa, h_hsa.data(), 8 * nprim); }
+    if (F.has_lw) {
+        up(F.b_ilgap, h_lgap.data(), 8 * nprim); up(F.b_ilgapmax, h_lgapmax.data(), 8 * nprim);
+        up(F.b_ile0, h_le0.data(), 8 * nprim);
+    }
     // pattern rows of this batch -> CDF rows
     const int64_t nrows = n_host_rows + (int64_t)dev_rows.size();
     std::vector<float> h_rows((size_t)n_host_rows * n_ch);
@@ -1224,6 +1259,8 @@ static void clone_tables(const Frontend &a, Frontend &b) {
     b.s2_op_u0 = a.s2_op_u0; b.s2_op_u1 = a.s2_op_u1;
     b.gf_t = a.gf_t; b.gf_x = a.gf_x; b.gf_rows = a.gf_rows; b.gf_cols = a.gf_cols;
     b.gg_cdf = a.gg_cdf; b.gg_rows = a.gg_rows; b.gg_len = a.gg_len;
+    b.lumw_alpha = a.lumw_alpha; b.lumw_ue = a.lumw_ue; b.lumw_pressure = a.lumw_pressure;
+    b.lumw_ra = a.lumw_ra; b.lumw_rw = a.lumw_rw; b.lumw_dr = a.lumw_dr;
     b.s1_pat = a.s1_pat; b.s2_pat = a.s2_pat;
 }
 
@@ -1483,8 +1520,12 @@ void Handle::frontend_init(const wfs_tables &t) {
         F->gg_cdf = upload_table(t.gg_cdf, (size_t)t.gg_rows * t.gg_len, owned);
         F->gg_rows = t.gg_rows; F->gg_len = t.gg_len;
     } else if (p.s2_luminescence_model == 0 && F->lum_len <= 0) {
-        throw std::runtime_error("s2_luminescence_model 'simple' with enable_gas_gap_warping needs per-position gas gaps: not built yet; set enable_gas_gap_warping=False");
+        // per-position gas gaps (enable_gas_gap_warping): the instructions carry lum_gap / lum_e0
+        if (!(t.lumw_dr > 0.0 && t.lumw_alpha > 0.0 && t.lumw_ra > t.lumw_rw && t.lumw_rw > 0.0))
+            throw std::runtime_error("s2_luminescence_model 'simple': neither the constant-gap table (lum_cdf) nor the field scalars (lumw_*) were given");
     }
+    F->lumw_alpha = t.lumw_alpha; F->lumw_ue = t.lumw_ue; F->lumw_pressure = t.lumw_pressure;
+    F->lumw_ra = t.lumw_ra; F->lumw_rw = t.lumw_rw; F->lumw_dr = t.lumw_dr;
     frontend = F;
 }
 

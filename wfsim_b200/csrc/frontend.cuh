@@ -92,10 +92,12 @@ struct Frontend {
     int32_t gf_rows = 0, gf_cols = 0;
     double *gg_cdf = nullptr;       // 'garfield_gas_gap' luminescence table
     int32_t gg_rows = 0, gg_len = 0;
+    // 'simple' luminescence with per-position gas gaps (wfs_tables.lumw_*); dr == 0: not available
+    double lumw_alpha = 0, lumw_ue = 0, lumw_pressure = 0, lumw_ra = 0, lumw_rw = 0, lumw_dr = 0;
     Primitives prim;
     // workspaces
     DevBuf b_itype, b_itime, b_ix, b_iy, b_iz, b_iamp, b_igidx, b_ilce, b_iscg, b_icy, b_ipat,
-        b_ivd, b_idl, b_ixo, b_iyo, b_irecoil, b_ilrow, b_ioptfirst, b_ioptn, b_igglo, b_igghi, b_iggfrac, b_iggmean, b_ihsr, b_ihsa,
+        b_ivd, b_idl, b_ixo, b_iyo, b_irecoil, b_ilrow, b_ioptfirst, b_ioptn, b_igglo, b_igghi, b_iggfrac, b_iggmean, b_ihsr, b_ihsa, b_ilgap, b_ilgapmax, b_ile0, b_ilavgt,
         b_ggpartial,
         b_dmean, b_dspread, b_nemit, b_emitoff, b_nhits, b_acc, b_cdf, b_cdfok, b_pattern,
         b_et, b_einstr, b_enph, b_ephoff, b_pht, b_phch, b_phgain, b_phinstr, b_phflags, b_phnap,
@@ -108,6 +110,7 @@ struct Frontend {
     bool has_opt = false;       // the current call supplies photons (wfs_instr_maps.opt_*)
     int64_t cdf_rows = -1;      // pattern CDF rows resident in b_cdf (few-row case only) and their hash
     uint64_t cdf_hash = 0;
+    bool has_lw = false;                 // per-instruction gas gaps given (wfs_instr_maps.lum_gap / lum_e0)
     bool has_hd = false;                 // transverse-diffusion sigmas given (wfs_instr_maps.hdiff_sigma_*)
     int64_t first_dev_row = 0, n_pattern_rows = 0;   // pattern rows of the current batch: [0, first_dev_row) from the host
     bool has_vd = false, has_dl = false, has_xy = false;   // optional per-instruction arrays of the current batch

@@ -20,6 +20,10 @@ struct GenCtx {
     double *i_vd, *i_dl;          // per-instruction drift velocity / longitudinal diffusion, or nullptr
     double *i_xo, *i_yo;          // observed xy (field distortion), or nullptr
     double *i_hsr, *i_hsa;        // transverse-diffusion sigma (radial, azimuthal) [cm], or nullptr
+    // 'simple' luminescence with per-position gas gaps (s2.py:317-378): gap of the instruction, largest gap
+    // of its S2 call, field scale E0, and the mean emission time subtracted (filled by k_instr); or nullptr
+    double *i_lgap, *i_lgapmax, *i_le0, *i_lavgt;
+    double lumw_alpha, lumw_ue, lumw_pressure, lumw_ra, lumw_rw, lumw_dr;
     int32_t *i_recoil;
     int32_t *i_lrow;              // garfield luminescence: table row of the instruction
     // 'garfield_gas_gap' luminescence (s2.py:411-483): table, per-instruction rows / fraction, and the
@@ -200,6 +204,52 @@ k_pattern_eval(uint32_t n_instr, int32_t first_dev_row, const int32_t *__restric
     }
 }
 
+// 'simple' S2 luminescence with a per-position gas gap (S2._luminescence_timings_simple, s2.py:317-341).
+// An electron drifts from the liquid surface (r = dG from the wire) to the anode wire (r = rW) with velocity
+// alpha * E(r), E(r) = E0 * rr(r), rr = clip(1/r, 1/rA, 1/rW), and emits photons at the rate
+// dy(r) = E(r)/uE - 0.8 p per unit length.  The reference tabulates both on a radial grid of step dr that
+// starts at the LARGEST gap of the call, subtracts the yield-weighted mean time over that whole grid
+// (avgt, s2.py:329-331), and inverts the yield CDF from the instruction's own gap down (s2.py:333-339).
+//   lumw_mean_time: avgt with the reference's own discrete sums (r_k = gapmax - k dr > rW).
+__device__ inline double lumw_mean_time(const GenCtx &g, double gapmax, double e0) {
+    const double dr = g.lumw_dr, inv_ra = 1.0 / g.lumw_ra, inv_rw = 1.0 / g.lumw_rw;
+    const int64_t n = (int64_t)ceil((gapmax - g.lumw_rw) / dr);          // len(np.arange(gapmax, rW, -dr))
+    double t = 0.0, num = 0.0, den = 0.0;
+    for (int64_t k = 0; k < n; k++) {
+        const double r = gapmax - (double)k * dr;
+        const double rr = fmin(fmax(1.0 / r, inv_ra), inv_rw);
+        t += dr / (g.lumw_alpha * e0 * rr);
+        const double dy = e0 * rr / g.lumw_ue - 0.8 * g.lumw_pressure;
+        num += t * dy;
+        den += dy;
+    }
+    return den != 0.0 ? num / den : 0.0;
+}
+//   lumw_time: emission time of one photon -- the inverse of the yield CDF in closed form (the continuum
+//   limit of np.interp(U, cumsum(dy)/sum, cumsum(dt)); the grid step is 0.1 um, i.e. < 1 ns): uniform
+//   field above rA (linear), 1/r field below (a few Newton steps).
+__device__ inline double lumw_time(const GenCtx &g, double gap, double e0, double avgt, double u) {
+    const double ra = g.lumw_ra, rw = g.lumw_rw, c = e0 / g.lumw_ue, q = 0.8 * g.lumw_pressure;
+    const double ae = g.lumw_alpha * e0;
+    const double rb = fmin(ra, gap);                        // top of the 1/r region
+    const double dy_a = c / ra - q;                         // yield density in the uniform-field region
+    const double y_a = gap > ra ? dy_a * (gap - ra) : 0.0;
+    const double y_b = c * log(rb / rw) - q * (rb - rw);
+    const double target = u * (y_a + y_b);
+    if (target < y_a) return (target / dy_a) * ra / ae - avgt;
+    const double t_a = gap > ra ? (gap - ra) * ra / ae : 0.0;
+    const double yb = target - y_a;
+    double r = rb * exp(-yb / c);                           // exact for q = 0
+#pragma unroll 1
+    for (int it = 0; it < 8; it++) {
+        const double f = c * log(rb / r) - q * (rb - r) - yb;
+        const double step = f / (c / r - q);                // d/dr of the yield integral is -(c/r - q)
+        r = fmin(fmax(r + step, rw), rb);
+        if (fabs(step) < 1e-12) break;
+    }
+    return t_a + (rb * rb - r * r) / (2.0 * ae) - avgt;
+}
+
 // Transverse diffusion of the S2 hit pattern (S2.s2_pattern_map_diffuse, s2.py:560-613): the pattern of an
 // S2 instruction is the average of the pattern map over its electrons, each displaced by
 // N(0, sigma_r) along the radius and N(0, sigma_a) along the azimuth (rotated by theta = atan2(y, x),
@@ -329,6 +379,7 @@ __global__ void k_instr(GenCtx g, wfs_params p, uint32_t i0, uint32_t i1) {
             }
             g.i_lrow[i] = best;
         }
+        if (p.s2_luminescence_model == 0 && g.i_lgap) g.i_lavgt[i] = lumw_mean_time(g, g.i_lgapmax[i], g.i_le0[i]);
         double cy = p.electron_extraction_yield * exp(-mean / p.electron_lifetime_liquid) * g.i_cy[i];
         cy = fmin(fmax(cy, 0.0), 1.0);
         int64_t ne = sample_binomial(amp, cy, rng.ud53());
@@ -480,7 +531,9 @@ k_photons(GenCtx g, wfs_params p, const double *gains, int n_ch, uint32_t n_emit
             }
         }
     } else {
-        if (p.s2_luminescence_model == 0 && g.lum_len > 0)
+        if (p.s2_luminescence_model == 0 && g.i_lgap)
+            t += (int64_t)lumw_time(g, g.i_lgap[i], g.i_le0[i], g.i_lavgt[i], u01_32(w0.v[1]));
+        else if (p.s2_luminescence_model == 0 && g.lum_len > 0)
             t += (int64_t)interp_table(g.lum_cdf, g.lum_t, g.lum_len, u01_32(w0.v[1]));
         else if (p.s2_luminescence_model == 1 && g.gf_rows > 0) {   // s2.py:405-409
             const int col = (int)(((uint64_t)w0.v[1] * (uint32_t)g.gf_cols) >> 32);
@@ -763,6 +816,7 @@ k_photoionization(GenCtx g, wfs_params p, uint32_t n_prim, int fill, uint32_t *c
                     g.i_pat[o] = g.i_pat[i];
                     g.i_recoil[o] = g.i_recoil[i];
                     if (g.i_gglo) { g.i_gglo[o] = g.i_gglo[i]; g.i_gghi[o] = g.i_gghi[i]; g.i_ggfrac[o] = g.i_ggfrac[i]; }
+                    if (g.i_lgap) { g.i_lgap[o] = g.i_lgap[i]; g.i_lgapmax[o] = g.i_lgapmax[i]; g.i_le0[o] = g.i_le0[i]; }
                     if (g.i_vd) g.i_vd[o] = g.i_vd[i];
                     if (g.i_dl) g.i_dl[o] = g.i_dl[i];
                     if (g.i_xo) { g.i_xo[o] = r * cos(ang); g.i_yo[o] = r * sin(ang); }
@@ -826,6 +880,7 @@ k_photoelectric(GenCtx g, wfs_params p, uint32_t n_prim, int fill, uint32_t *cou
         g.i_pat[o] = g.i_pat[i];
         g.i_recoil[o] = g.i_recoil[i];
         if (g.i_gglo) { g.i_gglo[o] = g.i_gglo[i]; g.i_gghi[o] = g.i_gghi[i]; g.i_ggfrac[o] = g.i_ggfrac[i]; }
+        if (g.i_lgap) { g.i_lgap[o] = g.i_lgap[i]; g.i_lgapmax[o] = g.i_lgapmax[i]; g.i_le0[o] = g.i_le0[i]; }
         if (g.i_vd) g.i_vd[o] = g.i_vd[i];
         if (g.i_dl) g.i_dl[o] = g.i_dl[i];
         if (g.i_xo) { g.i_xo[o] = r * cos(ang); g.i_yo[o] = r * sin(ang); }

@@ -70,7 +70,9 @@ class Tables(C.Structure):
         ('gg_cdf', vp), ('gg_rows', i32), ('gg_len', i32),
         ('s1_pat_grid', vp), ('s1_pat_n', i32 * 3), ('s1_pat_npmt', i32), ('s1_pat_lo', f64 * 3), ('s1_pat_hi', f64 * 3),
         ('s2_pat_grid', vp), ('s2_pat_n', i32 * 2), ('s2_pat_npmt', i32), ('s2_pat_pad', i32),
-        ('s2_pat_lo', f64 * 2), ('s2_pat_hi', f64 * 2)]
+        ('s2_pat_lo', f64 * 2), ('s2_pat_hi', f64 * 2),
+        ('lumw_alpha', f64), ('lumw_ue', f64), ('lumw_pressure', f64), ('lumw_ra', f64), ('lumw_rw', f64),
+        ('lumw_dr', f64)]
 
 
 class InstrMaps(C.Structure):
@@ -79,7 +81,7 @@ class InstrMaps(C.Structure):
                 ('rng_id', vp), ('drift_velocity', vp), ('diffusion_long', vp), ('x_obs', vp), ('y_obs', vp),
                 ('group_base', i64), ('opt_first', vp), ('opt_last', vp), ('opt_channels', vp), ('opt_timings', vp),
                 ('n_opt', i64), ('opt_time_cutoff', i64), ('gg_lo_row', vp), ('gg_hi_row', vp), ('gg_frac', vp),
-                ('hdiff_sigma_r', vp), ('hdiff_sigma_a', vp)]
+                ('hdiff_sigma_r', vp), ('hdiff_sigma_a', vp), ('lum_gap', vp), ('lum_e0', vp)]
 
 
 class Outputs(C.Structure):

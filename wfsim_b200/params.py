@@ -151,6 +151,11 @@ def build_tables(cfg, resource=None):
         t.set('lum_cdf', cdf, np.float64)
         t.set('lum_t', tt, np.float64)
         t.struct.lum_len = len(cdf)
+    elif cfg.get('s2_luminescence_model', 'simple') == 'simple' and cfg.get('enable_gas_gap_warping', False):
+        # per-position gas gaps (resource.gas_gap_length): the device evaluates the field model itself
+        sc = wtab.luminescence_field_scalars(cfg)
+        for k, v in sc.items():
+            setattr(t.struct, 'lumw_' + k, float(v))
     # PMT afterpulse elements (afterpulse.py:155-159, 181-186)
     ap = get('uniform_to_pmt_ap')
     if cfg.get('enable_pmt_afterpulses', True) and ap:

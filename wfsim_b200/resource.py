@@ -107,7 +107,7 @@ class Resource:
                      # load_resource.py:262-330: timing splines, luminescence tables, field maps
                      's1_optical_propagation_spline', 's2_optical_propagation_spline', 's2_luminescence',
                      'fdc_3d', 'fd_comsol', 'diffusion_longitudinal_map', 'drift_velocity_scaling',
-                     's2_luminescence_gg', 'garfield_gas_gap_map'):
+                     's2_luminescence_gg', 'garfield_gas_gap_map', 'gas_gap_length'):
             if name in overrides:
                 setattr(self, name, overrides[name])
         if not hasattr(self, 'drift_velocity_scaling'):
@@ -241,6 +241,15 @@ def evaluate_instruction_maps(config, resource, instructions, seed=0, device_pat
                            dtype=np.float64).reshape(-1) * 1e-9          # cm^2/s -> cm^2/ns
             dst[is_s2] = np.sqrt(2 * d * t_mean)
         out['hdiff_sigma_r'], out['hdiff_sigma_a'] = sr, sa
+    if config.get('s2_luminescence_model', 'simple') == 'simple' and config.get('enable_gas_gap_warping', False) \
+            and is_s2.any():
+        # s2.py:361-370: local gas gap at the observed position and the field scale that follows from it
+        from .tables import luminescence_field_scale
+        gap = np.zeros(n)
+        gap[is_s2] = np.asarray(resource.gas_gap_length(pos_obs[is_s2]), dtype=np.float64).reshape(-1)
+        e0 = np.zeros(n)
+        e0[is_s2] = luminescence_field_scale(config, gap[is_s2])
+        out['lum_gap'], out['lum_e0'] = gap, e0
     if config.get('s2_luminescence_model', 'simple') == 'garfield_gas_gap' and is_s2.any():
         # s2.py:460-483: the excitation-time inverse CDF is interpolated between the two tabulated gas gaps
         # around the local one (np.digitize - 1: below the first gap python's index -1 picks the LAST row)

@@ -176,7 +176,7 @@ class Simulator:
             m.n_opt = len(keep['opt_channels'])
             m.opt_time_cutoff = int(self.config.get('nveto_time_max_cutoff', int(1e6)))
         for k in ('drift_velocity', 'diffusion_long', 'x_obs', 'y_obs', 'gg_lo_row', 'gg_hi_row', 'gg_frac',
-                  'hdiff_sigma_r', 'hdiff_sigma_a'):
+                  'hdiff_sigma_r', 'hdiff_sigma_a', 'lum_gap', 'lum_e0'):
             if k in keep:
                 setattr(m, k, _ptr(keep[k]))
         if rng_id is not None:

@@ -117,6 +117,23 @@ def luminescence_table(cfg, gas_gap=None):
     return y / y[-1], t
 
 
+def luminescence_field_scalars(cfg):
+    """Scalars of the 'simple' luminescence field model (s2.py:355-373) that do not depend on the gas gap."""
+    number_density_gas = cfg['pressure'] / (_BOLTZMANN * cfg['temperature'])
+    return dict(alpha=cfg['gas_drift_velocity_slope'] / number_density_gas, ue=_KV_PER_CM,
+                pressure=cfg['pressure'] / _BAR, ra=cfg['anode_field_domination_distance'],
+                rw=cfg['anode_wire_radius'], dr=0.0001)
+
+
+def luminescence_field_scale(cfg, gas_gap):
+    """E0 [V/cm] of s2.py:365-370 for an array of gas gaps [cm]."""
+    dG = np.asarray(gas_gap, dtype=np.float64)
+    rA, rW = cfg['anode_field_domination_distance'], cfg['anode_wire_radius']
+    dL = cfg['gate_to_anode_distance'] - dG
+    VG = cfg['anode_voltage'] / (1 + dL / dG / cfg['lxe_dielectric_constant'])
+    return VG / ((dG - rA) / rA + np.log(rA / rW))
+
+
 def template_maxima(templates):
     """current_max of pulse.py:32."""
     return np.max(np.asarray(templates), axis=1)
