@@ -1029,6 +1029,44 @@ __global__ void k_class_counts(int64_t n_rec, const uint64_t *keys, int class_sh
 // fill pattern (baseline below `length`, zero behind it), appended to a block stream through one
 // atomic per warp (the header carries the offset, so the stream order does not matter).
 constexpr int kPackWarpRecs = 8, kPackWarps = 4, kPackRecs = kPackWarpRecs * kPackWarps;
+// Assemble the records of one warp in shared memory.  kFull: all kPackWarpRecs records exist (every warp
+// but the last one) -- no per-record guards, so the code is straight-line with predicated loads; the
+// header word of a lane is picked with selects (an if-chain on the lane compiles to an indirect branch).
+template <bool kFull>
+__device__ __forceinline__ void pack_assemble(int nhere, int lane, int dt, const RecDesc *s_desc,
+                                              const int16_t *__restrict__ dense, uint32_t *s_rec) {
+    uint32_t v0[kPackWarpRecs], v1[kPackWarpRecs];
+#pragma unroll
+    for (int r = 0; r < kPackWarpRecs; r++) {
+        v0[r] = v1[r] = 0;
+        if (kFull || r < nhere) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(dense + s_desc[r].src);
+            const int length = s_desc[r].length;
+            if (2 * lane < length) v0[r] = src[lane];
+            if (lane + 32 < 55 && 2 * (lane + 32) < length) v1[r] = src[lane + 32];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kPackWarpRecs; r++) {
+        if (!kFull && r >= nhere) continue;
+        const RecDesc d = s_desc[r];
+        const int length = d.length;
+        uint32_t a0 = v0[r], a1 = v1[r];
+        a0 = 2 * lane + 1 >= length ? a0 & 0xffffu : a0;
+        a1 = 2 * (lane + 32) + 1 >= length ? a1 & 0xffffu : a1;
+        uint32_t h = (uint32_t)(uint64_t)d.time;
+        h = lane == 1 ? (uint32_t)((uint64_t)d.time >> 32) : h;
+        h = lane == 2 ? (uint32_t)length : h;
+        h = lane == 3 ? (((uint32_t)(uint16_t)dt) | ((uint32_t)(uint16_t)d.channel << 16)) : h;
+        h = lane == 4 ? (uint32_t)d.pulse_length : h;
+        h = lane == 5 ? (uint32_t)(uint16_t)d.record_i : h;       // record_i, baseline = 0
+        uint32_t *o = s_rec + r * 61;
+        if (lane < 6) o[lane] = h;
+        o[6 + lane] = a0;
+        if (lane + 32 < 55) o[6 + 32 + lane] = a1;
+    }
+}
+
 template <bool kCompact>
 __global__ void __launch_bounds__(kPackWarps * 32)
 k_pack(int64_t n_rec, DeviceConfig c, const uint32_t *__restrict__ rec_vals,
@@ -1047,37 +1085,8 @@ k_pack(int64_t n_rec, DeviceConfig c, const uint32_t *__restrict__ rec_vals,
     if (lane < nhere) s_desc[lane] = desc[rec_vals[j0 + lane]];
     if (kCompact && lane < kPackWarpRecs) s_mask[lane] = 0;
     __syncwarp();
-    uint32_t v0[kPackWarpRecs], v1[kPackWarpRecs];
-#pragma unroll
-    for (int r = 0; r < kPackWarpRecs; r++) {
-        v0[r] = v1[r] = 0;
-        if (r < nhere) {
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(dense + s_desc[r].src);
-            const int length = s_desc[r].length;
-            if (2 * lane < length) v0[r] = src[lane];
-            if (lane + 32 < 55 && 2 * (lane + 32) < length) v1[r] = src[lane + 32];
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < kPackWarpRecs; r++) {
-        if (r >= nhere) continue;
-        const RecDesc d = s_desc[r];
-        const int length = d.length;
-        uint32_t a0 = v0[r], a1 = v1[r];
-        if (2 * lane + 1 >= length) a0 &= 0xffffu;
-        if (2 * (lane + 32) + 1 >= length) a1 &= 0xffffu;
-        uint32_t h = 0;
-        if (lane == 0) h = (uint32_t)(uint64_t)d.time;
-        else if (lane == 1) h = (uint32_t)((uint64_t)d.time >> 32);
-        else if (lane == 2) h = (uint32_t)length;
-        else if (lane == 3) h = ((uint32_t)(uint16_t)c.p.dt) | ((uint32_t)(uint16_t)d.channel << 16);
-        else if (lane == 4) h = (uint32_t)d.pulse_length;
-        else if (lane == 5) h = (uint32_t)(uint16_t)d.record_i;   // record_i, baseline = 0
-        uint32_t *o = s_rec + r * 61;
-        if (lane < 6) o[lane] = h;
-        o[6 + lane] = a0;
-        if (lane + 32 < 55) o[6 + 32 + lane] = a1;
-    }
+    if (nhere == kPackWarpRecs) pack_assemble<true>(nhere, lane, c.p.dt, s_desc, dense, s_rec);
+    else pack_assemble<false>(nhere, lane, c.p.dt, s_desc, dense, s_rec);
     __syncwarp();
     if (!kCompact) {
         // contiguous span of nhere * 244 bytes starting at a 16-byte aligned address (8 * 244 = 122 * 16)
