@@ -1131,12 +1131,11 @@ k_pack(int64_t n_rec, DeviceConfig c, const uint32_t *__restrict__ rec_vals,
     for (int idx = lane; idx < nhere * 6; idx += 32) {
         const int r = idx / 6, k = idx - r * 6;
         const uint32_t *o = s_rec + r * 61;
-        uint32_t h;
-        if (k < 2) h = o[k];                                             // time
-        else if (k == 2) h = o[4];                                       // pulse_length
-        else if (k == 3) h = (o[3] >> 16) | ((o[5] & 0xffffu) << 16);    // channel, record_i
-        else if (k == 4) h = s_off[r];
-        else h = s_mask[r];
+        uint32_t h = o[k & 1];                                           // time (selects, not a branch chain)
+        h = k == 2 ? o[4] : h;                                           // pulse_length
+        h = k == 3 ? ((o[3] >> 16) | ((o[5] & 0xffffu) << 16)) : h;      // channel, record_i
+        h = k == 4 ? s_off[r] : h;
+        h = k == 5 ? s_mask[r] : h;
         chdr[(j0 + r) * 6 + k] = h;
     }
     for (int idx = lane; idx < nhere * kBlocksPerRecord; idx += 32) {
