@@ -1,0 +1,69 @@
+"""CPU: the oracle's restatements of the optional S2 model rows (oracle/wfsim_oracle_models.py) against
+samples drawn by the unmodified reference (tests/golden/stoch_lumw.npz, stoch_diffuse.npz; generating
+scripts tests/golden/make_golden_lumw.py, make_golden_diffuse.py).  p > 0.01 throughout."""
+import os
+
+import numpy as np
+
+from oracle import wfsim_oracle_models as OM
+from tests.conftest import GOLDEN, load_c0_config
+from tests.golden import synth_maps as SM
+from tests.stat_helpers import P_MIN, ks_p
+
+
+def jitter(a, seed=0):
+    return np.asarray(a, float) + np.random.default_rng(seed).random(len(a))
+
+
+def test_warped_gas_gap_luminescence_matches_reference():
+    from tests.golden.make_golden_lumw import POSITIONS
+    gold = np.load(os.path.join(GOLDEN, 'stoch_lumw.npz'))
+    cfg = load_c0_config(enable_gas_gap_warping=True)
+    gap_of = SM.GasGapLength()
+    rng = np.random.default_rng(7)
+    n = 60_000
+    for name, xy in POSITIONS.items():
+        t = OM.luminescence_timings_warped(gap_of(np.array([xy])), [n], cfg, rng)
+        assert ks_p(jitter(t), jitter(gold['lumw_' + name], 1)) > P_MIN, name
+    # two instructions in one call: the grid starts at the larger gap, which shifts the smaller one's times
+    gaps = gap_of(np.array([POSITIONS['a'], POSITIONS['c']]))
+    t = OM.luminescence_timings_warped(gaps, [n, n], cfg, rng)
+    assert ks_p(jitter(t[:n]), jitter(gold['lumw_a_with_c'], 1)) > P_MIN
+    assert ks_p(jitter(t[n:]), jitter(gold['lumw_c_with_a'], 1)) > P_MIN
+    assert ks_p(jitter(t[:n]), jitter(gold['lumw_a'], 1)) < 1e-6
+    # the product's host-side field scale is the oracle's
+    from wfsim_b200 import tables
+    assert np.allclose(tables.luminescence_field_scale(cfg, gaps), OM.field_scale(cfg, gaps), rtol=1e-14)
+
+
+def test_transverse_diffusion_pattern_matches_reference():
+    from tests.golden.make_golden_diffuse import CASES, N_ELECTRON, N_ELECTRON_FEW, normalised
+    gold = np.load(os.path.join(GOLDEN, 'stoch_diffuse.npz'))
+    efd = dict(survival_probability_map=False, drift_speed_map=True, diffusion_longitudinal_map=False,
+               diffusion_transverse_map=True)
+    cfg = load_c0_config(enable_field_dependencies=efd, diffusion_constant_transverse=1.0)
+    fd = SM.FieldDependencies()
+    grid = SM.s2_pattern_grid(int(cfg['n_top_pmts']))
+    rng = np.random.default_rng(11)
+    for name, (x, y, z) in CASES.items():
+        sr, sa = OM.hdiff_sigmas(cfg, np.array([z]), np.array([[x, y]]), fd.field_dependencies_map)
+        if name != 'edge':           # displacement samples of the reference (untruncated cases)
+            assert ks_p(rng.normal(0, sr[0], 10000), gold[f'diff_{name}_radial']) > P_MIN
+            assert ks_p(rng.normal(0, sa[0], 10000), gold[f'diff_{name}_azimuthal']) > P_MIN
+        for tag, n_i, n_e in (('', 1500, N_ELECTRON), ('_few', 3000, N_ELECTRON_FEW)):
+            pat = OM.s2_pattern_diffuse(np.full(n_i, n_e), np.tile([[x, y]], (n_i, 1)), np.full(n_i, sr[0]),
+                                        np.full(n_i, sa[0]), grid, cfg['tpc_radius'], rng)
+            ok = ~np.isnan(pat).any(axis=1)
+            nan_rows, n_gold = gold[f'diff_{name}{tag}_nan_rows']
+            f, f_gold = (~ok).mean(), nan_rows / n_gold
+            assert abs(f - f_gold) < 5 * np.sqrt(max(f_gold, 1e-3) * (1 / n_i + 1 / n_gold)), (name, tag)
+            p = normalised(pat[ok], cfg)
+            k = int(gold[f'diff_{name}{tag}_peak'][0])
+            ref = gold[f'diff_{name}{tag}_peak_p']
+            # (the golden's channel was picked for its large fluctuation in that very sample, so its mean
+            # there is biased upwards by about one standard error: compare the spread, and all means below)
+            assert abs(p[:, k].std() - ref.std()) < 0.12 * ref.std(), (name, tag)
+            assert abs(p[:, k].mean() - ref.mean()) < 5 * np.sqrt(ref.var() / len(ref) + p[:, k].var() / len(p))
+            # the whole mean pattern: every channel within 5 standard errors of the reference's mean
+            se = np.sqrt(p.var(axis=0) / len(p) + p.var(axis=0) / n_gold)
+            assert (np.abs(p.mean(axis=0) - gold[f'diff_{name}{tag}_p']) <= 5 * se + 1e-12).all(), (name, tag)
