@@ -85,3 +85,103 @@ def hdiff_sigmas(cfg, z_obs, xy_obs, field_dependencies_map, drift_velocity_scal
         d = np.asarray(field_dependencies_map(z_obs, xy_obs, map_name=name), np.float64).reshape(-1) * 1e-9
         out.append(np.sqrt(2 * d * t_drift))
     return out
+
+
+# ---- further optional model rows, pinned to tests/golden/stoch_models.npz and stoch_gg.npz ------------
+
+def singlet_triplet_delays(n, singlet_fraction, t_singlet, t_triplet, rng):
+    """Excimer decay delay (pulse.py:321-341): lifetime picked per photon, Exp(1) x lifetime, truncated."""
+    life = np.where(rng.random(n) < singlet_fraction, t_singlet, t_triplet)
+    return (rng.exponential(1.0, n) * life).astype(np.int64)
+
+
+def s1_photon_delays(channels, z, cfg, rng, spline=None, recoil=None):
+    """Arrival-time terms of S1 photons relative to the interaction time (s1.py:162-260), each truncated to
+    integer ns on its own: optical propagation from the (z, U) spline of the photon's array, the `simple`
+    exponential decay + normal spread, the `custom` recoil-dependent excimer delays (NR 0, alpha 6: singlet
+    / triplet in liquid; LED 20: uniform over the pulse length)."""
+    channels = np.asarray(channels)
+    n = len(channels)
+    model = cfg['s1_model_type']
+    t = np.zeros(n, np.int64)
+    if 'optical_propagation' in model:
+        pts = np.stack([np.full(n, float(z)), rng.random(n)], axis=1)
+        top = channels < cfg['n_top_pmts']
+        prop = np.zeros(n, np.int64)
+        prop[top] = np.asarray(spline(pts[top], map_name='top')).astype(np.int64)
+        prop[~top] = np.asarray(spline(pts[~top], map_name='bottom')).astype(np.int64)
+        t += prop
+    if 'simple' in model:
+        t += rng.exponential(cfg['s1_decay_time'], n).astype(np.int64)
+        t += rng.normal(0, cfg['s1_decay_spread'], n).astype(np.int64)
+    if 'custom' in model:
+        if recoil == 20:
+            t += rng.uniform(0, cfg['led_pulse_length'], n).astype(np.int64)
+        elif recoil in (0, 6):
+            frac = cfg['s1_NR_singlet_fraction'] if recoil == 0 else cfg['s1_ER_alpha_singlet_fraction']
+            t += singlet_triplet_delays(n, frac, cfg['singlet_lifetime_liquid'], cfg['triplet_lifetime_liquid'], rng)
+        else:
+            raise AttributeError('Recoil type must be ER, NR, alpha or LED')
+    return t
+
+
+def garfield_luminescence(xy, n_photons, table, cfg, rng, confine_position=None):
+    """'garfield' luminescence (s2.py:381-409): the table row nearest to the instruction's distance from
+    the closest anode wire (or to a uniform draw within +-confine_position), a uniformly drawn column per
+    photon, minus the integer mean of the whole table."""
+    xy = np.asarray(xy, dtype=np.float64)
+    if isinstance(confine_position, float):
+        dist = rng.uniform(-confine_position, confine_position, len(xy))
+    else:
+        tilt, pitch = cfg.get('anode_xaxis_angle', np.pi / 4), cfg.get('anode_pitch', 0.5)
+        across = -xy[:, 0] * np.sin(tilt) + xy[:, 1] * np.cos(tilt)
+        dist = (across + pitch / 2) % pitch - pitch / 2
+    rows = np.array([int(np.argmin(np.abs(d - table['x']))) for d in dist], dtype=np.int64)
+    rows = np.repeat(rows, n_photons)
+    cols = rng.integers(0, table['t'].shape[1], len(rows))
+    return table['t'][rows, cols].astype(np.int64) - int(np.average(table['t']))
+
+
+def garfield_gas_gap_luminescence(gas_gaps, n_photons, gg_table, rng):
+    """'garfield_gas_gap' luminescence (s2.py:411-483): inverse CDF blended linearly between the tabulated
+    gas gap below the local one (np.digitize - 1, python indexing) and the next, sampled at U(0, len - 2)
+    with linear interpolation between entries, minus the mean over the instruction's photons (float;
+    the caller truncates, s2.py:532-533)."""
+    grid = np.asarray(gg_table['gas_gap'], dtype=np.float64)
+    cdfs = np.asarray(gg_table['timing_inv_cdf'], dtype=np.float64)
+    spacing = grid[1] - grid[0]
+    out = []
+    for gap, n in zip(np.asarray(gas_gaps, dtype=np.float64), n_photons):
+        lo = int(np.digitize(gap, grid)) - 1
+        hi = min(max(lo + 1, 0), len(grid) - 1)
+        curve = (cdfs[hi] - cdfs[lo]) * ((gap - grid[lo]) / spacing) + cdfs[lo]
+        s = rng.uniform(0, cdfs.shape[1] - 2, int(n))
+        a, b = curve[np.floor(s).astype(int)], curve[np.ceil(s).astype(int)]
+        t = (b - a) * (s - np.floor(s)) + a
+        out.append(t - t.mean() if n else t)
+    return np.concatenate(out) if out else np.zeros(0)
+
+
+def s2_photon_delays(luminescence, channels, cfg, rng, spline=None):
+    """S2 photon time relative to its electron (s2.py:504-557): luminescence + excimer delay in gas +
+    optical propagation (U spline per array) / zero / normal spread, each truncated on its own."""
+    channels = np.asarray(channels)
+    n = len(channels)
+    t = np.asarray(luminescence).astype(np.int64)
+    t = t + singlet_triplet_delays(n, cfg['singlet_fraction_gas'], cfg['singlet_lifetime_gas'],
+                                   cfg['triplet_lifetime_gas'], rng)
+    model = cfg['s2_time_model']
+    if 'optical_propagation' in model:
+        u = rng.random(n)[:, None]
+        top = channels < cfg['n_top_pmts']
+        prop = np.zeros(n, np.int64)
+        prop[top] = np.asarray(spline(u[top], map_name='top')).astype(np.int64)
+        prop[~top] = np.asarray(spline(u[~top], map_name='bottom')).astype(np.int64)
+        t = t + prop
+    elif 'zero_delay' in model:
+        pass
+    elif 's2_time_spread around zero' in model:
+        t = t + rng.normal(0, cfg['s2_time_spread'], n).astype(np.int64)
+    else:
+        raise KeyError(model)
+    return t

@@ -67,3 +67,47 @@ def test_transverse_diffusion_pattern_matches_reference():
             # the whole mean pattern: every channel within 5 standard errors of the reference's mean
             se = np.sqrt(p.var(axis=0) / len(p) + p.var(axis=0) / n_gold)
             assert (np.abs(p.mean(axis=0) - gold[f'diff_{name}{tag}_p']) <= 5 * se + 1e-12).all(), (name, tag)
+
+
+def test_timing_model_rows_match_reference():
+    """S1 optical propagation / custom models, garfield luminescence (+ confined, + optical propagation),
+    garfield gas-gap luminescence: oracle restatements against tests/golden/stoch_models.npz, stoch_gg.npz."""
+    from tests.golden.make_golden_gg import POSITIONS as GG_POS
+    from tests.stat_helpers import discrete_p
+    gm = np.load(os.path.join(GOLDEN, 'stoch_models.npz'))
+    gg = np.load(os.path.join(GOLDEN, 'stoch_gg.npz'))
+    rng = np.random.default_rng(3)
+    n = 60_000
+    ch = np.concatenate([np.full(n, 10), np.full(n, 300)])
+    # S1: optical propagation + simple
+    cfg = load_c0_config(s1_model_type='optical_propagation+simple')
+    t = OM.s1_photon_delays(ch, -60.0, cfg, rng, spline=SM.s1_optical_spline())
+    assert ks_p(jitter(t[:n]), jitter(gm['s1_op_top'], 1)) > P_MIN
+    assert ks_p(jitter(t[n:]), jitter(gm['s1_op_bottom'], 1)) > P_MIN
+    assert ks_p(jitter(t[:n]), jitter(gm['s1_op_bottom'], 1)) < 1e-6
+    # S1: custom
+    cfg = load_c0_config(s1_model_type='custom', led_pulse_length=300.0)
+    for name, rc in (('nr', 0), ('alpha', 6), ('led', 20)):
+        t = OM.s1_photon_delays(ch, -60.0, cfg, rng, recoil=rc)
+        assert ks_p(jitter(t), jitter(gm['s1_custom_' + name], 1)) > P_MIN, name
+    # S2: garfield + optical propagation
+    cfg = load_c0_config(s2_luminescence_model='garfield', s2_time_model='optical_propagation')
+    table, spline = SM.garfield_table(), SM.s2_optical_spline()
+    for name, xy in (('a', [3.0, -4.0]), ('b', [10.1, 20.3])):
+        lum = OM.garfield_luminescence(np.array([xy]), [2 * n], table, cfg, rng)
+        t = OM.s2_photon_delays(lum, ch, cfg, rng, spline=spline)
+        assert discrete_p(t[:n], gm[f's2_gf_op_{name}_top']) > P_MIN, name
+        assert discrete_p(t[n:], gm[f's2_gf_op_{name}_bottom']) > P_MIN, name
+    n_c = 40_000
+    lum = OM.garfield_luminescence(np.tile([[3.0, -4.0]], (n_c, 1)), np.ones(n_c, np.int64), table, cfg, rng,
+                                   confine_position=0.1)
+    t = OM.s2_photon_delays(lum, np.full(n_c, 10), cfg, rng, spline=spline)
+    assert discrete_p(t, gm['s2_gf_confined_top']) > P_MIN
+    # S2: garfield gas gap
+    tab, gap_of = SM.garfield_gas_gap_table(), SM.GasGapMap()
+    for name, xy in GG_POS.items():
+        t = OM.garfield_gas_gap_luminescence(gap_of(np.array([xy])), [120_000], tab, rng).astype(np.int64)
+        assert ks_p(jitter(t), jitter(gg['gg_' + name], 1)) > P_MIN, name
+    t = OM.garfield_gas_gap_luminescence(np.full(3000, gap_of(np.array([GG_POS['b']]))[0]), np.full(3000, 40), tab, rng)
+    sums = t.astype(np.int64).reshape(3000, 40).sum(axis=1)
+    assert ks_p(jitter(sums), jitter(gg['gg_small_sum'], 1)) > P_MIN
