@@ -112,6 +112,8 @@ def test_gas_gap_warping_map_values():
     VG = cfg['anode_voltage'] / (1 + (cfg['gate_to_anode_distance'] - dG) / dG / cfg['lxe_dielectric_constant'])
     rA, rW = cfg['anode_field_domination_distance'], cfg['anode_wire_radius']
     assert np.allclose(m['lum_e0'][:2], VG / ((dG - rA) / rA + np.log(rA / rW)), rtol=1e-14) and m['lum_e0'][2] == 0
+    with pytest.raises(RuntimeError, match='gas_gap_length'):
+        R.evaluate_instruction_maps(cfg, R.Resource(cfg), rows)
     t = params.build_tables(cfg, res)
     assert t.struct.lum_len == 0 and t.struct.lumw_dr == 0.0001 and t.struct.lumw_ra == rA and t.struct.lumw_rw == rW
     # constant gap: E0 of the table builder is the same formula

@@ -245,6 +245,10 @@ def evaluate_instruction_maps(config, resource, instructions, seed=0, device_pat
             and is_s2.any():
         # s2.py:361-370: local gas gap at the observed position and the field scale that follows from it
         from .tables import luminescence_field_scale
+        if not hasattr(resource, 'gas_gap_length'):
+            # load_resource.py:319-321 reads the warping map (a pickled histogram) through straxen
+            raise RuntimeError('enable_gas_gap_warping needs resource.gas_gap_length: pass a callable '
+                               'xy -> gas gap [cm] through the Resource overrides')
         gap = np.zeros(n)
         gap[is_s2] = np.asarray(resource.gas_gap_length(pos_obs[is_s2]), dtype=np.float64).reshape(-1)
         e0 = np.zeros(n)
