@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define WFS_ABI_VERSION 2
+#define WFS_ABI_VERSION 3
 #define WFS_E_CAPACITY 1
 #define WFS_E_CUDA (-1)
 #define WFS_E_ARG (-2)

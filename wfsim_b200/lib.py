@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'csrc', 'libwfsim_b200.so')
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 E_CAPACITY = 1
 E_CUDA = -1
 E_ARG = -2
