@@ -185,3 +185,31 @@ def s2_photon_delays(luminescence, channels, cfg, rng, spline=None):
     else:
         raise KeyError(model)
     return t
+
+
+def photoelectric_electrons(photon_times, cfg, rng):
+    """Photo-electric (gate) electrons of one S2 pulse call (afterpulse.py:105-139): Poisson(p x photons x
+    modifier) single-electron instructions of type 6; creation time = a random parent photon + gate drift
+    time, depth from a normal delay clipped at 0, position uniform over the TPC cross-section."""
+    photon_times = np.asarray(photon_times)
+    n = rng.poisson(cfg['photoelectric_p'] * len(photon_times) * cfg.get('photoelectric_modifier', 1))
+    delay = np.clip(rng.normal(cfg['photoelectric_t_center'] + cfg['drift_time_gate'],
+                               cfg['photoelectric_t_spread'], n), 0, None)
+    time = photon_times[rng.integers(0, len(photon_times), n)] + cfg['drift_time_gate']
+    r = np.sqrt(rng.uniform(0, cfg['tpc_radius'] ** 2, n))
+    phi = rng.uniform(-np.pi, np.pi, n)
+    return dict(time=time.astype(np.int64), x=(r * np.cos(phi)).astype(np.float32),
+                y=(r * np.sin(phi)).astype(np.float32),
+                z=(-delay * cfg['drift_velocity_liquid']).astype(np.float32))
+
+
+def smear_area_fraction_top(pattern, n_top, sigma, skewness, rng):
+    """s2.py:660-665 on one normalised pattern row: the top-array share is multiplied by a skew-normal
+    factor around 1 (clipped to [0, 1]) and the bottom share rescaled to keep the sum."""
+    from scipy.stats import skewnorm
+    p = np.array(pattern, dtype=np.float64)
+    cur = p[:n_top].sum() / p.sum()
+    new = float(np.clip(cur * skewnorm.rvs(loc=1.0, scale=sigma, a=skewness, random_state=rng), 0, 1))
+    p[:n_top] *= new / cur
+    p[n_top:] *= (1 - new) / (1 - cur)
+    return p

@@ -111,3 +111,30 @@ def test_timing_model_rows_match_reference():
     t = OM.garfield_gas_gap_luminescence(np.full(3000, gap_of(np.array([GG_POS['b']]))[0]), np.full(3000, 40), tab, rng)
     sums = t.astype(np.int64).reshape(3000, 40).sum(axis=1)
     assert ks_p(jitter(sums), jitter(gg['gg_small_sum'], 1)) > P_MIN
+
+
+def test_photoelectric_electrons_and_aft_smearing_match_reference():
+    from tests.stat_helpers import discrete_p
+    gm = np.load(os.path.join(GOLDEN, 'stoch_models.npz'))
+    rng = np.random.default_rng(5)
+    cfg = load_c0_config(enable_gate_afterpulses=True, photoelectric_p=0.004)
+    photons = np.arange(5000, dtype=np.int64) + 1_000_000
+    calls = [OM.photoelectric_electrons(photons, cfg, rng) for _ in range(600)]
+    n = np.array([len(c['time']) for c in calls])
+    assert discrete_p(n, gm['pe_n']) > P_MIN
+    z = np.concatenate([c['z'] for c in calls]).astype(np.float64)
+    assert ks_p(-z / cfg['drift_velocity_liquid'], gm['pe_delay']) > P_MIN
+    r2 = np.concatenate([c['x'].astype(np.float64) ** 2 + c['y'].astype(np.float64) ** 2 for c in calls])
+    assert ks_p(r2, gm['pe_r2']) > P_MIN
+    t0 = np.concatenate([c['time'] for c in calls]) - 1_000_000
+    assert ks_p(jitter(t0), jitter(gm['pe_t0'], 1)) > P_MIN
+    # area fraction top: constant pattern over the live PMTs, 400 photons per S2
+    cfg = load_c0_config(s2_aft_sigma=0.12, s2_aft_skewness=-1.5)
+    n_top = int(cfg['n_top_pmts'])
+    pat = (np.asarray(cfg['gains']) != 0).astype(np.float64)
+    pat /= pat.sum()
+    counts = []
+    for _ in range(3000):
+        p = OM.smear_area_fraction_top(pat, n_top, 0.12, -1.5, rng)
+        counts.append(rng.binomial(400, p[:n_top].sum()))
+    assert discrete_p(np.array(counts), gm['aft_top_count']) > P_MIN
