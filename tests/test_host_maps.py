@@ -120,3 +120,42 @@ def test_gas_gap_warping_map_values():
     t0 = params.build_tables(load_c0_config(), R.Resource(load_c0_config()))
     assert t0.struct.lum_len > 0 and t0.struct.lumw_dr == 0
     assert 'lum_gap' not in R.evaluate_instruction_maps(load_c0_config(), R.Resource(load_c0_config()), rows)
+
+
+def test_resource_from_reference_object():
+    """The deployment adapter copies the reference Resource's attributes (load_resource.py:176-380):
+    dummy maps keep sharing one pattern row, other map objects are used as callables, tables travel."""
+    from tests.golden.make_golden_stoch import fixed_rows
+    from wfsim_b200.dtypes import instruction_dtype
+
+    class DummyMap:                       # the reference's own class has this name and these attributes
+        def __init__(self, const, shape=()):
+            self.const, self.shape = const, shape
+
+        def __call__(self, x, **kw):
+            return np.ones([len(x)] + list(self.shape)) * self.const
+
+    class RefResource:
+        pass
+    cfg = load_c0_config()
+    ref = RefResource()
+    ref.s1_pattern_map = DummyMap(14e-5, [494])
+    ref.s2_pattern_map = lambda pos, **kw: np.tile(np.linspace(1, 2, 494), (len(pos), 1))
+    ref.s1_lce_correction_map = DummyMap(14e-5 * 494, [1])
+    ref.s2_correction_map = DummyMap(1.0, [1])
+    ref.noise_data = np.zeros((100, 494))
+    ref.gas_gap_length = SM.GasGapLength()
+    ref.drift_velocity_scaling = 0.97
+    res = R.resource_from_reference(ref, cfg)
+    assert isinstance(res.s1_pattern_map, R.DummyMap) and not isinstance(res.s2_pattern_map, R.DummyMap)
+    assert res.noise_data is ref.noise_data and res.gas_gap_length is ref.gas_gap_length
+    assert res.drift_velocity_scaling == 0.97
+    rows = fixed_rows(np.dtype(instruction_dtype), 2, 40, 4, -30.0)
+    rows['type'][::2] = 1
+    m = R.evaluate_instruction_maps(cfg, res, rows)
+    # S1 rows share the dummy row, every S2 row got its own host-evaluated row
+    assert len(set(m['pattern_row'][::2])) == 1 and len(set(m['pattern_row'][1::2])) == 2
+    assert np.allclose(m['pattern'][m['pattern_row'][1]], np.linspace(1, 2, 494))
+    assert np.allclose(m['s1_lce'][::2], 14e-5 * 494)
+    from wfsim_b200.strax_interface import resource_from_reference
+    assert resource_from_reference is R.resource_from_reference

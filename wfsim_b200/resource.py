@@ -114,6 +114,28 @@ class Resource:
             self.drift_velocity_scaling = 1.0
 
 
+def resource_from_reference(ref_resource, config):
+    """Adapter for a WFSim deployment: a Resource holding the maps and tables of the reference's own
+    `wfsim.load_config(config)` object (load_resource.py:176-380), attribute by attribute.  Constant
+    dummy maps are re-wrapped so that they share one pattern row; every other map object is used as
+    the callable it is (evaluated on the host per instruction) -- pass wfsim_b200.resource.GridMap
+    objects instead for the maps that should be interpolated on the device."""
+    names = Resource.MAPS + ('photon_area_distribution', 'noise_data', 'uniform_to_pmt_ap',
+                             'uniform_to_ele_ap', 's1_optical_propagation_spline',
+                             's2_optical_propagation_spline', 's2_luminescence', 's2_luminescence_gg',
+                             'garfield_gas_gap_map', 'gas_gap_length', 'fdc_3d', 'fd_comsol',
+                             'diffusion_longitudinal_map', 'drift_velocity_scaling')
+    overrides = {}
+    for name in names:
+        if not hasattr(ref_resource, name):
+            continue
+        v = getattr(ref_resource, name)
+        if type(v).__name__ == 'DummyMap' and hasattr(v, 'const') and hasattr(v, 'shape'):
+            v = DummyMap(v.const, v.shape)
+        overrides[name] = v
+    return Resource(config, **overrides)
+
+
 def _rz_wrapper(m):
     def rz_map(z, xy, **kwargs):            # load_resource.py:335-338
         r = np.sqrt(xy[:, 0] ** 2 + xy[:, 1] ** 2)

@@ -20,7 +20,7 @@ import numpy as np
 from . import config as wcfg
 from .dtypes import (RECORD_LENGTH, extra_truth_dtype_per_pmt, instruction_dtype, optical_extra_dtype, raw_record_dtype,
                      truth_extra_dtype)
-from .resource import Resource
+from .resource import Resource, resource_from_reference  # noqa: F401  (re-exported for deployments)
 
 log = logging.getLogger('wfsim_b200.interface')
 
