@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define WFS_ABI_VERSION 3
+#define WFS_ABI_VERSION 4
 #define WFS_E_CAPACITY 1
 #define WFS_E_CUDA (-1)
 #define WFS_E_ARG (-2)
@@ -182,10 +182,6 @@ typedef struct wfs_instr_maps {
     /* observed S2 position after the field-distortion model (s2.py:80-87); used by the garfield
      * luminescence model for the distance to the anode wires; NULL -> the instruction's x, y */
     const double *x_obs, *y_obs;
-    /* Index of the first digitisation group of this call in the caller's numbering: the noise start
-     * offset of group g is a Philox draw keyed by group_base + g (rawdata.py:407-417), so a run
-     * simulated in several calls draws what the single call would.  0 for a call of its own. */
-    int64_t group_base;
     /* Externally supplied photons (RawDataOptical.sim_primary, rawdata.py:478-495: G4 optical output,
      * neutron-veto style inputs): a type-1 instruction with opt_last[i] > opt_first[i] takes its photons
      * from the lists below instead of sampling them -- channel opt_channels[k], arrival time
@@ -263,6 +259,12 @@ int wfs_abi_version(void);
 void wfs_struct_sizes(int64_t *out6);       /* sizeof of the six structs of this header, for binding checks */
 int wfs_device_count(void);
 
+/* Smallest signal-time gap [ns] at which the caller may cut a run into independent calls (plugin
+ * pieces, GPU shards): right_raw_extension (rawdata.py:63) plus the longest delay of the secondary
+ * instructions an S2 can spawn (afterpulse.py:63-80, 105-115).  The library cuts its own device batches
+ * at the same gaps.  Replaces nothing in the reference (which simulates a run in one generator). */
+int64_t wfs_quiet_gap(void *handle);
+
 /* Pinned host memory for output buffers (so device->host copies are plain DMA). */
 void *wfs_host_alloc(int64_t bytes);
 void wfs_host_free(void *p);
@@ -284,7 +286,9 @@ int wfs_expand_compact(const void *hdr, const void *blocks, int64_t n_records, u
  * and (time, channel) sort of ChunkRawRecords (strax_interface.py:391-436,446-453).
  *   pulse_call[i]  id of the Pulse call photon i belongs to (0..n_pulse_calls-1)
  *   group_of[p]    digitisation group of pulse call p (0..n_groups-1)
- *   ix_rand[g]     noise start offset of group g (rawdata.py:407-417); NULL -> drawn by Philox(seed)
+ *   ix_rand[g]     noise start offset of group g (rawdata.py:407-417); NULL -> a Philox draw keyed by
+ *                  (seed, first sample of the group's digitisation window): unique per group, and the
+ *                  same however a run is cut into calls, device batches or GPU shards
  * Output: `records` holds [raw_records | raw_records_he | raw_records_aqmon], each segment sorted
  * by (time, channel); segment lengths in counts->n_records[].  `groups` (optional, [n_groups]).
  * Host pointers unless `on_device` is non-zero (then all photon arrays and `records` are device
@@ -324,6 +328,26 @@ typedef struct wfs_outputs {
 int wfs_simulate(void *handle, const uint8_t *instructions, int64_t n_instructions,
                  const wfs_instr_maps *maps, uint64_t seed, wfs_outputs *out, wfs_counts *counts);
 
+/* The scheduling decisions of the full path on their own (host code, no GPU): which instructions form
+ * a Pulse call and which Pulse calls are digitised together.
+ * Replaces the bookkeeping of RawData.__call__ (wfsim/core/rawdata.py:61-63 signal times and primary
+ * clusters, :87-93 re-clustering with pending secondaries, :96-98 when the pulse cache is pushed out,
+ * :102-150 Pulse calls per type incl. save_full_truth on / off and stop_at_this_group) given what the
+ * sampling stages produced: the end of the last pulse of every instruction and the secondary (type 4 / 6)
+ * instructions every S2 spawned.  wfs_simulate runs the same function on the device's numbers.
+ *   time, z, type      [n_prim] primary instructions, any order
+ *   sec_*              [n_sec] secondary instructions and the primary (index) that spawned each
+ *   pulse_end          [n_prim + n_sec] max(right) * dt over the pulses of the instruction incl. its PMT
+ *                      afterpulses (rawdata.py:186-190); INT64_MIN = the instruction made no pulse
+ * Output: run_of[n_prim + n_sec] = Pulse call of each instruction in execution order (-1: none),
+ * run_type / run_group [cap_runs] = type and digitisation group of each Pulse call; *n_groups = number
+ * of groups that hold pulses (trailing calls that made no pulse carry the next, unused index). */
+int wfs_schedule(int64_t right_raw_extension, double drift_velocity_liquid, int save_full_truth,
+                 int64_t n_prim, const int64_t *time, const float *z, const int8_t *type,
+                 int64_t n_sec, const int64_t *sec_time, const float *sec_z, const int8_t *sec_type,
+                 const int32_t *sec_parent, const int64_t *pulse_end, int32_t *run_of, int32_t *run_type,
+                 int32_t *run_group, int64_t cap_runs, int64_t *n_runs, int64_t *n_groups);
+
 /* Device-resident variant for throughput measurement: instructions/maps are parsed, planned and
  * uploaded once by wfs_stage_instructions; wfs_run_staged then runs the whole path with every
  * buffer in HBM and leaves the records on the device (counts are returned; `out` may carry
@@ -338,6 +362,10 @@ int wfs_run_staged(void *handle, uint64_t seed, wfs_outputs *out, wfs_counts *co
  *                       given array; the parent S2 for secondaries); int32 flags (1 = double-pe,
  *                       2 = PMT afterpulse, 4 = photo-ionisation secondary); int32 secondary id
  *   stage 1 (emitters): int64 t_ns; double 0; int32 n_photons; int32 instruction; int32 flags; int32 id
+ *   stage 2 / 3 (secondary instructions, afterpulse.py:24-139): int64 time; double z (2) or x^2 + y^2 (3);
+ *                       int32 amp; int32 parent instruction; int32 type (4 / 6); int32 id
+ *   stage 4 (secondary instructions in full): int64 time; float32 x, y; int32 amp; int32 parent
+ *                       instruction; int32 type; float32 z -- row k is the secondary with id k
  * Replaces nothing in the reference; it exposes S1/S2.photon_timings/photon_channels (s1.py:138-238,
  * s2.py:258-315,504-682) and Pulse.__call__'s TTS/DPE/SPE draws (pulse.py:53-103) for testing. */
 int wfs_sample_stage(void *handle, int stage, const uint8_t *instructions, int64_t n_instructions,

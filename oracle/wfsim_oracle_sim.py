@@ -225,9 +225,10 @@ class OracleSimulator:
         gain = gain + np.where(dpe, extra, 0.0)
         return t, dpe, gain
 
-    def truth_counters(self, t, ch, gain, dpe):
+    def truth_counters(self, t, ch, gain, dpe, keep_order=False):
         """pulse.py:229-271 incl. the `[:n_double_pe]` quirk (per channel, first photons in the
-        channel slice; the slice order here is time order)."""
+        channel slice; the slice order here is time order, or -- keep_order -- the order given, for
+        inputs that already are channel slices as Pulse.__call__ cut them)."""
         cfg = self.cfg
         out = dict.fromkeys(['n_photon', 'n_pe', 'n_photon_trigger', 'n_pe_trigger', 'raw_area',
                              'raw_area_trigger'], 0)
@@ -236,7 +237,7 @@ class OracleSimulator:
         if not live.any():
             return out
         t, ch, gain, dpe = t[live], ch[live], gain[live], dpe[live]
-        order = np.lexsort((t, ch))
+        order = np.argsort(ch, kind='stable') if keep_order else np.lexsort((t, ch))
         t, ch, gain, dpe = t[order], ch[order], gain[order], dpe[order]
         thr = np.full(self.n_ch, cfg['zle_threshold'] - 0.5)
         for k, v in (cfg.get('special_thresholds') or {}).items():
@@ -349,10 +350,27 @@ class OracleSimulator:
                     end=(int(P.right.max()) * self.dt if len(P) else None))
 
     # ---- scheduler (rawdata.py:38-157) + truth rows (rawdata.py:313-375) ----------------------
-    def simulate(self, instructions, truth_dtype=None):
+    def noise_offset(self, first_sample, span):
+        """randint(0, high) of rawdata.py:407-417 (the stochastic oracle draws it from its generator)."""
+        high = len(self.noise) - span - 1
+        if high < 0:
+            high = len(self.noise) - 1
+        return int(self.rng.integers(0, high)) if high > 0 else 0
+
+    def simulate(self, instructions, truth_dtype=None, ids=None):
+        """rawdata.py:38-157.  Every instruction row carries an identity `_id` (primaries: `ids`, default
+        their index; secondaries: what pulse_call gave them, or fresh numbers); `runs` lists the Pulse calls
+        in execution order as (type, ids, digitisation group)."""
         cfg = self.cfg
         v, rext = cfg['drift_velocity_liquid'], cfg['right_raw_extension']
         save_full = cfg.get('save_full_truth', True)
+        wdt = np.dtype([(n, instructions.dtype[n]) for n in instructions.dtype.names if n != '_id'] + [('_id', np.int64)])
+        work = np.zeros(len(instructions), wdt)
+        for n in instructions.dtype.names:
+            work[n] = instructions[n]
+        work['_id'] = np.arange(len(work)) if ids is None else ids
+        instructions = work
+        next_id = int(instructions['_id'].max()) + 1 if len(instructions) else 0
 
         def sig_time(rows):
             zf = rows['z'].astype(np.float32) / np.float32(v)
@@ -364,8 +382,7 @@ class OracleSimulator:
         queue = np.split(order, cuts)
         buf = instructions[:0].copy()
         last_end, cache = None, []
-        groups, truth_rows, records = [], [], []
-        noise_rng = self.rng
+        groups, truth_rows, records, runs = [], [], [], []
 
         def flush():
             nonlocal cache
@@ -376,10 +393,7 @@ class OracleSimulator:
             ix = 0
             if cfg.get('enable_noise', True) and self.noise is not None:
                 span = int(P.right.max() - P.left.min()) + 2 * cfg['trigger_window']
-                high = len(self.noise) - span - 1
-                if high < 0:
-                    high = len(self.noise) - 1
-                ix = int(noise_rng.integers(0, high)) if high > 0 else 0
+                ix = self.noise_offset(int(P.left.min()) - cfg['trigger_window'], span)
             out = det.digitize_zle(cfg, P, noise=self.noise, ix_rand=ix)
             groups.append((out[5][0], out[5][1], len(out[0])))
             records.append(det.pack_records(cfg, *out[:5]))
@@ -415,11 +429,17 @@ class OracleSimulator:
                     for s in sets:
                         rows = buf[s]
                         res = self.pulse_call(rows)
+                        runs.append((ptype, rows['_id'].copy(), len(groups)))
                         if len(res['pulses']):
                             cache.append(res['pulses'])
                             last_end = res['end'] if last_end is None else max(last_end, res['end'])
                         if len(res['spawned']):
-                            spawned_all.append(res['spawned'])
+                            sp = res['spawned']
+                            if not res.get('spawned_have_ids'):
+                                sp = sp.copy()
+                                sp['_id'] = np.arange(next_id, next_id + len(sp))
+                                next_id += len(sp)
+                            spawned_all.append(sp)
                         row = self.truth_row(rows, res, truth_dtype)
                         if row is not None:
                             truth_rows.append(row)
@@ -435,7 +455,7 @@ class OracleSimulator:
         rec = np.concatenate(records) if records else np.zeros(0, det.raw_record_dtype())
         rec = det.sort_by_time(rec)
         truth = np.concatenate(truth_rows) if truth_rows else None
-        return dict(records=rec, truth=truth, groups=groups)
+        return dict(records=rec, truth=truth, groups=groups, runs=runs)
 
     def truth_row(self, rows, res, truth_dtype):
         if truth_dtype is None:
@@ -456,8 +476,9 @@ class OracleSimulator:
                 tb[f'n_{q}'] = 0
                 for f in ('t_mean_', 't_first_', 't_last_', 't_sigma_'):
                     tb[f + q] = np.nan
-        tb['x_mean_electron'] = np.nan
-        tb['y_mean_electron'] = np.nan
+        xy = res.get('xy_obs')         # rawdata.py:377-390: only S2 calls under a field-distortion model
+        tb['x_mean_electron'] = np.nan if xy is None else np.mean(xy[:, 0])
+        tb['y_mean_electron'] = np.nan if xy is None else np.mean(xy[:, 1])
         if np.isnan(tb['t_last_photon'][0]):
             tb['endtime'] = rows['time'][0]
         else:
@@ -465,6 +486,8 @@ class OracleSimulator:
         for k, val in res['truth'].items():
             tb[k] = val
         for f in INSTR_FIELDS:
+            if f not in rows.dtype.names:
+                continue
             val = rows[f]
             if len(rows) > 1 and f in 'xyz':
                 tb[f] = np.mean(val)
@@ -508,3 +531,72 @@ def chunk_boundaries(cfg, t_min_instr, groups, time_zero=None):
     ct = max((last_right + 1) * dt, pre + dt)
     out.append((pre, ct))
     return out
+
+
+class ReplayOracle(OracleSimulator):
+    """Scheduler, Pulse calls, digitiser, ZLE, record packing and truth rows on PRESET stage outputs:
+    the photons (time after transit-time spread, channel, gain, double-pe flag, PMT-afterpulse flag) and
+    electron times of every instruction, and the secondary instructions every S2 spawned.  Nothing is
+    sampled, so the result is a deterministic function of the presets -- comparable bit for bit with the
+    reference run on the same presets (tests/golden/make_golden_sched.py) and with the CUDA path run on
+    the photons it generated itself (tests/test_gpu_replay.py).
+
+      photons      structured array: id, t, channel, gain, dpe, ap  (id = instruction identity)
+      electrons    structured array: id, t
+      secondaries  instruction rows + `_id` + `_parent` (identity of the S2 that spawned each)
+      noise_seed   Philox seed of the noise start offsets (keyed by the first sample of the group)"""
+
+    def __init__(self, cfg, photons, electrons=None, secondaries=None, noise=None, noise_seed=0, xy_obs=None):
+        super().__init__(cfg, spe_table=np.zeros((len(cfg['gains']), 2001)), noise=noise)
+        self.ph = photons[np.argsort(photons['id'], kind='stable')]
+        self.el = None if electrons is None else electrons[np.argsort(electrons['id'], kind='stable')]
+        self.sec = secondaries
+        self.noise_seed = noise_seed
+        self.xy_obs = xy_obs
+
+    def noise_offset(self, first_sample, span):
+        from .philox import noise_offset
+        return noise_offset(self.noise_seed, first_sample, span, len(self.noise))
+
+    @staticmethod
+    def _take(arr, ids):
+        parts = []
+        for i in ids:
+            a, b = np.searchsorted(arr['id'], i, 'left'), np.searchsorted(arr['id'], i, 'right')
+            parts.append(arr[a:b])
+        return np.concatenate(parts) if parts else arr[:0]
+
+    def pulse_call(self, rows):
+        cfg = self.cfg
+        typ = int(rows['type'][0])
+        ids = rows['_id']
+        ph = self._take(self.ph, ids)
+        main, ap = ph[~ph['ap'].astype(bool)], ph[ph['ap'].astype(bool)]
+        te = None
+        if typ != 1:
+            te = self._take(self.el, ids)['t'] if self.el is not None else np.zeros(0, np.int64)
+        pulses = []
+        if not cfg.get('enable_pmt_afterpulses', True):
+            ap = ap[:0]
+        for part in (main, ap):           # the Pulse call itself, then its PMT afterpulses (rawdata.py:176-190)
+            live = part['channel'] >= 0
+            if live.any():
+                pulses.append(det.pulse_call(cfg, self.templates, part['t'][live], part['channel'][live],
+                                             part['gain'][live]))
+        P = det.Pulses.concat(pulses)
+        spawned = rows[:0].copy()
+        if typ == 2 and self.sec is not None and len(self.sec) and len(main):      # rawdata.py:193-201
+            sel = np.isin(self.sec['_parent'], ids) & (
+                ((self.sec['type'] == 4) & bool(cfg.get('enable_electron_afterpulses', True))) |
+                ((self.sec['type'] == 6) & bool(cfg.get('enable_gate_afterpulses', False))))
+            if sel.any():
+                spawned = np.zeros(int(sel.sum()), rows.dtype)
+                for n in rows.dtype.names:
+                    spawned[n] = self.sec[n][sel]
+        xy = None
+        if typ == 2 and self.xy_obs is not None:
+            xy = np.array([self.xy_obs[int(i)] for i in ids])
+        return dict(pulses=P, t=main['t'], te=te,
+                    truth=self.truth_counters(main['t'], main['channel'], main['gain'], main['dpe'].astype(bool)),
+                    spawned=spawned, spawned_have_ids=True, xy_obs=xy,
+                    end=(int(P.right.max()) * self.dt if len(P) else None))

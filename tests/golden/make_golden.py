@@ -219,6 +219,9 @@ def main():
     if 'chunks' in which:
         from tests.golden import make_golden_chunks
         make_golden_chunks.main(ref, c0_config)
+    if 'sched' in which:
+        from tests.golden import make_golden_sched
+        make_golden_sched.main(ref, c0_config)
     if 'stoch' in which:
         from tests.golden import make_golden_stoch
         make_golden_stoch.main(ref, c0_config)

@@ -61,6 +61,25 @@ def main(ref, c0_config):
     out['delay_he'] = t[~is_uni].astype(np.float32)
     out['delay_uniform'] = t[is_uni].astype(np.float32)
     out['n_direct'] = np.array([n, (~is_uni).sum(), is_uni.sum()])
+    # a larger photo-ionisation sample (drawn last, so the samples above stay what they were): many draws of
+    # electron_afterpulse (afterpulse.py:29-88) on S2 calls of known size -- per call the number of type-4
+    # instructions, per instruction the coarse delay (= -z / v), the electron count, r^2 and whether its
+    # time zero is one of the parent's photons
+    n2, d2, a2, r2, nph2, ok2 = [], [], [], [], [], []
+    for r in rows[:6]:
+        s2(np.array([r]))
+        for _ in range(60):
+            sec = pi.generate_instruction(s2, np.array([r]))
+            n2.append(len(sec))
+            nph2.append(len(s2._photon_timings))
+            if len(sec):
+                d2.append(-sec['z'].astype(np.float64) / cfg['drift_velocity_liquid'])
+                a2.append(sec['amp'])
+                r2.append(sec['x'].astype(np.float64) ** 2 + sec['y'].astype(np.float64) ** 2)
+                ok2.append(np.isin(sec['time'] + cfg['drift_time_gate'], s2._photon_timings))
+    out.update(pi2_n=np.array(n2, np.int32), pi2_n_parent_photons=np.array(nph2, np.int32),
+               pi2_delay=np.concatenate(d2).astype(np.float32), pi2_amp=np.concatenate(a2).astype(np.int32),
+               pi2_r2=np.concatenate(r2).astype(np.float32), pi2_t0_is_parent_photon=np.concatenate(ok2))
     for k, v in out.items():
         print(k, v.shape, v.dtype, float(np.mean(v)))
     np.savez_compressed(os.path.join(HERE, 'stoch_ap.npz'), **out)

@@ -70,6 +70,49 @@ def test_pmt_afterpulses_and_photoionization_vs_reference(gold):
     sim.close()
 
 
+def test_photoionization_instructions_vs_reference(gold):
+    """PhotoIonization_Electron.electron_afterpulse (afterpulse.py:29-88) against a sample drawn by the
+    reference (`pi2_*`, tests/golden/make_golden_ap.py): type-4 instructions per S2 call, their coarse
+    delays, electron counts and positions; time zero and the coarse grid are checked exactly.
+    k_photoionization draws an independent Poisson per coarse bin -- in law the reference's Poisson total
+    followed by binning (Poisson splitting)."""
+    from oracle.wfsim_oracle_sim import OracleSimulator
+    sim, cfg = make_sim(enable_pmt_afterpulses=False, enable_electron_afterpulses=True)
+    rows = fixed_rows(IDT, 2, AP_S2_AMP, 360, -30.0, spacing=20_000_000)
+    sec = sim.sample_secondaries(rows, seed=5)
+    ph = sim.sample_stage(rows, stage=0, seed=5)
+    prim = ph[(ph['flags'] & 4) == 0]
+    assert (sec['type'] == 4).all() and len(sec) > 1000
+    n_sec = np.bincount(sec['parent'], minlength=len(rows))
+    n_ph = np.bincount(prim['instruction'], minlength=len(rows))
+    # the S2 calls of the reference sample have the same size distribution (same instruction rows)
+    assert abs(n_ph.mean() - gold['pi2_n_parent_photons'].mean()) < 0.02 * n_ph.mean()
+    assert discrete_p(n_sec, gold['pi2_n']) > P_MIN
+    v = cfg['drift_velocity_liquid']
+    delay = -sec['z'].astype(np.float64) / v
+    assert ks_p(delay, gold['pi2_delay']) > P_MIN
+    assert discrete_p(sec['amp'], gold['pi2_amp']) > P_MIN or (sec['amp'] == 1).mean() > 0.99
+    assert abs((sec['amp'] == 1).mean() - (gold['pi2_amp'] == 1).mean()) < 0.01
+    r2 = sec['x'].astype(np.float64) ** 2 + sec['y'].astype(np.float64) ** 2
+    assert ks_p(r2, gold['pi2_r2']) > P_MIN
+    assert r2.max() <= cfg['tpc_radius'] ** 2 * (1 + 1e-6)
+    ang = np.arctan2(sec['y'], sec['x'])
+    from scipy import stats
+    assert stats.kstest(ang, stats.uniform(-np.pi, 2 * np.pi).cdf).pvalue > P_MIN
+    # exact: z = -coarse_time * v on the grid of _reduce_instruction_timing (afterpulse.py:63-80)
+    orc = OracleSimulator(cfg, spe_table=np.zeros((494, 2001)), ele_ap=EleApHist())
+    grid_z = (-orc.pi_coarse_grid() * v).astype(np.float32)
+    assert np.isin(sec['z'], grid_z).all()
+    # one instruction per (S2 call, coarse bin): np.unique(idx) in the reference
+    assert len(np.unique(np.stack([sec['parent'].astype(np.int64), sec['z'].view(np.int32).astype(np.int64)]), axis=1).T) == len(sec)
+    # exact: time zero is one of the parent's photons, minus drift_time_gate (afterpulse.py:49-56)
+    assert gold['pi2_t0_is_parent_photon'].all()
+    for i in np.unique(sec['parent'])[:40]:
+        t_par = prim['t'][prim['instruction'] == i]
+        assert np.isin(sec['time'][sec['parent'] == i] + int(cfg['drift_time_gate']), t_par).all()
+    sim.close()
+
+
 def test_pmt_afterpulse_delay_distributions(gold):
     """Parent-resolved delays: one channel, photons at t = 0 (afterpulse.py:212-223)."""
     sim, cfg = make_sim(enable_pmt_afterpulses=True, enable_electron_afterpulses=False)

@@ -386,7 +386,7 @@ __global__ void k_truth_pulses(int64_t n_pulses, PhotonBatch b, DeviceConfig c, 
 
 // Noise start offset per group (rawdata.py:407-417) when not supplied by the caller.
 __global__ void k_group_noise(int64_t n_groups, DeviceConfig c, const int64_t *group_lr,
-                              const int64_t *ix_in, uint64_t seed, int64_t group_base,
+                              const int64_t *ix_in, uint64_t seed,
                               int64_t *ix_out, int64_t *scalars) {
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_groups) return;
@@ -405,7 +405,9 @@ __global__ void k_group_noise(int64_t n_groups, DeviceConfig c, const int64_t *g
         int64_t high = c.noise_len - span - 1;
         if (high < 0) high = c.noise_len - 1;
         if (high > 0) {
-            Philox4 r = philox4x32(seed, RS_NOISE, (uint64_t)(group_base + g), 0);
+            // keyed by the first sample of the group's window: unique per group (groups are disjoint in
+            // time) and independent of how the run is cut into calls, device batches or GPU shards
+            Philox4 r = philox4x32(seed, RS_NOISE, (uint64_t)(lo - c.p.trigger_window), 0);
             uint64_t u = ((uint64_t)r.v[0] << 32) | r.v[1];
             ix = (int64_t)__umul64hi(u, (uint64_t)high);
         }
@@ -1317,7 +1319,7 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
                sg_.as<double>(), pulse_first_.as<uint32_t>(), pulse_win_.as<uint32_t>(),
                prim_.sort_vals_alt.as<uint32_t>());
     LAUNCH(k_group_noise, div_up(ng, T), T, ng, c, group_lr_.as<int64_t>(), b.ix_rand, b.seed,
-           b.group_base, group_ix_buf.as<int64_t>(), scal);
+           group_ix_buf.as<int64_t>(), scal);
     if (nw > 0) {
         // total tiles / interval slots live in win_scan[nwt]
         uint64_t tot;

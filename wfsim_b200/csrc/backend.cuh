@@ -39,9 +39,8 @@ struct PhotonBatch {
     const int32_t *pc_rank = nullptr;      // [n_pulse_calls] rank of the pulse call inside its group
     int32_t max_rank = 0;
     int64_t n_groups = 0;
-    const int64_t *ix_rand = nullptr;      // [n_groups] or nullptr -> Philox(seed, group_base + g)
+    const int64_t *ix_rand = nullptr;      // [n_groups] or nullptr -> Philox(seed, first sample of the group's window)
     uint64_t seed = 0;
-    int64_t group_base = 0;                // global index of group 0 of this batch (RNG counter)
     // Optional: the photons of group g are the ranges [group_start[r][g], group_start[r][g+1]),
     // r < group_ranges, of the arrays above (device array, [group_ranges][n_groups+1]; the generate
     // path has up to four runs: photons of the primaries, of the secondaries, and the PMT-afterpulse

@@ -65,9 +65,11 @@ struct LaunchCounter {
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-// Wait for the work queued on a stream: cudaStreamSynchronize (spinning), or with WFS_BLOCKING_SYNC=1 a
-// sleep on a blocking event (for hosts with very few cores per GPU; slower everywhere it was measured).
+// Wait for the work queued on a stream: cudaStreamSynchronize (spinning) while every lane thread of
+// every rank has a core of its own; a sleep on a blocking event when the lane threads would take more
+// than half of this rank's cores (WFS_BLOCKING_SYNC=0/1 overrides).
 cudaError_t stream_sync(cudaStream_t s);
+int host_cores_per_rank();   // cores of the affinity mask / LOCAL_WORLD_SIZE (transport.cu)
 
 constexpr int kSegSortMax = 8192;   // items per segment of Primitives::segment_sort_pairs
 

@@ -66,7 +66,10 @@ struct SchedIn {
     double v = 1.0;
 };
 
-static void schedule(const SchedIn &in, std::vector<Run> &runs, int32_t &n_groups) {
+// n_groups = number of group indices in use.  Only the last one can be without pulses (the counter moves on
+// when a non-empty cache is pushed out): it holds the trailing Pulse calls that made nothing (secondaries
+// without electrons, S1s without hits) and is reported with n_intervals = -1; *n_real = groups that digitise.
+static void schedule(const SchedIn &in, std::vector<Run> &runs, int32_t &n_groups, int32_t *n_real = nullptr) {
     const int64_t n_tot = (int64_t)in.stime.size();
     std::vector<std::vector<int32_t>> children((size_t)in.n_prim);
     for (int64_t i = in.n_prim; i < n_tot; i++) children[in.parent[i]].push_back((int32_t)i);
@@ -144,6 +147,7 @@ static void schedule(const SchedIn &in, std::vector<Run> &runs, int32_t &n_group
         finished = (k == in.clusters.size()) && buffer.empty();
     }
     flush();
+    if (n_real) *n_real = group;
     n_groups = 0;
     for (auto &r : runs) n_groups = std::max(n_groups, r.group + 1);
 }
@@ -154,7 +158,6 @@ struct BatchSpec {
 };
 
 struct Plan {
-    int64_t group_base = 0;      // wfs_instr_maps.group_base
     std::vector<int32_t> gg_lo, gg_hi;   // 'garfield_gas_gap' luminescence rows / fraction per instruction
     std::vector<double> gg_frac;
     std::vector<int64_t> opt_first;   // externally supplied photons: first list index / count per instruction
@@ -184,6 +187,21 @@ static int64_t env_i64(const char *name, int64_t dflt) {
     return s ? atoll(s) : dflt;
 }
 
+// Signal-time gap behind which nothing of the instructions in front can still arrive: the clustering
+// gap (rawdata.py:63) plus the longest delay of a secondary instruction an S2 can spawn (photo-ionisation
+// electrons: the end of the coarse delay grid, afterpulse.py:63-80; photo-electric electrons: 6 sigma
+// of their delay, :105-115).  Device batches, plugin pieces and GPU shards are all cut at such gaps only.
+static double quiet_gap_ns(const Handle *H) {
+    const wfs_params &p = H->cfg.p;
+    const bool secondaries = p.enable_electron_afterpulses && H->frontend && H->frontend->pi_coarse_len > 0;
+    double quiet = (double)p.right_raw_extension +
+                   (secondaries ? H->frontend->h_pi_coarse_time.back() + 50000.0 : 0.0);
+    if (p.enable_gate_afterpulses && p.photoelectric_p > 0.0)
+        quiet = std::max(quiet, (double)p.right_raw_extension + p.photoelectric_t_center + p.drift_time_gate +
+                                    6.0 * p.photoelectric_t_spread + 50000.0);
+    return quiet;
+}
+
 static void make_plan(Handle *H, const uint8_t *rows, int64_t n, const wfs_instr_maps *maps, Plan &P) {
     const wfs_params &p = H->cfg.p;
     parse_instructions(rows, n, P.instr);
@@ -210,7 +228,6 @@ static void make_plan(Handle *H, const uint8_t *rows, int64_t n, const wfs_instr
     P.scg.assign((size_t)n, P.scg_default);
     P.cy.assign((size_t)n, 1.0);
     P.patrow.assign((size_t)n, 0);
-    P.group_base = maps ? maps->group_base : 0;
     P.gg_lo.clear(); P.gg_hi.clear(); P.gg_frac.clear();
     if (p.s2_luminescence_model == 2) {
         if (!maps || !maps->gg_lo_row || !maps->gg_hi_row || !maps->gg_frac)
@@ -296,12 +313,7 @@ static void make_plan(Handle *H, const uint8_t *rows, int64_t n, const wfs_instr
     const int64_t ph_budget = env_i64("WFS_BATCH_PHOTONS", 48000000);
     const int64_t sample_budget = env_i64("WFS_BATCH_SAMPLES", 1500000000);
     const int64_t instr_budget = env_i64("WFS_BATCH_INSTRUCTIONS", 400000);
-    const bool secondaries = p.enable_electron_afterpulses && H->frontend && H->frontend->pi_coarse_len > 0;
-    double quiet = (double)p.right_raw_extension +
-                   (secondaries ? H->frontend->h_pi_coarse_time.back() + 50000.0 : 0.0);
-    if (p.enable_gate_afterpulses && p.photoelectric_p > 0.0)
-        quiet = std::max(quiet, (double)p.right_raw_extension + p.photoelectric_t_center + p.drift_time_gate +
-                                    6.0 * p.photoelectric_t_spread + 50000.0);
+    const double quiet = quiet_gap_ns(H);
     const int64_t n_cl = (int64_t)P.cluster_start.size() - 1;
     P.batches.clear();
     int64_t c0 = 0;
@@ -322,7 +334,7 @@ static void make_plan(Handle *H, const uint8_t *rows, int64_t n, const wfs_instr
         bool over2 = ph > 2 * ph_budget || smp > 2 * sample_budget || ni > 2 * instr_budget;
         if (over && c + 1 < n_cl) {
             double gap = (double)(P.stime[P.order[P.cluster_start[c + 1]]] - P.stime[P.order[P.cluster_start[c + 1] - 1]]);
-            if (gap > quiet || over2) {   // `secondaries` only documents why quiet is long
+            if (gap > quiet || over2) {
                 P.batches.push_back({c0, c + 1});
                 c0 = c + 1;
                 ph = smp = 0;
@@ -337,8 +349,8 @@ static void make_plan(Handle *H, const uint8_t *rows, int64_t n, const wfs_instr
 // Lanes: device batches are independent units (closed sets of instruction clusters), so batch k
 // runs on lane k % n_lanes -- a stream, a workspace set and a host thread of its own.  While one
 // lane's host thread replays the scheduler or waits for a count, the other lane's kernels keep
-// the GPU busy.  Group numbering (noise RNG identity) and output offsets are published in batch
-// order through `Order`, so results do not depend on the number of lanes.
+// the GPU busy.  Output offsets are published in batch order through `Order` (the noise RNG identity of a
+// digitisation group is its first sample), so results do not depend on the number of lanes.
 struct Lane {
     int id = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
@@ -351,8 +363,6 @@ struct Lane {
 struct Order {
     std::mutex mu;
     std::condition_variable cv;
-    int64_t sched_done = 0;      // batches [0, sched_done) have published their group count
-    int64_t group_base = 0;      // number of digitisation groups in those batches
     int64_t out_done = 0;        // batches [0, out_done) have reserved their output ranges
     bool abort = false;
 };
@@ -365,6 +375,7 @@ struct PhotonDump {     // wfs_sample_stage
     int stage = 0;
     uint8_t *out = nullptr;
     int64_t cap = 0, n = 0;
+    int64_t sec_base = 0;   // secondaries of the batches dumped so far: secondary ids count through the call
 };
 
 struct SimOut {
@@ -549,7 +560,8 @@ static void generate(Handle *H, Frontend &F, cudaStream_t s, uint64_t seed, int6
 static void write_truth_row(uint8_t *row, const HostInstr &h0, int run_type, int64_t time, float x, float y,
                             float z, int32_t amp, const int64_t *acc_sum /*A_COUNT summed*/,
                             long double ph_mean, long double ph_sigma, long double e_mean,
-                            long double e_sigma, int32_t trig_dpe, int32_t trig_dpe_b, const wfs_params &p) {
+                            long double e_sigma, int32_t trig_dpe, int32_t trig_dpe_b, const wfs_params &p,
+                            float x_mean_e, float y_mean_e) {
     const double nan = std::numeric_limits<double>::quiet_NaN();
     memset(row, 0, WFS_TRUTH_BYTES);
     wr<int32_t>(row + 0, h0.event_number);
@@ -585,8 +597,8 @@ static void write_truth_row(uint8_t *row, const HostInstr &h0, int run_type, int
     wr<double>(row + 154, t_last);
     wr<double>(row + 162, has_ph ? (double)ph_mean : nan);
     wr<double>(row + 170, has_ph ? (double)ph_sigma : nan);
-    wr<float>(row + 178, std::numeric_limits<float>::quiet_NaN());
-    wr<float>(row + 182, std::numeric_limits<float>::quiet_NaN());
+    wr<float>(row + 178, x_mean_e);      // rawdata.py:377-390
+    wr<float>(row + 182, y_mean_e);
     wr<double>(row + 186, has_e ? (double)acc_sum[A_ETMIN] : nan);
     wr<double>(row + 194, has_e ? (double)acc_sum[A_ETMAX] : nan);
     wr<double>(row + 202, has_e ? (double)e_mean : nan);
@@ -779,7 +791,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         if (nsec > 0) {
             ntot = nprim + nsec;
             grow_instr(F, ntot, nprim, s);
-            DevBuf d_parent;
+            struct Scoped : DevBuf { ~Scoped() { release(); } } d_parent;      // freed on every exit path
             d_parent.reserve(4 * (size_t)ntot);
             g = make_ctx(F, seed);
             if (nsec_pi)
@@ -848,10 +860,26 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
                     wr<int64_t>(r, t[q]); wr<double>(r + 8, gn[q]); wr<int32_t>(r + 16, ch[q]);
                     wr<int32_t>(r + 20, (int32_t)P.order[j0 + root]);
                     wr<int32_t>(r + 24, (int32_t)fl[q] | (sec ? 4 : 0));
-                    wr<int32_t>(r + 28, sec ? li - (int32_t)nprim : -1);
+                    wr<int32_t>(r + 28, sec ? (int32_t)(d.sec_base + li - nprim) : -1);
                 }
             }
             d.n += m;
+        } else if (d.stage == 4) {
+            // secondary instructions in full: t = time, the 8 gain bytes = float32 x, y; channel = amp,
+            // instruction = parent, flags = type, secondary = the bits of float32 z
+            const int64_t nsec = ntot - nprim;
+            for (int64_t q = 0; q < nsec; q++) {
+                if (base + q < d.cap) {
+                    uint8_t *r = d.out + (base + q) * 32;
+                    wr<int64_t>(r, sec_time[q]);
+                    wr<float>(r + 8, sec_x[q]); wr<float>(r + 12, sec_y[q]);
+                    wr<int32_t>(r + 16, sec_amp[q]);
+                    wr<int32_t>(r + 20, (int32_t)P.order[j0 + h_parent[q]]);
+                    wr<int32_t>(r + 24, sec_type[q]);
+                    wr<float>(r + 28, sec_z[q]);
+                }
+            }
+            d.n += nsec;
         } else if (d.stage >= 2) {
             // secondary instructions (photo-ionisation type 4, photo-electric type 6):
             // t = time, gain = z (stage 2) or x^2 + y^2 (stage 3), channel = amp, flags = type
@@ -865,7 +893,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
                     wr<int32_t>(r + 16, sec_amp[q]);
                     wr<int32_t>(r + 20, (int32_t)P.order[j0 + h_parent[q]]);
                     wr<int32_t>(r + 24, sec_type[q]);
-                    wr<int32_t>(r + 28, (int32_t)q);
+                    wr<int32_t>(r + 28, (int32_t)(d.sec_base + q));
                 }
             }
             d.n += nsec;
@@ -884,11 +912,12 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
                     wr<int64_t>(r, t[q]); wr<double>(r + 8, 0.0); wr<int32_t>(r + 16, (int32_t)np_[q]);
                     wr<int32_t>(r + 20, (int32_t)P.order[j0 + root]);
                     wr<int32_t>(r + 24, sec ? 4 : 0);
-                    wr<int32_t>(r + 28, sec ? li - (int32_t)nprim : -1);
+                    wr<int32_t>(r + 28, sec ? (int32_t)(d.sec_base + li - nprim) : -1);
                 }
             }
             d.n += n_emit;
         }
+        d.sec_base += ntot - nprim;
         return;
     }
     // ---- per-instruction truth accumulators ----
@@ -1015,17 +1044,10 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
                     (long long)max_group_photons);
     }
     const double ms_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
-    // ---- group numbering, in batch order ----
-    int64_t group_base = 0;
     {
-        std::unique_lock<std::mutex> lk(ord.mu);
-        ord.cv.wait(lk, [&] { return ord.abort || ord.sched_done == batch_index; });
+        std::lock_guard<std::mutex> lk(ord.mu);
         if (ord.abort) throw LaneAborted();
-        group_base = ord.group_base;
-        ord.group_base += ngroups;
-        ord.sched_done = batch_index + 1;
     }
-    ord.cv.notify_all();
     // ---- back end ----
     PhotonBatch b;
     b.n = n_ph + n_ap;
@@ -1039,7 +1061,6 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     b.max_rank = max_rank;
     b.n_groups = ngroups;
     b.seed = seed;
-    b.group_base = group_base;
     if (!gstart.empty()) {
         b.group_start = F.b_gstart.as<uint32_t>();
         b.group_ranges = n_ranges;
@@ -1089,9 +1110,9 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     if (ngroups > 0) {
         L.B->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res, compact ? &co : nullptr);
         if (res.error) {
-            H->last_error = res.error == WFS_E_PULSE_CACHE_TOO_LONG ? "Pulse cache too long"
-                                                                    : "back end error (key bits)";
-            throw std::runtime_error(H->last_error);
+            // reported through failure[] of run_plan: lanes never write the handle's error string
+            throw std::runtime_error(res.error == WFS_E_PULSE_CACHE_TOO_LONG ? "Pulse cache too long"
+                                                                             : "back end error (key bits)");
         }
         if (want_records && res.n_records > cap_here) {
             // the device buffer was too small: grow it and redo the back end
@@ -1223,8 +1244,17 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
             } else {
                 x = fx(i0); y = fy(i0); z = fz(i0); amp = fa(i0);
             }
+            // mean observed position of the S2 call under a field-distortion model (rawdata.py:377-390):
+            // the same model output the electrons were drifted with (wfs_instr_maps.x_obs / y_obs)
+            float xme = std::numeric_limits<float>::quiet_NaN(), yme = xme;
+            if (run.type == 2 && !P.xo.empty()) {
+                double sx = 0, sy = 0;
+                for (int32_t i : run.instr) { sx += P.xo[P.order[j0 + i]]; sy += P.yo[P.order[j0 + i]]; }
+                xme = (float)(sx / (double)run.instr.size());
+                yme = (float)(sy / (double)run.instr.size());
+            }
             write_truth_row(out->truth + (size_t)trow * WFS_TRUTH_BYTES, h0, run.type, T[i0], x, y, z,
-                            amp, rsum[r].sum, pm, psig, em, esig, trig[4 * r], trig[4 * r + 1], p);
+                            amp, rsum[r].sum, pm, psig, em, esig, trig[4 * r], trig[4 * r + 1], p, xme, yme);
             if (per_pmt) {
                 memcpy(out->truth_pmt_counts + (size_t)trow * 4 * n_ch, &pmt_cnt[(size_t)r * 4 * n_ch],
                        sizeof(int32_t) * 4 * (size_t)n_ch);
@@ -1355,7 +1385,6 @@ static int run_plan(Handle *H, Plan &P, uint64_t seed, wfs_outputs *out, wfs_cou
     cudaStream_t s = H->stream;
     WFS_CUDA_CHECK(cudaEventRecord(H->ev_a, s));
     Order ord;
-    ord.group_base = P.group_base;
     std::exception_ptr failure[8] = {};
     auto lane_loop = [&](int li) {
         try {
@@ -1558,6 +1587,65 @@ using namespace wfs;
     }
 
 extern "C" {
+
+int64_t wfs_quiet_gap(void *handle) {
+    Handle *H = reinterpret_cast<Handle *>(handle);
+    return H ? (int64_t)std::ceil(quiet_gap_ns(H)) : -1;
+}
+
+int wfs_schedule(int64_t right_raw_extension, double drift_velocity_liquid, int save_full_truth,
+                 int64_t n_prim, const int64_t *time, const float *z, const int8_t *type,
+                 int64_t n_sec, const int64_t *sec_time, const float *sec_z, const int8_t *sec_type,
+                 const int32_t *sec_parent, const int64_t *pulse_end, int32_t *run_of, int32_t *run_type,
+                 int32_t *run_group, int64_t cap_runs, int64_t *n_runs, int64_t *n_groups) {
+    try {
+        if (n_prim < 0 || n_sec < 0 || !n_runs || !n_groups) return WFS_E_ARG;
+        const int64_t n_tot = n_prim + n_sec;
+        // primaries in signal-time order, clustered at gaps > rext: what make_plan hands to a device batch
+        std::vector<int64_t> st((size_t)n_prim), order((size_t)n_prim), where((size_t)n_prim);
+        for (int64_t i = 0; i < n_prim; i++) {
+            st[i] = signal_time(time[i], z[i], type[i], drift_velocity_liquid);
+            order[i] = i;
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return st[a] < st[b]; });
+        for (int64_t j = 0; j < n_prim; j++) where[order[j]] = j;
+        SchedIn in;
+        in.n_prim = n_prim;
+        in.rext = right_raw_extension;
+        in.save_full_truth = save_full_truth != 0;
+        in.v = drift_velocity_liquid;
+        in.stime.resize(n_tot); in.type.resize(n_tot); in.parent.assign(n_tot, -1); in.pend.resize(n_tot);
+        for (int64_t j = 0; j < n_prim; j++) {
+            in.stime[j] = st[order[j]];
+            in.type[j] = type[order[j]];
+            in.pend[j] = pulse_end[order[j]];
+            if (j == 0 || in.stime[j] - in.stime[j - 1] > in.rext) in.clusters.push_back({(int32_t)j, (int32_t)j});
+            in.clusters.back().second = (int32_t)(j + 1);
+        }
+        for (int64_t k = 0; k < n_sec; k++) {
+            if (sec_parent[k] < 0 || sec_parent[k] >= n_prim) return WFS_E_ARG;
+            in.stime[n_prim + k] = signal_time(sec_time[k], sec_z[k], sec_type[k], drift_velocity_liquid);
+            in.type[n_prim + k] = sec_type[k];
+            in.parent[n_prim + k] = (int32_t)where[sec_parent[k]];
+            in.pend[n_prim + k] = pulse_end[n_prim + k];
+        }
+        std::vector<Run> runs;
+        int32_t ngroups = 0, nreal = 0;
+        schedule(in, runs, ngroups, &nreal);
+        *n_runs = (int64_t)runs.size();
+        *n_groups = nreal;
+        if ((int64_t)runs.size() > cap_runs) return WFS_E_CAPACITY;
+        for (int64_t i = 0; i < n_tot; i++) run_of[i] = -1;
+        for (size_t r = 0; r < runs.size(); r++) {
+            run_type[r] = runs[r].type;
+            run_group[r] = runs[r].group;
+            for (int32_t i : runs[r].instr) run_of[i < n_prim ? order[i] : i] = (int32_t)r;
+        }
+        return 0;
+    } catch (const std::exception &) {
+        return WFS_E_ARG;
+    }
+}
 
 int wfs_simulate(void *handle, const uint8_t *instructions, int64_t n_instructions,
                  const wfs_instr_maps *maps, uint64_t seed, wfs_outputs *out, wfs_counts *counts) {

@@ -1,6 +1,7 @@
 // Per-GPU simulator handle: device tables, streams, workspaces, back end + front end.
 #pragma once
 #include "backend.cuh"
+#include <mutex>
 
 namespace wfs {
 
@@ -41,8 +42,9 @@ struct Handle {
         if (cudaPointerGetAttributes(&attr, dst) != cudaSuccess) { cudaGetLastError(); return true; }
         return attr.type != cudaMemoryTypeHost;      // pinned destination: plain DMA straight into it
     }
-    HostPool *host_pool() {
-        if (!pool) pool = new HostPool(HostPool::default_threads());
+    std::once_flag pool_once;
+    HostPool *host_pool() {            // lanes call this from their own host threads
+        std::call_once(pool_once, [this] { pool = new HostPool(HostPool::default_threads()); });
         return pool;
     }
     int16_t record_fill() const { return (int16_t)std::max(cfg.p.baseline, 0); }

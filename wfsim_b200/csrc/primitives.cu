@@ -10,9 +10,13 @@ namespace wfs {
 
 static bool blocking_sync_mode() {
     // measured on a 4-GPU box with 8 cores per rank: sleeping on a blocking event costs more (144 ms per
-    // step) than the spinning waits take from the other ranks (119 ms): off unless asked for
+    // step) than the spinning waits take from the other ranks (119 ms) -- so spin while the lane threads
+    // leave at least half of the rank's cores to the record expanders, sleep when they would not
+    // (8 ranks on 32 cores: 3 spinning lanes would take 3 of the 4 cores of a rank)
     if (const char *e = getenv("WFS_BLOCKING_SYNC")) return atoi(e) != 0;
-    return false;
+    const char *l = getenv("WFS_LANES");
+    const int lanes = l ? std::max(1, atoi(l)) : 3;
+    return 2 * lanes > host_cores_per_rank();
 }
 
 cudaError_t stream_sync(cudaStream_t s) {

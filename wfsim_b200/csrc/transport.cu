@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -55,12 +56,20 @@ void ExpandJob::abandon() {
     cv.notify_all();
 }
 
+int host_cores_per_rank() {
+    // the cores this process may run on (cgroup / taskset aware, unlike hardware_concurrency), shared
+    // with the LOCAL_WORLD_SIZE - 1 other per-GPU processes of the box (torchrun sets it)
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int hw = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : 0;
+    if (hw <= 0) hw = (int)std::thread::hardware_concurrency();
+    if (const char *w = getenv("LOCAL_WORLD_SIZE")) hw /= std::max(1, atoi(w));
+    return std::max(1, hw);
+}
+
 int HostPool::default_threads() {
     if (const char *e = getenv("WFS_EXPAND_THREADS")) return std::max(1, atoi(e));
-    // one process per GPU shares the host with LOCAL_WORLD_SIZE - 1 others (torchrun sets it)
-    int hw = (int)std::thread::hardware_concurrency();
-    if (const char *w = getenv("LOCAL_WORLD_SIZE")) hw /= std::max(1, atoi(w));
-    return std::max(1, std::min(16, hw - 2));
+    return std::max(1, std::min(16, host_cores_per_rank() - 2));
 }
 
 HostPool::HostPool(int n_threads) {

@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'csrc', 'libwfsim_b200.so')
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 E_CAPACITY = 1
 E_CUDA = -1
 E_ARG = -2
@@ -79,7 +79,7 @@ class InstrMaps(C.Structure):
     _fields_ = [('s1_lce', vp), ('s2_sc_gain', vp), ('s2_cy_extra', vp), ('pattern', vp),
                 ('pattern_row', vp), ('n_pattern_rows', i64), ('s2_sc_gain_default', f64),
                 ('rng_id', vp), ('drift_velocity', vp), ('diffusion_long', vp), ('x_obs', vp), ('y_obs', vp),
-                ('group_base', i64), ('opt_first', vp), ('opt_last', vp), ('opt_channels', vp), ('opt_timings', vp),
+                ('opt_first', vp), ('opt_last', vp), ('opt_channels', vp), ('opt_timings', vp),
                 ('n_opt', i64), ('opt_time_cutoff', i64), ('gg_lo_row', vp), ('gg_hi_row', vp), ('gg_frac', vp),
                 ('hdiff_sigma_r', vp), ('hdiff_sigma_a', vp), ('lum_gap', vp), ('lum_e0', vp)]
 
@@ -114,7 +114,7 @@ class GroupInfo(C.Structure):
 EXPORTS = ['wfs_create', 'wfs_destroy', 'wfs_last_error', 'wfs_abi_version', 'wfs_struct_sizes',
            'wfs_device_count', 'wfs_host_alloc', 'wfs_host_free', 'wfs_simulate_photons',
            'wfs_simulate', 'wfs_stage_instructions', 'wfs_run_staged', 'wfs_sample_stage',
-           'wfs_expand_compact']
+           'wfs_expand_compact', 'wfs_quiet_gap', 'wfs_schedule']
 
 _lib = None
 
@@ -142,6 +142,10 @@ def load():
     lib.wfs_host_alloc.argtypes = [i64]
     lib.wfs_host_free.argtypes = [vp]
     lib.wfs_destroy.argtypes = [vp]
+    lib.wfs_schedule.argtypes = [i64, f64, C.c_int, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i64,
+                                 C.POINTER(i64), C.POINTER(i64)]
+    lib.wfs_quiet_gap.restype = i64
+    lib.wfs_quiet_gap.argtypes = [vp]
     lib.wfs_expand_compact.argtypes = [vp, vp, i64, vp, C.c_int, C.c_int, C.c_int]
     lib.wfs_create.argtypes = [C.POINTER(Params), C.POINTER(Tables), C.c_int, C.POINTER(vp)]
     lib.wfs_simulate_photons.argtypes = [

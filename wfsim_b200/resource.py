@@ -177,14 +177,16 @@ def _on_device(m, nd, n_ch, need_full):
     return ok and (vals.shape[-1] == n_ch or not need_full)
 
 
-def evaluate_instruction_maps(config, resource, instructions, seed=0, device_patterns=True):
+def evaluate_instruction_maps(config, resource, instructions, seed=0, device_patterns=True, rng_id=None):
     """Per-instruction map values handed to the device (struct wfs_instr_maps):
     S1 light yield (s1.py:125), observed S2 positions after the field-distortion model
     (s2.py:80-87), S2 secondary-scintillation gain (s2.py:182-209), the survival / extraction
     factor of the electron yield (s2.py:227-252), drift velocity / longitudinal diffusion from the
     field-dependency maps (s2.py:139-179) and the un-normalised PMT patterns (s1.py:148,
-    s2.py:637-665, with the optional area-fraction-top smearing)."""
+    s2.py:637-665, with the optional area-fraction-top smearing -- its draw is a Philox function of
+    (seed, rng_id of the instruction; default: its index), like every draw on the device)."""
     n = len(instructions)
+    rng_id = np.arange(n, dtype=np.uint64) if rng_id is None else np.asarray(rng_id, np.uint64)
     n_ch = len(config['gains'])
     typ = instructions['type']
     is_s1 = typ == 1
@@ -321,16 +323,15 @@ def evaluate_instruction_maps(config, resource, instructions, seed=0, device_pat
         if is_s2_map and pat.shape[1] < n_ch:        # top-only S2 map: s2.py:642-644
             pat = np.pad(pat, [[0, 0], [0, n_ch - pat.shape[1]]], 'constant', constant_values=1)
         if smear:                                    # s2.py:660-665
-            from scipy.stats import skewnorm
-            rng = np.random.default_rng([int(seed) & 0xffffffff, 0xAF7])
+            from .philox import skewnorm
             n_top = int(config['n_top_pmts'])
             pat = pat.copy()
             pat[:, np.asarray(config['gains']) == 0] = 0
             tot = pat.sum(axis=1, keepdims=True)
             pat = np.divide(pat, tot, out=np.zeros_like(pat), where=tot != 0)
             cur = pat[:, :n_top].sum(axis=1) / pat.sum(axis=1)
-            new = np.clip(cur * skewnorm.rvs(loc=1.0, scale=aft_sigma, a=config.get('s2_aft_skewness', 0.0),
-                                             size=len(cur), random_state=rng), 0, 1)
+            new = np.clip(cur * skewnorm(seed, rng_id[mask], 1.0, aft_sigma, config.get('s2_aft_skewness', 0.0)),
+                          0, 1)
             pat[:, :n_top] *= (new / cur)[:, None]
             pat[:, n_top:] *= ((1 - new) / (1 - cur))[:, None]
         base = sum(len(r) for r in rows)

@@ -11,19 +11,32 @@ def signal_time(instructions, drift_velocity_liquid):
     return instructions['time'].astype(np.int64) + (zf * k).astype(np.int64)
 
 
+def default_quiet_gap(config):
+    """Upper bound of Simulator.quiet_gap() (wfs_quiet_gap) from the config alone, for callers that hold
+    no handle: the clustering gap plus the longest delay of a secondary an S2 can spawn -- photo-ionisation
+    electrons up to the end of the delay histogram of the afterpulse file (bounded here by 1 ms or two full
+    drift lengths, whichever is longer), photo-electric electrons 6 sigma behind their centre."""
+    gap = int(config.get('right_raw_extension', 100000))
+    extra = 0
+    if config.get('enable_electron_afterpulses', False):
+        extra = max(int(2 * config.get('tpc_length', 150) / config['drift_velocity_liquid']), 1000000) + 50000
+    if config.get('enable_gate_afterpulses', False):
+        extra = max(extra, int(config.get('photoelectric_t_center', 0) + config.get('drift_time_gate', 0)
+                               + 6 * config.get('photoelectric_t_spread', 0)) + 50000)
+    return gap + extra
+
+
 def shard_instructions(instructions, n_shards, config, min_gap=None):
     """Indices of `instructions` per shard: contiguous in signal time, cut only at gaps larger than
-    `min_gap` (default: right_raw_extension plus the longest photo-ionisation delay when electron
-    afterpulses are enabled), balanced by sum(amp) as a photon-count proxy.  Shards may be empty."""
+    `min_gap` (Simulator.quiet_gap(): what the library cuts its device batches at; default:
+    default_quiet_gap(config)), balanced by sum(amp) as a photon-count proxy.  Shards may be empty."""
     n = len(instructions)
     if n == 0:
         return [np.zeros(0, np.int64) for _ in range(n_shards)]
     st = signal_time(instructions, config['drift_velocity_liquid'])
     order = np.argsort(st, kind='stable')
     if min_gap is None:
-        min_gap = int(config.get('right_raw_extension', 100000))
-        if config.get('enable_electron_afterpulses', False):
-            min_gap += int(config.get('tpc_length', 150) / config['drift_velocity_liquid']) + 100000
+        min_gap = default_quiet_gap(config)
     gaps = np.diff(st[order])
     cut_ok = np.flatnonzero(gaps > min_gap) + 1            # positions where a cut is allowed
     w = np.cumsum(instructions['amp'][order].astype(np.float64))
@@ -47,7 +60,12 @@ def merge_results(results):
     time order)."""
     keys = ('raw_records', 'raw_records_he', 'raw_records_aqmon', 'truth', 'groups')
     results = [r for r in results if r is not None]
-    return {k: np.concatenate([r[k] for r in results]) for k in keys}
+    out = {k: np.concatenate([r[k] for r in results]) for k in keys}
+    for k in keys[:3]:      # shards are cut at quiet gaps; should one ever reach back, restore the order
+        r = out[k]
+        if len(r) > 1 and (np.diff(r['time']) < 0).any():
+            out[k] = r[np.lexsort((r['channel'], r['time']))]
+    return out
 
 
 class ShardedSimulator:
@@ -66,7 +84,7 @@ class ShardedSimulator:
 
     def simulate(self, instructions, seed=0):
         from concurrent.futures import ThreadPoolExecutor
-        parts = shard_instructions(instructions, len(self.sims), self.config)
+        parts = shard_instructions(instructions, len(self.sims), self.config, min_gap=self.sims[0].quiet_gap())
 
         def run(k):
             idx = parts[k]

@@ -87,6 +87,11 @@ class Simulator:
         except Exception:
             pass
 
+    def quiet_gap(self):
+        """Smallest signal-time gap [ns] at which a run may be cut into independent calls (pieces,
+        shards) -- the bound the library itself cuts its device batches at (wfs_quiet_gap)."""
+        return int(self.lib.wfs_quiet_gap(self.handle))
+
     def _raise(self, rc):
         msg = self.lib.wfs_last_error(self.handle).decode()
         if rc == wlib.E_PULSE_CACHE_TOO_LONG:
@@ -141,11 +146,11 @@ class Simulator:
         return out
 
     # -----------------------------------------------------------------------------------------
-    def _maps_struct(self, instructions, maps=None, rng_id=None, seed=0, group_base=0, optical=None):
+    def _maps_struct(self, instructions, maps=None, rng_id=None, seed=0, optical=None):
         if maps is None:
             if self.resource is None or isinstance(self.resource, dict):
                 raise SimulatorError('simulate() needs a Resource (maps) -- pass resource= to Simulator')
-            maps = evaluate_instruction_maps(self.config, self.resource, instructions, seed=seed)
+            maps = evaluate_instruction_maps(self.config, self.resource, instructions, seed=seed, rng_id=rng_id)
         keep = {k: np.ascontiguousarray(v, dtype=(np.float32 if k == 'pattern' else
                                                    np.int32 if k in ('pattern_row', 'gg_lo_row', 'gg_hi_row')
                                                    else np.float64))
@@ -158,7 +163,6 @@ class Simulator:
         m.pattern_row = _ptr(keep['pattern_row'])
         m.n_pattern_rows = keep['pattern'].shape[0]
         m.s2_sc_gain_default = 0.0
-        m.group_base = int(group_base)
         if optical is not None:
             # externally supplied photons (RawDataOptical, rawdata.py:461-495): optical = (first, last,
             # channels, timings); `first` / `last` are the `_first` / `_last` columns of the instructions
@@ -197,7 +201,7 @@ class Simulator:
         return c
 
     def simulate(self, instructions, seed=0, maps=None, cap_records=None, pinned=False, rng_id=None,
-                 per_pmt_truth=None, records_out=None, group_base=0, optical=None):
+                 per_pmt_truth=None, records_out=None, optical=None):
         """Full path for one set of instructions (see wfs_simulate in the header).
 
         Returns dict(raw_records, raw_records_he, raw_records_aqmon, truth, groups); records of
@@ -214,7 +218,7 @@ class Simulator:
         if instructions.dtype.itemsize != 70:
             raise ValueError('instructions must have the packed 70-byte instruction_dtype')
         n = len(instructions)
-        m, keep = self._maps_struct(instructions, maps, rng_id, seed=seed, group_base=group_base, optical=optical)
+        m, keep = self._maps_struct(instructions, maps, rng_id, seed=seed, optical=optical)
         counts = wlib.Counts()
         cap_rec = int(cap_records) if cap_records is not None else \
             (len(records_out) if records_out is not None else max(4096, 1500 * n))
@@ -292,7 +296,10 @@ class Simulator:
                 full[f + '_per_pmt'] = pmt_areas[:len(truth), k]
             truth = full
         res['truth'] = truth
-        res['groups'] = groups[:counts.n_groups]
+        groups = groups[:counts.n_groups]
+        # n_intervals < 0 marks a group index without pulses (trailing Pulse calls that made nothing, at the
+        # end of a device batch): the reference digitises nothing for it (rawdata.py:207-208)
+        res['groups'] = groups[groups['n_intervals'] >= 0]
         res['_pinned'] = None
         return res
 
@@ -330,6 +337,14 @@ class Simulator:
 
     PHOTON_DUMP_DTYPE = np.dtype([('t', np.int64), ('gain', np.float64), ('channel', np.int32),
                                   ('instruction', np.int32), ('flags', np.int32), ('secondary', np.int32)])
+
+    SECONDARY_DUMP_DTYPE = np.dtype([('time', np.int64), ('x', np.float32), ('y', np.float32), ('amp', np.int32),
+                                     ('parent', np.int32), ('type', np.int32), ('z', np.float32)])
+
+    def sample_secondaries(self, instructions, seed=0, maps=None):
+        """The secondary (type 4 / 6) instructions the S2 calls spawn (stage 4 of wfs_sample_stage): row k
+        is the secondary the photon / electron dumps call `secondary == k`."""
+        return self.sample_stage(instructions, stage=4, seed=seed, maps=maps).view(self.SECONDARY_DUMP_DTYPE)
 
     def sample_stage(self, instructions, stage=0, seed=0, maps=None, optical=None):
         """Front-end only: photons (stage 0) or emitters/electrons (stage 1) as a structured array

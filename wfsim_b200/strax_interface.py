@@ -135,7 +135,7 @@ class _ArenaPool:
         return self.arenas[-1]
 
 
-def _pieces(instructions, config, piece_max, time_zero=None):
+def _pieces(instructions, config, piece_max, time_zero=None, min_gap=None):
     """Index arrays of the pieces the run is simulated in: contiguous in signal time, cut only at quiet
     gaps (sharding.shard_instructions explains which), first where the chunk clock will cut -- so that the
     records of a chunk come from one library call and are handed on without a copy -- then further down to
@@ -145,9 +145,9 @@ def _pieces(instructions, config, piece_max, time_zero=None):
     st = signal_time(instructions, config['drift_velocity_liquid'])
     order = np.argsort(st, kind='stable')
     sts = st[order]
-    min_gap = int(config.get('right_raw_extension', 100000))
-    if config.get('enable_electron_afterpulses', False):
-        min_gap += int(config.get('tpc_length', 150) / config['drift_velocity_liquid']) + 100000
+    if min_gap is None:
+        from .sharding import default_quiet_gap
+        min_gap = default_quiet_gap(config)
     cut_ok = np.flatnonzero(np.diff(sts) > min_gap) + 1
     cuts = set()
     if len(cut_ok):
@@ -220,10 +220,12 @@ class ChunkRawRecords(object):
         # The run is simulated PIECE BY PIECE (contiguous in signal time, cut only at quiet gaps, so the
         # pieces are independent) and the chunks are yielded as soon as they are complete: host memory is
         # bounded by one piece (config 'b200_piece_instructions', default 40000) instead of the whole run.
-        # Philox identities are the instruction indices and the noise draws are keyed by the running
-        # group number, so the records do not depend on how the run is cut.
+        # Philox identities are the instruction indices and the noise draw of a digitisation group is keyed
+        # by its first sample, so the records do not depend on how the run is cut.
         piece = max(int(cfg.get('b200_piece_instructions', 40000)), 1)
-        parts = _pieces(instructions, cfg, piece, time_zero)
+        # pieces are cut at the gaps the library itself cuts its device batches at (wfs_quiet_gap)
+        quiet = self.simulator.quiet_gap() if hasattr(self.simulator, 'quiet_gap') else None
+        parts = _pieces(instructions, cfg, piece, time_zero, min_gap=quiet)
         clock = ChunkClock(cfg, np.min(instructions['time']), time_zero)
         keys = ('raw_records', 'raw_records_he', 'raw_records_aqmon')
         side = {k: [] for k in keys[1:]}    # he / aqmon records not yet delivered (few): arrays in time order
@@ -261,12 +263,18 @@ class ChunkRawRecords(object):
             nonlocal held_truth, a0
             res = {}
             rec = arena[a0:used] if arena is not None else empty
+            if len(rec) > 1 and not last and (np.diff(rec['time']) < 0).any():
+                # pieces are cut at quiet gaps, so their records follow each other in time; should a piece
+                # ever reach back behind its predecessor, restore the (time, channel) order in place
+                rec[:] = rec[np.lexsort((rec['channel'], rec['time']))]
             stop = len(rec) if last else int(np.searchsorted(rec['time'], ct, side='right'))
             res['raw_records'] = rec[:stop]
             a0 += stop
             for k in keys[1:]:
                 parts_k = [x for x in side[k] if len(x)]
                 rec = empty if not parts_k else parts_k[0] if len(parts_k) == 1 else np.concatenate(parts_k)
+                if len(rec) > 1 and (np.diff(rec['time']) < 0).any():
+                    rec = rec[np.lexsort((rec['channel'], rec['time']))]
                 stop = len(rec) if last else int(np.searchsorted(rec['time'], ct, side='right'))
                 res[k], side[k] = rec[:stop], [rec[stop:]]
             # truth rows of this chunk (strax_interface.py:458-483)
@@ -296,7 +304,7 @@ class ChunkRawRecords(object):
             room_for(max(instr_per_chunk, len(idx)) if delivered else len(idx), fresh=delivered and arena is not None)
             delivered = False
             out = self.simulator.simulate(instructions[idx], seed=self.seed, rng_id=idx.astype(np.uint64),
-                                          group_base=n_groups, optical=optical, records_out=arena[used:])
+                                          optical=optical, records_out=arena[used:])
             if optical is not None:
                 out['truth'] = _with_optical_columns(out['truth'], instructions[idx], tdt)
             n_groups += len(out['groups'])
