@@ -238,10 +238,13 @@ typedef struct wfs_counts {
     double ms_h2d, ms_d2h;
     /* device time per phase, summed over batches (CUDA events on the library stream):
      * 0 sampling front end, 1 photon keys + sort, 2 pulses/windows, 3 digitize, 4 ZLE,
-     * 5 record keys + sort, 6 record pack, 7 host scheduler + truth (wall clock); compact transport
+     * 5 record keys + sort, 6 record pack (or plain -> compact transport form), 7 host scheduler + truth (wall clock); compact transport
      * (wall clock): 8 batch shipped -> its D2H copies complete, 9 copies complete -> expanded;
      * 10 / 11: number of batches whose photons / records were ordered per group in shared memory */
     double ms_phase[12];
+    int64_t n_fused_batches;        /* device batches that went through the group-resident fused kernel (one CTA per
+                                     * digitisation group, photons -> records; then ms_phase[3] is that kernel and
+                                     * phases 1, 2, 4, 5 are zero) */
 } wfs_counts;
 
 /* Digitisation-group bookkeeping returned to the host-side chunker

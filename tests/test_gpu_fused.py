@@ -1,0 +1,128 @@
+"""GPU: the group-resident fused back end (csrc/fused.cu: one CTA per digitisation group, photons ->
+records) against the multi-pass back end (csrc/backend.cu) on the same photons: records, truth rows,
+group bookkeeping and counters must be identical byte for byte.  The multi-pass path is itself bit-exact
+against the reference's records (tests/test_gpu_deterministic.py, golden det_*.npz), and both are
+compared with the oracle on the GPU's photons in tests/test_gpu_replay.py."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.golden.synth_instructions import c0_like, c1_like
+from tests.test_gpu_afterpulse_plugin import make_sim
+
+pytestmark = pytest.mark.gpu
+
+
+class env:
+    def __init__(self, **kv):
+        self.kv = kv
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        os.environ.update({k: str(v) for k, v in self.kv.items()})
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+def both_paths(sim, inst, seed, **kw):
+    with env(WFS_FUSED=1):
+        a = sim.simulate(inst, seed=seed, **kw)
+        ca = dict(sim.last_counts)
+    with env(WFS_FUSED=0):
+        b = sim.simulate(inst, seed=seed, **kw)
+        cb = dict(sim.last_counts)
+    assert ca['n_fused_batches'] == ca['n_batches'] > 0, 'the fused kernel did not run'
+    assert cb['n_fused_batches'] == 0
+    return a, b, ca, cb
+
+
+def assert_same(a, b, ca, cb):
+    for k in ('raw_records', 'raw_records_he', 'raw_records_aqmon', 'truth', 'groups'):
+        assert len(a[k]) == len(b[k]), k
+        assert a[k].tobytes() == b[k].tobytes(), k
+    for k in ('n_records', 'n_records_total', 'n_truth', 'n_photons', 'n_pe', 'n_pulses', 'n_windows', 'n_intervals',
+              'n_samples', 'n_groups', 'n_pulse_calls'):
+        assert ca[k] == cb[k], k
+    assert len(a['raw_records']) > 0
+
+
+CONFIGS = {
+    'c0': (dict(), lambda: c0_like(14, seed=3)),
+    'c1_low_energy': (dict(), lambda: c1_like(300, seed=5)),
+    'afterpulses': (dict(enable_pmt_afterpulses=True, enable_electron_afterpulses=True), lambda: c0_like(12, seed=4, e_range=(5, 60))),
+    'pile_up_merged': (dict(enable_pmt_afterpulses=True, save_full_truth=False),
+                       lambda: c0_like(30, seed=6, event_rate=6000.0, e_range=(2, 30))),
+    'thresholds': (dict(zle_threshold=40, special_thresholds={'7': 60, '255': 5, '300': 25}), lambda: c0_like(10, seed=7)),
+    'gate': (dict(enable_gate_afterpulses=True, photoelectric_p=0.004), lambda: c0_like(10, seed=8)),
+}
+
+
+@pytest.mark.parametrize('name', list(CONFIGS))
+def test_fused_back_end_equals_multi_pass_back_end(name):
+    extra, make = CONFIGS[name]
+    sim, cfg = make_sim(**extra)
+    a, b, ca, cb = both_paths(sim, make(), seed=31)
+    assert_same(a, b, ca, cb)
+    sim.close()
+
+
+def test_fused_with_dead_pmts_and_per_pmt_truth():
+    from wfsim_b200.resource import Resource
+    from wfsim_b200.simulator import Simulator
+    from tests.conftest import load_c0_config
+    from tests.test_gpu_afterpulse_plugin import spe
+    cfg = load_c0_config(per_pmt_truth=True)
+    gains = cfg['gains'].copy()
+    gains[[3, 100, 300, 493]] = 0
+    cfg['gains'] = gains
+    uniq, row = spe()
+    sim = Simulator(cfg, resource=Resource(cfg, spe_ppf=uniq, spe_row=row))
+    a, b, ca, cb = both_paths(sim, c0_like(8, seed=9), seed=5)
+    assert_same(a, b, ca, cb)
+    assert a['truth']['n_photon_per_pmt'].sum() == a['truth']['n_photon'].sum()
+    assert not np.isin(a['raw_records']['channel'], [3, 100, 300, 493]).any()
+    sim.close()
+
+
+def test_fused_over_several_batches_lanes_and_transports():
+    """Several device batches on several lanes; compact transport (pageable destination) against the plain
+    DMA (pinned destination); a record buffer that is too small is grown and the call repeated."""
+    sim, cfg = make_sim(enable_pmt_afterpulses=True, enable_electron_afterpulses=True)
+    inst = c0_like(40, seed=11, e_range=(3, 50))
+    with env(WFS_FUSED=1):
+        ref = sim.simulate(inst, seed=2)
+        with env(WFS_BATCH_INSTRUCTIONS=10):
+            cut = sim.simulate(inst, seed=2)
+            assert sim.last_counts['n_batches'] > 2 and sim.last_counts['n_fused_batches'] == sim.last_counts['n_batches']
+            pinned = sim.simulate(inst, seed=2, pinned=True)
+            small = sim.simulate(inst, seed=2, cap_records=100)
+    for other in (cut, pinned, small):
+        for k in ('raw_records', 'raw_records_he', 'truth', 'groups'):
+            assert other[k].tobytes() == ref[k].tobytes(), k
+    sim.close()
+
+
+def test_groups_that_do_not_fit_take_the_multi_pass_path():
+    """A heavy S2 (more photons than a CTA holds) sends its batch through the multi-pass back end; the
+    light batches of the same call still use the fused kernel; the result does not depend on that."""
+    sim, cfg = make_sim()
+    inst = c0_like(12, seed=13, e_range=(2, 20))
+    inst['amp'][inst['type'] == 2][:1] = 1
+    heavy = np.flatnonzero(inst['type'] == 2)[5]
+    inst['amp'][heavy] = 4000                      # ~ 70 000 photons in one group
+    with env(WFS_BATCH_INSTRUCTIONS=4):
+        with env(WFS_FUSED=1):
+            a = sim.simulate(inst, seed=3)
+            ca = dict(sim.last_counts)
+        with env(WFS_FUSED=0):
+            b = sim.simulate(inst, seed=3)
+    assert 0 < ca['n_fused_batches'] < ca['n_batches']
+    for k in ('raw_records', 'truth', 'groups'):
+        assert a[k].tobytes() == b[k].tobytes(), k
+    sim.close()

@@ -62,6 +62,18 @@ Handle::Handle(const wfs_params &p, const wfs_tables &t, int dev) : device(dev) 
         cfg.noise_len = t.noise_len;
         cfg.noise_nch = t.noise_nch;
     }
+    {
+        const int base = std::max(p.baseline, 0);
+        const bool noisy = p.enable_noise && cfg.noise_t;
+        for (int ch = 0; ch < p.n_tpc_pmts; ch++) {
+            if (t.zle_thresholds[ch] > base) cfg.thr_above_baseline = true;
+            if (p.detector_nt && ch < p.n_top_pmts) {
+                const int hch = p.he_first + ch;
+                if (p.he_mult != 0 || (noisy && hch < cfg.noise_nch) || (hch < p.n_rows && t.zle_thresholds[hch] > p.baseline))
+                    cfg.he_rows_possible = true;
+            }
+        }
+    }
     if (const char *e = getenv("WFS_COMPACT")) compact_mode = atoi(e);
     backend = new Backend(&cfg, stream, &launches);
     frontend_init(t);

@@ -1069,41 +1069,16 @@ __device__ __forceinline__ void pack_assemble(int nhere, int lane, int dt, const
     }
 }
 
-template <bool kCompact>
-__global__ void __launch_bounds__(kPackWarps * 32)
-k_pack(int64_t n_rec, DeviceConfig c, const uint32_t *__restrict__ rec_vals,
-       const RecDesc *__restrict__ desc, const int16_t *__restrict__ dense, uint32_t *__restrict__ out,
-       uint32_t *__restrict__ chdr, uint2 *__restrict__ cblk, int64_t *scalars) {
-    __shared__ __align__(16) uint32_t s_rec_all[kPackWarps][kPackWarpRecs * 61];
-    __shared__ RecDesc s_desc_all[kPackWarps][kPackWarpRecs];
-    __shared__ uint32_t s_mask_all[kPackWarps][kPackWarpRecs], s_off_all[kPackWarps][kPackWarpRecs];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t j0 = ((int64_t)blockIdx.x * kPackWarps + warp) * kPackWarpRecs;
-    const int nhere = (int)min((int64_t)kPackWarpRecs, n_rec - j0);
-    if (nhere <= 0) return;
-    uint32_t *s_rec = s_rec_all[warp];
-    RecDesc *s_desc = s_desc_all[warp];
-    uint32_t *s_mask = s_mask_all[warp], *s_off = s_off_all[warp];
-    if (lane < nhere) s_desc[lane] = desc[rec_vals[j0 + lane]];
-    if (kCompact && lane < kPackWarpRecs) s_mask[lane] = 0;
-    __syncwarp();
-    if (nhere == kPackWarpRecs) pack_assemble<true>(nhere, lane, c.p.dt, s_desc, dense, s_rec);
-    else pack_assemble<false>(nhere, lane, c.p.dt, s_desc, dense, s_rec);
-    __syncwarp();
-    if (!kCompact) {
-        // contiguous span of nhere * 244 bytes starting at a 16-byte aligned address (8 * 244 = 122 * 16)
-        uint4 *dst = reinterpret_cast<uint4 *>(out + j0 * 61);
-        const uint4 *srcv = reinterpret_cast<const uint4 *>(s_rec);
-        const int nvec = (nhere * 61) / 4, rem = (nhere * 61) % 4;
-        for (int i = lane; i < nvec; i += 32) dst[i] = srcv[i];
-        if (lane < rem) out[j0 * 61 + nvec * 4 + lane] = s_rec[nvec * 4 + lane];
-        return;
-    }
-    // ---- compact form ----
-    const uint32_t fill_h = (uint32_t)(uint16_t)(int16_t)max(c.p.baseline, 0);
+// Compact transport form of the 8 records a warp holds in shared memory (61 words each, header word 2 =
+// length): mask of the 4-sample blocks that differ from the fill pattern, one atomic per warp for the
+// block stream, 24-byte headers at the records' positions.
+__device__ __forceinline__ void compact_emit(int nhere, int lane, int64_t j0, int baseline, const uint32_t *s_rec,
+                                             uint32_t *s_mask, uint32_t *s_off, uint32_t *__restrict__ chdr,
+                                             uint2 *__restrict__ cblk, int64_t *scalars) {
+    const uint32_t fill_h = (uint32_t)(uint16_t)(int16_t)max(baseline, 0);
     for (int idx = lane; idx < nhere * kBlocksPerRecord; idx += 32) {
         const int r = idx / kBlocksPerRecord, b = idx - r * kBlocksPerRecord;
-        const int length = s_desc[r].length;
+        const int length = (int)s_rec[r * 61 + 2];
         const uint32_t *w = s_rec + r * 61 + 6 + 2 * b;
         const int nw = b == kBlocksPerRecord - 1 ? 1 : 2;
         bool diff = false;
@@ -1147,6 +1122,63 @@ k_pack(int64_t n_rec, DeviceConfig c, const uint32_t *__restrict__ rec_vals,
         const uint32_t *w = s_rec + r * 61 + 6 + 2 * b;
         cblk[s_off[r] + __popc(m & ((1u << b) - 1u))] = make_uint2(w[0], b == kBlocksPerRecord - 1 ? 0u : w[1]);
     }
+}
+
+template <bool kCompact>
+__global__ void __launch_bounds__(kPackWarps * 32)
+k_pack(int64_t n_rec, DeviceConfig c, const uint32_t *__restrict__ rec_vals,
+       const RecDesc *__restrict__ desc, const int16_t *__restrict__ dense, uint32_t *__restrict__ out,
+       uint32_t *__restrict__ chdr, uint2 *__restrict__ cblk, int64_t *scalars) {
+    __shared__ __align__(16) uint32_t s_rec_all[kPackWarps][kPackWarpRecs * 61];
+    __shared__ RecDesc s_desc_all[kPackWarps][kPackWarpRecs];
+    __shared__ uint32_t s_mask_all[kPackWarps][kPackWarpRecs], s_off_all[kPackWarps][kPackWarpRecs];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t j0 = ((int64_t)blockIdx.x * kPackWarps + warp) * kPackWarpRecs;
+    const int nhere = (int)min((int64_t)kPackWarpRecs, n_rec - j0);
+    if (nhere <= 0) return;
+    uint32_t *s_rec = s_rec_all[warp];
+    RecDesc *s_desc = s_desc_all[warp];
+    uint32_t *s_mask = s_mask_all[warp], *s_off = s_off_all[warp];
+    if (lane < nhere) s_desc[lane] = desc[rec_vals[j0 + lane]];
+    if (kCompact && lane < kPackWarpRecs) s_mask[lane] = 0;
+    __syncwarp();
+    if (nhere == kPackWarpRecs) pack_assemble<true>(nhere, lane, c.p.dt, s_desc, dense, s_rec);
+    else pack_assemble<false>(nhere, lane, c.p.dt, s_desc, dense, s_rec);
+    __syncwarp();
+    if (!kCompact) {
+        // contiguous span of nhere * 244 bytes starting at a 16-byte aligned address (8 * 244 = 122 * 16)
+        uint4 *dst = reinterpret_cast<uint4 *>(out + j0 * 61);
+        const uint4 *srcv = reinterpret_cast<const uint4 *>(s_rec);
+        const int nvec = (nhere * 61) / 4, rem = (nhere * 61) % 4;
+        for (int i = lane; i < nvec; i += 32) dst[i] = srcv[i];
+        if (lane < rem) out[j0 * 61 + nvec * 4 + lane] = s_rec[nvec * 4 + lane];
+        return;
+    }
+    // ---- compact form ----
+    compact_emit(nhere, lane, j0, c.p.baseline, s_rec, s_mask, s_off, chdr, cblk, scalars);
+}
+
+// Plain 244-byte records, already at their final position in HBM (the group-resident fused kernel writes
+// them there) -> compact transport form.  Every warp streams 8 consecutive records (1952 bytes, 16-byte
+// aligned) through its slice of shared memory.
+__global__ void __launch_bounds__(kPackWarps * 32)
+k_compact_records(int64_t n_rec, int baseline, const uint32_t *__restrict__ rec, uint32_t *__restrict__ chdr,
+                  uint2 *__restrict__ cblk, int64_t *scalars) {
+    __shared__ __align__(16) uint32_t s_rec_all[kPackWarps][kPackWarpRecs * 61];
+    __shared__ uint32_t s_mask_all[kPackWarps][kPackWarpRecs], s_off_all[kPackWarps][kPackWarpRecs];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t j0 = ((int64_t)blockIdx.x * kPackWarps + warp) * kPackWarpRecs;
+    const int nhere = (int)min((int64_t)kPackWarpRecs, n_rec - j0);
+    if (nhere <= 0) return;
+    uint32_t *s_rec = s_rec_all[warp];
+    if (lane < kPackWarpRecs) s_mask_all[warp][lane] = 0;
+    const uint4 *src = reinterpret_cast<const uint4 *>(rec + j0 * 61);
+    uint4 *dstv = reinterpret_cast<uint4 *>(s_rec);
+    const int nvec = (nhere * 61) / 4, rem = (nhere * 61) % 4;
+    for (int i = lane; i < nvec; i += 32) dstv[i] = src[i];
+    if (lane < rem) s_rec[nvec * 4 + lane] = rec[j0 * 61 + nvec * 4 + lane];
+    __syncwarp();
+    compact_emit(nhere, lane, j0, baseline, s_rec, s_mask_all[warp], s_off_all[warp], chdr, cblk, scalars);
 }
 
 __global__ void k_group_info(int64_t n_groups, DeviceConfig c, const int64_t *group_lr,
@@ -1196,7 +1228,7 @@ void Backend::release() {
                      &win_first_pulse_, &win_meta_, &win_scan_, &group_tmin_, &group_lr_, &scalars_,
                      &dense_, &itv_, &itv_nrec_, &itv_rec0_, &rec_keys_, &rec_vals_,
                      &rec_itv_, &group_nitv_, &group_ix_, &pstart_, &flag8_, &cta_first_, &phq_,
-                     &group_nvalid_, &group_out_, &group_win_, &rec_seg_};
+                     &group_nvalid_, &group_out_, &group_win_, &rec_seg_, &fused_status_, &fused_scal_, &fused_records_};
     for (DevBuf *b : all) b->release();
     prim_.release();
 }
@@ -1214,6 +1246,35 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
     const int64_t n = b.n, ng = b.n_groups;
     if (ng <= 0) return;
     if (n >= (int64_t(1) << 31)) throw std::runtime_error("photon batch too large (>= 2^31)");
+    if (n > 0 && fused_eligible(b)) {
+        // small groups: one CTA per group from the photons to the records (fused.cu); for a host destination
+        // the records then stream once more through k_compact_records into the compact transport form
+        uint8_t *dst = records_out;
+        if (compact) {
+            fused_records_.reserve((size_t)WFS_RECORD_BYTES * (size_t)std::max<int64_t>(cap_records, 1) + 64);
+            dst = fused_records_.as<uint8_t>();
+        }
+        if (run_fused(b, dst, cap_records, group_info_out, res)) {
+            if (compact && !res.error && res.n_records > 0 && res.n_records <= cap_records) {
+                if ((uint64_t)res.n_records * kBlocksPerRecord >= (uint64_t(1) << 32)) { res.error = WFS_E_KEYBITS; return; }
+                scalars_.reserve(sizeof(int64_t) * S_COUNT);
+                WFS_CUDA_CHECK(cudaMemsetAsync(scalars_.p, 0, sizeof(int64_t) * S_COUNT, stream_));
+                WFS_CUDA_CHECK(cudaEventRecord(evp_[5], stream_));
+                LAUNCH(k_compact_records, div_up(res.n_records, kPackRecs), kPackWarps * 32, res.n_records, c.p.baseline,
+                       reinterpret_cast<const uint32_t *>(dst), reinterpret_cast<uint32_t *>(compact->hdr),
+                       compact->blocks, scalars_.as<int64_t>());
+                WFS_CUDA_CHECK(cudaEventRecord(evp_[6], stream_));
+                WFS_CUDA_CHECK(cudaMemcpyAsync(h_scalars_, scalars_.p, sizeof(int64_t) * S_COUNT, cudaMemcpyDeviceToHost, stream_));
+                WFS_CUDA_CHECK(stream_sync(stream_));
+                res.n_blocks = h_scalars_[S_NBLOCKS];
+                cudaEventElapsedTime(&res.ms_phase[6], evp_[5], evp_[6]);
+            }
+            return;
+        }
+        res = BackendResult();
+        if (b.trig_dpe_out)      // the fused attempt has added to the trigger counters: start over
+            WFS_CUDA_CHECK(cudaMemsetAsync(b.trig_dpe_out, 0, sizeof(int32_t) * 2 * (size_t)b.n_pulse_calls, stream_));
+    }
     KeyLayout kl;
     kl.bits_rank = bits_for((uint64_t)b.max_rank + 1);
     kl.bits_group = bits_for((uint64_t)ng + 1);

@@ -20,6 +20,10 @@ struct DeviceConfig {
     double *current_max = nullptr;   // [dt] max of each template row (pulse.py:32)
     int64_t noise_len = 0;
     int32_t noise_nch = 0;
+    // host-side facts about the tables (set at wfs_create): can a high-energy twin row (rawdata.py:241-249)
+    // ever hold data, and is any TPC threshold above the clamped baseline (then every sample is flagged)
+    bool he_rows_possible = false;
+    bool thr_above_baseline = false;
 };
 
 // Photons of one batch, resident in HBM, in arbitrary order.
@@ -50,6 +54,12 @@ struct PhotonBatch {
     const uint32_t *group_start = nullptr;
     int group_ranges = 1;
     int64_t max_group_photons = 0;
+    // Optional (generate mode), for the group-resident fused back end (fused.cu): per group a lower bound
+    // of its photon times and its first Pulse call (the calls of a group are consecutive), and the bits
+    // needed for 2 * (calls of the largest group)
+    const int64_t *group_t0 = nullptr;
+    const int32_t *group_run0 = nullptr;
+    int relpc_bits = 0;
     // Optional per-PMT truth (generate mode): per Pulse call r = pulse-call id >> 1 and PMT, written
     // by the thread that owns the (pulse call, channel) pulse -- pulse.py:257-269 with per_pmt_truth.
     int32_t *pmt_counts = nullptr;         // [n_pulse_calls / 2][4][n_tpc_pmts] n_photon, n_pe, n_photon_trigger, n_pe_trigger
@@ -66,6 +76,7 @@ struct BackendResult {
     float ms_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 1 sort, 2 windows, 3 digitize, 4 zle, 5 rec sort, 6 pack
     int error = 0;
     int segment_sorted_photons = 0, segment_sorted_records = 0;   // 1: ordered per group in shared memory
+    int fused = 0;                   // 1: the batch went through the group-resident fused kernel
 };
 
 class Backend {
@@ -82,6 +93,10 @@ public:
     void run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_records,
              wfs_group_info *group_info_out, BackendResult &res, const CompactOut *compact = nullptr);
     void release();
+    bool fused_eligible(const PhotonBatch &b) const;
+    // false: not run / a group outgrew the shared-memory lists -- the caller takes the multi-pass path
+    bool run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_records,
+                   wfs_group_info *group_info_out, BackendResult &res);
 
 private:
     const DeviceConfig *cfg_;
@@ -94,7 +109,9 @@ private:
     DevBuf keys_, vals_, st_, sg_, flags64_, pulse_first_, pulse_left_, pulse_win_, win_first_pulse_,
         win_meta_, win_scan_, group_tmin_, group_lr_, scalars_, dense_, itv_, itv_nrec_,
         itv_rec0_, rec_keys_, rec_vals_, rec_itv_, group_nitv_, group_ix_, pstart_, flag8_, cta_first_, phq_,
-        group_nvalid_, group_out_, group_win_, rec_seg_;
+        group_nvalid_, group_out_, group_win_, rec_seg_, fused_status_, fused_scal_, fused_records_;
+    bool fused_attr_set_ = false;
+    int fused_smem_set_ = 0;
 };
 
 }  // namespace wfs

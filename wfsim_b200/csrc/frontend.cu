@@ -605,6 +605,31 @@ static void write_truth_row(uint8_t *row, const HostInstr &h0, int run_type, int
     wr<double>(row + 210, has_e ? (double)e_sigma : nan);
 }
 
+// np.mean of a float32 array as numpy evaluates it (rawdata.py:362-364 `tb[field] = np.mean(value)` over
+// the x / y / z of an instruction cluster): float32 pairwise summation -- plain loop below 8 elements,
+// eight interleaved partial sums up to 128 elements, recursive halving (to multiples of 8) above -- and
+// a float32 division by the count.
+static float np_pairwise_sum_f32(const float *a, size_t n) {
+    if (n < 8) {
+        float r = 0.f;
+        for (size_t i = 0; i < n; i++) r += a[i];
+        return r;
+    }
+    if (n <= 128) {
+        float r[8];
+        for (int k = 0; k < 8; k++) r[k] = a[k];
+        size_t i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int k = 0; k < 8; k++) r[k] += a[i + k];
+        float res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; i++) res += a[i];
+        return res;
+    }
+    size_t n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_pairwise_sum_f32(a, n2) + np_pairwise_sum_f32(a + n2, n - n2);
+}
+
 // exact first/second moments of times over the instructions of a run -> mean and population std
 static void combine_moments(const std::vector<int32_t> &set, const std::vector<int64_t> &T,
                             const int64_t *acc, int a_n, int a_s, int a_hi2, int a_hilo, int a_lo2,
@@ -1043,6 +1068,29 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
                     (long long)batch_index, (long long)n_ph, (long long)n_ap, ngroups, (int)contiguous,
                     (long long)max_group_photons);
     }
+    // for the group-resident fused back end: first Pulse call of every group (the calls of a group are
+    // consecutive in execution order) and a lower bound of its photon times (PMT afterpulses may precede
+    // their parent by pmt_ap_t_modifier, afterpulse.py:219-223)
+    int relpc_bits = 0;
+    if (!gstart.empty()) {
+        std::vector<int64_t> g_t0((size_t)ngroups, LLONG_MAX);
+        std::vector<int32_t> g_run0((size_t)ngroups, 0), g_nruns((size_t)ngroups, 0);
+        const int64_t ap_margin = p.enable_pmt_afterpulses ? (int64_t)std::ceil(std::max(p.pmt_ap_t_modifier, 0.0)) + 1 : 0;
+        for (int64_t r = 0; r < nruns; r++) {
+            const int32_t gi = runs[r].group;
+            if (g_nruns[gi]++ == 0) g_run0[gi] = (int32_t)r;
+            for (int32_t i : runs[r].instr)
+                if (acc[(size_t)i * A_COUNT + A_NPHALL] > 0)
+                    g_t0[gi] = std::min(g_t0[gi], acc[(size_t)i * A_COUNT + A_TMIN] - ap_margin);
+        }
+        int32_t max_runs = 1;
+        for (int32_t gi = 0; gi < ngroups; gi++) max_runs = std::max(max_runs, g_nruns[gi]);
+        while ((int64_t(1) << relpc_bits) < 2 * (int64_t)max_runs) relpc_bits++;
+        F.b_gt0.reserve(8 * (size_t)ngroups);
+        F.b_grun0.reserve(4 * (size_t)ngroups);
+        up(F.b_gt0, g_t0.data(), 8 * (size_t)ngroups);
+        up(F.b_grun0, g_run0.data(), 4 * (size_t)ngroups);
+    }
     const double ms_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
     {
         std::lock_guard<std::mutex> lk(ord.mu);
@@ -1065,6 +1113,9 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         b.group_start = F.b_gstart.as<uint32_t>();
         b.group_ranges = n_ranges;
         b.max_group_photons = max_group_photons;
+        b.group_t0 = F.b_gt0.as<int64_t>();
+        b.group_run0 = F.b_grun0.as<int32_t>();
+        b.relpc_bits = relpc_bits;
     }
     const bool per_pmt = so.out && so.out->truth_pmt_counts && so.out->truth_pmt_areas && nruns > 0;
     if (per_pmt) {
@@ -1192,6 +1243,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         cn->ms_phase[0] += ms_front;
         cn->ms_phase[7] += ms_host;
         for (int k = 1; k <= 6; k++) cn->ms_phase[k] += res.ms_phase[k];
+        cn->n_fused_batches += res.fused;
         cn->ms_phase[10] += res.segment_sorted_photons;
         cn->ms_phase[11] += res.segment_sorted_records;
         ord.out_done = batch_index + 1;
@@ -1237,10 +1289,14 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
             auto fz = [&](int32_t i) { return i < nprim ? h_z[i] : sec_z[i - nprim]; };
             auto fa = [&](int32_t i) { return i < nprim ? h_amp[i] : sec_amp[i - nprim]; };
             if (run.instr.size() > 1) {
-                float sx = 0, sy = 0, sz = 0; int64_t sa = 0;
-                for (int32_t i : run.instr) { sx += fx(i); sy += fy(i); sz += fz(i); sa += fa(i); }
+                std::vector<float> vx, vy, vz;
+                int64_t sa = 0;
+                for (int32_t i : run.instr) { vx.push_back(fx(i)); vy.push_back(fy(i)); vz.push_back(fz(i)); sa += fa(i); }
                 const float nn = (float)run.instr.size();
-                x = sx / nn; y = sy / nn; z = sz / nn; amp = (int32_t)sa;
+                x = np_pairwise_sum_f32(vx.data(), vx.size()) / nn;
+                y = np_pairwise_sum_f32(vy.data(), vy.size()) / nn;
+                z = np_pairwise_sum_f32(vz.data(), vz.size()) / nn;
+                amp = (int32_t)sa;
             } else {
                 x = fx(i0); y = fy(i0); z = fz(i0); amp = fa(i0);
             }
@@ -1333,7 +1389,7 @@ static void release_frontend_buffers(Frontend &F) {
                      &F.b_enph, &F.b_ephoff, &F.b_pht, &F.b_phch, &F.b_phgain, &F.b_phinstr, &F.b_phflags,
                      &F.b_phnap, &F.b_apoff, &F.b_picount, &F.b_pioff, &F.b_pecount, &F.b_peoff, &F.b_irun, &F.b_pcgroup,
                      &F.b_pcrank, &F.b_trig, &F.b_records, &F.b_records2, &F.b_groups, &F.b_scal, &F.b_phstart,
-                     &F.b_gstart, &F.b_pmtcnt, &F.b_pmtarea};
+                     &F.b_gstart, &F.b_gt0, &F.b_grun0, &F.b_pmtcnt, &F.b_pmtarea};
     for (DevBuf *b : all) b->release();
     for (CompactStage &cs : F.cstage) cs.release();
     F.cdf_rows = -1;

@@ -102,7 +102,7 @@ struct Frontend {
         b_dmean, b_dspread, b_nemit, b_emitoff, b_nhits, b_acc, b_cdf, b_cdfok, b_pattern,
         b_et, b_einstr, b_enph, b_ephoff, b_pht, b_phch, b_phgain, b_phinstr, b_phflags, b_phnap,
         b_apoff, b_picount, b_pioff, b_pecount, b_peoff, b_irun, b_pcgroup, b_pcrank, b_trig, b_records, b_records2,
-        b_groups, b_scal, b_phstart, b_gstart, b_pmtcnt, b_pmtarea;
+        b_groups, b_scal, b_phstart, b_gstart, b_gt0, b_grun0, b_pmtcnt, b_pmtarea;
     CompactStage cstage[2];     // compact record transport: batch k ships while batch k+1 runs
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_ready = nullptr;
     bool copy_pending[2] = {false, false};

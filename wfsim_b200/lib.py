@@ -98,7 +98,7 @@ class Counts(C.Structure):
                     'n_batches', 'gpu_launches', 'need_records', 'need_truth', 'need_groups',
                     'need_batches', 'd2h_bytes')]
                 + [(n, f64) for n in ('ms_total', 'ms_digitize', 'ms_h2d', 'ms_d2h')]
-                + [('ms_phase', f64 * 12)])
+                + [('ms_phase', f64 * 12), ('n_fused_batches', i64)])
 
     def as_dict(self):
         d = {n: getattr(self, n) for n, _ in self._fields_ if n not in ('n_records', 'ms_phase')}
