@@ -52,14 +52,18 @@ def assert_same(a, b, ca, cb):
     assert len(a['raw_records']) > 0
 
 
+# energies that keep every digitisation group within the photons one CTA holds (kFusedMaxPhotons)
 CONFIGS = {
-    'c0': (dict(), lambda: c0_like(14, seed=3)),
+    'c0': (dict(), lambda: c0_like(14, seed=3, e_range=(1, 12))),
     'c1_low_energy': (dict(), lambda: c1_like(300, seed=5)),
-    'afterpulses': (dict(enable_pmt_afterpulses=True, enable_electron_afterpulses=True), lambda: c0_like(12, seed=4, e_range=(5, 60))),
+    'afterpulses': (dict(enable_pmt_afterpulses=True, enable_electron_afterpulses=True), lambda: c0_like(12, seed=4, e_range=(2, 10))),
     'pile_up_merged': (dict(enable_pmt_afterpulses=True, save_full_truth=False),
-                       lambda: c0_like(30, seed=6, event_rate=6000.0, e_range=(2, 30))),
-    'thresholds': (dict(zle_threshold=40, special_thresholds={'7': 60, '255': 5, '300': 25}), lambda: c0_like(10, seed=7)),
-    'gate': (dict(enable_gate_afterpulses=True, photoelectric_p=0.004), lambda: c0_like(10, seed=8)),
+                       lambda: c0_like(30, seed=6, event_rate=6000.0, e_range=(0.5, 3))),
+    'pile_up_full_truth': (dict(enable_pmt_afterpulses=True, enable_electron_afterpulses=True),
+                           lambda: c0_like(24, seed=16, event_rate=9000.0, e_range=(0.5, 3))),
+    'thresholds': (dict(zle_threshold=40, special_thresholds={'7': 60, '255': 5, '300': 25}), lambda: c0_like(10, seed=7, e_range=(1, 12))),
+    'gate': (dict(enable_gate_afterpulses=True, photoelectric_p=0.004), lambda: c0_like(10, seed=8, e_range=(1, 12))),
+    'bright_s1': (dict(), lambda: c0_like(10, seed=21, e_range=(8, 12), s1_per_kev=400.0, s2_per_kev=2.0)),
 }
 
 
@@ -83,7 +87,7 @@ def test_fused_with_dead_pmts_and_per_pmt_truth():
     cfg['gains'] = gains
     uniq, row = spe()
     sim = Simulator(cfg, resource=Resource(cfg, spe_ppf=uniq, spe_row=row))
-    a, b, ca, cb = both_paths(sim, c0_like(8, seed=9), seed=5)
+    a, b, ca, cb = both_paths(sim, c0_like(8, seed=9, e_range=(1, 12)), seed=5, per_pmt_truth=True)
     assert_same(a, b, ca, cb)
     assert a['truth']['n_photon_per_pmt'].sum() == a['truth']['n_photon'].sum()
     assert not np.isin(a['raw_records']['channel'], [3, 100, 300, 493]).any()
@@ -94,7 +98,7 @@ def test_fused_over_several_batches_lanes_and_transports():
     """Several device batches on several lanes; compact transport (pageable destination) against the plain
     DMA (pinned destination); a record buffer that is too small is grown and the call repeated."""
     sim, cfg = make_sim(enable_pmt_afterpulses=True, enable_electron_afterpulses=True)
-    inst = c0_like(40, seed=11, e_range=(3, 50))
+    inst = c0_like(40, seed=11, e_range=(1, 6))
     with env(WFS_FUSED=1):
         ref = sim.simulate(inst, seed=2)
         with env(WFS_BATCH_INSTRUCTIONS=10):
@@ -102,7 +106,10 @@ def test_fused_over_several_batches_lanes_and_transports():
             assert sim.last_counts['n_batches'] > 2 and sim.last_counts['n_fused_batches'] == sim.last_counts['n_batches']
             pinned = sim.simulate(inst, seed=2, pinned=True)
             small = sim.simulate(inst, seed=2, cap_records=100)
-    for other in (cut, pinned, small):
+            with env(WFS_FUSED_REC_CAP=64):       # the groups outgrow the record lists: second attempt with large ones
+                retried = sim.simulate(inst, seed=2)
+                assert sim.last_counts['n_fused_batches'] == sim.last_counts['n_batches']
+    for other in (cut, pinned, small, retried):
         for k in ('raw_records', 'raw_records_he', 'truth', 'groups'):
             assert other[k].tobytes() == ref[k].tobytes(), k
     sim.close()

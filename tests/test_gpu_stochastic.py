@@ -185,6 +185,7 @@ def test_group_local_photon_order_equals_device_wide_sort(monkeypatch):
     s, cfg = make_sim()
     inst = c1_like(300, seed=12)
     outs = {}
+    monkeypatch.setenv('WFS_FUSED', '0')       # the two photon orderings of the multi-pass back end
     for mode in ('0', '1'):
         monkeypatch.setenv('WFS_SEGMENT_SORT', mode)
         outs[mode] = s.simulate(inst, seed=33)

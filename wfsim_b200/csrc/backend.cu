@@ -1228,7 +1228,8 @@ void Backend::release() {
                      &win_first_pulse_, &win_meta_, &win_scan_, &group_tmin_, &group_lr_, &scalars_,
                      &dense_, &itv_, &itv_nrec_, &itv_rec0_, &rec_keys_, &rec_vals_,
                      &rec_itv_, &group_nitv_, &group_ix_, &pstart_, &flag8_, &cta_first_, &phq_,
-                     &group_nvalid_, &group_out_, &group_win_, &rec_seg_, &fused_status_, &fused_scal_, &fused_records_};
+                     &group_nvalid_, &group_out_, &group_win_, &rec_seg_, &fused_lists_, &fused_scal_, &fused_records_,
+                     &fused_tkey_, &fused_gain_, &fused_desc_};
     for (DevBuf *b : all) b->release();
     prim_.release();
 }
@@ -1274,6 +1275,8 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
         res = BackendResult();
         if (b.trig_dpe_out)      // the fused attempt has added to the trigger counters: start over
             WFS_CUDA_CHECK(cudaMemsetAsync(b.trig_dpe_out, 0, sizeof(int32_t) * 2 * (size_t)b.n_pulse_calls, stream_));
+        if (b.pmt_areas)
+            WFS_CUDA_CHECK(cudaMemsetAsync(b.pmt_areas, 0, sizeof(int64_t) * (size_t)b.n_pulse_calls * c.p.n_tpc_pmts, stream_));
     }
     KeyLayout kl;
     kl.bits_rank = bits_for((uint64_t)b.max_rank + 1);

@@ -52,6 +52,7 @@ struct PhotonBatch {
     // done per group in shared memory (Primitives::segment_sort_pairs) instead of by the device-wide
     // radix sort.
     const uint32_t *group_start = nullptr;
+    const uint32_t *h_group_start = nullptr;   // the same table on the host (fused back end: size classes)
     int group_ranges = 1;
     int64_t max_group_photons = 0;
     // Optional (generate mode), for the group-resident fused back end (fused.cu): per group a lower bound
@@ -109,8 +110,8 @@ private:
     DevBuf keys_, vals_, st_, sg_, flags64_, pulse_first_, pulse_left_, pulse_win_, win_first_pulse_,
         win_meta_, win_scan_, group_tmin_, group_lr_, scalars_, dense_, itv_, itv_nrec_,
         itv_rec0_, rec_keys_, rec_vals_, rec_itv_, group_nitv_, group_ix_, pstart_, flag8_, cta_first_, phq_,
-        group_nvalid_, group_out_, group_win_, rec_seg_, fused_status_, fused_scal_, fused_records_;
-    bool fused_attr_set_ = false;
+        group_nvalid_, group_out_, group_win_, rec_seg_, fused_lists_, fused_scal_, fused_records_, fused_tkey_,
+        fused_gain_, fused_desc_;
     int fused_smem_set_ = 0;
 };
 

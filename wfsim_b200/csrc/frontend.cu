@@ -1111,6 +1111,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     b.seed = seed;
     if (!gstart.empty()) {
         b.group_start = F.b_gstart.as<uint32_t>();
+        b.h_group_start = gstart.data();
         b.group_ranges = n_ranges;
         b.max_group_photons = max_group_photons;
         b.group_t0 = F.b_gt0.as<int64_t>();
@@ -1170,7 +1171,9 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
             reserve_records(res.n_records);
             d_rec = rb.as<uint8_t>();
             WFS_CUDA_CHECK(cudaMemsetAsync(F.b_trig.p, 0, 4 * (size_t)std::max<int64_t>(2 * npc, 1), s));
-            L.B->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res, compact ? &co : nullptr);   // per-PMT truth: plain stores, safe to redo
+            if (per_pmt)   // the fused kernel adds the per-PMT areas photon by photon
+                WFS_CUDA_CHECK(cudaMemsetAsync(F.b_pmtarea.p, 0, sizeof(int64_t) * 2 * (size_t)n_ch * (size_t)nruns, s));
+            L.B->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res, compact ? &co : nullptr);
         }
     }
     std::vector<wfs_group_info> h_groups((size_t)ngroups);

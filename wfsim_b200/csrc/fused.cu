@@ -1,26 +1,34 @@
-// Group-resident back end: ONE CTA owns a digitisation group from its photons to its raw_records.
+// Group-resident back end: ONE CTA owns a digitisation group from its photons to its ZLE intervals and record
+// order; a second kernel writes the records.  Two launches, count then fill, no pass over dense samples:
 //
+// k_group_analyse (one CTA per group; groups are binned by photon count so that small groups run many CTAs per SM)
 //   photons of the group (generation order, HBM, read once)
 //     -> key (channel | pulse call | sample | ns remainder | index | dpe) in shared memory, bucketed by
 //        channel (counting sort) and ordered inside the channel by (pulse call, time)
 //                                                                   Pulse.__call__   pulse.py:82-144
-//     -> phase A, one warp per (group, channel) window: pulse / window extents (pulse.py:118-127,
-//        rawdata.py:231-235,258-259), truth counters of every pulse (pulse.py:229-271), template
-//        superposition in a REGISTER ring -- lane j holds the fp64 current of sample (base + j); photons are
-//        taken in ascending time, equal-ns photons merged first, mul and add unfused: the summation order
-//        of Pulse.add_current (pulse.py:276-318) -- one rounding per pulse and sample, -around(current *
-//        current_2_adc) (rawdata.py:236-239); baseline, clamp, threshold (rawdata.py:290-296,441-458);
-//        the hysteresis interval search (utils.py:13-58, rawdata.py:296-308) straight on the ballot words
-//     -> record keys (time, channel) of the group ordered in shared memory (strax.sort_by_time)
-//     -> the group's first record index: decoupled look-back over the groups in front (groups are disjoint
-//        in time, so group order IS record order)
-//     -> phase B, one warp per ZLE interval: the samples again (same arithmetic), 244-byte records
-//        assembled by the warp and written ONCE, at their final sorted position
+//     -> per PHOTON (one thread each): gain into shared memory, the trigger bit of the truth counters
+//        (pulse.py:229-271), equal-ns photons merged (pulse.py:301-318), and the samples the photon OWNS
+//        (from its first sample to the next photon's first sample on the channel) evaluated with every
+//        photon that overlaps them -- fp64, ascending time, mul and add unfused: the summation order of
+//        Pulse.add_current (pulse.py:276-318), one rounding per pulse and sample, -around(current *
+//        current_2_adc) (rawdata.py:236-239), baseline, clamp, threshold (rawdata.py:290-296,441-458).
+//        Only the first and the last owned sample below threshold are kept (5 + 5 bits in the key): a
+//        template is shorter than the ZLE hold-off, so nothing else can change an interval.
+//     -> per WINDOW (one lane each; a warp for the rare window with several pulse calls): window extents
+//        (pulse.py:118-127, rawdata.py:231-235,258-259), truth counters, the hysteresis interval search
+//        (utils.py:13-58, rawdata.py:296-308) over the photons' flagged runs
+//     -> record order (time, channel) of the group: counting sort over time bins in shared memory
+//        (strax.sort_by_time)
+//     -> to HBM: 12 bytes per photon (time | first-of-pulse bit, merged gain) in channel order, 16 bytes per
+//        record (channel, first sample, pulse length, record_i, the photons that reach it) at the record's rank
+//        in the group, the group's record count
+// exclusive scan of the record counts: groups are disjoint in time, so group order IS record order
+// k_group_records (one warp per record, lane = record word): the samples again (same arithmetic, only the
+//   photons that reach the record), 244-byte records written ONCE, at their final sorted position
 //                                                                   strax_interface.py:425-436
-// Nothing but the photons is read from HBM and nothing but the records is written: no sort keys, no dense
-// ADC buffer, no flags, no record descriptors.  Used when every group of a batch fits (<= kFusedMaxPhotons
-// photons, no noise, no high-energy twin rows); anything else takes the multi-pass back end (backend.cu),
-// which stays the reference implementation of the same arithmetic for heavy S2s.
+// No sort keys, no dense ADC buffer, no flags travel through HBM.  Used when every group of a batch fits
+// (<= kFusedMaxPhotons photons, no noise, no high-energy twin rows); anything else takes the multi-pass back
+// end (backend.cu), which stays the reference implementation of the same arithmetic for heavy S2s.
 #include "backend.cuh"
 #include "fused.cuh"
 
@@ -33,42 +41,42 @@ namespace wfs {
 namespace {
 
 constexpr int kNegPos = -(1 << 29);
-constexpr uint32_t kPadKey = 0xffffffffu;
-
-// look-back status word: [63:62] state, [61:0] record count (aggregate of the group or inclusive prefix)
-constexpr uint64_t kStEmpty = 0, kStAgg = 1ull << 62, kStPrefix = 2ull << 62, kStMask = 3ull << 62;
+constexpr int kNoFlag = 31;                     // f0 field: no owned sample below threshold
 
 struct FusedShared {          // fixed-size part of the shared memory, the arrays follow
     int64_t origin_q;         // absolute sample index of key sample 0
-    int32_t n_valid, n_win, n_itv, n_rec, n_pulses, n_emitted;
-    int32_t next_win, next_itv;
-    int32_t lo, hi;           // min pulse left / max pulse right of the group, relative to origin_q
-    int32_t group;
-    uint32_t rec_base;
-    int32_t overflow;
     unsigned long long n_samples;
+    int32_t n_valid, n_win, n_itv, n_rec, n_pulses, n_emitted;
+    int32_t n_multi, n_slow;
+    int32_t lo, hi;           // min pulse left / max pulse right of the group, relative to origin_q
+    int32_t tmax_q;           // largest photon sample of the group, relative to origin_q
+    int32_t max_bin;          // most records in one time bin
+    int32_t group;
+    uint32_t desc_off;        // the group's first record descriptor in the pool
+    int32_t overflow;
+    int32_t warp_sums[32];
+    int32_t trig[2 * kFusedTrigSlots];
 };
 
 struct Layout {               // byte offsets into the dynamic shared memory
-    int keys, chan_start, chan_fill, win_ch, tmpl, scratch, tiles, rkey, itv, total;
+    int keys, gains, chan_start, chan_fill, win_ch, multi, tmpl, cmax, itv, rkey, order, bins, total;
 };
 
-__host__ __device__ inline Layout make_layout(int n_cap, int n_ch, int n_warps, int tmpl_len) {
+__host__ __device__ inline Layout make_layout(int n_cap, int itv_cap, int rec_cap, int n_ch, int tmpl_len, int dt) {
     Layout L;
     int o = (int)((sizeof(FusedShared) + 15) & ~15u);
     L.keys = o; o += 8 * n_cap;
+    L.gains = o; o += 8 * n_cap;                 // unsorted keys while loading, gains afterwards
+    L.itv = o; o += 8 * itv_cap;
+    L.tmpl = o; o += 8 * tmpl_len;
+    L.cmax = o; o += 8 * dt;
     L.chan_start = o; o += 4 * (n_ch + 1);
     L.chan_fill = o; o += 4 * (n_ch + 1);
+    L.rkey = o; o += 4 * rec_cap;                // record keys, then record ranks
+    L.bins = o; o += 4 * kFusedBins;
+    L.order = o; o += 2 * (rec_cap > n_cap ? rec_cap : n_cap);   // photons with neighbours, then record slots
     L.win_ch = o; o += 2 * (n_ch + 2);
-    o = (o + 15) & ~15;
-    L.tmpl = o; o += 8 * tmpl_len;
-    // scratch: unsorted keys while loading; afterwards per-warp sample tiles, record keys, intervals
-    L.scratch = o;
-    L.tiles = o;
-    L.rkey = L.tiles + n_warps * kFusedTile * 4;
-    L.itv = L.rkey + kFusedRecCap * 4;
-    const int after = L.itv + kFusedItvCap * 8;
-    o = after > L.scratch + 8 * n_cap ? after : L.scratch + 8 * n_cap;
+    L.multi = o; o += 2 * (n_ch + 2);
     L.total = (o + 15) & ~15;
     return L;
 }
@@ -78,125 +86,121 @@ __device__ __forceinline__ int64_t floordiv64(int64_t a, int64_t b) {
     return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
 }
 
-struct KeyFmt {
-    int shift_pc, shift_ch;   // key = ch << shift_ch | relpc << shift_pc | sample << 18 | rem << 14 | idx << 1 | dpe
-};
+// key = ch << shift_ch | relpc << shift_pc | sample << 18 | rem << 14 | field << 1 | dpe
+//   field (13 bits): the photon's index in the group while the channel lists are ordered; afterwards
+//   bit 0 above trigger threshold, bit 1 follower of an equal-ns photon, bits 2-6 / 7-11 first / last owned
+//   sample below the ZLE threshold (offset from the photon's own sample; first = 31: none), bit 12 first
+//   photon of a pulse (channel, pulse call)
 constexpr int kShiftSample = 18, kShiftRem = 14, kSampleBits = 20;
+constexpr uint64_t kFieldMask = 0x3ffeull;
 
 __device__ __forceinline__ int key_sample(uint64_t k) { return (int)((k >> kShiftSample) & ((1u << kSampleBits) - 1u)); }
 __device__ __forceinline__ int key_rem(uint64_t k) { return (int)((k >> kShiftRem) & 15u); }
-__device__ __forceinline__ uint32_t key_time(uint64_t k) { return (uint32_t)((k >> kShiftRem) & ((1u << (kSampleBits + 4)) - 1u)); }
 __device__ __forceinline__ int key_idx(uint64_t k) { return (int)((k >> 1) & 8191u); }
 __device__ __forceinline__ int key_dpe(uint64_t k) { return (int)(k & 1u); }
+__device__ __forceinline__ int key_above(uint64_t k) { return (int)((k >> 1) & 1u); }
+__device__ __forceinline__ bool key_follower(uint64_t k) { return ((k >> 2) & 1u) != 0; }
+__device__ __forceinline__ int key_f0(uint64_t k) { return (int)((k >> 3) & 31u); }
+__device__ __forceinline__ int key_f1(uint64_t k) { return (int)((k >> 8) & 31u); }
+__device__ __forceinline__ uint32_t key_pulse_start(uint64_t k) { return (uint32_t)((k >> 13) & 1u); }
 
-struct Window {               // one (group, channel) window, warp-uniform
-    int ch, a, e;             // photons keys[a, e)
-    int wl, len;              // first sample relative to origin_q, samples
-    int n_pulses;
-    int thr, mult;
-};
+__device__ __forceinline__ int adc_of(double cur, double c2a) {
+    return -__double2int_rn(__dmul_rn(cur, c2a));      // one rounding per pulse and sample: rawdata.py:236-239
+}
 
-// The photons of pulse [pa, pe) that can reach samples [lo, hi] (relative to origin_q) are superposed in the
-// register ring; every finished sample is handed to `sink(sample, value, lane_active)` exactly once, in
-// ascending sample order per call.  All lanes run the same control flow.
-//   gains: lane j holds the gain of photon keys[a0 + j] (prefetched by the caller, one round trip to L2 per
-//   window); photons further back in a long list are fetched one by one through `gain_of`.
-template <typename GainOf, typename Sink>
-__device__ __forceinline__ void superpose_pulse(const uint64_t *keys, int pa, int pe, int a0, double gpre, GainOf &&gain_of,
-                                                const double *s_tmpl, int tlen, int lo, int hi, int lane, Sink &&sink) {
-    auto gain_at = [&](int k) -> double {
-        const double pre = __shfl_sync(0xffffffffu, gpre, (k - a0) & 31);
-        return (k - a0) < 32 ? pre : gain_of(key_idx(keys[k]));
-    };
-    double acc = 0.0;
-    int base = 0;
-    bool have = false;
-    int k = pa;
-    while (k < pe) {
-        const uint64_t key = keys[k];
-        const uint32_t tk = key_time(key);
-        double g = gain_at(k);
-        int k2 = k + 1;
-        while (k2 < pe && key_time(keys[k2]) == tk) {      // equal-ns photons: gains summed first (pulse.py:301-318)
-            g = __dadd_rn(g, gain_at(k2));
-            k2++;
+// interval in shared memory: left + bias (21 bits) | samples (20) | channel (10) | first record slot (13)
+__device__ __forceinline__ uint64_t pack_itv(uint32_t lb, uint32_t plen, uint32_t ch, uint32_t r0) {
+    return ((uint64_t)lb << 43) | ((uint64_t)plen << 23) | ((uint64_t)ch << 13) | (uint64_t)r0;
+}
+// photon in HBM for the record kernel: sample << 4 | ns remainder, bit 24: first photon of a pulse
+constexpr uint32_t kTkeyPulseStart = 1u << 24;
+// record descriptor in HBM (uint4): x = left of the INTERVAL + bias (21) << 10 | channel; y = pulse length |
+// record_i (low 12 bits) << 20; z = first photon (13) | photons (14) << 13 | record_i >> 12 (2 bits) << 27
+
+// all-ascending bitonic network on items [0, n): every compare-exchange leaves the smaller item at the lower
+// index, so the virtual +inf padding behind n never moves and pairs that reach into it are skipped.
+// `first` / `step`: this thread's share of the items; `sync()` separates the stages.
+template <typename Less, typename Swap, typename Sync>
+__device__ __forceinline__ void bitonic_ascending(int n, int first, int step, Less &&less, Swap &&swap, Sync &&sync) {
+    for (int k = 2; (k >> 1) < n; k <<= 1) {
+        for (int i = first; i < n; i += step) {
+            const int p = i ^ (k - 1);
+            if (p > i && p < n && less(p, i)) swap(i, p);
         }
-        k = k2;
-        const int T = key_sample(key);
-        if (T + tlen - 1 < lo) continue;
-        if (T > hi) break;
-        if (have) {
-            const int d = T - base;
-            if (d > 0) {
-                sink(base + lane, acc, lane < d && lane < tlen);
-                const double moved = __shfl_down_sync(0xffffffffu, acc, (unsigned)min(d, 31));
-                acc = (d < 32 && lane + d < 32) ? moved : 0.0;
+        sync();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int i = first; i < n; i += step) {
+                const int p = i ^ j;
+                if (p > i && p < n && less(p, i)) swap(i, p);
             }
+            sync();
         }
-        base = T;
-        have = true;
-        if (lane < tlen) acc = __dadd_rn(acc, __dmul_rn(s_tmpl[key_rem(key) * tlen + lane], g));
     }
-    if (have) sink(base + lane, acc, lane < tlen);
 }
-
-__device__ __forceinline__ int adc_of(double cur, double c2a, int mult) {
-    return -__double2int_rn(__dmul_rn(cur, c2a)) * mult;      // one rounding per pulse and sample: rawdata.py:236-239
-}
-
-struct ZleState {
-    int last = kNegPos, start = kNegPos;
-};
 
 }  // namespace
 
-__global__ void __launch_bounds__(kFusedThreads)
-k_group_fused(FusedArgs A) {
+__global__ void __launch_bounds__(kFusedThreads, 2)
+k_group_analyse(FusedArgs A, FusedClass K) {
     extern __shared__ __align__(16) uint8_t smem[];
     const PhotonBatch &b = A.b;
     const DeviceConfig &c = A.c;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
     const int n_ch = c.p.n_tpc_pmts, dt = c.p.dt, tlen = c.p.template_length;
-    const Layout L = make_layout(A.n_cap, n_ch, n_warps, dt * tlen);
+    const Layout L = make_layout(K.n_cap, K.itv_cap, K.rec_cap, n_ch, dt * tlen, dt);
     FusedShared &S = *reinterpret_cast<FusedShared *>(smem);
     uint64_t *s_keys = reinterpret_cast<uint64_t *>(smem + L.keys);
+    double *s_gain = reinterpret_cast<double *>(smem + L.gains);
+    uint64_t *s_raw = reinterpret_cast<uint64_t *>(smem + L.gains);
+    uint64_t *s_itv = reinterpret_cast<uint64_t *>(smem + L.itv);
+    double *s_tmpl = reinterpret_cast<double *>(smem + L.tmpl);
+    double *s_cmax = reinterpret_cast<double *>(smem + L.cmax);
     int32_t *s_cstart = reinterpret_cast<int32_t *>(smem + L.chan_start);
     int32_t *s_cfill = reinterpret_cast<int32_t *>(smem + L.chan_fill);
-    uint16_t *s_winch = reinterpret_cast<uint16_t *>(smem + L.win_ch);
-    double *s_tmpl = reinterpret_cast<double *>(smem + L.tmpl);
-    uint64_t *s_raw = reinterpret_cast<uint64_t *>(smem + L.scratch);
-    int32_t *s_tile = reinterpret_cast<int32_t *>(smem + L.tiles) + warp * kFusedTile;
     uint32_t *s_rkey = reinterpret_cast<uint32_t *>(smem + L.rkey);
-    uint64_t *s_itv = reinterpret_cast<uint64_t *>(smem + L.itv);
+    int32_t *s_bin = reinterpret_cast<int32_t *>(smem + L.bins);
+    uint16_t *s_order = reinterpret_cast<uint16_t *>(smem + L.order);
+    uint16_t *s_winch = reinterpret_cast<uint16_t *>(smem + L.win_ch);
+    uint16_t *s_multi = reinterpret_cast<uint16_t *>(smem + L.multi);
 
     const double c2a = c.p.current_2_adc;
     const int LM = c.p.pulse_left_margin, RM = c.p.pulse_right_margin, tw = c.p.trigger_window, H = 2 * tw + 1;
     const int baseline = c.p.baseline;
     const int key_bias = LM + tw + 2;                 // record key time = left relative to origin + bias >= 0
-    const KeyFmt kf{kShiftSample + kSampleBits, kShiftSample + kSampleBits + A.relpc_bits};
+    const int shift_pc = kShiftSample + kSampleBits, shift_ch = shift_pc + A.relpc_bits;
+    const uint32_t pc_mask = (1u << A.relpc_bits) - 1u;
+    const bool smem_trig = (2 << A.relpc_bits) <= 2 * kFusedTrigSlots;     // 2 counters per pulse call of the group
+    const bool per_pmt = b.pmt_counts != nullptr;
 
     for (int i = tid; i < dt * tlen; i += blockDim.x) s_tmpl[i] = c.templates[i];
+    for (int i = tid; i < dt; i += blockDim.x) s_cmax[i] = c.current_max[i];
 
     for (;;) {
         __syncthreads();                              // everything of the previous group is done
-        if (tid == 0) S.group = (int32_t)atomicAdd(A.ticket, 1u);
+        if (tid == 0) {
+            const uint32_t i = atomicAdd(K.ticket, 1u);
+            S.group = i < K.n_list ? (int32_t)K.list[i] : -1;
+        }
         __syncthreads();
         const int g = S.group;
-        if (g >= (int)b.n_groups) break;
+        if (g < 0) break;
         // ------------------------------------------------------------------ load ----
         if (tid == 0) {
             S.n_valid = S.n_win = S.n_itv = S.n_rec = S.n_pulses = S.n_emitted = 0;
-            S.next_win = S.next_itv = 0;
+            S.n_multi = S.n_slow = 0;
             S.lo = INT_MAX; S.hi = INT_MIN;
+            S.tmax_q = 0; S.max_bin = 0;
             S.overflow = 0;
             S.n_samples = 0;
             S.origin_q = floordiv64(A.group_t0[g], dt);
         }
         for (int i = tid; i <= n_ch; i += blockDim.x) s_cfill[i] = 0;
+        if (smem_trig)
+            for (int i = tid; i < (2 << A.relpc_bits); i += blockDim.x) S.trig[i] = 0;
         __syncthreads();
         const int64_t origin_t = S.origin_q * dt;
         const int32_t run0 = A.group_run0[g];
-        uint32_t r_lo[4], r_n[4];
+        uint32_t r_lo[4], r_n[4], pbase = 0;
         int n_g = 0;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
@@ -205,6 +209,7 @@ k_group_fused(FusedArgs A) {
                 const uint32_t *gs = b.group_start + (size_t)r * (b.n_groups + 1);
                 r_lo[r] = gs[g];
                 r_n[r] = gs[g + 1] - gs[g];
+                pbase += gs[g] - gs[0];               // photons of the groups in front: this group's place in the sorted arrays
             }
             n_g += (int)r_n[r];
         }
@@ -217,28 +222,46 @@ k_group_fused(FusedArgs A) {
             if (i < (int)r_n[2]) return r_lo[2] + i;
             return r_lo[3] + (i - r_n[2]);
         };
-        for (int i = tid; i < n_g; i += blockDim.x) {
-            const uint32_t gi = global_index(i);
-            const int32_t ch = b.channel[gi];
-            const int32_t run = b.instr_run[b.pulse_call[gi]];
-            const uint8_t fl = b.flags[gi];
-            uint64_t key = ~0ull;
-            if (ch >= 0 && ch < n_ch && run >= 0 && c.gains[ch] != 0.0) {
-                const int64_t rel = b.t[gi] - origin_t;
-                const int64_t q = rel / dt;                       // rel >= 0: origin is a lower bound
-                const int relpc = 2 * (run - run0) + ((fl >> 1) & 1);
-                if (rel < 0 || q >= (1 << kSampleBits) || relpc < 0 || relpc >= (1 << A.relpc_bits)) {
-                    A.scalars[FS_OVERFLOW] = 1;        // outside the key range: the multi-pass back end decides
-                } else {
-                    key = ((uint64_t)ch << kf.shift_ch) | ((uint64_t)relpc << kf.shift_pc) |
-                          ((uint64_t)q << kShiftSample) | ((uint64_t)(rel - q * dt) << kShiftRem) |
-                          ((uint64_t)i << 1) | (uint64_t)(fl & 1);
-                    atomicAdd(&s_cfill[ch], 1);
+        if (n_g > K.n_cap) {                           // (the host bins the groups: cannot happen)
+            if (tid == 0) A.scalars[FS_OVERFLOW] = 2;
+            continue;
+        }
+        {
+            int qmax = 0;
+            for (int i = tid; i < n_g; i += blockDim.x) {
+                const uint32_t gi = global_index(i);
+                const int32_t ch = b.channel[gi];
+                const int32_t run = b.instr_run[b.pulse_call[gi]];
+                const uint8_t fl = b.flags[gi];
+                uint64_t key = ~0ull;
+                if (ch >= 0 && ch < n_ch && run >= 0 && c.gains[ch] != 0.0) {
+                    const int64_t rel = b.t[gi] - origin_t;
+                    const int64_t q = rel / dt;                       // rel >= 0: origin is a lower bound
+                    const int relpc = 2 * (run - run0) + ((fl >> 1) & 1);
+                    if (rel < 0 || q >= (1 << kSampleBits) - 2 * (RM + tw + key_bias) || relpc < 0 ||
+                        relpc >= (1 << A.relpc_bits) || i >= 8192) {
+                        A.scalars[FS_OVERFLOW] = 2;        // outside the key range: the multi-pass back end decides
+                    } else {
+                        key = ((uint64_t)ch << shift_ch) | ((uint64_t)relpc << shift_pc) |
+                              ((uint64_t)q << kShiftSample) | ((uint64_t)(rel - q * dt) << kShiftRem) |
+                              ((uint64_t)i << 1) | (uint64_t)(fl & 1);
+                        atomicAdd(&s_cfill[ch], 1);
+                        qmax = max(qmax, (int)q);
+                    }
                 }
+                s_raw[i] = key;
             }
-            s_raw[i] = key;
+            qmax = __reduce_max_sync(0xffffffffu, qmax);
+            if (lane == 0 && qmax > 0) atomicMax(&S.tmax_q, qmax);
         }
         __syncthreads();
+        // time bins of the record order: as fine as the bin array allows
+        int bin_shift = 0;
+        {
+            const int span = S.tmax_q + RM + tw + key_bias + 1;
+            while ((span >> bin_shift) >= kFusedBins) bin_shift++;
+        }
+        const int n_bins = ((S.tmax_q + RM + tw + key_bias + 1) >> bin_shift) + 1;
         // channel offsets (exclusive scan of the counts) by warp 0; list of non-empty channels
         if (warp == 0) {
             int carry = 0, nwin = 0;
@@ -251,7 +274,7 @@ k_group_fused(FusedArgs A) {
                     const int v = __shfl_up_sync(0xffffffffu, inc, o);
                     if (lane >= o) inc += v;
                 }
-                if (ch < n_ch) s_cstart[ch] = carry + inc - cnt;
+                if (ch < n_ch) { s_cstart[ch] = carry + inc - cnt; s_cfill[ch] = carry + inc - cnt; }
                 const unsigned m = __ballot_sync(0xffffffffu, cnt > 0);
                 if (cnt > 0) s_winch[nwin + __popc(m & ((1u << lane) - 1u))] = (uint16_t)ch;
                 nwin += __popc(m);
@@ -259,21 +282,32 @@ k_group_fused(FusedArgs A) {
             }
             if (lane == 0) { s_cstart[n_ch] = carry; S.n_valid = carry; S.n_win = nwin; }
         }
-        __syncthreads();
-        for (int i = tid; i <= n_ch; i += blockDim.x) s_cfill[i] = 0;
+        if (n_warps == 1 || warp > 0) {
+            const int t0 = n_warps == 1 ? tid : tid - 32, step = n_warps == 1 ? 32 : (int)blockDim.x - 32;
+            for (int i = t0; i < n_bins; i += step) s_bin[i] = 0;
+        }
         __syncthreads();
         for (int i = tid; i < n_g; i += blockDim.x) {
             const uint64_t key = s_raw[i];
             if (key == ~0ull) continue;
-            const int ch = (int)(key >> kf.shift_ch);
-            s_keys[s_cstart[ch] + atomicAdd(&s_cfill[ch], 1)] = key;
+            const int ch = (int)(key >> shift_ch);
+            s_keys[atomicAdd(&s_cfill[ch], 1)] = key;
         }
         __syncthreads();
+        const int n_valid = S.n_valid, n_win = S.n_win;
         // inside a channel: ascending (pulse call, time, index) -- insertion sort by one thread for short
-        // lists, rank sort by a warp for long ones
-        for (int w = tid; w < S.n_win; w += blockDim.x) {
+        // lists, a bitonic network run by a warp for long ones
+        for (int w = warp; w < n_win; w += n_warps) {
             const int ch = s_winch[w], a = s_cstart[ch], n = s_cstart[ch + 1] - a;
-            if (n > 48) continue;
+            if (n <= 16) continue;
+            uint64_t *k = s_keys + a;
+            bitonic_ascending(n, lane, 32, [&](int x, int y) { return k[x] < k[y]; },
+                              [&](int x, int y) { const uint64_t t = k[x]; k[x] = k[y]; k[y] = t; },
+                              [&]() { __syncwarp(); });
+        }
+        for (int w = tid; w < n_win; w += blockDim.x) {
+            const int ch = s_winch[w], a = s_cstart[ch], n = s_cstart[ch + 1] - a;
+            if (n > 16) continue;
             for (int i = 1; i < n; i++) {
                 const uint64_t x = s_keys[a + i];
                 int j = i - 1;
@@ -281,348 +315,570 @@ k_group_fused(FusedArgs A) {
                 s_keys[a + j + 1] = x;
             }
         }
-        __syncthreads();
-        for (int w = warp; w < S.n_win; w += n_warps) {
-            const int ch = s_winch[w], a = s_cstart[ch], n = s_cstart[ch + 1] - a;
-            if (n <= 48) continue;
-            for (int i = lane; i < n; i += 32) {                  // keys are distinct (index bits)
-                const uint64_t x = s_keys[a + i];
-                int rank = 0;
-                for (int j = 0; j < n; j++) rank += s_keys[a + j] < x ? 1 : 0;
-                s_raw[a + rank] = x;
+        __syncthreads();      // s_raw is dead from here on: the area now takes the gains
+        // ------------------------------------------------------------------ per photon: gain, trigger bit ----
+        for (int k = tid; k < n_valid; k += blockDim.x) {
+            const uint64_t key = s_keys[k];
+            const int ch = (int)(key >> shift_ch);
+            const double gn = b.gain[global_index(key_idx(key))];
+            s_gain[k] = gn;
+            uint64_t field = (uint64_t)kNoFlag << 2;
+            // equal ns on the same pulse: the gains are summed first (pulse.py:301-318) -- by the first of them
+            const uint64_t prev = k > s_cstart[ch] ? s_keys[k - 1] : ~key;
+            if ((prev >> kShiftRem) == (key >> kShiftRem)) field |= 2u;
+            if ((prev >> shift_pc) != (key >> shift_pc)) field |= 1u << 12;
+            if (b.trig_dpe_out) {        // pulse.py:229-271
+                const double thr_t = (double)(baseline - 1 - c.zle_thr[ch]) - 0.5;
+                const bool above = gn * s_cmax[key_rem(key)] * c2a > thr_t;
+                if (above) field |= 1u;
+                if (per_pmt && !(((uint32_t)(key >> shift_pc) & pc_mask) & 1u)) {
+                    const int32_t pc = 2 * run0 + (int)((uint32_t)(key >> shift_pc) & pc_mask);
+                    const long long ar = llrint(gn / c.gains[ch] * 4294967296.0);
+                    unsigned long long *ar_out = reinterpret_cast<unsigned long long *>(
+                        b.pmt_areas + ((int64_t)(pc >> 1) * 2) * (int64_t)n_ch + ch);
+                    atomicAdd(ar_out, (unsigned long long)ar);
+                    if (above) atomicAdd(ar_out + n_ch, (unsigned long long)ar);
+                }
             }
-            __syncwarp();
-            for (int i = lane; i < n; i += 32) s_keys[a + i] = s_raw[a + i];
+            s_keys[k] = (key & ~kFieldMask) | (field << 1);
         }
-        __syncthreads();      // s_raw (the scratch area) is free from here on: tiles, record keys, intervals
+        __syncthreads();
+        // leaders take the sum of their followers, followers add nothing any more; photons whose template meets
+        // no other photon of the channel take the short way below, the others are listed
+        for (int kb = warp * 32; kb < n_valid; kb += blockDim.x) {
+            const int k = kb + lane;
+            const bool valid = k < n_valid;
+            const uint64_t key = valid ? s_keys[k] : 0;
+            const int ch = (int)(key >> shift_ch);
+            bool alone = false, listed = false;
+            if (valid && !key_follower(key)) {
+                const int a = s_cstart[ch], e = s_cstart[ch + 1];
+                if (k + 1 < e && key_follower(s_keys[k + 1])) {
+                    double gsum = s_gain[k];
+                    for (int j = k + 1; j < e && key_follower(s_keys[j]); j++) gsum = __dadd_rn(gsum, s_gain[j]);
+                    s_gain[k] = gsum;
+                }
+                const int T = key_sample(key);
+                alone = (s_keys[a] >> shift_pc) == (s_keys[e - 1] >> shift_pc) &&
+                        (k == a || key_sample(s_keys[k - 1]) <= T - tlen) &&
+                        (k + 1 == e || key_sample(s_keys[k + 1]) >= T + tlen);
+                listed = !alone;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, listed);
+            int base = 0;
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) base = atomicAdd(&S.n_slow, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+            }
+            if (listed) s_order[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)k;
+            if (alone) {
+                // one photon, one pulse: every sample of the template against the threshold
+                const double gn = s_gain[k];
+                const double *tm = s_tmpl + key_rem(key) * tlen;
+                const int thr = c.zle_thr[ch];
+                int f0 = kNoFlag, f1 = 0;
+                for (int j = 0; j < tlen; j++) {
+                    if (max(adc_of(__dmul_rn(tm[j], gn), c2a) + baseline, 0) < thr) {
+                        if (f0 == kNoFlag) f0 = j;
+                        f1 = j;
+                    }
+                }
+                if (f0 != kNoFlag)
+                    s_keys[k] = (key & ~((uint64_t)0x3ff << 3)) | ((uint64_t)f0 << 3) | ((uint64_t)f1 << 8);
+            }
+        }
+        __syncthreads();
+        for (int k = tid; k < n_valid; k += blockDim.x)
+            if (key_follower(s_keys[k])) s_gain[k] = 0.0;
+        __syncthreads();
+        // ------------------------------------------------------------------ per photon: owned samples ----
+        for (int q = tid; q < S.n_slow; q += blockDim.x) {
+            const int k = s_order[q];
+            const uint64_t key = s_keys[k];
+            const int ch = (int)(key >> shift_ch);
+            const int a = s_cstart[ch], e = s_cstart[ch + 1];
+            const uint64_t pck = key >> shift_pc;
+            const int T = key_sample(key);
+            const bool single = (s_keys[a] >> shift_pc) == (s_keys[e - 1] >> shift_pc);
+            const int thr = c.zle_thr[ch];
+            int kn = k + 1;
+            while (kn < e && key_follower(s_keys[kn])) kn++;
+            const int Tn = (kn < e && (s_keys[kn] >> shift_pc) == pck) ? key_sample(s_keys[kn]) : INT_MAX;
+            const int s_end = min(T + tlen, Tn);           // owned samples [T, s_end)
+            int f0 = kNoFlag, f1 = 0;
+            if (single) {
+                int klo = k;
+                while (klo > a && key_sample(s_keys[klo - 1]) > T - tlen) klo--;
+                for (int s = T; s < s_end; s++) {
+                    while (key_sample(s_keys[klo]) <= s - tlen) klo++;
+                    double acc = 0.0;
+                    for (int j = klo; j <= k; j++) {
+                        const uint64_t kj = s_keys[j];
+                        acc = __dadd_rn(acc, __dmul_rn(s_tmpl[key_rem(kj) * tlen + (s - key_sample(kj))], s_gain[j]));
+                    }
+                    if (max(adc_of(acc, c2a) + baseline, 0) < thr) {
+                        if (f0 == kNoFlag) f0 = s - T;
+                        f1 = s - T;
+                    }
+                }
+            } else {
+                // several pulse calls on the channel: one rounding per pulse, integer sum over the pulses
+                for (int s = T; s < s_end; s++) {
+                    int adc = 0;
+                    double acc = 0.0;
+                    uint64_t cur = ~0ull;
+                    for (int j = a; j < e; j++) {
+                        const uint64_t kj = s_keys[j];
+                        const unsigned d = (unsigned)(s - key_sample(kj));
+                        if (d >= (unsigned)tlen) continue;
+                        if ((kj >> shift_pc) != cur) { adc += adc_of(acc, c2a); acc = 0.0; cur = kj >> shift_pc; }
+                        acc = __dadd_rn(acc, __dmul_rn(s_tmpl[key_rem(kj) * tlen + (int)d], s_gain[j]));
+                    }
+                    adc += adc_of(acc, c2a);
+                    if (max(adc + baseline, 0) < thr) {
+                        if (f0 == kNoFlag) f0 = s - T;
+                        f1 = s - T;
+                    }
+                }
+            }
+            if (f0 != kNoFlag)
+                s_keys[k] = (key & ~((uint64_t)0x3ff << 3)) | ((uint64_t)f0 << 3) | ((uint64_t)f1 << 8);
+        }
+        __syncthreads();
 
-        // gains stay in HBM / L2 (8 bytes per photon of shared memory buy a second CTA per SM instead):
-        // read by list index, prefetched per window
-        auto gain_of = [&](int idx) -> double { return b.gain[global_index(idx)]; };
-
-        // a window of the group, warp-uniform
-        auto window_of = [&](int ch) -> Window {
-            Window W;
-            W.ch = ch;
-            W.a = s_cstart[ch];
-            W.e = s_cstart[ch + 1];
-            W.thr = c.zle_thr[ch];
-            W.mult = 1;
+        // ------------------------------------------------------------------ per window: truth, ZLE intervals ----
+        // one ZLE interval of a window: utils.py:44-52, rawdata.py:303-308; s, e window-local
+        auto emit = [&](int ch, int wl, int wlen, int s, int e) {
+            int l = s - tw, r = e + tw;
+            l = max(0, min(l, wlen - 1));
+            r = max(0, min(r, wlen - 1));
+            l = (l + 1) & ~1;
+            r = r & ~1;
+            const int plen = max(r - l + 1, 0);
+            const int nrec = (plen + WFS_SAMPLES_PER_RECORD - 1) / WFS_SAMPLES_PER_RECORD;
+            if (nrec <= 0) return;
+            const int slot = atomicAdd(&S.n_itv, 1);
+            const int r0 = atomicAdd(&S.n_rec, nrec);
+            const int lb = wl + l + key_bias;
+            if (slot < K.itv_cap && r0 + nrec <= K.rec_cap && lb >= 0 &&
+                lb + WFS_SAMPLES_PER_RECORD * (nrec - 1) < ((n_bins << bin_shift)) && plen < (1 << 20)) {
+                s_itv[slot] = pack_itv((uint32_t)lb, (uint32_t)plen, (uint32_t)ch, (uint32_t)r0);
+                for (int i = 0; i < nrec; i++) {
+                    const uint32_t tk = (uint32_t)(lb + WFS_SAMPLES_PER_RECORD * i);
+                    s_rkey[r0 + i] = (tk << 10) | (uint32_t)ch;
+                    const int cnt = atomicAdd(&s_bin[tk >> bin_shift], 1) + 1;
+                    if (cnt > 24) atomicMax(&S.max_bin, cnt);
+                }
+            } else {
+                S.overflow = 1;
+            }
+        };
+        {
+            // windows with one pulse call: one lane each
+            int my_lo = INT_MAX, my_hi = INT_MIN, my_pulses = 0, my_emitted = 0;
+            unsigned long long my_samples = 0;
+            for (int w = tid; w < n_win; w += blockDim.x) {
+                const int ch = s_winch[w], a = s_cstart[ch], e = s_cstart[ch + 1];
+                const uint64_t kfirst = s_keys[a], klast = s_keys[e - 1];
+                if ((kfirst >> shift_pc) != (klast >> shift_pc)) {
+                    s_multi[atomicAdd(&S.n_multi, 1)] = (uint16_t)ch;
+                    continue;
+                }
+                const int wl = key_sample(kfirst) - LM - tw;                 // pulse.py:118-127, rawdata.py:258-259
+                const int wlen = (key_sample(klast) + RM + tw) - wl + 1;
+                if (wlen > kMaxGroupSamples + 1) { A.scalars[FS_ERR] = WFS_E_PULSE_CACHE_TOO_LONG; continue; }
+                my_lo = min(my_lo, wl + tw);
+                my_hi = max(my_hi, wl + wlen - 1 - tw);
+                my_pulses++;
+                my_samples += (unsigned long long)wlen;
+                const int relpc = (int)((uint32_t)(kfirst >> shift_pc) & pc_mask);
+                if (b.trig_dpe_out && !(relpc & 1)) {        // odd calls are PMT afterpulses: no truth
+                    int ndpe = 0, n_trig = 0, trig = 0;
+                    for (int k = a; k < e; k++) { const uint64_t key = s_keys[k]; ndpe += key_dpe(key); n_trig += key_above(key); }
+                    for (int k = a; k < a + ndpe; k++) trig += key_above(s_keys[k]);       // the [:n_double_pe] quirk, pulse.py:255
+                    const int32_t pc = 2 * run0 + relpc;
+                    if (trig) {
+                        if (smem_trig) {
+                            atomicAdd(&S.trig[2 * relpc], trig);
+                            if (ch >= c.p.n_top_pmts) atomicAdd(&S.trig[2 * relpc + 1], trig);
+                        } else {
+                            atomicAdd(&b.trig_dpe_out[2 * pc], trig);
+                            if (ch >= c.p.n_top_pmts) atomicAdd(&b.trig_dpe_out[2 * pc + 1], trig);
+                        }
+                    }
+                    if (per_pmt) {
+                        int32_t *cnt = b.pmt_counts + ((int64_t)(pc >> 1) * 4) * (int64_t)n_ch + ch;
+                        cnt[0] = e - a;
+                        cnt[n_ch] = e - a + ndpe;
+                        cnt[2 * n_ch] = n_trig;
+                        cnt[3 * n_ch] = n_trig + trig;
+                    }
+                }
+                int last = kNegPos, start = kNegPos;
+                for (int k = a; k < e; k++) {
+                    const uint64_t key = s_keys[k];
+                    const int f0 = key_f0(key);
+                    if (f0 == kNoFlag) continue;
+                    const int p0 = key_sample(key) + f0 - wl, p1 = key_sample(key) + key_f1(key) - wl;
+                    if (last == kNegPos) start = p0;
+                    else if (p0 - last > H) { emit(ch, wl, wlen, start, last); my_emitted++; start = p0; }
+                    last = p1;
+                }
+                if (last != kNegPos) { emit(ch, wl, wlen, start, last); my_emitted++; }
+            }
+            my_lo = __reduce_min_sync(0xffffffffu, my_lo);
+            my_hi = __reduce_max_sync(0xffffffffu, my_hi);
+            my_pulses = __reduce_add_sync(0xffffffffu, my_pulses);
+            my_emitted = __reduce_add_sync(0xffffffffu, my_emitted);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) my_samples += __shfl_xor_sync(0xffffffffu, my_samples, o);
+            if (lane == 0 && my_pulses) {
+                atomicMin(&S.lo, my_lo);
+                atomicMax(&S.hi, my_hi);
+                atomicAdd(&S.n_pulses, my_pulses);
+                atomicAdd(&S.n_emitted, my_emitted);
+                atomicAdd(&S.n_samples, my_samples);
+            }
+        }
+        __syncthreads();
+        // windows with several pulse calls: one warp each
+        for (int w = warp; w < S.n_multi; w += n_warps) {
+            const int ch = s_multi[w], a = s_cstart[ch], e = s_cstart[ch + 1];
             int qmin = INT_MAX, qmax = INT_MIN, np = 0;
-            for (int k0 = W.a; k0 < W.e; k0 += 32) {
+            for (int k0 = a; k0 < e; k0 += 32) {
                 const int k = k0 + lane;
-                const bool in = k < W.e;
+                const bool in = k < e;
                 const uint64_t key = in ? s_keys[k] : 0;
-                const uint64_t prev = (in && k > W.a) ? s_keys[k - 1] : ~0ull;
-                const bool first = in && (k == W.a || (key >> kf.shift_pc) != (prev >> kf.shift_pc));
-                np += __popc(__ballot_sync(0xffffffffu, first));
-                const int q = in ? key_sample(key) : INT_MAX;
-                qmin = min(qmin, q);
-                qmax = max(qmax, in ? q : INT_MIN);
+                np += __popc(__ballot_sync(0xffffffffu, in && key_pulse_start(key)));
+                qmin = min(qmin, in ? key_sample(key) : INT_MAX);
+                qmax = max(qmax, in ? key_sample(key) : INT_MIN);
             }
             qmin = __reduce_min_sync(0xffffffffu, qmin);
             qmax = __reduce_max_sync(0xffffffffu, qmax);
-            W.n_pulses = np;
-            W.wl = qmin - LM - tw;                                 // pulse.py:118-127, rawdata.py:258-259
-            W.len = (qmax + RM + tw) - W.wl + 1;
-            return W;
-        };
-
-        // ------------------------------------------------------------------ phase A ----
-        for (;;) {
-            int w = 0;
-            if (lane == 0) w = atomicAdd(&S.next_win, 1);
-            w = __shfl_sync(0xffffffffu, w, 0);
-            if (w >= S.n_win) break;
-            const Window W = window_of(s_winch[w]);
-            if (W.len > kMaxGroupSamples + 1) {
+            const int wl = qmin - LM - tw;
+            const int wlen = (qmax + RM + tw) - wl + 1;
+            if (wlen > kMaxGroupSamples + 1) {
                 if (lane == 0) A.scalars[FS_ERR] = WFS_E_PULSE_CACHE_TOO_LONG;
                 continue;
             }
-            const double gpre = W.a + lane < W.e ? gain_of(key_idx(s_keys[W.a + lane])) : 0.0;
-            if (lane == 0) {
-                atomicMin(&S.lo, W.wl + tw);
-                atomicMax(&S.hi, W.wl + W.len - 1 - tw);
-                atomicAdd(&S.n_pulses, W.n_pulses);
-                atomicAdd(&S.n_samples, (unsigned long long)W.len);
-            }
-            // ---- truth counters of every pulse (pulse.py:229-271; odd calls are PMT afterpulses: none) ----
             if (b.trig_dpe_out) {
-                const double thr_t = (double)(baseline - 1 - W.thr) - 0.5;
-                const double gch = c.gains[W.ch];
-                const bool per_pmt = b.pmt_counts != nullptr;
-                int pa = W.a;
-                while (pa < W.e) {
-                    const uint64_t pck = s_keys[pa] >> kf.shift_pc;
+                int pa = a;
+                while (pa < e) {
+                    const uint64_t pck = s_keys[pa] >> shift_pc;
                     int pe = pa + 1;
-                    while (pe < W.e && (s_keys[pe] >> kf.shift_pc) == pck) pe++;
-                    const int relpc = (int)(pck & ((1u << A.relpc_bits) - 1u));
+                    while (pe < e && (s_keys[pe] >> shift_pc) == pck) pe++;
+                    const int relpc = (int)((uint32_t)pck & pc_mask);
                     if (!(relpc & 1)) {
-                        int ndpe = 0;
-                        for (int k = pa + lane; k < pe; k += 32) ndpe += key_dpe(s_keys[k]);
+                        int ndpe = 0, n_trig = 0, trig = 0;
+                        for (int k = pa + lane; k < pe; k += 32) { const uint64_t key = s_keys[k]; ndpe += key_dpe(key); n_trig += key_above(key); }
                         ndpe = __reduce_add_sync(0xffffffffu, ndpe);
-                        int trig = 0, n_trig = 0;
-                        long long area = 0, area_trig = 0;
-                        const int stop = per_pmt ? pe : pa + ndpe;
-                        for (int k = pa + lane; k < stop; k += 32) {
-                            const uint64_t key = s_keys[k];
-                            const double gn = k - W.a == lane ? gpre : gain_of(key_idx(key));
-                            const bool above = gn * c.current_max[key_rem(key)] * c2a > thr_t;
-                            if (above && k < pa + ndpe) trig++;
-                            if (per_pmt) {
-                                const long long ar = llrint(gn / gch * 4294967296.0);
-                                area += ar;
-                                if (above) { n_trig++; area_trig += ar; }
-                            }
-                        }
+                        n_trig = __reduce_add_sync(0xffffffffu, n_trig);
+                        for (int k = pa + lane; k < pa + ndpe; k += 32) trig += key_above(s_keys[k]);
                         trig = __reduce_add_sync(0xffffffffu, trig);
                         const int32_t pc = 2 * run0 + relpc;
-                        if (per_pmt) {
-                            n_trig = __reduce_add_sync(0xffffffffu, n_trig);
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) {
-                                area += __shfl_xor_sync(0xffffffffu, area, o);
-                                area_trig += __shfl_xor_sync(0xffffffffu, area_trig, o);
-                            }
-                        }
                         if (lane == 0) {
                             if (trig) {
-                                atomicAdd(&b.trig_dpe_out[2 * pc], trig);
-                                if (W.ch >= c.p.n_top_pmts) atomicAdd(&b.trig_dpe_out[2 * pc + 1], trig);
+                                if (smem_trig) {
+                                    atomicAdd(&S.trig[2 * relpc], trig);
+                                    if (ch >= c.p.n_top_pmts) atomicAdd(&S.trig[2 * relpc + 1], trig);
+                                } else {
+                                    atomicAdd(&b.trig_dpe_out[2 * pc], trig);
+                                    if (ch >= c.p.n_top_pmts) atomicAdd(&b.trig_dpe_out[2 * pc + 1], trig);
+                                }
                             }
                             if (per_pmt) {
-                                const int64_t npmt = n_ch;
-                                int32_t *cnt = b.pmt_counts + ((int64_t)(pc >> 1) * 4) * npmt + W.ch;
-                                int64_t *ar_out = b.pmt_areas + ((int64_t)(pc >> 1) * 2) * npmt + W.ch;
+                                int32_t *cnt = b.pmt_counts + ((int64_t)(pc >> 1) * 4) * (int64_t)n_ch + ch;
                                 cnt[0] = pe - pa;
-                                cnt[npmt] = pe - pa + ndpe;
-                                cnt[2 * npmt] = n_trig;
-                                cnt[3 * npmt] = n_trig + trig;
-                                ar_out[0] = area;
-                                ar_out[npmt] = area_trig;
+                                cnt[n_ch] = pe - pa + ndpe;
+                                cnt[2 * n_ch] = n_trig;
+                                cnt[3 * n_ch] = n_trig + trig;
                             }
                         }
                     }
                     pa = pe;
                 }
             }
-            // ---- samples below threshold -> ZLE intervals ----
-            ZleState Z;
-            int n_emitted = 0;
-            auto emit = [&](int s, int e) {            // utils.py:44-52, rawdata.py:303-308; s, e window-local
-                int l = s - tw, r = e + tw;
-                l = max(0, min(l, W.len - 1));
-                r = max(0, min(r, W.len - 1));
-                l = (l + 1) & ~1;
-                r = r & ~1;
-                const int plen = max(r - l + 1, 0);
-                const int nrec = (plen + WFS_SAMPLES_PER_RECORD - 1) / WFS_SAMPLES_PER_RECORD;
-                n_emitted++;
-                if (lane == 0 && nrec > 0) {
-                    const int slot = atomicAdd(&S.n_itv, 1);
-                    const int r0 = atomicAdd(&S.n_rec, nrec);
-                    if (slot < kFusedItvCap && r0 + nrec <= kFusedRecCap) {
-                        // interval: left relative to origin (biased, 22 bits) | length (21 bits) | channel (10)
-                        s_itv[slot] = ((uint64_t)(uint32_t)(W.wl + l + key_bias) << 32) | ((uint64_t)(uint32_t)plen << 10) |
-                                      (uint64_t)W.ch;
-                        for (int i = 0; i < nrec; i++)
-                            s_rkey[r0 + i] = ((uint32_t)(W.wl + l + key_bias + WFS_SAMPLES_PER_RECORD * i) << 10) | (uint32_t)W.ch;
-                    } else {
-                        S.overflow = 1;
-                    }
+            // flagged runs in ascending (first sample, list position): selection by the warp
+            int last = kNegPos, start = kNegPos, n_emitted = 0;
+            unsigned long long cursor = 0;          // (p0 + 1) << 14 | position + 1 of the last run taken
+            for (;;) {
+                unsigned long long best = ~0ull;
+                for (int k = a + lane; k < e; k += 32) {
+                    const uint64_t key = s_keys[k];
+                    if (key_f0(key) == kNoFlag) continue;
+                    const unsigned long long cand =
+                        ((unsigned long long)(key_sample(key) + key_f0(key) - wl + 1) << 14) | (unsigned long long)(k - a + 1);
+                    if (cand > cursor && cand < best) best = cand;
                 }
-            };
-            auto feed = [&](int pos0, uint32_t word) {   // flagged samples pos0 + bit, ascending over calls
-                while (word) {
-                    const int bit = __ffs(word) - 1;
-                    const uint32_t run = word | (word - 1);
-                    const uint32_t stopb = ~run & (run + 1);
-                    const int run_end = stopb == 0 ? 31 : __ffs(stopb) - 2;
-                    const int p0 = pos0 + bit, p1 = pos0 + run_end;
-                    if (Z.last == kNegPos) Z.start = p0;
-                    else if (p0 - Z.last > H) { emit(Z.start, Z.last); Z.start = p0; }
-                    Z.last = p1;
-                    word = run_end >= 31 ? 0u : (word & ~((2u << run_end) - 1u));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long v = __shfl_xor_sync(0xffffffffu, best, o);
+                    best = v < best ? v : best;
                 }
-            };
-            if (W.n_pulses == 1) {
-                // one pulse: a finished sample of the ring is final -- no sample buffer at all
-                superpose_pulse(s_keys, W.a, W.e, W.a, gpre, gain_of, s_tmpl, tlen, INT_MIN / 2, INT_MAX / 2, lane,
-                                [&](int s, double cur, bool on) {
-                                    bool flag = false;
-                                    if (on && cur != 0.0) flag = max(adc_of(cur, c2a, 1) + baseline, 0) < W.thr;
-                                    const uint32_t word = __ballot_sync(0xffffffffu, flag);
-                                    if (word) feed(s - lane - W.wl, word);
-                                });
-            } else {
-                // several pulse calls on the channel: integer sum over the pulses in a sample tile
-                for (int t0 = 0; t0 < W.len; t0 += kFusedTile) {
-                    const int n = min(kFusedTile, W.len - t0);
-                    for (int i = lane; i < n; i += 32) s_tile[i] = 0;
-                    __syncwarp();
-                    int pa = W.a;
-                    while (pa < W.e) {
-                        const uint64_t pck = s_keys[pa] >> kf.shift_pc;
-                        int pe = pa + 1;
-                        while (pe < W.e && (s_keys[pe] >> kf.shift_pc) == pck) pe++;
-                        superpose_pulse(s_keys, pa, pe, W.a, gpre, gain_of, s_tmpl, tlen, W.wl + t0, W.wl + t0 + n - 1, lane,
-                                        [&](int s, double cur, bool on) {
-                                            const int i = s - W.wl - t0;
-                                            if (on && cur != 0.0 && i >= 0 && i < n) s_tile[i] += adc_of(cur, c2a, 1);
-                                        });
-                        __syncwarp();
-                        pa = pe;
-                    }
-                    for (int i0 = 0; i0 < n; i0 += 32) {
-                        const int i = i0 + lane;
-                        const bool flag = i < n && max(s_tile[i] + baseline, 0) < W.thr;
-                        const uint32_t word = __ballot_sync(0xffffffffu, flag);
-                        if (word) feed(t0 + i0, word);
-                    }
-                    __syncwarp();
-                }
+                if (best == ~0ull) break;
+                cursor = best;
+                const uint64_t key = s_keys[a + (int)(best & 16383u) - 1];
+                const int p0 = key_sample(key) + key_f0(key) - wl, p1 = key_sample(key) + key_f1(key) - wl;
+                if (last == kNegPos) { start = p0; last = p1; }
+                else if (p0 - last > H) {
+                    if (lane == 0) emit(ch, wl, wlen, start, last);
+                    n_emitted++;
+                    start = p0; last = p1;
+                } else last = max(last, p1);
             }
-            if (Z.last != kNegPos) emit(Z.start, Z.last);
-            if (lane == 0 && n_emitted) atomicAdd(&S.n_emitted, n_emitted);
+            if (last != kNegPos) {
+                if (lane == 0) emit(ch, wl, wlen, start, last);
+                n_emitted++;
+            }
+            if (lane == 0) {
+                atomicMin(&S.lo, wl + tw);
+                atomicMax(&S.hi, wl + wlen - 1 - tw);
+                atomicAdd(&S.n_pulses, np);
+                atomicAdd(&S.n_emitted, n_emitted);
+                atomicAdd(&S.n_samples, (unsigned long long)wlen);
+            }
         }
         __syncthreads();
         // ------------------------------------------------------------------ record order ----
-        const bool overflow = S.overflow != 0;
-        const int n_rec = overflow ? 0 : S.n_rec, n_itv = overflow ? 0 : S.n_itv;
-        if (overflow && tid == 0) A.scalars[FS_OVERFLOW] = 1;
-        int n_sort = 32;
-        while (n_sort < n_rec) n_sort <<= 1;
-        for (int i = n_rec + tid; i < n_sort; i += blockDim.x) s_rkey[i] = kPadKey;
-        __syncthreads();
-        for (int k = 2; k <= n_sort; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = tid; i < n_sort; i += blockDim.x) {
-                    const int ixj = i ^ j;
-                    if (ixj > i) {
-                        const uint32_t x = s_rkey[i], y = s_rkey[ixj];
-                        const bool up = (i & k) == 0;
-                        if ((x > y) == up) { s_rkey[i] = y; s_rkey[ixj] = x; }
-                    }
-                }
-                __syncthreads();
+        if (S.overflow) {
+            // the group outgrew the interval / record lists of its class: listed for the largest class
+            if (tid == 0) {
+                if (K.overflow_list) K.overflow_list[atomicAdd(A.over_count, 1u)] = (uint32_t)g;
+                else A.scalars[FS_OVERFLOW] = 1;
             }
+            continue;
         }
-        // ------------------------------------------------------------------ first record of the group ----
-        if (warp == 0) {
-            volatile uint64_t *st = A.status;
-            uint64_t base = 0;
-            if (g == 0) {
-                if (lane == 0) { __threadfence(); st[0] = kStPrefix | (uint64_t)n_rec; }
-            } else {
-                if (lane == 0) { __threadfence(); st[g] = kStAgg | (uint64_t)n_rec; }
-                int pos = g - 1;
-                for (;;) {
-                    const int p = pos - lane;
-                    uint64_t v = kStPrefix;                        // in front of group 0: prefix 0
-                    if (p >= 0) {
-                        do { v = st[p]; } while ((v & kStMask) == kStEmpty);
-                    }
-                    const unsigned is_prefix = __ballot_sync(0xffffffffu, (v & kStMask) == kStPrefix);
-                    const int first = __ffs(is_prefix) - 1;        // nearest group with an inclusive prefix
-                    uint64_t add = (first < 0 || lane <= first) ? (v & ~kStMask) : 0;
+        const int n_rec = S.n_rec, n_itv = S.n_itv;
+        if (tid == 0) {
+            // the group's descriptors: a block of the pool (any order; the scan over n_rec orders the records)
+            const unsigned long long off = atomicAdd((unsigned long long *)&A.scalars[FS_NREC], (unsigned long long)n_rec);
+            S.desc_off = (uint32_t)off;
+            if (off + (unsigned long long)n_rec > (unsigned long long)A.cap_records) S.desc_off = 0xffffffffu;
+            A.group_nrec[g] = (uint32_t)n_rec;
+            A.group_desc[g] = S.desc_off;
+        }
+        if (smem_trig && b.trig_dpe_out)
+            for (int i = tid; i < (2 << A.relpc_bits); i += blockDim.x)
+                if (S.trig[i]) atomicAdd(&b.trig_dpe_out[2 * (2 * run0) + i], S.trig[i]);
+        // the photons in channel order for the record kernel
+        for (int k = tid; k < n_valid; k += blockDim.x) {
+            const uint64_t key = s_keys[k];
+            A.tkey[pbase + k] = (uint32_t)((key >> kShiftRem) & 0xffffffu) | (key_pulse_start(key) ? kTkeyPulseStart : 0u);
+            A.mgain[pbase + k] = s_gain[k];
+        }
+        if (S.max_bin <= 24) {
+            // counting sort over the time bins, then every bin ordered by (time, channel) by one thread
+            const int ipt = (n_bins + (int)blockDim.x - 1) / (int)blockDim.x;
+            const int b0 = min(tid * ipt, n_bins), b1 = min(b0 + ipt, n_bins);
+            int sum = 0;
+            for (int i = b0; i < b1; i++) sum += s_bin[i];
+            int inc = sum;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
-                    base += add;
-                    if (first >= 0) break;
-                    pos -= 32;
-                }
-                if (lane == 0) { __threadfence(); st[g] = kStPrefix | (base + (uint64_t)n_rec); }
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
             }
-            if (lane == 0) {
-                S.rec_base = (uint32_t)base;
-                if (g == (int)b.n_groups - 1) A.scalars[FS_NREC] = (int64_t)(base + (uint64_t)n_rec);
-                // group bookkeeping for the chunker (rawdata.py:215-222)
-                wfs_group_info gi;
-                if (S.lo == INT_MAX) {
-                    gi.left = 0; gi.right = 0; gi.n_intervals = -1;
-                } else {
-                    gi.left = S.origin_q + S.lo - tw;
-                    gi.right = S.origin_q + S.hi + tw;
-                    if (gi.right - gi.left >= kMaxGroupSamples) A.scalars[FS_ERR] = WFS_E_PULSE_CACHE_TOO_LONG;
-                    if (gi.left % 2 != 0) gi.left -= 1;
-                    gi.n_intervals = S.n_emitted;
+            if (lane == 31) S.warp_sums[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                int v = lane < n_warps ? S.warp_sums[lane] : 0, iv = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, iv, o);
+                    if (lane >= o) iv += u;
                 }
-                if (A.group_info) A.group_info[g] = gi;
-                atomicAdd((unsigned long long *)&A.scalars[FS_NVALID], (unsigned long long)S.n_valid);
-                atomicAdd((unsigned long long *)&A.scalars[FS_NPULSES], (unsigned long long)S.n_pulses);
-                atomicAdd((unsigned long long *)&A.scalars[FS_NWIN], (unsigned long long)S.n_win);
-                atomicAdd((unsigned long long *)&A.scalars[FS_NITV], (unsigned long long)S.n_emitted);
-                atomicAdd((unsigned long long *)&A.scalars[FS_NSAMPLES], S.n_samples);
+                S.warp_sums[lane] = iv - v;
             }
+            __syncthreads();
+            int run = S.warp_sums[warp] + inc - sum;
+            for (int i = b0; i < b1; i++) { const int cnt = s_bin[i]; s_bin[i] = run; run += cnt; }
+            __syncthreads();
+            for (int slot = tid; slot < n_rec; slot += blockDim.x)
+                s_order[atomicAdd(&s_bin[s_rkey[slot] >> (10 + bin_shift)], 1)] = (uint16_t)slot;
+            __syncthreads();
+            for (int bi = tid; bi < n_bins; bi += blockDim.x) {
+                const int lo = bi ? s_bin[bi - 1] : 0, hi = s_bin[bi];
+                for (int i = lo + 1; i < hi; i++) {
+                    const uint16_t x = s_order[i];
+                    const uint32_t kx = s_rkey[x];
+                    int j = i - 1;
+                    while (j >= lo && s_rkey[s_order[j]] > kx) { s_order[j + 1] = s_order[j]; j--; }
+                    s_order[j + 1] = x;
+                }
+                for (int i = lo; i < hi; i++) s_rkey[s_order[i]] = (uint32_t)i;      // key -> rank
+            }
+        } else {
+            // many records in one bin (a long group): bitonic network over all records of the group
+            for (int i = tid; i < n_rec; i += blockDim.x) s_order[i] = (uint16_t)i;
+            __syncthreads();
+            bitonic_ascending(n_rec, tid, blockDim.x, [&](int x, int y) { return s_rkey[s_order[x]] < s_rkey[s_order[y]]; },
+                              [&](int x, int y) { const uint16_t t = s_order[x]; s_order[x] = s_order[y]; s_order[y] = t; },
+                              [&]() { __syncthreads(); });
+            // the network's last barrier is behind us: nobody reads a key any more, ranks replace them
+            for (int i = tid; i < n_rec; i += blockDim.x) s_rkey[s_order[i]] = (uint32_t)i;
         }
         __syncthreads();
-        // ------------------------------------------------------------------ phase B ----
-        const int64_t rec_base = S.rec_base;
-        for (;;) {
-            int it = 0;
-            if (lane == 0) it = atomicAdd(&S.next_itv, 1);
-            it = __shfl_sync(0xffffffffu, it, 0);
-            if (it >= n_itv) break;
-            const uint64_t iv = s_itv[it];
-            const int ch = (int)(iv & 1023u), plen = (int)((iv >> 10) & ((1u << 21) - 1u));
-            const int left = (int)(uint32_t)(iv >> 32) - key_bias;          // relative to origin_q
-            const int a = s_cstart[ch], e = s_cstart[ch + 1];
-            const double gpre = a + lane < e ? gain_of(key_idx(s_keys[a + lane])) : 0.0;
-            constexpr int kChunkRecs = kFusedTile / WFS_SAMPLES_PER_RECORD;
-            const int n_recs = (plen + WFS_SAMPLES_PER_RECORD - 1) / WFS_SAMPLES_PER_RECORD;
-            for (int r0 = 0; r0 < n_recs; r0 += kChunkRecs) {
-                const int tl = left + r0 * WFS_SAMPLES_PER_RECORD;
-                const int n = min(kChunkRecs * WFS_SAMPLES_PER_RECORD, plen - r0 * WFS_SAMPLES_PER_RECORD);
-                for (int i = lane; i < n; i += 32) s_tile[i] = 0;
-                __syncwarp();
-                int pa = a;
-                while (pa < e) {
-                    const uint64_t pck = s_keys[pa] >> kf.shift_pc;
-                    int pe = pa + 1;
-                    while (pe < e && (s_keys[pe] >> kf.shift_pc) == pck) pe++;
-                    superpose_pulse(s_keys, pa, pe, a, gpre, gain_of, s_tmpl, tlen, tl, tl + n - 1, lane,
-                                    [&](int s, double cur, bool on) {
-                                        const int i = s - tl;
-                                        if (on && cur != 0.0 && i >= 0 && i < n) s_tile[i] += adc_of(cur, c2a, 1);
-                                    });
-                    __syncwarp();
-                    pa = pe;
+        // ------------------------------------------------------------------ descriptors, group bookkeeping ----
+        if (S.desc_off != 0xffffffffu && A.desc) {
+            for (int it = tid; it < n_itv; it += blockDim.x) {
+                const uint64_t iv = s_itv[it];
+                const int ch = (int)((iv >> 13) & 1023u), plen = (int)((iv >> 23) & ((1u << 20) - 1u));
+                const uint32_t lb = (uint32_t)(iv >> 43);
+                const int left = (int)lb - key_bias;                        // relative to origin_q
+                const int r0 = (int)(iv & 8191u);
+                const int a = s_cstart[ch], e = s_cstart[ch + 1];
+                const bool single = (s_keys[a] >> shift_pc) == (s_keys[e - 1] >> shift_pc);
+                const int n_recs = (plen + WFS_SAMPLES_PER_RECORD - 1) / WFS_SAMPLES_PER_RECORD;
+                int ka = a, kb = a;
+                for (int r = 0; r < n_recs; r++) {
+                    const int first = left + r * WFS_SAMPLES_PER_RECORD;
+                    const int length = min(plen - r * WFS_SAMPLES_PER_RECORD, WFS_SAMPLES_PER_RECORD);
+                    if (single) {          // time order: the photons that reach the record are one run of the list
+                        while (ka < e && key_sample(s_keys[ka]) + tlen <= first) ka++;
+                        kb = max(kb, ka);
+                        while (kb < e && key_sample(s_keys[kb]) < first + length) kb++;
+                    } else { ka = a; kb = e; }
+                    uint4 d;
+                    d.x = (lb << 10) | (uint32_t)ch;
+                    d.y = (uint32_t)plen | ((uint32_t)(r & 0xfff) << 20);
+                    d.z = (kb > ka ? (uint32_t)ka : 0u) | ((uint32_t)(kb - ka) << 13) | ((uint32_t)(r >> 12) << 27);
+                    d.w = 0;
+                    A.desc[(size_t)S.desc_off + s_rkey[r0 + r]] = d;
                 }
-                const int here = min(kChunkRecs, n_recs - r0);
-                for (int r = 0; r < here; r++) {
-                    const int rec_i = r0 + r;
-                    const int first = tl + r * WFS_SAMPLES_PER_RECORD;
-                    const uint32_t key = ((uint32_t)(first + key_bias) << 10) | (uint32_t)ch;
-                    int lo = 0, hi = n_rec;                        // rank of the record in the group
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        if (s_rkey[mid] < key) lo = mid + 1; else hi = mid;
-                    }
-                    const int64_t dest = rec_base + lo;
-                    if (dest >= A.cap_records) continue;
-                    const int length = min(plen, WFS_SAMPLES_PER_RECORD * (rec_i + 1)) - WFS_SAMPLES_PER_RECORD * rec_i;
-                    const int64_t time = (int64_t)dt * (S.origin_q + first);
-                    uint32_t *out = reinterpret_cast<uint32_t *>(A.records_out + dest * WFS_RECORD_BYTES);
-                    // strax_interface.py:425-436: time, length, dt, channel, pulse_length, record_i, baseline = 0
-                    uint32_t h = (uint32_t)(uint64_t)time;
-                    h = lane == 1 ? (uint32_t)((uint64_t)time >> 32) : h;
-                    h = lane == 2 ? (uint32_t)length : h;
-                    h = lane == 3 ? (((uint32_t)(uint16_t)dt) | ((uint32_t)(uint16_t)ch << 16)) : h;
-                    h = lane == 4 ? (uint32_t)plen : h;
-                    h = lane == 5 ? (uint32_t)(uint16_t)rec_i : h;
-                    const int base_i = r * WFS_SAMPLES_PER_RECORD;
-                    auto sample = [&](int j) -> uint32_t {         // record-local sample j -> int16 ADC
-                        if (j >= length) return 0u;
-                        return (uint32_t)(uint16_t)(int16_t)max(s_tile[base_i + j] + baseline, 0);
-                    };
-                    // word w of the record: lanes 0..5 header, data word d = w - 6 holds samples 2d, 2d + 1
-                    uint32_t w0 = h;
-                    if (lane >= 6) { const int d = lane - 6; w0 = sample(2 * d) | (sample(2 * d + 1) << 16); }
-                    out[lane] = w0;
-                    if (lane + 32 < 61) { const int d = lane + 26; out[lane + 32] = sample(2 * d) | (sample(2 * d + 1) << 16); }
-                }
-                __syncwarp();
             }
+        }
+        if (tid == 0) {
+            // group bookkeeping for the chunker (rawdata.py:215-222)
+            wfs_group_info gi;
+            if (S.lo == INT_MAX) {
+                gi.left = 0; gi.right = 0; gi.n_intervals = -1;
+            } else {
+                gi.left = S.origin_q + S.lo - tw;
+                gi.right = S.origin_q + S.hi + tw;
+                if (gi.right - gi.left >= kMaxGroupSamples) A.scalars[FS_ERR] = WFS_E_PULSE_CACHE_TOO_LONG;
+                if (gi.left % 2 != 0) gi.left -= 1;
+                gi.n_intervals = S.n_emitted;
+            }
+            if (A.group_info) A.group_info[g] = gi;
+            atomicAdd((unsigned long long *)&A.scalars[FS_NVALID], (unsigned long long)S.n_valid);
+            atomicAdd((unsigned long long *)&A.scalars[FS_NPULSES], (unsigned long long)S.n_pulses);
+            atomicAdd((unsigned long long *)&A.scalars[FS_NWIN], (unsigned long long)S.n_win);
+            atomicAdd((unsigned long long *)&A.scalars[FS_NITV], (unsigned long long)S.n_emitted);
+            atomicAdd((unsigned long long *)&A.scalars[FS_NSAMPLES], S.n_samples);
+        }
+    }
+}
+
+// One warp per record, lane = record word.  The record's descriptor names the photons (channel order, merged
+// gains) that can reach it; every sample is summed over them in the order of Pulse.add_current, rounded once
+// per pulse (rawdata.py:236-239), and the 244-byte record is written at rec_base[group] + rank.
+__global__ void __launch_bounds__(kFusedRecordThreads)
+k_group_records(FusedArgs A) {
+    __shared__ double s_tmpl[16 * 32];
+    const PhotonBatch &b = A.b;
+    const DeviceConfig &c = A.c;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int dt = c.p.dt, tlen = c.p.template_length;
+    for (int i = threadIdx.x; i < dt * tlen; i += blockDim.x) s_tmpl[i] = c.templates[i];
+    __syncthreads();
+    const double c2a = c.p.current_2_adc;
+    const int baseline = c.p.baseline;
+    const int key_bias = c.p.pulse_left_margin + c.p.trigger_window + 2;
+    const uint32_t fill = (uint32_t)(uint16_t)(int16_t)max(baseline, 0);
+    // record word `lane` holds header words 0..5 or samples 2(lane-6), 2(lane-6)+1; word lane+32 samples 2(lane+26), +1
+    const int sa = 2 * (lane - 6), sb = 2 * (lane + 26);
+    for (int g = blockIdx.x; g < (int)b.n_groups; g += gridDim.x) {
+        const uint32_t n_rec = A.group_nrec[g], desc_off = A.group_desc[g];
+        if (n_rec == 0 || desc_off == 0xffffffffu) continue;
+        const int64_t rec_base = (int64_t)A.rec_base[g];
+        const int64_t origin_q = floordiv64(A.group_t0[g], dt);
+        uint32_t pbase = 0;
+        for (int r = 0; r < b.group_ranges; r++) {
+            const uint32_t *gs = b.group_start + (size_t)r * (b.n_groups + 1);
+            pbase += gs[g] - gs[0];
+        }
+        const uint32_t *tkey = A.tkey + pbase;
+        const double *mgain = A.mgain + pbase;
+        for (uint32_t rank = warp; rank < n_rec; rank += n_warps) {
+            const int64_t dest = rec_base + rank;
+            if (dest >= A.cap_records) continue;
+            const uint4 d = A.desc[(size_t)desc_off + rank];
+            const int ch = (int)(d.x & 1023u), plen = (int)(d.y & 0xfffffu);
+            const int rec_i = (int)((d.y >> 20) | ((d.z >> 27) << 12));
+            const int ka = (int)(d.z & 8191u), nk = (int)((d.z >> 13) & 16383u);
+            const int first = (int)(d.x >> 10) - key_bias + rec_i * WFS_SAMPLES_PER_RECORD;     // relative to origin_q
+            const int length = min(plen - rec_i * WFS_SAMPLES_PER_RECORD, WFS_SAMPLES_PER_RECORD);
+            int adc0 = 0, adc1 = 0, adc2 = 0, adc3 = 0;
+            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+            bool any = false;
+            for (int k0 = 0; k0 < nk; k0 += 32) {
+                const int kk = k0 + lane;
+                const uint32_t tk = kk < nk ? tkey[ka + kk] : 0u;
+                const double gk = kk < nk ? mgain[ka + kk] : 0.0;
+                const int Tk = (int)((tk >> 4) & 0xfffffu) - first;
+                unsigned m = __ballot_sync(0xffffffffu, kk < nk && Tk + tlen > 0 && Tk < length);
+                // a pulse that starts among the photons skipped in front still separates the roundings
+                unsigned starts = __ballot_sync(0xffffffffu, kk < nk && (tk & kTkeyPulseStart));
+                unsigned seen = 0;
+                while (m) {
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t tb = __shfl_sync(0xffffffffu, tk, bit);
+                    const double gb = __shfl_sync(0xffffffffu, gk, bit);
+                    const unsigned upto = bit == 31 ? 0xffffffffu : ((2u << bit) - 1u);
+                    if (any && (starts & upto & ~seen)) {          // next pulse call: one rounding per pulse and sample
+                        adc0 += adc_of(acc0, c2a); adc1 += adc_of(acc1, c2a);
+                        adc2 += adc_of(acc2, c2a); adc3 += adc_of(acc3, c2a);
+                        acc0 = acc1 = acc2 = acc3 = 0.0;
+                    }
+                    seen = upto;
+                    any = true;
+                    const int Tb = (int)((tb >> 4) & 0xfffffu) - first;
+                    const double *tm = s_tmpl + (int)(tb & 15u) * tlen;
+                    if (Tb < 52) {                              // samples of words 0..31
+                        const unsigned d0 = (unsigned)(sa - Tb), d1 = (unsigned)(sa + 1 - Tb);
+                        if (lane >= 6 && d0 < (unsigned)tlen) acc0 = __dadd_rn(acc0, __dmul_rn(tm[d0], gb));
+                        if (lane >= 6 && d1 < (unsigned)tlen) acc1 = __dadd_rn(acc1, __dmul_rn(tm[d1], gb));
+                    }
+                    if (Tb + tlen > 52) {                       // samples of words 32..60
+                        const unsigned d2 = (unsigned)(sb - Tb), d3 = (unsigned)(sb + 1 - Tb);
+                        if (d2 < (unsigned)tlen) acc2 = __dadd_rn(acc2, __dmul_rn(tm[d2], gb));
+                        if (d3 < (unsigned)tlen) acc3 = __dadd_rn(acc3, __dmul_rn(tm[d3], gb));
+                    }
+                }
+                // pulses that start behind the last photon taken from this chunk
+                if (any && (starts & ~seen)) {
+                    adc0 += adc_of(acc0, c2a); adc1 += adc_of(acc1, c2a);
+                    adc2 += adc_of(acc2, c2a); adc3 += adc_of(acc3, c2a);
+                    acc0 = acc1 = acc2 = acc3 = 0.0;
+                }
+            }
+            uint32_t w0, w1;
+            if (any) {
+                adc0 += adc_of(acc0, c2a); adc1 += adc_of(acc1, c2a);
+                adc2 += adc_of(acc2, c2a); adc3 += adc_of(acc3, c2a);
+                const uint32_t v0 = sa < length ? (uint32_t)(uint16_t)(int16_t)max(adc0 + baseline, 0) : 0u;
+                const uint32_t v1 = sa + 1 < length ? (uint32_t)(uint16_t)(int16_t)max(adc1 + baseline, 0) : 0u;
+                const uint32_t v2 = sb < length ? (uint32_t)(uint16_t)(int16_t)max(adc2 + baseline, 0) : 0u;
+                const uint32_t v3 = sb + 1 < length ? (uint32_t)(uint16_t)(int16_t)max(adc3 + baseline, 0) : 0u;
+                w0 = v0 | (v1 << 16);
+                w1 = v2 | (v3 << 16);
+            } else {
+                w0 = (sa < length ? fill : 0u) | (sa + 1 < length ? fill << 16 : 0u);
+                w1 = (sb < length ? fill : 0u) | (sb + 1 < length ? fill << 16 : 0u);
+            }
+            // strax_interface.py:425-436: time, length, dt, channel, pulse_length, record_i, baseline = 0
+            const int64_t time = (int64_t)dt * (origin_q + first);
+            uint32_t h = (uint32_t)(uint64_t)time;
+            h = lane == 1 ? (uint32_t)((uint64_t)time >> 32) : h;
+            h = lane == 2 ? (uint32_t)length : h;
+            h = lane == 3 ? (((uint32_t)(uint16_t)dt) | ((uint32_t)(uint16_t)ch << 16)) : h;
+            h = lane == 4 ? (uint32_t)plen : h;
+            h = lane == 5 ? (uint32_t)(uint16_t)rec_i : h;
+            uint32_t *out = reinterpret_cast<uint32_t *>(A.records_out + dest * WFS_RECORD_BYTES);
+            out[lane] = lane < 6 ? h : w0;
+            if (lane + 32 < 61) out[lane + 32] = w1;
         }
     }
 }
@@ -632,13 +888,14 @@ bool Backend::fused_eligible(const PhotonBatch &b) const {
     const char *env = getenv("WFS_FUSED");      // WFS_FUSED=0: always the multi-pass back end (A/B tests)
     const bool on = !(env && atoi(env) == 0);
     const DeviceConfig &c = *cfg_;
-    if (!on || !b.group_start || !b.group_t0 || !b.group_run0 || !b.instr_run || !b.flags) return false;
+    if (!on || !b.group_start || !b.h_group_start || !b.group_t0 || !b.group_run0 || !b.instr_run || !b.flags) return false;
     if (b.group_ranges < 1 || b.group_ranges > 4) return false;
     if (b.max_group_photons > kFusedMaxPhotons || b.max_group_photons < 0) return false;
     if (b.relpc_bits < 1 || kShiftSample + kSampleBits + b.relpc_bits + kChannelBits > 64) return false;
     if (c.p.enable_noise && c.noise_t) return false;          // every sample carries noise: dense path
     if (c.he_rows_possible || c.thr_above_baseline) return false;
-    if (c.p.dt > 16 || c.p.template_length > 32) return false;
+    if (c.p.dt > 16 || c.p.template_length > 30 || c.p.n_tpc_pmts > 1023) return false;
+    if (2 * c.p.trigger_window + 1 < c.p.template_length) return false;   // flagged runs of a photon may then split an interval
     return true;
 }
 
@@ -646,47 +903,112 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
                         wfs_group_info *group_info_out, BackendResult &res) {
     const DeviceConfig &c = *cfg_;
     const int64_t ng = b.n_groups;
-    int n_cap = (int)std::max<int64_t>(1024, (b.max_group_photons + 1023) / 1024 * 1024);
-    // 8 warps and two CTAs per SM while the photons of a group leave room for it, else one CTA
-    const int threads = kFusedThreads;
-    const Layout L = make_layout(n_cap, c.p.n_tpc_pmts, threads / 32, c.p.dt * c.p.template_length);
-    if (L.total > 227 * 1024) return false;
-    if (!fused_attr_set_ || L.total > fused_smem_set_) {
-        WFS_CUDA_CHECK(cudaFuncSetAttribute(k_group_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        fused_attr_set_ = true;
-        fused_smem_set_ = L.total;
+    const int n_ch = c.p.n_tpc_pmts, tmpl_len = c.p.dt * c.p.template_length;
+    // groups by photon count: small groups get small shared-memory lists and many CTAs per SM
+    struct ClassDef { int n_cap, itv_cap, rec_cap, threads; };
+    ClassDef defs[kFusedClasses] = {{512, 512, 1024, 128}, {2048, 1024, 3072, 256}, {4096, 2048, 6144, 512},
+                                    {kFusedMaxPhotons, 4096, kFusedMaxRecCap, 512}};
+    if (const char *e = getenv("WFS_FUSED_REC_CAP"))          // tests: small lists, so that groups take the second attempt
+        for (int k = 0; k + 1 < kFusedClasses; k++) defs[k].rec_cap = std::max(32, std::min(defs[k].rec_cap, atoi(e)));
+    std::vector<uint32_t> list((size_t)ng);
+    uint32_t cls_n[kFusedClasses] = {0, 0, 0, 0}, cls_off[kFusedClasses + 1];
+    std::vector<uint8_t> cls_of((size_t)ng);
+    for (int64_t g = 0; g < ng; g++) {
+        int64_t n = 0;
+        for (int r = 0; r < b.group_ranges; r++) {
+            const uint32_t *gs = b.h_group_start + (size_t)r * (ng + 1);
+            n += gs[g + 1] - gs[g];
+        }
+        int k = 0;
+        while (k + 1 < kFusedClasses && n > defs[k].n_cap) k++;
+        if (n > defs[k].n_cap) return false;
+        cls_of[g] = (uint8_t)k;
+        cls_n[k]++;
     }
-    int ctas_per_sm = 1;
-    WFS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_group_fused, threads, L.total));
-    if (ctas_per_sm < 1) return false;
-    fused_status_.reserve(sizeof(uint64_t) * (size_t)(ng + 1) + 64);
-    uint32_t *ticket = reinterpret_cast<uint32_t *>(fused_status_.as<uint64_t>() + ng);
-    fused_scal_.reserve(sizeof(int64_t) * FS_COUNT);
-    WFS_CUDA_CHECK(cudaMemsetAsync(fused_status_.p, 0, sizeof(uint64_t) * (size_t)(ng + 1), stream_));
-    WFS_CUDA_CHECK(cudaMemsetAsync(fused_scal_.p, 0, sizeof(int64_t) * FS_COUNT, stream_));
+    cls_off[0] = 0;
+    for (int k = 0; k < kFusedClasses; k++) cls_off[k + 1] = cls_off[k] + cls_n[k];
+    {
+        uint32_t fill[kFusedClasses];
+        for (int k = 0; k < kFusedClasses; k++) fill[k] = cls_off[k];
+        for (int64_t g = 0; g < ng; g++) list[fill[cls_of[g]]++] = (uint32_t)g;
+    }
+    // workspaces: [ng] group list, [ng] overflow list, [ng + 1] record counts, [ng + 1] record bases, [ng] descriptor offsets
+    fused_lists_.reserve(sizeof(uint32_t) * (size_t)(5 * ng + 8));
+    uint32_t *d_list = fused_lists_.as<uint32_t>(), *d_over = d_list + ng, *d_nrec = d_over + ng,
+             *d_base = d_nrec + ng + 1, *d_desc_off = d_base + ng + 1;
+    fused_scal_.reserve(sizeof(int64_t) * (FS_COUNT + 8));
+    int64_t *d_scal = fused_scal_.as<int64_t>();
+    uint32_t *d_u32 = reinterpret_cast<uint32_t *>(d_scal + FS_COUNT);        // [0] overflow count, [1..] tickets
+    fused_tkey_.reserve(sizeof(uint32_t) * (size_t)std::max<int64_t>(b.n, 1));
+    fused_gain_.reserve(sizeof(double) * (size_t)std::max<int64_t>(b.n, 1));
+    const bool want = records_out != nullptr && cap_records > 0;
+    if (want) fused_desc_.reserve(sizeof(uint4) * (size_t)cap_records);
+    WFS_CUDA_CHECK(cudaMemcpyAsync(d_list, list.data(), sizeof(uint32_t) * (size_t)ng, cudaMemcpyHostToDevice, stream_));
+    WFS_CUDA_CHECK(cudaMemsetAsync(d_nrec, 0, sizeof(uint32_t) * (size_t)(ng + 1), stream_));
+    WFS_CUDA_CHECK(cudaMemsetAsync(d_scal, 0, sizeof(int64_t) * (FS_COUNT + 8), stream_));
     FusedArgs A;
     A.b = b;
     A.c = c;
-    A.n_cap = n_cap;
     A.relpc_bits = b.relpc_bits;
     A.group_t0 = b.group_t0;
     A.group_run0 = b.group_run0;
-    A.status = fused_status_.as<uint64_t>();
-    A.ticket = ticket;
-    A.scalars = fused_scal_.as<int64_t>();
-    A.group_nitv = nullptr;
+    A.scalars = d_scal;
+    A.over_count = d_u32;
+    A.group_nrec = d_nrec;
+    A.group_desc = d_desc_off;
+    A.rec_base = d_base;
+    A.tkey = fused_tkey_.as<uint32_t>();
+    A.mgain = fused_gain_.as<double>();
+    A.desc = want ? fused_desc_.as<uint4>() : nullptr;
     A.records_out = records_out;
-    A.cap_records = records_out ? cap_records : 0;
+    A.cap_records = want ? cap_records : 0;
     A.group_info = group_info_out;
+    auto launch_class = [&](const ClassDef &d, const uint32_t *lst, uint32_t n, uint32_t *ticket, uint32_t *overflow_list) -> bool {
+        const Layout L = make_layout(d.n_cap, d.itv_cap, d.rec_cap, n_ch, tmpl_len, c.p.dt);
+        if (L.total > 227 * 1024) return false;
+        if (L.total > fused_smem_set_) {
+            WFS_CUDA_CHECK(cudaFuncSetAttribute(k_group_analyse, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+            fused_smem_set_ = L.total;
+        }
+        int ctas_per_sm = 1;
+        WFS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_group_analyse, d.threads, L.total));
+        if (ctas_per_sm < 1) return false;
+        FusedClass K;
+        K.n_cap = d.n_cap; K.itv_cap = d.itv_cap; K.rec_cap = d.rec_cap;
+        K.list = lst; K.n_list = n; K.ticket = ticket; K.overflow_list = overflow_list;
+        const int grid = (int)std::min<int64_t>(n, (int64_t)kNumSMs * ctas_per_sm);
+        k_group_analyse<<<grid, d.threads, L.total, stream_>>>(A, K);
+        lc_->n++;
+        return true;
+    };
+    auto records = [&]() {
+        if (!want) return;
+        prim_.exclusive_scan_u32(d_nrec, d_base, ng, true);
+        k_group_records<<<(unsigned)ng, kFusedRecordThreads, 0, stream_>>>(A);
+        lc_->n++;
+    };
+    auto read_scalars = [&]() {
+        WFS_CUDA_CHECK(cudaMemcpyAsync(h_scalars_, d_scal, sizeof(int64_t) * (FS_COUNT + 1), cudaMemcpyDeviceToHost, stream_));
+        WFS_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
+        WFS_CUDA_CHECK(stream_sync(stream_));
+        WFS_CUDA_CHECK(cudaGetLastError());
+    };
     WFS_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
-    const int grid = (int)std::min<int64_t>(ng, (int64_t)kNumSMs * ctas_per_sm);
-    k_group_fused<<<grid, threads, L.total, stream_>>>(A);
-    lc_->n++;
-    WFS_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
-    WFS_CUDA_CHECK(cudaMemcpyAsync(h_scalars_, A.scalars, sizeof(int64_t) * FS_COUNT, cudaMemcpyDeviceToHost, stream_));
-    WFS_CUDA_CHECK(stream_sync(stream_));
-    WFS_CUDA_CHECK(cudaGetLastError());
-    if (h_scalars_[FS_OVERFLOW]) return false;               // a group outgrew the shared-memory lists
+    for (int k = kFusedClasses - 1; k >= 0; k--)            // large groups first: the small ones fill the tail
+        if (cls_n[k] && !launch_class(defs[k], d_list + cls_off[k], cls_n[k], d_u32 + 1 + k, k + 1 < kFusedClasses ? d_over : nullptr))
+            return false;
+    records();        // records that do not fit the buffer are skipped by the kernel: no decision on the host in between
+    read_scalars();
+    const uint32_t n_over = reinterpret_cast<const uint32_t *>(h_scalars_ + FS_COUNT)[0];
+    if (n_over > 0 && !h_scalars_[FS_OVERFLOW] && !h_scalars_[FS_ERR]) {
+        // groups that outgrew the lists of their class: once more with the largest lists (their truth counters
+        // are untouched -- a group adds them only when it fits -- except the per-PMT areas), then all records again
+        if (b.pmt_areas) return false;
+        if (!launch_class(defs[kFusedClasses - 1], d_over, n_over, d_u32 + 1 + kFusedClasses, nullptr)) return false;
+        records();
+        read_scalars();
+    }
+    if (h_scalars_[FS_OVERFLOW]) return false;               // key range / lists of the largest class: multi-pass back end
     res = BackendResult();
     if (h_scalars_[FS_ERR]) { res.error = (int)h_scalars_[FS_ERR]; return true; }
     res.fused = 1;

@@ -4,28 +4,42 @@
 
 namespace wfs {
 
-constexpr int kFusedThreads = 256;
+constexpr int kFusedThreads = 512;
 constexpr int kFusedMaxPhotons = 8192;      // photons of one group (13 index bits in the key)
-constexpr int kFusedTile = 512;             // samples of a warp's tile: 4 records (440 samples) fit
-constexpr int kFusedRecCap = 4096;          // records of one group ordered in shared memory
-constexpr int kFusedItvCap = 2048;          // ZLE intervals of one group
+constexpr int kFusedMaxRecCap = 8192;       // records of one group ordered in shared memory (13 bits of record slot)
+constexpr int kFusedBins = 1024;            // time bins of the record order
+constexpr int kFusedTrigSlots = 64;         // (pulse call, total / bottom) trigger counters kept in shared memory
+
+constexpr int kFusedClasses = 4;            // groups are binned by photon count
+constexpr int kFusedRecordThreads = 128;
 
 enum FusedScalar { FS_NVALID = 0, FS_NPULSES, FS_NWIN, FS_NITV, FS_NSAMPLES, FS_NREC, FS_ERR, FS_OVERFLOW, FS_COUNT };
 
 struct FusedArgs {
     PhotonBatch b;
     DeviceConfig c;
-    int n_cap;                      // photon capacity of the shared-memory key array
     int relpc_bits;
     const int64_t *group_t0;        // [n_groups] lower bound of the photon times of the group [ns]
     const int32_t *group_run0;      // [n_groups] first Pulse call (run) of the group
-    uint64_t *status;               // [n_groups] look-back words, zeroed
-    uint32_t *ticket;               // group counter, zeroed
-    int64_t *scalars;               // [FS_COUNT], zeroed
-    uint32_t *group_nitv;           // unused (kept for layout stability)
+    int64_t *scalars;               // [FS_COUNT], zeroed; FS_NREC doubles as the bump allocator of the descriptor pool
+    uint32_t *over_count;           // groups that outgrew the lists of their class
+    uint32_t *group_nrec;           // [n_groups + 1] records of every group (zeroed)
+    uint32_t *group_desc;           // [n_groups] first descriptor of the group in the pool
+    const uint32_t *rec_base;       // [n_groups + 1] exclusive scan of group_nrec
+    uint32_t *tkey;                 // [photons] channel-ordered photons of every group: time | first-of-pulse bit
+    double *mgain;                  // [photons] merged gains
+    uint4 *desc;                    // [cap_records] record descriptors
     uint8_t *records_out;
     int64_t cap_records;
     wfs_group_info *group_info;
+};
+
+struct FusedClass {                 // one launch of k_group_analyse: the groups of one size class
+    int n_cap, itv_cap, rec_cap;    // photons / intervals / records of a group held in shared memory
+    const uint32_t *list;           // group ids
+    uint32_t n_list;
+    uint32_t *ticket;
+    uint32_t *overflow_list;        // nullptr: an overflow fails the batch (multi-pass back end)
 };
 
 }  // namespace wfs
