@@ -112,10 +112,11 @@ __device__ __forceinline__ int adc_of(double cur, double c2a) {
 __device__ __forceinline__ uint64_t pack_itv(uint32_t lb, uint32_t plen, uint32_t ch, uint32_t r0) {
     return ((uint64_t)lb << 43) | ((uint64_t)plen << 23) | ((uint64_t)ch << 13) | (uint64_t)r0;
 }
-// photon in HBM for the record kernel: sample << 4 | ns remainder, bit 24: first photon of a pulse
-constexpr uint32_t kTkeyPulseStart = 1u << 24;
-// record descriptor in HBM (uint4): x = left of the INTERVAL + bias (21) << 10 | channel; y = pulse length |
-// record_i (low 12 bits) << 20; z = first photon (13) | photons (14) << 13 | record_i >> 12 (2 bits) << 27
+// photon in HBM for the record kernel: sample << 4 | ns remainder, bits 27-31: samples it owns; their ADC values at
+// adc16[first photon of the group * template length + sample offset * photons of the group + photon]
+// record descriptor in HBM (uint4): x = first sample of the record + bias (21) << 10 | channel; y = pulse length |
+// record_i (low 12 bits) << 20; z = first photon that reaches the record (13) | photons (14) << 13 |
+// record_i >> 12 (2 bits) << 27
 
 // all-ascending bitonic network on items [0, n): every compare-exchange leaves the smaller item at the lower
 // index, so the virtual +inf padding behind n never moves and pairs that reach into it are skipped.
@@ -222,6 +223,8 @@ k_group_analyse(FusedArgs A, FusedClass K) {
             if (i < (int)r_n[2]) return r_lo[2] + i;
             return r_lo[3] + (i - r_n[2]);
         };
+        // ADC values of the samples every photon owns, sample-major over the photons of the group (coalesced)
+        uint16_t *adc_out = A.adc16 + (size_t)pbase * tlen;
         if (n_g > K.n_cap) {                           // (the host bins the groups: cannot happen)
             if (tid == 0) A.scalars[FS_OVERFLOW] = 2;
             continue;
@@ -379,7 +382,9 @@ k_group_analyse(FusedArgs A, FusedClass K) {
                 const int thr = c.zle_thr[ch];
                 int f0 = kNoFlag, f1 = 0;
                 for (int j = 0; j < tlen; j++) {
-                    if (max(adc_of(__dmul_rn(tm[j], gn), c2a) + baseline, 0) < thr) {
+                    const int v = max(adc_of(__dmul_rn(tm[j], gn), c2a) + baseline, 0);
+                    adc_out[(size_t)j * n_g + k] = (uint16_t)(int16_t)v;
+                    if (v < thr) {
                         if (f0 == kNoFlag) f0 = j;
                         f1 = j;
                     }
@@ -417,7 +422,9 @@ k_group_analyse(FusedArgs A, FusedClass K) {
                         const uint64_t kj = s_keys[j];
                         acc = __dadd_rn(acc, __dmul_rn(s_tmpl[key_rem(kj) * tlen + (s - key_sample(kj))], s_gain[j]));
                     }
-                    if (max(adc_of(acc, c2a) + baseline, 0) < thr) {
+                    const int v = max(adc_of(acc, c2a) + baseline, 0);
+                    adc_out[(size_t)(s - T) * n_g + k] = (uint16_t)(int16_t)v;
+                    if (v < thr) {
                         if (f0 == kNoFlag) f0 = s - T;
                         f1 = s - T;
                     }
@@ -436,7 +443,9 @@ k_group_analyse(FusedArgs A, FusedClass K) {
                         acc = __dadd_rn(acc, __dmul_rn(s_tmpl[key_rem(kj) * tlen + (int)d], s_gain[j]));
                     }
                     adc += adc_of(acc, c2a);
-                    if (max(adc + baseline, 0) < thr) {
+                    const int v = max(adc + baseline, 0);
+                    adc_out[(size_t)(s - T) * n_g + k] = (uint16_t)(int16_t)v;
+                    if (v < thr) {
                         if (f0 == kNoFlag) f0 = s - T;
                         f1 = s - T;
                     }
@@ -661,11 +670,18 @@ k_group_analyse(FusedArgs A, FusedClass K) {
         if (smem_trig && b.trig_dpe_out)
             for (int i = tid; i < (2 << A.relpc_bits); i += blockDim.x)
                 if (S.trig[i]) atomicAdd(&b.trig_dpe_out[2 * (2 * run0) + i], S.trig[i]);
-        // the photons in channel order for the record kernel
+        // the photons in channel order for the record kernel; bits 27-31: samples the photon owns
         for (int k = tid; k < n_valid; k += blockDim.x) {
             const uint64_t key = s_keys[k];
-            A.tkey[pbase + k] = (uint32_t)((key >> kShiftRem) & 0xffffffu) | (key_pulse_start(key) ? kTkeyPulseStart : 0u);
-            A.mgain[pbase + k] = s_gain[k];
+            int n_own = 0;
+            if (!key_follower(key)) {
+                const int e = s_cstart[(int)(key >> shift_ch) + 1], T = key_sample(key);
+                int kn = k + 1;
+                while (kn < e && key_follower(s_keys[kn])) kn++;
+                const int Tn = (kn < e && !key_pulse_start(s_keys[kn])) ? key_sample(s_keys[kn]) : INT_MAX;
+                n_own = min(T + tlen, Tn) - T;
+            }
+            A.tkey[pbase + k] = (uint32_t)((key >> kShiftRem) & 0xffffffu) | ((uint32_t)n_own << 27);
         }
         if (S.max_bin <= 24) {
             // counting sort over the time bins, then every bin ordered by (time, channel) by one thread
@@ -740,7 +756,7 @@ k_group_analyse(FusedArgs A, FusedClass K) {
                         while (kb < e && key_sample(s_keys[kb]) < first + length) kb++;
                     } else { ka = a; kb = e; }
                     uint4 d;
-                    d.x = (lb << 10) | (uint32_t)ch;
+                    d.x = ((lb + (uint32_t)(r * WFS_SAMPLES_PER_RECORD)) << 10) | (uint32_t)ch;
                     d.y = (uint32_t)plen | ((uint32_t)(r & 0xfff) << 20);
                     d.z = (kb > ka ? (uint32_t)ka : 0u) | ((uint32_t)(kb - ka) << 13) | ((uint32_t)(r >> 12) << 27);
                     d.w = 0;
@@ -770,115 +786,126 @@ k_group_analyse(FusedArgs A, FusedClass K) {
     }
 }
 
-// One warp per record, lane = record word.  The record's descriptor names the photons (channel order, merged
-// gains) that can reach it; every sample is summed over them in the order of Pulse.add_current, rounded once
-// per pulse (rawdata.py:236-239), and the 244-byte record is written at rec_base[group] + rank.
+// Records of a group, a tile of consecutive records at a time, assembled in shared memory and streamed out with
+// aligned 16-byte stores: baseline fill, then headers, zero padding behind the pulse, and -- one thread per
+// (record, photon that reaches it) -- the ADC values of the samples that photon owns inside the record, as
+// k_group_analyse left them.  No arithmetic on samples here: the kernel is a gather.
+constexpr int kTileRecs = 64, kTileWords = kTileRecs * 61 + 8;
+
 __global__ void __launch_bounds__(kFusedRecordThreads)
 k_group_records(FusedArgs A) {
-    __shared__ double s_tmpl[16 * 32];
+    __shared__ __align__(16) uint32_t s_tile[kTileWords];
+    __shared__ uint4 s_desc[kTileRecs];
+    __shared__ int s_pref[kTileRecs + 1];
     const PhotonBatch &b = A.b;
     const DeviceConfig &c = A.c;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
     const int dt = c.p.dt, tlen = c.p.template_length;
-    for (int i = threadIdx.x; i < dt * tlen; i += blockDim.x) s_tmpl[i] = c.templates[i];
-    __syncthreads();
-    const double c2a = c.p.current_2_adc;
     const int baseline = c.p.baseline;
     const int key_bias = c.p.pulse_left_margin + c.p.trigger_window + 2;
-    const uint32_t fill = (uint32_t)(uint16_t)(int16_t)max(baseline, 0);
-    // record word `lane` holds header words 0..5 or samples 2(lane-6), 2(lane-6)+1; word lane+32 samples 2(lane+26), +1
-    const int sa = 2 * (lane - 6), sb = 2 * (lane + 26);
+    const uint32_t fill = (uint32_t)(uint16_t)(int16_t)max(baseline, 0), fill2 = fill | (fill << 16);
+    constexpr int SPR = WFS_SAMPLES_PER_RECORD;
+    uint16_t *s_tile16 = reinterpret_cast<uint16_t *>(s_tile);
     for (int g = blockIdx.x; g < (int)b.n_groups; g += gridDim.x) {
         const uint32_t n_rec = A.group_nrec[g], desc_off = A.group_desc[g];
         if (n_rec == 0 || desc_off == 0xffffffffu) continue;
         const int64_t rec_base = (int64_t)A.rec_base[g];
         const int64_t origin_q = floordiv64(A.group_t0[g], dt);
-        uint32_t pbase = 0;
+        uint32_t pbase = 0, n_g = 0;
         for (int r = 0; r < b.group_ranges; r++) {
             const uint32_t *gs = b.group_start + (size_t)r * (b.n_groups + 1);
             pbase += gs[g] - gs[0];
+            n_g += gs[g + 1] - gs[g];
         }
         const uint32_t *tkey = A.tkey + pbase;
-        const double *mgain = A.mgain + pbase;
-        for (uint32_t rank = warp; rank < n_rec; rank += n_warps) {
-            const int64_t dest = rec_base + rank;
-            if (dest >= A.cap_records) continue;
-            const uint4 d = A.desc[(size_t)desc_off + rank];
-            const int ch = (int)(d.x & 1023u), plen = (int)(d.y & 0xfffffu);
-            const int rec_i = (int)((d.y >> 20) | ((d.z >> 27) << 12));
-            const int ka = (int)(d.z & 8191u), nk = (int)((d.z >> 13) & 16383u);
-            const int first = (int)(d.x >> 10) - key_bias + rec_i * WFS_SAMPLES_PER_RECORD;     // relative to origin_q
-            const int length = min(plen - rec_i * WFS_SAMPLES_PER_RECORD, WFS_SAMPLES_PER_RECORD);
-            int adc0 = 0, adc1 = 0, adc2 = 0, adc3 = 0;
-            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-            bool any = false;
-            for (int k0 = 0; k0 < nk; k0 += 32) {
-                const int kk = k0 + lane;
-                const uint32_t tk = kk < nk ? tkey[ka + kk] : 0u;
-                const double gk = kk < nk ? mgain[ka + kk] : 0.0;
-                const int Tk = (int)((tk >> 4) & 0xfffffu) - first;
-                unsigned m = __ballot_sync(0xffffffffu, kk < nk && Tk + tlen > 0 && Tk < length);
-                // a pulse that starts among the photons skipped in front still separates the roundings
-                unsigned starts = __ballot_sync(0xffffffffu, kk < nk && (tk & kTkeyPulseStart));
-                unsigned seen = 0;
-                while (m) {
-                    const int bit = __ffs(m) - 1;
-                    m &= m - 1;
-                    const uint32_t tb = __shfl_sync(0xffffffffu, tk, bit);
-                    const double gb = __shfl_sync(0xffffffffu, gk, bit);
-                    const unsigned upto = bit == 31 ? 0xffffffffu : ((2u << bit) - 1u);
-                    if (any && (starts & upto & ~seen)) {          // next pulse call: one rounding per pulse and sample
-                        adc0 += adc_of(acc0, c2a); adc1 += adc_of(acc1, c2a);
-                        adc2 += adc_of(acc2, c2a); adc3 += adc_of(acc3, c2a);
-                        acc0 = acc1 = acc2 = acc3 = 0.0;
-                    }
-                    seen = upto;
-                    any = true;
-                    const int Tb = (int)((tb >> 4) & 0xfffffu) - first;
-                    const double *tm = s_tmpl + (int)(tb & 15u) * tlen;
-                    if (Tb < 52) {                              // samples of words 0..31
-                        const unsigned d0 = (unsigned)(sa - Tb), d1 = (unsigned)(sa + 1 - Tb);
-                        if (lane >= 6 && d0 < (unsigned)tlen) acc0 = __dadd_rn(acc0, __dmul_rn(tm[d0], gb));
-                        if (lane >= 6 && d1 < (unsigned)tlen) acc1 = __dadd_rn(acc1, __dmul_rn(tm[d1], gb));
-                    }
-                    if (Tb + tlen > 52) {                       // samples of words 32..60
-                        const unsigned d2 = (unsigned)(sb - Tb), d3 = (unsigned)(sb + 1 - Tb);
-                        if (d2 < (unsigned)tlen) acc2 = __dadd_rn(acc2, __dmul_rn(tm[d2], gb));
-                        if (d3 < (unsigned)tlen) acc3 = __dadd_rn(acc3, __dmul_rn(tm[d3], gb));
-                    }
-                }
-                // pulses that start behind the last photon taken from this chunk
-                if (any && (starts & ~seen)) {
-                    adc0 += adc_of(acc0, c2a); adc1 += adc_of(acc1, c2a);
-                    adc2 += adc_of(acc2, c2a); adc3 += adc_of(acc3, c2a);
-                    acc0 = acc1 = acc2 = acc3 = 0.0;
-                }
+        const uint16_t *adc = A.adc16 + (size_t)pbase * tlen;
+        for (uint32_t t0 = blockIdx.y * kTileRecs; t0 < n_rec; t0 += gridDim.y * kTileRecs) {
+            const int64_t dest0 = rec_base + t0;
+            const int nr = (int)min((int64_t)min(n_rec - t0, (uint32_t)kTileRecs), A.cap_records - dest0);
+            if (nr <= 0) break;
+            const int hw = (int)(((uint64_t)dest0 * WFS_RECORD_BYTES) & 15u) >> 2;      // words in front of the tile in its first 16-byte vector
+            const int n_words = nr * 61, n_vec = (hw + n_words + 3) >> 2;
+            __syncthreads();                              // the previous tile has left
+            if (tid < nr) s_desc[tid] = A.desc[(size_t)desc_off + t0 + tid];
+            {
+                uint4 *v = reinterpret_cast<uint4 *>(s_tile);
+                const uint4 f4 = make_uint4(fill2, fill2, fill2, fill2);
+                for (int i = tid; i < n_vec; i += nthr) v[i] = f4;
             }
-            uint32_t w0, w1;
-            if (any) {
-                adc0 += adc_of(acc0, c2a); adc1 += adc_of(acc1, c2a);
-                adc2 += adc_of(acc2, c2a); adc3 += adc_of(acc3, c2a);
-                const uint32_t v0 = sa < length ? (uint32_t)(uint16_t)(int16_t)max(adc0 + baseline, 0) : 0u;
-                const uint32_t v1 = sa + 1 < length ? (uint32_t)(uint16_t)(int16_t)max(adc1 + baseline, 0) : 0u;
-                const uint32_t v2 = sb < length ? (uint32_t)(uint16_t)(int16_t)max(adc2 + baseline, 0) : 0u;
-                const uint32_t v3 = sb + 1 < length ? (uint32_t)(uint16_t)(int16_t)max(adc3 + baseline, 0) : 0u;
-                w0 = v0 | (v1 << 16);
-                w1 = v2 | (v3 << 16);
-            } else {
-                w0 = (sa < length ? fill : 0u) | (sa + 1 < length ? fill << 16 : 0u);
-                w1 = (sb < length ? fill : 0u) | (sb + 1 < length ? fill << 16 : 0u);
+            __syncthreads();
+            // photons that reach every record: prefix over the tile (warp 0); headers and zero padding (the others)
+            if (warp == 0) {
+                const int n0 = lane < nr ? (int)((s_desc[lane].z >> 13) & 16383u) : 0;
+                const int n1 = lane + 32 < nr ? (int)((s_desc[lane + 32].z >> 13) & 16383u) : 0;
+                int i0 = n0, i1 = n1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u0 = __shfl_up_sync(0xffffffffu, i0, o), u1 = __shfl_up_sync(0xffffffffu, i1, o);
+                    if (lane >= o) { i0 += u0; i1 += u1; }
+                }
+                const int tot0 = __shfl_sync(0xffffffffu, i0, 31);
+                s_pref[lane] = i0 - n0;
+                s_pref[lane + 32] = tot0 + i1 - n1;
+                if (lane == 31) s_pref[64] = tot0 + i1;
             }
-            // strax_interface.py:425-436: time, length, dt, channel, pulse_length, record_i, baseline = 0
-            const int64_t time = (int64_t)dt * (origin_q + first);
-            uint32_t h = (uint32_t)(uint64_t)time;
-            h = lane == 1 ? (uint32_t)((uint64_t)time >> 32) : h;
-            h = lane == 2 ? (uint32_t)length : h;
-            h = lane == 3 ? (((uint32_t)(uint16_t)dt) | ((uint32_t)(uint16_t)ch << 16)) : h;
-            h = lane == 4 ? (uint32_t)plen : h;
-            h = lane == 5 ? (uint32_t)(uint16_t)rec_i : h;
-            uint32_t *out = reinterpret_cast<uint32_t *>(A.records_out + dest * WFS_RECORD_BYTES);
-            out[lane] = lane < 6 ? h : w0;
-            if (lane + 32 < 61) out[lane + 32] = w1;
+            for (int i = tid; i < 6 * nr; i += nthr) {
+                // strax_interface.py:425-436: time, length, dt, channel, pulse_length, record_i, baseline = 0
+                const int r = i / 6, f = i - 6 * r;
+                const uint4 d = s_desc[r];
+                const int ch = (int)(d.x & 1023u), plen = (int)(d.y & 0xfffffu);
+                const int rec_i = (int)(((d.y >> 20) & 0xfffu) | (((d.z >> 27) & 3u) << 12));
+                const int64_t time = (int64_t)dt * (origin_q + (int)(d.x >> 10) - key_bias);
+                const int length = min(plen - rec_i * SPR, SPR);
+                uint32_t h = (uint32_t)(uint64_t)time;
+                h = f == 1 ? (uint32_t)((uint64_t)time >> 32) : h;
+                h = f == 2 ? (uint32_t)length : h;
+                h = f == 3 ? (((uint32_t)(uint16_t)dt) | ((uint32_t)(uint16_t)ch << 16)) : h;
+                h = f == 4 ? (uint32_t)plen : h;
+                h = f == 5 ? (uint32_t)(uint16_t)rec_i : h;
+                s_tile[hw + r * 61 + f] = h;
+            }
+            for (int r = tid; r < nr; r += nthr) {          // zeros behind `length` (the last record of a pulse)
+                const uint4 d = s_desc[r];
+                const int plen = (int)(d.y & 0xfffffu);
+                const int rec_i = (int)(((d.y >> 20) & 0xfffu) | (((d.z >> 27) & 3u) << 12));
+                const int length = plen - rec_i * SPR;
+                uint16_t *p = s_tile16 + 2 * (hw + r * 61 + 6);
+                for (int sidx = length; sidx < SPR; sidx++) p[sidx] = 0;
+            }
+            __syncthreads();
+            const int n_pairs = s_pref[nr];
+            for (int q = tid; q < n_pairs; q += nthr) {
+                int r = 0;                                  // the record of pair q: last r with s_pref[r] <= q
+#pragma unroll
+                for (int o = 32; o > 0; o >>= 1)
+                    if (r + o < nr && s_pref[r + o] <= q) r += o;
+                const uint4 d = s_desc[r];
+                const int ka = (int)(d.z & 8191u), kend = ka + (int)((d.z >> 13) & 16383u);
+                const int k = ka + (q - s_pref[r]);
+                const uint32_t tk = __ldg(tkey + k);
+                const int n_own = (int)(tk >> 27);
+                if (n_own == 0) continue;                   // its gain went to the first photon of the same ns
+                const int plen = (int)(d.y & 0xfffffu);
+                const int rec_i = (int)(((d.y >> 20) & 0xfffu) | (((d.z >> 27) & 3u) << 12));
+                const int first = (int)(d.x >> 10) - key_bias;              // relative to origin_q
+                const int length = min(plen - rec_i * SPR, SPR);
+                const int T = (int)((tk >> 4) & 0xfffffu);
+                uint16_t *rec16 = s_tile16 + 2 * (hw + r * 61 + 6);
+                const int j0 = max(0, first - T), j1 = min(n_own, first + length - T);
+                for (int j = j0; j < j1; j++) rec16[T + j - first] = __ldg(adc + (size_t)j * n_g + k);
+            }
+            __syncthreads();
+            // whole 16-byte vectors to their final place, single words at the ragged ends
+            {
+                uint32_t *out_w = reinterpret_cast<uint32_t *>(A.records_out) + dest0 * 61 - hw;      // word 0 of the tile's first vector
+                const int v0 = hw ? 1 : 0, v1 = (hw + n_words) >> 2;
+                const uint4 *sv = reinterpret_cast<const uint4 *>(s_tile);
+                uint4 *ov = reinterpret_cast<uint4 *>(out_w);
+                for (int i = v0 + tid; i < v1; i += nthr) ov[i] = sv[i];
+                if (hw && tid >= hw && tid < 4 && tid < hw + n_words) out_w[tid] = s_tile[tid];
+                const int wt = tid + 4 * v1;
+                if (v1 >= v0 && tid < 4 && wt < hw + n_words && wt >= hw) out_w[wt] = s_tile[wt];
+            }
         }
     }
 }
@@ -940,7 +967,7 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
     int64_t *d_scal = fused_scal_.as<int64_t>();
     uint32_t *d_u32 = reinterpret_cast<uint32_t *>(d_scal + FS_COUNT);        // [0] overflow count, [1..] tickets
     fused_tkey_.reserve(sizeof(uint32_t) * (size_t)std::max<int64_t>(b.n, 1));
-    fused_gain_.reserve(sizeof(double) * (size_t)std::max<int64_t>(b.n, 1));
+    fused_gain_.reserve(sizeof(uint16_t) * (size_t)c.p.template_length * (size_t)std::max<int64_t>(b.n, 1));
     const bool want = records_out != nullptr && cap_records > 0;
     if (want) fused_desc_.reserve(sizeof(uint4) * (size_t)cap_records);
     WFS_CUDA_CHECK(cudaMemcpyAsync(d_list, list.data(), sizeof(uint32_t) * (size_t)ng, cudaMemcpyHostToDevice, stream_));
@@ -958,7 +985,7 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
     A.group_desc = d_desc_off;
     A.rec_base = d_base;
     A.tkey = fused_tkey_.as<uint32_t>();
-    A.mgain = fused_gain_.as<double>();
+    A.adc16 = fused_gain_.as<uint16_t>();
     A.desc = want ? fused_desc_.as<uint4>() : nullptr;
     A.records_out = records_out;
     A.cap_records = want ? cap_records : 0;
@@ -966,9 +993,10 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
     auto launch_class = [&](const ClassDef &d, const uint32_t *lst, uint32_t n, uint32_t *ticket, uint32_t *overflow_list) -> bool {
         const Layout L = make_layout(d.n_cap, d.itv_cap, d.rec_cap, n_ch, tmpl_len, c.p.dt);
         if (L.total > 227 * 1024) return false;
-        if (L.total > fused_smem_set_) {
-            WFS_CUDA_CHECK(cudaFuncSetAttribute(k_group_analyse, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-            fused_smem_set_ = L.total;
+        if (!fused_smem_set_) {
+            // the attribute belongs to the function, not to this back end: every lane sets the same (largest) value
+            WFS_CUDA_CHECK(cudaFuncSetAttribute(k_group_analyse, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            fused_smem_set_ = 227 * 1024;
         }
         int ctas_per_sm = 1;
         WFS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_group_analyse, d.threads, L.total));
@@ -984,7 +1012,7 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
     auto records = [&]() {
         if (!want) return;
         prim_.exclusive_scan_u32(d_nrec, d_base, ng, true);
-        k_group_records<<<(unsigned)ng, kFusedRecordThreads, 0, stream_>>>(A);
+        k_group_records<<<dim3((unsigned)ng, 4), kFusedRecordThreads, 0, stream_>>>(A);
         lc_->n++;
     };
     auto read_scalars = [&]() {
@@ -1008,7 +1036,11 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
         records();
         read_scalars();
     }
-    if (h_scalars_[FS_OVERFLOW]) return false;               // key range / lists of the largest class: multi-pass back end
+    if (h_scalars_[FS_OVERFLOW]) {                           // key range / lists of the largest class: multi-pass back end
+        if (getenv("WFS_DEBUG_SEG")) fprintf(stderr, "[wfs] fused back end gives up: overflow code %lld, %u groups retried\n",
+                                             (long long)h_scalars_[FS_OVERFLOW], n_over);
+        return false;
+    }
     res = BackendResult();
     if (h_scalars_[FS_ERR]) { res.error = (int)h_scalars_[FS_ERR]; return true; }
     res.fused = 1;
