@@ -113,10 +113,32 @@ __device__ __forceinline__ uint64_t pack_itv(uint32_t lb, uint32_t plen, uint32_
     return ((uint64_t)lb << 43) | ((uint64_t)plen << 23) | ((uint64_t)ch << 13) | (uint64_t)r0;
 }
 // photon in HBM for the record kernel: sample << 4 | ns remainder, bits 27-31: samples it owns; their ADC values at
-// adc16[first photon of the group * template length + sample offset * photons of the group + photon]
+// adc_slots[(first photon of the group + photon) * kSlotVecs]
 // record descriptor in HBM (uint4): x = first sample of the record + bias (21) << 10 | channel; y = pulse length |
 // record_i (low 12 bits) << 20; z = first photon that reaches the record (13) | photons (14) << 13 |
 // record_i >> 12 (2 bits) << 27
+
+
+// ADC values of the samples a photon owns: a slot of kSlotVecs 16-byte vectors per photon, filled through four
+// registers (sample j -> half (j & 1) of word (j >> 1) & 3 of vector j >> 3)
+constexpr int kSlotVecs = 4;                    // 32 samples: template_length <= 30
+struct SlotWriter {
+    uint4 *slot;
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+    __device__ __forceinline__ void put(int j, int v) {
+        const uint32_t hv = (uint32_t)(uint16_t)(int16_t)v << (16 * (j & 1));
+        const int wi = (j >> 1) & 3;
+        w0 |= wi == 0 ? hv : 0u; w1 |= wi == 1 ? hv : 0u; w2 |= wi == 2 ? hv : 0u; w3 |= wi == 3 ? hv : 0u;
+        if ((j & 7) == 7) flush(j);
+    }
+    __device__ __forceinline__ void flush(int j) {      // j: the last sample put
+        slot[j >> 3] = make_uint4(w0, w1, w2, w3);
+        w0 = w1 = w2 = w3 = 0;
+    }
+    __device__ __forceinline__ void finish(int n) {     // n samples were put
+        if (n > 0 && (n & 7) != 0) flush(n - 1);
+    }
+};
 
 // all-ascending bitonic network on items [0, n): every compare-exchange leaves the smaller item at the lower
 // index, so the virtual +inf padding behind n never moves and pairs that reach into it are skipped.
@@ -223,8 +245,8 @@ k_group_analyse(FusedArgs A, FusedClass K) {
             if (i < (int)r_n[2]) return r_lo[2] + i;
             return r_lo[3] + (i - r_n[2]);
         };
-        // ADC values of the samples every photon owns, sample-major over the photons of the group (coalesced)
-        uint16_t *adc_out = A.adc16 + (size_t)pbase * tlen;
+        // ADC values of the samples every photon owns
+        uint4 *adc_out = A.adc_slots + (size_t)pbase * kSlotVecs;
         if (n_g > K.n_cap) {                           // (the host bins the groups: cannot happen)
             if (tid == 0) A.scalars[FS_OVERFLOW] = 2;
             continue;
@@ -381,14 +403,16 @@ k_group_analyse(FusedArgs A, FusedClass K) {
                 const double *tm = s_tmpl + key_rem(key) * tlen;
                 const int thr = c.zle_thr[ch];
                 int f0 = kNoFlag, f1 = 0;
+                SlotWriter sw{adc_out + (size_t)k * kSlotVecs};
                 for (int j = 0; j < tlen; j++) {
                     const int v = max(adc_of(__dmul_rn(tm[j], gn), c2a) + baseline, 0);
-                    adc_out[(size_t)j * n_g + k] = (uint16_t)(int16_t)v;
+                    sw.put(j, v);
                     if (v < thr) {
                         if (f0 == kNoFlag) f0 = j;
                         f1 = j;
                     }
                 }
+                sw.finish(tlen);
                 if (f0 != kNoFlag)
                     s_keys[k] = (key & ~((uint64_t)0x3ff << 3)) | ((uint64_t)f0 << 3) | ((uint64_t)f1 << 8);
             }
@@ -412,6 +436,7 @@ k_group_analyse(FusedArgs A, FusedClass K) {
             const int Tn = (kn < e && (s_keys[kn] >> shift_pc) == pck) ? key_sample(s_keys[kn]) : INT_MAX;
             const int s_end = min(T + tlen, Tn);           // owned samples [T, s_end)
             int f0 = kNoFlag, f1 = 0;
+            SlotWriter sw{adc_out + (size_t)k * kSlotVecs};
             if (single) {
                 int klo = k;
                 while (klo > a && key_sample(s_keys[klo - 1]) > T - tlen) klo--;
@@ -423,7 +448,7 @@ k_group_analyse(FusedArgs A, FusedClass K) {
                         acc = __dadd_rn(acc, __dmul_rn(s_tmpl[key_rem(kj) * tlen + (s - key_sample(kj))], s_gain[j]));
                     }
                     const int v = max(adc_of(acc, c2a) + baseline, 0);
-                    adc_out[(size_t)(s - T) * n_g + k] = (uint16_t)(int16_t)v;
+                    sw.put(s - T, v);
                     if (v < thr) {
                         if (f0 == kNoFlag) f0 = s - T;
                         f1 = s - T;
@@ -444,13 +469,14 @@ k_group_analyse(FusedArgs A, FusedClass K) {
                     }
                     adc += adc_of(acc, c2a);
                     const int v = max(adc + baseline, 0);
-                    adc_out[(size_t)(s - T) * n_g + k] = (uint16_t)(int16_t)v;
+                    sw.put(s - T, v);
                     if (v < thr) {
                         if (f0 == kNoFlag) f0 = s - T;
                         f1 = s - T;
                     }
                 }
             }
+            sw.finish(max(s_end - T, 0));
             if (f0 != kNoFlag)
                 s_keys[k] = (key & ~((uint64_t)0x3ff << 3)) | ((uint64_t)f0 << 3) | ((uint64_t)f1 << 8);
         }
@@ -818,7 +844,7 @@ k_group_records(FusedArgs A) {
             n_g += gs[g + 1] - gs[g];
         }
         const uint32_t *tkey = A.tkey + pbase;
-        const uint16_t *adc = A.adc16 + (size_t)pbase * tlen;
+        const uint4 *adc = A.adc_slots + (size_t)pbase * kSlotVecs;
         for (uint32_t t0 = blockIdx.y * kTileRecs; t0 < n_rec; t0 += gridDim.y * kTileRecs) {
             const int64_t dest0 = rec_base + t0;
             const int nr = (int)min((int64_t)min(n_rec - t0, (uint32_t)kTileRecs), A.cap_records - dest0);
@@ -892,7 +918,18 @@ k_group_records(FusedArgs A) {
                 const int T = (int)((tk >> 4) & 0xfffffu);
                 uint16_t *rec16 = s_tile16 + 2 * (hw + r * 61 + 6);
                 const int j0 = max(0, first - T), j1 = min(n_own, first + length - T);
-                for (int j = j0; j < j1; j++) rec16[T + j - first] = __ldg(adc + (size_t)j * n_g + k);
+                if (j0 >= j1) continue;
+                uint16_t *dst = rec16 + (T - first);
+                const uint4 *slot = adc + (size_t)k * kSlotVecs;
+                for (int v = j0 >> 3; v <= (j1 - 1) >> 3; v++) {
+                    const uint4 q4 = __ldg(slot + v);
+                    const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int j = 8 * v + u;
+                        if (j >= j0 && j < j1) dst[j] = (uint16_t)(w[u >> 1] >> (16 * (u & 1)));
+                    }
+                }
             }
             __syncthreads();
             // whole 16-byte vectors to their final place, single words at the ragged ends
@@ -967,7 +1004,7 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
     int64_t *d_scal = fused_scal_.as<int64_t>();
     uint32_t *d_u32 = reinterpret_cast<uint32_t *>(d_scal + FS_COUNT);        // [0] overflow count, [1..] tickets
     fused_tkey_.reserve(sizeof(uint32_t) * (size_t)std::max<int64_t>(b.n, 1));
-    fused_gain_.reserve(sizeof(uint16_t) * (size_t)c.p.template_length * (size_t)std::max<int64_t>(b.n, 1));
+    fused_gain_.reserve(sizeof(uint4) * kSlotVecs * (size_t)std::max<int64_t>(b.n, 1));
     const bool want = records_out != nullptr && cap_records > 0;
     if (want) fused_desc_.reserve(sizeof(uint4) * (size_t)cap_records);
     WFS_CUDA_CHECK(cudaMemcpyAsync(d_list, list.data(), sizeof(uint32_t) * (size_t)ng, cudaMemcpyHostToDevice, stream_));
@@ -985,7 +1022,7 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
     A.group_desc = d_desc_off;
     A.rec_base = d_base;
     A.tkey = fused_tkey_.as<uint32_t>();
-    A.adc16 = fused_gain_.as<uint16_t>();
+    A.adc_slots = fused_gain_.as<uint4>();
     A.desc = want ? fused_desc_.as<uint4>() : nullptr;
     A.records_out = records_out;
     A.cap_records = want ? cap_records : 0;

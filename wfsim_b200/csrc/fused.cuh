@@ -27,7 +27,7 @@ struct FusedArgs {
     uint32_t *group_desc;           // [n_groups] first descriptor of the group in the pool
     const uint32_t *rec_base;       // [n_groups + 1] exclusive scan of group_nrec
     uint32_t *tkey;                 // [photons] channel-ordered photons of every group: time | samples owned
-    uint16_t *adc16;                // [photons x template length] ADC values of the owned samples, sample-major per group
+    uint4 *adc_slots;               // [photons x 4] ADC values of the samples every photon owns (64-byte slot per photon)
     uint4 *desc;                    // [cap_records] record descriptors
     uint8_t *records_out;
     int64_t cap_records;
