@@ -970,12 +970,11 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
     const int n_ch = c.p.n_tpc_pmts, tmpl_len = c.p.dt * c.p.template_length;
     // groups by photon count: small groups get small shared-memory lists and many CTAs per SM
     struct ClassDef { int n_cap, itv_cap, rec_cap, threads; };
-    ClassDef defs[kFusedClasses] = {{512, 512, 1024, 128}, {2048, 1024, 3072, 256}, {4096, 2048, 6144, 512},
-                                    {kFusedMaxPhotons, 4096, kFusedMaxRecCap, 512}};
+    ClassDef defs[kFusedClasses] = {{512, 512, 1024, 128}, {2048, 1024, 3072, 256}, {kFusedMaxPhotons, 4096, kFusedMaxRecCap, 512}};
     if (const char *e = getenv("WFS_FUSED_REC_CAP"))          // tests: small lists, so that groups take the second attempt
         for (int k = 0; k + 1 < kFusedClasses; k++) defs[k].rec_cap = std::max(32, std::min(defs[k].rec_cap, atoi(e)));
     std::vector<uint32_t> list((size_t)ng);
-    uint32_t cls_n[kFusedClasses] = {0, 0, 0, 0}, cls_off[kFusedClasses + 1];
+    uint32_t cls_n[kFusedClasses] = {}, cls_off[kFusedClasses + 1];
     std::vector<uint8_t> cls_of((size_t)ng);
     for (int64_t g = 0; g < ng; g++) {
         int64_t n = 0;
@@ -1000,7 +999,7 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
     fused_lists_.reserve(sizeof(uint32_t) * (size_t)(5 * ng + 8));
     uint32_t *d_list = fused_lists_.as<uint32_t>(), *d_over = d_list + ng, *d_nrec = d_over + ng,
              *d_base = d_nrec + ng + 1, *d_desc_off = d_base + ng + 1;
-    fused_scal_.reserve(sizeof(int64_t) * (FS_COUNT + 8));
+    fused_scal_.reserve(sizeof(int64_t) * (FS_COUNT + 8));       // + overflow count and one ticket per launch
     int64_t *d_scal = fused_scal_.as<int64_t>();
     uint32_t *d_u32 = reinterpret_cast<uint32_t *>(d_scal + FS_COUNT);        // [0] overflow count, [1..] tickets
     fused_tkey_.reserve(sizeof(uint32_t) * (size_t)std::max<int64_t>(b.n, 1));
@@ -1027,7 +1026,8 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
     A.records_out = records_out;
     A.cap_records = want ? cap_records : 0;
     A.group_info = group_info_out;
-    auto launch_class = [&](const ClassDef &d, const uint32_t *lst, uint32_t n, uint32_t *ticket, uint32_t *overflow_list) -> bool {
+    auto launch_class = [&](const ClassDef &d, const uint32_t *lst, uint32_t n, uint32_t *ticket, uint32_t *overflow_list,
+                            cudaStream_t st) -> bool {
         const Layout L = make_layout(d.n_cap, d.itv_cap, d.rec_cap, n_ch, tmpl_len, c.p.dt);
         if (L.total > 227 * 1024) return false;
         if (!fused_smem_set_) {
@@ -1042,7 +1042,7 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
         K.n_cap = d.n_cap; K.itv_cap = d.itv_cap; K.rec_cap = d.rec_cap;
         K.list = lst; K.n_list = n; K.ticket = ticket; K.overflow_list = overflow_list;
         const int grid = (int)std::min<int64_t>(n, (int64_t)kNumSMs * ctas_per_sm);
-        k_group_analyse<<<grid, d.threads, L.total, stream_>>>(A, K);
+        k_group_analyse<<<grid, d.threads, L.total, st>>>(A, K);
         lc_->n++;
         return true;
     };
@@ -1059,9 +1059,19 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
         WFS_CUDA_CHECK(cudaGetLastError());
     };
     WFS_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
-    for (int k = kFusedClasses - 1; k >= 0; k--)            // large groups first: the small ones fill the tail
-        if (cls_n[k] && !launch_class(defs[k], d_list + cls_off[k], cls_n[k], d_u32 + 1 + k, k + 1 < kFusedClasses ? d_over : nullptr))
+    // the classes run side by side (one stream each): the small groups fill the tail of the large ones
+    WFS_CUDA_CHECK(cudaEventRecord(ev_fork_, stream_));
+    for (int k = kFusedClasses - 1; k >= 0; k--) {
+        if (!cls_n[k]) continue;
+        cudaStream_t st = k == kFusedClasses - 1 ? stream_ : aux_[k];
+        if (st != stream_) WFS_CUDA_CHECK(cudaStreamWaitEvent(st, ev_fork_, 0));
+        if (!launch_class(defs[k], d_list + cls_off[k], cls_n[k], d_u32 + 1 + k, k + 1 < kFusedClasses ? d_over : nullptr, st))
             return false;
+        if (st != stream_) {
+            WFS_CUDA_CHECK(cudaEventRecord(ev_join_[k], st));
+            WFS_CUDA_CHECK(cudaStreamWaitEvent(stream_, ev_join_[k], 0));
+        }
+    }
     records();        // records that do not fit the buffer are skipped by the kernel: no decision on the host in between
     read_scalars();
     const uint32_t n_over = reinterpret_cast<const uint32_t *>(h_scalars_ + FS_COUNT)[0];
@@ -1069,7 +1079,7 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
         // groups that outgrew the lists of their class: once more with the largest lists (their truth counters
         // are untouched -- a group adds them only when it fits -- except the per-PMT areas), then all records again
         if (b.pmt_areas) return false;
-        if (!launch_class(defs[kFusedClasses - 1], d_over, n_over, d_u32 + 1 + kFusedClasses, nullptr)) return false;
+        if (!launch_class(defs[kFusedClasses - 1], d_over, n_over, d_u32 + 1 + kFusedClasses, nullptr, stream_)) return false;
         records();
         read_scalars();
     }

@@ -10,7 +10,7 @@ constexpr int kFusedMaxRecCap = 8192;       // records of one group ordered in s
 constexpr int kFusedBins = 1024;            // time bins of the record order
 constexpr int kFusedTrigSlots = 64;         // (pulse call, total / bottom) trigger counters kept in shared memory
 
-constexpr int kFusedClasses = 4;            // groups are binned by photon count
+constexpr int kFusedClasses = 3;            // groups are binned by photon count
 constexpr int kFusedRecordThreads = 128;
 
 enum FusedScalar { FS_NVALID = 0, FS_NPULSES, FS_NWIN, FS_NITV, FS_NSAMPLES, FS_NREC, FS_ERR, FS_OVERFLOW, FS_COUNT };
