@@ -1213,7 +1213,7 @@ Backend::Backend(const DeviceConfig *cfg, cudaStream_t stream, LaunchCounter *lc
     WFS_CUDA_CHECK(cudaEventCreate(&ev1_));
     for (int i = 0; i < 8; i++) WFS_CUDA_CHECK(cudaEventCreate(&evp_[i]));
     WFS_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 5; i++) {
         WFS_CUDA_CHECK(cudaStreamCreateWithFlags(&aux_[i], cudaStreamNonBlocking));
         WFS_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join_[i], cudaEventDisableTiming));
     }
@@ -1226,7 +1226,7 @@ Backend::~Backend() {
     cudaEventDestroy(ev1_);
     for (int i = 0; i < 8; i++) cudaEventDestroy(evp_[i]);
     cudaEventDestroy(ev_fork_);
-    for (int i = 0; i < 2; i++) { cudaEventDestroy(ev_join_[i]); cudaStreamDestroy(aux_[i]); }
+    for (int i = 0; i < 5; i++) { cudaEventDestroy(ev_join_[i]); cudaStreamDestroy(aux_[i]); }
     if (h_scalars_) cudaFreeHost(h_scalars_);
 }
 

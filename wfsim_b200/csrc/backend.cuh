@@ -106,8 +106,8 @@ private:
     Primitives prim_;
     cudaEvent_t ev0_, ev1_;
     cudaEvent_t evp_[8];
-    cudaStream_t aux_[2] = {nullptr, nullptr};     // the size classes of the fused back end run side by side
-    cudaEvent_t ev_fork_ = nullptr, ev_join_[2] = {nullptr, nullptr};
+    cudaStream_t aux_[5] = {};     // the size classes of the fused back end run side by side
+    cudaEvent_t ev_fork_ = nullptr, ev_join_[5] = {};
     int64_t *h_scalars_ = nullptr;   // pinned readback area
     DevBuf keys_, vals_, st_, sg_, flags64_, pulse_first_, pulse_left_, pulse_win_, win_first_pulse_,
         win_meta_, win_scan_, group_tmin_, group_lr_, scalars_, dense_, itv_, itv_nrec_,

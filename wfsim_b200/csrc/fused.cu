@@ -35,19 +35,21 @@
 #include <algorithm>
 #include <limits.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace wfs {
 
 namespace {
 
 constexpr int kNegPos = -(1 << 29);
+constexpr int kDenseAhead = 3;                 // photon k + 3 starts inside the template of photon k: a dense channel
 constexpr int kNoFlag = 31;                     // f0 field: no owned sample below threshold
 
 struct FusedShared {          // fixed-size part of the shared memory, the arrays follow
     int64_t origin_q;         // absolute sample index of key sample 0
     unsigned long long n_samples;
     int32_t n_valid, n_win, n_itv, n_rec, n_pulses, n_emitted;
-    int32_t n_multi, n_slow;
+    int32_t n_multi, n_slow, n_cw;
     int32_t lo, hi;           // min pulse left / max pulse right of the group, relative to origin_q
     int32_t tmax_q;           // largest photon sample of the group, relative to origin_q
     int32_t max_bin;          // most records in one time bin
@@ -163,7 +165,7 @@ __device__ __forceinline__ void bitonic_ascending(int n, int first, int step, Le
 
 }  // namespace
 
-__global__ void __launch_bounds__(kFusedThreads, 2)
+__global__ void __launch_bounds__(kFusedThreads, 1)
 k_group_analyse(FusedArgs A, FusedClass K) {
     extern __shared__ __align__(16) uint8_t smem[];
     const PhotonBatch &b = A.b;
@@ -197,6 +199,7 @@ k_group_analyse(FusedArgs A, FusedClass K) {
 
     for (int i = tid; i < dt * tlen; i += blockDim.x) s_tmpl[i] = c.templates[i];
     for (int i = tid; i < dt; i += blockDim.x) s_cmax[i] = c.current_max[i];
+    for (int i = tid; i < kFusedBins; i += blockDim.x) s_bin[i] = 0;     // (the bins double as per-channel flags below)
 
     for (;;) {
         __syncthreads();                              // everything of the previous group is done
@@ -210,7 +213,7 @@ k_group_analyse(FusedArgs A, FusedClass K) {
         // ------------------------------------------------------------------ load ----
         if (tid == 0) {
             S.n_valid = S.n_win = S.n_itv = S.n_rec = S.n_pulses = S.n_emitted = 0;
-            S.n_multi = S.n_slow = 0;
+            S.n_multi = S.n_slow = S.n_cw = 0;
             S.lo = INT_MAX; S.hi = INT_MIN;
             S.tmax_q = 0; S.max_bin = 0;
             S.overflow = 0;
@@ -369,7 +372,7 @@ k_group_analyse(FusedArgs A, FusedClass K) {
         }
         __syncthreads();
         // leaders take the sum of their followers, followers add nothing any more; photons whose template meets
-        // no other photon of the channel take the short way below, the others are listed
+        // no other photon of the channel take the short way below; channels with overlapping photons are flagged
         for (int kb = warp * 32; kb < n_valid; kb += blockDim.x) {
             const int k = kb + lane;
             const bool valid = k < n_valid;
@@ -384,19 +387,14 @@ k_group_analyse(FusedArgs A, FusedClass K) {
                     s_gain[k] = gsum;
                 }
                 const int T = key_sample(key);
-                alone = (s_keys[a] >> shift_pc) == (s_keys[e - 1] >> shift_pc) &&
-                        (k == a || key_sample(s_keys[k - 1]) <= T - tlen) &&
+                const bool single = (s_keys[a] >> shift_pc) == (s_keys[e - 1] >> shift_pc);
+                alone = single && (k == a || key_sample(s_keys[k - 1]) <= T - tlen) &&
                         (k + 1 == e || key_sample(s_keys[k + 1]) >= T + tlen);
                 listed = !alone;
+                // many photons on top of each other: a warp takes the channel below
+                if (single && k + kDenseAhead < e && key_sample(s_keys[k + kDenseAhead]) < T + tlen) s_bin[ch] = 1;
             }
-            const unsigned m = __ballot_sync(0xffffffffu, listed);
-            int base = 0;
-            if (m) {
-                const int leader = __ffs(m) - 1;
-                if (lane == leader) base = atomicAdd(&S.n_slow, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, leader);
-            }
-            if (listed) s_order[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)k;
+            if (listed) s_keys[k] = key | ((uint64_t)1 << 8);       // "to be evaluated": last-sample field 1 with no first sample
             if (alone) {
                 // one photon, one pulse: every sample of the template against the threshold
                 const double gn = s_gain[k];
@@ -418,10 +416,81 @@ k_group_analyse(FusedArgs A, FusedClass K) {
             }
         }
         __syncthreads();
-        for (int k = tid; k < n_valid; k += blockDim.x)
-            if (key_follower(s_keys[k])) s_gain[k] = 0.0;
+        // photons still to be evaluated: listed for one thread each unless a warp takes their channel
+        for (int kb = warp * 32; kb < n_valid; kb += blockDim.x) {
+            const int k = kb + lane;
+            const uint64_t key = k < n_valid ? s_keys[k] : 0;
+            if (k < n_valid && key_follower(key)) s_gain[k] = 0.0;
+            const bool listed = k < n_valid && key_f0(key) == kNoFlag && key_f1(key) == 1 && !s_bin[(int)(key >> shift_ch)];
+            const unsigned m = __ballot_sync(0xffffffffu, listed);
+            int base = 0;
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) base = atomicAdd(&S.n_slow, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+            }
+            if (listed) s_order[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)k;
+        }
+        for (int w = tid; w < n_win; w += blockDim.x) {
+            const int ch = s_winch[w];
+            if (s_bin[ch]) s_multi[atomicAdd(&S.n_cw, 1)] = (uint16_t)ch;
+        }
         __syncthreads();
-        // ------------------------------------------------------------------ per photon: owned samples ----
+        // ------------------------------------------------------------------ overlapping photons of one pulse ----
+        // One warp per channel.  A cluster = photons whose templates chain (each starts before the previous one ends);
+        // its samples are evaluated 32 at a time, lane = sample, summed over the photons that reach it in list (time)
+        // order.  Every sample belongs to the last photon that starts at or before it: value into that photon's
+        // slot, first / last sample below threshold into its key.
+        for (int w = warp; w < S.n_cw; w += n_warps) {
+            const int ch = s_multi[w], a = s_cstart[ch], e = s_cstart[ch + 1];
+            const int thr = c.zle_thr[ch];
+            int ks = a;
+            while (ks < e) {
+                int ke = ks;                                // last photon of the cluster that starts at ks
+                for (;;) {
+                    const int k = ke + lane;
+                    const bool ends = k < e && (k + 1 == e || key_sample(s_keys[k + 1]) - key_sample(s_keys[k]) >= tlen);
+                    const unsigned m = __ballot_sync(0xffffffffu, ends);
+                    if (m) { ke += __ffs(m) - 1; break; }
+                    ke += 32;
+                }
+                if (ke > ks) {
+                    const int s1 = key_sample(s_keys[ke]) + tlen;
+                    int jlo = ks;
+                    for (int c0 = key_sample(s_keys[ks]); c0 < s1; c0 += 32) {
+                        const int sm = c0 + lane;
+                        while (key_sample(s_keys[jlo]) + tlen <= c0) jlo++;       // (the cluster reaches s1 > c0: jlo <= ke)
+                        double acc = 0.0;
+                        int owner = -1, owner_t = 0;
+                        for (int j = jlo; j <= ke; j++) {
+                            const uint64_t kj = s_keys[j];
+                            const int Tj = key_sample(kj);
+                            if (Tj > c0 + 31) break;
+                            const unsigned d = (unsigned)(sm - Tj);
+                            if (d < (unsigned)tlen) {
+                                acc = __dadd_rn(acc, __dmul_rn(s_tmpl[key_rem(kj) * tlen + (int)d], s_gain[j]));
+                                if (!key_follower(kj)) { owner = j; owner_t = Tj; }
+                            }
+                        }
+                        const bool in = sm < s1 && owner >= 0;
+                        const int v = max(adc_of(acc, c2a) + baseline, 0);
+                        if (in) reinterpret_cast<uint16_t *>(adc_out + (size_t)owner * kSlotVecs)[sm - owner_t] = (uint16_t)(int16_t)v;
+                        const unsigned same = __match_any_sync(0xffffffffu, in ? owner : -1 - lane);
+                        const unsigned below = __ballot_sync(0xffffffffu, in && v < thr) & same;
+                        if (in && below && lane == __ffs(same) - 1) {
+                            const uint64_t key = s_keys[owner];
+                            const int f0 = key_f0(key) == kNoFlag ? c0 + (__ffs(below) - 1) - owner_t : key_f0(key);
+                            const int f1 = c0 + (31 - __clz(below)) - owner_t;
+                            s_keys[owner] = (key & ~((uint64_t)0x3ff << 3)) | ((uint64_t)f0 << 3) | ((uint64_t)f1 << 8);
+                        }
+                        __syncwarp();
+                    }
+                }
+                ks = ke + 1;
+            }
+        }
+        for (int w = tid; w < S.n_cw; w += blockDim.x) s_bin[s_multi[w]] = 0;      // the flags are bins again
+        // ------------------------------------------------------------------ per photon: owned samples (several pulse calls) ----
         for (int q = tid; q < S.n_slow; q += blockDim.x) {
             const int k = s_order[q];
             const uint64_t key = s_keys[k];
@@ -970,11 +1039,26 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
     const int n_ch = c.p.n_tpc_pmts, tmpl_len = c.p.dt * c.p.template_length;
     // groups by photon count: small groups get small shared-memory lists and many CTAs per SM
     struct ClassDef { int n_cap, itv_cap, rec_cap, threads; };
-    ClassDef defs[kFusedClasses] = {{512, 512, 1024, 128}, {2048, 1024, 3072, 256}, {kFusedMaxPhotons, 4096, kFusedMaxRecCap, 512}};
+    ClassDef defs[kFusedMaxClasses] = {{512, 512, 1024, 128}, {2048, 1024, 3072, 256}, {kFusedMaxPhotons, 4096, kFusedMaxRecCap, 512}};
+    int kFusedClasses = 3;
+    if (const char *e = getenv("WFS_FUSED_CLASSES")) {        // experiments: "photons:intervals:records:threads,..." ascending, the last one catches all
+        int n = 0;
+        const char *p = e;
+        while (n < kFusedMaxClasses) {
+            ClassDef d;
+            if (sscanf(p, "%d:%d:%d:%d", &d.n_cap, &d.itv_cap, &d.rec_cap, &d.threads) != 4) break;
+            defs[n++] = d;
+            p = strchr(p, ',');
+            if (!p) break;
+            p++;
+        }
+        if (n > 0 && defs[n - 1].n_cap == kFusedMaxPhotons && defs[n - 1].rec_cap <= kFusedMaxRecCap) kFusedClasses = n;
+        else throw std::runtime_error("WFS_FUSED_CLASSES: the last class must hold 8192 photons");
+    }
     if (const char *e = getenv("WFS_FUSED_REC_CAP"))          // tests: small lists, so that groups take the second attempt
         for (int k = 0; k + 1 < kFusedClasses; k++) defs[k].rec_cap = std::max(32, std::min(defs[k].rec_cap, atoi(e)));
     std::vector<uint32_t> list((size_t)ng);
-    uint32_t cls_n[kFusedClasses] = {}, cls_off[kFusedClasses + 1];
+    uint32_t cls_n[kFusedMaxClasses] = {}, cls_off[kFusedMaxClasses + 1];
     std::vector<uint8_t> cls_of((size_t)ng);
     for (int64_t g = 0; g < ng; g++) {
         int64_t n = 0;
@@ -991,7 +1075,7 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
     cls_off[0] = 0;
     for (int k = 0; k < kFusedClasses; k++) cls_off[k + 1] = cls_off[k] + cls_n[k];
     {
-        uint32_t fill[kFusedClasses];
+        uint32_t fill[kFusedMaxClasses];
         for (int k = 0; k < kFusedClasses; k++) fill[k] = cls_off[k];
         for (int64_t g = 0; g < ng; g++) list[fill[cls_of[g]]++] = (uint32_t)g;
     }

@@ -4,13 +4,13 @@
 
 namespace wfs {
 
-constexpr int kFusedThreads = 512;
+constexpr int kFusedThreads = 1024;
 constexpr int kFusedMaxPhotons = 8192;      // photons of one group (13 index bits in the key)
 constexpr int kFusedMaxRecCap = 8192;       // records of one group ordered in shared memory (13 bits of record slot)
 constexpr int kFusedBins = 1024;            // time bins of the record order
 constexpr int kFusedTrigSlots = 64;         // (pulse call, total / bottom) trigger counters kept in shared memory
 
-constexpr int kFusedClasses = 3;            // groups are binned by photon count
+constexpr int kFusedMaxClasses = 6;         // groups are binned by photon count
 constexpr int kFusedRecordThreads = 128;
 
 enum FusedScalar { FS_NVALID = 0, FS_NPULSES, FS_NWIN, FS_NITV, FS_NSAMPLES, FS_NREC, FS_ERR, FS_OVERFLOW, FS_COUNT };
