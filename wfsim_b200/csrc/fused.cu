@@ -401,16 +401,23 @@ k_group_analyse(FusedArgs A, FusedClass K) {
                 const double *tm = s_tmpl + key_rem(key) * tlen;
                 const int thr = c.zle_thr[ch];
                 int f0 = kNoFlag, f1 = 0;
-                SlotWriter sw{adc_out + (size_t)k * kSlotVecs};
-                for (int j = 0; j < tlen; j++) {
-                    const int v = max(adc_of(__dmul_rn(tm[j], gn), c2a) + baseline, 0);
-                    sw.put(j, v);
-                    if (v < thr) {
-                        if (f0 == kNoFlag) f0 = j;
-                        f1 = j;
+                uint4 *slot = adc_out + (size_t)k * kSlotVecs;
+                for (int j0 = 0; j0 < tlen; j0 += 8) {             // eight samples = one 16-byte vector of the slot
+                    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int j = j0 + u;
+                        if (j < tlen) {
+                            const int v = max(adc_of(__dmul_rn(tm[j], gn), c2a) + baseline, 0);
+                            w[u >> 1] |= (uint32_t)(uint16_t)(int16_t)v << (16 * (u & 1));
+                            if (v < thr) {
+                                f0 = f0 == kNoFlag ? j : f0;
+                                f1 = j;
+                            }
+                        }
                     }
+                    slot[j0 >> 3] = make_uint4(w[0], w[1], w[2], w[3]);
                 }
-                sw.finish(tlen);
                 if (f0 != kNoFlag)
                     s_keys[k] = (key & ~((uint64_t)0x3ff << 3)) | ((uint64_t)f0 << 3) | ((uint64_t)f1 << 8);
             }
@@ -509,18 +516,32 @@ k_group_analyse(FusedArgs A, FusedClass K) {
             if (single) {
                 int klo = k;
                 while (klo > a && key_sample(s_keys[klo - 1]) > T - tlen) klo--;
-                for (int s = T; s < s_end; s++) {
-                    while (key_sample(s_keys[klo]) <= s - tlen) klo++;
-                    double acc = 0.0;
+                // four owned samples at a time: key, gain and template row of a contributor are read once per four
+                // samples; every sample still sums its contributors in list (time) order
+                for (int s0 = T; s0 < s_end; s0 += 4) {
+                    while (key_sample(s_keys[klo]) <= s0 - tlen) klo++;
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
                     for (int j = klo; j <= k; j++) {
                         const uint64_t kj = s_keys[j];
-                        acc = __dadd_rn(acc, __dmul_rn(s_tmpl[key_rem(kj) * tlen + (s - key_sample(kj))], s_gain[j]));
+                        const double gj = s_gain[j];
+                        const int d = s0 - key_sample(kj);              // >= 0: the contributors start at or before T
+                        const double *row = s_tmpl + key_rem(kj) * tlen + d;
+                        if (d < tlen) a0 = __dadd_rn(a0, __dmul_rn(row[0], gj));
+                        if (d + 1 < tlen) a1 = __dadd_rn(a1, __dmul_rn(row[1], gj));
+                        if (d + 2 < tlen) a2 = __dadd_rn(a2, __dmul_rn(row[2], gj));
+                        if (d + 3 < tlen) a3 = __dadd_rn(a3, __dmul_rn(row[3], gj));
                     }
-                    const int v = max(adc_of(acc, c2a) + baseline, 0);
-                    sw.put(s - T, v);
-                    if (v < thr) {
-                        if (f0 == kNoFlag) f0 = s - T;
-                        f1 = s - T;
+                    const double acc4[4] = {a0, a1, a2, a3};
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (s0 + u < s_end) {
+                            const int v = max(adc_of(acc4[u], c2a) + baseline, 0);
+                            sw.put(s0 + u - T, v);
+                            if (v < thr) {
+                                f0 = f0 == kNoFlag ? s0 + u - T : f0;
+                                f1 = s0 + u - T;
+                            }
+                        }
                     }
                 }
             } else {
@@ -943,29 +964,25 @@ k_group_records(FusedArgs A) {
                 s_pref[lane + 32] = tot0 + i1 - n1;
                 if (lane == 31) s_pref[64] = tot0 + i1;
             }
-            for (int i = tid; i < 6 * nr; i += nthr) {
+            for (int r = tid; r < nr; r += nthr) {
                 // strax_interface.py:425-436: time, length, dt, channel, pulse_length, record_i, baseline = 0
-                const int r = i / 6, f = i - 6 * r;
                 const uint4 d = s_desc[r];
                 const int ch = (int)(d.x & 1023u), plen = (int)(d.y & 0xfffffu);
                 const int rec_i = (int)(((d.y >> 20) & 0xfffu) | (((d.z >> 27) & 3u) << 12));
                 const int64_t time = (int64_t)dt * (origin_q + (int)(d.x >> 10) - key_bias);
                 const int length = min(plen - rec_i * SPR, SPR);
-                uint32_t h = (uint32_t)(uint64_t)time;
-                h = f == 1 ? (uint32_t)((uint64_t)time >> 32) : h;
-                h = f == 2 ? (uint32_t)length : h;
-                h = f == 3 ? (((uint32_t)(uint16_t)dt) | ((uint32_t)(uint16_t)ch << 16)) : h;
-                h = f == 4 ? (uint32_t)plen : h;
-                h = f == 5 ? (uint32_t)(uint16_t)rec_i : h;
-                s_tile[hw + r * 61 + f] = h;
-            }
-            for (int r = tid; r < nr; r += nthr) {          // zeros behind `length` (the last record of a pulse)
-                const uint4 d = s_desc[r];
-                const int plen = (int)(d.y & 0xfffffu);
-                const int rec_i = (int)(((d.y >> 20) & 0xfffu) | (((d.z >> 27) & 3u) << 12));
-                const int length = plen - rec_i * SPR;
-                uint16_t *p = s_tile16 + 2 * (hw + r * 61 + 6);
-                for (int sidx = length; sidx < SPR; sidx++) p[sidx] = 0;
+                uint32_t *h = s_tile + hw + r * 61;
+                h[0] = (uint32_t)(uint64_t)time;
+                h[1] = (uint32_t)((uint64_t)time >> 32);
+                h[2] = (uint32_t)length;
+                h[3] = ((uint32_t)(uint16_t)dt) | ((uint32_t)(uint16_t)ch << 16);
+                h[4] = (uint32_t)plen;
+                h[5] = (uint32_t)(uint16_t)rec_i;
+                // zeros behind `length` (the last record of a pulse)
+                if (length < SPR) {
+                    if (length & 1) h[6 + (length >> 1)] &= 0xffffu;
+                    for (int wd = (length + 1) >> 1; wd < SPR / 2; wd++) h[6 + wd] = 0u;
+                }
             }
             __syncthreads();
             const int n_pairs = s_pref[nr];
@@ -1039,8 +1056,9 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
     const int n_ch = c.p.n_tpc_pmts, tmpl_len = c.p.dt * c.p.template_length;
     // groups by photon count: small groups get small shared-memory lists and many CTAs per SM
     struct ClassDef { int n_cap, itv_cap, rec_cap, threads; };
-    ClassDef defs[kFusedMaxClasses] = {{512, 512, 1024, 128}, {2048, 1024, 3072, 256}, {kFusedMaxPhotons, 4096, kFusedMaxRecCap, 512}};
-    int kFusedClasses = 3;
+    ClassDef defs[kFusedMaxClasses] = {{512, 512, 1024, 256}, {2048, 1024, 3072, 512}, {4096, 2048, 6144, 1024},
+                                       {kFusedMaxPhotons, 4096, kFusedMaxRecCap, 1024}};      // (profiles/tools/class_sweep.sh)
+    int kFusedClasses = 4;
     if (const char *e = getenv("WFS_FUSED_CLASSES")) {        // experiments: "photons:intervals:records:threads,..." ascending, the last one catches all
         int n = 0;
         const char *p = e;
