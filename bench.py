@@ -256,6 +256,7 @@ def run_b200(args, rank, world, local_rank):
     # caller-owned destination: an ordinary (pageable) numpy array, touched once, as a plugin would
     # hold it -- the library's host threads expand the compact records straight into it
     records_out = host_array(cap, raw_record_dtype())
+    dest_pinned = (not os.environ.get('WFS_BENCH_PAGEABLE')) and sim.pin(records_out)
     e2e_ms, e2e_lib = [], []
     h2d = inst.nbytes + 494 * 4 * 2 + len(inst) * (8 * 3 + 4)
     d2h = 0
@@ -268,7 +269,8 @@ def run_b200(args, rank, world, local_rank):
         dt = time.perf_counter() - t0
         if k >= args.warmup:
             e2e_ms.append(dt * 1e3)
-            e2e_lib.append([sim.last_counts['ms_total']] + list(sim.last_counts['ms_phase'][8:10]))
+            e2e_lib.append([sim.last_counts['ms_total']] + list(sim.last_counts['ms_phase'][8:10])
+                           + [sim.last_counts['n_plain_records']])
         # record bytes that crossed PCIe (compact transport: headers + non-baseline sample blocks,
         # expanded to 244-byte records by the library's host threads) + truth rows + group info
         d2h = (sim.last_counts['d2h_bytes'] + sim.last_counts['n_truth'] * TRUTH_BYTES
@@ -308,7 +310,11 @@ def run_b200(args, rank, world, local_rank):
                 # batches of (batch shipped -> its compact D2H done) and (D2H done -> expanded by host threads)
                 'ms_device': float(np.mean([x[0] for x in e2e_lib])),
                 'ms_batches_d2h': float(np.mean([x[1] for x in e2e_lib])),
-                'ms_batches_expand': float(np.mean([x[2] for x in e2e_lib]))},
+                'ms_batches_expand': float(np.mean([x[2] for x in e2e_lib])),
+                # split transport: the destination is the caller's numpy array, page-locked with wfs_host_register
+                # as the plugin's record arenas are; this share of the records arrived as plain rows by DMA
+                'destination': 'caller-owned numpy array, ' + ('page-locked (wfs_host_register)' if dest_pinned else 'pageable'),
+                'plain_record_share': [round(x[3] / max(c['n_records_total'], 1), 3) for x in e2e_lib]},
         'gpu_launches': int(launches_all),
         'ms_phase_per_step': dict(zip(['frontend', 'photon_sort', 'windows', 'digitize', 'zle', 'record_sort',
                                        'record_pack', 'host_scheduler_truth'], (phases[:8] / args.steps).round(3).tolist())),

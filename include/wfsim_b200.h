@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define WFS_ABI_VERSION 4
+#define WFS_ABI_VERSION 5
 #define WFS_E_CAPACITY 1
 #define WFS_E_CUDA (-1)
 #define WFS_E_ARG (-2)
@@ -244,7 +244,10 @@ typedef struct wfs_counts {
     double ms_phase[12];
     int64_t n_fused_batches;        /* device batches that went through the group-resident fused kernel (one CTA per
                                      * digitisation group, photons -> records; then ms_phase[3] is that kernel and
-                                     * phases 1, 2, 4, 5 are zero) */
+                                     * phases 1, 2, 4, 5 are zero; 3 = k_group_analyse, 6 = k_group_records
+                                     * [+ plain -> compact transport form]) */
+    int64_t n_plain_records;        /* records that crossed PCIe as plain 244-byte rows (split transport into a
+                                     * page-locked destination; the rest travelled compact and was expanded on the host) */
 } wfs_counts;
 
 /* Digitisation-group bookkeeping returned to the host-side chunker
@@ -271,6 +274,13 @@ int64_t wfs_quiet_gap(void *handle);
 /* Pinned host memory for output buffers (so device->host copies are plain DMA). */
 void *wfs_host_alloc(int64_t bytes);
 void wfs_host_free(void *p);
+/* Page-locks / releases memory the caller owns (the record arenas of ChunkRawRecords,
+ * strax_interface.py:387-392: one buffer reused for the whole run).  Into a page-locked destination
+ * wfs_simulate sends part of every batch as plain 244-byte rows by DMA (no host core involved) and the rest
+ * in the compact form, the share following which of the two finished first for the previous batches; into
+ * ordinary memory everything travels compact.  The records are the same either way.  Returns 0 or WFS_E_CUDA. */
+int wfs_host_register(void *p, int64_t bytes);
+int wfs_host_unregister(void *p);
 
 /* Host half of the compact record transport (csrc/transport.cuh): when the destination of the records
  * is host memory they cross PCIe as 24-byte headers + the 8-byte (4-sample) blocks that differ from the

@@ -63,6 +63,8 @@ CONFIGS = {
                            lambda: c0_like(24, seed=16, event_rate=9000.0, e_range=(0.5, 3))),
     'thresholds': (dict(zle_threshold=40, special_thresholds={'7': 60, '255': 5, '300': 25}), lambda: c0_like(10, seed=7, e_range=(1, 12))),
     'gate': (dict(enable_gate_afterpulses=True, photoelectric_p=0.004), lambda: c0_like(10, seed=8, e_range=(1, 12))),
+    # many groups per launch (CTAs take several groups in turn) with channels that hold several pulse calls
+    'afterpulses_many_groups': (dict(enable_pmt_afterpulses=True), lambda: c1_like(400, seed=9)),
     'bright_s1': (dict(), lambda: c0_like(10, seed=21, e_range=(8, 12), s1_per_kev=400.0, s2_per_kev=2.0)),
 }
 
@@ -112,6 +114,38 @@ def test_fused_over_several_batches_lanes_and_transports():
     for other in (cut, pinned, small, retried):
         for k in ('raw_records', 'raw_records_he', 'truth', 'groups'):
             assert other[k].tobytes() == ref[k].tobytes(), k
+    sim.close()
+
+
+@pytest.mark.parametrize('fraction', ['adaptive', '0', '0.3', '1'])
+def test_split_transport_into_page_locked_destinations(fraction):
+    """A destination the caller page-locked (Simulator.pin -> wfs_host_register) receives part of every batch as
+    plain rows by DMA and the rest compact + expanded; the records do not depend on the share."""
+    from wfsim_b200.dtypes import raw_record_dtype
+    sim, cfg = make_sim(enable_pmt_afterpulses=True)
+    inst = c1_like(400, seed=9)
+    ref = sim.simulate(inst, seed=5)
+    n = len(ref['raw_records'])
+    dest = np.empty(n + 5000, raw_record_dtype())
+    dest.view(np.uint8)[:] = 0xAB
+    assert sim.pin(dest)
+    kv = dict(WFS_BATCH_INSTRUCTIONS=100)
+    if fraction != 'adaptive':
+        kv['WFS_PLAIN_FRACTION'] = fraction
+    with env(**kv):
+        for rep in range(3):          # the adaptive share moves from call to call
+            out = sim.simulate(inst, seed=5, records_out=dest)
+            c = sim.last_counts
+            assert c['n_batches'] > 2 and c['n_fused_batches'] == c['n_batches']
+            if fraction == '0':
+                assert c['n_plain_records'] == 0
+            elif fraction == '1':
+                assert c['n_plain_records'] >= n - 4 * c['n_batches']
+            elif fraction == '0.3':
+                assert 0 < c['n_plain_records'] < n
+            assert out['raw_records'].tobytes() == ref['raw_records'].tobytes()
+            assert out['truth'].tobytes() == ref['truth'].tobytes()
+    del out, dest
     sim.close()
 
 

@@ -177,6 +177,18 @@ void *wfs_host_alloc(int64_t bytes) {
 
 void wfs_host_free(void *p) { if (p) cudaFreeHost(p); }
 
+int wfs_host_register(void *p, int64_t bytes) {
+    if (!p || bytes <= 0) return WFS_E_ARG;
+    if (cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return WFS_E_CUDA; }
+    return 0;
+}
+
+int wfs_host_unregister(void *p) {
+    if (!p) return WFS_E_ARG;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return WFS_E_CUDA; }
+    return 0;
+}
+
 int wfs_expand_compact(const void *hdr, const void *blocks, int64_t n_records, uint8_t *records,
                        int fill, int dt, int n_threads) {
     if (n_records < 0 || (n_records > 0 && (!hdr || !records))) return WFS_E_ARG;

@@ -1248,7 +1248,8 @@ void Backend::release() {
     } while (0)
 
 void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_records,
-                  wfs_group_info *group_info_out, BackendResult &res, const CompactOut *compact) {
+                  wfs_group_info *group_info_out, BackendResult &res, const CompactOut *compact,
+                  double plain_fraction) {
     const DeviceConfig &c = *cfg_;
     res = BackendResult();
     const int64_t n = b.n, ng = b.n_groups;
@@ -1258,24 +1259,33 @@ void Backend::run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_record
         // small groups: one CTA per group from the photons to the records (fused.cu); for a host destination
         // the records then stream once more through k_compact_records into the compact transport form
         uint8_t *dst = records_out;
-        if (compact) {
+        const bool split = compact && plain_fraction > 0.0 && records_out;
+        if (compact && !split) {
             fused_records_.reserve((size_t)WFS_RECORD_BYTES * (size_t)std::max<int64_t>(cap_records, 1) + 64);
             dst = fused_records_.as<uint8_t>();
         }
         if (run_fused(b, dst, cap_records, group_info_out, res)) {
             if (compact && !res.error && res.n_records > 0 && res.n_records <= cap_records) {
-                if ((uint64_t)res.n_records * kBlocksPerRecord >= (uint64_t(1) << 32)) { res.error = WFS_E_KEYBITS; return; }
-                scalars_.reserve(sizeof(int64_t) * S_COUNT);
-                WFS_CUDA_CHECK(cudaMemsetAsync(scalars_.p, 0, sizeof(int64_t) * S_COUNT, stream_));
-                WFS_CUDA_CHECK(cudaEventRecord(evp_[5], stream_));
-                LAUNCH(k_compact_records, div_up(res.n_records, kPackRecs), kPackWarps * 32, res.n_records, c.p.baseline,
-                       reinterpret_cast<const uint32_t *>(dst), reinterpret_cast<uint32_t *>(compact->hdr),
-                       compact->blocks, scalars_.as<int64_t>());
-                WFS_CUDA_CHECK(cudaEventRecord(evp_[6], stream_));
-                WFS_CUDA_CHECK(cudaMemcpyAsync(h_scalars_, scalars_.p, sizeof(int64_t) * S_COUNT, cudaMemcpyDeviceToHost, stream_));
-                WFS_CUDA_CHECK(stream_sync(stream_));
-                res.n_blocks = h_scalars_[S_NBLOCKS];
-                cudaEventElapsedTime(&res.ms_phase[6], evp_[5], evp_[6]);
+                // split transport: the leading rows stay as they are (a multiple of four rows keeps the rest 16-byte aligned)
+                const int64_t n_plain = split ? (int64_t)(std::min(plain_fraction, 1.0) * (double)res.n_records) & ~int64_t(3) : 0;
+                const int64_t n_comp = res.n_records - n_plain;
+                res.n_plain = n_plain;
+                if ((uint64_t)n_comp * kBlocksPerRecord >= (uint64_t(1) << 32)) { res.error = WFS_E_KEYBITS; return; }
+                if (n_comp > 0) {
+                    scalars_.reserve(sizeof(int64_t) * S_COUNT);
+                    WFS_CUDA_CHECK(cudaMemsetAsync(scalars_.p, 0, sizeof(int64_t) * S_COUNT, stream_));
+                    WFS_CUDA_CHECK(cudaEventRecord(evp_[5], stream_));
+                    LAUNCH(k_compact_records, div_up(n_comp, kPackRecs), kPackWarps * 32, n_comp, c.p.baseline,
+                           reinterpret_cast<const uint32_t *>(dst + (size_t)n_plain * WFS_RECORD_BYTES),
+                           reinterpret_cast<uint32_t *>(compact->hdr), compact->blocks, scalars_.as<int64_t>());
+                    WFS_CUDA_CHECK(cudaEventRecord(evp_[6], stream_));
+                    WFS_CUDA_CHECK(cudaMemcpyAsync(h_scalars_, scalars_.p, sizeof(int64_t) * S_COUNT, cudaMemcpyDeviceToHost, stream_));
+                    WFS_CUDA_CHECK(stream_sync(stream_));
+                    res.n_blocks = h_scalars_[S_NBLOCKS];
+                    float ms_compact = 0.f;
+                    cudaEventElapsedTime(&ms_compact, evp_[5], evp_[6]);
+                    res.ms_phase[6] += ms_compact;
+                }
             }
             return;
         }

@@ -71,6 +71,8 @@ struct BackendResult {
     int64_t n_valid_photons = 0, n_pulses = 0, n_windows = 0, n_tiles = 0;
     int64_t n_intervals = 0, n_records = 0, n_samples = 0;
     int64_t n_blocks = 0;            // compact transport: 8-byte blocks in the stream
+    int64_t n_plain = 0;             // split transport: records [0, n_plain) stay plain rows in records_out, the
+                                     // compact streams hold records [n_plain, n_records)
     int64_t n_dense_tiles = 0;       // digitize tiles that took the gather (dense) path
     int64_t n_rec_class[3] = {0, 0, 0};
     float ms_digitize = 0.f;
@@ -90,9 +92,12 @@ public:
     // If cap_records is too small, res.n_records holds the need and nothing is written.
     // With `compact` the records leave in the compact transport form (transport.cuh) instead:
     // headers at compact->hdr[0 .. n_records), res.n_blocks blocks at compact->blocks; cap_records
-    // then bounds those buffers and records_out is unused.
+    // then bounds those buffers and records_out is unused -- unless plain_fraction > 0 (split transport): then
+    // records_out (cap_records rows as well) receives the plain rows of the batch, res.n_plain of them are
+    // meant to travel as they are and the compact streams start at record res.n_plain.
     void run(const PhotonBatch &b, uint8_t *records_out, int64_t cap_records,
-             wfs_group_info *group_info_out, BackendResult &res, const CompactOut *compact = nullptr);
+             wfs_group_info *group_info_out, BackendResult &res, const CompactOut *compact = nullptr,
+             double plain_fraction = 0.0);
     void release();
     bool fused_eligible(const PhotonBatch &b) const;
     // false: not run / a group outgrew the shared-memory lists -- the caller takes the multi-pass path

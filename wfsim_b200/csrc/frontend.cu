@@ -386,6 +386,7 @@ struct SimOut {
     int64_t n_rec = 0, n_truth = 0, n_groups = 0, n_batches = 0;
     bool overflow = false;
     bool compact = false;        // records travel in the compact transport form (decided once per call)
+    bool split = false;          // ... and, the destination being page-locked, partly as plain rows (transport.cuh)
 };
 
 static GenCtx make_ctx(Frontend &F, uint64_t seed) {
@@ -1147,11 +1148,16 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     const bool compact = !so.resident && want_records && so.compact;
     CompactOut co;
     int64_t cap_here = 0;
+    const double plain_fraction = compact && so.split ? H->split.fraction() : 0.0;
     auto reserve_records = [&](int64_t n_rec) {
         if (compact) {
             cs.reserve_device(n_rec);
             cap_here = cs.cap_records();
             co = cs.out();
+            if (plain_fraction > 0.0) {
+                rb.reserve((size_t)WFS_RECORD_BYTES * (size_t)n_rec);
+                cap_here = std::min(cap_here, (int64_t)(rb.cap / WFS_RECORD_BYTES));
+            }
         } else if (want_records) {
             rb.reserve((size_t)WFS_RECORD_BYTES * (size_t)n_rec);
             cap_here = (int64_t)(rb.cap / WFS_RECORD_BYTES);
@@ -1160,7 +1166,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     reserve_records(std::max<int64_t>(2 * (n_ph + n_ap) + 65536, 1));
     uint8_t *d_rec = rb.as<uint8_t>();
     if (ngroups > 0) {
-        L.B->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res, compact ? &co : nullptr);
+        L.B->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res, compact ? &co : nullptr, plain_fraction);
         if (res.error) {
             // reported through failure[] of run_plan: lanes never write the handle's error string
             throw std::runtime_error(res.error == WFS_E_PULSE_CACHE_TOO_LONG ? "Pulse cache too long"
@@ -1173,7 +1179,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
             WFS_CUDA_CHECK(cudaMemsetAsync(F.b_trig.p, 0, 4 * (size_t)std::max<int64_t>(2 * npc, 1), s));
             if (per_pmt)   // the fused kernel adds the per-PMT areas photon by photon
                 WFS_CUDA_CHECK(cudaMemsetAsync(F.b_pmtarea.p, 0, sizeof(int64_t) * 2 * (size_t)n_ch * (size_t)nruns, s));
-            L.B->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res, compact ? &co : nullptr);
+            L.B->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res, compact ? &co : nullptr, plain_fraction);
         }
     }
     std::vector<wfs_group_info> h_groups((size_t)ngroups);
@@ -1232,7 +1238,8 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         so.n_batches = std::max(so.n_batches, batch_index + 1);
         for (int k = 0; k < 3; k++) cn->n_records[k] += fits ? res.n_rec_class[k] : 0;
         if (!so.resident && fits)
-            cn->d2h_bytes += compact ? (int64_t)sizeof(CompactHdr) * res.n_records + kBlockBytes * res.n_blocks
+            cn->d2h_bytes += compact ? (int64_t)sizeof(CompactHdr) * (res.n_records - res.n_plain) + kBlockBytes * res.n_blocks +
+                                           (int64_t)WFS_RECORD_BYTES * res.n_plain
                                      : (int64_t)WFS_RECORD_BYTES * res.n_records;
         cn->n_pe += n_pe;
         cn->n_photons += res.n_valid_photons;
@@ -1260,8 +1267,22 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         const size_t total_bytes = (size_t)res.n_records * WFS_RECORD_BYTES, piece = size_t(8) << 20;
         uint8_t *dst = out->records + (size_t)rec0 * WFS_RECORD_BYTES;
         if (compact) {
-            cs.ship(H->host_pool(), L.copy_stream, res.n_records, res.n_blocks, dst, H->record_fill(),
-                    (int16_t)p.dt, &H->tstats);
+            // the compact streams first (the expansion starts as soon as they have arrived), the plain rows behind them
+            const int64_t n_plain = res.n_plain, n_comp = res.n_records - n_plain;
+            const bool both = n_plain > 0 && n_comp > 0;
+            if (n_comp > 0)
+                cs.ship(H->host_pool(), L.copy_stream, n_comp, res.n_blocks, dst + (size_t)n_plain * WFS_RECORD_BYTES,
+                        H->record_fill(), (int16_t)p.dt, &H->tstats, both ? &H->split : nullptr);
+            if (n_plain > 0) {
+                const size_t plain_bytes = (size_t)n_plain * WFS_RECORD_BYTES;
+                for (size_t o = 0; o < plain_bytes; o += piece)
+                    WFS_CUDA_CHECK(cudaMemcpyAsync(dst + o, d_rec + o, std::min(piece, plain_bytes - o),
+                                                   cudaMemcpyDeviceToHost, L.copy_stream));
+                if (both) WFS_CUDA_CHECK(cudaLaunchHostFunc(L.copy_stream, ExpandJob::plain_done_callback, &cs.job));
+                WFS_CUDA_CHECK(cudaEventRecord(F.ev_copy[par], L.copy_stream));
+                F.copy_pending[par] = true;
+                H->tstats.n_plain += n_plain;
+            }
         } else {
             for (size_t o = 0; o < total_bytes; o += piece)
                 WFS_CUDA_CHECK(cudaMemcpyAsync(dst + o, d_rec + o, std::min(piece, total_bytes - o),
@@ -1432,12 +1453,15 @@ static int run_plan(Handle *H, Plan &P, uint64_t seed, wfs_outputs *out, wfs_cou
     const int64_t launches0 = H->launches.n;
     H->tstats.ns_copy = 0;
     H->tstats.ns_expand = 0;
+    H->tstats.n_plain = 0;
     SimOut so;
     so.out = out;
     so.counts = counts;
     so.resident = resident;
     so.dump = dump;
     so.compact = !resident && out && out->records && H->use_compact(out->records);
+    so.split = so.compact && H->compact_mode == 1 && Handle::page_locked(out->records);
+    if (so.split) H->split.init(H->host_pool()->size());
     const int64_t nb = (int64_t)P.batches.size();
     const int n_lanes = dump ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(env_i64("WFS_LANES", 3), 8), nb));
     ensure_lanes(H, std::max(n_lanes, 1));
@@ -1493,6 +1517,7 @@ static int run_plan(Handle *H, Plan &P, uint64_t seed, wfs_outputs *out, wfs_cou
     counts->ms_total = ms;
     counts->ms_phase[8] = H->tstats.ns_copy.load() * 1e-6;
     counts->ms_phase[9] = H->tstats.ns_expand.load() * 1e-6;
+    counts->n_plain_records = H->tstats.n_plain.load();
     counts->n_records_total = so.n_rec;
     counts->n_truth = so.n_truth;
     counts->n_groups = so.n_groups;

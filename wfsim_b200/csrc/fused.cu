@@ -312,7 +312,8 @@ k_group_analyse(FusedArgs A, FusedClass K) {
         }
         if (n_warps == 1 || warp > 0) {
             const int t0 = n_warps == 1 ? tid : tid - 32, step = n_warps == 1 ? 32 : (int)blockDim.x - 32;
-            for (int i = t0; i < n_bins; i += step) s_bin[i] = 0;
+            // (the bins double as per-channel flags below: the previous group's bin offsets must not be read as flags)
+            for (int i = t0; i < max(n_bins, n_ch); i += step) s_bin[i] = 0;
         }
         __syncthreads();
         for (int i = tid; i < n_g; i += blockDim.x) {
@@ -1174,6 +1175,7 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
             WFS_CUDA_CHECK(cudaStreamWaitEvent(stream_, ev_join_[k], 0));
         }
     }
+    WFS_CUDA_CHECK(cudaEventRecord(evp_[4], stream_));
     records();        // records that do not fit the buffer are skipped by the kernel: no decision on the host in between
     read_scalars();
     const uint32_t n_over = reinterpret_cast<const uint32_t *>(h_scalars_ + FS_COUNT)[0];
@@ -1200,8 +1202,9 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
     res.n_samples = h_scalars_[FS_NSAMPLES];
     res.n_records = h_scalars_[FS_NREC];
     res.n_rec_class[0] = res.n_records <= cap_records ? res.n_records : 0;
-    WFS_CUDA_CHECK(cudaEventElapsedTime(&res.ms_digitize, ev0_, ev1_));
+    WFS_CUDA_CHECK(cudaEventElapsedTime(&res.ms_digitize, ev0_, evp_[4]));       // k_group_analyse (all classes)
     res.ms_phase[3] = res.ms_digitize;
+    if (!n_over) WFS_CUDA_CHECK(cudaEventElapsedTime(&res.ms_phase[6], evp_[4], ev1_));      // scan + k_group_records
     res.segment_sorted_photons = res.segment_sorted_records = 1;
     return true;
 }

@@ -29,6 +29,12 @@ struct Handle {
     HostPool *pool = nullptr;
     CompactStage cstage;
     TransportStats tstats;
+    SplitControl split;                 // share of the records that travels as plain rows (page-locked destinations)
+    static bool page_locked(const void *p) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return attr.type == cudaMemoryTypeHost;
+    }
     int compact_mode = 1;               // WFS_COMPACT: 0 never, 1 (default) see use_compact, 2 always
 
     // Compact transport + host expansion, or a plain DMA of the 244-byte rows?  With the noise on

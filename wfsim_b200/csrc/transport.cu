@@ -56,6 +56,43 @@ void ExpandJob::abandon() {
     cv.notify_all();
 }
 
+void SplitControl::init(int expand_threads) {
+    if (const char *e = getenv("WFS_PLAIN_FRACTION")) {      // fixed share (tests, measurements); read at every call
+        fixed = true;
+        permille = (int)std::max(0.0, std::min(1000.0, atof(e) * 1000.0));
+        return;
+    }
+    if (fixed) { fixed = false; permille = -1; }
+    if (permille.load() >= 0) return;
+    // first guess: E = what the expansion threads write (GB/s of records), P = the link, c = compact / plain bytes;
+    // both sides finish together at f = (1/E - c/P) / ((1 - c)/P + 1/E)
+    const double E = 6.0 * std::max(1, expand_threads), P = 50.0, c = 0.28;
+    const double f = (1.0 / E - c / P) / ((1.0 - c) / P + 1.0 / E);
+    permille = (int)std::max(0.0, std::min(950.0, f * 1000.0));
+}
+
+void SplitControl::feedback(int64_t t_ship, int64_t t_plain_done, int64_t t_expand_done) {
+    if (fixed) return;
+    const double dp = (double)(t_plain_done - t_ship), de = (double)(t_expand_done - t_ship);
+    const double span = std::max(std::max(dp, de), 1.0);
+    const double err = (de - dp) / span;                  // > 0: the expansion finished last -> more plain rows
+    int cur = permille.load(), next;
+    do {
+        next = (int)std::max(0.0, std::min(950.0, cur + 120.0 * err));
+    } while (!permille.compare_exchange_weak(cur, next));
+}
+
+void ExpandJob::arrive() {
+    if (arrivals.fetch_add(1) == 1 && split) split->feedback(t_ship, t_plain_done.load(), t_expand_done.load());
+}
+
+void CUDART_CB ExpandJob::plain_done_callback(void *p) {
+    ExpandJob *job = reinterpret_cast<ExpandJob *>(p);
+    job->t_plain_done = std::chrono::duration_cast<std::chrono::nanoseconds>(
+                            std::chrono::steady_clock::now().time_since_epoch()).count();
+    job->arrive();
+}
+
 int host_cores_per_rank() {
     // the cores this process may run on (cgroup / taskset aware, unlike hardware_concurrency), shared
     // with the LOCAL_WORLD_SIZE - 1 other per-GPU processes of the box (torchrun sets it)
@@ -122,9 +159,14 @@ void HostPool::worker() {
             std::lock_guard<std::mutex> lk(job->mu);
             last = --job->remaining == 0;
             if (last) {
+                const int64_t t_done = now_ns();
                 if (job->stats) {
                     job->stats->ns_copy += job->t_callback - job->t_ship;
-                    job->stats->ns_expand += now_ns() - job->t_callback;
+                    job->stats->ns_expand += t_done - job->t_callback;
+                }
+                if (job->split) {
+                    job->t_expand_done = t_done;
+                    job->arrive();
                 }
                 job->pending = false;
             }
@@ -134,7 +176,7 @@ void HostPool::worker() {
 }
 
 void CompactStage::ship(HostPool *pool, cudaStream_t copy_stream, int64_t n_rec, int64_t n_blocks,
-                        uint8_t *dst, int16_t fill, int16_t dt, TransportStats *stats) {
+                        uint8_t *dst, int16_t fill, int16_t dt, TransportStats *stats, SplitControl *split) {
     const size_t hdr_bytes = sizeof(CompactHdr) * (size_t)n_rec, blk_bytes = (size_t)kBlockBytes * (size_t)n_blocks;
     job.wait();
     h_hdr.reserve(hdr_bytes);
@@ -150,6 +192,8 @@ void CompactStage::ship(HostPool *pool, cudaStream_t copy_stream, int64_t n_rec,
                                        cudaMemcpyDeviceToHost, copy_stream));
     job.pool = pool;
     job.stats = stats;
+    job.split = split;
+    job.arrivals = 0;
     job.t_ship = now_ns();
     job.hdr = reinterpret_cast<const CompactHdr *>(h_hdr.p);
     job.blocks = reinterpret_cast<const uint8_t *>(h_blk.p);

@@ -37,6 +37,20 @@ class HostPool;
 struct TransportStats {          // wall clock, summed over the batches of one call
     std::atomic<int64_t> ns_copy{0};      // ship -> copies complete (waits for the stream included)
     std::atomic<int64_t> ns_expand{0};    // copies complete -> last slice expanded
+    std::atomic<int64_t> n_plain{0};      // records that travelled as plain 244-byte rows (split transport)
+};
+
+// Split transport (page-locked destinations only): the leading rows of a batch leave HBM as they are (DMA
+// straight into the caller's array, no host core involved), the rest as the compact form that the pool expands.
+// The fraction follows what the host can do: each batch reports when its DMA and when its expansion finished,
+// and the share moves towards the side that finished first.  The records do not depend on it.
+struct SplitControl {
+    std::atomic<int> permille{-1};        // share of plain rows; -1: not initialised
+    bool fixed = false;                   // WFS_PLAIN_FRACTION given
+    void init(int expand_threads);
+    double fraction() const { return std::max(0, permille.load()) * 1e-3; }
+    // t_*: steady-clock ns; expansion / DMA of one batch finished
+    void feedback(int64_t t_ship, int64_t t_plain_done, int64_t t_expand_done);
 };
 
 // One batch in flight: filled in by the producer, enqueued (from a stream callback) when its D2H
@@ -51,6 +65,12 @@ struct ExpandJob {
     int slices = 0;
     TransportStats *stats = nullptr;
     int64_t t_ship = 0, t_callback = 0;
+    // split transport: the plain rows of the same batch travel behind the compact streams
+    SplitControl *split = nullptr;
+    std::atomic<int64_t> t_plain_done{0}, t_expand_done{0};
+    std::atomic<int> arrivals{0};
+    void arrive();               // DMA done / expansion done: the second one reports to the controller
+    static void CUDART_CB plain_done_callback(void *job);
     // completion
     std::mutex mu;
     std::condition_variable cv;
@@ -116,8 +136,10 @@ struct CompactStage {
     CompactOut out() { return CompactOut{d_hdr.as<CompactHdr>(), d_blk.as<uint2>()}; }
     // Queues the D2H copies of (n_rec headers, n_blocks blocks) on `copy_stream` and, behind them,
     // the expansion into dst.  The caller must job.wait() before touching the stage again.
+    // `split`: plain rows of the same batch follow on the stream; the caller queues them and then
+    // ExpandJob::plain_done_callback(&job).
     void ship(HostPool *pool, cudaStream_t copy_stream, int64_t n_rec, int64_t n_blocks, uint8_t *dst,
-              int16_t fill, int16_t dt, TransportStats *stats = nullptr);
+              int16_t fill, int16_t dt, TransportStats *stats = nullptr, SplitControl *split = nullptr);
     void release() {
         d_hdr.release(); d_blk.release(); h_hdr.release(); h_blk.release();
     }

@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'csrc', 'libwfsim_b200.so')
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 E_CAPACITY = 1
 E_CUDA = -1
 E_ARG = -2
@@ -98,7 +98,7 @@ class Counts(C.Structure):
                     'n_batches', 'gpu_launches', 'need_records', 'need_truth', 'need_groups',
                     'need_batches', 'd2h_bytes')]
                 + [(n, f64) for n in ('ms_total', 'ms_digitize', 'ms_h2d', 'ms_d2h')]
-                + [('ms_phase', f64 * 12), ('n_fused_batches', i64)])
+                + [('ms_phase', f64 * 12), ('n_fused_batches', i64), ('n_plain_records', i64)])
 
     def as_dict(self):
         d = {n: getattr(self, n) for n, _ in self._fields_ if n not in ('n_records', 'ms_phase')}
@@ -112,7 +112,8 @@ class GroupInfo(C.Structure):
 
 
 EXPORTS = ['wfs_create', 'wfs_destroy', 'wfs_last_error', 'wfs_abi_version', 'wfs_struct_sizes',
-           'wfs_device_count', 'wfs_host_alloc', 'wfs_host_free', 'wfs_simulate_photons',
+           'wfs_device_count', 'wfs_host_alloc', 'wfs_host_free', 'wfs_host_register', 'wfs_host_unregister',
+           'wfs_simulate_photons',
            'wfs_simulate', 'wfs_stage_instructions', 'wfs_run_staged', 'wfs_sample_stage',
            'wfs_expand_compact', 'wfs_quiet_gap', 'wfs_schedule']
 
@@ -141,6 +142,8 @@ def load():
     lib.wfs_host_alloc.restype = vp
     lib.wfs_host_alloc.argtypes = [i64]
     lib.wfs_host_free.argtypes = [vp]
+    lib.wfs_host_register.argtypes = [vp, i64]
+    lib.wfs_host_unregister.argtypes = [vp]
     lib.wfs_destroy.argtypes = [vp]
     lib.wfs_schedule.argtypes = [i64, f64, C.c_int, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i64,
                                  C.POINTER(i64), C.POINTER(i64)]

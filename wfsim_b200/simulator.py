@@ -24,6 +24,20 @@ def host_records(n, dtype=None):
     return np.empty(int(n), np.dtype(raw_record_dtype() if dtype is None else dtype))
 
 
+def pin_array(lib, array):
+    """Page-locks the memory of a numpy array the caller owns (wfs_host_register) until the array is
+    garbage-collected.  Into such a destination the library moves part of the records by plain DMA.  Returns
+    False (and leaves the array usable as ordinary memory) when the driver refuses."""
+    import weakref
+    if array.nbytes == 0 or not array.flags['C_CONTIGUOUS'] or not array.flags['OWNDATA']:
+        return False
+    ptr = array.ctypes.data
+    if lib.wfs_host_register(ptr, array.nbytes) != 0:
+        return False
+    weakref.finalize(array, lib.wfs_host_unregister, ptr)
+    return True
+
+
 class PinnedArray:
     """numpy view over pinned host memory obtained from the library (plain DMA target)."""
 
@@ -72,6 +86,10 @@ class Simulator:
         self.device = device
         self.last_counts = None
         self._pinned_cache = None      # reusable pinned record buffer (pinning is slow)
+
+    def pin(self, array):
+        """Page-lock a caller-owned record array (see pin_array)."""
+        return pin_array(self.lib, array)
 
     def close(self):
         if getattr(self, '_pinned_cache', None) is not None:

@@ -14,6 +14,7 @@ stand-in base class is used so the same compute loop can be exercised by the tes
 The simulation itself always runs in libwfsim_b200.so (ctypes); there is no CPU fallback.
 """
 import logging
+import os
 
 import numpy as np
 
@@ -115,8 +116,9 @@ class _ArenaPool:
     """Record arenas of one chunker.  take(n) hands out an arena of at least n records: one of its own
     that nobody else references any more (the consumer dropped every chunk view into it), else a new one."""
 
-    def __init__(self):
+    def __init__(self, pin=None):
         self.arenas = []
+        self.pin = pin          # page-locks a new arena (Simulator.pin): part of the records then arrive by plain DMA
 
     def take(self, n, dtype):
         import sys
@@ -132,6 +134,8 @@ class _ArenaPool:
         # released and allocated again pays for unmapping and for the page faults of fresh memory
         quantum = 1 << 22
         self.arenas.append(np.empty((int(n * 1.25) // quantum + 1) * quantum, dtype))
+        if self.pin is not None and not os.environ.get('WFS_NO_PINNED_ARENAS'):
+            self.pin(self.arenas[-1])
         return self.arenas[-1]
 
 
@@ -206,7 +210,7 @@ class ChunkRawRecords(object):
         if self.channels is not None:
             self.truth_dtype = optical_extra_dtype + self.truth_dtype
         self.seed = int(seed if seed is not None else (config.get('seed') or 0))
-        self._arena_pool = _ArenaPool()
+        self._arena_pool = _ArenaPool(pin=getattr(self.simulator, 'pin', None))
         self._finished = False
         self.chunk_time_pre = self.chunk_time = 0
 
