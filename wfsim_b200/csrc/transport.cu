@@ -64,15 +64,24 @@ void SplitControl::init(int expand_threads) {
     }
     if (fixed) { fixed = false; permille = -1; }
     if (permille.load() >= 0) return;
-    // first guess: E = what the expansion threads write (GB/s of records), P = the link, c = compact / plain bytes;
-    // both sides finish together at f = (1/E - c/P) / ((1 - c)/P + 1/E)
-    const double E = 6.0 * std::max(1, expand_threads), P = 50.0, c = 0.28;
+    frozen = false;
+    // Measured on the B200 boxes of this pool (profiles/r2w_split_transport.md): one expansion thread writes
+    // ~9.8 GB/s of records, eight or more reach what the host memory takes (~80 GB/s) and plain rows on top of
+    // that gain nothing; the link moves P = 47 GB/s; compact / plain bytes c = 0.28 for single-photon records.
+    // Few threads (several ranks sharing the cores of one box): both sides finish together at
+    // f = (1/E - c/P) / ((1 - c)/P + 1/E), then the feedback below takes over.
+    if (expand_threads >= 8) {
+        frozen = true;
+        permille = 0;
+        return;
+    }
+    const double E = 9.8 * std::max(1, expand_threads), P = 47.0, c = 0.28;
     const double f = (1.0 / E - c / P) / ((1.0 - c) / P + 1.0 / E);
     permille = (int)std::max(0.0, std::min(950.0, f * 1000.0));
 }
 
 void SplitControl::feedback(int64_t t_ship, int64_t t_plain_done, int64_t t_expand_done) {
-    if (fixed) return;
+    if (fixed || frozen) return;
     const double dp = (double)(t_plain_done - t_ship), de = (double)(t_expand_done - t_ship);
     const double span = std::max(std::max(dp, de), 1.0);
     const double err = (de - dp) / span;                  // > 0: the expansion finished last -> more plain rows

@@ -47,6 +47,7 @@ struct TransportStats {          // wall clock, summed over the batches of one c
 struct SplitControl {
     std::atomic<int> permille{-1};        // share of plain rows; -1: not initialised
     bool fixed = false;                   // WFS_PLAIN_FRACTION given
+    bool frozen = false;                  // enough expansion threads: everything compact, no feedback
     void init(int expand_threads);
     double fraction() const { return std::max(0, permille.load()) * 1e-3; }
     // t_*: steady-clock ns; expansion / DMA of one batch finished
