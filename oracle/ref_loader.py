@@ -21,7 +21,17 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get('WFSIM_REFERENCE_ROOT', '/root/reference')
+def _reference_root():
+    # the checkout in the build container; on the GPU box the modules staged by oracle/make_ref.sh (git-ignored)
+    env = os.environ.get('WFSIM_REFERENCE_ROOT')
+    if env:
+        return env
+    if os.path.isfile('/root/reference/wfsim/core/pulse.py'):
+        return '/root/reference'
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')
+
+
+REFERENCE_ROOT = _reference_root()
 
 N_TPC_PMTS = 494      # straxen.n_tpc_pmts
 N_TOP_PMTS = 253      # straxen.n_top_pmts
