@@ -24,8 +24,11 @@ def make_groups(seed, n_groups, mean_gap_s):
 
 def main(ref, c0_config):
     cases = {}
-    for name, seed, n_groups, gap, chunk_size in [('sparse', 1, 40, 0.8, 2), ('dense', 2, 60, 0.05, 1),
-                                                  ('long_chunks', 3, 25, 1.5, 10)]:
+    # the last two: a record buffer smaller than a chunk's records (strax_interface.py:409-422 -- the class
+    # allocates 5e6 records; a short buffer reaches the same branch with few groups)
+    for name, seed, n_groups, gap, chunk_size, buffer_length in [
+            ('sparse', 1, 40, 0.8, 2, None), ('dense', 2, 60, 0.05, 1, None), ('long_chunks', 3, 25, 1.5, 10, None),
+            ('buffer_overflow_dense', 4, 80, 0.05, 1, 60), ('buffer_overflow_long', 5, 50, 0.4, 10, 36)]:
         cfg, _, _ = c0_config()
         cfg['chunk_size'] = chunk_size
         groups = make_groups(seed, n_groups, gap)
@@ -45,13 +48,15 @@ def main(ref, c0_config):
                 self.source_finished = True
 
         crr = ref.ChunkRawRecords(cfg, rawdata_generator=Replay)
+        if buffer_length is not None:
+            crr.record_buffer = crr.record_buffer[:buffer_length]
         inst = np.zeros(1, dtype=ref.strax_interface.instruction_dtype)
         inst['time'] = groups[0][0] * 10 + 600
         bounds, counts = [], []
         for res in crr(inst):
             bounds.append((int(crr.chunk_time_pre), int(crr.chunk_time)))
             counts.append(len(res['raw_records']))
-        cases[name] = dict(chunk_size=chunk_size, t_min_instruction=int(inst['time'][0]),
+        cases[name] = dict(chunk_size=chunk_size, t_min_instruction=int(inst['time'][0]), record_buffer=buffer_length,
                            groups=groups, bounds=bounds, records_per_chunk=counts)
         print(name, len(bounds), 'chunks', sum(counts), 'records')
     with open(os.path.join(HERE, 'chunks.json'), 'w') as f:

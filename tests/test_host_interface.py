@@ -21,9 +21,12 @@ def test_chunk_boundaries_match_reference():
         cfg = load_c0_config()
         cfg['chunk_size'] = c['chunk_size']
         groups = [tuple(g) for g in c['groups']]
-        got = chunk_boundaries(cfg, c['t_min_instruction'], groups)
+        n_records = [2 * g[2] for g in groups]          # 120 samples per interval -> 2 records
+        got = chunk_boundaries(cfg, c['t_min_instruction'], groups, n_records=n_records, record_buffer=c.get('record_buffer'))
         assert [list(b) for b in got] == c['bounds'], name
-        assert oracle_cb(cfg, c['t_min_instruction'], groups) == got
+        if not c.get('record_buffer'):
+            assert oracle_cb(cfg, c['t_min_instruction'], groups) == got
+            assert chunk_boundaries(cfg, c['t_min_instruction'], groups) == got      # 5e6 records are never reached here
         # records per chunk: an interval's record belongs to the first chunk whose end >= its time
         times = []
         for left, right, n in groups:
@@ -167,10 +170,10 @@ def test_chunk_clock_fed_in_pieces_with_peek_gives_the_reference_bounds():
         for trial in range(20):
             cuts = sorted(set(rng.integers(1, max(len(groups), 2), rng.integers(0, 6)).tolist()))
             pieces = [groups[a:b] for a, b in zip([0] + cuts, cuts + [len(groups)])]
-            clock = ChunkClock(cfg, c['t_min_instruction'])
+            clock = ChunkClock(cfg, c['t_min_instruction'], record_buffer=c.get('record_buffer'))
             got = []
             for k, piece in enumerate(pieces):
-                got += clock.feed(piece)
+                got += clock.feed(piece, [2 * g[2] for g in piece])
                 if k + 1 < len(pieces) and pieces[k + 1]:
                     # the next piece starts at its first group's left edge; any earlier time is a valid bound
                     t_next = pieces[k + 1][0][0] * cfg['sample_duration'] - int(rng.integers(0, 50000))

@@ -59,18 +59,25 @@ class ChunkClock:
     reads from RawData.left / RawData.right while iterating the ZLE intervals -- and returns the
     chunks [(chunk_time_pre, chunk_time), ...] that became complete; `finish()` returns the last one."""
 
-    def __init__(self, config, t_min_instruction, time_zero=None):
+    RECORD_BUFFER = 5000000      # records the reference's chunker holds (strax_interface.py:360)
+
+    def __init__(self, config, t_min_instruction, time_zero=None, record_buffer=None):
         self.dt = config['sample_duration']
         self.rext = int(config['right_raw_extension'])
         self.cksz = int(config['chunk_size'] * 1e9)
         self.pre = (time_zero - self.rext) if time_zero else (int(t_min_instruction) - self.rext)
         self.ct = self.pre + self.cksz
         self.cur_right = self.last_right = 0
+        self.buffer_length = int(record_buffer or self.RECORD_BUFFER)
+        self.blevel = 0              # records held since the last chunk left (the reference's buffer level)
 
-    def feed(self, groups):
+    def feed(self, groups, n_records=None):
+        """`n_records`: records per group (all data types).  With it the record-buffer rule of
+        strax_interface.py:409-418 applies: a group that does not fit behind the records held closes the chunk
+        at the end of the previous group, whatever the chunk clock says."""
         out = []
         dt, rext = self.dt, self.rext
-        for left, right, n_itv in groups:
+        for g, (left, right, n_itv) in enumerate(groups):
             for _ in range(max(int(n_itv), 0)):
                 if right != self.cur_right:
                     self.last_right, self.cur_right = self.cur_right, right
@@ -80,8 +87,25 @@ class ChunkClock:
                     out.append((self.pre, self.ct))
                     self.pre = self.ct
                     self.ct += self.cksz
+                    self.blevel = 0      # every record of the earlier groups has left
                 else:
                     break
+            if n_records is not None and int(n_itv) > 0:
+                n = int(n_records[g])
+                if self.blevel + n > self.buffer_length:
+                    log.warning('Chunck size too large, insufficient record buffer \n'
+                                'No longer in sync if simulating nVeto with TPC \n'
+                                'Consider reducing the chunk size')
+                    self.ct = (self.last_right + 1) * dt
+                    out.append((self.pre, self.ct))
+                    self.pre = self.ct
+                    self.ct += self.cksz
+                    self.blevel = 0
+                    if n > self.buffer_length:
+                        # strax_interface.py:420-422 drops the pulses that do not fit ("skipping pulse"); a group
+                        # of more than 5e6 records is not simulated here either way
+                        raise ValueError('Pulse length too large, insufficient record buffer')
+                self.blevel += n
         return out
 
     def peek(self, t_next):
@@ -95,6 +119,7 @@ class ChunkClock:
         out = [(self.pre, self.ct)]
         self.pre = self.ct
         self.ct += self.cksz
+        self.blevel = 0
         return out
 
     def finish(self):
@@ -103,11 +128,11 @@ class ChunkClock:
         return (self.pre, self.ct)
 
 
-def chunk_boundaries(config, t_min_instruction, groups, time_zero=None):
+def chunk_boundaries(config, t_min_instruction, groups, time_zero=None, n_records=None, record_buffer=None):
     """All chunks of one run: [(chunk_time_pre, chunk_time), ...] in the order the reference yields
     them (see ChunkClock)."""
-    clock = ChunkClock(config, t_min_instruction, time_zero)
-    out = clock.feed(groups)
+    clock = ChunkClock(config, t_min_instruction, time_zero, record_buffer=record_buffer)
+    out = clock.feed(groups, n_records)
     out.append(clock.finish())
     return out
 
@@ -230,7 +255,7 @@ class ChunkRawRecords(object):
         # pieces are cut at the gaps the library itself cuts its device batches at (wfs_quiet_gap)
         quiet = self.simulator.quiet_gap() if hasattr(self.simulator, 'quiet_gap') else None
         parts = _pieces(instructions, cfg, piece, time_zero, min_gap=quiet)
-        clock = ChunkClock(cfg, np.min(instructions['time']), time_zero)
+        clock = ChunkClock(cfg, np.min(instructions['time']), time_zero, record_buffer=cfg.get('b200_record_buffer'))
         keys = ('raw_records', 'raw_records_he', 'raw_records_aqmon')
         side = {k: [] for k in keys[1:]}    # he / aqmon records not yet delivered (few): arrays in time order
         tdt = np.dtype(instruction_dtype + self.truth_dtype)
@@ -328,7 +353,18 @@ class ChunkRawRecords(object):
                 side[k].append(np.asarray(out[k]))
             held_truth = out['truth'] if held_truth is None or not len(held_truth) \
                 else np.concatenate([held_truth, out['truth']])
-            done = clock.feed(out['groups'])
+            # records per digitisation group (all data types), for the record-buffer rule of the chunk clock
+            g = out['groups']
+            n_rec_group = np.zeros(len(g), np.int64)
+            if len(g):
+                lo, hi = g['left'] * cfg['sample_duration'], (g['right'] + 1) * cfg['sample_duration']
+                for k in keys:
+                    t_k = np.asarray(out[k]['time']) if k != 'raw_records' else rr['time']
+                    if len(t_k):
+                        if len(t_k) > 1 and (np.diff(t_k) < 0).any():
+                            t_k = np.sort(t_k)
+                        n_rec_group += np.searchsorted(t_k, hi, side='left') - np.searchsorted(t_k, lo, side='left')
+            done = clock.feed(g, n_rec_group)
             if i_part + 1 < len(parts) and n_groups:
                 # nothing of the next piece can start before its first signal time minus the longest
                 # backward reach of a pulse (left margin, trigger window, diffusion of the drift)
