@@ -110,8 +110,11 @@ def _install_stubs(resource_hook=None):
     strax_utils = types.ModuleType('strax.utils')
 
     class _NoBar:
-        def __init__(self, *a, **k):
-            pass
+        def __init__(self, iterable=None, *a, **k):
+            self._it = iterable
+
+        def __iter__(self):
+            return iter(self._it)
 
         def update(self, *a):
             pass

@@ -246,6 +246,37 @@ def test_plugin_compute_loop_and_chunks():
         p2.check_instructions()
 
 
+def test_plugin_generates_its_own_instructions():
+    """RawRecordsFromFaxNT without injected instructions and without a fax_file: rand_instructions
+    (strax_interface.py:119-135, 680) supplies them -- event_rate x chunk_size x n_chunk events -- and the
+    reference's assertions on them (:682-693) hold."""
+    import json as _json
+    from wfsim_b200.strax_interface import RawRecordsFromFaxNT
+    uniq, row = spe()
+    with open(os.path.join(GOLDEN, 'c0_config.json')) as f:
+        cfg_fax = _json.load(f)
+    plugin = RawRecordsFromFaxNT(config=dict(fax_config=cfg_fax, gain_model_mc=np.full(494, 0.008),
+                                             chunk_size=1, n_chunk=2, event_rate=3, seed=77))
+    plugin.resource_overrides = dict(spe_ppf=uniq, spe_row=row)
+    plugin.setup()
+    inst = plugin.instructions
+    assert len(inst) == 2 * 3 * 1 * 2 and set(inst['type']) == {1, 2}
+    assert (np.hypot(inst['x'], inst['y']) < plugin.config['tpc_radius']).all()
+    chunks = []
+    for i in range(50):
+        if not plugin.is_ready(i):
+            if plugin.source_finished():
+                break
+            continue
+        chunks.append(plugin.compute())
+    assert plugin.source_finished() and len(chunks) >= 2
+    tr = np.concatenate([c['truth']['data'] for c in chunks])
+    rr = np.concatenate([c['raw_records']['data'] for c in chunks])
+    assert len(tr) == len(inst) and len(rr) > 0 and np.all(np.diff(rr['time']) >= 0)
+    s1 = tr[tr['type'] == 1]
+    assert (s1['n_photon'] > 0).all() and (s1['n_photon'] < s1['amp']).all()       # binomial thinning by the dummy LCE map
+
+
 @pytest.mark.parametrize('noise,he', [(False, False), (True, False), (False, True)])
 def test_chunker_streams_the_run_piece_by_piece(noise, he):
     """ChunkRawRecords simulates the run in pieces of `b200_piece_instructions` instructions (bounded

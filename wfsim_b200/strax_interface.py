@@ -525,7 +525,9 @@ class RawRecordsFromFaxNT(SimulatorPlugin):
             assert self.config['fax_file'].endswith('csv'), 'Only csv input is supported'
             self.instructions = instruction_from_csv(self.config['fax_file'])
         elif getattr(self, 'instructions', None) is None:
-            raise RuntimeError('rand_instructions needs nestpy (third party); pass instructions or a csv fax_file')
+            # strax_interface.py:680; nestpy yields when nestpy is installed, else the fixed-yield stand-in
+            from .instructions import rand_instructions
+            self.instructions = rand_instructions(self.config, seed=self.config.get('seed') or None)
 
     def check_instructions(self):
         # Let below cathode S1 instructions pass but remove S2 instructions
