@@ -199,6 +199,12 @@ static double quiet_gap_ns(const Handle *H) {
     if (p.enable_gate_afterpulses && p.photoelectric_p > 0.0)
         quiet = std::max(quiet, (double)p.right_raw_extension + p.photoelectric_t_center + p.drift_time_gate +
                                     6.0 * p.photoelectric_t_spread + 50000.0);
+    // The reference starts a new digitisation group when the next cluster begins more than rext behind the END of
+    // the last pulse (rawdata.py:87-98), not behind its signal time: photons trail the signal time by the S2 width
+    // (diffusion, trapping, luminescence, the gate offset: 50 us covers 6 sigma at full drift several times over)
+    // and by the longest PMT-afterpulse delay of the tables.  A cut inside that reach could split a group.
+    quiet += 50000.0;
+    if (p.enable_pmt_afterpulses && H->frontend) quiet += H->frontend->ap_max_delay_ns;
     return quiet;
 }
 
@@ -1573,7 +1579,19 @@ void Handle::frontend_init(const wfs_tables &t) {
         F->ap_delay_len[e] = F->ap_amp_len[e] = F->ap_amp_rows[e] = 0;
         F->ap_delay_bin[e] = F->ap_amp_bin[e] = 0;
     }
+    F->ap_max_delay_ns = 0.0;
     for (int e = 0; e < F->n_ap; e++) {
+        if (t.ap_delay_cdf[e] && t.ap_delay_len[e] > 0) {
+            // longest delay the element can draw: the last bin of the cdf, or the upper edge of a 'Uniform' row
+            // ([t_low_bin, t_high_bin, P], afterpulse.py:192,214-215)
+            double reach = (double)t.ap_delay_len[e];
+            if (t.ap_is_uniform[e] && t.ap_delay_len[e] >= 2) {
+                reach = 0.0;
+                for (int ch = 0; ch < p.n_tpc_pmts; ch++)
+                    reach = std::max(reach, t.ap_delay_cdf[e][(size_t)ch * t.ap_delay_len[e] + 1]);
+            }
+            F->ap_max_delay_ns = std::max(F->ap_max_delay_ns, reach * t.ap_delay_bin[e]);
+        }
         F->ap_is_uniform[e] = t.ap_is_uniform[e];
         F->ap_delay_len[e] = t.ap_delay_len[e];
         F->ap_delay_bin[e] = t.ap_delay_bin[e];

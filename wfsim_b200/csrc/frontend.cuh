@@ -77,6 +77,7 @@ struct Frontend {
     double *ap_delay_cdf[WFS_MAX_AP_ELEMENTS];
     int32_t ap_delay_len[WFS_MAX_AP_ELEMENTS];
     double ap_delay_bin[WFS_MAX_AP_ELEMENTS];
+    double ap_max_delay_ns = 0.0;      // longest PMT-afterpulse delay the tables can draw (quiet_gap_ns)
     double *ap_amp_cdf[WFS_MAX_AP_ELEMENTS];
     int32_t ap_amp_len[WFS_MAX_AP_ELEMENTS], ap_amp_rows[WFS_MAX_AP_ELEMENTS];
     double ap_amp_bin[WFS_MAX_AP_ELEMENTS];

@@ -23,7 +23,10 @@ def default_quiet_gap(config):
     if config.get('enable_gate_afterpulses', False):
         extra = max(extra, int(config.get('photoelectric_t_center', 0) + config.get('drift_time_gate', 0)
                                + 6 * config.get('photoelectric_t_spread', 0)) + 50000)
-    return gap + extra
+    # photons trail the signal time by the S2 width and the PMT-afterpulse delays (the library reads the longest
+    # delay from the afterpulse tables; without them: 100 us)
+    reach = 50000 + (100000 if config.get('enable_pmt_afterpulses', False) else 0)
+    return gap + extra + reach
 
 
 def shard_instructions(instructions, n_shards, config, min_gap=None):
