@@ -903,76 +903,84 @@ k_group_analyse(FusedArgs A, FusedClass K) {
     }
 }
 
-// Records of a group, a tile of consecutive records at a time, assembled in shared memory and streamed out with
-// aligned 16-byte stores: baseline fill, then headers, zero padding behind the pulse, and -- one thread per
-// (record, photon that reaches it) -- the ADC values of the samples that photon owns inside the record, as
-// k_group_analyse left them.  No arithmetic on samples here: the kernel is a gather.
-constexpr int kTileRecs = 64, kTileWords = kTileRecs * 61 + 8;
+// Records of a group, a tile of 16 consecutive records at a time, one WARP per tile: assembled in the warp's own
+// slice of shared memory and streamed out with aligned 16-byte stores -- baseline fill, then headers and zero
+// padding behind the pulse (one lane per record), and, one lane per (record, photon that reaches it), the ADC
+// values of the samples that photon owns inside the record, as k_group_analyse left them.  No arithmetic on samples
+// here: the kernel is a gather.  Warps never wait for each other (no CTA barrier): the dependent loads of one
+// tile (descriptor -> photon word -> slot) overlap with the stores of the others.
+constexpr int kTileRecs = 16, kTileWords = kTileRecs * 61 + 8, kRecordWarps = kFusedRecordThreads / 32;
 
 __global__ void __launch_bounds__(kFusedRecordThreads)
 k_group_records(FusedArgs A) {
-    __shared__ __align__(16) uint32_t s_tile[kTileWords];
-    __shared__ uint4 s_desc[kTileRecs];
-    __shared__ int s_pref[kTileRecs + 1];
+    __shared__ __align__(16) uint32_t s_tile_all[kRecordWarps][kTileWords];
+    __shared__ uint4 s_desc_all[kRecordWarps][kTileRecs];
+    __shared__ int s_pref_all[kRecordWarps][kTileRecs + 1];
     const PhotonBatch &b = A.b;
     const DeviceConfig &c = A.c;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
-    const int dt = c.p.dt, tlen = c.p.template_length;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int dt = c.p.dt;
     const int baseline = c.p.baseline;
     const int key_bias = c.p.pulse_left_margin + c.p.trigger_window + 2;
     const uint32_t fill = (uint32_t)(uint16_t)(int16_t)max(baseline, 0), fill2 = fill | (fill << 16);
     constexpr int SPR = WFS_SAMPLES_PER_RECORD;
+    uint32_t *s_tile = s_tile_all[warp];
+    uint4 *s_desc = s_desc_all[warp];
+    int *s_pref = s_pref_all[warp];
     uint16_t *s_tile16 = reinterpret_cast<uint16_t *>(s_tile);
     for (int g = blockIdx.x; g < (int)b.n_groups; g += gridDim.x) {
         const uint32_t n_rec = A.group_nrec[g], desc_off = A.group_desc[g];
         if (n_rec == 0 || desc_off == 0xffffffffu) continue;
+        const uint32_t first_tile = (blockIdx.y * kRecordWarps + warp) * kTileRecs;
+        if (first_tile >= n_rec) continue;
         const int64_t rec_base = (int64_t)A.rec_base[g];
         const int64_t origin_q = floordiv64(A.group_t0[g], dt);
-        uint32_t pbase = 0, n_g = 0;
+        uint32_t pbase = 0;
         for (int r = 0; r < b.group_ranges; r++) {
             const uint32_t *gs = b.group_start + (size_t)r * (b.n_groups + 1);
             pbase += gs[g] - gs[0];
-            n_g += gs[g + 1] - gs[g];
         }
         const uint32_t *tkey = A.tkey + pbase;
         const uint4 *adc = A.adc_slots + (size_t)pbase * kSlotVecs;
-        for (uint32_t t0 = blockIdx.y * kTileRecs; t0 < n_rec; t0 += gridDim.y * kTileRecs) {
+        const uint32_t tile_step = gridDim.y * kRecordWarps * kTileRecs;
+        uint4 d_next = make_uint4(0u, 0u, 0u, 0u);
+        if (first_tile + lane < n_rec && lane < kTileRecs) d_next = A.desc[(size_t)desc_off + first_tile + lane];
+        for (uint32_t t0 = first_tile; t0 < n_rec; t0 += tile_step) {
             const int64_t dest0 = rec_base + t0;
             const int nr = (int)min((int64_t)min(n_rec - t0, (uint32_t)kTileRecs), A.cap_records - dest0);
             if (nr <= 0) break;
+            uint4 d = d_next;                             // this tile's descriptors, loaded while the previous tile was assembled
+            if (t0 + tile_step + lane < n_rec && lane < kTileRecs) d_next = A.desc[(size_t)desc_off + t0 + tile_step + lane];
             const int hw = (int)(((uint64_t)dest0 * WFS_RECORD_BYTES) & 15u) >> 2;      // words in front of the tile in its first 16-byte vector
             const int n_words = nr * 61, n_vec = (hw + n_words + 3) >> 2;
-            __syncthreads();                              // the previous tile has left
-            if (tid < nr) s_desc[tid] = A.desc[(size_t)desc_off + t0 + tid];
+            __syncwarp();                                 // the previous tile has left
+            if (lane < nr) s_desc[lane] = d;
+            else d = make_uint4(0u, 0u, 0u, 0u);
             {
                 uint4 *v = reinterpret_cast<uint4 *>(s_tile);
                 const uint4 f4 = make_uint4(fill2, fill2, fill2, fill2);
-                for (int i = tid; i < n_vec; i += nthr) v[i] = f4;
+                for (int i = lane; i < n_vec; i += 32) v[i] = f4;
             }
-            __syncthreads();
-            // photons that reach every record: prefix over the tile (warp 0); headers and zero padding (the others)
-            if (warp == 0) {
-                const int n0 = lane < nr ? (int)((s_desc[lane].z >> 13) & 16383u) : 0;
-                const int n1 = lane + 32 < nr ? (int)((s_desc[lane + 32].z >> 13) & 16383u) : 0;
-                int i0 = n0, i1 = n1;
+            // photons that reach every record: prefix over the tile
+            {
+                const int n0 = lane < nr ? (int)((d.z >> 13) & 16383u) : 0;
+                int i0 = n0;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int u0 = __shfl_up_sync(0xffffffffu, i0, o), u1 = __shfl_up_sync(0xffffffffu, i1, o);
-                    if (lane >= o) { i0 += u0; i1 += u1; }
+                for (int o = 1; o < kTileRecs; o <<= 1) {
+                    const int u0 = __shfl_up_sync(0xffffffffu, i0, o);
+                    if (lane >= o) i0 += u0;
                 }
-                const int tot0 = __shfl_sync(0xffffffffu, i0, 31);
-                s_pref[lane] = i0 - n0;
-                s_pref[lane + 32] = tot0 + i1 - n1;
-                if (lane == 31) s_pref[64] = tot0 + i1;
+                if (lane < kTileRecs) s_pref[lane] = i0 - n0;
+                if (lane == kTileRecs - 1) s_pref[kTileRecs] = i0;
             }
-            for (int r = tid; r < nr; r += nthr) {
+            __syncwarp();
+            if (lane < nr) {
                 // strax_interface.py:425-436: time, length, dt, channel, pulse_length, record_i, baseline = 0
-                const uint4 d = s_desc[r];
                 const int ch = (int)(d.x & 1023u), plen = (int)(d.y & 0xfffffu);
                 const int rec_i = (int)(((d.y >> 20) & 0xfffu) | (((d.z >> 27) & 3u) << 12));
                 const int64_t time = (int64_t)dt * (origin_q + (int)(d.x >> 10) - key_bias);
                 const int length = min(plen - rec_i * SPR, SPR);
-                uint32_t *h = s_tile + hw + r * 61;
+                uint32_t *h = s_tile + hw + lane * 61;
                 h[0] = (uint32_t)(uint64_t)time;
                 h[1] = (uint32_t)((uint64_t)time >> 32);
                 h[2] = (uint32_t)length;
@@ -985,50 +993,47 @@ k_group_records(FusedArgs A) {
                     for (int wd = (length + 1) >> 1; wd < SPR / 2; wd++) h[6 + wd] = 0u;
                 }
             }
-            __syncthreads();
-            const int n_pairs = s_pref[nr];
-            for (int q = tid; q < n_pairs; q += nthr) {
+            __syncwarp();
+            const int n_pairs = s_pref[kTileRecs];
+            for (int q = lane; q < n_pairs; q += 32) {
                 int r = 0;                                  // the record of pair q: last r with s_pref[r] <= q
 #pragma unroll
-                for (int o = 32; o > 0; o >>= 1)
+                for (int o = kTileRecs >> 1; o > 0; o >>= 1)
                     if (r + o < nr && s_pref[r + o] <= q) r += o;
-                const uint4 d = s_desc[r];
-                const int ka = (int)(d.z & 8191u), kend = ka + (int)((d.z >> 13) & 16383u);
+                const uint4 dd = s_desc[r];
+                const int ka = (int)(dd.z & 8191u);
                 const int k = ka + (q - s_pref[r]);
+                // the photon word and its whole slot at once: neither address depends on the other load
+                const uint4 *slot = adc + (size_t)k * kSlotVecs;
                 const uint32_t tk = __ldg(tkey + k);
+                const uint4 q0 = __ldg(slot), q1 = __ldg(slot + 1), q2 = __ldg(slot + 2), q3 = __ldg(slot + 3);
                 const int n_own = (int)(tk >> 27);
                 if (n_own == 0) continue;                   // its gain went to the first photon of the same ns
-                const int plen = (int)(d.y & 0xfffffu);
-                const int rec_i = (int)(((d.y >> 20) & 0xfffu) | (((d.z >> 27) & 3u) << 12));
-                const int first = (int)(d.x >> 10) - key_bias;              // relative to origin_q
+                const int plen = (int)(dd.y & 0xfffffu);
+                const int rec_i = (int)(((dd.y >> 20) & 0xfffu) | (((dd.z >> 27) & 3u) << 12));
+                const int first = (int)(dd.x >> 10) - key_bias;              // relative to origin_q
                 const int length = min(plen - rec_i * SPR, SPR);
                 const int T = (int)((tk >> 4) & 0xfffffu);
                 uint16_t *rec16 = s_tile16 + 2 * (hw + r * 61 + 6);
                 const int j0 = max(0, first - T), j1 = min(n_own, first + length - T);
                 if (j0 >= j1) continue;
                 uint16_t *dst = rec16 + (T - first);
-                const uint4 *slot = adc + (size_t)k * kSlotVecs;
-                for (int v = j0 >> 3; v <= (j1 - 1) >> 3; v++) {
-                    const uint4 q4 = __ldg(slot + v);
-                    const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
+                const uint32_t w[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
 #pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const int j = 8 * v + u;
-                        if (j >= j0 && j < j1) dst[j] = (uint16_t)(w[u >> 1] >> (16 * (u & 1)));
-                    }
-                }
+                for (int j = 0; j < 8 * kSlotVecs; j++)
+                    if (j >= j0 && j < j1) dst[j] = (uint16_t)(w[j >> 1] >> (16 * (j & 1)));
             }
-            __syncthreads();
+            __syncwarp();
             // whole 16-byte vectors to their final place, single words at the ragged ends
             {
                 uint32_t *out_w = reinterpret_cast<uint32_t *>(A.records_out) + dest0 * 61 - hw;      // word 0 of the tile's first vector
                 const int v0 = hw ? 1 : 0, v1 = (hw + n_words) >> 2;
                 const uint4 *sv = reinterpret_cast<const uint4 *>(s_tile);
                 uint4 *ov = reinterpret_cast<uint4 *>(out_w);
-                for (int i = v0 + tid; i < v1; i += nthr) ov[i] = sv[i];
-                if (hw && tid >= hw && tid < 4 && tid < hw + n_words) out_w[tid] = s_tile[tid];
-                const int wt = tid + 4 * v1;
-                if (v1 >= v0 && tid < 4 && wt < hw + n_words && wt >= hw) out_w[wt] = s_tile[wt];
+                for (int i = v0 + lane; i < v1; i += 32) ov[i] = sv[i];
+                if (hw && lane >= hw && lane < 4 && lane < hw + n_words) out_w[lane] = s_tile[lane];
+                const int wt = lane + 4 * v1;
+                if (v1 >= v0 && lane < 4 && wt < hw + n_words && wt >= hw) out_w[wt] = s_tile[wt];
             }
         }
     }
@@ -1152,7 +1157,7 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
     auto records = [&]() {
         if (!want) return;
         prim_.exclusive_scan_u32(d_nrec, d_base, ng, true);
-        k_group_records<<<dim3((unsigned)ng, 4), kFusedRecordThreads, 0, stream_>>>(A);
+        k_group_records<<<dim3((unsigned)ng, 2), kFusedRecordThreads, 0, stream_>>>(A);
         lc_->n++;
     };
     auto read_scalars = [&]() {

@@ -11,7 +11,7 @@ constexpr int kFusedBins = 1024;            // time bins of the record order
 constexpr int kFusedTrigSlots = 64;         // (pulse call, total / bottom) trigger counters kept in shared memory
 
 constexpr int kFusedMaxClasses = 6;         // groups are binned by photon count
-constexpr int kFusedRecordThreads = 128;
+constexpr int kFusedRecordThreads = 256;
 
 enum FusedScalar { FS_NVALID = 0, FS_NPULSES, FS_NWIN, FS_NITV, FS_NSAMPLES, FS_NREC, FS_ERR, FS_OVERFLOW, FS_COUNT };
 
