@@ -13,7 +13,7 @@ Workloads (synthetic instructions from tests/golden/synth_
   C3  mixed stream (95 % C1-like, 5 % C2-like), noise + ZLE, cut into 8 chunks in time: chunk k runs on rank
       k mod N (strong scaling; no collective), chunk after chunk into one recycled page-locked record arena.
   C4  pulse-superposition microbench: pulses of 1e6 photons over 494 channels through wfs_simulate_photons,
-      template sweep (22 / 44 / 88 taps per ns shift); metric photons/s.
+      template sweep (11 / 22 / 32 samples per template; longer ones are refused by the library); metric photons/s.
 One step = one pass of the whole path over the workload.  The default run also carries bounded samples of
 C2, C3 and C4 in `configs` (rank 0, N = 1 only).
 
@@ -608,16 +608,20 @@ def run_c3(args, D, rank, local_rank, n_events, clocks=True, n_chunks=8):
     return line
 
 
-def stretched_templates(cfg, factor):
-    """The shipped single-pe pulse shape sampled `factor` times longer (22 -> 44 -> 88 taps per ns shift)."""
-    if factor == 1:
+def stretched_templates(cfg, taps):
+    """The shipped single-pe pulse shape stretched in time to `taps` = (samples before, samples after the pulse centre)
+    (pulse.py:146-187: the template spans before + after samples; shipped: 2 + 20)."""
+    before, after = taps
+    if (before, after) == (2, 20):
         return cfg
     cfg = dict(cfg)
-    cfg['pe_pulse_ts'] = (np.asarray(cfg['pe_pulse_ts'], float) * factor).tolist()
+    cfg['pe_pulse_ts'] = (np.asarray(cfg['pe_pulse_ts'], float) * (before + after) / 22.0).tolist()
+    cfg['samples_before_pulse_center'], cfg['samples_after_pulse_center'] = before, after
     return cfg
 
 
-def run_c4(args, D, rank, local_rank, n_pulses, per_pulse=1_000_000, pulses_per_call=50, taps=(1, 2, 4)):
+def run_c4(args, D, rank, local_rank, n_pulses, per_pulse=1_000_000, pulses_per_call=50,
+           taps=((2, 20), (1, 10), (3, 29), (4, 40))):
     """Photons generated on the device (torch: plumbing for the synthetic input), pulses split over the ranks
     (weak: every rank its own `n_pulses`).  value: photons/s with the photons resident (on_device call, CUDA-event
     time of the call); e2e: the same call with host arrays in and a host record buffer out."""
@@ -630,12 +634,13 @@ def run_c4(args, D, rank, local_rank, n_pulses, per_pulse=1_000_000, pulses_per_
     peak, peak_src = measured_peak()
     dev = torch.device('cuda', local_rank)
     results = {}
-    for factor in taps:
-        cfg = stretched_templates(base, factor)
+    for tp in taps:
+        factor = sum(tp)
+        cfg = stretched_templates(base, tp)
         try:
             sim = Simulator(cfg, device=local_rank)
-        except Exception as e:      # a template the kernels do not take
-            results[f'taps_x{factor}'] = {'error': str(e)[:200]}
+        except Exception as e:      # the library takes templates of up to 32 samples (k_digitize's owner layers): 44 is refused
+            results[f'taps_{factor}'] = {'error': str(e)[:200]}
             continue
         gains = torch.tensor(np.asarray(cfg['gains'], np.float64), device=dev)
         K = min(pulses_per_call, n_pulses)
@@ -702,8 +707,8 @@ def run_c4(args, D, rank, local_rank, n_pulses, per_pulse=1_000_000, pulses_per_
             n_ph_all, launches_all = D.reduce([n * n_calls * args.steps, launches])
             byt = PHOTON_BYTES * n * n_calls + 2 * nsamp * n_calls          # photons in, int16 window samples out
             s_digi = ms_digi / args.steps / 1e3
-            results[f'taps_x{factor}'] = {
-                'template_taps': int(22 * factor), 'photons_per_s': n_ph_all / t_dev, 'ms_per_step': t_dev / args.steps * 1e3,
+            results[f'taps_{factor}'] = {
+                'template_taps': int(sim.params.template_length), 'photons_per_s': n_ph_all / t_dev, 'ms_per_step': t_dev / args.steps * 1e3,
                 'e2e_photons_per_s': n_ph_all / t_e2e, 'e2e_ms_per_step': t_e2e / args.steps * 1e3,
                 'h2d_bytes_per_step': int(PHOTON_BYTES * n * n_calls), 'd2h_bytes_per_step': d2h_bytes,
                 'records_per_call': int(nrec), 'window_samples_per_call': int(nsamp), 'gpu_launches': int(launches_all),
@@ -714,11 +719,11 @@ def run_c4(args, D, rank, local_rank, n_pulses, per_pulse=1_000_000, pulses_per_
                                'frac': byt / s_digi / 1e9 / peak if s_digi > 0 else None}}
             del batches, rec_host
         except Exception as e:
-            results[f'taps_x{factor}'] = {'error': f'{type(e).__name__}: {str(e)[:200]}'}
+            results[f'taps_{factor}'] = {'error': f'{type(e).__name__}: {str(e)[:200]}'}
         del d_rec
         sim.close()
         torch.cuda.empty_cache()
-    first = results.get('taps_x1', {})
+    first = results.get('taps_22', {})
     line = {
         'metric': 'photons_per_s', 'value': first.get('photons_per_s'), 'unit': 'photons/s', 'n_gpus': D.world,
         'steps': args.steps, 'warmup': max(args.warmup, 1), 'ms_per_step': first.get('ms_per_step'), 'higher_is_better': True,

@@ -15,7 +15,7 @@ static bool blocking_sync_mode() {
     // (8 ranks on 32 cores: 3 spinning lanes would take 3 of the 4 cores of a rank)
     if (const char *e = getenv("WFS_BLOCKING_SYNC")) return atoi(e) != 0;
     const char *l = getenv("WFS_LANES");
-    const int lanes = l ? std::max(1, atoi(l)) : 3;
+    const int lanes = l ? std::max(1, atoi(l)) : default_lanes();
     return 2 * lanes > host_cores_per_rank();
 }
 
@@ -178,7 +178,7 @@ __device__ __forceinline__ unsigned match_digit8(uint32_t d, unsigned valid) {
 
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortIPT = 8;
+constexpr int kSortIPT = 12;
 constexpr int kSortTile = kSortThreads * kSortIPT;
 
 __global__ void __launch_bounds__(kSortThreads)
@@ -202,62 +202,90 @@ k_radix_upsweep(const uint64_t *__restrict__ keys, uint32_t *__restrict__ hist, 
     hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
+// Downsweep of one pass: the tile's items are ranked by digit (stable: warp-striped item order, match-based
+// ranking inside a warp, warps in order), laid out in shared memory in digit order, and written from there, so
+// that consecutive threads write consecutive addresses of a digit's run (a tile of 4096 items holds 16 items per
+// digit on average: 128-byte runs of keys instead of the single 8-byte writes of a direct scatter).
 __global__ void __launch_bounds__(kSortThreads)
 k_radix_downsweep(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                   uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                   const uint32_t *__restrict__ hist_scanned, int64_t n, int shift, int nblocks) {
+    __shared__ uint64_t s_key[kSortTile];
+    __shared__ uint32_t s_val[kSortTile];
     __shared__ uint32_t wcount[kSortWarps][256];
-    __shared__ uint32_t gbase[256];
+    __shared__ uint32_t dstart[256];       // first position of digit d in the tile's digit order
+    __shared__ int32_t gdelta[256];        // global position of the digit's first item minus dstart
+    __shared__ uint32_t s_wtot[kSortWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&wcount[0][0])[i] = 0;
     __syncthreads();
-    int64_t chunk = (int64_t)blockIdx.x * kSortTile + (int64_t)warp * 32 * kSortIPT;
+    const int64_t tile0 = (int64_t)blockIdx.x * kSortTile;
+    const int64_t chunk = tile0 + (int64_t)warp * 32 * kSortIPT;
     uint64_t key[kSortIPT];
-    uint32_t val[kSortIPT];
-    uint32_t rank[kSortIPT];
+    uint16_t rank[kSortIPT];
 #pragma unroll
     for (int k = 0; k < kSortIPT; k++) {
-        int64_t i = chunk + k * 32 + lane;
-        bool valid = i < n;
-        key[k] = valid ? keys_in[i] : ~0ull;
-        val[k] = valid ? vals_in[i] : 0u;
+        const int64_t i = chunk + k * 32 + lane;
+        key[k] = i < n ? keys_in[i] : ~0ull;
     }
 #pragma unroll
     for (int k = 0; k < kSortIPT; k++) {
-        int64_t i = chunk + k * 32 + lane;
-        bool valid = i < n;
-        uint32_t d = (uint32_t)((key[k] >> shift) & 255u);
-        unsigned vm = __ballot_sync(0xffffffffu, valid);
-        unsigned m = match_digit8(d, vm);
-        uint32_t r = __popc(m & ((1u << lane) - 1u));
-        uint32_t old = valid ? wcount[warp][d] : 0u;
+        const int64_t i = chunk + k * 32 + lane;
+        const bool valid = i < n;
+        const uint32_t d = (uint32_t)((key[k] >> shift) & 255u);
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
+        const unsigned m = match_digit8(d, vm);
+        const uint32_t r = __popc(m & ((1u << lane) - 1u));
+        const uint32_t old = valid ? wcount[warp][d] : 0u;
         __syncwarp();
         if (valid && r == 0) wcount[warp][d] = old + __popc(m);
         __syncwarp();
-        rank[k] = old + r;
+        rank[k] = (uint16_t)(old + r);
     }
     __syncthreads();
     {
+        // per digit: exclusive offsets of the warps, the digit's count; then an exclusive scan over the digits
         const int d = threadIdx.x;
         uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < kSortWarps; w++) {
-            uint32_t c = wcount[w][d];
+            const uint32_t c = wcount[w][d];
             wcount[w][d] = run;
             run += c;
         }
-        gbase[d] = hist_scanned[(int64_t)d * nblocks + blockIdx.x];
+        uint32_t inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) s_wtot[warp] = inc;
+        __syncthreads();
+        uint32_t base = 0;
+        for (int w = 0; w < warp; w++) base += s_wtot[w];
+        const uint32_t start = base + inc - run;
+        dstart[d] = start;
+        gdelta[d] = (int32_t)(hist_scanned[(int64_t)d * nblocks + blockIdx.x] - start);
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kSortIPT; k++) {
-        int64_t i = chunk + k * 32 + lane;
+        const int64_t i = chunk + k * 32 + lane;
         if (i < n) {
-            uint32_t d = (uint32_t)((key[k] >> shift) & 255u);
-            uint32_t dst = gbase[d] + wcount[warp][d] + rank[k];
-            keys_out[dst] = key[k];
-            vals_out[dst] = val[k];
+            const uint32_t d = (uint32_t)((key[k] >> shift) & 255u);
+            const uint32_t pos = dstart[d] + wcount[warp][d] + rank[k];
+            s_key[pos] = key[k];
+            s_val[pos] = vals_in[i];          // (read here, not kept in registers over the ranking)
         }
+    }
+    __syncthreads();
+    const int n_here = (int)min((int64_t)kSortTile, n - tile0);
+    for (int pos = threadIdx.x; pos < n_here; pos += kSortThreads) {
+        const uint64_t kk = s_key[pos];
+        const uint32_t d = (uint32_t)((kk >> shift) & 255u);
+        const uint32_t dst = (uint32_t)((int32_t)pos + gdelta[d]);
+        keys_out[dst] = kk;
+        vals_out[dst] = s_val[pos];
     }
 }
 
