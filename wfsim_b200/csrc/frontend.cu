@@ -1035,6 +1035,10 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     // concatenation of one range per run and the back end can order it in shared memory.
     std::vector<uint32_t> gstart;
     int64_t max_group_photons = 0;
+    // records the batch is expected to make: a photon alone on its channel makes one record, photons that pile up
+    // on a channel share records -- at most ~40 per (group, channel) window counted here; an underestimate only
+    // costs the repeated back end below, an overestimate of 2 records per photon cost 23 GB per buffer for heavy S2s
+    int64_t est_records = -1;
     const int n_ranges = 4;
     {
         bool contiguous = n_ph > 0 && ngroups > 0;
@@ -1061,11 +1065,13 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
             }
         }
         if (contiguous) {
+            est_records = 0;
             for (int32_t gi = 0; gi < ngroups; gi++) {
                 int64_t cnt = 0;
                 for (int cls = 0; cls < n_ranges; cls++)
                     cnt += gstart[(size_t)cls * (ngroups + 1) + gi + 1] - gstart[(size_t)cls * (ngroups + 1) + gi];
                 max_group_photons = std::max(max_group_photons, cnt);
+                est_records += std::min<int64_t>(cnt, (int64_t)40 * n_ch);
             }
             F.b_gstart.reserve(4 * gstart.size());
             up(F.b_gstart, gstart.data(), 4 * gstart.size());
@@ -1171,7 +1177,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
             cap_here = (int64_t)(rb.cap / WFS_RECORD_BYTES);
         }
     };
-    reserve_records(std::max<int64_t>(2 * (n_ph + n_ap) + 65536, 1));
+    reserve_records(est_records >= 0 ? est_records + est_records / 2 + 65536 : std::max<int64_t>(2 * (n_ph + n_ap) + 65536, 1));
     uint8_t *d_rec = rb.as<uint8_t>();
     if (ngroups > 0) {
         L.B->run(b, d_rec, cap_here, F.b_groups.as<wfs_group_info>(), res, compact ? &co : nullptr, plain_fraction);
