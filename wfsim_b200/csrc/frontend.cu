@@ -959,9 +959,20 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
     g = make_ctx(F, seed);
     {
         // heavy instructions (S2s with 1e5..1e6 photons) are split over several CTAs
-        const unsigned ny = (unsigned)std::max<int64_t>(1, std::min<int64_t>(256, max_instr_photons / 8192));
-        if (ny > 1) FLAUNCH(k_acc_init, div_up(ntot * A_COUNT, 256), 256, ntot * (int64_t)A_COUNT, F.b_acc.as<int64_t>());
-        FLAUNCH(k_instr_truth, dim3((unsigned)ntot, ny), 128, g, H->cfg, (uint32_t)ntot, (uint32_t)n_ph, (uint32_t)n_ph);
+        const bool split = max_instr_photons > (int64_t)kTruthSlice;
+        if (split) FLAUNCH(k_acc_init, div_up(ntot * A_COUNT, 256), 256, ntot * (int64_t)A_COUNT, F.b_acc.as<int64_t>());
+        FLAUNCH(k_instr_truth, (unsigned)ntot, 128, g, H->cfg, (uint32_t)ntot, (uint32_t)n_ph, (uint32_t)n_ph, split ? 1 : 0,
+                (const uint2 *)nullptr, (const uint32_t *)nullptr);
+        if (split) {
+            const int64_t cap_items = n_ph / kTruthSlice + 1;
+            F.b_titems.reserve(sizeof(uint2) * (size_t)cap_items + 16);
+            uint32_t *d_n = F.b_titems.as<uint32_t>();                     // [0]: item count; items from byte 16
+            uint2 *d_items = reinterpret_cast<uint2 *>(F.b_titems.as<uint8_t>() + 16);
+            WFS_CUDA_CHECK(cudaMemsetAsync(d_n, 0, 16, s));
+            FLAUNCH(k_truth_items, div_up(ntot, 256), 256, g, (uint32_t)ntot, d_items, d_n);
+            FLAUNCH(k_instr_truth, (unsigned)cap_items, 128, g, H->cfg, (uint32_t)ntot, (uint32_t)n_ph, (uint32_t)n_ph, 1,
+                    (const uint2 *)d_items, (const uint32_t *)d_n);
+        }
     }
     WFS_CUDA_CHECK(cudaEventRecord(L.ev_d, s));
     std::vector<int64_t> acc((size_t)ntot * A_COUNT);
@@ -1423,7 +1434,7 @@ static void release_frontend_buffers(Frontend &F) {
     DevBuf *all[] = {&F.b_itype, &F.b_itime, &F.b_ix, &F.b_iy, &F.b_iz, &F.b_iamp, &F.b_igidx, &F.b_ilce,
                      &F.b_iscg, &F.b_icy, &F.b_ipat, &F.b_ivd, &F.b_idl, &F.b_ixo, &F.b_iyo, &F.b_irecoil, &F.b_ilrow, &F.b_ioptfirst, &F.b_ioptn,
                      &F.b_igglo, &F.b_igghi, &F.b_iggfrac, &F.b_iggmean, &F.b_ggpartial, &F.b_dmean, &F.b_dspread, &F.b_nemit, &F.b_emitoff,
-                     &F.b_nhits, &F.b_acc, &F.b_cdf, &F.b_cdfok, &F.b_pattern, &F.b_et, &F.b_einstr,
+                     &F.b_nhits, &F.b_acc, &F.b_titems, &F.b_cdf, &F.b_cdfok, &F.b_pattern, &F.b_et, &F.b_einstr,
                      &F.b_enph, &F.b_ephoff, &F.b_pht, &F.b_phch, &F.b_phgain, &F.b_phinstr, &F.b_phflags,
                      &F.b_phnap, &F.b_apoff, &F.b_picount, &F.b_pioff, &F.b_pecount, &F.b_peoff, &F.b_irun, &F.b_pcgroup,
                      &F.b_pcrank, &F.b_trig, &F.b_records, &F.b_records2, &F.b_groups, &F.b_scal, &F.b_phstart,

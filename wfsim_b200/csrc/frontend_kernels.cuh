@@ -667,19 +667,44 @@ __global__ void k_acc_init(int64_t n, int64_t *acc) {
     acc[k] = (a == A_TMIN || a == A_ETMIN) ? LLONG_MAX : (a == A_TMAX || a == A_ETMAX || a == A_PTMAX) ? LLONG_MIN : 0;
 }
 
-// grid (n_instr, ny): CTA (i, y) takes the y-th slice of the photons / electrons / afterpulses of
-// instruction i.  ny == 1: plain stores; ny > 1 (heavy S2 instructions with millions of photons, which
-// one CTA would walk alone): integer atomics into accumulators preset by k_acc_init -- sums, minima and
-// maxima of integers, so the result does not depend on the order.
-__global__ void __launch_bounds__(128)
-k_instr_truth(GenCtx g, DeviceConfig c, uint32_t n_instr, uint32_t n_ph, uint32_t ap0) {
-    __shared__ int64_t sm[4][A_COUNT];
-    const uint32_t i = blockIdx.x;
+// One CTA per instruction; an instruction with more than kTruthSlice photons (heavy S2s with millions of photons,
+// which one CTA would walk alone) is cut into ny slices: slice 0 by its own CTA, the others through the work list
+// of k_truth_items (a (n_instr, ny) grid launched ~1e7 empty CTAs for a batch with a few heavy S2s and thousands of
+// single-electron secondaries: 10 ms).  ny == 1: plain stores; ny > 1: integer atomics into accumulators preset by
+// k_acc_init -- sums, minima and maxima of integers, so the result does not depend on the order.
+constexpr uint32_t kTruthSlice = 8192, kTruthSlicesMax = 256;      // photons per CTA of a heavy instruction
+__device__ __forceinline__ uint32_t truth_slices(uint32_t n_photons) {
+    return min(max((n_photons + kTruthSlice - 1) / kTruthSlice, 1u), kTruthSlicesMax);
+}
+
+// Work list of the heavy instructions: the slices 1 .. ny - 1 of every instruction with more than kTruthSlice
+// photons (slice 0 is taken by the instruction's own CTA).  sum(ny_i - 1) <= n_photons / kTruthSlice.
+__global__ void k_truth_items(GenCtx g, uint32_t n_instr, uint2 *items, uint32_t *n_items) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_instr) return;
-    const uint32_t ny = gridDim.y, yi = blockIdx.y;
+    const uint32_t ny = truth_slices(g.e_phoff[g.i_emitoff[i + 1]] - g.e_phoff[g.i_emitoff[i]]);
+    if (ny <= 1) return;
+    const uint32_t base = atomicAdd(n_items, ny - 1);
+    for (uint32_t y = 1; y < ny; y++) items[base + y - 1] = make_uint2(i, y);
+}
+
+// `split`: instructions may be heavy (accumulators preset by k_acc_init, combined by atomics).  `items` == nullptr:
+// CTA i takes slice 0 of instruction i; else CTA k takes the slice items[k] names (k < *n_items).
+__global__ void __launch_bounds__(128)
+k_instr_truth(GenCtx g, DeviceConfig c, uint32_t n_instr, uint32_t n_ph, uint32_t ap0, int split,
+              const uint2 *__restrict__ items, const uint32_t *__restrict__ n_items) {
+    __shared__ int64_t sm[4][A_COUNT];
+    uint32_t i = blockIdx.x, yi = 0;
+    if (items) {
+        if (blockIdx.x >= *n_items) return;
+        i = items[blockIdx.x].x;
+        yi = items[blockIdx.x].y;
+    }
+    if (i >= n_instr) return;
     const int64_t T0 = g.i_time[i];
     const uint32_t e0_all = g.i_emitoff[i], e1_all = g.i_emitoff[i + 1];
     const uint32_t q0_all = g.e_phoff[e0_all], q1_all = g.e_phoff[e1_all];
+    const uint32_t ny = split ? truth_slices(q1_all - q0_all) : 1u;
     auto slice = [&](uint32_t lo, uint32_t hi, uint32_t &a, uint32_t &b) {
         const uint64_t n = hi - lo;
         a = lo + (uint32_t)(n * yi / ny);
