@@ -138,7 +138,8 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            # (an nvidia-smi query takes the driver's locks: with one sampler per rank, 8 ranks, keep them rare)
+            self._halt.wait(0.2 if int(os.environ.get('WORLD_SIZE', 1)) == 1 else 1.0)
 
     def stop(self):
         self._halt.set()
@@ -335,7 +336,7 @@ def measure_path(sim, inst, args, D, clocks_gpu=None, rng_id=None, e2e=True):
     for _ in range(args.warmup):
         c = sim.run_staged(seed=1)
     D.barrier()
-    sampler = ClockSampler(clocks_gpu) if clocks_gpu is not None else None
+    sampler = ClockSampler(clocks_gpu) if clocks_gpu is not None and not os.environ.get('WFS_BENCH_NO_CLOCKS') else None
     if sampler:
         sampler.start()
     ms, launches = [], 0
@@ -354,7 +355,7 @@ def measure_path(sim, inst, args, D, clocks_gpu=None, rng_id=None, e2e=True):
     D.barrier()
     r = dict(counts=c, t_dev=float(np.sum(ms)) / 1e3, launches=launches, phases=phases / args.steps,
              phases_alone=ph_alone, clocks=clocks)
-    if not e2e:
+    if not e2e or getattr(args, 'no_e2e', False):
         return r
     cap = int(c['n_records_total'] * 1.02) + 1024
     records_out = host_array(cap, raw_record_dtype())
@@ -441,6 +442,8 @@ def path_line(name, r, D, args, weak=True, extra_config=None):
                         'l2': 'inputs and outputs of every batch exceed the 126 MB L2 (no flush needed)'},
                        **(extra_config or {})),
     }
+    if D.world > 1:
+        line['ms_per_step_per_rank'] = [round(x['t_dev'] / args.steps * 1e3, 2) for x in D.gather_objects({'t_dev': r['t_dev']})]
     if r.get('clocks') is not None:
         line['clocks'] = r['clocks']
     if 't_e2e' in r:
@@ -806,6 +809,7 @@ def main():
                     help='events per worker process of the oracle-port CPU figure')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-configs', action='store_true', help='C1 only: skip the bounded C2 / C3 / C4 samples')
+    ap.add_argument('--no-e2e', action='store_true', help='device-resident leg only (diagnostics)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

@@ -132,6 +132,8 @@ def test_split_transport_into_page_locked_destinations(fraction):
     kv = dict(WFS_BATCH_INSTRUCTIONS=100)
     if fraction != 'adaptive':
         kv['WFS_PLAIN_FRACTION'] = fraction
+    else:
+        kv.update(WFS_PLAIN_ADAPTIVE=1, WFS_EXPAND_THREADS=2)
     with env(**kv):
         for rep in range(3):          # the adaptive share moves from call to call
             out = sim.simulate(inst, seed=5, records_out=dest)

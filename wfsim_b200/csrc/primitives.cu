@@ -9,14 +9,13 @@
 namespace wfs {
 
 static bool blocking_sync_mode() {
-    // measured on a 4-GPU box with 8 cores per rank: sleeping on a blocking event costs more (144 ms per
-    // step) than the spinning waits take from the other ranks (119 ms) -- so spin while the lane threads
-    // leave at least half of the rank's cores to the record expanders, sleep when they would not
-    // (8 ranks on 32 cores: 3 spinning lanes would take 3 of the 4 cores of a rank)
+    // Spin by default.  Measured: sleeping on a blocking event costs more than the spinning waits take from the
+    // other ranks -- 144 vs 119 ms per step on a 4-GPU box with 8 cores per rank (round 1), 74 vs 72 ms with 8
+    // ranks on 32 cores (round 2) -- and next to anything that holds the driver's locks (an nvidia-smi query
+    // every 0.2 s per rank) the sleeping waits stall outright: 154 ms per step on every rank
+    // (profiles/tools/n8_device_leg.sh).  WFS_BLOCKING_SYNC=1 asks for the sleeping form.
     if (const char *e = getenv("WFS_BLOCKING_SYNC")) return atoi(e) != 0;
-    const char *l = getenv("WFS_LANES");
-    const int lanes = l ? std::max(1, atoi(l)) : default_lanes();
-    return 2 * lanes > host_cores_per_rank();
+    return false;
 }
 
 cudaError_t stream_sync(cudaStream_t s) {

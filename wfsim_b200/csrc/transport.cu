@@ -70,7 +70,12 @@ void SplitControl::init(int expand_threads) {
     // that gain nothing; the link moves P = 47 GB/s; compact / plain bytes c = 0.28 for single-photon records.
     // Few threads (several ranks sharing the cores of one box): both sides finish together at
     // f = (1/E - c/P) / ((1 - c)/P + 1/E), then the feedback below takes over.
-    if (expand_threads >= 8) {
+    // ... and measured with 8 ranks on one 32-core box (profiles/r3f_n8_*.json): 8 x 0.7 x 30 GB of DMA rows per step
+    // into one host memory system took 4.7 s per step where the compact form alone takes 2.6 s -- the cores are not
+    // the bound there either, the memory system is, and it takes DMA writes from eight devices worse than the
+    // expanders' streaming stores.  So the split is opt-in: WFS_PLAIN_ADAPTIVE=1 (or a fixed WFS_PLAIN_FRACTION).
+    const char *adaptive = getenv("WFS_PLAIN_ADAPTIVE");
+    if (expand_threads >= 8 || !(adaptive && atoi(adaptive) != 0)) {
         frozen = true;
         permille = 0;
         return;
