@@ -961,8 +961,8 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         // heavy instructions (S2s with 1e5..1e6 photons) are split over several CTAs
         const bool split = max_instr_photons > (int64_t)kTruthSlice;
         if (split) FLAUNCH(k_acc_init, div_up(ntot * A_COUNT, 256), 256, ntot * (int64_t)A_COUNT, F.b_acc.as<int64_t>());
-        FLAUNCH(k_instr_truth, (unsigned)ntot, 128, g, H->cfg, (uint32_t)ntot, (uint32_t)n_ph, (uint32_t)n_ph, split ? 1 : 0,
-                (const uint2 *)nullptr, (const uint32_t *)nullptr);
+        FLAUNCH(k_instr_truth, (unsigned)ntot, 128, g, H->cfg, (uint32_t)ntot, (uint32_t)n_ph,
+                (uint32_t)n_ph, split ? 1 : 0, (const uint2 *)nullptr, (const uint32_t *)nullptr);
         if (split) {
             const int64_t cap_items = n_ph / kTruthSlice + 1;
             F.b_titems.reserve(sizeof(uint2) * (size_t)cap_items + 16);

@@ -483,6 +483,8 @@ k_photons(GenCtx g, wfs_params p, const double *gains, int n_ch, uint32_t n_emit
           uint32_t p1) {
     uint32_t ph = p0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (ph >= p1) return;
+    // (the lanes of a warp search adjacent keys: all but the last levels of the search are broadcast loads already;
+    // searching once per warp and walking on from there was tried and is slower, 3.5 vs 2.8 ms per 2e4 events)
     const uint32_t em = upper_bound_dev(g.e_phoff, n_emit + 1, ph) - 1;
     const int32_t i = g.e_instr[em];
     const uint32_t ord = ph - g.e_phoff[g.i_emitoff[i]];
@@ -694,6 +696,9 @@ __global__ void __launch_bounds__(128)
 k_instr_truth(GenCtx g, DeviceConfig c, uint32_t n_instr, uint32_t n_ph, uint32_t ap0, int split,
               const uint2 *__restrict__ items, const uint32_t *__restrict__ n_items) {
     __shared__ int64_t sm[4][A_COUNT];
+    // (one warp per instruction for light batches -- no CTA-wide combination of the 35 accumulators -- was tried: slower,
+    // 3.4 vs 2.8 ms of front end per 2e4 C1 events: an S2 instruction's ~1200 photons are a long walk for 32 lanes)
+    const int tid = (int)threadIdx.x, nthr = (int)blockDim.x;
     uint32_t i = blockIdx.x, yi = 0;
     if (items) {
         if (blockIdx.x >= *n_items) return;
@@ -720,7 +725,7 @@ k_instr_truth(GenCtx g, DeviceConfig c, uint32_t n_instr, uint32_t n_ph, uint32_
     v[A_TMIN] = LLONG_MAX; v[A_TMAX] = LLONG_MIN; v[A_ETMIN] = LLONG_MAX; v[A_ETMAX] = LLONG_MIN;
     v[A_PTMAX] = LLONG_MIN;
     const int dt = c.p.dt;
-    for (uint32_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+    for (uint32_t q = q0 + tid; q < q1; q += nthr) {
         const int64_t t = g.ph_t[q];
         const int ch = g.ph_ch[q];
         v[A_NPHALL]++;
@@ -746,7 +751,7 @@ k_instr_truth(GenCtx g, DeviceConfig c, uint32_t n_instr, uint32_t n_ph, uint32_
         }
     }
     if (g.i_type[i] != 1) {
-        for (uint32_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        for (uint32_t e = e0 + tid; e < e1; e += nthr) {
             const int64_t t = g.e_t[e];
             v[A_NE]++;
             v[A_ETMIN] = t < v[A_ETMIN] ? t : v[A_ETMIN];
@@ -756,7 +761,7 @@ k_instr_truth(GenCtx g, DeviceConfig c, uint32_t n_instr, uint32_t n_ph, uint32_
     }
     if (g.n_ap > 0 && q1 > q0) {   // PMT-afterpulse children (of my photons) extend the last pulse end
         const uint32_t a0 = ap0 + g.ap_off[q0], a1 = ap0 + (q1 < n_ph ? g.ap_off[q1] : g.ap_off[n_ph]);
-        for (uint32_t a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
+        for (uint32_t a = a0 + tid; a < a1; a += nthr) {
             const int64_t t = g.ph_t[a];
             v[A_NAP]++;
             v[A_PTMAX] = t > v[A_PTMAX] ? t : v[A_PTMAX];
