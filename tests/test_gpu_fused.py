@@ -151,6 +151,49 @@ def test_split_transport_into_page_locked_destinations(fraction):
     sim.close()
 
 
+def test_overlapping_groups_take_the_multi_pass_path():
+    """Delayed secondaries can form a digitisation group that starts before the previous one has ended; the records
+    of the two interleave in time, which the group-ordered fused back end cannot deliver: such a batch is detected
+    (k_groups_disjoint) and handed to the multi-pass back end.  (Found by profiles/tools/fuzz_simulate.py, seed 12,
+    iteration 77.)"""
+    from tests.golden.synth_tables import EleApHist, pmt_ap_tables
+    from tests.test_gpu_configs import make_sim as make_sim_res
+    from wfsim_b200.dtypes import instruction_dtype
+    sim, cfg = make_sim_res(dict(uniform_to_pmt_ap=pmt_ap_tables(494), uniform_to_ele_ap=EleApHist()),
+                            enable_pmt_afterpulses=True, enable_electron_afterpulses=True)
+    found = False
+    for seed in range(40):
+        rng = np.random.default_rng(1000 + seed)
+        n = 31
+        inst = np.zeros(n, instruction_dtype)
+        inst['type'] = rng.choice([1, 2], n)
+        inst['time'] = np.sort(rng.integers(0, 70000, n))
+        r = np.sqrt(rng.uniform(0, 55 ** 2, n)); th = rng.uniform(-np.pi, np.pi, n)
+        inst['x'], inst['y'] = r * np.cos(th), r * np.sin(th)
+        inst['z'] = rng.uniform(-110, 0, n)
+        inst['amp'] = (10 ** rng.uniform(0, 3.7, n)).astype(int)
+        inst['recoil'], inst['local_field'], inst['event_number'] = 7, 82.0, np.arange(n)
+        inst = inst[inst['amp'] > 0]
+        with env(WFS_FUSED=1):
+            a = sim.simulate(inst, seed=seed)
+            ca = dict(sim.last_counts)
+        g = a['groups']
+        rr = a['raw_records']
+        key = rr['time'].astype(np.int64) * 1024 + rr['channel']
+        assert (np.diff(key) >= 0).all(), seed
+        with_records = g[g['n_intervals'] > 0]
+        overlap = len(with_records) > 1 and (with_records['left'][1:] <= with_records['right'][:-1]).any()
+        if overlap:
+            found = True
+            assert ca['n_fused_batches'] == 0
+            with env(WFS_FUSED=0):
+                b = sim.simulate(inst, seed=seed)
+            assert a['raw_records'].tobytes() == b['raw_records'].tobytes()
+            break
+    assert found, 'no case with overlapping groups among the seeds'
+    sim.close()
+
+
 def test_groups_that_do_not_fit_take_the_multi_pass_path():
     """A heavy S2 (more photons than a CTA holds) sends its batch through the multi-pass back end; the
     light batches of the same call still use the fused kernel; the result does not depend on that."""

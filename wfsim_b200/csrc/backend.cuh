@@ -118,7 +118,7 @@ private:
         win_meta_, win_scan_, group_tmin_, group_lr_, scalars_, dense_, itv_, itv_nrec_,
         itv_rec0_, rec_keys_, rec_vals_, rec_itv_, group_nitv_, group_ix_, pstart_, flag8_, cta_first_, phq_,
         group_nvalid_, group_out_, group_win_, rec_seg_, fused_lists_, fused_scal_, fused_records_, fused_tkey_,
-        fused_gain_, fused_desc_;
+        fused_gain_, fused_desc_, fused_ginfo_;
     int fused_smem_set_ = 0;
 };
 

@@ -1039,6 +1039,18 @@ k_group_records(FusedArgs A) {
     }
 }
 
+// "Group order IS record order" needs the groups to follow each other in time.  The reference scheduler can hand out
+// a group of delayed secondaries that starts before the previous group has ended (rawdata.py:87-98 looks at the
+// clusters' start times): then the records of the two interleave and the batch takes the multi-pass back end, which
+// orders the records of a batch globally.
+__global__ void k_groups_disjoint(int64_t n_groups, const wfs_group_info *__restrict__ info, int64_t *scalars) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups || g == 0 || info[g].n_intervals <= 0) return;
+    int64_t p = g - 1;
+    while (p >= 0 && info[p].n_intervals <= 0) p--;          // the last group in front that has records
+    if (p >= 0 && info[g].left <= info[p].right) scalars[FS_OVERFLOW] = 3;
+}
+
 // ---------------------------------------------------------------------------------------------
 bool Backend::fused_eligible(const PhotonBatch &b) const {
     const char *env = getenv("WFS_FUSED");      // WFS_FUSED=0: always the multi-pass back end (A/B tests)
@@ -1133,7 +1145,11 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
     A.desc = want ? fused_desc_.as<uint4>() : nullptr;
     A.records_out = records_out;
     A.cap_records = want ? cap_records : 0;
-    A.group_info = group_info_out;
+    // (the bookkeeping rows are also what k_groups_disjoint checks: kept in a buffer of our own if the caller wants none)
+    if (!group_info_out) fused_ginfo_.reserve(sizeof(wfs_group_info) * (size_t)std::max<int64_t>(ng, 1));
+    A.group_info = group_info_out ? group_info_out : fused_ginfo_.as<wfs_group_info>();
+    // (rows of groups that are still to be repeated with larger lists read as "no records" in the first check)
+    WFS_CUDA_CHECK(cudaMemsetAsync(A.group_info, 0, sizeof(wfs_group_info) * (size_t)ng, stream_));
     auto launch_class = [&](const ClassDef &d, const uint32_t *lst, uint32_t n, uint32_t *ticket, uint32_t *overflow_list,
                             cudaStream_t st) -> bool {
         const Layout L = make_layout(d.n_cap, d.itv_cap, d.rec_cap, n_ch, tmpl_len, c.p.dt);
@@ -1155,6 +1171,8 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
         return true;
     };
     auto records = [&]() {
+        k_groups_disjoint<<<(unsigned)div_up(ng, 256), 256, 0, stream_>>>(ng, A.group_info, d_scal);
+        lc_->n++;
         if (!want) return;
         prim_.exclusive_scan_u32(d_nrec, d_base, ng, true);
         k_group_records<<<dim3((unsigned)ng, 2), kFusedRecordThreads, 0, stream_>>>(A);
