@@ -151,6 +151,22 @@ def test_split_transport_into_page_locked_destinations(fraction):
     sim.close()
 
 
+def test_repeated_group_with_many_pulse_calls_counts_its_triggers_once():
+    """A pile-up group with more Pulse calls than shared-memory trigger counters (they then go straight to HBM) that
+    also outgrows the record list of its size class and is repeated with the largest lists: n_pe_trigger must not
+    be counted twice.  (Found by profiles/tools/fuzz_fused.py.)"""
+    sim, cfg = make_sim()
+    inst = c0_like(20, seed=16, event_rate=50000.0, e_range=(0.2, 0.5))      # 40 Pulse calls within 0.4 ms
+    with env(WFS_FUSED_REC_CAP=64):
+        a, b, ca, cb = both_paths(sim, inst, 5)
+    g = a['groups']
+    per_group = [int(((inst['time'] >= l * 10 - 1_000_000) & (inst['time'] <= r * 10)).sum()) for l, r in zip(g['left'], g['right'])]
+    assert max(per_group) > 32, 'the events were meant to pile up: more than 32 Pulse calls in one group'
+    assert_same(a, b, ca, cb)
+    assert (a['truth']['n_pe_trigger'] > a['truth']['n_photon_trigger']).any()
+    sim.close()
+
+
 def test_overlapping_groups_take_the_multi_pass_path():
     """Delayed secondaries can form a digitisation group that starts before the previous one has ended; the records
     of the two interleave in time, which the group-ordered fused back end cannot deliver: such a batch is detected

@@ -624,14 +624,9 @@ k_group_analyse(FusedArgs A, FusedClass K) {
                     for (int k = a; k < e; k++) { const uint64_t key = s_keys[k]; ndpe += key_dpe(key); n_trig += key_above(key); }
                     for (int k = a; k < a + ndpe; k++) trig += key_above(s_keys[k]);       // the [:n_double_pe] quirk, pulse.py:255
                     const int32_t pc = 2 * run0 + relpc;
-                    if (trig) {
-                        if (smem_trig) {
-                            atomicAdd(&S.trig[2 * relpc], trig);
-                            if (ch >= c.p.n_top_pmts) atomicAdd(&S.trig[2 * relpc + 1], trig);
-                        } else {
-                            atomicAdd(&b.trig_dpe_out[2 * pc], trig);
-                            if (ch >= c.p.n_top_pmts) atomicAdd(&b.trig_dpe_out[2 * pc + 1], trig);
-                        }
+                    if (trig && smem_trig) {          // (more pulse calls than counters: added behind the overflow check)
+                        atomicAdd(&S.trig[2 * relpc], trig);
+                        if (ch >= c.p.n_top_pmts) atomicAdd(&S.trig[2 * relpc + 1], trig);
                     }
                     if (per_pmt) {
                         int32_t *cnt = b.pmt_counts + ((int64_t)(pc >> 1) * 4) * (int64_t)n_ch + ch;
@@ -704,14 +699,9 @@ k_group_analyse(FusedArgs A, FusedClass K) {
                         trig = __reduce_add_sync(0xffffffffu, trig);
                         const int32_t pc = 2 * run0 + relpc;
                         if (lane == 0) {
-                            if (trig) {
-                                if (smem_trig) {
-                                    atomicAdd(&S.trig[2 * relpc], trig);
-                                    if (ch >= c.p.n_top_pmts) atomicAdd(&S.trig[2 * relpc + 1], trig);
-                                } else {
-                                    atomicAdd(&b.trig_dpe_out[2 * pc], trig);
-                                    if (ch >= c.p.n_top_pmts) atomicAdd(&b.trig_dpe_out[2 * pc + 1], trig);
-                                }
+                            if (trig && smem_trig) {
+                                atomicAdd(&S.trig[2 * relpc], trig);
+                                if (ch >= c.p.n_top_pmts) atomicAdd(&S.trig[2 * relpc + 1], trig);
                             }
                             if (per_pmt) {
                                 int32_t *cnt = b.pmt_counts + ((int64_t)(pc >> 1) * 4) * (int64_t)n_ch + ch;
@@ -787,6 +777,31 @@ k_group_analyse(FusedArgs A, FusedClass K) {
         if (smem_trig && b.trig_dpe_out)
             for (int i = tid; i < (2 << A.relpc_bits); i += blockDim.x)
                 if (S.trig[i]) atomicAdd(&b.trig_dpe_out[2 * (2 * run0) + i], S.trig[i]);
+        if (!smem_trig && b.trig_dpe_out) {
+            // more pulse calls in the group than shared-memory counters: the trigger counts go straight to HBM, but
+            // only now that the group is known to fit -- a group that is repeated with larger lists must not have
+            // counted already (pulse.py:229-271; one thread per channel walks the channel's pulses)
+            for (int w = tid; w < n_win; w += blockDim.x) {
+                const int ch = s_winch[w], a = s_cstart[ch], e = s_cstart[ch + 1];
+                int pa = a;
+                while (pa < e) {
+                    const uint64_t pck = s_keys[pa] >> shift_pc;
+                    int pe = pa + 1, ndpe = key_dpe(s_keys[pa]);
+                    while (pe < e && (s_keys[pe] >> shift_pc) == pck) { ndpe += key_dpe(s_keys[pe]); pe++; }
+                    const int relpc = (int)((uint32_t)pck & pc_mask);
+                    if (!(relpc & 1)) {
+                        int trig = 0;
+                        for (int k = pa; k < pa + ndpe; k++) trig += key_above(s_keys[k]);      // the [:n_double_pe] quirk
+                        if (trig) {
+                            const int32_t pc = 2 * run0 + relpc;
+                            atomicAdd(&b.trig_dpe_out[2 * pc], trig);
+                            if (ch >= c.p.n_top_pmts) atomicAdd(&b.trig_dpe_out[2 * pc + 1], trig);
+                        }
+                    }
+                    pa = pe;
+                }
+            }
+        }
         // the photons in channel order for the record kernel; bits 27-31: samples the photon owns
         for (int k = tid; k < n_valid; k += blockDim.x) {
             const uint64_t key = s_keys[k];
