@@ -28,7 +28,10 @@ def main(ref, c0_config):
     # allocates 5e6 records; a short buffer reaches the same branch with few groups)
     for name, seed, n_groups, gap, chunk_size, buffer_length in [
             ('sparse', 1, 40, 0.8, 2, None), ('dense', 2, 60, 0.05, 1, None), ('long_chunks', 3, 25, 1.5, 10, None),
-            ('buffer_overflow_dense', 4, 80, 0.05, 1, 60), ('buffer_overflow_long', 5, 50, 0.4, 10, 36)]:
+            ('buffer_overflow_dense', 4, 80, 0.05, 1, 60), ('buffer_overflow_long', 5, 50, 0.4, 10, 36),
+            # chunks much shorter than the spacing of the groups: the class closes at most one chunk per ZLE interval,
+            # so its chunk clock lags behind the data
+            ('lagging_clock', 6, 30, 0.4, 0.05, None), ('lagging_clock_overflow', 7, 40, 0.4, 0.05, 24)]:
         cfg, _, _ = c0_config()
         cfg['chunk_size'] = chunk_size
         groups = make_groups(seed, n_groups, gap)

@@ -42,6 +42,47 @@ def test_chunk_boundaries_match_reference():
         assert counts == c['records_per_chunk'], name
 
 
+def test_chunk_clock_pieces_with_a_lagging_clock():
+    """Random group sequences with chunks far shorter than the spacing of the groups (the reference closes at most one
+    chunk per ZLE interval, so its clock lags) and short record buffers: feeding in pieces with peek() gives the
+    one-pass bounds, as long as an interval follows the peek; if none ever does (a run that ends with groups without
+    intervals) the only difference is one more, empty, chunk at the end."""
+    import logging
+    from tests.golden.make_golden_chunks import make_groups
+    from wfsim_b200.strax_interface import ChunkClock
+    logging.disable(logging.WARNING)
+    try:
+        rng = np.random.default_rng(0)
+        cfg = load_c0_config()
+        tails = 0
+        for trial in range(400):
+            cfg['chunk_size'] = float(rng.choice([0.05, 0.5, 2]))
+            groups = make_groups(int(rng.integers(1 << 30)), int(rng.integers(3, 40)), float(rng.choice([0.05, 0.4, 1.0])))
+            nrec = [2 * g[2] for g in groups]
+            buf = int(rng.choice([12, 40, 100000]))
+            t0 = groups[0][0] * 10 + 600
+            c = ChunkClock(cfg, t0, record_buffer=buf)
+            one = c.feed(groups, nrec)
+            one.append(c.finish())
+            cuts = sorted(set(rng.integers(1, len(groups), rng.integers(1, 6)).tolist()))
+            pieces = [(groups[a:b], nrec[a:b]) for a, b in zip([0] + cuts, cuts + [len(groups)])]
+            c = ChunkClock(cfg, t0, record_buffer=buf)
+            got = []
+            for k, (pg, pn) in enumerate(pieces):
+                got += c.feed(pg, pn)
+                if k + 1 < len(pieces):
+                    got += c.peek(pieces[k + 1][0][0][0] * 10 - int(rng.integers(0, 50000)))
+            got.append(c.finish())
+            if any(g[2] > 0 for g in pieces[-1][0]) or got == one:
+                assert got == one, trial
+            else:
+                tails += 1
+                assert got[:-2] == one[:-1] and got[-2][0] == one[-1][0] and got[-1][0] == got[-2][1], trial
+        assert tails < 40
+    finally:
+        logging.disable(logging.NOTSET)
+
+
 def test_dtypes_and_config_loader():
     from wfsim_b200 import dtypes, config
     assert np.dtype(dtypes.instruction_dtype).itemsize == 70

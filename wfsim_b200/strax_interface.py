@@ -70,6 +70,7 @@ class ChunkClock:
         self.cur_right = self.last_right = 0
         self.buffer_length = int(record_buffer or self.RECORD_BUFFER)
         self.blevel = 0              # records held since the last chunk left (the reference's buffer level)
+        self.borrowed = False        # peek() has made the cut that the next interval would have made
 
     def feed(self, groups, n_records=None):
         """`n_records`: records per group (all data types).  With it the record-buffer rule of
@@ -81,6 +82,11 @@ class ChunkClock:
             for _ in range(max(int(n_itv), 0)):
                 if right != self.cur_right:
                     self.last_right, self.cur_right = self.cur_right, right
+                if self.borrowed:
+                    # the reference closes at most ONE chunk per ZLE interval (strax_interface.py:401-410); the chunk
+                    # this interval would have closed has left through peek() already
+                    self.borrowed = False
+                    continue
                 if left * dt > self.ct + rext:
                     if (self.last_right + 1) * dt > self.ct:
                         self.ct += (self.last_right + 1) * dt - self.ct
@@ -112,7 +118,7 @@ class ChunkClock:
         """Every group still to come starts after `t_next` [ns]: if the first of them is going to close the
         current chunk, close it now (same bounds: they depend on the groups seen so far only) so that its
         records can leave before the next piece is simulated."""
-        if t_next <= self.ct + self.rext:
+        if self.borrowed or t_next <= self.ct + self.rext:
             return []
         if (self.cur_right + 1) * self.dt > self.ct:      # cur_right is what last_right will be by then
             self.ct += (self.cur_right + 1) * self.dt - self.ct
@@ -120,6 +126,7 @@ class ChunkClock:
         self.pre = self.ct
         self.ct += self.cksz
         self.blevel = 0
+        self.borrowed = True
         return out
 
     def finish(self):
