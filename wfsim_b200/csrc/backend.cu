@@ -846,6 +846,8 @@ k_digitize(int64_t n_blocks, int tile_blk, int n_tiles, int64_t n_wtot, DeviceCo
                 if (W.win[slot].mult != 0) rows += W.win[slot].p1 - W.win[slot].p0;
             // (tiles that see several windows keep the search: building their rows costs more than it saves -- C2
             // digitize 13.6 ms per 100 heavy events with this condition, 15.1 without, 16.8 with the search everywhere)
+            // (tried on top of the table and dropped: lane = sample, 32 samples per round, every photon a broadcast load
+            // -- correct, but 2.5x the instructions of a block per lane: C2 digitize 35.6 instead of 13.6 ms)
             const bool tabulated = nwin == 1 && rows > 0 && rows * stride <= kTileSmpMax;
             if (tabulated) {
                 uint32_t *tab = W.own;                  // all zero on entry (the sparse path leaves it so)
