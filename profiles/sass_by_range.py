@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """Like sass_by_line.py, but sums instructions / stall samples over source-line ranges.
-usage: sass_by_range.py <ncu_source.csv> <nvdisasm.sass> <kernel-substring> name:lo-hi [name:lo-hi ...]"""
+usage: sass_by_range.py <ncu_source.csv> <nvdisasm.sass> <kernel-substring> [launch] name:lo-hi [name:lo-hi ...]"""
 import csv, re, sys, collections
 ncu_csv, sass, kern = sys.argv[1:4]
+launch = 0
+if ':' not in sys.argv[4]: launch = int(sys.argv[4]); del sys.argv[4]      # optional: which launch of the report (default the first)
 ranges = []
 for a in sys.argv[4:]:
     n, r = a.split(':'); lo, hi = r.split('-'); ranges.append((n, int(lo), int(hi)))
@@ -18,7 +20,7 @@ for l in lines[start + 1:]:
     if re.match(r'\s+/\*[0-9a-f]{4,}\*/', l):
         idx2line.append(cur_line); idx += 1
 rows = list(csv.reader(open(ncu_csv)))
-h = next(i for i, r in enumerate(rows) if r and r[0] == 'Address')
+h = [i for i, r in enumerate(rows) if r and r[0] == 'Address'][launch]
 H = rows[h]
 ie, ss = H.index('Instructions Executed'), H.index('# Samples')
 body = []

@@ -44,12 +44,13 @@ namespace {
 constexpr int kNegPos = -(1 << 29);
 constexpr int kDenseAhead = 3;                 // photon k + 3 starts inside the template of photon k: a dense channel
 constexpr int kNoFlag = 31;                     // f0 field: no owned sample below threshold
+constexpr int kRankSortMax = 32;                // photons on a channel ordered by counting smaller keys; more: a warp's bitonic network
 
 struct FusedShared {          // fixed-size part of the shared memory, the arrays follow
     int64_t origin_q;         // absolute sample index of key sample 0
     unsigned long long n_samples;
     int32_t n_valid, n_win, n_itv, n_rec, n_pulses, n_emitted;
-    int32_t n_multi, n_slow, n_cw;
+    int32_t n_multi, n_slow, n_cw, n_alone, n_mixed, n_long;
     int32_t lo, hi;           // min pulse left / max pulse right of the group, relative to origin_q
     int32_t tmax_q;           // largest photon sample of the group, relative to origin_q
     int32_t max_bin;          // most records in one time bin
@@ -69,7 +70,7 @@ __host__ __device__ inline Layout make_layout(int n_cap, int itv_cap, int rec_ca
     int o = (int)((sizeof(FusedShared) + 15) & ~15u);
     L.keys = o; o += 8 * n_cap;
     L.gains = o; o += 8 * n_cap;                 // unsorted keys while loading, gains afterwards
-    L.itv = o; o += 8 * itv_cap;
+    L.itv = o; o += 8 * itv_cap > ((2 * n_cap + 15) & ~15) ? 8 * itv_cap : ((2 * n_cap + 15) & ~15);      // intervals; before them the list of lone photons (u16 each)
     L.tmpl = o; o += 8 * tmpl_len;
     L.cmax = o; o += 8 * dt;
     L.chan_start = o; o += 4 * (n_ch + 1);
@@ -108,6 +109,17 @@ __device__ __forceinline__ uint32_t key_pulse_start(uint64_t k) { return (uint32
 
 __device__ __forceinline__ int adc_of(double cur, double c2a) {
     return -__double2int_rn(__dmul_rn(cur, c2a));      // one rounding per pulse and sample: rawdata.py:236-239
+}
+
+// Time bins of the record order.  The records of a group crowd behind its first photon (key time 0) and thin out
+// towards late PMT afterpulses: bins one sample wide up to 64, then 64 bins per octave -- 1024 bins for 2^21 samples.
+constexpr int kTimeKeyBits = 21;
+constexpr int kBinMax = 64;                     // records of one bin ranked by counting; more: bitonic network over the group
+static_assert(64 * (kTimeKeyBits - 5) <= kFusedBins, "time_bin() must fit the bin array");
+__device__ __forceinline__ int time_bin(uint32_t t) {
+    if (t < 64u) return (int)t;
+    const int k = 31 - __clz(t);
+    return ((k - 5) << 6) + (int)((t >> (k - 6)) & 63u);
 }
 
 // interval in shared memory: left + bias (21 bits) | samples (20) | channel (10) | first record slot (13)
@@ -176,8 +188,10 @@ k_group_analyse(FusedArgs A, FusedClass K) {
     FusedShared &S = *reinterpret_cast<FusedShared *>(smem);
     uint64_t *s_keys = reinterpret_cast<uint64_t *>(smem + L.keys);
     double *s_gain = reinterpret_cast<double *>(smem + L.gains);
-    uint64_t *s_raw = reinterpret_cast<uint64_t *>(smem + L.gains);
+    uint64_t *s_raw = reinterpret_cast<uint64_t *>(smem + L.keys);       // keys in generation order while loading
+    uint64_t *s_buck = reinterpret_cast<uint64_t *>(smem + L.gains);     // bucketed by channel, then ranked back into s_keys
     uint64_t *s_itv = reinterpret_cast<uint64_t *>(smem + L.itv);
+    uint16_t *s_alone = reinterpret_cast<uint16_t *>(smem + L.itv);      // lone photons, until the intervals are made
     double *s_tmpl = reinterpret_cast<double *>(smem + L.tmpl);
     double *s_cmax = reinterpret_cast<double *>(smem + L.cmax);
     int32_t *s_cstart = reinterpret_cast<int32_t *>(smem + L.chan_start);
@@ -213,7 +227,7 @@ k_group_analyse(FusedArgs A, FusedClass K) {
         // ------------------------------------------------------------------ load ----
         if (tid == 0) {
             S.n_valid = S.n_win = S.n_itv = S.n_rec = S.n_pulses = S.n_emitted = 0;
-            S.n_multi = S.n_slow = S.n_cw = 0;
+            S.n_multi = S.n_slow = S.n_cw = S.n_alone = S.n_mixed = S.n_long = 0;
             S.lo = INT_MAX; S.hi = INT_MIN;
             S.tmax_q = 0; S.max_bin = 0;
             S.overflow = 0;
@@ -263,15 +277,16 @@ k_group_analyse(FusedArgs A, FusedClass K) {
                 const uint8_t fl = b.flags[gi];
                 uint64_t key = ~0ull;
                 if (ch >= 0 && ch < n_ch && run >= 0 && c.gains[ch] != 0.0) {
-                    const int64_t rel = b.t[gi] - origin_t;
-                    const int64_t q = rel / dt;                       // rel >= 0: origin is a lower bound
+                    const int64_t rel = b.t[gi] - origin_t;           // rel >= 0: origin is a lower bound
+                    const uint32_t rel32 = (uint32_t)rel;
+                    const uint32_t q = rel32 / (uint32_t)dt;          // (32-bit division: rel is checked against 2^31 below)
                     const int relpc = 2 * (run - run0) + ((fl >> 1) & 1);
-                    if (rel < 0 || q >= (1 << kSampleBits) - 2 * (RM + tw + key_bias) || relpc < 0 ||
-                        relpc >= (1 << A.relpc_bits) || i >= 8192) {
+                    if (rel < 0 || rel >= ((int64_t)1 << 31) || (int)q >= (1 << kSampleBits) - 2 * (RM + tw + key_bias) ||
+                        relpc < 0 || relpc >= (1 << A.relpc_bits) || i >= 8192) {
                         A.scalars[FS_OVERFLOW] = 2;        // outside the key range: the multi-pass back end decides
                     } else {
                         key = ((uint64_t)ch << shift_ch) | ((uint64_t)relpc << shift_pc) |
-                              ((uint64_t)q << kShiftSample) | ((uint64_t)(rel - q * dt) << kShiftRem) |
+                              ((uint64_t)q << kShiftSample) | ((uint64_t)(rel32 - q * (uint32_t)dt) << kShiftRem) |
                               ((uint64_t)i << 1) | (uint64_t)(fl & 1);
                         atomicAdd(&s_cfill[ch], 1);
                         qmax = max(qmax, (int)q);
@@ -283,16 +298,11 @@ k_group_analyse(FusedArgs A, FusedClass K) {
             if (lane == 0 && qmax > 0) atomicMax(&S.tmax_q, qmax);
         }
         __syncthreads();
-        // time bins of the record order: as fine as the bin array allows
-        int bin_shift = 0;
-        {
-            const int span = S.tmax_q + RM + tw + key_bias + 1;
-            while ((span >> bin_shift) >= kFusedBins) bin_shift++;
-        }
-        const int n_bins = ((S.tmax_q + RM + tw + key_bias + 1) >> bin_shift) + 1;
+        // time bins of the record order (time_bin: one sample wide at the start of the group, where the records are)
+        const int n_bins = time_bin((uint32_t)(S.tmax_q + RM + tw + key_bias + 1)) + 1;
         // channel offsets (exclusive scan of the counts) by warp 0; list of non-empty channels
         if (warp == 0) {
-            int carry = 0, nwin = 0;
+            int carry = 0, nwin = 0, nlong = 0;
             for (int c0 = 0; c0 < n_ch; c0 += 32) {
                 const int ch = c0 + lane;
                 const int cnt = ch < n_ch ? s_cfill[ch] : 0;
@@ -306,9 +316,12 @@ k_group_analyse(FusedArgs A, FusedClass K) {
                 const unsigned m = __ballot_sync(0xffffffffu, cnt > 0);
                 if (cnt > 0) s_winch[nwin + __popc(m & ((1u << lane) - 1u))] = (uint16_t)ch;
                 nwin += __popc(m);
+                const unsigned ml = __ballot_sync(0xffffffffu, cnt > kRankSortMax);      // ordered by a warp below
+                if (cnt > kRankSortMax) s_multi[nlong + __popc(ml & ((1u << lane) - 1u))] = (uint16_t)ch;
+                nlong += __popc(ml);
                 carry += __shfl_sync(0xffffffffu, inc, 31);
             }
-            if (lane == 0) { s_cstart[n_ch] = carry; S.n_valid = carry; S.n_win = nwin; }
+            if (lane == 0) { s_cstart[n_ch] = carry; S.n_valid = carry; S.n_win = nwin; S.n_long = nlong; }
         }
         if (n_warps == 1 || warp > 0) {
             const int t0 = n_warps == 1 ? tid : tid - 32, step = n_warps == 1 ? 32 : (int)blockDim.x - 32;
@@ -320,31 +333,30 @@ k_group_analyse(FusedArgs A, FusedClass K) {
             const uint64_t key = s_raw[i];
             if (key == ~0ull) continue;
             const int ch = (int)(key >> shift_ch);
-            s_keys[atomicAdd(&s_cfill[ch], 1)] = key;
+            s_buck[atomicAdd(&s_cfill[ch], 1)] = key;
         }
         __syncthreads();
         const int n_valid = S.n_valid, n_win = S.n_win;
-        // inside a channel: ascending (pulse call, time, index) -- insertion sort by one thread for short
-        // lists, a bitonic network run by a warp for long ones
-        for (int w = warp; w < n_win; w += n_warps) {
-            const int ch = s_winch[w], a = s_cstart[ch], n = s_cstart[ch + 1] - a;
-            if (n <= 16) continue;
-            uint64_t *k = s_keys + a;
+        // inside a channel: ascending (pulse call, time, index).  The keys are distinct (they carry the photon's index), so
+        // a photon's place is the number of smaller keys on its channel: one thread per photon, from the bucketed copy
+        // back into s_keys.  Long lists are ordered in place by a warp (bitonic network) and copied.
+        for (int w = warp; w < S.n_long; w += n_warps) {
+            const int ch = s_multi[w], a = s_cstart[ch], n = s_cstart[ch + 1] - a;
+            uint64_t *k = s_buck + a;
             bitonic_ascending(n, lane, 32, [&](int x, int y) { return k[x] < k[y]; },
                               [&](int x, int y) { const uint64_t t = k[x]; k[x] = k[y]; k[y] = t; },
                               [&]() { __syncwarp(); });
+            for (int i = lane; i < n; i += 32) s_keys[a + i] = k[i];
         }
-        for (int w = tid; w < n_win; w += blockDim.x) {
-            const int ch = s_winch[w], a = s_cstart[ch], n = s_cstart[ch + 1] - a;
-            if (n > 16) continue;
-            for (int i = 1; i < n; i++) {
-                const uint64_t x = s_keys[a + i];
-                int j = i - 1;
-                while (j >= 0 && s_keys[a + j] > x) { s_keys[a + j + 1] = s_keys[a + j]; j--; }
-                s_keys[a + j + 1] = x;
-            }
+        for (int k = tid; k < n_valid; k += blockDim.x) {
+            const uint64_t x = s_buck[k];
+            const int ch = (int)(x >> shift_ch), a = s_cstart[ch], e = s_cstart[ch + 1];
+            if (e - a > kRankSortMax) continue;
+            int r = a;
+            for (int j = a; j < e; j++) r += s_buck[j] < x ? 1 : 0;
+            s_keys[r] = x;
         }
-        __syncthreads();      // s_raw is dead from here on: the area now takes the gains
+        __syncthreads();      // the bucketed copy is dead from here on: the area now takes the gains
         // ------------------------------------------------------------------ per photon: gain, trigger bit ----
         for (int k = tid; k < n_valid; k += blockDim.x) {
             const uint64_t key = s_keys[k];
@@ -372,72 +384,81 @@ k_group_analyse(FusedArgs A, FusedClass K) {
             s_keys[k] = (key & ~kFieldMask) | (field << 1);
         }
         __syncthreads();
-        // leaders take the sum of their followers, followers add nothing any more; photons whose template meets
-        // no other photon of the channel take the short way below; channels with overlapping photons are flagged
+        // Leaders take the sum of their followers, followers add nothing any more.  Every leader is classed by what can
+        // reach the samples it owns (from its first sample to the next photon's of the same pulse call, at most a template):
+        //   lone   -- no other photon of its pulse call within a template, no photon of another call of the channel
+        //             reaches it: the template alone (listed here)
+        //   plain  -- only photons of its own pulse call reach its samples: summed in time order (listed below, unless a
+        //             warp takes the whole channel)
+        //   mixed  -- photons of another pulse call of the channel reach its samples (PMT afterpulses on top of the
+        //             signal): one rounding per pulse call, integer sum (rawdata.py:236-239)
+        // field f1 = 1 (plain) / 2 (mixed) with no first sample marks "to be evaluated".
         for (int kb = warp * 32; kb < n_valid; kb += blockDim.x) {
             const int k = kb + lane;
             const bool valid = k < n_valid;
             const uint64_t key = valid ? s_keys[k] : 0;
             const int ch = (int)(key >> shift_ch);
-            bool alone = false, listed = false;
+            bool alone = false;
             if (valid && !key_follower(key)) {
                 const int a = s_cstart[ch], e = s_cstart[ch + 1];
-                if (k + 1 < e && key_follower(s_keys[k + 1])) {
+                const uint64_t pck = key >> shift_pc;
+                const int T = key_sample(key);
+                int kn = k + 1;
+                if (kn < e && key_follower(s_keys[kn])) {
                     double gsum = s_gain[k];
-                    for (int j = k + 1; j < e && key_follower(s_keys[j]); j++) gsum = __dadd_rn(gsum, s_gain[j]);
+                    for (; kn < e && key_follower(s_keys[kn]); kn++) gsum = __dadd_rn(gsum, s_gain[kn]);
                     s_gain[k] = gsum;
                 }
-                const int T = key_sample(key);
                 const bool single = (s_keys[a] >> shift_pc) == (s_keys[e - 1] >> shift_pc);
-                alone = single && (k == a || key_sample(s_keys[k - 1]) <= T - tlen) &&
-                        (k + 1 == e || key_sample(s_keys[k + 1]) >= T + tlen);
-                listed = !alone;
+                const int Tp = (k > a && (s_keys[k - 1] >> shift_pc) == pck) ? key_sample(s_keys[k - 1]) : kNegPos;
+                const int Tn = (kn < e && (s_keys[kn] >> shift_pc) == pck) ? key_sample(s_keys[kn]) : INT_MAX;
+                bool clean = true;
+                if (!single) {
+                    const int s_end = min(T + tlen, Tn);
+                    for (int j = a; j < e; j++) {
+                        const uint64_t kj = s_keys[j];
+                        const int Tj = key_sample(kj);
+                        if ((kj >> shift_pc) != pck && Tj > T - tlen && Tj < s_end) { clean = false; break; }
+                    }
+                }
+                alone = clean && kn == k + 1 && Tp <= T - tlen && Tn >= T + tlen;
+                if (!alone) s_keys[k] = key | ((uint64_t)(clean ? 1 : 2) << 8);
                 // many photons on top of each other: a warp takes the channel below
                 if (single && k + kDenseAhead < e && key_sample(s_keys[k + kDenseAhead]) < T + tlen) s_bin[ch] = 1;
             }
-            if (listed) s_keys[k] = key | ((uint64_t)1 << 8);       // "to be evaluated": last-sample field 1 with no first sample
-            if (alone) {
-                // one photon, one pulse: every sample of the template against the threshold
-                const double gn = s_gain[k];
-                const double *tm = s_tmpl + key_rem(key) * tlen;
-                const int thr = c.zle_thr[ch];
-                int f0 = kNoFlag, f1 = 0;
-                uint4 *slot = adc_out + (size_t)k * kSlotVecs;
-                for (int j0 = 0; j0 < tlen; j0 += 8) {             // eight samples = one 16-byte vector of the slot
-                    uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const int j = j0 + u;
-                        if (j < tlen) {
-                            const int v = max(adc_of(__dmul_rn(tm[j], gn), c2a) + baseline, 0);
-                            w[u >> 1] |= (uint32_t)(uint16_t)(int16_t)v << (16 * (u & 1));
-                            if (v < thr) {
-                                f0 = f0 == kNoFlag ? j : f0;
-                                f1 = j;
-                            }
-                        }
-                    }
-                    slot[j0 >> 3] = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-                if (f0 != kNoFlag)
-                    s_keys[k] = (key & ~((uint64_t)0x3ff << 3)) | ((uint64_t)f0 << 3) | ((uint64_t)f1 << 8);
+            const unsigned m = __ballot_sync(0xffffffffu, alone);
+            int base = 0;
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) base = atomicAdd(&S.n_alone, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
             }
+            if (alone) s_alone[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)k;
         }
         __syncthreads();
-        // photons still to be evaluated: listed for one thread each unless a warp takes their channel
+        // photons still to be evaluated: listed for one thread each unless a warp takes their channel -- plain ones from
+        // the bottom of the list, mixed ones from its top, so that the lanes of a warp run the same loop
         for (int kb = warp * 32; kb < n_valid; kb += blockDim.x) {
             const int k = kb + lane;
             const uint64_t key = k < n_valid ? s_keys[k] : 0;
             if (k < n_valid && key_follower(key)) s_gain[k] = 0.0;
-            const bool listed = k < n_valid && key_f0(key) == kNoFlag && key_f1(key) == 1 && !s_bin[(int)(key >> shift_ch)];
-            const unsigned m = __ballot_sync(0xffffffffu, listed);
-            int base = 0;
+            const bool todo = k < n_valid && key_f0(key) == kNoFlag && !key_follower(key);
+            const bool plain = todo && key_f1(key) == 1 && !s_bin[(int)(key >> shift_ch)];
+            const bool mixed = todo && key_f1(key) == 2;
+            const unsigned m = __ballot_sync(0xffffffffu, plain), m2 = __ballot_sync(0xffffffffu, mixed);
+            int base = 0, base2 = 0;
             if (m) {
                 const int leader = __ffs(m) - 1;
                 if (lane == leader) base = atomicAdd(&S.n_slow, __popc(m));
                 base = __shfl_sync(0xffffffffu, base, leader);
             }
-            if (listed) s_order[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)k;
+            if (m2) {
+                const int leader = __ffs(m2) - 1;
+                if (lane == leader) base2 = atomicAdd(&S.n_mixed, __popc(m2));
+                base2 = __shfl_sync(0xffffffffu, base2, leader);
+            }
+            if (plain) s_order[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)k;
+            if (mixed) s_order[K.n_cap - 1 - (base2 + __popc(m2 & ((1u << lane) - 1u)))] = (uint16_t)k;
         }
         for (int w = tid; w < n_win; w += blockDim.x) {
             const int ch = s_winch[w];
@@ -498,7 +519,36 @@ k_group_analyse(FusedArgs A, FusedClass K) {
             }
         }
         for (int w = tid; w < S.n_cw; w += blockDim.x) s_bin[s_multi[w]] = 0;      // the flags are bins again
-        // ------------------------------------------------------------------ per photon: owned samples (several pulse calls) ----
+        // ------------------------------------------------------------------ lone photons ----
+        // one photon, one pulse: every sample of the template against the threshold
+        for (int q = tid; q < S.n_alone; q += blockDim.x) {
+            const int k = s_alone[q];
+            const uint64_t key = s_keys[k];
+            const double gn = s_gain[k];
+            const double *tm = s_tmpl + key_rem(key) * tlen;
+            const int thr = c.zle_thr[(int)(key >> shift_ch)];
+            int f0 = kNoFlag, f1 = 0;
+            uint4 *slot = adc_out + (size_t)k * kSlotVecs;
+            for (int j0 = 0; j0 < tlen; j0 += 8) {             // eight samples = one 16-byte vector of the slot
+                uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int j = j0 + u;
+                    if (j < tlen) {
+                        const int v = max(adc_of(__dmul_rn(tm[j], gn), c2a) + baseline, 0);
+                        w[u >> 1] |= (uint32_t)(uint16_t)(int16_t)v << (16 * (u & 1));
+                        if (v < thr) {
+                            f0 = f0 == kNoFlag ? j : f0;
+                            f1 = j;
+                        }
+                    }
+                }
+                slot[j0 >> 3] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            if (f0 != kNoFlag)
+                s_keys[k] = (key & ~((uint64_t)0x3ff << 3)) | ((uint64_t)f0 << 3) | ((uint64_t)f1 << 8);
+        }
+        // ------------------------------------------------------------------ plain photons: owned samples, one pulse call ----
         for (int q = tid; q < S.n_slow; q += blockDim.x) {
             const int k = s_order[q];
             const uint64_t key = s_keys[k];
@@ -506,7 +556,64 @@ k_group_analyse(FusedArgs A, FusedClass K) {
             const int a = s_cstart[ch], e = s_cstart[ch + 1];
             const uint64_t pck = key >> shift_pc;
             const int T = key_sample(key);
-            const bool single = (s_keys[a] >> shift_pc) == (s_keys[e - 1] >> shift_pc);
+            const int thr = c.zle_thr[ch];
+            int kn = k + 1;
+            while (kn < e && key_follower(s_keys[kn])) kn++;
+            const int Tn = (kn < e && (s_keys[kn] >> shift_pc) == pck) ? key_sample(s_keys[kn]) : INT_MAX;
+            const int s_end = min(T + tlen, Tn);           // owned samples [T, s_end)
+            int f0 = kNoFlag, f1 = 0;
+            uint4 *slot = adc_out + (size_t)k * kSlotVecs;
+            int klo = k;
+            while (klo > a && (s_keys[klo - 1] >> shift_pc) == pck && key_sample(s_keys[klo - 1]) > T - tlen) klo--;
+            // four owned samples at a time: key, gain and template row of a contributor are read once per four
+            // samples; every sample still sums its contributors in list (time) order
+            uint32_t w0 = 0, w1 = 0;
+            for (int s0 = T; s0 < s_end; s0 += 4) {
+                while (key_sample(s_keys[klo]) <= s0 - tlen) klo++;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                for (int j = klo; j <= k; j++) {
+                    const uint64_t kj = s_keys[j];
+                    const double gj = s_gain[j];
+                    const int d = s0 - key_sample(kj);              // >= 0: the contributors start at or before T
+                    const double *row = s_tmpl + key_rem(kj) * tlen + d;
+                    if (d < tlen) a0 = __dadd_rn(a0, __dmul_rn(row[0], gj));
+                    if (d + 1 < tlen) a1 = __dadd_rn(a1, __dmul_rn(row[1], gj));
+                    if (d + 2 < tlen) a2 = __dadd_rn(a2, __dmul_rn(row[2], gj));
+                    if (d + 3 < tlen) a3 = __dadd_rn(a3, __dmul_rn(row[3], gj));
+                }
+                const double acc4[4] = {a0, a1, a2, a3};
+                uint32_t h[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    h[u] = 0u;
+                    if (s0 + u < s_end) {
+                        const int v = max(adc_of(acc4[u], c2a) + baseline, 0);
+                        h[u] = (uint32_t)(uint16_t)(int16_t)v;
+                        if (v < thr) {
+                            f0 = f0 == kNoFlag ? s0 + u - T : f0;
+                            f1 = s0 + u - T;
+                        }
+                    }
+                }
+                // sample j = s0 - T + u sits in half (j & 1) of word (j >> 1) & 3 of vector j >> 3; s0 - T is a multiple of 4
+                const int j0 = s0 - T;
+                if (j0 & 4) slot[j0 >> 3] = make_uint4(w0, w1, h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+                else {
+                    w0 = h[0] | (h[1] << 16); w1 = h[2] | (h[3] << 16);
+                    if (s0 + 4 >= s_end) slot[j0 >> 3] = make_uint4(w0, w1, 0u, 0u);
+                }
+            }
+            if (f0 != kNoFlag)
+                s_keys[k] = (key & ~((uint64_t)0x3ff << 3)) | ((uint64_t)f0 << 3) | ((uint64_t)f1 << 8);
+        }
+        // ------------------------------------------------------------------ mixed photons: several pulse calls reach the samples ----
+        for (int q = tid; q < S.n_mixed; q += blockDim.x) {
+            const int k = s_order[K.n_cap - 1 - q];
+            const uint64_t key = s_keys[k];
+            const int ch = (int)(key >> shift_ch);
+            const int a = s_cstart[ch], e = s_cstart[ch + 1];
+            const uint64_t pck = key >> shift_pc;
+            const int T = key_sample(key);
             const int thr = c.zle_thr[ch];
             int kn = k + 1;
             while (kn < e && key_follower(s_keys[kn])) kn++;
@@ -514,57 +621,24 @@ k_group_analyse(FusedArgs A, FusedClass K) {
             const int s_end = min(T + tlen, Tn);           // owned samples [T, s_end)
             int f0 = kNoFlag, f1 = 0;
             SlotWriter sw{adc_out + (size_t)k * kSlotVecs};
-            if (single) {
-                int klo = k;
-                while (klo > a && key_sample(s_keys[klo - 1]) > T - tlen) klo--;
-                // four owned samples at a time: key, gain and template row of a contributor are read once per four
-                // samples; every sample still sums its contributors in list (time) order
-                for (int s0 = T; s0 < s_end; s0 += 4) {
-                    while (key_sample(s_keys[klo]) <= s0 - tlen) klo++;
-                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                    for (int j = klo; j <= k; j++) {
-                        const uint64_t kj = s_keys[j];
-                        const double gj = s_gain[j];
-                        const int d = s0 - key_sample(kj);              // >= 0: the contributors start at or before T
-                        const double *row = s_tmpl + key_rem(kj) * tlen + d;
-                        if (d < tlen) a0 = __dadd_rn(a0, __dmul_rn(row[0], gj));
-                        if (d + 1 < tlen) a1 = __dadd_rn(a1, __dmul_rn(row[1], gj));
-                        if (d + 2 < tlen) a2 = __dadd_rn(a2, __dmul_rn(row[2], gj));
-                        if (d + 3 < tlen) a3 = __dadd_rn(a3, __dmul_rn(row[3], gj));
-                    }
-                    const double acc4[4] = {a0, a1, a2, a3};
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        if (s0 + u < s_end) {
-                            const int v = max(adc_of(acc4[u], c2a) + baseline, 0);
-                            sw.put(s0 + u - T, v);
-                            if (v < thr) {
-                                f0 = f0 == kNoFlag ? s0 + u - T : f0;
-                                f1 = s0 + u - T;
-                            }
-                        }
-                    }
+            // one rounding per pulse, integer sum over the pulses
+            for (int s = T; s < s_end; s++) {
+                int adc = 0;
+                double acc = 0.0;
+                uint64_t cur = ~0ull;
+                for (int j = a; j < e; j++) {
+                    const uint64_t kj = s_keys[j];
+                    const unsigned d = (unsigned)(s - key_sample(kj));
+                    if (d >= (unsigned)tlen) continue;
+                    if ((kj >> shift_pc) != cur) { adc += adc_of(acc, c2a); acc = 0.0; cur = kj >> shift_pc; }
+                    acc = __dadd_rn(acc, __dmul_rn(s_tmpl[key_rem(kj) * tlen + (int)d], s_gain[j]));
                 }
-            } else {
-                // several pulse calls on the channel: one rounding per pulse, integer sum over the pulses
-                for (int s = T; s < s_end; s++) {
-                    int adc = 0;
-                    double acc = 0.0;
-                    uint64_t cur = ~0ull;
-                    for (int j = a; j < e; j++) {
-                        const uint64_t kj = s_keys[j];
-                        const unsigned d = (unsigned)(s - key_sample(kj));
-                        if (d >= (unsigned)tlen) continue;
-                        if ((kj >> shift_pc) != cur) { adc += adc_of(acc, c2a); acc = 0.0; cur = kj >> shift_pc; }
-                        acc = __dadd_rn(acc, __dmul_rn(s_tmpl[key_rem(kj) * tlen + (int)d], s_gain[j]));
-                    }
-                    adc += adc_of(acc, c2a);
-                    const int v = max(adc + baseline, 0);
-                    sw.put(s - T, v);
-                    if (v < thr) {
-                        if (f0 == kNoFlag) f0 = s - T;
-                        f1 = s - T;
-                    }
+                adc += adc_of(acc, c2a);
+                const int v = max(adc + baseline, 0);
+                sw.put(s - T, v);
+                if (v < thr) {
+                    if (f0 == kNoFlag) f0 = s - T;
+                    f1 = s - T;
                 }
             }
             sw.finish(max(s_end - T, 0));
@@ -588,13 +662,14 @@ k_group_analyse(FusedArgs A, FusedClass K) {
             const int r0 = atomicAdd(&S.n_rec, nrec);
             const int lb = wl + l + key_bias;
             if (slot < K.itv_cap && r0 + nrec <= K.rec_cap && lb >= 0 &&
-                lb + WFS_SAMPLES_PER_RECORD * (nrec - 1) < ((n_bins << bin_shift)) && plen < (1 << 20)) {
+                lb + WFS_SAMPLES_PER_RECORD * (nrec - 1) < (1 << kTimeKeyBits) &&
+                time_bin((uint32_t)(lb + WFS_SAMPLES_PER_RECORD * (nrec - 1))) < n_bins && plen < (1 << 20)) {
                 s_itv[slot] = pack_itv((uint32_t)lb, (uint32_t)plen, (uint32_t)ch, (uint32_t)r0);
                 for (int i = 0; i < nrec; i++) {
                     const uint32_t tk = (uint32_t)(lb + WFS_SAMPLES_PER_RECORD * i);
                     s_rkey[r0 + i] = (tk << 10) | (uint32_t)ch;
-                    const int cnt = atomicAdd(&s_bin[tk >> bin_shift], 1) + 1;
-                    if (cnt > 24) atomicMax(&S.max_bin, cnt);
+                    const int cnt = atomicAdd(&s_bin[time_bin(tk)], 1) + 1;
+                    if (cnt > kBinMax) atomicMax(&S.max_bin, cnt);
                 }
             } else {
                 S.overflow = 1;
@@ -815,8 +890,10 @@ k_group_analyse(FusedArgs A, FusedClass K) {
             }
             A.tkey[pbase + k] = (uint32_t)((key >> kShiftRem) & 0xffffffu) | ((uint32_t)n_own << 27);
         }
-        if (S.max_bin <= 24) {
-            // counting sort over the time bins, then every bin ordered by (time, channel) by one thread
+        constexpr int kRankIters = 8;                   // records per thread of the largest class
+        if (S.max_bin <= kBinMax && n_rec <= kRankIters * (int)blockDim.x) {
+            // counting sort over the time bins; inside its bin a record's place is the number of smaller (time, channel)
+            // keys: one thread per record
             const int ipt = (n_bins + (int)blockDim.x - 1) / (int)blockDim.x;
             const int b0 = min(tid * ipt, n_bins), b1 = min(b0 + ipt, n_bins);
             int sum = 0;
@@ -843,18 +920,30 @@ k_group_analyse(FusedArgs A, FusedClass K) {
             for (int i = b0; i < b1; i++) { const int cnt = s_bin[i]; s_bin[i] = run; run += cnt; }
             __syncthreads();
             for (int slot = tid; slot < n_rec; slot += blockDim.x)
-                s_order[atomicAdd(&s_bin[s_rkey[slot] >> (10 + bin_shift)], 1)] = (uint16_t)slot;
+                s_order[atomicAdd(&s_bin[time_bin(s_rkey[slot] >> 10)], 1)] = (uint16_t)slot;      // (s_bin[b]: now the END of bin b)
             __syncthreads();
-            for (int bi = tid; bi < n_bins; bi += blockDim.x) {
-                const int lo = bi ? s_bin[bi - 1] : 0, hi = s_bin[bi];
-                for (int i = lo + 1; i < hi; i++) {
-                    const uint16_t x = s_order[i];
-                    const uint32_t kx = s_rkey[x];
-                    int j = i - 1;
-                    while (j >= lo && s_rkey[s_order[j]] > kx) { s_order[j + 1] = s_order[j]; j--; }
-                    s_order[j + 1] = x;
+            int my_rank[kRankIters];
+#pragma unroll
+            for (int it = 0; it < kRankIters; it++) {
+                const int i = tid + it * (int)blockDim.x;
+                my_rank[it] = 0;
+                if (i < n_rec) {
+                    const uint32_t x = s_order[i], kx = s_rkey[x];
+                    const int bi = time_bin(kx >> 10);
+                    const int lo = bi ? s_bin[bi - 1] : 0, hi = s_bin[bi];
+                    int r = lo;
+                    for (int j = lo; j < hi; j++) {
+                        const uint32_t y = s_order[j], ky = s_rkey[y];
+                        r += (ky < kx || (ky == kx && y < x)) ? 1 : 0;
+                    }
+                    my_rank[it] = r;
                 }
-                for (int i = lo; i < hi; i++) s_rkey[s_order[i]] = (uint32_t)i;      // key -> rank
+            }
+            __syncthreads();                              // every key has been read: the ranks replace them
+#pragma unroll
+            for (int it = 0; it < kRankIters; it++) {
+                const int i = tid + it * (int)blockDim.x;
+                if (i < n_rec) s_rkey[s_order[i]] = (uint32_t)my_rank[it];
             }
         } else {
             // many records in one bin (a long group): bitonic network over all records of the group
