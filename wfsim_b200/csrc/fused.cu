@@ -58,6 +58,7 @@ struct FusedShared {          // fixed-size part of the shared memory, the array
     uint32_t desc_off;        // the group's first record descriptor in the pool
     int32_t overflow;
     int32_t warp_sums[32];
+    uint8_t chunk_nz[32], chunk_long[32];      // non-empty / long channels of every chunk of 32 channels
     int32_t trig[2 * kFusedTrigSlots];
 };
 
@@ -177,8 +178,7 @@ __device__ __forceinline__ void bitonic_ascending(int n, int first, int step, Le
 
 }  // namespace
 
-__global__ void __launch_bounds__(kFusedThreads, 1)
-k_group_analyse(FusedArgs A, FusedClass K) {
+__device__ __forceinline__ void group_analyse(const FusedArgs &A, const FusedClass &K) {
     extern __shared__ __align__(16) uint8_t smem[];
     const PhotonBatch &b = A.b;
     const DeviceConfig &c = A.c;
@@ -192,6 +192,7 @@ k_group_analyse(FusedArgs A, FusedClass K) {
     uint64_t *s_buck = reinterpret_cast<uint64_t *>(smem + L.gains);     // bucketed by channel, then ranked back into s_keys
     uint64_t *s_itv = reinterpret_cast<uint64_t *>(smem + L.itv);
     uint16_t *s_alone = reinterpret_cast<uint16_t *>(smem + L.itv);      // lone photons, until the intervals are made
+    uint32_t *s_keyb = reinterpret_cast<uint32_t *>(smem + L.gains);     // record keys in bin order (the gains are dead by then)
     double *s_tmpl = reinterpret_cast<double *>(smem + L.tmpl);
     double *s_cmax = reinterpret_cast<double *>(smem + L.cmax);
     int32_t *s_cstart = reinterpret_cast<int32_t *>(smem + L.chan_start);
@@ -300,33 +301,53 @@ k_group_analyse(FusedArgs A, FusedClass K) {
         __syncthreads();
         // time bins of the record order (time_bin: one sample wide at the start of the group, where the records are)
         const int n_bins = time_bin((uint32_t)(S.tmax_q + RM + tw + key_bias + 1)) + 1;
-        // channel offsets (exclusive scan of the counts) by warp 0; list of non-empty channels
-        if (warp == 0) {
-            int carry = 0, nwin = 0, nlong = 0;
-            for (int c0 = 0; c0 < n_ch; c0 += 32) {
-                const int ch = c0 + lane;
-                const int cnt = ch < n_ch ? s_cfill[ch] : 0;
-                int inc = cnt;
+        // channel offsets (exclusive scan of the counts), list of non-empty channels, list of long channels: every warp
+        // scans chunks of 32 channels, the chunk totals are scanned by every warp for itself
+        const int n_chunks = (n_ch + 31) >> 5;            // <= 32 (n_tpc_pmts <= 1023)
+        for (int cx = warp; cx < n_chunks; cx += n_warps) {
+            const int ch = cx * 32 + lane;
+            const int cnt = ch < n_ch ? s_cfill[ch] : 0;
+            int inc = cnt;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += v;
-                }
-                if (ch < n_ch) { s_cstart[ch] = carry + inc - cnt; s_cfill[ch] = carry + inc - cnt; }
-                const unsigned m = __ballot_sync(0xffffffffu, cnt > 0);
-                if (cnt > 0) s_winch[nwin + __popc(m & ((1u << lane) - 1u))] = (uint16_t)ch;
-                nwin += __popc(m);
-                const unsigned ml = __ballot_sync(0xffffffffu, cnt > kRankSortMax);      // ordered by a warp below
-                if (cnt > kRankSortMax) s_multi[nlong + __popc(ml & ((1u << lane) - 1u))] = (uint16_t)ch;
-                nlong += __popc(ml);
-                carry += __shfl_sync(0xffffffffu, inc, 31);
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
             }
-            if (lane == 0) { s_cstart[n_ch] = carry; S.n_valid = carry; S.n_win = nwin; S.n_long = nlong; }
+            if (ch < n_ch) s_cstart[ch] = inc - cnt;          // offset inside the chunk
+            const unsigned m = __ballot_sync(0xffffffffu, cnt > 0);
+            const unsigned ml = __ballot_sync(0xffffffffu, cnt > kRankSortMax);
+            if (lane == 31) {
+                S.warp_sums[cx] = inc;
+                S.chunk_nz[cx] = (uint8_t)__popc(m);
+                S.chunk_long[cx] = (uint8_t)__popc(ml);
+            }
         }
-        if (n_warps == 1 || warp > 0) {
-            const int t0 = n_warps == 1 ? tid : tid - 32, step = n_warps == 1 ? 32 : (int)blockDim.x - 32;
-            // (the bins double as per-channel flags below: the previous group's bin offsets must not be read as flags)
-            for (int i = t0; i < max(n_bins, n_ch); i += step) s_bin[i] = 0;
+        // (the bins double as per-channel flags below: the previous group's bin offsets must not be read as flags)
+        for (int i = tid; i < max(n_bins, n_ch); i += blockDim.x) s_bin[i] = 0;
+        __syncthreads();
+        {
+            const int tot = lane < n_chunks ? S.warp_sums[lane] : 0;
+            const int nz = lane < n_chunks ? (int)S.chunk_nz[lane] : 0, nl = lane < n_chunks ? (int)S.chunk_long[lane] : 0;
+            int packed_lo = tot, packed_hi = nz | (nl << 16);       // two scans: photons; non-empty | long channels
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, packed_lo, o), u = __shfl_up_sync(0xffffffffu, packed_hi, o);
+                if (lane >= o) { packed_lo += v; packed_hi += u; }
+            }
+            const int ex_lo = packed_lo - tot, ex_hi = packed_hi - (nz | (nl << 16));
+            for (int cx = warp; cx < n_chunks; cx += n_warps) {
+                const int base = __shfl_sync(0xffffffffu, ex_lo, cx), bh = __shfl_sync(0xffffffffu, ex_hi, cx);
+                const int ch = cx * 32 + lane;
+                const int cnt = ch < n_ch ? s_cfill[ch] : 0;
+                const unsigned m = __ballot_sync(0xffffffffu, cnt > 0);
+                const unsigned ml = __ballot_sync(0xffffffffu, cnt > kRankSortMax);      // ordered by a warp below
+                if (ch < n_ch) { const int st = base + s_cstart[ch]; s_cstart[ch] = st; s_cfill[ch] = st; }
+                if (cnt > 0) s_winch[(bh & 0xffff) + __popc(m & ((1u << lane) - 1u))] = (uint16_t)ch;
+                if (cnt > kRankSortMax) s_multi[(bh >> 16) + __popc(ml & ((1u << lane) - 1u))] = (uint16_t)ch;
+            }
+            if (warp == 0 && lane == 31) {
+                s_cstart[n_ch] = packed_lo; S.n_valid = packed_lo; S.n_win = packed_hi & 0xffff; S.n_long = packed_hi >> 16;
+            }
         }
         __syncthreads();
         for (int i = tid; i < n_g; i += blockDim.x) {
@@ -890,8 +911,7 @@ k_group_analyse(FusedArgs A, FusedClass K) {
             }
             A.tkey[pbase + k] = (uint32_t)((key >> kShiftRem) & 0xffffffu) | ((uint32_t)n_own << 27);
         }
-        constexpr int kRankIters = 8;                   // records per thread of the largest class
-        if (S.max_bin <= kBinMax && n_rec <= kRankIters * (int)blockDim.x) {
+        if (S.max_bin <= kBinMax && K.rec_cap <= 2 * K.n_cap) {       // (the bin-ordered keys take the place of the gains)
             // counting sort over the time bins; inside its bin a record's place is the number of smaller (time, channel)
             // keys: one thread per record
             const int ipt = (n_bins + (int)blockDim.x - 1) / (int)blockDim.x;
@@ -919,31 +939,23 @@ k_group_analyse(FusedArgs A, FusedClass K) {
             int run = S.warp_sums[warp] + inc - sum;
             for (int i = b0; i < b1; i++) { const int cnt = s_bin[i]; s_bin[i] = run; run += cnt; }
             __syncthreads();
-            for (int slot = tid; slot < n_rec; slot += blockDim.x)
-                s_order[atomicAdd(&s_bin[time_bin(s_rkey[slot] >> 10)], 1)] = (uint16_t)slot;      // (s_bin[b]: now the END of bin b)
-            __syncthreads();
-            int my_rank[kRankIters];
-#pragma unroll
-            for (int it = 0; it < kRankIters; it++) {
-                const int i = tid + it * (int)blockDim.x;
-                my_rank[it] = 0;
-                if (i < n_rec) {
-                    const uint32_t x = s_order[i], kx = s_rkey[x];
-                    const int bi = time_bin(kx >> 10);
-                    const int lo = bi ? s_bin[bi - 1] : 0, hi = s_bin[bi];
-                    int r = lo;
-                    for (int j = lo; j < hi; j++) {
-                        const uint32_t y = s_order[j], ky = s_rkey[y];
-                        r += (ky < kx || (ky == kx && y < x)) ? 1 : 0;
-                    }
-                    my_rank[it] = r;
-                }
+            for (int slot = tid; slot < n_rec; slot += blockDim.x) {
+                const uint32_t key = s_rkey[slot];
+                const int pos = atomicAdd(&s_bin[time_bin(key >> 10)], 1);      // (s_bin[b]: now the END of bin b)
+                s_order[pos] = (uint16_t)slot;
+                s_keyb[pos] = key;
             }
-            __syncthreads();                              // every key has been read: the ranks replace them
-#pragma unroll
-            for (int it = 0; it < kRankIters; it++) {
-                const int i = tid + it * (int)blockDim.x;
-                if (i < n_rec) s_rkey[s_order[i]] = (uint32_t)my_rank[it];
+            __syncthreads();
+            for (int i = tid; i < n_rec; i += blockDim.x) {
+                const uint32_t kx = s_keyb[i];
+                const int bi = time_bin(kx >> 10);
+                const int lo = bi ? s_bin[bi - 1] : 0, hi = s_bin[bi];
+                int r = lo;
+                for (int j = lo; j < hi; j++) {
+                    const uint32_t ky = s_keyb[j];
+                    r += (ky < kx || (ky == kx && j < i)) ? 1 : 0;
+                }
+                s_rkey[s_order[i]] = (uint32_t)r;          // key -> rank (the keys are read from the bin-ordered copy)
             }
         } else {
             // many records in one bin (a long group): bitonic network over all records of the group
@@ -1006,6 +1018,14 @@ k_group_analyse(FusedArgs A, FusedClass K) {
         }
     }
 }
+
+// Two builds of the same body: the classes of large groups run 1024 threads per CTA (64 registers each); the small
+// classes (<= 512 threads) are bound by barrier waits, not by registers, and trade registers for 1536 resident threads.
+__global__ void __launch_bounds__(kFusedThreads, 1)
+k_group_analyse(FusedArgs A, FusedClass K) { group_analyse(A, K); }
+
+__global__ void __launch_bounds__(kFusedSmallThreads, 3)
+k_group_analyse_small(FusedArgs A, FusedClass K) { group_analyse(A, K); }
 
 // Records of a group, a tile of 16 consecutive records at a time, one WARP per tile: assembled in the warp's own
 // slice of shared memory and streamed out with aligned 16-byte stores -- baseline fill, then headers and zero
@@ -1258,19 +1278,22 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
                             cudaStream_t st) -> bool {
         const Layout L = make_layout(d.n_cap, d.itv_cap, d.rec_cap, n_ch, tmpl_len, c.p.dt);
         if (L.total > 227 * 1024) return false;
+        static const bool small_build = !(getenv("WFS_FUSED_SMALL") && atoi(getenv("WFS_FUSED_SMALL")) == 0);
+        auto *kern = (small_build && d.threads <= kFusedSmallThreads) ? k_group_analyse_small : k_group_analyse;
         if (!fused_smem_set_) {
             // the attribute belongs to the function, not to this back end: every lane sets the same (largest) value
             WFS_CUDA_CHECK(cudaFuncSetAttribute(k_group_analyse, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            WFS_CUDA_CHECK(cudaFuncSetAttribute(k_group_analyse_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             fused_smem_set_ = 227 * 1024;
         }
         int ctas_per_sm = 1;
-        WFS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_group_analyse, d.threads, L.total));
+        WFS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, d.threads, L.total));
         if (ctas_per_sm < 1) return false;
         FusedClass K;
         K.n_cap = d.n_cap; K.itv_cap = d.itv_cap; K.rec_cap = d.rec_cap;
         K.list = lst; K.n_list = n; K.ticket = ticket; K.overflow_list = overflow_list;
         const int grid = (int)std::min<int64_t>(n, (int64_t)kNumSMs * ctas_per_sm);
-        k_group_analyse<<<grid, d.threads, L.total, st>>>(A, K);
+        kern<<<grid, d.threads, L.total, st>>>(A, K);
         lc_->n++;
         return true;
     };

@@ -5,6 +5,7 @@
 namespace wfs {
 
 constexpr int kFusedThreads = 1024;
+constexpr int kFusedSmallThreads = 512;     // classes up to this many threads per CTA run the 3-CTAs-per-SM build
 constexpr int kFusedMaxPhotons = 8192;      // photons of one group (13 index bits in the key)
 constexpr int kFusedMaxRecCap = 8192;       // records of one group ordered in shared memory (13 bits of record slot)
 constexpr int kFusedBins = 1024;            // time bins of the record order
