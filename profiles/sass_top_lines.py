@@ -5,6 +5,12 @@ import csv, re, sys, collections
 ncu_csv, sass, kern, launch, src = sys.argv[1:6]
 n_top = int(sys.argv[6]) if len(sys.argv) > 6 else 40
 launch = int(launch)
+rows = list(csv.reader(open(ncu_csv)))
+hs = [i for i, r in enumerate(rows) if r and r[0] == 'Address']
+# the launch's own kernel: 'wfs::k_x(...)' -> the mangled '<len>k_x' + 'E' picks the SASS section (k_x vs k_x_small)
+kname = rows[hs[launch] - 1][1].split('(')[0].split('::')[-1] if hs[launch] > 0 and rows[hs[launch] - 1][0] == 'Kernel Name' else kern
+if kern in kname: kern = '%d%sE' % (len(kname), kname)
+print('kernel', kname)
 lines = open(sass).read().splitlines()
 start = next(i for i, l in enumerate(lines) if '.text.' in l and kern in l and l.strip().startswith('.section'))
 cur, idx2 = None, []
@@ -14,8 +20,6 @@ for l in lines[start + 1:]:
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m: cur = (m.group(1).split('/')[-1], int(m.group(2))); continue
     if re.match(r'\s+/\*[0-9a-f]{4,}\*/', l): idx2.append(cur)
-rows = list(csv.reader(open(ncu_csv)))
-hs = [i for i, r in enumerate(rows) if r and r[0] == 'Address']
 H = rows[hs[launch]]
 ie, ss, te, sb = H.index('Instructions Executed'), H.index('# Samples'), H.index('Thread Instructions Executed'), H.index('stall_barrier')
 agg = collections.defaultdict(lambda: [0, 0, 0, 0])

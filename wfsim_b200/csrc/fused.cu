@@ -51,6 +51,7 @@ struct FusedShared {          // fixed-size part of the shared memory, the array
     unsigned long long n_samples;
     int32_t n_valid, n_win, n_itv, n_rec, n_pulses, n_emitted;
     int32_t n_multi, n_slow, n_cw, n_alone, n_mixed, n_long;
+    int32_t work;             // next item of the evaluation phase
     int32_t lo, hi;           // min pulse left / max pulse right of the group, relative to origin_q
     int32_t tmax_q;           // largest photon sample of the group, relative to origin_q
     int32_t max_bin;          // most records in one time bin
@@ -62,11 +63,17 @@ struct FusedShared {          // fixed-size part of the shared memory, the array
     int32_t trig[2 * kFusedTrigSlots];
 };
 
+// bins of the record order for 2^m bins per octave (they double as per-channel flags: at least one per channel)
+__host__ __device__ inline int fused_bins(int m, int n_ch) {
+    const int n = (22 - m) << m;
+    return n > n_ch + 1 ? n : n_ch + 1;
+}
+
 struct Layout {               // byte offsets into the dynamic shared memory
     int keys, gains, chan_start, chan_fill, win_ch, multi, tmpl, cmax, itv, rkey, order, bins, total;
 };
 
-__host__ __device__ inline Layout make_layout(int n_cap, int itv_cap, int rec_cap, int n_ch, int tmpl_len, int dt) {
+__host__ __device__ inline Layout make_layout(int n_cap, int itv_cap, int rec_cap, int n_ch, int tmpl_len, int dt, int bin_bits) {
     Layout L;
     int o = (int)((sizeof(FusedShared) + 15) & ~15u);
     L.keys = o; o += 8 * n_cap;
@@ -77,7 +84,7 @@ __host__ __device__ inline Layout make_layout(int n_cap, int itv_cap, int rec_ca
     L.chan_start = o; o += 4 * (n_ch + 1);
     L.chan_fill = o; o += 4 * (n_ch + 1);
     L.rkey = o; o += 4 * rec_cap;                // record keys, then record ranks
-    L.bins = o; o += 4 * kFusedBins;
+    L.bins = o; o += 4 * fused_bins(bin_bits, n_ch);
     L.order = o; o += 2 * (rec_cap > n_cap ? rec_cap : n_cap);   // photons with neighbours, then record slots
     L.win_ch = o; o += 2 * (n_ch + 2);
     L.multi = o; o += 2 * (n_ch + 2);
@@ -113,14 +120,14 @@ __device__ __forceinline__ int adc_of(double cur, double c2a) {
 }
 
 // Time bins of the record order.  The records of a group crowd behind its first photon (key time 0) and thin out
-// towards late PMT afterpulses: bins one sample wide up to 64, then 64 bins per octave -- 1024 bins for 2^21 samples.
+// towards late PMT afterpulses: bins one sample wide up to 2^m, then 2^m bins per octave (m = bin_bits of the class:
+// 6 -> 1024 bins for the 2^21 samples of the key time, 8 -> 3584).
 constexpr int kTimeKeyBits = 21;
-constexpr int kBinMax = 64;                     // records of one bin ranked by counting; more: bitonic network over the group
-static_assert(64 * (kTimeKeyBits - 5) <= kFusedBins, "time_bin() must fit the bin array");
-__device__ __forceinline__ int time_bin(uint32_t t) {
-    if (t < 64u) return (int)t;
+constexpr int kBinMax = 96;                     // records of one bin ranked by counting; more: bitonic network over the group
+__device__ __forceinline__ int time_bin(uint32_t t, int m) {
+    if (t < (1u << m)) return (int)t;
     const int k = 31 - __clz(t);
-    return ((k - 5) << 6) + (int)((t >> (k - 6)) & 63u);
+    return ((k - m + 1) << m) + (int)((t >> (k - m)) & ((1u << m) - 1u));
 }
 
 // interval in shared memory: left + bias (21 bits) | samples (20) | channel (10) | first record slot (13)
@@ -184,7 +191,8 @@ __device__ __forceinline__ void group_analyse(const FusedArgs &A, const FusedCla
     const DeviceConfig &c = A.c;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
     const int n_ch = c.p.n_tpc_pmts, dt = c.p.dt, tlen = c.p.template_length;
-    const Layout L = make_layout(K.n_cap, K.itv_cap, K.rec_cap, n_ch, dt * tlen, dt);
+    const int bin_bits = K.bin_bits;
+    const Layout L = make_layout(K.n_cap, K.itv_cap, K.rec_cap, n_ch, dt * tlen, dt, bin_bits);
     FusedShared &S = *reinterpret_cast<FusedShared *>(smem);
     uint64_t *s_keys = reinterpret_cast<uint64_t *>(smem + L.keys);
     double *s_gain = reinterpret_cast<double *>(smem + L.gains);
@@ -214,13 +222,16 @@ __device__ __forceinline__ void group_analyse(const FusedArgs &A, const FusedCla
 
     for (int i = tid; i < dt * tlen; i += blockDim.x) s_tmpl[i] = c.templates[i];
     for (int i = tid; i < dt; i += blockDim.x) s_cmax[i] = c.current_max[i];
-    for (int i = tid; i < kFusedBins; i += blockDim.x) s_bin[i] = 0;     // (the bins double as per-channel flags below)
+    for (int i = tid; i < fused_bins(bin_bits, n_ch); i += blockDim.x) s_bin[i] = 0;     // (the bins double as per-channel flags below)
 
+    // (the ticket of a group is drawn one group ahead: the round trip of the atomic is over when the group starts)
+    uint32_t ticket_next = 0;
+    if (tid == 0) ticket_next = atomicAdd(K.ticket, 1u);
     for (;;) {
         __syncthreads();                              // everything of the previous group is done
         if (tid == 0) {
-            const uint32_t i = atomicAdd(K.ticket, 1u);
-            S.group = i < K.n_list ? (int32_t)K.list[i] : -1;
+            S.group = ticket_next < K.n_list ? (int32_t)K.list[ticket_next] : -1;
+            if (ticket_next < K.n_list) ticket_next = atomicAdd(K.ticket, 1u);
         }
         __syncthreads();
         const int g = S.group;
@@ -229,6 +240,7 @@ __device__ __forceinline__ void group_analyse(const FusedArgs &A, const FusedCla
         if (tid == 0) {
             S.n_valid = S.n_win = S.n_itv = S.n_rec = S.n_pulses = S.n_emitted = 0;
             S.n_multi = S.n_slow = S.n_cw = S.n_alone = S.n_mixed = S.n_long = 0;
+            S.work = 0;
             S.lo = INT_MAX; S.hi = INT_MIN;
             S.tmax_q = 0; S.max_bin = 0;
             S.overflow = 0;
@@ -300,7 +312,7 @@ __device__ __forceinline__ void group_analyse(const FusedArgs &A, const FusedCla
         }
         __syncthreads();
         // time bins of the record order (time_bin: one sample wide at the start of the group, where the records are)
-        const int n_bins = time_bin((uint32_t)(S.tmax_q + RM + tw + key_bias + 1)) + 1;
+        const int n_bins = time_bin((uint32_t)(S.tmax_q + RM + tw + key_bias + 1), bin_bits) + 1;
         // channel offsets (exclusive scan of the counts), list of non-empty channels, list of long channels: every warp
         // scans chunks of 32 channels, the chunk totals are scanned by every warp for itself
         const int n_chunks = (n_ch + 31) >> 5;            // <= 32 (n_tpc_pmts <= 1023)
@@ -491,7 +503,7 @@ __device__ __forceinline__ void group_analyse(const FusedArgs &A, const FusedCla
         // its samples are evaluated 32 at a time, lane = sample, summed over the photons that reach it in list (time)
         // order.  Every sample belongs to the last photon that starts at or before it: value into that photon's
         // slot, first / last sample below threshold into its key.
-        for (int w = warp; w < S.n_cw; w += n_warps) {
+        auto eval_dense_channel = [&](int w) {
             const int ch = s_multi[w], a = s_cstart[ch], e = s_cstart[ch + 1];
             const int thr = c.zle_thr[ch];
             int ks = a;
@@ -538,11 +550,10 @@ __device__ __forceinline__ void group_analyse(const FusedArgs &A, const FusedCla
                 }
                 ks = ke + 1;
             }
-        }
-        for (int w = tid; w < S.n_cw; w += blockDim.x) s_bin[s_multi[w]] = 0;      // the flags are bins again
+        };
         // ------------------------------------------------------------------ lone photons ----
         // one photon, one pulse: every sample of the template against the threshold
-        for (int q = tid; q < S.n_alone; q += blockDim.x) {
+        auto eval_lone = [&](int q) {
             const int k = s_alone[q];
             const uint64_t key = s_keys[k];
             const double gn = s_gain[k];
@@ -568,9 +579,9 @@ __device__ __forceinline__ void group_analyse(const FusedArgs &A, const FusedCla
             }
             if (f0 != kNoFlag)
                 s_keys[k] = (key & ~((uint64_t)0x3ff << 3)) | ((uint64_t)f0 << 3) | ((uint64_t)f1 << 8);
-        }
+        };
         // ------------------------------------------------------------------ plain photons: owned samples, one pulse call ----
-        for (int q = tid; q < S.n_slow; q += blockDim.x) {
+        auto eval_plain = [&](int q) {
             const int k = s_order[q];
             const uint64_t key = s_keys[k];
             const int ch = (int)(key >> shift_ch);
@@ -626,9 +637,9 @@ __device__ __forceinline__ void group_analyse(const FusedArgs &A, const FusedCla
             }
             if (f0 != kNoFlag)
                 s_keys[k] = (key & ~((uint64_t)0x3ff << 3)) | ((uint64_t)f0 << 3) | ((uint64_t)f1 << 8);
-        }
+        };
         // ------------------------------------------------------------------ mixed photons: several pulse calls reach the samples ----
-        for (int q = tid; q < S.n_mixed; q += blockDim.x) {
+        auto eval_mixed = [&](int q) {
             const int k = s_order[K.n_cap - 1 - q];
             const uint64_t key = s_keys[k];
             const int ch = (int)(key >> shift_ch);
@@ -665,7 +676,26 @@ __device__ __forceinline__ void group_analyse(const FusedArgs &A, const FusedCla
             sw.finish(max(s_end - T, 0));
             if (f0 != kNoFlag)
                 s_keys[k] = (key & ~((uint64_t)0x3ff << 3)) | ((uint64_t)f0 << 3) | ((uint64_t)f1 << 8);
+        };
+        // The work of this phase is handed out warp by warp through a counter, the long items first (a piled-up channel,
+        // then 32 mixed, plain, lone photons at a time): a warp that is done takes the next item instead of waiting at
+        // the barrier for the warp that drew a piled-up channel.
+        {
+            const int n_cw = S.n_cw, n_mixed = S.n_mixed, n_plain = S.n_slow, n_lone = S.n_alone;
+            const int w1 = n_cw + ((n_mixed + 31) >> 5), w2 = w1 + ((n_plain + 31) >> 5), w3 = w2 + ((n_lone + 31) >> 5);
+            for (;;) {
+                int w = 0;
+                if (lane == 0) w = atomicAdd(&S.work, 1);
+                w = __shfl_sync(0xffffffffu, w, 0);
+                if (w >= w3) break;
+                if (w < n_cw) eval_dense_channel(w);
+                else if (w < w1) { const int q = ((w - n_cw) << 5) + lane; if (q < n_mixed) eval_mixed(q); }
+                else if (w < w2) { const int q = ((w - w1) << 5) + lane; if (q < n_plain) eval_plain(q); }
+                else { const int q = ((w - w2) << 5) + lane; if (q < n_lone) eval_lone(q); }
+                __syncwarp();
+            }
         }
+        for (int w = tid; w < S.n_cw; w += blockDim.x) s_bin[s_multi[w]] = 0;      // the flags are bins again
         __syncthreads();
 
         // ------------------------------------------------------------------ per window: truth, ZLE intervals ----
@@ -684,12 +714,12 @@ __device__ __forceinline__ void group_analyse(const FusedArgs &A, const FusedCla
             const int lb = wl + l + key_bias;
             if (slot < K.itv_cap && r0 + nrec <= K.rec_cap && lb >= 0 &&
                 lb + WFS_SAMPLES_PER_RECORD * (nrec - 1) < (1 << kTimeKeyBits) &&
-                time_bin((uint32_t)(lb + WFS_SAMPLES_PER_RECORD * (nrec - 1))) < n_bins && plen < (1 << 20)) {
+                time_bin((uint32_t)(lb + WFS_SAMPLES_PER_RECORD * (nrec - 1)), bin_bits) < n_bins && plen < (1 << 20)) {
                 s_itv[slot] = pack_itv((uint32_t)lb, (uint32_t)plen, (uint32_t)ch, (uint32_t)r0);
                 for (int i = 0; i < nrec; i++) {
                     const uint32_t tk = (uint32_t)(lb + WFS_SAMPLES_PER_RECORD * i);
                     s_rkey[r0 + i] = (tk << 10) | (uint32_t)ch;
-                    const int cnt = atomicAdd(&s_bin[time_bin(tk)], 1) + 1;
+                    const int cnt = atomicAdd(&s_bin[time_bin(tk, bin_bits)], 1) + 1;
                     if (cnt > kBinMax) atomicMax(&S.max_bin, cnt);
                 }
             } else {
@@ -941,14 +971,14 @@ __device__ __forceinline__ void group_analyse(const FusedArgs &A, const FusedCla
             __syncthreads();
             for (int slot = tid; slot < n_rec; slot += blockDim.x) {
                 const uint32_t key = s_rkey[slot];
-                const int pos = atomicAdd(&s_bin[time_bin(key >> 10)], 1);      // (s_bin[b]: now the END of bin b)
+                const int pos = atomicAdd(&s_bin[time_bin(key >> 10, bin_bits)], 1);      // (s_bin[b]: now the END of bin b)
                 s_order[pos] = (uint16_t)slot;
                 s_keyb[pos] = key;
             }
             __syncthreads();
             for (int i = tid; i < n_rec; i += blockDim.x) {
                 const uint32_t kx = s_keyb[i];
-                const int bi = time_bin(kx >> 10);
+                const int bi = time_bin(kx >> 10, bin_bits);
                 const int lo = bi ? s_bin[bi - 1] : 0, hi = s_bin[bi];
                 int r = lo;
                 for (int j = lo; j < hi; j++) {
@@ -1197,16 +1227,18 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
     const int64_t ng = b.n_groups;
     const int n_ch = c.p.n_tpc_pmts, tmpl_len = c.p.dt * c.p.template_length;
     // groups by photon count: small groups get small shared-memory lists and many CTAs per SM
-    struct ClassDef { int n_cap, itv_cap, rec_cap, threads; };
-    ClassDef defs[kFusedMaxClasses] = {{512, 512, 1024, 256}, {2048, 1024, 3072, 512}, {4096, 2048, 6144, 1024},
-                                       {kFusedMaxPhotons, 4096, kFusedMaxRecCap, 1024}};      // (profiles/tools/class_sweep.sh)
+    struct ClassDef { int n_cap, itv_cap, rec_cap, threads, bin_bits; };
+    ClassDef defs[kFusedMaxClasses] = {{512, 512, 1024, 256, 6}, {2048, 1024, 3072, 512, 6}, {4096, 2048, 6144, 1024, 8},
+                                       {kFusedMaxPhotons, 4096, kFusedMaxRecCap, 1024, 7}};      // (profiles/tools/class_sweep.sh)
     int kFusedClasses = 4;
-    if (const char *e = getenv("WFS_FUSED_CLASSES")) {        // experiments: "photons:intervals:records:threads,..." ascending, the last one catches all
+    if (const char *e = getenv("WFS_FUSED_CLASSES")) {        // experiments: "photons:intervals:records:threads[:bin_bits],..." ascending, the last one catches all
         int n = 0;
         const char *p = e;
         while (n < kFusedMaxClasses) {
             ClassDef d;
-            if (sscanf(p, "%d:%d:%d:%d", &d.n_cap, &d.itv_cap, &d.rec_cap, &d.threads) != 4) break;
+            d.bin_bits = 6;
+            if (sscanf(p, "%d:%d:%d:%d:%d", &d.n_cap, &d.itv_cap, &d.rec_cap, &d.threads, &d.bin_bits) < 4) break;
+            d.bin_bits = std::max(6, std::min(d.bin_bits, 8));
             defs[n++] = d;
             p = strchr(p, ',');
             if (!p) break;
@@ -1276,7 +1308,7 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
     WFS_CUDA_CHECK(cudaMemsetAsync(A.group_info, 0, sizeof(wfs_group_info) * (size_t)ng, stream_));
     auto launch_class = [&](const ClassDef &d, const uint32_t *lst, uint32_t n, uint32_t *ticket, uint32_t *overflow_list,
                             cudaStream_t st) -> bool {
-        const Layout L = make_layout(d.n_cap, d.itv_cap, d.rec_cap, n_ch, tmpl_len, c.p.dt);
+        const Layout L = make_layout(d.n_cap, d.itv_cap, d.rec_cap, n_ch, tmpl_len, c.p.dt, d.bin_bits);
         if (L.total > 227 * 1024) return false;
         static const bool small_build = !(getenv("WFS_FUSED_SMALL") && atoi(getenv("WFS_FUSED_SMALL")) == 0);
         auto *kern = (small_build && d.threads <= kFusedSmallThreads) ? k_group_analyse_small : k_group_analyse;
@@ -1290,7 +1322,7 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
         WFS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, d.threads, L.total));
         if (ctas_per_sm < 1) return false;
         FusedClass K;
-        K.n_cap = d.n_cap; K.itv_cap = d.itv_cap; K.rec_cap = d.rec_cap;
+        K.n_cap = d.n_cap; K.itv_cap = d.itv_cap; K.rec_cap = d.rec_cap; K.bin_bits = d.bin_bits;
         K.list = lst; K.n_list = n; K.ticket = ticket; K.overflow_list = overflow_list;
         const int grid = (int)std::min<int64_t>(n, (int64_t)kNumSMs * ctas_per_sm);
         kern<<<grid, d.threads, L.total, st>>>(A, K);

@@ -8,7 +8,6 @@ constexpr int kFusedThreads = 1024;
 constexpr int kFusedSmallThreads = 512;     // classes up to this many threads per CTA run the 3-CTAs-per-SM build
 constexpr int kFusedMaxPhotons = 8192;      // photons of one group (13 index bits in the key)
 constexpr int kFusedMaxRecCap = 8192;       // records of one group ordered in shared memory (13 bits of record slot)
-constexpr int kFusedBins = 1024;            // time bins of the record order
 constexpr int kFusedTrigSlots = 64;         // (pulse call, total / bottom) trigger counters kept in shared memory
 
 constexpr int kFusedMaxClasses = 6;         // groups are binned by photon count
@@ -37,6 +36,7 @@ struct FusedArgs {
 
 struct FusedClass {                 // one launch of k_group_analyse: the groups of one size class
     int n_cap, itv_cap, rec_cap;    // photons / intervals / records of a group held in shared memory
+    int bin_bits;                   // time bins of the record order: 2^bin_bits per octave
     const uint32_t *list;           // group ids
     uint32_t n_list;
     uint32_t *ticket;
