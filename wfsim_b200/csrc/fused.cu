@@ -312,7 +312,8 @@ __device__ __forceinline__ void group_analyse(const FusedArgs &A, const FusedCla
         }
         __syncthreads();
         // time bins of the record order (time_bin: one sample wide at the start of the group, where the records are)
-        const int n_bins = time_bin((uint32_t)(S.tmax_q + RM + tw + key_bias + 1), bin_bits) + 1;
+        const int t_key_max = S.tmax_q + RM + tw + key_bias + 1;      // (< 2^kTimeKeyBits: the photon samples are checked above)
+        const int n_bins = time_bin((uint32_t)t_key_max, bin_bits) + 1;
         // channel offsets (exclusive scan of the counts), list of non-empty channels, list of long channels: every warp
         // scans chunks of 32 channels, the chunk totals are scanned by every warp for itself
         const int n_chunks = (n_ch + 31) >> 5;            // <= 32 (n_tpc_pmts <= 1023)
@@ -713,15 +714,11 @@ __device__ __forceinline__ void group_analyse(const FusedArgs &A, const FusedCla
             const int r0 = atomicAdd(&S.n_rec, nrec);
             const int lb = wl + l + key_bias;
             if (slot < K.itv_cap && r0 + nrec <= K.rec_cap && lb >= 0 &&
-                lb + WFS_SAMPLES_PER_RECORD * (nrec - 1) < (1 << kTimeKeyBits) &&
-                time_bin((uint32_t)(lb + WFS_SAMPLES_PER_RECORD * (nrec - 1)), bin_bits) < n_bins && plen < (1 << 20)) {
+                lb + WFS_SAMPLES_PER_RECORD * (nrec - 1) <= t_key_max && plen < (1 << 20)) {
                 s_itv[slot] = pack_itv((uint32_t)lb, (uint32_t)plen, (uint32_t)ch, (uint32_t)r0);
-                for (int i = 0; i < nrec; i++) {
-                    const uint32_t tk = (uint32_t)(lb + WFS_SAMPLES_PER_RECORD * i);
-                    s_rkey[r0 + i] = (tk << 10) | (uint32_t)ch;
-                    const int cnt = atomicAdd(&s_bin[time_bin(tk, bin_bits)], 1) + 1;
-                    if (cnt > kBinMax) atomicMax(&S.max_bin, cnt);
-                }
+                // (the records are counted into their time bins further down, one thread per record)
+                for (int i = 0; i < nrec; i++)
+                    s_rkey[r0 + i] = ((uint32_t)(lb + WFS_SAMPLES_PER_RECORD * i) << 10) | (uint32_t)ch;
             } else {
                 S.overflow = 1;
             }
@@ -928,6 +925,11 @@ __device__ __forceinline__ void group_analyse(const FusedArgs &A, const FusedCla
                 }
             }
         }
+        // the records counted into their time bins
+        for (int slot = tid; slot < n_rec; slot += blockDim.x) {
+            const int cnt = atomicAdd(&s_bin[time_bin(s_rkey[slot] >> 10, bin_bits)], 1) + 1;
+            if (cnt > kBinMax) atomicMax(&S.max_bin, cnt);
+        }
         // the photons in channel order for the record kernel; bits 27-31: samples the photon owns
         for (int k = tid; k < n_valid; k += blockDim.x) {
             const uint64_t key = s_keys[k];
@@ -941,6 +943,7 @@ __device__ __forceinline__ void group_analyse(const FusedArgs &A, const FusedCla
             }
             A.tkey[pbase + k] = (uint32_t)((key >> kShiftRem) & 0xffffffu) | ((uint32_t)n_own << 27);
         }
+        __syncthreads();
         if (S.max_bin <= kBinMax && K.rec_cap <= 2 * K.n_cap) {       // (the bin-ordered keys take the place of the gains)
             // counting sort over the time bins; inside its bin a record's place is the number of smaller (time, channel)
             // keys: one thread per record
@@ -1228,7 +1231,7 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
     const int n_ch = c.p.n_tpc_pmts, tmpl_len = c.p.dt * c.p.template_length;
     // groups by photon count: small groups get small shared-memory lists and many CTAs per SM
     struct ClassDef { int n_cap, itv_cap, rec_cap, threads, bin_bits; };
-    ClassDef defs[kFusedMaxClasses] = {{512, 512, 1024, 256, 6}, {2048, 1024, 3072, 512, 6}, {4096, 2048, 6144, 1024, 8},
+    ClassDef defs[kFusedMaxClasses] = {{512, 512, 1024, 256, 7}, {2048, 1024, 3072, 512, 7}, {4096, 2048, 6144, 1024, 8},
                                        {kFusedMaxPhotons, 4096, kFusedMaxRecCap, 1024, 7}};      // (profiles/tools/class_sweep.sh)
     int kFusedClasses = 4;
     if (const char *e = getenv("WFS_FUSED_CLASSES")) {        // experiments: "photons:intervals:records:threads[:bin_bits],..." ascending, the last one catches all
