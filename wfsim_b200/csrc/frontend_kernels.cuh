@@ -482,10 +482,18 @@ __global__ void __launch_bounds__(256)
 k_photons(GenCtx g, wfs_params p, const double *gains, int n_ch, uint32_t n_emit, uint32_t p0,
           uint32_t p1) {
     uint32_t ph = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+    // The emitter of a photon: the CTA's first and last photon are searched in the whole list by two threads, every
+    // thread then searches between those two emitters only (a few levels instead of ~18 dependent loads).
+    // (searching once per warp and walking on from there was tried and is slower, 3.5 vs 2.8 ms per 2e4 events)
+    __shared__ uint32_t s_em[2];
+    {
+        const uint32_t first = p0 + blockIdx.x * blockDim.x, last = min(first + blockDim.x, p1) - 1u;
+        if (threadIdx.x == 0) s_em[0] = upper_bound_dev(g.e_phoff, n_emit + 1, first) - 1;
+        if (threadIdx.x == blockDim.x - 1) s_em[1] = upper_bound_dev(g.e_phoff, n_emit + 1, last) - 1;
+    }
+    __syncthreads();
     if (ph >= p1) return;
-    // (the lanes of a warp search adjacent keys: all but the last levels of the search are broadcast loads already;
-    // searching once per warp and walking on from there was tried and is slower, 3.5 vs 2.8 ms per 2e4 events)
-    const uint32_t em = upper_bound_dev(g.e_phoff, n_emit + 1, ph) - 1;
+    const uint32_t em = s_em[0] + upper_bound_dev(g.e_phoff + s_em[0], s_em[1] - s_em[0] + 1, ph) - 1;
     const int32_t i = g.e_instr[em];
     const uint32_t ord = ph - g.e_phoff[g.i_emitoff[i]];
     const int type = g.i_type[i];
@@ -656,6 +664,27 @@ struct OpAdd { __device__ int64_t operator()(int64_t a, int64_t b) const { retur
 struct OpMin { __device__ int64_t operator()(int64_t a, int64_t b) const { return a < b ? a : b; } };
 struct OpMax { __device__ int64_t operator()(int64_t a, int64_t b) const { return a > b ? a : b; } };
 
+// warp-wide reductions of 64-bit integers on the 32-bit reduce unit
+__device__ __forceinline__ int64_t warp_sum_i64(int64_t v) {      // modulo 2^64, any sign: chunks of 24 + 24 + 16 bits
+    const uint64_t u = (uint64_t)v;
+    const uint32_t s0 = __reduce_add_sync(0xffffffffu, (uint32_t)(u & 0xffffffu));
+    const uint32_t s1 = __reduce_add_sync(0xffffffffu, (uint32_t)((u >> 24) & 0xffffffu));
+    const uint32_t s2 = __reduce_add_sync(0xffffffffu, (uint32_t)(u >> 48));
+    return (int64_t)((uint64_t)s0 + ((uint64_t)s1 << 24) + ((uint64_t)s2 << 48));
+}
+__device__ __forceinline__ int64_t warp_min_i64(int64_t v) {
+    const int32_t hi = (int32_t)(v >> 32);
+    const int32_t mh = __reduce_min_sync(0xffffffffu, hi);
+    const uint32_t ml = __reduce_min_sync(0xffffffffu, hi == mh ? (uint32_t)v : 0xffffffffu);
+    return (int64_t)(((uint64_t)(uint32_t)mh << 32) | ml);
+}
+__device__ __forceinline__ int64_t warp_max_i64(int64_t v) {
+    const int32_t hi = (int32_t)(v >> 32);
+    const int32_t mh = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? (uint32_t)v : 0u);
+    return (int64_t)(((uint64_t)(uint32_t)mh << 32) | ml);
+}
+
 __device__ __forceinline__ void time_moments(int64_t rel, int64_t &s, int64_t &hi2, int64_t &hilo, int64_t &lo2) {
     int64_t hi = rel >> 12, lo = rel & 4095;
     s += rel; hi2 += hi * hi; hilo += hi * lo; lo2 += lo * lo;
@@ -770,15 +799,16 @@ k_instr_truth(GenCtx g, DeviceConfig c, uint32_t n_instr, uint32_t n_ph, uint32_
     // warp partials of all accumulators, ONE barrier, then accumulator a is combined by thread a
     // (integer sums / min / max: the order does not matter, the result is deterministic)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // (warp reductions through the 32-bit reduce instruction: counters directly, 64-bit sums in three chunks, minima /
+    // maxima by high word then low word -- a fifth of the instructions of 35 64-bit shuffle trees, which were three
+    // quarters of this kernel for an instruction of a few hundred photons)
 #pragma unroll
     for (int a = 0; a < A_COUNT; a++) {
-        int64_t r = v[a];
         const bool is_min = a == A_TMIN || a == A_ETMIN, is_max = a == A_TMAX || a == A_ETMAX || a == A_PTMAX;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const int64_t u = __shfl_xor_sync(0xffffffffu, r, o);
-            r = is_min ? (u < r ? u : r) : is_max ? (u > r ? u : r) : r + u;
-        }
+        const bool is_count = a == A_NPH || a == A_NDPE || a == A_NTRIG || a == A_NPH_B || a == A_NDPE_B ||
+                              a == A_NTRIG_B || a == A_NPHALL || a == A_NE || a == A_NAP;
+        const int64_t r = is_min ? warp_min_i64(v[a]) : is_max ? warp_max_i64(v[a])
+                          : is_count ? (int64_t)__reduce_add_sync(0xffffffffu, (uint32_t)v[a]) : warp_sum_i64(v[a]);
         if (lane == 0) sm[warp][a] = r;
     }
     __syncthreads();
