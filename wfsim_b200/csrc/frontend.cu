@@ -561,9 +561,11 @@ static void generate(Handle *H, Frontend &F, cudaStream_t s, uint64_t seed, int6
         FLAUNCH(k_gg_sum, dim3((unsigned)(i1 - i0), (unsigned)ny), 128, g, (uint32_t)i0, (uint32_t)i1, F.b_ggpartial.as<double>());
         FLAUNCH(k_gg_mean, div_up(i1 - i0, 128), 128, g, (uint32_t)i0, (uint32_t)i1, ny, F.b_ggpartial.as<double>());
     }
-    if (p1 > p0)
+    if (p1 > p0) {
+        FLAUNCH(k_photon_emitter, div_up(e1 - e0, 256), 256, g, (uint32_t)e0, (uint32_t)e1);
         FLAUNCH(k_photons, div_up(p1 - p0, 256), 256, g, p, H->cfg.gains, p.n_tpc_pmts, (uint32_t)e1,
                 (uint32_t)p0, (uint32_t)p1);
+    }
     n_emit = e1;
     n_ph = p1;
     WFS_CUDA_CHECK(cudaGetLastError());

@@ -476,24 +476,31 @@ __global__ void k_gg_mean(GenCtx g, uint32_t i0, uint32_t i1, int ny, const doub
     g.i_ggmean[i] = n ? s / (double)n : 0.0;
 }
 
+// The emitter of every photon, left in ph_instr for k_photons (which replaces it by the instruction): a warp takes 32
+// emitters and writes the index of each over its photons, lanes side by side.  (k_photons used to search e_phoff per
+// photon: ~18 dependent loads, 40 % of its stall samples and a fifth of its instructions.)
+__global__ void __launch_bounds__(256)
+k_photon_emitter(GenCtx g, uint32_t e0, uint32_t e1) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t e = e0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t q0 = e < e1 ? g.e_phoff[e] : 0u, q1 = e < e1 ? g.e_phoff[e + 1] : 0u;
+    for (int k = 0; k < 32; k++) {
+        const uint32_t a = __shfl_sync(0xffffffffu, q0, k), b = __shfl_sync(0xffffffffu, q1, k);
+        const int32_t ek = (int32_t)(e - lane + (uint32_t)k);
+        for (uint32_t q = a + lane; q < b; q += 32u) g.ph_instr[q] = ek;
+    }
+}
+
 // Per photon: channel (s1.py:138-159 / s2.py:616-682), arrival time (s1.py:162-238 /
 // s2.py:504-557, pulse.py:321-341), then the PMT stage (pulse.py:53-56,76-79,95-103).
 __global__ void __launch_bounds__(256)
 k_photons(GenCtx g, wfs_params p, const double *gains, int n_ch, uint32_t n_emit, uint32_t p0,
           uint32_t p1) {
     uint32_t ph = p0 + blockIdx.x * blockDim.x + threadIdx.x;
-    // The emitter of a photon: the CTA's first and last photon are searched in the whole list by two threads, every
-    // thread then searches between those two emitters only (a few levels instead of ~18 dependent loads).
-    // (searching once per warp and walking on from there was tried and is slower, 3.5 vs 2.8 ms per 2e4 events)
-    __shared__ uint32_t s_em[2];
-    {
-        const uint32_t first = p0 + blockIdx.x * blockDim.x, last = min(first + blockDim.x, p1) - 1u;
-        if (threadIdx.x == 0) s_em[0] = upper_bound_dev(g.e_phoff, n_emit + 1, first) - 1;
-        if (threadIdx.x == blockDim.x - 1) s_em[1] = upper_bound_dev(g.e_phoff, n_emit + 1, last) - 1;
-    }
-    __syncthreads();
     if (ph >= p1) return;
-    const uint32_t em = s_em[0] + upper_bound_dev(g.e_phoff + s_em[0], s_em[1] - s_em[0] + 1, ph) - 1;
+    const uint32_t em = (uint32_t)g.ph_instr[ph];        // left there by k_photon_emitter
+    // (tried before that: one search per warp and walking on from there, 3.5 vs 2.8 ms per 2e4 events; the search
+    // narrowed to the emitters of the CTA's first and last photon, 305 vs 297 us per batch)
     const int32_t i = g.e_instr[em];
     const uint32_t ord = ph - g.e_phoff[g.i_emitoff[i]];
     const int type = g.i_type[i];
