@@ -435,14 +435,14 @@ static GenCtx make_ctx(Frontend &F, uint64_t seed) {
     g.i_dmean = F.b_dmean.as<double>(); g.i_dspread = F.b_dspread.as<double>();
     g.i_nemit = F.b_nemit.as<uint32_t>(); g.i_emitoff = F.b_emitoff.as<uint32_t>();
     g.i_nhits = F.b_nhits.as<int64_t>(); g.i_acc = F.b_acc.as<int64_t>();
-    g.cdf = F.b_cdf.as<double>(); g.cdf_ok = F.b_cdfok.as<int32_t>();
+    g.cdf = F.b_cdf.as<double>(); g.cdf_ok = F.b_cdfok.as<int32_t>(); g.cdf_guide = F.b_cdfguide.as<uint16_t>();
     g.e_t = F.b_et.as<int64_t>(); g.e_instr = F.b_einstr.as<int32_t>();
     g.e_nph = F.b_enph.as<uint32_t>(); g.e_phoff = F.b_ephoff.as<uint32_t>();
     g.ph_t = F.b_pht.as<int64_t>(); g.ph_ch = F.b_phch.as<int32_t>(); g.ph_gain = F.b_phgain.as<double>();
     g.ph_instr = F.b_phinstr.as<int32_t>(); g.ph_flags = F.b_phflags.as<uint8_t>();
     g.ph_nap = F.b_phnap.as<uint8_t>(); g.ap_off = F.b_apoff.as<uint32_t>();
     g.spe_ppf = F.spe_ppf; g.spe_row = F.spe_row; g.spe_len = F.spe_len;
-    g.lum_cdf = F.lum_cdf; g.lum_t = F.lum_t; g.lum_len = F.lum_len;
+    g.lum_cdf = F.lum_cdf; g.lum_t = F.lum_t; g.lum_len = F.lum_len; g.lum_guide = F.lum_guide;
     g.n_ap = F.H->cfg.p.enable_pmt_afterpulses ? F.n_ap : 0;
     for (int e = 0; e < WFS_MAX_AP_ELEMENTS; e++) {
         g.ap_is_uniform[e] = F.ap_is_uniform[e];
@@ -530,7 +530,8 @@ static void generate(Handle *H, Frontend &F, cudaStream_t s, uint64_t seed, int6
         FLAUNCH(k_pattern_diffuse, (unsigned)(i1 - i0), 128, g, (int32_t)F.first_dev_row, F.s2_pat, (int)p.n_tpc_pmts,
                 p.tpc_radius, F.b_pattern.as<float>());
         FLAUNCH(k_pattern_cdf, div_up(F.n_pattern_rows, 64), 64, F.n_pattern_rows, (int)p.n_tpc_pmts,
-                F.b_pattern.as<float>(), H->cfg.gains, F.b_cdf.as<double>(), F.b_cdfok.as<int32_t>());
+                F.b_pattern.as<float>(), H->cfg.gains, F.b_cdf.as<double>(), F.b_cdfok.as<int32_t>(),
+                F.b_cdfguide.as<uint16_t>());
     }
     F.b_et.reserve_keep(8 * (size_t)std::max<int64_t>(e1, 1), 8 * (size_t)e0, s);
     F.b_einstr.reserve_keep(4 * (size_t)std::max<int64_t>(e1, 1), 4 * (size_t)e0, s);
@@ -778,6 +779,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
         F.b_pattern.reserve(sizeof(float) * (size_t)nrows * n_ch);
         F.b_cdf.reserve(sizeof(double) * (size_t)nrows * n_ch);
         F.b_cdfok.reserve(sizeof(int32_t) * nrows);
+        F.b_cdfguide.reserve(sizeof(uint16_t) * (size_t)nrows * (kCdfGuide + 1));
         if (n_host_rows) up(F.b_pattern, h_rows.data(), sizeof(float) * h_rows.size());
         if (!dev_rows.empty())
             FLAUNCH(k_pattern_eval, div_up(nprim * 32, 128), 128, (uint32_t)nprim, (int32_t)n_host_rows,
@@ -785,7 +787,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
                     F.has_xy ? F.b_ixo.as<double>() : nullptr, F.has_xy ? F.b_iyo.as<double>() : nullptr,
                     F.b_ipat.as<int32_t>(), F.s1_pat, F.s2_pat, n_ch, F.b_pattern.as<float>());
         FLAUNCH(k_pattern_cdf, div_up(nrows, 64), 64, nrows, n_ch, F.b_pattern.as<float>(), H->cfg.gains,
-                F.b_cdf.as<double>(), F.b_cdfok.as<int32_t>());
+                F.b_cdf.as<double>(), F.b_cdfok.as<int32_t>(), F.b_cdfguide.as<uint16_t>());
         F.cdf_rows = (dev_rows.empty() && nrows <= 16) ? nrows : -1;
         F.cdf_hash = rows_hash;
     }
@@ -1382,7 +1384,7 @@ static void simulate_batch(Handle *H, Lane &L, Plan &P, int64_t batch_index, con
 // workspaces and share the device tables.
 static void clone_tables(const Frontend &a, Frontend &b) {
     b.spe_ppf = a.spe_ppf; b.spe_row = a.spe_row; b.n_spe_rows = a.n_spe_rows; b.spe_len = a.spe_len;
-    b.lum_cdf = a.lum_cdf; b.lum_t = a.lum_t; b.lum_len = a.lum_len;
+    b.lum_cdf = a.lum_cdf; b.lum_t = a.lum_t; b.lum_len = a.lum_len; b.lum_guide = a.lum_guide;
     b.n_ap = a.n_ap;
     for (int e = 0; e < WFS_MAX_AP_ELEMENTS; e++) {
         b.ap_is_uniform[e] = a.ap_is_uniform[e];
@@ -1439,7 +1441,7 @@ static void release_frontend_buffers(Frontend &F) {
     DevBuf *all[] = {&F.b_itype, &F.b_itime, &F.b_ix, &F.b_iy, &F.b_iz, &F.b_iamp, &F.b_igidx, &F.b_ilce,
                      &F.b_iscg, &F.b_icy, &F.b_ipat, &F.b_ivd, &F.b_idl, &F.b_ixo, &F.b_iyo, &F.b_irecoil, &F.b_ilrow, &F.b_ioptfirst, &F.b_ioptn,
                      &F.b_igglo, &F.b_igghi, &F.b_iggfrac, &F.b_iggmean, &F.b_ggpartial, &F.b_dmean, &F.b_dspread, &F.b_nemit, &F.b_emitoff,
-                     &F.b_nhits, &F.b_acc, &F.b_titems, &F.b_cdf, &F.b_cdfok, &F.b_pattern, &F.b_et, &F.b_einstr,
+                     &F.b_nhits, &F.b_acc, &F.b_titems, &F.b_cdf, &F.b_cdfok, &F.b_cdfguide, &F.b_pattern, &F.b_et, &F.b_einstr,
                      &F.b_enph, &F.b_ephoff, &F.b_pht, &F.b_phch, &F.b_phgain, &F.b_phinstr, &F.b_phflags,
                      &F.b_phnap, &F.b_apoff, &F.b_picount, &F.b_pioff, &F.b_pecount, &F.b_peoff, &F.b_irun, &F.b_pcgroup,
                      &F.b_pcrank, &F.b_trig, &F.b_records, &F.b_records2, &F.b_groups, &F.b_scal, &F.b_phstart,
@@ -1600,6 +1602,11 @@ void Handle::frontend_init(const wfs_tables &t) {
         F->lum_cdf = upload_table(t.lum_cdf, (size_t)t.lum_len, owned);
         F->lum_t = upload_table(t.lum_t, (size_t)t.lum_len, owned);
         F->lum_len = t.lum_len;
+        // guide[c] = first entry above c / kLumGuide: u in [c, c + 1) / kLumGuide is searched between guide[c] and guide[c + 1]
+        std::vector<uint32_t> guide(kLumGuide + 1);
+        for (int c = 0; c <= kLumGuide; c++)
+            guide[c] = (uint32_t)(std::upper_bound(t.lum_cdf, t.lum_cdf + t.lum_len, (double)c / (double)kLumGuide) - t.lum_cdf);
+        F->lum_guide = upload_table(guide.data(), guide.size(), owned);
     }
     F->n_ap = std::min<int32_t>(t.n_ap_elements, WFS_MAX_AP_ELEMENTS);
     for (int e = 0; e < WFS_MAX_AP_ELEMENTS; e++) {

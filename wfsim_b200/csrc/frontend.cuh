@@ -71,6 +71,7 @@ struct Frontend {
     int32_t *spe_row = nullptr;
     int32_t n_spe_rows = 0, spe_len = 0;
     double *lum_cdf = nullptr, *lum_t = nullptr;
+    uint32_t *lum_guide = nullptr;      // guide of the search in lum_cdf (interp_table)
     int32_t lum_len = 0;
     int32_t n_ap = 0;
     int32_t ap_is_uniform[WFS_MAX_AP_ELEMENTS];
@@ -100,7 +101,7 @@ struct Frontend {
     DevBuf b_itype, b_itime, b_ix, b_iy, b_iz, b_iamp, b_igidx, b_ilce, b_iscg, b_icy, b_ipat,
         b_ivd, b_idl, b_ixo, b_iyo, b_irecoil, b_ilrow, b_ioptfirst, b_ioptn, b_igglo, b_igghi, b_iggfrac, b_iggmean, b_ihsr, b_ihsa, b_ilgap, b_ilgapmax, b_ile0, b_ilavgt,
         b_ggpartial,
-        b_dmean, b_dspread, b_nemit, b_emitoff, b_nhits, b_acc, b_titems, b_cdf, b_cdfok, b_pattern,
+        b_dmean, b_dspread, b_nemit, b_emitoff, b_nhits, b_acc, b_titems, b_cdf, b_cdfok, b_cdfguide, b_pattern,
         b_et, b_einstr, b_enph, b_ephoff, b_pht, b_phch, b_phgain, b_phinstr, b_phflags, b_phnap,
         b_apoff, b_picount, b_pioff, b_pecount, b_peoff, b_irun, b_pcgroup, b_pcrank, b_trig, b_records, b_records2,
         b_groups, b_scal, b_phstart, b_gstart, b_gt0, b_grun0, b_pmtcnt, b_pmtarea;

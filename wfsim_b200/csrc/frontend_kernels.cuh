@@ -46,6 +46,7 @@ struct GenCtx {
     // pattern CDF rows
     double *cdf;          // [rows][n_ch]
     int32_t *cdf_ok;      // [rows]
+    const uint16_t *cdf_guide;   // [rows][kCdfGuide + 1], see k_pattern_cdf
     // emitters
     int64_t *e_t;
     int32_t *e_instr;
@@ -62,6 +63,7 @@ struct GenCtx {
     const int32_t *spe_row;
     int32_t spe_len;
     const double *lum_cdf, *lum_t;
+    const uint32_t *lum_guide;      // [kLumGuide + 1] guide of the search in lum_cdf (see k_pattern_cdf)
     int32_t lum_len;
     int32_t n_ap;
     int32_t ap_is_uniform[WFS_MAX_AP_ELEMENTS];
@@ -133,8 +135,12 @@ __global__ void k_widen_u8(const uint8_t *a, uint32_t *b, uint32_t n) {
 
 // Pattern row -> normalised CDF (np.random.choice(p=...) builds exactly this: cumsum, /= last;
 // s1.py:148-158, s2.py:646-677).  One thread per row.
+// Beside every row a guide for the search of k_photons: guide[j] = first channel whose CDF value exceeds j / kCdfGuide,
+// so that the channel of u lies in [guide[j], guide[j + 1]] for j = floor(u * kCdfGuide) -- a couple of entries
+// instead of log2(n_ch) dependent loads (the result is the same upper bound).
+constexpr int kCdfGuide = 256;
 __global__ void k_pattern_cdf(int64_t rows, int n_ch, const float *pattern, const double *gains,
-                              double *cdf, int32_t *ok) {
+                              double *cdf, int32_t *ok, uint16_t *guide) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     const float *p = pattern + r * n_ch;
@@ -150,6 +156,13 @@ __global__ void k_pattern_cdf(int64_t rows, int n_ch, const float *pattern, cons
     if (bad || !(s > 0.0)) { ok[r] = 0; return; }
     for (int ch = 0; ch < n_ch; ch++) c[ch] /= s;
     ok[r] = 1;
+    uint16_t *gd = guide + r * (kCdfGuide + 1);
+    int i = 0;
+    for (int j = 0; j <= kCdfGuide; j++) {
+        const double thr = (double)j / (double)kCdfGuide;
+        while (i < n_ch && c[i] <= thr) i++;
+        gd[j] = (uint16_t)i;
+    }
 }
 
 // Pattern rows of the instructions whose map lives on the device as a regular grid (rows >=
@@ -416,11 +429,22 @@ __global__ void k_emitters(GenCtx g, wfs_params p, uint32_t n_instr, uint32_t e0
     g.e_nph[e] = (uint32_t)nph;
 }
 
-__device__ __forceinline__ double interp_table(const double *xp, const double *fp, int n, double x) {
+// `guide` (optional, x in [0, 1)): guide[c] = upper bound of c / kLumGuide in xp, built on the host at wfs_create --
+// the search then runs between guide[c] and guide[c + 1] for c = floor(x * kLumGuide) (same result)
+constexpr int kLumGuide = 1024;
+__device__ __forceinline__ double interp_table(const double *xp, const double *fp, int n, double x,
+                                               const uint32_t *guide = nullptr) {
     // np.interp semantics for ascending xp
     if (x <= xp[0]) return fp[0];
     if (x >= xp[n - 1]) return fp[n - 1];
-    uint32_t j = upper_bound_dev(xp, (uint32_t)n, x) - 1;
+    uint32_t j;
+    if (guide) {
+        const int cell = (int)(x * (double)kLumGuide);
+        const uint32_t lo = guide[cell], hi = guide[cell + 1];
+        j = lo + upper_bound_dev(xp + lo, hi - lo, x) - 1;
+    } else {
+        j = upper_bound_dev(xp, (uint32_t)n, x) - 1;
+    }
     double slope = (fp[j + 1] - fp[j]) / (xp[j + 1] - xp[j]);
     return slope * (x - xp[j]) + fp[j];
 }
@@ -513,7 +537,10 @@ k_photons(GenCtx g, wfs_params p, const double *gains, int n_ch, uint32_t n_emit
     const int row = g.i_pat[i];
     if (g.cdf_ok[row]) {
         const double u = u01_32(w0.v[0]);
-        ch = (int)upper_bound_dev(g.cdf + (int64_t)row * n_ch, (uint32_t)n_ch, u);
+        const uint16_t *gd = g.cdf_guide + (int64_t)row * (kCdfGuide + 1);
+        const int cell = (int)(u * (double)kCdfGuide);           // u < 1
+        const uint32_t lo = gd[cell], hi = gd[cell + 1];
+        ch = (int)(lo + upper_bound_dev(g.cdf + (int64_t)row * n_ch + lo, hi - lo, u));
         if (ch >= n_ch) ch = n_ch - 1;
     }
     float zs, zt;
@@ -551,7 +578,7 @@ k_photons(GenCtx g, wfs_params p, const double *gains, int n_ch, uint32_t n_emit
         if (p.s2_luminescence_model == 0 && g.i_lgap)
             t += (int64_t)lumw_time(g, g.i_lgap[i], g.i_le0[i], g.i_lavgt[i], u01_32(w0.v[1]));
         else if (p.s2_luminescence_model == 0 && g.lum_len > 0)
-            t += (int64_t)interp_table(g.lum_cdf, g.lum_t, g.lum_len, u01_32(w0.v[1]));
+            t += (int64_t)interp_table(g.lum_cdf, g.lum_t, g.lum_len, u01_32(w0.v[1]), g.lum_guide);
         else if (p.s2_luminescence_model == 1 && g.gf_rows > 0) {   // s2.py:405-409
             const int col = (int)(((uint64_t)w0.v[1] * (uint32_t)g.gf_cols) >> 32);
             t += (int64_t)g.gf_t[(int64_t)g.i_lrow[i] * g.gf_cols + col] - (int64_t)p.gf_avgt;
