@@ -788,6 +788,7 @@ k_instr_truth(GenCtx g, DeviceConfig c, uint32_t n_instr, uint32_t n_ph, uint32_
     v[A_TMIN] = LLONG_MAX; v[A_TMAX] = LLONG_MIN; v[A_ETMIN] = LLONG_MAX; v[A_ETMAX] = LLONG_MIN;
     v[A_PTMAX] = LLONG_MIN;
     const int dt = c.p.dt;
+    int r0 = (int)(T0 % dt); if (r0 < 0) r0 += dt;          // T0 mod dt (floor)
     for (uint32_t q = q0 + tid; q < q1; q += nthr) {
         const int64_t t = g.ph_t[q];
         const int ch = g.ph_ch[q];
@@ -801,7 +802,15 @@ k_instr_truth(GenCtx g, DeviceConfig c, uint32_t n_instr, uint32_t n_ph, uint32_
         v[A_PTMAX] = t > v[A_PTMAX] ? t : v[A_PTMAX];
         const double gain = g.ph_gain[q];
         const int dpe = g.ph_flags[q] & 1;
-        int64_t q_ = t / dt; int r = (int)(t - q_ * dt); if (r < 0) r += dt;
+        // t mod dt (floor) from the instruction's remainder and the photon's offset to it: 32-bit arithmetic unless the
+        // photon is more than 2 s from its instruction
+        int r;
+        const int64_t rel = t - T0;
+        if (rel >= 0 && rel < ((int64_t)1 << 31)) {
+            r = (int)(((uint32_t)rel % (uint32_t)dt + (uint32_t)r0) % (uint32_t)dt);
+        } else {
+            int64_t q_ = t / dt; r = (int)(t - q_ * dt); if (r < 0) r += dt;
+        }
         const double thr = (double)(c.p.baseline - 1 - c.zle_thr[ch]) - 0.5;
         const bool above = gain * c.current_max[r] * c.p.current_2_adc > thr;
         const int64_t area = llrint(gain / gch * kAreaScale);

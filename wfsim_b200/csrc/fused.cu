@@ -1144,10 +1144,23 @@ k_group_records(FusedArgs A) {
                 h[3] = ((uint32_t)(uint16_t)dt) | ((uint32_t)(uint16_t)ch << 16);
                 h[4] = (uint32_t)plen;
                 h[5] = (uint32_t)(uint16_t)rec_i;
-                // zeros behind `length` (the last record of a pulse)
+                if (length < SPR && (length & 1)) h[6 + (length >> 1)] &= 0xffffu;
+            }
+            // zeros behind `length` (the last record of a pulse): two lanes per record, a half of the words each, 16-byte
+            // stores between the unaligned ends (one lane walking ~45 words was a seventh of the kernel's instructions)
+            if ((lane & (kTileRecs - 1)) < nr) {
+                const int rl = lane & (kTileRecs - 1);
+                const uint4 dd = s_desc[rl];
+                const int plen = (int)(dd.y & 0xfffffu);
+                const int rec_i = (int)(((dd.y >> 20) & 0xfffu) | (((dd.z >> 27) & 3u) << 12));
+                const int length = min(plen - rec_i * SPR, SPR);
                 if (length < SPR) {
-                    if (length & 1) h[6 + (length >> 1)] &= 0xffffu;
-                    for (int wd = (length + 1) >> 1; wd < SPR / 2; wd++) h[6 + wd] = 0u;
+                    const int w_lo = (length + 1) >> 1, w_mid = (w_lo + SPR / 2) >> 1;
+                    uint32_t *p = s_tile + hw + rl * 61 + 6 + (lane < kTileRecs ? w_lo : w_mid);
+                    int n = lane < kTileRecs ? w_mid - w_lo : SPR / 2 - w_mid;
+                    for (; n > 0 && ((uintptr_t)p & 15u); n--) *p++ = 0u;
+                    for (; n >= 4; n -= 4, p += 4) *reinterpret_cast<uint4 *>(p) = make_uint4(0u, 0u, 0u, 0u);
+                    for (; n > 0; n--) *p++ = 0u;
                 }
             }
             __syncwarp();
