@@ -1244,9 +1244,10 @@ bool Backend::run_fused(const PhotonBatch &b, uint8_t *records_out, int64_t cap_
     const int n_ch = c.p.n_tpc_pmts, tmpl_len = c.p.dt * c.p.template_length;
     // groups by photon count: small groups get small shared-memory lists and many CTAs per SM
     struct ClassDef { int n_cap, itv_cap, rec_cap, threads, bin_bits; };
-    ClassDef defs[kFusedMaxClasses] = {{512, 512, 1024, 256, 7}, {2048, 1024, 3072, 512, 7}, {4096, 2048, 6144, 1024, 8},
+    ClassDef defs[kFusedMaxClasses] = {{256, 256, 512, 128, 6}, {512, 512, 1024, 256, 7}, {2048, 1024, 3072, 512, 7},
+                                       {4096, 2048, 6144, 1024, 8},
                                        {kFusedMaxPhotons, 4096, kFusedMaxRecCap, 1024, 7}};      // (profiles/tools/class_sweep.sh)
-    int kFusedClasses = 4;
+    int kFusedClasses = 5;
     if (const char *e = getenv("WFS_FUSED_CLASSES")) {        // experiments: "photons:intervals:records:threads[:bin_bits],..." ascending, the last one catches all
         int n = 0;
         const char *p = e;
