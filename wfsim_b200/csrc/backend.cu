@@ -111,17 +111,54 @@ __global__ void k_group_tmin(PhotonBatch b, DeviceConfig c, int64_t *group_tmin,
             t = b.t[i];
         }
     }
-    // warp-aggregate: one atomic per distinct group in the warp
-    unsigned m = __match_any_sync(0xffffffffu, g);
-    int lane = threadIdx.x & 31;
-    int64_t mn = t;
-    for (int o = 0; o < 32; o++) {
-        int64_t other = __shfl_sync(0xffffffffu, t, o);
-        if ((m >> o) & 1u) mn = other < mn ? other : mn;
+    // Photons come instruction by instruction, so a warp -- mostly a whole CTA -- sees one group: the minimum on the
+    // 32-bit reduce unit (high word, then low word), one atomic per CTA through shared memory.  A warp with several
+    // groups takes one atomic per distinct group.
+    __shared__ int64_t s_mn[32];
+    __shared__ int s_g[32], s_cnt[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31) >> 5;
+    const unsigned vm = __ballot_sync(0xffffffffu, valid);
+    const int g0 = __shfl_sync(0xffffffffu, g, vm ? __ffs(vm) - 1 : 0);
+    const bool uniform = __all_sync(0xffffffffu, !valid || g == g0);
+    int wg = -1, wcnt = 0;
+    int64_t wmn = LLONG_MAX;
+    if (uniform) {
+        if (vm) {
+            const int32_t hi = (int32_t)(t >> 32);
+            const int32_t mh = __reduce_min_sync(0xffffffffu, hi);
+            const uint32_t ml = __reduce_min_sync(0xffffffffu, hi == mh ? (uint32_t)t : 0xffffffffu);
+            wmn = (int64_t)(((uint64_t)(uint32_t)mh << 32) | ml);
+            wg = g0; wcnt = __popc(vm);
+        }
+    } else {
+        const unsigned m = __match_any_sync(0xffffffffu, g);
+        int64_t mn = t;
+        for (int o = 0; o < 32; o++) {
+            int64_t other = __shfl_sync(0xffffffffu, t, o);
+            if ((m >> o) & 1u) mn = other < mn ? other : mn;
+        }
+        if (valid && (m & ((1u << lane) - 1u)) == 0) {
+            atomicMin((long long *)&group_tmin[g], (long long)mn);
+            if (group_nvalid) atomicAdd(&group_nvalid[g], (uint32_t)__popc(m));   // invalid lanes carry g = -1
+        }
     }
-    if (valid && (m & ((1u << lane) - 1u)) == 0) {
-        atomicMin((long long *)&group_tmin[g], (long long)mn);
-        if (group_nvalid) atomicAdd(&group_nvalid[g], (uint32_t)__popc(m));   // invalid lanes carry g = -1
+    if (lane == 0) { s_g[warp] = wg; s_mn[warp] = wmn; s_cnt[warp] = wcnt; }
+    __syncthreads();
+    if (warp == 0) {
+        // runs of warps with the same group: their first warp's lane sends the atomic for the run
+        const int mg = lane < n_warps ? s_g[lane] : -1;
+        const unsigned same = __match_any_sync(0xffffffffu, mg);
+        if (mg >= 0 && (same & ((1u << lane) - 1u)) == 0) {
+            int64_t mn = LLONG_MAX;
+            uint32_t cnt = 0;
+            for (unsigned rest = same; rest; rest &= rest - 1) {
+                const int w = __ffs(rest) - 1;
+                mn = s_mn[w] < mn ? s_mn[w] : mn;
+                cnt += (uint32_t)s_cnt[w];
+            }
+            atomicMin((long long *)&group_tmin[mg], (long long)mn);
+            if (group_nvalid) atomicAdd(&group_nvalid[mg], cnt);
+        }
     }
 }
 
