@@ -13,9 +13,21 @@ for r in rows[2:]:
     launches.append({'kernel': r[H.index('Kernel Name')].split('(')[0], 'grid': int(float(r[H.index('launch__grid_size')])),
                      'block': int(float(r[H.index('launch__block_size')])), 'us': col(r, 'gpu__time_duration.sum'),
                      'dram_read': col(r, 'dram__bytes_read.sum'), 'dram_write': col(r, 'dram__bytes_write.sum')})
+# The lanes' batches interleave in the capture, so one batch is put together from class averages: every size class
+# (kernel, threads per CTA, full grid or not) and k_group_records launch once per device batch.
+classes = {}
+for l in launches:
+    key = (l['kernel'], l['block'], l['grid'] >= 148)
+    classes.setdefault(key, []).append(l)
+launches = []
+for key, ls in sorted(classes.items()):
+    n = len(ls)
+    launches.append({'kernel': key[0], 'block': key[1], 'grid': int(sum(l['grid'] for l in ls) / n), 'captured': n,
+                     'us': sum(l['us'] for l in ls) / n, 'dram_read': sum(l['dram_read'] for l in ls) / n,
+                     'dram_write': sum(l['dram_write'] for l in ls) / n})
 tot = sum(l['dram_read'] + l['dram_write'] for l in launches)
 json.dump({'source': f'{name}: ncu --set full --clock-control none of one device batch of the C1 workload (4000 events, 5.4e6 '
                      'photons, 4.98e6 records): dram__bytes_read.sum + dram__bytes_write.sum summed over the size-class '
-                     'launches of k_group_analyse / k_group_analyse_small and k_group_records',
+                     'launches of k_group_analyse / k_group_analyse_small and k_group_records (averages per class over the captured launches)',
            'dram_bytes_per_batch': tot, 'launches': launches}, open(out, 'w'), indent=1)
 print(f'{len(launches)} launches, {tot / 1e9:.3f} GB per batch')

@@ -982,10 +982,19 @@ k_zle(int64_t n_wtot, DeviceConfig c, const WinMeta *__restrict__ meta,
             const uint8_t *f = flag8 + blk0;
             for (int b = 0; b < nblk; b++) {
                 // most flag bytes are zero (baseline): skip them eight at a time
-                if (((reinterpret_cast<uintptr_t>(f + b) & 7) == 0) && b + 8 <= nblk &&
-                    *reinterpret_cast<const unsigned long long *>(f + b) == 0ull) {
-                    b += 7;
-                    continue;
+                if (((reinterpret_cast<uintptr_t>(f + b) & 7) == 0) && b + 8 <= nblk) {
+                    const unsigned long long word = *reinterpret_cast<const unsigned long long *>(f + b);
+                    if (word == 0ull) {
+                        b += 7;
+                        continue;
+                    }
+                    // inside a heavy S2 every sample is below threshold: 64 flagged samples that continue the open
+                    // interval only move its end (one thread walks the ~40 000 samples of such a window)
+                    if (word == ~0ull && last != kNeg && b * kBlk - last <= H) {
+                        last = b * kBlk + 8 * kBlk - 1;
+                        b += 7;
+                        continue;
+                    }
                 }
                 uint32_t byte = f[b];
                 while (byte) {

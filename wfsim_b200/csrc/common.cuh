@@ -70,7 +70,7 @@ static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); 
 // than half of this rank's cores (WFS_BLOCKING_SYNC=0/1 overrides).
 cudaError_t stream_sync(cudaStream_t s);
 int host_cores_per_rank();   // cores of the affinity mask / LOCAL_WORLD_SIZE (transport.cu)
-int default_lanes(bool records_to_host);   // host threads driving device batches side by side (frontend.cu)
+int default_lanes();         // host threads driving device batches side by side (frontend.cu)
 
 constexpr int kSegSortMax = 8192;   // items per segment of Primitives::segment_sort_pairs
 

@@ -191,10 +191,7 @@ static int64_t env_i64(const char *name, int64_t dflt) {
 // gap (rawdata.py:63) plus the longest delay of a secondary instruction an S2 can spawn (photo-ionisation
 // electrons: the end of the coarse delay grid, afterpulse.py:63-80; photo-electric electrons: 6 sigma
 // of their delay, :105-115).  Device batches, plugin pieces and GPU shards are all cut at such gaps only.
-int default_lanes(bool records_to_host) {
-    if (host_cores_per_rank() < 12) return 3;
-    return records_to_host ? 4 : 5;      // (the record expanders want the cores when the records leave the device)
-}
+int default_lanes() { return host_cores_per_rank() >= 12 ? 4 : 3; }
 
 static double quiet_gap_ns(const Handle *H) {
     const wfs_params &p = H->cfg.p;
@@ -1495,11 +1492,11 @@ static int run_plan(Handle *H, Plan &P, uint64_t seed, wfs_outputs *out, wfs_cou
     so.split = so.compact && H->compact_mode == 1 && Handle::page_locked(out->records);
     if (so.split) H->split.init(H->host_pool()->size());
     const int64_t nb = (int64_t)P.batches.size();
-    // lanes: host threads that each drive every n-th device batch on their own streams.  With the records staying on
-    // the device five keep the GPU busy (1e5 C1 events: 53.4 / 47.9 / 47.8 ms with four / five / six); with the records
-    // going to the host four, next to the record expanders (end to end 379 / 390 / 401 ms); three on a rank with
-    // fewer than 12 cores.
-    const int n_lanes = dump ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(env_i64("WFS_LANES", default_lanes(!resident && out && out->records)), 8), nb));
+    // lanes: host threads that each drive every n-th device batch on their own streams.  Four keep the GPU busy when
+    // the rank has the cores for them next to the record expanders; three otherwise.  (Five: 44.2 against 45.9 ms per
+    // 1e5 C1 events with the records staying on the device, but 390 against 379 ms end to end, and the C3 sample that
+    // follows C1 and C2 in one process fell from 363 to 527 ms per step -- not taken.)
+    const int n_lanes = dump ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(env_i64("WFS_LANES", default_lanes()), 8), nb));
     ensure_lanes(H, std::max(n_lanes, 1));
     cudaStream_t s = H->stream;
     WFS_CUDA_CHECK(cudaEventRecord(H->ev_a, s));
