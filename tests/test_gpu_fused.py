@@ -96,6 +96,33 @@ def test_fused_with_dead_pmts_and_per_pmt_truth():
     sim.close()
 
 
+def test_fused_with_few_live_pmts_long_channel_lists():
+    """All but 40 PMTs switched off: the photons of a group crowd on a few channels -- channel lists longer than the
+    rank sort takes (a warp's bitonic network orders them), piled-up channels evaluated by a warp, PMT afterpulses on
+    top of the signal (photons whose samples another pulse call reaches), and hundreds of records in one time bin of
+    the record order."""
+    from wfsim_b200.resource import Resource
+    from wfsim_b200.simulator import Simulator
+    from tests.conftest import load_c0_config
+    from tests.golden.synth_tables import pmt_ap_tables
+    from tests.test_gpu_afterpulse_plugin import spe
+    cfg = load_c0_config(enable_pmt_afterpulses=True)
+    gains = cfg['gains'].copy()
+    live = np.r_[np.arange(0, 250, 10), np.arange(260, 490, 16)]
+    dead = np.setdiff1d(np.arange(len(gains)), live)
+    gains[dead] = 0
+    cfg['gains'] = gains
+    uniq, row = spe()
+    sim = Simulator(cfg, resource=Resource(cfg, spe_ppf=uniq, spe_row=row, uniform_to_pmt_ap=pmt_ap_tables()))
+    inst = c0_like(12, seed=13, e_range=(4, 12), s1_per_kev=120.0)
+    a, b, ca, cb = both_paths(sim, inst, seed=17)
+    assert_same(a, b, ca, cb)
+    per_channel = np.bincount(a['raw_records']['channel'], minlength=len(gains))
+    assert per_channel[dead].sum() == 0 and per_channel[live].min() > 0
+    assert ca['n_photons'] / max(ca['n_groups'], 1) / len(live) > 20, 'the channel lists are not long'
+    sim.close()
+
+
 def test_fused_over_several_batches_lanes_and_transports():
     """Several device batches on several lanes; compact transport (pageable destination) against the plain
     DMA (pinned destination); a record buffer that is too small is grown and the call repeated."""
