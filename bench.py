@@ -406,7 +406,7 @@ def roofline_of(c, ph_alone, ph_lanes, peak, peak_src):
                                                 'achieved_gbs': RECORD_BYTES * c['n_records_total'] / (t_rec / 1e3) / 1e9 if t_rec > 0 else None}},
                 'timing': 'CUDA events on the library stream around the launches of every device batch, summed per step, '
                           'in a pass of the same steps with one lane (kernels alone on the GPU); a launch = the back end of one '
-                          'device batch (4 size classes of k_group_analyse side by side, scan, k_group_records)'}
+                          'device batch (the size classes of k_group_analyse / k_group_analyse_small side by side, scan, k_group_records)'}
     ms = float(ph_alone[3])
     byt = PHOTON_BYTES * c['n_photons'] + 2 * c['n_samples']
     return {'bound': 'hbm', 'kernel': 'k_digitize (multi-pass back end: photons in, dense int16 samples out)',
