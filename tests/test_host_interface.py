@@ -221,3 +221,18 @@ def test_chunk_clock_fed_in_pieces_with_peek_gives_the_reference_bounds():
                     got += clock.peek(t_next)
             got.append(clock.finish())
             assert [list(b) for b in got] == c['bounds'], (name, cuts)
+
+
+def test_committed_ncu_traffic_is_what_bench_reads():
+    """bench.py takes roofline.traffic from the committed ncu summary of the fused back end (profiles/r2_fused_ncu.json,
+    written by profiles/tools/fused_traffic.py): one k_group_records launch and the size-class launches per batch."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(root, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    t = bench.ncu_traffic()
+    assert t and t['dram_bytes_per_batch'] > 1e9 and 'ncu --set full' in t['source']
+    kernels = [l['kernel'] for l in t['launches']]
+    assert kernels.count('k_group_records') == 1 and any(k.startswith('k_group_analyse') for k in kernels)
+    assert abs(sum(l['dram_read'] + l['dram_write'] for l in t['launches']) - t['dram_bytes_per_batch']) < 1.0
