@@ -1,30 +1,35 @@
 // Group-resident back end: ONE CTA owns a digitisation group from its photons to its ZLE intervals and record
 // order; a second kernel writes the records.  Two launches, count then fill, no pass over dense samples:
 //
-// k_group_analyse (one CTA per group; groups are binned by photon count so that small groups run many CTAs per SM)
+// k_group_analyse (one CTA per group; groups are binned by photon count so that small groups run many CTAs per SM;
+// the classes up to 512 threads run a second build of the body with fewer registers, k_group_analyse_small)
 //   photons of the group (generation order, HBM, read once)
 //     -> key (channel | pulse call | sample | ns remainder | index | dpe) in shared memory, bucketed by
-//        channel (counting sort) and ordered inside the channel by (pulse call, time)
-//                                                                   Pulse.__call__   pulse.py:82-144
+//        channel (counting sort) and ranked inside the channel by (pulse call, time): a photon's place is the number
+//        of smaller keys on its channel                             Pulse.__call__   pulse.py:82-144
 //     -> per PHOTON (one thread each): gain into shared memory, the trigger bit of the truth counters
-//        (pulse.py:229-271), equal-ns photons merged (pulse.py:301-318), and the samples the photon OWNS
-//        (from its first sample to the next photon's first sample on the channel) evaluated with every
-//        photon that overlaps them -- fp64, ascending time, mul and add unfused: the summation order of
-//        Pulse.add_current (pulse.py:276-318), one rounding per pulse and sample, -around(current *
-//        current_2_adc) (rawdata.py:236-239), baseline, clamp, threshold (rawdata.py:290-296,441-458).
-//        Only the first and the last owned sample below threshold are kept (5 + 5 bits in the key): a
-//        template is shorter than the ZLE hold-off, so nothing else can change an interval.
+//        (pulse.py:229-271), equal-ns photons merged (pulse.py:301-318), and its class: lone (nothing else reaches
+//        its template), plain (only its own pulse call reaches the samples it owns), mixed (another pulse call of the
+//        channel does) -- listed apart, so that a warp runs one loop
+//     -> the samples the photon OWNS (from its first sample to the next photon's first sample on the channel)
+//        evaluated with every photon that overlaps them -- fp64, ascending time, mul and add unfused: the summation
+//        order of Pulse.add_current (pulse.py:276-318), one rounding per pulse and sample, -around(current *
+//        current_2_adc) (rawdata.py:236-239), baseline, clamp, threshold (rawdata.py:290-296,441-458).  The lists
+//        (and the channels where photons pile up, which a warp takes, lane = sample) are handed out warp by warp
+//        through a counter.  The ADC values go to the photon's 64-byte slot in HBM; only the first and the last
+//        owned sample below threshold are kept (5 + 5 bits in the key): a template is shorter than the ZLE
+//        hold-off, so nothing else can change an interval.
 //     -> per WINDOW (one lane each; a warp for the rare window with several pulse calls): window extents
 //        (pulse.py:118-127, rawdata.py:231-235,258-259), truth counters, the hysteresis interval search
 //        (utils.py:13-58, rawdata.py:296-308) over the photons' flagged runs
-//     -> record order (time, channel) of the group: counting sort over time bins in shared memory
-//        (strax.sort_by_time)
-//     -> to HBM: 12 bytes per photon (time | first-of-pulse bit, merged gain) in channel order, 16 bytes per
+//     -> record order (time, channel) of the group: counting sort over log-spaced time bins in shared memory, rank
+//        inside a bin by counting smaller keys (strax.sort_by_time)
+//     -> to HBM: 4 bytes per photon (sample | ns remainder | samples owned) in channel order, 16 bytes per
 //        record (channel, first sample, pulse length, record_i, the photons that reach it) at the record's rank
 //        in the group, the group's record count
 // exclusive scan of the record counts: groups are disjoint in time, so group order IS record order
-// k_group_records (one warp per record, lane = record word): the samples again (same arithmetic, only the
-//   photons that reach the record), 244-byte records written ONCE, at their final sorted position
+// k_group_records (one warp per tile of 16 records): a gather -- baseline fill, headers, the owned samples of the
+//   photons that reach a record out of their slots; 244-byte records written ONCE, at their final sorted position
 //                                                                   strax_interface.py:425-436
 // No sort keys, no dense ADC buffer, no flags travel through HBM.  Used when every group of a batch fits
 // (<= kFusedMaxPhotons photons, no noise, no high-energy twin rows); anything else takes the multi-pass back
